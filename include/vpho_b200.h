@@ -1,0 +1,150 @@
+/* vpho_b200 -- C ABI of the B200-native VPHO evaluation hot path.
+ *
+ * Every entry point takes raw device pointers, explicit sizes and a CUDA stream handle (passed as void* so the
+ * header needs no CUDA include) and returns an int status: 0 = ok, -1 = invalid argument, -2 = kernel launch
+ * failure, -3 = allocation failure.  No exceptions cross this boundary, nothing is allocated per call, inputs are
+ * never written.  All calls are stream-ordered and issue no host synchronisation unless stated.
+ *
+ * The reference (zhoujun-7/VPHO) has no FFI layer: the seam is the set of Python methods wired in
+ * `vpho_net.__init__` (lib/model/VPHO.py:56-76).  Each function below names the reference interface it replaces;
+ * INTEGRATION.md shows the ctypes binding a maintainer would add on the reference side.
+ */
+#ifndef VPHO_B200_H_
+#define VPHO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vpho_mano_t;      /* packed MANO model on the device          */
+typedef void* vpho_denoiser_t;  /* packed score-network weights on the device */
+typedef void* vpho_assets_t;    /* force-anchor tables + object point tables  */
+
+int vpho_version(void);
+
+/* ------------------------------------------------------------------------------------------------ MANO ---- */
+/* Packs the MANO tensors (HOST pointers, float32, manopth layouts: v_template [778][3], shapedirs [778][3][10],
+ * posedirs [778][3][135], J_regressor [16][778], weights [778][16]) into the device layout.
+ * Replaces the `ManoLayer(...)` construction at lib/model/head_mano.py:48-55. */
+int vpho_mano_create(const float* v_template, const float* shapedirs, const float* posedirs,
+                     const float* J_regressor, const float* weights, vpho_mano_t* out);
+int vpho_mano_destroy(vpho_mano_t h);
+
+/* verts [n][778][3] (may be NULL: joints only), joints [n][21][3]; pose [n][48] axis-angle, shape [n][10];
+ * metres, wrist-centred.  Replaces `HeadMano.get_hand_verts` (lib/model/head_mano.py:78-87). */
+int vpho_mano_forward(vpho_mano_t h, const float* pose, const float* shape, int n, float* verts, float* joints,
+                      void* stream);
+
+/* --------------------------------------------------------------------------------------------- sampler ---- */
+/* Packs a BaseDenoiser state dict (HOST pointers, float32, reference layouts -- lib/model/denoiser.py:33-66,
+ * lib/model/parallel_linear.py:15-16):
+ *   fourier_W [64]; t_w [128][128], t_b [128]; p1_w [256][D], p1_b [256]; p2_w [256][256], p2_b [256];
+ *   ha_w [n][1408][256], ha_b [n][256]; hb_w [n][256][3], hb_b [n][3];  D = 3n (96 hand / 9 object). */
+int vpho_denoiser_create(int n_heads, const float* fourier_W, const float* t_w, const float* t_b, const float* p1_w,
+                         const float* p1_b, const float* p2_w, const float* p2_b, const float* ha_w,
+                         const float* ha_b, const float* hb_w, const float* hb_b, vpho_denoiser_t* out);
+int vpho_denoiser_destroy(vpho_denoiser_t h);
+
+/* One score-network evaluation: out[N][D] = denoiser(x[N][D], t, feat) / (sigma(t)+1e-7), t a single float shared
+ * by all rows (as on the sampling path).  feat is [N/rows_per_feat][1024]; row r uses feat[r / rows_per_feat].
+ * workspace: vpho_sample_workspace_bytes(...) bytes.  Replaces `BaseDenoiser.forward`
+ * (lib/model/denoiser.py:68-82) for the sampling call pattern. */
+int vpho_score_eval(vpho_denoiser_t h, const float* x, float t, const float* feat, int n_rows, int rows_per_feat,
+                    float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+size_t vpho_sample_workspace_bytes(int n_heads, int n_rows, int rows_per_feat, int n_eval);
+
+/* Probability-flow ODE sampler with SciPy's adaptive RK45 controller run entirely on the device.
+ * Replaces `ScoreBasedModelAgent.sample` -> `cond_ode_sampler` (lib/model/score_based_model.py:45-105,130-146).
+ *   init_x   [N][D] f32  prior draw randn*sigma(T0) (lib/model/sde.py:26-28) -- passed in so both sides share noise
+ *   t_eval   [n_eval] f64 HOST pointer, = np.linspace(T0, eps, n_eval)
+ *   xs       [n_eval][N][D] f64 (may be NULL), x [N][D] f64 (after the final predictor step)
+ *   counters [8] int32 device: {status, nfev, accepted, rejected, nan_seen, attempts_launched, -, -}
+ *            status 1 = finished, 0 = needs more attempts (call vpho_sample_continue), -1 = step too small.
+ * `max_attempts` RK step attempts are enqueued; attempts after convergence are skipped on the device. */
+int vpho_sample_begin(vpho_denoiser_t h, const float* feat, int n_rows, int rows_per_feat, const float* init_x,
+                      double T0, double eps, const double* t_eval, int n_eval, double rtol, double atol,
+                      double max_step, int max_attempts, double* xs, double* x, int32_t* counters, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int vpho_sample_continue(vpho_denoiser_t h, int max_attempts, void* workspace, size_t workspace_bytes, void* stream);
+/* Final "denoise" predictor step (score_based_model.py:95-104); call once status == 1. */
+int vpho_sample_finish(vpho_denoiser_t h, int num_steps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* 6D -> axis-angle for the hand finals (+ regressed shape): `vpho_net.postprocess_diffusion_hand`
+ * branch 'mano_pose' (lib/model/VPHO.py:318-326).  x6d [n][16][6] f32 -> pose_aa [n][48] f32. */
+int vpho_rot6d_to_axis_angle(const float* x6d, int n_rot, float* aa, void* stream);
+
+/* ---------------------------------------------------------------------------------- assets / aggregation ---- */
+/* Force-anchor tables (lib/utils/physics_fn.py:121-257, lib/utils/hand_fn.py:427-448) and per-object point tables
+ * (lib/model/head_object.py:9-34).  HOST pointers: face_vertex_idx [32][3] int32, anchor_weight [32][2] f32,
+ * vert2joint [21][778] f32, kpt3d [n_obj][27][3], verts [n_obj][n_pts][3], com [n_obj][3]. */
+int vpho_assets_create(const int32_t* face_vertex_idx, const float* anchor_weight, const float* vert2joint,
+                       int n_obj, int n_pts, const float* kpt3d, const float* verts, const float* com,
+                       vpho_assets_t* out);
+int vpho_assets_destroy(vpho_assets_t h);
+
+/* `HeadObject.forward` + `flip_pt3d` (lib/model/head_object.py:36-67): out[b][c][v][3] = R(pose6d[b][c]) p_v + t,
+ * x negated where !is_right.  which: 0 keypoints(27) 1 sampled verts 2 CoM.  pose6d f32 [bs][C][9]. */
+int vpho_object_points(vpho_assets_t h, const float* pose6d, const int32_t* obj_id, const uint8_t* is_right, int bs,
+                       int C, int which, int flip, float* out, void* stream);
+
+/* `from_local_to_global` (lib/model/physics.py:362-371) over `VERT2ANCHOR` : verts [n][778][3] (camera frame),
+ * force_local [n/group][32][3] -> force_point [n][32][3], force_global [n][32][3]. */
+int vpho_force_anchors(vpho_assets_t h, const float* verts, const float* force_local, int n, int group,
+                       float* force_point, float* force_global, void* stream);
+
+typedef struct {
+  int bs;          /* images in this batch                         */
+  int S;           /* sample_num: diffusion candidates per image   */
+  int topk_hand;   /* <= 64                                        */
+  int topk_obj;    /* <= 16                                        */
+  int phy_topk;    /* hard-coded 5 in the reference (aggregation.py:1246) */
+  /* inputs (device) */
+  const float* cam_intrinsic;    /* [bs][3][3]   cam_intr_crop_flip */
+  const float* root_joint_flip;  /* [bs][3] */
+  const float* root_joint;       /* [bs][3] */
+  const uint8_t* is_right;       /* [bs] */
+  const uint8_t* is_grasped;     /* [bs] */
+  const float* force_local;      /* [bs][32][3] */
+  const float* hand_pose_diff;   /* [bs*S][48] */
+  const float* hand_pose_reg;    /* [bs][48] */
+  const float* hand_shape;       /* [bs*S][10] */
+  const float* hand_heatmap;     /* [bs][21][64][64] */
+  const float* hand_bbox;        /* [bs][4] */
+  const double* obj_pose6d;      /* [bs][S][9] float64 */
+  const float* obj_heatmap;      /* [bs][27][64][64] */
+  const float* obj_bbox;         /* [bs][4] */
+  const int32_t* obj_id;         /* [bs] index into the object tables */
+  /* outputs (device) -- keys of the dict returned by HOI_Aggregator.__call__ (aggregation.py:1339-1348) */
+  double* obj_agg_6d;            /* [bs][9] f64 */
+  double* pose6d_candidate;      /* [bs][topk_obj^2][9] f64 */
+  float* agg_obj_vert;           /* [bs][n_pts][3] */
+  float* hand_agg_mano;          /* [bs][58] */
+  float* hand_agg_vert;          /* [bs][778][3] */
+  float* hand_agg_joint;         /* [bs][21][3] */
+  /* optional diagnostics (may be NULL): scores / indices of every selection, for stage-wise parity tests */
+  float* dbg_hand_score;         /* [4][bs][2S][5]  (level 0 uses [..][0]) */
+  int32_t* dbg_hand_topk;        /* [4][bs][5][topk_hand] */
+  float* dbg_cascade_pose;       /* [bs][48] fused pose after the cascade */
+  float* dbg_obj_score;          /* [4][bs][max(S,topk_obj^2)]: transl heat, rot heat, physics3, final heat */
+  int32_t* dbg_obj_topk;         /* [4][bs][topk_obj] */
+  float* dbg_finger_score;       /* [bs][5][topk_hand+1] */
+  int32_t* dbg_finger_topk;      /* [bs][5][phy_topk] */
+  float* dbg_force_point;        /* [bs][32][3] */
+  float* dbg_force_global;       /* [bs][32][3] */
+} vpho_hoi_args;
+
+size_t vpho_hoi_workspace_bytes(int bs, int S, int topk_hand, int topk_obj, int n_pts);
+
+/* Whole `HOI_Aggregator.__call__` (lib/model/aggregation.py:1167-1353): hand heat-map cascade, object
+ * heat-map / physics selection, hand physics refinement. */
+int vpho_hoi_aggregate(vpho_mano_t mano, vpho_assets_t assets, const vpho_hoi_args* args, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPHO_B200_H_ */

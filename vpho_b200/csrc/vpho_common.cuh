@@ -1,0 +1,41 @@
+// Common definitions for the vpho_b200 sm_100a kernels.
+// The same sources compile under -DVPHO_EMU against tests/emu/cuda_emu.h (test-only SIMT emulator).
+#pragma once
+
+#ifndef VPHO_EMU
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#define VPHO_DYN_SMEM(type, name)                                 \
+  extern __shared__ __align__(16) unsigned char name##_raw_[];    \
+  type* name = reinterpret_cast<type*>(name##_raw_)
+#define VPHO_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#define VPHO_OK 0
+#define VPHO_ERR_INVALID (-1)
+#define VPHO_ERR_LAUNCH (-2)
+#define VPHO_ERR_ALLOC (-3)
+
+#define VPHO_CHECK_LAUNCH()                                 \
+  do {                                                      \
+    cudaError_t e__ = cudaGetLastError();                   \
+    if (e__ != cudaSuccess) return VPHO_ERR_LAUNCH;         \
+  } while (0)
+
+namespace vpho {
+
+// ---- MANO geometry constants (manopth ManoLayer, right hand) ----
+constexpr int kVerts = 778;
+constexpr int kJoints16 = 16;
+constexpr int kJoints21 = 21;
+constexpr int kBlendK = 145;       // 10 shape + 135 pose-corrective coefficients
+constexpr int kVChunk = 195;       // vertices handled by one CTA of the skinning kernel
+constexpr int kVChunkPad = 224;    // packed stride of a chunk (7 warps, 128 B aligned rows)
+constexpr int kNumVChunks = 4;
+constexpr int kVPad = kVChunkPad * kNumVChunks;  // 896 packed vertex slots
+
+__device__ __forceinline__ int packed_vertex(int v) { return (v / kVChunk) * kVChunkPad + (v % kVChunk); }
+
+}  // namespace vpho

@@ -60,18 +60,24 @@ size_t vpho_sample_workspace_bytes(int n_heads, int n_rows, int rows_per_feat, i
 /* Probability-flow ODE sampler with SciPy's adaptive RK45 controller run entirely on the device.
  * Replaces `ScoreBasedModelAgent.sample` -> `cond_ode_sampler` (lib/model/score_based_model.py:45-105,130-146).
  *   init_x   [N][D] f32  prior draw randn*sigma(T0) (lib/model/sde.py:26-28) -- passed in so both sides share noise
- *   t_eval   [n_eval] f64 HOST pointer, = np.linspace(T0, eps, n_eval)
- *   xs       [n_eval][N][D] f64 (may be NULL), x [N][D] f64 (after the final predictor step)
- *   counters [8] int32 device: {status, nfev, accepted, rejected, nan_seen, attempts_launched, -, -}
- *            status 1 = finished, 0 = needs more attempts (call vpho_sample_continue), -1 = step too small.
- * `max_attempts` RK step attempts are enqueued; attempts after convergence are skipped on the device. */
+ *   t_eval   [n_eval] f64 DEVICE pointer, or NULL for numpy.linspace(T0, eps, n_eval) computed on the device
+ *   num_steps            the reference's `num_steps` (scale of the final predictor step; = n_eval on the eval path)
+ *   xs       [n_eval][N][D] f64 (may be NULL), x [N][D] f64 (written by vpho_sample_finish)
+ *   counters [8] int32 device (may be NULL): {status, nfev, accepted, rejected, nan_seen, attempts, -, -}
+ *            status 1 = finished, 0 = needs more attempts (vpho_sample_continue), -1 = step size too small.
+ * `max_attempts` RK step attempts (6 network calls each) are enqueued; attempts after the integration has
+ * finished are skipped on the device.  No host synchronisation. */
 int vpho_sample_begin(vpho_denoiser_t h, const float* feat, int n_rows, int rows_per_feat, const float* init_x,
                       double T0, double eps, const double* t_eval, int n_eval, double rtol, double atol,
-                      double max_step, int max_attempts, double* xs, double* x, int32_t* counters, void* workspace,
-                      size_t workspace_bytes, void* stream);
-int vpho_sample_continue(vpho_denoiser_t h, int max_attempts, void* workspace, size_t workspace_bytes, void* stream);
-/* Final "denoise" predictor step (score_based_model.py:95-104); call once status == 1. */
-int vpho_sample_finish(vpho_denoiser_t h, int num_steps, void* workspace, size_t workspace_bytes, void* stream);
+                      double max_step, int num_steps, int max_attempts, double* xs, double* x, int32_t* counters,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* Enqueues `max_attempts` more attempts on the same workspace (same n_rows / rows_per_feat / n_eval as begin). */
+int vpho_sample_continue(vpho_denoiser_t h, int n_rows, int rows_per_feat, int n_eval, int max_attempts,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* Final "denoise" predictor step (score_based_model.py:95-104) -> x.  A no-op on the device while status != 1,
+ * so it can be enqueued right behind begin/continue and repeated after a continue. */
+int vpho_sample_finish(vpho_denoiser_t h, int n_rows, int rows_per_feat, int n_eval, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* 6D -> axis-angle for the hand finals (+ regressed shape): `vpho_net.postprocess_diffusion_hand`
  * branch 'mano_pose' (lib/model/VPHO.py:318-326).  x6d [n][16][6] f32 -> pose_aa [n][48] f32. */

@@ -1,0 +1,58 @@
+"""MANO layer parity: CUDA kernel (C ABI `vpho_mano_forward`) vs the oracle restatement of manopth
+(`HeadMano.get_hand_verts`, lib/model/head_mano.py:78-87).  Tolerance: 1e-5 relative, FP32 (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vpho_oracle as O
+from vpho_b200.head_mano import HeadMano
+
+REL_TOL = 1e-5
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def _check(hm, om, n, dev, seed, scale=0.5):
+    g = torch.Generator().manual_seed(seed)
+    p = torch.randn(n, 48, generator=g) * scale
+    s = torch.randn(n, 10, generator=g)
+    v, j = hm.get_hand_verts(pose=p.to(dev), shape=s.to(dev))
+    v2, j2 = om(p, s)
+    assert v.shape == (n, 778, 3) and j.shape == (n, 21, 3)
+    assert _rel(v.cpu(), v2) < REL_TOL and _rel(j.cpu(), j2) < REL_TOL
+    # per-element: relative to the hand's size (~0.1 m) so wrist-centred zeros do not blow up the ratio
+    assert (v.cpu() - v2).abs().max().item() < 1e-5 * 0.2
+    _, j3 = hm.get_hand_verts(pose=p.to(dev), shape=s.to(dev), need_verts=False)
+    assert torch.equal(j3, j)
+
+
+def test_mano_emulated_kernel(assets, emu_lib):
+    hm, om = HeadMano(assets["mano"], lib=emu_lib), O.OracleMano(assets["mano"])
+    for n in (1, 5, 19):
+        _check(hm, om, n, "cpu", seed=n)
+
+
+def test_mano_zero_pose_is_template(assets, emu_lib):
+    hm = HeadMano(assets["mano"], lib=emu_lib)
+    v, j = hm.get_hand_verts(pose=torch.zeros(1, 48), shape=torch.zeros(1, 10))
+    m = assets["mano"]
+    wrist = (m["J_regressor"].astype(np.float64) @ m["v_template"].astype(np.float64))[0]
+    ref = torch.from_numpy((m["v_template"] - wrist).astype(np.float32))
+    assert (v[0] - ref).abs().max().item() < 2e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 3, 64, 1984, 6400, 12800])
+def test_mano_cuda(assets, cuda_lib, n):
+    hm, om = HeadMano(assets["mano"]), O.OracleMano(assets["mano"])
+    _check(hm, om, n, "cuda", seed=n)
+
+
+@pytest.mark.gpu
+def test_mano_cuda_large_angles_and_empty(assets, cuda_lib):
+    hm, om = HeadMano(assets["mano"]), O.OracleMano(assets["mano"])
+    _check(hm, om, 257, "cuda", seed=7, scale=2.5)
+    v, j = hm.get_hand_verts(pose=torch.zeros(0, 48, device="cuda"), shape=torch.zeros(0, 10, device="cuda"))
+    assert v.shape == (0, 778, 3) and j.shape == (0, 21, 3)

@@ -1,0 +1,112 @@
+"""Sampler parity: the device-resident RK45 probability-flow sampler + score network (csrc/sampler.cu, C ABI
+`vpho_score_eval` / `vpho_sample_*`) against the oracle restatement of `cond_ode_sampler`
+(lib/model/score_based_model.py:45-105) which calls scipy's RK45 exactly as the reference does.
+
+Tolerances (written here, float32 network / float64 state):
+  * one network call: 5e-6 relative L2 (different FP32 summation order than MKL's sgemm);
+  * sampler output: identical controller trajectory (nfev, accepted, rejected bit-equal) and
+    |x - x_oracle| <= 2e-5 * max(1, |x|) element-wise (2e-4 for the deliberately stiff last_std >= 0.5 cases, whose
+    100x larger scores amplify the float32 rounding of the network through the ODE).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vpho_oracle as O
+from vpho_b200 import synthetic as syn
+from vpho_b200.score_based_model import Denoiser, ScoreBasedModelAgent, ve_prior_std
+
+
+def _setup(head, lib, bs, S, last_std, seed=0, dev="cpu"):
+    st = syn.make_denoiser_state(head, seed, last_std=last_std)
+    den, od = Denoiser(st, lib=lib), O.OracleDenoiser(st)
+    g = torch.Generator().manual_seed(100 + seed)
+    enc = torch.relu(torch.randn(bs, 1024, generator=g))
+    feat = enc[:, None].repeat(1, S, 1).reshape(-1, 1024)
+    return den, od, enc, feat, g
+
+
+def _check_eval(den, od, feat, g, S, dev):
+    D = den.out_dim
+    x = torch.randn(feat.shape[0], D, generator=g) * 2.5
+    for t in (0.65, 0.31, 1e-5):
+        tt = torch.ones(feat.shape[0], 1) * t
+        o1 = den({"feat": feat.to(dev), "sampled_pose": x.to(dev), "t": tt.to(dev), "sample_num": S}).cpu()
+        o2 = od({"feat": feat, "sampled_pose": x, "t": tt})
+        assert ((o1 - o2).norm() / o2.norm()).item() < 5e-6
+
+
+def _check_sample(den, od, feat, S, dev, seed, steps=50, T0=0.65, expect_reject=None, tol=2e-5):
+    agent = ScoreBasedModelAgent(sampling_steps=steps, sample_num=S)
+    torch.manual_seed(seed)
+    xs, x = agent.sample({"feat": feat.to(dev)}, den, T0)
+    torch.manual_seed(seed)
+    init = torch.randn(feat.shape[0], den.out_dim) * ve_prior_std(T0)     # the same global-RNG draw (sde.py:26-28)
+    xs2, x2, info = O.oracle_sample(od, feat, T0, init, steps)
+    li = agent.last_info
+    assert li["status"] == 1 and info["status"] == 0
+    assert li["nfev"] == info["nfev"] and li["net_calls"] == info["net_calls"]
+    assert xs.dtype == torch.float64 and x.dtype == torch.float64
+    assert tuple(xs.shape) == tuple(xs2.shape) and tuple(x.shape) == tuple(x2.shape)
+    assert ((x.cpu() - x2).abs() <= tol * x2.abs().clamp(min=1)).all()
+    assert ((xs.cpu() - xs2).abs() <= tol * xs2.abs().clamp(min=1)).all()
+    assert torch.equal(xs[:, 0].cpu().float(), init)                      # first t_eval point is the prior draw
+    if expect_reject is not None:
+        assert (li["rejected"] > 0) == expect_reject
+    return li
+
+
+def test_sampler_emulated_object_head(emu_lib):
+    den, od, enc, feat, g = _setup("obj", emu_lib, bs=2, S=12, last_std=0.05)
+    _check_eval(den, od, feat, g, 12, "cpu")
+    _check_sample(den, od, feat, 12, "cpu", seed=3)
+
+
+def test_sampler_emulated_stiff_scores_need_more_attempts(emu_lib):
+    # a much larger last layer makes the ODE move: more accepted steps than the first enqueue (continue path)
+    den, od, enc, feat, g = _setup("obj", emu_lib, bs=2, S=6, last_std=3.0)
+    li = _check_sample(den, od, feat, 6, "cpu", seed=4, steps=11, tol=2e-4)
+    assert li["attempts"] >= 6
+
+
+def test_sampler_emulated_ragged_rows(emu_lib):
+    # N = 7 rows is not a multiple of any tile; rows_per_feat = 1 (no repeat structure)
+    st = syn.make_denoiser_state("obj", 1, last_std=0.05)
+    den, od = Denoiser(st, lib=emu_lib), O.OracleDenoiser(st)
+    g = torch.Generator().manual_seed(9)
+    feat = torch.relu(torch.randn(7, 1024, generator=g))
+    _check_eval(den, od, feat, g, 0, "cpu")
+    _check_sample(den, od, feat, 0, "cpu", seed=5, steps=5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("head,bs,S,last_std", [("obj", 4, 100, 0.05), ("mano_pose", 4, 100, 0.05),
+                                                ("mano_pose", 3, 37, 0.5), ("obj", 5, 100, 3.0)])
+def test_sampler_cuda(cuda_lib, head, bs, S, last_std):
+    den, od, enc, feat, g = _setup(head, None, bs, S, last_std)
+    _check_eval(den, od, feat, g, S, "cuda")
+    _check_sample(den, od, feat, S, "cuda", seed=bs, tol=2e-4 if last_std >= 0.5 else 2e-5)
+
+
+@pytest.mark.gpu
+def test_sampler_cuda_feat_unique_equals_repeated(cuda_lib):
+    den, od, enc, feat, g = _setup("mano_pose", None, 3, 100, 0.05)
+    agent = ScoreBasedModelAgent(50, 100)
+    torch.manual_seed(1)
+    xs1, x1 = agent.sample({"feat": feat.cuda()}, den, 0.65)
+    torch.manual_seed(1)
+    xs2, x2 = agent.sample({"feat_unique": enc.cuda(), "n_rows": 300}, den, 0.65)
+    assert torch.equal(x1, x2) and torch.equal(xs1, xs2)
+
+
+@pytest.mark.gpu
+def test_sampler_cuda_readme_batch_runs(cuda_lib):
+    # README shape (bs 64 x 100): finishes, finite, deterministic across two runs
+    den, od, enc, feat, g = _setup("mano_pose", None, 64, 100, 0.05)
+    agent = ScoreBasedModelAgent(50, 100)
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(2)
+        _, x = agent.sample({"feat_unique": enc.cuda(), "n_rows": 6400}, den, 0.65, return_inprocess=False)
+        outs.append(x)
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])

@@ -1,0 +1,866 @@
+// Score-based sampler for sm_100a: VE-SDE probability-flow ODE integrated by an adaptive Dormand-Prince RK45
+// controller that lives entirely on the device (no host round trip per stage), around a factored score network.
+//
+// Replaces ScoreBasedModelAgent.sample -> cond_ode_sampler (lib/model/score_based_model.py:45-105,130-146),
+// BaseDenoiser.forward (lib/model/denoiser.py:68-82), ParallelLinear (lib/model/parallel_linear.py:27-35) and
+// the VE-SDE coefficients (lib/model/sde.py:15-24).  scipy.integrate.solve_ivp(RK45) is an un-vendored third
+// party (reference pins scipy==1.12.0): its step controller (rk.py RungeKutta._step_impl, rk_step), initial step
+// heuristic (common.py select_initial_step), RMS norm (common.py norm), t_eval handling (ivp.py) and quartic
+// dense output (rk.py RkDenseOutput, RK45.P) are restated here operation by operation.
+//
+// Factoring of the first ParallelLinear (K = 1408 = 128 time + 256 pose + 1024 conditioning features):
+//   feat-term  F[img][hid]   once per sample()        (k_feat_term)
+//   time-term  Tt[hid]       once per network call    (k_time_term; all rows share t on the sampling path)
+//   pose-term  P2 . Wa_p     per candidate per call   (k_head_simt: FP32 register-tiled GEMM, K = 256,
+//                                                      fused bias/ReLU/second ParallelLinear/sigma division)
+// State, stage combinations, error norm and dense output are float64 as in scipy; the network is float32.
+#include "sampler.cuh"
+#include "vpho_b200.h"
+
+#include <vector>
+
+namespace vpho {
+
+// ------------------------------------------------------------------------------------------------------------
+// Dormand-Prince coefficients exactly as scipy/integrate/_ivp/rk.py (class RK45) writes them
+// ------------------------------------------------------------------------------------------------------------
+VPHO_CONSTANT double kC[7] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
+VPHO_CONSTANT double kA[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};   // row 6 = B (y_new)
+VPHO_CONSTANT double kE[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
+VPHO_CONSTANT double kP[7][4] = {
+    {1, -8048581381.0 / 2820520608, 8663915743.0 / 2820520608, -12715105075.0 / 11282082432},
+    {0, 0, 0, 0},
+    {0, 131558114200.0 / 32700410799, -68118460800.0 / 10900136933, 87487479700.0 / 32700410799},
+    {0, -1754552775.0 / 470086768, 14199869525.0 / 1410260304, -10690763975.0 / 1880347072},
+    {0, 127303824393.0 / 49829197408, -318862633887.0 / 49829197408, 701980252875.0 / 199316789632},
+    {0, -282668133.0 / 205662961, 2019193451.0 / 616988883, -1453857185.0 / 822651844},
+    {0, 40617522.0 / 29380423, -110615467.0 / 29380423, 69997945.0 / 29380423}};
+
+constexpr double kSafety = 0.9, kMinFactor = 0.2, kMaxFactor = 10.0, kErrExponent = -0.2;
+constexpr double kSigmaMin = 0.01, kSigmaRatio = 5000.0;   // sigma_max / sigma_min = 50 / 0.01 (sde.py:92-93)
+// sqrt(2 * (log(50) - log(0.01))) evaluated in float64 (torch.tensor(np.float64), sde.py:23)
+constexpr double kSqrt2LogRatio = 4.1272734804992597;
+
+struct DenoiserHost {
+  DenoiserDev dev;
+  float* blob = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// time of an evaluation and the SDE scalars that go with it
+// ------------------------------------------------------------------------------------------------------------
+struct EvalTime {
+  float t32;      // time fed to the network: torch.ones(N,1) * t  -> float32
+  float std32;    // sigma(t32) + 1e-7 in float32 (denoiser.py:78-81)
+  double coef;    // 0.5 * g(t)^2 in float64 (score_based_model.py:84, numpy >= 2 promotion)
+  float g32;      // float32 diffusion for the predictor step (sde_coeff(vec_eps))
+};
+
+__device__ __forceinline__ float sigma_f32(float t32) {
+  // torch: 0.01 * (5000.0 ** t) on a float32 tensor; pow evaluated in double and rounded once
+  float p = (float)pow(5000.0, (double)t32);
+  return __fmul_rn(0.01f, p);
+}
+
+__device__ __forceinline__ EvalTime eval_time(const RkCtrl& c, int mode, int s) {
+  EvalTime e;
+  double t64;
+  if (mode == kModeInit0) t64 = c.T0;
+  else if (mode == kModeInit1) t64 = c.T0 + c.h0 * c.direction;
+  else if (mode == kModeStage) t64 = (s == 6) ? (c.t + c.h) : (c.t + kC[s] * c.h);
+  else if (mode == kModeFinal) t64 = c.eps;
+  else t64 = (double)c.eval_t32;
+  e.t32 = (float)t64;
+  e.std32 = __fadd_rn(sigma_f32(e.t32), 1e-7f);
+  double sigma;
+  if (mode == kModeInit0) sigma = (double)sigma_f32((float)c.T0);          // torch.tensor(python float) is float32
+  else sigma = kSigmaMin * pow(kSigmaRatio, t64);
+  double g = sigma * kSqrt2LogRatio;
+  e.coef = 0.5 * (g * g);
+  e.g32 = __fmul_rn(sigma_f32(e.t32), (float)kSqrt2LogRatio);
+  return e;
+}
+
+// K slot value with the reference's `nan_to_num(score, 0, 0, 0)` applied when that evaluation produced a NaN
+__device__ __forceinline__ double kval(const double* K, const RkCtrl& c, int slot, int n, int i) {
+  double v = K[(size_t)slot * n + i];
+  if (c.nan_stage[slot] && !isfinite(v)) v = 0.0;
+  return v;
+}
+
+__device__ __forceinline__ bool eval_active(const RkCtrl& c, int mode) {
+  if (mode == kModeEval) return true;
+  if (mode == kModeFinal) return c.status == 1;
+  return c.status == 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// controller set-up
+// ------------------------------------------------------------------------------------------------------------
+struct SampleCfg {
+  double T0, eps, rtol, atol, max_step;
+  int n_rows, D, n_eval, num_steps, rows_per_feat;
+  const double* t_eval_in;   // device pointer or nullptr (= numpy.linspace(T0, eps, n_eval))
+  double* xs;
+  double* x_out;
+  int32_t* counters;
+};
+
+__global__ void k_init_ctrl(SampleCfg cfg, SamplerWs ws) {
+  RkCtrl& c = *ws.ctrl;
+  const int tid = threadIdx.x;
+  // numpy.linspace: step = (stop-start)/div ; y = arange(num)*step + start ; y[-1] = stop
+  const int div = cfg.n_eval - 1;
+  for (int i = tid; i < cfg.n_eval; i += blockDim.x) {
+    double v;
+    if (cfg.t_eval_in) v = cfg.t_eval_in[i];
+    else if (div > 0) {
+      double step = (cfg.eps - cfg.T0) / (double)div;
+      v = __dadd_rn(__dmul_rn((double)i, step), cfg.T0);
+      if (i == cfg.n_eval - 1) v = cfg.eps;
+    } else v = cfg.T0;
+    ws.t_eval[i] = v;
+  }
+  if (tid == 0) {
+    c.T0 = cfg.T0; c.eps = cfg.eps; c.rtol = cfg.rtol; c.atol = cfg.atol; c.max_step = cfg.max_step;
+    c.n = cfg.n_rows * cfg.D; c.n_rows = cfg.n_rows; c.D = cfg.D; c.n_eval = cfg.n_eval; c.num_steps = cfg.num_steps;
+    c.rows_per_feat = cfg.rows_per_feat;
+    c.direction = cfg.eps >= cfg.T0 ? 1.0 : -1.0;
+    c.t = cfg.T0; c.h_abs = 0; c.h = 0; c.t_new = cfg.T0; c.h0 = 0; c.d0 = 0; c.d1 = 0;
+    c.status = (c.n == 0 || cfg.T0 == cfg.eps) ? 1 : 0;
+    c.step_rejected = 0; c.accepted_now = 0; c.t_old = cfg.T0; c.h_done = 0;
+    c.te_next = 0; c.te_lo = 0; c.te_hi = 0;
+    c.nfev = 0; c.n_acc = 0; c.n_rej = 0; c.attempts = 0; c.finished_final = 0; c.nan_seen = 0;
+    for (int k = 0; k < 8; ++k) c.nan_stage[k] = 0;
+    c.block_counter = 0u;
+    c.eval_t32 = 0.f;
+    c.xs = cfg.xs; c.x_out = cfg.x_out; c.counters = cfg.counters;
+    if (c.counters) for (int k = 0; k < 8; ++k) c.counters[k] = 0;
+  }
+}
+
+__global__ void k_init_state(SamplerWs ws, const float* __restrict__ init_x, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) ws.y[i] = (double)init_x[i];
+}
+
+__global__ void k_set_eval_time(SamplerWs ws, float t32) {
+  RkCtrl& c = *ws.ctrl;
+  c.eval_t32 = t32;
+  c.status = 0;
+  c.nan_seen = 0;
+  for (int k = 0; k < 8; ++k) c.nan_stage[k] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// feat-term: F[r][col] = sum_k feat[r][k] Wa_f[k][col] + ba[col]       (once per sample(); R = images)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kFtRows = 32, kFtCols = 128, kFtK = 32;
+
+__global__ void __launch_bounds__(256) k_feat_term(DenoiserDev dn, const float* __restrict__ feat, int R, float* __restrict__ F) {
+  __shared__ __align__(16) float fs[kFtK][kFtRows];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int c0 = blockIdx.x * kFtCols, r0 = blockIdx.y * kFtRows;
+  const int hid = dn.hid;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < kFDim; k0 += kFtK) {
+    __syncthreads();
+    for (int it = tid; it < kFtK * kFtRows; it += 256) {
+      const int r = it / kFtK, k = it % kFtK;
+      fs[k][r] = (r0 + r < R) ? feat[(size_t)(r0 + r) * kFDim + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < kFtK; ++k) {
+      const float4 f = *reinterpret_cast<const float4*>(&fs[k][4 * ty]);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(dn.Wa_f + (size_t)(k0 + k) * hid + c0 + 4 * tx));
+      const float fr[4] = {f.x, f.y, f.z, f.w}, wc[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(fr[i], wc[j], acc[i][j]);
+    }
+  }
+  const float4 b = __ldg(reinterpret_cast<const float4*>(dn.ba + c0 + 4 * tx));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + 4 * ty + i;
+    if (r >= R) continue;
+    float4 o = make_float4(acc[i][0] + b.x, acc[i][1] + b.y, acc[i][2] + b.z, acc[i][3] + b.w);
+    *reinterpret_cast<float4*>(F + (size_t)r * hid + c0 + 4 * tx) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// time-term: Fourier embedding -> t_encoder -> Tt[col] = sum_k t_feat[k] Wa_t[k][col]   (one per network call)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_time_term(DenoiserDev dn, SamplerWs ws, int mode, int s) {
+  const RkCtrl& c = *ws.ctrl;
+  if (!eval_active(c, mode)) return;
+  __shared__ float four[kTDim];
+  __shared__ float tfeat[kTDim];
+  const int tid = threadIdx.x;
+  const EvalTime et = eval_time(c, mode, s);
+  if (tid < 64) {
+    // x_proj = t * W * 2 * np.pi in float32, left to right (denoiser.py:29-31)
+    float xp = __fmul_rn(__fmul_rn(__fmul_rn(et.t32, dn.fourier_W[tid]), 2.0f), 3.14159265358979323846f);
+    four[tid] = (float)sin((double)xp);
+    four[64 + tid] = (float)cos((double)xp);
+  }
+  __syncthreads();
+  if (tid < kTDim) {
+    float a = 0.f;
+    for (int k = 0; k < kTDim; ++k) a = fmaf(four[k], dn.Wt[k * kTDim + tid], a);
+    a += dn.bt[tid];
+    tfeat[tid] = a > 0.f ? a : 0.f;
+  }
+  __syncthreads();
+  const int col = blockIdx.x * 256 + tid;
+  if (col < dn.hid) {
+    float a = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < kTDim; ++k) a = fmaf(tfeat[k], __ldg(dn.Wa_t + (size_t)k * dn.hid + col), a);
+    ws.Tt[col] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// stage input (float64 RK combination -> float32) + pose encoder (D -> 256 -> 256, ReLU) -> P2T (k-major)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kPeRows = 32;
+constexpr int kMaxD = 96;
+
+__global__ void __launch_bounds__(256) k_pose_encoder(DenoiserDev dn, SamplerWs ws, int mode, int s) {
+  const RkCtrl& c = *ws.ctrl;
+  if (!eval_active(c, mode)) return;
+  __shared__ __align__(16) float xs[kMaxD][kPeRows];
+  __shared__ __align__(16) float h1s[kPDim][kPeRows];
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  const int D = dn.D, n = c.n, n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
+  const int r0 = blockIdx.x * kPeRows;
+  const double h = c.h;
+  for (int it = tid; it < kPeRows * D; it += 256) {
+    const int r = it / D, d = it - r * D;
+    const int row = r0 + r;
+    double v = 0.0;
+    if (row < n_rows) {
+      const int i = row * D + d;
+      if (mode == kModeEval) v = (double)ws.eval_x[i];
+      else {
+        const double y = ws.y[i];
+        if (mode == kModeInit0 || mode == kModeFinal) v = y;
+        else if (mode == kModeInit1) v = __dadd_rn(y, __dmul_rn(c.h0 * c.direction, kval(ws.K, c, 0, n, i)));
+        else {
+          // dy = np.dot(K[:s].T, a[:s]) * h ; y + dy          (rk.py rk_step)
+          double acc = 0.0;
+          const int ns = (s == 6) ? 6 : s;
+          for (int j = 0; j < ns; ++j) acc += kval(ws.K, c, j, n, i) * kA[s][j];
+          v = __dadd_rn(y, __dmul_rn(acc, h));
+          if (s == 6) ws.ynew[i] = v;
+        }
+      }
+    }
+    xs[d][r] = (float)v;
+  }
+  __syncthreads();
+  float acc[4][8];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(dn.b1 + 8 * ty));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(dn.b1 + 8 * ty + 4));
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = bb[j];
+  }
+  for (int k = 0; k < D; ++k) {
+    const float4 x4 = *reinterpret_cast<const float4*>(&xs[k][4 * tx]);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(dn.W1 + (size_t)k * kPDim + 8 * ty));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(dn.W1 + (size_t)k * kPDim + 8 * ty + 4));
+    const float xr[4] = {x4.x, x4.y, x4.z, x4.w};
+    const float wc[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xr[i], wc[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 o = make_float4(fmaxf(acc[0][j], 0.f), fmaxf(acc[1][j], 0.f), fmaxf(acc[2][j], 0.f), fmaxf(acc[3][j], 0.f));
+    *reinterpret_cast<float4*>(&h1s[8 * ty + j][4 * tx]) = o;
+  }
+  __syncthreads();
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(dn.b2 + 8 * ty));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(dn.b2 + 8 * ty + 4));
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = bb[j];
+  }
+#pragma unroll 4
+  for (int k = 0; k < kPDim; ++k) {
+    const float4 x4 = *reinterpret_cast<const float4*>(&h1s[k][4 * tx]);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(dn.W2 + (size_t)k * kPDim + 8 * ty));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(dn.W2 + (size_t)k * kPDim + 8 * ty + 4));
+    const float xr[4] = {x4.x, x4.y, x4.z, x4.w};
+    const float wc[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xr[i], wc[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 o = make_float4(fmaxf(acc[0][j], 0.f), fmaxf(acc[1][j], 0.f), fmaxf(acc[2][j], 0.f), fmaxf(acc[3][j], 0.f));
+    *reinterpret_cast<float4*>(ws.P2T + (size_t)(8 * ty + j) * ws.Npad + r0 + 4 * tx) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// what happens to one network output element, per evaluation mode
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_score(const SamplerWs& ws, RkCtrl& c, const EvalTime& et, int mode, int s, int i,
+                                           float score) {
+  if (mode == kModeEval) { ws.eval_out[i] = score; return; }
+  if (mode == kModeFinal) {
+    // drift = 0 - diffusion**2 * grad (float32); x = x + drift * ((1-eps)/num_steps)   (score_based_model.py:95-104)
+    const float g2 = __fmul_rn(et.g32, et.g32);
+    const float drift = __fsub_rn(0.f, __fmul_rn(g2, score));
+    const float scale = (float)((1.0 - c.eps) / (double)c.num_steps);
+    c.x_out[i] = __dadd_rn(ws.y[i], (double)__fmul_rn(drift, scale));
+    return;
+  }
+  const int slot = (mode == kModeInit0) ? 0 : (mode == kModeInit1 ? 1 : s);
+  if (isnan(score)) { c.nan_stage[slot] = 1; c.nan_seen = 1; }
+  // drift - 0.5 * diffusion**2 * score, float64 (numpy >= 2 promotion)
+  ws.K[(size_t)slot * c.n + i] = -(et.coef * (double)score);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// head GEMM, FP32 SIMT: one CTA = 128 candidate rows x one ParallelLinear head (256 hidden units, two 128-wide
+// passes), K = 256 pose features streamed with cp.async double buffering; epilogue fuses + F[img] + Tt, ReLU,
+// the 256 -> 3 second ParallelLinear, its bias and the division by sigma(t).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kHgBK = 16;
+
+__global__ void __launch_bounds__(256) k_head_simt(DenoiserDev dn, SamplerWs ws, int mode, int s) {
+  RkCtrl& c = *ws.ctrl;
+  if (!eval_active(c, mode)) return;
+  __shared__ __align__(16) float As[2][kHgBK][128];
+  __shared__ __align__(16) float Bs[2][kHgBK][128];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int head = blockIdx.y, r0 = blockIdx.x * kRowTile;
+  const int hid = dn.hid, Npad = ws.Npad;
+  const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
+  const int rpf = (mode == kModeEval) ? ws.eval_rpf : c.rows_per_feat;
+  const EvalTime et = eval_time(c, mode, s);
+
+  int rows[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rows[i] = r0 + (i < 4 ? 4 * ty + i : 64 + 4 * ty + (i - 4));
+  float o[8][3];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = 0.f;
+
+  for (int pass = 0; pass < 2; ++pass) {
+    const int c0 = head * kHeadHid + pass * 128;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    auto load_tiles = [&](int buf, int k0) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int it = tid + q * 256;          // 512 float4 per operand tile
+        const int k = it >> 5, x4 = (it & 31) * 4;
+        cp_async16(&As[buf][k][x4], ws.P2T + (size_t)(k0 + k) * Npad + r0 + x4);
+        cp_async16(&Bs[buf][k][x4], dn.Wa_p + (size_t)(k0 + k) * hid + c0 + x4);
+      }
+      cp_async_commit();
+    };
+    __syncthreads();
+    load_tiles(0, 0);
+    for (int kt = 0; kt < kPDim / kHgBK; ++kt) {
+      const int buf = kt & 1;
+      if (kt + 1 < kPDim / kHgBK) { load_tiles(buf ^ 1, (kt + 1) * kHgBK); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kHgBK; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][4 * ty]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + 4 * ty]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][4 * tx]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + 4 * tx]);
+        const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], bc[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+    // epilogue of this pass: hidden = relu(acc + F[img] + Tt); o += hidden * Wb
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int cb = c0 + jj * 64 + 4 * tx;
+      const float4 tt = *reinterpret_cast<const float4*>(ws.Tt + cb);
+      const float tta[4] = {tt.x, tt.y, tt.z, tt.w};
+      float4 wb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wb[j] = __ldg(reinterpret_cast<const float4*>(dn.Wb + (size_t)(cb + j) * 4));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (rows[i] >= n_rows) continue;
+        const float4 f4 = __ldg(reinterpret_cast<const float4*>(ws.F + (size_t)(rows[i] / rpf) * hid + cb));
+        const float fa[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float hval = (acc[i][jj * 4 + j] + fa[j]) + tta[j];
+          hval = hval > 0.f ? hval : 0.f;
+          o[i][0] = fmaf(hval, wb[j].x, o[i][0]);
+          o[i][1] = fmaf(hval, wb[j].y, o[i][1]);
+          o[i][2] = fmaf(hval, wb[j].z, o[i][2]);
+        }
+      }
+    }
+  }
+  // reduce the 16 column-threads of each row (lanes tx of a half-warp), fixed butterfly order
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      float v = o[i][d];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      o[i][d] = v;
+    }
+  if (tx == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (rows[i] >= n_rows) continue;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float out = o[i][d] + dn.bb[head * 3 + d];
+        const float score = __fdiv_rn(out, et.std32);
+        emit_score(ws, c, et, mode, s, rows[i] * dn.D + head * 3 + d, score);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// reductions + the step controller (one thread of the last block to finish)
+// ------------------------------------------------------------------------------------------------------------
+enum RedKind : int { kRedInit0 = 0, kRedInit1 = 1, kRedErr = 2 };
+
+__device__ void export_counters(const SamplerWs& ws, const RkCtrl& c) {
+  if (!c.counters) return;
+  c.counters[0] = c.status; c.counters[1] = c.nfev; c.counters[2] = c.n_acc; c.counters[3] = c.n_rej;
+  c.counters[4] = c.nan_seen; c.counters[5] = c.attempts;
+}
+
+// scipy RungeKutta._step_impl: head of one `while not step_accepted` iteration
+__device__ void begin_attempt(RkCtrl& c, bool new_step) {
+  const double min_step = 10.0 * fabs(nextafter(c.t, c.direction * (double)INFINITY) - c.t);
+  if (new_step) {
+    if (c.h_abs > c.max_step) c.h_abs = c.max_step;
+    else if (c.h_abs < min_step) c.h_abs = min_step;
+    c.step_rejected = 0;
+  }
+  if (c.h_abs < min_step) { c.status = -1; return; }
+  double h = c.h_abs * c.direction;
+  double t_new = c.t + h;
+  if (c.direction * (t_new - c.eps) > 0) t_new = c.eps;
+  h = t_new - c.t;
+  c.h_abs = fabs(h);
+  c.h = h;
+  c.t_new = t_new;
+}
+
+__device__ void controller(const SamplerWs& ws, RkCtrl& c, int kind, double s0, double s1) {
+  const double sqrt_n = sqrt((double)c.n);     // x.size ** 0.5
+  if (kind == kRedInit0) {
+    c.nfev = 1;
+    const double d0 = sqrt(s0) / sqrt_n, d1 = sqrt(s1) / sqrt_n;
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    const double interval = fabs(c.eps - c.T0);
+    h0 = fmin(h0, interval);
+    c.h0 = h0; c.d0 = d0; c.d1 = d1;
+  } else if (kind == kRedInit1) {
+    c.nfev = 2;
+    const double d2 = (sqrt(s0) / sqrt_n) / c.h0;
+    double h1;
+    if (c.d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, c.h0 * 1e-3);
+    else h1 = pow(0.01 / fmax(c.d1, d2), 1.0 / 5.0);           // order + 1 = 5
+    const double interval = fabs(c.eps - c.T0);
+    c.h_abs = fmin(fmin(100.0 * c.h0, h1), fmin(interval, c.max_step));
+    begin_attempt(c, true);
+  } else {
+    const double err = sqrt(s0) / sqrt_n;
+    c.attempts += 1;
+    c.nfev += 6;
+    if (err < 1.0) {
+      double factor = (err == 0.0) ? kMaxFactor : fmin(kMaxFactor, kSafety * pow(err, kErrExponent));
+      if (c.step_rejected) factor = fmin(1.0, factor);
+      c.h_abs *= factor;
+      c.t_old = c.t; c.h_done = c.h;
+      c.t = c.t_new;
+      c.n_acc += 1;
+      c.accepted_now = 1;
+      int hi = c.te_next;
+      while (hi < c.n_eval && ws.t_eval[hi] >= c.t) ++hi;      // ivp.py: searchsorted(side='left') on reversed t_eval
+      c.te_lo = c.te_next; c.te_hi = hi; c.te_next = hi;
+      if (c.direction * (c.t - c.eps) >= 0) c.status = 1;
+      else begin_attempt(c, true);
+    } else {
+      const double f = kSafety * pow(err, kErrExponent);
+      c.h_abs *= (f > kMinFactor ? f : kMinFactor);            // python max(MIN_FACTOR, x): NaN -> MIN_FACTOR
+      c.step_rejected = 1;
+      c.n_rej += 1;
+      c.accepted_now = 0;
+      for (int k = 1; k < 7; ++k) c.nan_stage[k] = 0;
+      begin_attempt(c, false);
+    }
+  }
+  export_counters(ws, c);
+}
+
+__global__ void __launch_bounds__(256) k_reduce(SamplerWs ws, int kind) {
+  RkCtrl& c = *ws.ctrl;
+  if (c.status != 0) return;
+  __shared__ double sh0[256], sh1[256];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x, n = c.n;
+  double a0 = 0.0, a1 = 0.0;
+  for (int i = blockIdx.x * 256 + tid; i < n; i += gridDim.x * 256) {
+    const double y = ws.y[i];
+    if (kind == kRedInit0) {
+      const double scale = c.atol + fabs(y) * c.rtol;
+      const double u = y / scale, v = kval(ws.K, c, 0, n, i) / scale;
+      a0 += u * u; a1 += v * v;
+    } else if (kind == kRedInit1) {
+      const double scale = c.atol + fabs(y) * c.rtol;
+      const double u = (kval(ws.K, c, 1, n, i) - kval(ws.K, c, 0, n, i)) / scale;
+      a0 += u * u;
+    } else {
+      const double scale = c.atol + fmax(fabs(y), fabs(ws.ynew[i])) * c.rtol;
+      double e = 0.0;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) e += kval(ws.K, c, j, n, i) * kE[j];
+      const double u = (e * c.h) / scale;
+      a0 += u * u;
+    }
+  }
+  sh0[tid] = a0; sh1[tid] = a1;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (tid < st) { sh0[tid] += sh0[tid + st]; sh1[tid] += sh1[tid + st]; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    ws.partial[blockIdx.x] = sh0[0];
+    ws.partial[kMaxRedBlocks + blockIdx.x] = sh1[0];
+    __threadfence();
+    const unsigned prev = atomicAdd(&c.block_counter, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && tid == 0) {
+    __threadfence();
+    double s0 = 0.0, s1 = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) { s0 += ws.partial[b]; s1 += ws.partial[kMaxRedBlocks + b]; }
+    c.block_counter = 0u;
+    controller(ws, c, kind, s0, s1);
+  }
+}
+
+// after an accepted step: quartic dense output at the t_eval points inside the step, then roll y <- y_new, f <- f_new
+__global__ void __launch_bounds__(256) k_post_step(SamplerWs ws) {
+  RkCtrl& c = *ws.ctrl;
+  if (c.status < 0 || !c.accepted_now) return;
+  const int n = c.n;
+  const int lo = c.te_lo, hi = c.te_hi;
+  const double h = c.h_done, t_old = c.t_old;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const double y_old = ws.y[i];
+    if (c.xs && hi > lo) {
+      double Q[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const double k = kval(ws.K, c, j, n, i);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Q[q] += k * kP[j][q];
+      }
+      for (int e = lo; e < hi; ++e) {
+        const double x = (ws.t_eval[e] - t_old) / h;
+        const double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x;      // np.cumprod
+        const double dot = ((Q[0] * p1 + Q[1] * p2) + Q[2] * p3) + Q[3] * p4;
+        c.xs[(size_t)e * n + i] = __dadd_rn(__dmul_rn(h, dot), y_old);
+      }
+    }
+    ws.y[i] = ws.ynew[i];
+    ws.K[i] = kval(ws.K, c, 6, n, i);
+  }
+  __shared__ bool is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(&c.block_counter, 1u);
+    is_last = (prev == gridDim.x - 1);
+    if (is_last) {
+      c.block_counter = 0u;
+      c.accepted_now = 0;
+      for (int k = 0; k < 7; ++k) c.nan_stage[k] = 0;
+    }
+  }
+}
+
+__global__ void k_export(SamplerWs ws) { export_counters(ws, *ws.ctrl); }
+
+__global__ void k_rot6d_to_aa(const float* __restrict__ x6d, int n, float* __restrict__ aa) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float d[6], R[9], a[3];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) d[k] = x6d[(size_t)i * 6 + k];
+  rot6d_to_matrix(d, R);
+  matrix_to_axis_angle(R, a);
+  aa[(size_t)i * 3 + 0] = a[0]; aa[(size_t)i * 3 + 1] = a[1]; aa[(size_t)i * 3 + 2] = a[2];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int n_eval, SamplerWs* ws) {
+  const int D = 3 * n_heads, hid = n_heads * kHeadHid;
+  const int R = (n_rows + rows_per_feat - 1) / rows_per_feat;
+  const int Npad = (int)align_up((size_t)(n_rows > 0 ? n_rows : 1), kRowTile);
+  const size_t n = (size_t)n_rows * D;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_ctrl = take(sizeof(RkCtrl));
+  const size_t o_F = take((size_t)R * hid * 4);
+  const size_t o_Tt = take((size_t)hid * 4);
+  const size_t o_P2T = take((size_t)kPDim * Npad * 4);
+  const size_t o_y = take(n * 8);
+  const size_t o_yn = take(n * 8);
+  const size_t o_K = take(7 * n * 8);
+  const size_t o_part = take((size_t)2 * kMaxRedBlocks * 8);
+  const size_t o_te = take((size_t)(n_eval > 0 ? n_eval : 1) * 8);
+  if (ws) {
+    char* b = static_cast<char*>(base);
+    ws->ctrl = reinterpret_cast<RkCtrl*>(b + o_ctrl);
+    ws->F = reinterpret_cast<float*>(b + o_F);
+    ws->Tt = reinterpret_cast<float*>(b + o_Tt);
+    ws->P2T = reinterpret_cast<float*>(b + o_P2T);
+    ws->y = reinterpret_cast<double*>(b + o_y);
+    ws->ynew = reinterpret_cast<double*>(b + o_yn);
+    ws->K = reinterpret_cast<double*>(b + o_K);
+    ws->partial = reinterpret_cast<double*>(b + o_part);
+    ws->t_eval = reinterpret_cast<double*>(b + o_te);
+    ws->eval_out = nullptr; ws->eval_x = nullptr;
+    ws->eval_rows = n_rows; ws->eval_rpf = rows_per_feat;
+    ws->Npad = Npad; ws->R = R;
+  }
+  return off;
+}
+
+static int red_blocks(int n) { int b = (n + 255) / 256; return b < 1 ? 1 : (b > kMaxRedBlocks ? kMaxRedBlocks : b); }
+
+static int launch_eval(const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, cudaStream_t st) {
+  VPHO_LAUNCH(k_time_term, dim3((dn.hid + 255) / 256), dim3(256), 0, st, dn, ws, mode, s);
+  VPHO_LAUNCH(k_pose_encoder, dim3(ws.Npad / kPeRows), dim3(256), 0, st, dn, ws, mode, s);
+  VPHO_LAUNCH(k_head_simt, dim3(ws.Npad / kRowTile, dn.n_heads), dim3(256), 0, st, dn, ws, mode, s);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
+
+static int launch_attempts(const DenoiserDev& dn, const SamplerWs& ws, int n, int max_attempts, cudaStream_t st) {
+  const int rb = red_blocks(n);
+  for (int a = 0; a < max_attempts; ++a) {
+    for (int s = 1; s <= 6; ++s) {
+      int rc = launch_eval(dn, ws, kModeStage, s, st);
+      if (rc) return rc;
+    }
+    VPHO_LAUNCH(k_reduce, dim3(rb), dim3(256), 0, st, ws, (int)kRedErr);
+    VPHO_LAUNCH(k_post_step, dim3(rb), dim3(256), 0, st, ws);
+    VPHO_CHECK_LAUNCH();
+  }
+  return VPHO_OK;
+}
+
+}  // namespace vpho
+
+using namespace vpho;
+
+extern "C" int vpho_version(void) { return 100; }
+
+extern "C" int vpho_denoiser_create(int n_heads, const float* fourier_W, const float* t_w, const float* t_b,
+                                    const float* p1_w, const float* p1_b, const float* p2_w, const float* p2_b,
+                                    const float* ha_w, const float* ha_b, const float* hb_w, const float* hb_b,
+                                    vpho_denoiser_t* out) {
+  if (n_heads <= 0 || 3 * n_heads > kMaxD || !fourier_W || !t_w || !t_b || !p1_w || !p1_b || !p2_w || !p2_b || !ha_w ||
+      !ha_b || !hb_w || !hb_b || !out)
+    return VPHO_ERR_INVALID;
+  const int D = 3 * n_heads, hid = n_heads * kHeadHid;
+  const size_t n_four = 64, n_wt = 128 * 128, n_bt = 128, n_w1 = (size_t)D * 256, n_b1 = 256, n_w2 = 256 * 256,
+               n_b2 = 256, n_wat = (size_t)128 * hid, n_wap = (size_t)256 * hid, n_waf = (size_t)1024 * hid,
+               n_ba = hid, n_wb = (size_t)hid * 4, n_bb = D;
+  size_t off = 0;
+  auto take = [&](size_t cnt) { size_t o = off; off += (cnt + 63) / 64 * 64; return o; };
+  const size_t o_four = take(n_four), o_wt = take(n_wt), o_bt = take(n_bt), o_w1 = take(n_w1), o_b1 = take(n_b1),
+               o_w2 = take(n_w2), o_b2 = take(n_b2), o_wat = take(n_wat), o_wap = take(n_wap), o_waf = take(n_waf),
+               o_ba = take(n_ba), o_wb = take(n_wb), o_bb = take(n_bb);
+  std::vector<float> h(off, 0.f);
+  for (size_t i = 0; i < n_four; ++i) h[o_four + i] = fourier_W[i];
+  for (int o = 0; o < 128; ++o)
+    for (int k = 0; k < 128; ++k) h[o_wt + (size_t)k * 128 + o] = t_w[(size_t)o * 128 + k];   // nn.Linear weight [out][in]
+  for (int i = 0; i < 128; ++i) h[o_bt + i] = t_b[i];
+  for (int o = 0; o < 256; ++o)
+    for (int k = 0; k < D; ++k) h[o_w1 + (size_t)k * 256 + o] = p1_w[(size_t)o * D + k];
+  for (int i = 0; i < 256; ++i) h[o_b1 + i] = p1_b[i];
+  for (int o = 0; o < 256; ++o)
+    for (int k = 0; k < 256; ++k) h[o_w2 + (size_t)k * 256 + o] = p2_w[(size_t)o * 256 + k];
+  for (int i = 0; i < 256; ++i) h[o_b2 + i] = p2_b[i];
+  // ParallelLinear weight [n][1408][256]: rows 0..127 time, 128..383 pose, 384..1407 conditioning (denoiser.py:75)
+  for (int nn = 0; nn < n_heads; ++nn)
+    for (int k = 0; k < 1408; ++k) {
+      const float* src = ha_w + ((size_t)nn * 1408 + k) * 256;
+      float* dst;
+      if (k < 128) dst = &h[o_wat + (size_t)k * hid];
+      else if (k < 384) dst = &h[o_wap + (size_t)(k - 128) * hid];
+      else dst = &h[o_waf + (size_t)(k - 384) * hid];
+      for (int cc = 0; cc < 256; ++cc) dst[nn * 256 + cc] = src[cc];
+    }
+  for (int i = 0; i < hid; ++i) h[o_ba + i] = ha_b[i];
+  for (int nn = 0; nn < n_heads; ++nn)
+    for (int cc = 0; cc < 256; ++cc)
+      for (int d = 0; d < 3; ++d) h[o_wb + ((size_t)nn * 256 + cc) * 4 + d] = hb_w[((size_t)nn * 256 + cc) * 3 + d];
+  for (int i = 0; i < D; ++i) h[o_bb + i] = hb_b[i];
+
+  DenoiserHost* dh = new DenoiserHost();
+  if (cudaMalloc((void**)&dh->blob, off * sizeof(float)) != cudaSuccess) { delete dh; return VPHO_ERR_ALLOC; }
+  if (cudaMemcpy(dh->blob, h.data(), off * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(dh->blob); delete dh; return VPHO_ERR_ALLOC;
+  }
+  const float* b = dh->blob;
+  DenoiserDev& d = dh->dev;
+  d.n_heads = n_heads; d.D = D; d.hid = hid;
+  d.fourier_W = b + o_four; d.Wt = b + o_wt; d.bt = b + o_bt; d.W1 = b + o_w1; d.b1 = b + o_b1; d.W2 = b + o_w2;
+  d.b2 = b + o_b2; d.Wa_t = b + o_wat; d.Wa_p = b + o_wap; d.Wa_f = b + o_waf; d.ba = b + o_ba; d.Wb = b + o_wb;
+  d.bb = b + o_bb; d.Wa_p_hi = nullptr; d.Wa_p_lo = nullptr;
+  *out = dh;
+  return VPHO_OK;
+}
+
+extern "C" int vpho_denoiser_destroy(vpho_denoiser_t h) {
+  if (!h) return VPHO_ERR_INVALID;
+  DenoiserHost* dh = static_cast<DenoiserHost*>(h);
+  cudaFree(dh->blob);
+  delete dh;
+  return VPHO_OK;
+}
+
+extern "C" size_t vpho_sample_workspace_bytes(int n_heads, int n_rows, int rows_per_feat, int n_eval) {
+  if (n_heads <= 0 || n_rows < 0 || rows_per_feat <= 0) return 0;
+  return carve(nullptr, n_heads, n_rows, rows_per_feat, n_eval, nullptr);
+}
+
+extern "C" int vpho_score_eval(vpho_denoiser_t h, const float* x, float t, const float* feat, int n_rows,
+                               int rows_per_feat, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || n_rows < 0 || rows_per_feat <= 0 || !workspace) return VPHO_ERR_INVALID;
+  if (n_rows == 0) return VPHO_OK;
+  if (!x || !feat || !out) return VPHO_ERR_INVALID;
+  const DenoiserDev& dn = static_cast<DenoiserHost*>(h)->dev;
+  SamplerWs ws;
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, 1, &ws) > workspace_bytes) return VPHO_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  ws.eval_x = x; ws.eval_out = out;
+  VPHO_LAUNCH(k_set_eval_time, dim3(1), dim3(1), 0, st, ws, t);
+  VPHO_LAUNCH(k_feat_term, dim3(dn.hid / kFtCols, (ws.R + kFtRows - 1) / kFtRows), dim3(256), 0, st, dn, feat, ws.R, ws.F);
+  VPHO_CHECK_LAUNCH();
+  return launch_eval(dn, ws, kModeEval, 0, st);
+}
+
+extern "C" int vpho_sample_begin(vpho_denoiser_t h, const float* feat, int n_rows, int rows_per_feat,
+                                 const float* init_x, double T0, double eps, const double* t_eval, int n_eval,
+                                 double rtol, double atol, double max_step, int num_steps, int max_attempts,
+                                 double* xs, double* x, int32_t* counters, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  if (!h || n_rows < 0 || rows_per_feat <= 0 || !workspace || n_eval < 1 || num_steps < 1 || max_attempts < 0)
+    return VPHO_ERR_INVALID;
+  if (n_rows > 0 && (!feat || !init_x || !x)) return VPHO_ERR_INVALID;
+  const DenoiserDev& dn = static_cast<DenoiserHost*>(h)->dev;
+  SamplerWs ws;
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws) > workspace_bytes) return VPHO_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = n_rows * dn.D;
+  SampleCfg cfg{T0, eps, rtol, atol, max_step, n_rows, dn.D, n_eval, num_steps, rows_per_feat, t_eval, xs, x, counters};
+  VPHO_LAUNCH(k_init_ctrl, dim3(1), dim3(64), 0, st, cfg, ws);
+  VPHO_CHECK_LAUNCH();
+  if (n_rows == 0) return VPHO_OK;
+  const int rb = red_blocks(n);
+  VPHO_LAUNCH(k_init_state, dim3(rb), dim3(256), 0, st, ws, init_x, n);
+  VPHO_LAUNCH(k_feat_term, dim3(dn.hid / kFtCols, (ws.R + kFtRows - 1) / kFtRows), dim3(256), 0, st, dn, feat, ws.R, ws.F);
+  VPHO_CHECK_LAUNCH();
+  int rc = launch_eval(dn, ws, kModeInit0, 0, st);
+  if (rc) return rc;
+  VPHO_LAUNCH(k_reduce, dim3(rb), dim3(256), 0, st, ws, (int)kRedInit0);
+  rc = launch_eval(dn, ws, kModeInit1, 0, st);
+  if (rc) return rc;
+  VPHO_LAUNCH(k_reduce, dim3(rb), dim3(256), 0, st, ws, (int)kRedInit1);
+  VPHO_CHECK_LAUNCH();
+  return launch_attempts(dn, ws, n, max_attempts, st);
+}
+
+extern "C" int vpho_sample_continue(vpho_denoiser_t h, int n_rows, int rows_per_feat, int n_eval, int max_attempts,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || n_rows < 0 || rows_per_feat <= 0 || !workspace || max_attempts < 0) return VPHO_ERR_INVALID;
+  if (n_rows == 0) return VPHO_OK;
+  const DenoiserDev& dn = static_cast<DenoiserHost*>(h)->dev;
+  SamplerWs ws;
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws) > workspace_bytes) return VPHO_ERR_INVALID;
+  return launch_attempts(dn, ws, n_rows * dn.D, max_attempts, (cudaStream_t)stream);
+}
+
+extern "C" int vpho_sample_finish(vpho_denoiser_t h, int n_rows, int rows_per_feat, int n_eval, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  if (!h || n_rows < 0 || rows_per_feat <= 0 || !workspace) return VPHO_ERR_INVALID;
+  if (n_rows == 0) return VPHO_OK;
+  const DenoiserDev& dn = static_cast<DenoiserHost*>(h)->dev;
+  SamplerWs ws;
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws) > workspace_bytes) return VPHO_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_eval(dn, ws, kModeFinal, 0, st);
+  if (rc) return rc;
+  VPHO_LAUNCH(k_export, dim3(1), dim3(1), 0, st, ws);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
+
+extern "C" int vpho_rot6d_to_axis_angle(const float* x6d, int n_rot, float* aa, void* stream) {
+  if (n_rot < 0) return VPHO_ERR_INVALID;
+  if (n_rot == 0) return VPHO_OK;
+  if (!x6d || !aa) return VPHO_ERR_INVALID;
+  VPHO_LAUNCH(k_rot6d_to_aa, dim3((n_rot + 255) / 256), dim3(256), 0, (cudaStream_t)stream, x6d, n_rot, aa);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}

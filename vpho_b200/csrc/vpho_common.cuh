@@ -11,6 +11,24 @@
   extern __shared__ __align__(16) unsigned char name##_raw_[];    \
   type* name = reinterpret_cast<type*>(name##_raw_)
 #define VPHO_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define VPHO_CONSTANT __constant__
+namespace vpho {
+// 16-byte asynchronous global->shared copy (LDGSTS) and its group fences
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+}  // namespace vpho
+#else
+#define VPHO_CONSTANT static
+namespace vpho {
+inline void cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
+inline void cp_async_commit() {}
+template <int N>
+inline void cp_async_wait() {}
+}  // namespace vpho
 #endif
 
 #define VPHO_OK 0

@@ -1,0 +1,169 @@
+"""Host-side mirror of the reference's score-based sampling interface over the CUDA sampler.
+
+  * `Denoiser`              <- `BaseDenoiser` (lib/model/denoiser.py:33-82), evaluation only
+  * `ScoreBasedModelAgent`  <- `ScoreBasedModelAgent` (lib/model/score_based_model.py:109-149): `sample(data, denoiser,
+                               T0, init_x=None) -> (xs (N, steps, D) f64, x (N, D) f64)`, `get_score(data, denoiser)`
+
+Everything numeric happens in `libvpho_b200.so` (csrc/sampler.cu); this file only allocates outputs, forwards
+pointers and polls the device-side controller's status word.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import capi
+
+SIGMA_MIN, SIGMA_MAX, SAMPLING_EPS = 0.01, 50, 1e-5   # lib/model/sde.py:90-97 ('ve')
+RTOL, ATOL, MAX_STEP = 3e-3, 3e-4, 10.0               # lib/model/score_based_model.py:51-52,91
+
+_KEYS = ("t_encoder.0.W", "t_encoder.1.weight", "t_encoder.1.bias", "pose_encoder.0.weight", "pose_encoder.0.bias",
+         "pose_encoder.2.weight", "pose_encoder.2.bias", "head.head.0.weight", "head.head.0.bias",
+         "head.head.2.weight", "head.head.2.bias")
+
+
+def ve_prior_std(T: float) -> float:
+    """sigma(T) as a python float (lib/model/sde.py:15-18,26-28)."""
+    return SIGMA_MIN * (SIGMA_MAX / SIGMA_MIN) ** T
+
+
+class Denoiser:
+    """Packed score network on the device.  `state` uses the reference's state-dict keys (denoiser.py:33-66)."""
+
+    def __init__(self, state: Dict[str, object], lib: Optional[capi.Library] = None):
+        self.lib = lib or capi.lib()
+        arrs = []
+        for k in _KEYS:
+            v = state[k]
+            if isinstance(v, torch.Tensor):
+                v = v.detach().cpu().numpy()
+            arrs.append(np.ascontiguousarray(v, dtype=np.float32))
+        n = arrs[7].shape[0]
+        assert arrs[7].shape == (n, 1408, 256) and arrs[9].shape == (n, 256, 3) and arrs[3].shape == (256, 3 * n)
+        self.n_heads = n
+        self.out_dim = 3 * n
+        h = C.c_void_p()
+        self.lib.check(self.lib.c.vpho_denoiser_create(n, *[capi.host_ptr(a) for a in arrs], C.byref(h)),
+                       "vpho_denoiser_create")
+        self.handle = h
+        self._ws: Dict[tuple, torch.Tensor] = {}
+        self.calls = 0   # network evaluations issued by the last sample() (nfev + 1)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.c.vpho_denoiser_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def workspace(self, n_rows: int, rows_per_feat: int, n_eval: int, device) -> torch.Tensor:
+        key = (n_rows, rows_per_feat, n_eval, str(device))
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = self.lib.c.vpho_sample_workspace_bytes(self.n_heads, n_rows, rows_per_feat, n_eval)
+            ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._ws = {key: ws}   # keep one
+        return ws
+
+    def __call__(self, data: dict) -> torch.Tensor:
+        """`BaseDenoiser.forward` for the sampling call pattern: every row shares one time value."""
+        x = data["sampled_pose"].contiguous().float()
+        t = data["t"]
+        t0 = float(t.reshape(-1)[0].item()) if isinstance(t, torch.Tensor) else float(t)
+        feat, rpf = _unique_feat(data, x.shape[0])
+        out = torch.empty_like(x)
+        ws = self.workspace(x.shape[0], rpf, 1, x.device)
+        st = self.lib.c.vpho_score_eval(self.handle, capi.ptr(x), C.c_float(t0), capi.ptr(feat), x.shape[0], rpf,
+                                        capi.ptr(out), capi.ptr(ws), ws.numel(), capi.stream_of(x))
+        self.lib.check(st, "vpho_score_eval")
+        return out
+
+
+def _unique_feat(data: dict, n_rows: int):
+    """Returns (feat (R,1024) contiguous f32, rows_per_feat).  `data['feat_unique']` (one row per image) avoids the
+    check; a plain repeated `data['feat']` (VPHO.py:239) is recognised by comparing each group with its first row."""
+    if "feat_unique" in data:
+        fu = data["feat_unique"].contiguous().float()
+        assert n_rows % max(fu.shape[0], 1) == 0
+        return fu, (n_rows // fu.shape[0] if fu.shape[0] else 1)
+    feat = data["feat"].contiguous().float()
+    assert feat.shape[0] == n_rows
+    S = int(data.get("sample_num", 0) or 0)
+    if S > 1 and n_rows % S == 0:
+        g = feat.view(n_rows // S, S, -1)
+        if bool((g == g[:, :1]).all().item()):
+            return g[:, 0].contiguous(), S
+    return feat, 1
+
+
+class ScoreBasedModelAgent:
+    """Drop-in for the evaluation-time methods of the reference's `ScoreBasedModelAgent`."""
+
+    def __init__(self, sampling_steps: int = 50, sample_num: int = 100, sampler: str = "ode",
+                 first_attempts: int = 6):
+        if sampler != "ode":
+            raise NotImplementedError("Only ode sampler is supported for now.")
+        self.sampling_steps = sampling_steps
+        self.sample_num = sample_num
+        self.sampling_eps = SAMPLING_EPS
+        self.T = 1.0
+        self.first_attempts = first_attempts
+        self.last_info: dict = {}
+
+    def prior_fn(self, shape, T):
+        """ve_prior (lib/model/sde.py:26-28): CPU draw from torch's global generator, as the reference does."""
+        return torch.randn(*shape) * ve_prior_std(T)
+
+    @torch.no_grad()
+    def sample(self, data: dict, denoiser: Denoiser, T0: float, init_x: Optional[torch.Tensor] = None,
+               return_inprocess: bool = True):
+        """-> (in_process (N, steps, D) float64 [permuted view, as the reference returns it], final (N, D) float64)."""
+        device = (data["feat_unique"] if "feat_unique" in data else data["feat"]).device
+        D = denoiser.out_dim
+        n_rows = int(data["n_rows"]) if "n_rows" in data else int(data["feat"].shape[0])
+        prior = self.prior_fn((n_rows, D), T0).to(device)
+        x0 = prior if init_x is None else init_x.to(device) + prior      # score_based_model.py:62
+        x0 = x0.contiguous().float()
+        d2 = dict(data)
+        d2.setdefault("sample_num", self.sample_num)
+        feat, rpf = _unique_feat(d2, n_rows)
+        n_eval = self.sampling_steps
+        lib = denoiser.lib
+        ws = denoiser.workspace(n_rows, rpf, n_eval, device)
+        xs = torch.empty((n_eval, n_rows, D), dtype=torch.float64, device=device) if return_inprocess else None
+        x = torch.empty((n_rows, D), dtype=torch.float64, device=device)
+        counters = torch.zeros(8, dtype=torch.int32, device=device)
+        stream = capi.stream_of(x0)
+        st = lib.c.vpho_sample_begin(denoiser.handle, capi.ptr(feat), n_rows, rpf, capi.ptr(x0), float(T0),
+                                     float(self.sampling_eps), None, n_eval, RTOL, ATOL, MAX_STEP, n_eval,
+                                     self.first_attempts, capi.ptr(xs), capi.ptr(x), capi.ptr(counters), capi.ptr(ws),
+                                     ws.numel(), stream)
+        lib.check(st, "vpho_sample_begin")
+        lib.check(lib.c.vpho_sample_finish(denoiser.handle, n_rows, rpf, n_eval, capi.ptr(ws), ws.numel(), stream),
+                  "vpho_sample_finish")
+        while True:
+            c = counters.cpu().tolist() if n_rows else [1, 0, 0, 0, 0, 0, 0, 0]
+            if c[0] != 0:
+                break
+            lib.check(lib.c.vpho_sample_continue(denoiser.handle, n_rows, rpf, n_eval, 4, capi.ptr(ws), ws.numel(),
+                                                 stream), "vpho_sample_continue")
+            lib.check(lib.c.vpho_sample_finish(denoiser.handle, n_rows, rpf, n_eval, capi.ptr(ws), ws.numel(), stream),
+                      "vpho_sample_finish")
+        self.last_info = {"status": c[0], "nfev": c[1], "accepted": c[2], "rejected": c[3], "nan": bool(c[4]),
+                          "attempts": c[5], "net_calls": c[1] + 1}
+        denoiser.calls = c[1] + 1
+        if c[0] < 0:
+            raise capi.VphoError("RK45: required step size is less than spacing between numbers")
+        if c[4]:
+            print("\033[31mWarning: NaN detected in score evaluation. \033[0m")   # score_based_model.py:70
+        self.first_attempts = max(self.first_attempts, c[5])
+        if xs is None:
+            return None, x
+        return xs.permute(1, 0, 2), x
+
+    def get_score(self, data, denoiser):
+        return denoiser(data)

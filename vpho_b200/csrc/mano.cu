@@ -19,16 +19,30 @@ struct ManoModelHost {
 
 template <int TC>
 __global__ void __launch_bounds__(kVChunkPad) mano_forward_kernel(ManoModelDev m, const float* __restrict__ pose,
-                                                                  const float* __restrict__ shape, int n,
-                                                                  float* __restrict__ verts, float* __restrict__ joints) {
+                                                                  const float* __restrict__ shape, int pose_stride,
+                                                                  int shape_stride, int n, float* __restrict__ verts,
+                                                                  float* __restrict__ joints) {
   VPHO_DYN_SMEM(ManoSmem<TC>, sp);
   ManoSmem<TC>& s = *sp;
   const int c0 = blockIdx.x * TC;
   const int chunk = blockIdx.y;
   const int tid = threadIdx.x;
   mano_pose_setup<TC>(
-      m, [&](int c) { return (c0 + c < n) ? pose + (size_t)(c0 + c) * 48 : (const float*)nullptr; },
-      [&](int c) { return (c0 + c < n) ? shape + (size_t)(c0 + c) * 10 : (const float*)nullptr; }, s);
+      m,
+      [&](int c, int j, float* a) {
+        if (c0 + c >= n) return false;
+        const float* pp = pose + (size_t)(c0 + c) * pose_stride + 3 * j;
+        a[0] = pp[0]; a[1] = pp[1]; a[2] = pp[2];
+        return true;
+      },
+      [&](int c, float* beta) {
+        if (c0 + c >= n) return false;
+        const float* sp = shape + (size_t)(c0 + c) * shape_stride;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) beta[k] = sp[k];
+        return true;
+      },
+      s);
 
   if (chunk == 0) {
     for (int it = tid; it < TC * 16; it += blockDim.x) {
@@ -91,8 +105,8 @@ __global__ void __launch_bounds__(kVChunkPad) mano_forward_kernel(ManoModelDev m
 }
 
 template <int TC>
-static int launch_mano_forward(const ManoModelDev& m, const float* pose, const float* shape, int n, float* verts,
-                               float* joints, cudaStream_t stream) {
+static int launch_mano_forward(const ManoModelDev& m, const float* pose, const float* shape, int pose_stride,
+                               int shape_stride, int n, float* verts, float* joints, cudaStream_t stream) {
   dim3 grid((n + TC - 1) / TC, kNumVChunks);
   const size_t smem = sizeof(ManoSmem<TC>);
 #ifndef VPHO_EMU
@@ -102,16 +116,18 @@ static int launch_mano_forward(const ManoModelDev& m, const float* pose, const f
     attr_set = true;
   }
 #endif
-  VPHO_LAUNCH(mano_forward_kernel<TC>, grid, dim3(kVChunkPad), smem, stream, m, pose, shape, n, verts, joints);
+  VPHO_LAUNCH(mano_forward_kernel<TC>, grid, dim3(kVChunkPad), smem, stream, m, pose, shape, pose_stride, shape_stride, n, verts,
+              joints);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }
 
-int mano_forward_dev(const ManoModelDev& m, const float* pose, const float* shape, int n, float* verts, float* joints,
-                     cudaStream_t stream) {
+// pose/shape rows may be strided (elements) so callers can pick e.g. candidate 0 of every image without a gather
+int mano_forward_dev(const ManoModelDev& m, const float* pose, const float* shape, int pose_stride, int shape_stride,
+                     int n, float* verts, float* joints, cudaStream_t stream) {
   if (n <= 0) return VPHO_OK;
-  if (n >= 148 * 8) return launch_mano_forward<16>(m, pose, shape, n, verts, joints, stream);
-  return launch_mano_forward<4>(m, pose, shape, n, verts, joints, stream);
+  if (n >= 148 * 8) return launch_mano_forward<16>(m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream);
+  return launch_mano_forward<4>(m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream);
 }
 
 const ManoModelDev& mano_model_dev(const void* handle) { return static_cast<const ManoModelHost*>(handle)->dev; }
@@ -193,6 +209,9 @@ extern "C" int vpho_mano_destroy(vpho_mano_t h) {
 
 extern "C" int vpho_mano_forward(vpho_mano_t h, const float* pose, const float* shape, int n, float* verts,
                                  float* joints, void* stream) {
-  if (!h || !pose || !shape || !joints || n < 0) return VPHO_ERR_INVALID;
-  return mano_forward_dev(static_cast<ManoModelHost*>(h)->dev, pose, shape, n, verts, joints, (cudaStream_t)stream);
+  if (!h || n < 0) return VPHO_ERR_INVALID;
+  if (n == 0) return VPHO_OK;
+  if (!pose || !shape || !joints) return VPHO_ERR_INVALID;
+  return mano_forward_dev(static_cast<ManoModelHost*>(h)->dev, pose, shape, 48, 10, n, verts, joints,
+                          (cudaStream_t)stream);
 }

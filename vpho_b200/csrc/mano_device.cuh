@@ -55,19 +55,17 @@ __device__ __forceinline__ void compose34(const float* P, const float* Rrel, con
   }
 }
 
-// Block-cooperative pose set-up for TC candidates starting at c0.  `pose_of(c)` / `shape_of(c)` return global
-// pointers to the 48 axis-angle values / 10 betas of local candidate c (nullptr = padding slot).
+// Block-cooperative pose set-up for TC candidates.  `pose_of(c, j, a)` writes the axis-angle of kinematic joint j of
+// local candidate c into a[3]; `shape_of(c, beta)` writes its 10 betas; both return false for a padding slot.
 template <int TC, typename PoseFn, typename ShapeFn>
 __device__ __forceinline__ void mano_pose_setup(const ManoModelDev& m, PoseFn pose_of, ShapeFn shape_of,
                                                 ManoSmem<TC>& s) {
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int it = tid; it < TC * 16; it += nt) {
     const int c = it >> 4, j = it & 15;
-    const float* pp = pose_of(c);
-    const float* sp = shape_of(c);
-    float R[9];
-    if (pp) {
-      float a[3] = {pp[3 * j + 0], pp[3 * j + 1], pp[3 * j + 2]};
+    float R[9], a[3], beta[10];
+    const bool valid = pose_of(c, j, a);
+    if (valid) {
       manopth_rodrigues(a, R);
     } else {
 #pragma unroll
@@ -79,9 +77,10 @@ __device__ __forceinline__ void mano_pose_setup(const ManoModelDev& m, PoseFn po
 #pragma unroll
       for (int e = 0; e < 9; ++e) s.coefT[10 + (j - 1) * 9 + e][c] = R[e] - ((e % 4 == 0) ? 1.f : 0.f);
     }
-    float beta[10];
+    if (!shape_of(c, beta)) {
 #pragma unroll
-    for (int k = 0; k < 10; ++k) beta[k] = sp ? sp[k] : 0.f;
+      for (int k = 0; k < 10; ++k) beta[k] = 0.f;
+    }
     if (j == 0) {
 #pragma unroll
       for (int k = 0; k < 10; ++k) s.coefT[k][c] = beta[k];

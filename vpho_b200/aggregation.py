@@ -1,0 +1,166 @@
+"""Host-side mirrors of the reference's scoring / aggregation interfaces over the CUDA kernels (csrc/aggregate.cu).
+
+  * `Assets`          force-anchor tables + per-object point tables on the device
+                      (lib/utils/physics_fn.py:121-140, lib/utils/hand_fn.py:427-433, lib/model/head_object.py:9-34)
+  * `HeadObject`      <- `HeadObject.forward` / `flip_pt3d` (lib/model/head_object.py:36-67)
+  * `HeadPhysics`     <- `from_local_to_global` (lib/model/physics.py:500 -> :362-371), evaluation only
+  * `HOI_Aggregator`  <- `HOI_Aggregator.__call__(**kwargs) -> dict` (lib/model/aggregation.py:1167-1353)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import capi
+from .head_mano import HeadMano
+
+PHY_TOPK = 5   # hard-coded in the reference (aggregation.py:1246)
+
+
+class Assets:
+    def __init__(self, anchors: Dict[str, np.ndarray], objects: Dict[str, object], lib: Optional[capi.Library] = None):
+        self.lib = lib or capi.lib()
+        self.names: List[str] = list(objects["names"])
+        face = np.ascontiguousarray(anchors["face_vertex_idx"], dtype=np.int32).reshape(32, 3)
+        aw = np.ascontiguousarray(anchors["anchor_weight"], dtype=np.float32).reshape(32, 2)
+        v2j = np.ascontiguousarray(anchors["vert2joint"], dtype=np.float32).reshape(21, 778)
+        kpt = np.ascontiguousarray(objects["kpt3d"], dtype=np.float32)
+        verts = np.ascontiguousarray(objects["verts_sampled"], dtype=np.float32)
+        com = np.ascontiguousarray(objects["CoM"], dtype=np.float32)
+        self.n_obj, self.n_pts = verts.shape[0], verts.shape[1]
+        assert kpt.shape == (self.n_obj, 27, 3) and com.shape == (self.n_obj, 3)
+        h = C.c_void_p()
+        self.lib.check(self.lib.c.vpho_assets_create(capi.host_ptr(face), capi.host_ptr(aw), capi.host_ptr(v2j), self.n_obj,
+                                                     self.n_pts, capi.host_ptr(kpt), capi.host_ptr(verts),
+                                                     capi.host_ptr(com), C.byref(h)), "vpho_assets_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.c.vpho_assets_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def ids(self, names: Sequence[str], device) -> torch.Tensor:
+        return torch.tensor([self.names.index(n) for n in names], dtype=torch.int32, device=device)
+
+
+class HeadObject:
+    _WHICH = {"keypoint": 0, "verts": 1, "CoM": 2}
+
+    def __init__(self, assets: Assets):
+        self.assets = assets
+
+    def __call__(self, pose: torch.Tensor, name, data_name: str = "keypoint", is_right: Optional[torch.Tensor] = None):
+        """pose (bs, ..., 9) -> points (bs, ..., V, 3).  `is_right` (optional) fuses `flip_pt3d` into the same launch."""
+        lib, a = self.assets.lib, self.assets
+        lead = pose.shape[:-1]
+        bs = lead[0]
+        p = pose.reshape(bs, -1, 9).contiguous().float()
+        Cn = p.shape[1]
+        ids = name if isinstance(name, torch.Tensor) else a.ids(name, p.device)
+        which = self._WHICH[data_name]
+        V = (27, a.n_pts, 1)[which]
+        out = torch.empty((bs, Cn, V, 3), dtype=torch.float32, device=p.device)
+        ir = None if is_right is None else is_right.to(torch.uint8).contiguous()
+        lib.check(lib.c.vpho_object_points(a.handle, capi.ptr(p), capi.ptr(ids), capi.ptr(ir), bs, Cn, which,
+                                           0 if ir is None else 1, capi.ptr(out), capi.stream_of(p)), "vpho_object_points")
+        return out.reshape(*lead, V, 3)
+
+    forward = __call__
+
+    @staticmethod
+    def flip_pt3d(pt3d: torch.Tensor, is_right: torch.Tensor):
+        idx = torch.arange(pt3d.shape[0], device=pt3d.device)[~is_right]
+        pt3d[idx, ..., 0] = pt3d[idx, ..., 0] * -1
+        return pt3d
+
+
+class HeadPhysics:
+    def __init__(self, assets: Assets):
+        self.assets = assets
+
+    def from_local_to_global(self, force_local: torch.Tensor, hand_vert: torch.Tensor):
+        """force_local (..., 32, 3), hand_vert (..., 778, 3) camera frame -> force_point, force_global (..., 32, 3)."""
+        lib, a = self.assets.lib, self.assets
+        lead = hand_vert.shape[:-2]
+        v = hand_vert.reshape(-1, 778, 3).contiguous().float()
+        fl = force_local.reshape(-1, 32, 3).contiguous().float()
+        n = v.shape[0]
+        assert fl.shape[0] == n
+        fp = torch.empty((n, 32, 3), dtype=torch.float32, device=v.device)
+        fg = torch.empty_like(fp)
+        lib.check(lib.c.vpho_force_anchors(a.handle, capi.ptr(v), capi.ptr(fl), n, 1, capi.ptr(fp), capi.ptr(fg),
+                                           capi.stream_of(v)), "vpho_force_anchors")
+        return fp.reshape(*lead, 32, 3), fg.reshape(*lead, 32, 3)
+
+
+class HOI_Aggregator:
+    """Drop-in for `HOI_Aggregator` (lib/model/aggregation.py:1160-1353): same kwargs, same returned keys/dtypes."""
+
+    def __init__(self, head_mano: HeadMano, assets: Assets, debug: bool = False):
+        self.head_mano = head_mano
+        self.assets = assets
+        self.lib = assets.lib
+        self.debug = debug
+        self._ws = None
+        self.last_debug: dict = {}
+
+    def __call__(self, **kw):
+        lib, a = self.lib, self.assets
+        f32 = lambda t: t.contiguous().float()   # noqa: E731
+        dev = kw["hand_heatmap"].device
+        bs = kw["root_joint"].shape[0]
+        Kh, Ko = int(kw["hand_topk"]), int(kw["obj_topk"])
+        obj_pose = kw["obj_pose6d"].contiguous().double()
+        S = obj_pose.shape[1]
+        hand_pose_diff = f32(kw["hand_pose_diff"]).reshape(-1, 48)
+        assert hand_pose_diff.shape[0] == bs * S
+        hold = dict(
+            cam=f32(kw["cam_intrinsic"]), rjf=f32(kw["root_joint_flip"]), rj=f32(kw["root_joint"]),
+            is_right=kw["is_right"].to(torch.uint8).contiguous(), is_grasped=kw["is_grasped"].to(torch.uint8).contiguous(),
+            force_local=f32(kw["force_local"]), pose_diff=hand_pose_diff, pose_reg=f32(kw["hand_pose_regression"]),
+            shape=f32(kw["hand_shape"]).reshape(-1, 10), hm_h=f32(kw["hand_heatmap"]), bb_h=f32(kw["hand_bbox"]),
+            obj_pose=obj_pose, hm_o=f32(kw["obj_heatmap"]), bb_o=f32(kw["obj_bbox"]),
+            obj_id=kw["obj_name"] if isinstance(kw["obj_name"], torch.Tensor) else a.ids(kw["obj_name"], dev))
+        assert hold["hm_h"].shape == (bs, 21, 64, 64) and hold["hm_o"].shape == (bs, 27, 64, 64)
+        kk, nc, omax = Ko * Ko, Kh + 1, max(S, Ko * Ko)
+        out = dict(
+            obj_agg_6d=torch.empty((bs, 9), dtype=torch.float64, device=dev),
+            pose6d_candidate=torch.empty((bs, kk, 9), dtype=torch.float64, device=dev),
+            agg_obj_vert=torch.empty((bs, a.n_pts, 3), dtype=torch.float32, device=dev),
+            hand_agg_mano=torch.empty((bs, 58), dtype=torch.float32, device=dev),
+            hand_agg_vert=torch.empty((bs, 778, 3), dtype=torch.float32, device=dev),
+            hand_agg_joint=torch.empty((bs, 21, 3), dtype=torch.float32, device=dev))
+        dbg = {}
+        if self.debug:
+            z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)   # noqa: E731
+            dbg = dict(hand_score=z(4, bs, 2 * S, 5), hand_topk=z(4, bs, 5, Kh, dt=torch.int32), cascade_pose=z(bs, 48),
+                       obj_score=z(4, bs * omax), obj_topk=z(4, bs, Ko, dt=torch.int32), finger_score=z(bs, 5, nc),
+                       finger_topk=z(bs, 5, PHY_TOPK, dt=torch.int32), force_point=z(bs, 32, 3), force_global=z(bs, 32, 3))
+        nbytes = int(lib.c.vpho_hoi_workspace_bytes(bs, S, Kh, Ko, a.n_pts))
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
+            self._ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+        P = capi.ptr
+        args = capi.HoiArgs(
+            bs, S, Kh, Ko, PHY_TOPK, P(hold["cam"]), P(hold["rjf"]), P(hold["rj"]), P(hold["is_right"]),
+            P(hold["is_grasped"]), P(hold["force_local"]), P(hold["pose_diff"]), P(hold["pose_reg"]), P(hold["shape"]),
+            P(hold["hm_h"]), P(hold["bb_h"]), P(hold["obj_pose"]), P(hold["hm_o"]), P(hold["bb_o"]), P(hold["obj_id"]),
+            P(out["obj_agg_6d"]), P(out["pose6d_candidate"]), P(out["agg_obj_vert"]), P(out["hand_agg_mano"]),
+            P(out["hand_agg_vert"]), P(out["hand_agg_joint"]),
+            P(dbg.get("hand_score")), P(dbg.get("hand_topk")), P(dbg.get("cascade_pose")), P(dbg.get("obj_score")),
+            P(dbg.get("obj_topk")), P(dbg.get("finger_score")), P(dbg.get("finger_topk")), P(dbg.get("force_point")),
+            P(dbg.get("force_global")))
+        st = lib.c.vpho_hoi_aggregate(self.head_mano.handle, a.handle, C.byref(args), capi.ptr(self._ws),
+                                      self._ws.numel(), capi.stream_of(hold["hm_h"]))
+        lib.check(st, "vpho_hoi_aggregate")
+        self._hold = hold   # inputs stay alive until the next call (stream-ordered kernels may still read them)
+        if self.debug:
+            dbg["obj_score"] = dbg["obj_score"].reshape(4, bs * omax)
+            self.last_debug = dbg
+        return out

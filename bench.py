@@ -1,0 +1,317 @@
+"""Benchmark of the VPHO evaluation hot path (BASELINE.json metric: hand-object pose candidates scored per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the whole hot path (hand + object ODE sampling with 50 output points, MANO, visual and physical
+scoring, top-30 / top-10 selection, aggregation) over one batch of 64 synthetic DexYCB-shaped images x 100 candidates
+per GPU (BASELINE config 2; with N GPUs this is config 4: 64 images per GPU, sharded by image, weak scaling).
+
+  value  : candidates/s over all ranks, inputs resident in HBM, per-step CUDA events (max over ranks)
+  e2e    : the same through `VphoHotPath.predict` fed from pinned HOST buffers, H2D of every input and D2H of the
+           aggregated results inside the timed region
+  --impl reference : the CPU oracle restatement of the reference (oracle/vpho_oracle.py, validated bit-exact against the
+           reference's own files in the build container) on the box's host cores -- the reference has no compiled code
+           on this path and /root/reference does not travel to the GPU box.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BS, S, STEPS_ODE, T0, K_HAND, K_OBJ = 64, 100, 50, 0.65, 30, 10
+# algorithmic work (restated in DESIGN.md §5)
+FLOP_HEAD_GEMM_HAND = 2 * (256 * 8192 + 8192 * 3)     # per candidate per network call, head GEMM + fused second layer
+FLOP_SCORE_HAND, FLOP_SCORE_OBJ = 4423680, 533504     # whole factored network per candidate per call
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "", 1).isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "", 1).isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_inputs(bs: int, seed: int):
+    from vpho_b200 import synthetic as syn
+    from vpho_b200.score_based_model import ve_prior_std
+    mano = syn.make_mano_model()
+    anchors = syn.make_anchor_assets(mano)
+    objects = syn.make_object_tables()
+    batch = syn.make_eval_batch(bs, seed=seed, sample_num=S, mano=mano, objects=objects)
+    g = torch.Generator().manual_seed(1000 + seed)
+    prior_h = torch.randn(bs * S, 96, generator=g) * ve_prior_std(T0)
+    prior_o = torch.randn(bs * S, 9, generator=g) * ve_prior_std(T0)
+    st_h, st_o = syn.make_denoiser_state("mano_pose", 0), syn.make_denoiser_state("obj", 0)
+    return mano, anchors, objects, batch, prior_h, prior_o, st_h, st_o
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle restatement of the reference)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_oracle(bs: int, seed: int, timing=None):
+    from oracle import vpho_oracle as O
+    mano, anchors, objects, batch, prior_h, prior_o, st_h, st_o = make_inputs(bs, seed)
+    den_h, den_o = O.OracleDenoiser(st_h), O.OracleDenoiser(st_o)
+    om, oo, oa = O.OracleMano(mano), O.OracleObject(objects), O.OracleAnchors(anchors)
+
+    def step():
+        t0 = time.perf_counter()
+        out = O.oracle_predict(batch, den_h, den_o, om, oo, oa, init_x_hand=prior_h, init_x_obj=prior_o, sample_num=S,
+                               sampling_steps=STEPS_ODE, T0=T0, topk_hand=K_HAND, topk_obj=K_OBJ, with_inprocess=True,
+                               timing=timing)
+        return time.perf_counter() - t0, out
+    return step
+
+
+def reference_arm(args, rank: int):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    budget = 150.0
+    probe = run_oracle(8, 0)
+    t_probe, _ = probe()          # includes first-call overheads
+    t_probe, _ = probe()
+    per_img = t_probe / 8
+    total_steps = args.steps + args.warmup
+    bs_ref = int(budget / max(total_steps, 1) / per_img) // 8 * 8
+    bs_ref = max(8, min(BS, bs_ref))
+    step = run_oracle(bs_ref, 0) if bs_ref != 8 else probe
+    for _ in range(args.warmup):
+        step()
+    times = [step()[0] for _ in range(args.steps)]
+    tot = sum(times)
+    value = bs_ref * S * args.steps / tot
+    sample = f"{bs_ref} images x {S} candidates per step (bounded sample of the {BS}-image batch), {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": "hand-object pose candidates scored/sec", "value": round(value, 2),
+        "unit": "candidates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(tot / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": round(value, 2), "unit": "candidates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 2), "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU oracle restatement of the reference's PyTorch/scipy path (bit-exact vs the reference's own files in "
+                "the build container); torch threads = all host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus: int):
+    return {"workload": f"vpho_net eval hot path, batch {BS} images/GPU x sample_num {S} x {STEPS_ODE} ODE output points, "
+                        f"topk_hand {K_HAND} / topk_obj {K_OBJ}, T0 {T0}, random-init weights, synthetic DexYCB-shaped input",
+            "images_per_gpu": BS, "candidates_per_step_per_gpu": BS * S, "sharding": f"by image, {n_gpus} rank(s)",
+            "l2": "no explicit flush: one step streams ~0.6 GB (xs 245 MB, verts 60 MB, heat-maps 50 MB, weights 52 MB, RK "
+                  "state 44 MB) through the 126 MB L2"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------------------------------------
+def cuda_arm(args, rank: int, world: int, local_rank: int):
+    import torch.distributed as dist
+    from vpho_b200 import capi
+    from vpho_b200.vpho import VphoHotPath
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = capi.lib()       # raises when the CUDA library is missing: there is no fallback
+    mano, anchors, objects, batch, prior_h, prior_o, st_h, st_o = make_inputs(BS, seed=rank)
+    hp = VphoHotPath(mano, anchors, objects, st_h, st_o, sample_num=S, sampling_steps=STEPS_ODE, sample_T0=T0,
+                     topk_hand=K_HAND, topk_obj=K_OBJ)
+    batch["obj_id"] = np.asarray(batch["obj_id"], np.int32)
+    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in batch.items() if isinstance(v, np.ndarray)}
+    host["prior_hand"], host["prior_obj"] = prior_h.pin_memory(), prior_o.pin_memory()
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
+    resident = {k: v.to(dev) for k, v in host.items()}
+    out_keys = ("agg_obj_6d", "agg_hand_mano", "agg_hand_vert", "agg_hand_joint")
+    host_out = {}
+
+    def step_resident():
+        return hp.predict(resident, prior_hand=resident["prior_hand"], prior_obj=resident["prior_obj"])
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        pd = hp.predict(d, prior_hand=d["prior_hand"], prior_obj=d["prior_obj"])
+        for k in out_keys:
+            if k not in host_out:
+                host_out[k] = torch.empty(pd[k].shape, dtype=pd[k].dtype).pin_memory()
+            host_out[k].copy_(pd[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return pd
+
+    def metrics_of(pd):
+        # fixed-width per-image record that the final NCCL gather moves (replaces gather_for_metrics,
+        # train_diff_hand_obj.py:333-335): fused wrist-relative joints (63) + fused object pose (9)
+        return torch.cat([pd["agg_hand_joint"].reshape(BS, 63), pd["agg_obj_6d"].float()], dim=1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, profile=False):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        l0 = lib.c.vpho_launch_count()
+        if profile:
+            lib.c.vpho_profile_enable(1)
+        wall0 = time.perf_counter()
+        last = None
+        for i in range(steps):
+            ev[i][0].record()
+            last = step_fn()
+            ev[i][1].record()
+        gathered = None
+        if world > 1:
+            m = metrics_of(last)
+            gathered = torch.empty((world,) + tuple(m.shape), dtype=m.dtype, device=dev)
+            dist.all_gather_into_tensor(gathered, m)
+        barrier()
+        wall = time.perf_counter() - wall0
+        if profile:
+            lib.c.vpho_profile_enable(0)
+        launches = lib.c.vpho_launch_count() - l0
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item(), t[1].item(), launches, last
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_res, wall_res, launches, last = timed(step_resident, args.steps, profile=True)
+    prof = {}
+    for tag, name in ((0, "head_gemm_hand"), (1, "head_gemm_obj"), (2, "pose_encoder"), (3, "mano_skinning"),
+                      (4, "physics3_scan"), (5, "hand_heat_score")):
+        tot, n = C.c_double(0), C.c_int(0)
+        lib.c.vpho_profile_collect(tag, C.byref(tot), C.byref(n))
+        prof[name] = {"ms_total": tot.value, "launches": n.value}
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, wall_e2e, _, _ = timed(step_e2e, args.steps)
+    if rank == 0:
+        clocks.stop_flag.set()
+        clocks.join(timeout=2)
+    info = hp.last_info
+    d2h_bytes = sum(t.numel() * t.element_size() for t in host_out.values())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cand = BS * S * world
+    value = cand * args.steps / (ms_res / 1e3)
+    e2e = cand * args.steps / (ms_e2e / 1e3)
+    peaks = _peaks()
+    hg = prof["head_gemm_hand"]
+    avg_ms = hg["ms_total"] / max(hg["launches"], 1)
+    achieved = BS * S * FLOP_HEAD_GEMM_HAND / (avg_ms * 1e-3) / 1e12 if hg["launches"] else None
+    line = {
+        "metric": "hand-object pose candidates scored/sec", "value": round(value, 1), "unit": "candidates/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_res / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world),
+        "e2e": {"value": round(e2e, 1), "unit": "candidates/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": {"kernel": "k_head_simt (hand score network: pose-feature GEMM K=256 x 8192 hidden, fused bias/ReLU/"
+                               "256->3 heads/sigma division)",
+                     "bound": "tensor", "achieved": round(achieved, 2) if achieved else None, "peak": peaks["bf16_tflops"],
+                     "unit": "TFLOP/s", "frac": round(achieved / peaks["bf16_tflops"], 4) if achieved else None,
+                     "traffic": None, "peak_source": peaks["source"] + " (cuBLAS bf16 burst)",
+                     "launches_timed": hg["launches"], "avg_launch_ms": round(avg_ms, 4),
+                     "flop_per_launch": BS * S * FLOP_HEAD_GEMM_HAND,
+                     "share_of_step": round(hg["ms_total"] / ms_res, 4)},
+        "kernel_ms_per_step": {k: round(v["ms_total"] / args.steps, 4) for k, v in prof.items()},
+        "sampler": {"hand_net_calls": info["hand"]["net_calls"], "obj_net_calls": info["obj"]["net_calls"],
+                    "hand_attempts": info["hand"]["attempts"], "rejected": info["hand"]["rejected"] + info["obj"]["rejected"]},
+        "wall_ms_per_step": round(wall_res / args.steps, 4),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        tm = {}
+        step = run_oracle(BS, 0, timing=tm)
+        t, out = step()
+        line["cpu_baseline"] = {"value": round(BS * S / t, 2), "unit": "candidates/s", "cores": torch.get_num_threads(),
+                                "kind": "port", "sample": f"one full step ({BS} images x {S} candidates), single cold run, "
+                                f"{t:.1f} s", "split_s": {k: round(v, 2) for k, v in tm.items()},
+                                "net_calls": out["_info"]["hand"]["net_calls"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    cuda_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,14 @@ typedef void* vpho_assets_t;    /* force-anchor tables + object point tables  */
 
 int vpho_version(void);
 
+/* Bookkeeping for benchmarks: number of kernels this library has launched since it was loaded, and optional CUDA-event
+ * brackets around tagged kernels (recorded on the launching stream).  vpho_profile_collect synchronises on the recorded
+ * events of `tag`, returns their summed duration and count, and clears them.
+ * tags: 0 hand head-GEMM, 1 object head-GEMM, 2 pose encoder, 3 MANO skinning, 4 physics3 scan, 5 hand heat-map scorer */
+unsigned long long vpho_launch_count(void);
+int vpho_profile_enable(int on);
+int vpho_profile_collect(int tag, double* total_ms, int* n_launches);
+
 /* ------------------------------------------------------------------------------------------------ MANO ---- */
 /* Packs the MANO tensors (HOST pointers, float32, manopth layouts: v_template [778][3], shapedirs [778][3][10],
  * posedirs [778][3][135], J_regressor [16][778], weights [778][16]) into the device layout.
@@ -135,8 +143,9 @@ typedef struct {
   float* dbg_hand_score;         /* [4][bs][2S][5]  (level 0 uses [..][0]) */
   int32_t* dbg_hand_topk;        /* [4][bs][5][topk_hand] */
   float* dbg_cascade_pose;       /* [bs][48] fused pose after the cascade */
-  float* dbg_obj_score;          /* [4][bs][max(S,topk_obj^2)]: transl heat, rot heat, physics3, final heat */
-  int32_t* dbg_obj_topk;         /* [4][bs][topk_obj] */
+  float* dbg_obj_score;          /* [4][bs*max(S,topk_obj^2)]: transl heat, rot heat (each [bs][S]), physics3, final heat
+                                    (each [bs][topk_obj^2]), packed at the start of their block */
+  int32_t* dbg_obj_topk;         /* [4][bs][max(topk_obj,phy_topk)] */
   float* dbg_finger_score;       /* [bs][5][topk_hand+1] */
   int32_t* dbg_finger_topk;      /* [bs][5][phy_topk] */
   float* dbg_force_point;        /* [bs][32][3] */

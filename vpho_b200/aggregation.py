@@ -141,7 +141,7 @@ class HOI_Aggregator:
         if self.debug:
             z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=dev)   # noqa: E731
             dbg = dict(hand_score=z(4, bs, 2 * S, 5), hand_topk=z(4, bs, 5, Kh, dt=torch.int32), cascade_pose=z(bs, 48),
-                       obj_score=z(4, bs * omax), obj_topk=z(4, bs, Ko, dt=torch.int32), finger_score=z(bs, 5, nc),
+                       obj_score=z(4, bs * omax), obj_topk=z(4, bs, max(Ko, PHY_TOPK), dt=torch.int32), finger_score=z(bs, 5, nc),
                        finger_topk=z(bs, 5, PHY_TOPK, dt=torch.int32), force_point=z(bs, 32, 3), force_global=z(bs, 32, 3))
         nbytes = int(lib.c.vpho_hoi_workspace_bytes(bs, S, Kh, Ko, a.n_pts))
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:

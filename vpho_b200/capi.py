@@ -36,6 +36,9 @@ class HoiArgs(C.Structure):
 
 _SIGNATURES = {
     "vpho_version": (c_int, []),
+    "vpho_launch_count": (C.c_ulonglong, []),
+    "vpho_profile_enable": (c_int, [c_int]),
+    "vpho_profile_collect": (c_int, [c_int, C.POINTER(c_double), C.POINTER(c_int)]),
     "vpho_mano_create": (c_int, [c_void_p] * 5 + [C.POINTER(c_void_p)]),
     "vpho_mano_destroy": (c_int, [c_void_p]),
     "vpho_mano_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
@@ -97,7 +100,7 @@ def lib() -> Library:
     if _default is None:
         if not torch.cuda.is_available():
             raise VphoError("vpho_b200 needs a CUDA device (built for sm_100a); there is no CPU implementation")
-        _default = Library(LIB_PATH, strict=False)  # TODO(strict) once every entry point is built
+        _default = Library(LIB_PATH)
     return _default
 
 

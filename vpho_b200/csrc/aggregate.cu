@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(32) k_obj_transl_fuse(HoiDev h) {
   const float* sc = h.oscore + (size_t)b * S;
   warp_topk<EL>(S, K, [&](int i) { return sc[i]; }, s_val, s_idx, lane);
   for (int r = lane; r < K; r += 32) h.t_topk[b * K + r] = s_idx[r];
-  if (h.a.dbg_obj_topk) for (int r = lane; r < K; r += 32) h.a.dbg_obj_topk[((size_t)0 * h.a.bs + b) * K + r] = s_idx[r];
+  if (h.a.dbg_obj_topk) for (int r = lane; r < K; r += 32) h.a.dbg_obj_topk[((size_t)0 * h.a.bs + b) * max(K, h.a.phy_topk) + r] = s_idx[r];
   if (lane < 3) {
     float vsum = 0.f;
     for (int r = 0; r < K; ++r) vsum += s_val[r];
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(32) k_obj_recombine(HoiDev h) {
   const int S = h.a.S, K = h.a.topk_obj;
   const float* sc = h.oscore + (size_t)b * S;
   warp_topk<EL>(S, K, [&](int i) { return sc[i]; }, s_val, s_idx, lane);
-  if (h.a.dbg_obj_topk) for (int r = lane; r < K; r += 32) h.a.dbg_obj_topk[((size_t)1 * h.a.bs + b) * K + r] = s_idx[r];
+  if (h.a.dbg_obj_topk) for (int r = lane; r < K; r += 32) h.a.dbg_obj_topk[((size_t)1 * h.a.bs + b) * max(K, h.a.phy_topk) + r] = s_idx[r];
   for (int it = lane; it < K * K * 9; it += 32) {
     const int cidx = it / 9, e = it % 9, i = cidx / K, j = cidx % K;
     const int src = (e < 6) ? s_idx[j] : h.t_topk[b * K + i];
@@ -441,8 +441,8 @@ __global__ void __launch_bounds__(256) k_obj_final(AssetsDev as, HoiDev h) {
   if (warp == 1) warp_topk<EL>(kk, K5, [&](int i) { return h.oscore[(size_t)b * kk + i]; }, q_val, q_idx, lane);
   __syncthreads();
   if (h.a.dbg_obj_topk && tid < K5) {
-    h.a.dbg_obj_topk[((size_t)2 * h.a.bs + b) * h.a.topk_obj + tid] = p_idx[tid];
-    h.a.dbg_obj_topk[((size_t)3 * h.a.bs + b) * h.a.topk_obj + tid] = q_idx[tid];
+    h.a.dbg_obj_topk[((size_t)2 * h.a.bs + b) * max(h.a.topk_obj, K5) + tid] = p_idx[tid];
+    h.a.dbg_obj_topk[((size_t)3 * h.a.bs + b) * max(h.a.topk_obj, K5) + tid] = q_idx[tid];
   }
   if (tid == 0) {
     const bool grasped = h.a.is_grasped[b] != 0;
@@ -685,7 +685,9 @@ static int run_hoi(const ManoModelDev& m, const AssetsDev& as, const HoiDev& h, 
   // ---- hand heat-map cascade (aggregation.py:115-178)
   for (int level = 0; level < 4; ++level) {
     const int ncand = level == 0 ? 2 * S : S + 1;
+    profile_begin(VPHO_TAG_HAND_SCORE, st);
     VPHO_LAUNCH(k_hand_level_score<TC>, dim3((ncand + TC - 1) / TC, bs), dim3(128), smem, st, m, h, level);
+    profile_end(VPHO_TAG_HAND_SCORE, st);
     VPHO_LAUNCH(k_hand_level_fuse<EL>, dim3(bs), dim3(160), 0, st, h, level);
   }
   VPHO_CHECK_LAUNCH();
@@ -706,7 +708,9 @@ static int run_hoi(const ManoModelDev& m, const AssetsDev& as, const HoiDev& h, 
   if (a.dbg_obj_score) VPHO_LAUNCH(k_copy_f32, dim3((bs * S + 255) / 256), dim3(256), 0, st, h.oscore, a.dbg_obj_score + (size_t)1 * bs * omax, bs * S);
   VPHO_LAUNCH(k_obj_recombine<EL>, dim3(bs), dim3(32), 0, st, h);
   // ---- object: physics / heat-map selection of the recombined candidates, fusion (aggregation.py:1247-1287)
+  profile_begin(VPHO_TAG_PHYSICS3, st);
   VPHO_LAUNCH(k_obj_physics3, dim3(h.kk, bs), dim3(kScanThreads), 0, st, as, h);
+  profile_end(VPHO_TAG_PHYSICS3, st);
   VPHO_LAUNCH(k_obj_heat_score, dim3((h.kk + 7) / 8, bs), dim3(256), 0, st, as, h, (const double*)a.pose6d_candidate, (const double*)nullptr, h.kk, h.oscore);
   if (a.dbg_obj_score) {
     VPHO_LAUNCH(k_copy_f32, dim3((bs * h.kk + 255) / 256), dim3(256), 0, st, h.pscore, a.dbg_obj_score + (size_t)2 * bs * omax, bs * h.kk);
@@ -807,7 +811,7 @@ extern "C" int vpho_hoi_aggregate(vpho_mano_t mano, vpho_assets_t assets, const 
   const int nc = a.topk_hand + 1, kk = a.topk_obj * a.topk_obj;
   if (a.topk_hand < 1 || a.topk_hand > 64 || a.topk_hand > 2 * a.S) return VPHO_ERR_INVALID;
   if (a.topk_obj < 1 || a.topk_obj > 16 || a.topk_obj > a.S) return VPHO_ERR_INVALID;
-  if (a.phy_topk < 1 || a.phy_topk > 64 || a.phy_topk > nc || a.phy_topk > kk || a.phy_topk > a.topk_obj) return VPHO_ERR_INVALID;
+  if (a.phy_topk < 1 || a.phy_topk > 64 || a.phy_topk > nc || a.phy_topk > kk) return VPHO_ERR_INVALID;
   if (!a.cam_intrinsic || !a.root_joint_flip || !a.root_joint || !a.is_right || !a.is_grasped || !a.force_local ||
       !a.hand_pose_diff || !a.hand_pose_reg || !a.hand_shape || !a.hand_heatmap || !a.hand_bbox || !a.obj_pose6d ||
       !a.obj_heatmap || !a.obj_bbox || !a.obj_id || !a.obj_agg_6d || !a.pose6d_candidate || !a.agg_obj_vert ||

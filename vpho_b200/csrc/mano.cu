@@ -116,8 +116,10 @@ static int launch_mano_forward(const ManoModelDev& m, const float* pose, const f
     attr_set = true;
   }
 #endif
+  profile_begin(VPHO_TAG_MANO_FULL, stream);
   VPHO_LAUNCH(mano_forward_kernel<TC>, grid, dim3(kVChunkPad), smem, stream, m, pose, shape, pose_stride, shape_stride, n, verts,
               joints);
+  profile_end(VPHO_TAG_MANO_FULL, stream);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }

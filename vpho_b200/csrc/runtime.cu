@@ -1,0 +1,62 @@
+// Library-wide bookkeeping: launch counter and optional CUDA-event brackets around tagged kernels (bench.py uses them
+// to time the dominant kernel live, on the launching stream, inside its timed region).
+#include "vpho_common.cuh"
+#include "vpho_b200.h"
+
+#include <utility>
+#include <vector>
+
+namespace vpho {
+
+unsigned long long g_launches = 0;
+static bool g_profile = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events[VPHO_NUM_TAGS];
+static cudaEvent_t g_open[VPHO_NUM_TAGS];
+
+void profile_begin(int tag, cudaStream_t st) {
+  if (!g_profile) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, st);
+  g_open[tag] = e;
+}
+
+void profile_end(int tag, cudaStream_t st) {
+  if (!g_profile) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, st);
+  g_events[tag].push_back({g_open[tag], e});
+}
+
+}  // namespace vpho
+
+using namespace vpho;
+
+extern "C" int vpho_version(void) { return 100; }
+
+extern "C" unsigned long long vpho_launch_count(void) { return g_launches; }
+
+extern "C" int vpho_profile_enable(int on) {
+  g_profile = on != 0;
+  return VPHO_OK;
+}
+
+extern "C" int vpho_profile_collect(int tag, double* total_ms, int* n_launches) {
+  if (tag < 0 || tag >= VPHO_NUM_TAGS || !total_ms || !n_launches) return VPHO_ERR_INVALID;
+  double tot = 0.0;
+  int n = 0;
+  for (auto& pr : g_events[tag]) {
+    if (cudaEventSynchronize(pr.second) != cudaSuccess) return VPHO_ERR_LAUNCH;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, pr.first, pr.second);
+    tot += ms;
+    ++n;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  g_events[tag].clear();
+  *total_ms = tot;
+  *n_launches = n;
+  return VPHO_OK;
+}

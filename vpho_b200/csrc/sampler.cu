@@ -687,8 +687,13 @@ static int red_blocks(int n) { int b = (n + 255) / 256; return b < 1 ? 1 : (b > 
 
 static int launch_eval(const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, cudaStream_t st) {
   VPHO_LAUNCH(k_time_term, dim3((dn.hid + 255) / 256), dim3(256), 0, st, dn, ws, mode, s);
+  profile_begin(VPHO_TAG_POSE_ENCODER, st);
   VPHO_LAUNCH(k_pose_encoder, dim3(ws.Npad / kPeRows), dim3(256), 0, st, dn, ws, mode, s);
+  profile_end(VPHO_TAG_POSE_ENCODER, st);
+  const int tag = dn.n_heads >= 16 ? VPHO_TAG_HEAD_GEMM_HAND : VPHO_TAG_HEAD_GEMM_OBJ;
+  profile_begin(tag, st);
   VPHO_LAUNCH(k_head_simt, dim3(ws.Npad / kRowTile, dn.n_heads), dim3(256), 0, st, dn, ws, mode, s);
+  profile_end(tag, st);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }
@@ -710,8 +715,6 @@ static int launch_attempts(const DenoiserDev& dn, const SamplerWs& ws, int n, in
 }  // namespace vpho
 
 using namespace vpho;
-
-extern "C" int vpho_version(void) { return 100; }
 
 extern "C" int vpho_denoiser_create(int n_heads, const float* fourier_W, const float* t_w, const float* t_b,
                                     const float* p1_w, const float* p1_b, const float* p2_w, const float* p2_b,

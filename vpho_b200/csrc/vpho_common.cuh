@@ -10,7 +10,13 @@
 #define VPHO_DYN_SMEM(type, name)                                 \
   extern __shared__ __align__(16) unsigned char name##_raw_[];    \
   type* name = reinterpret_cast<type*>(name##_raw_)
-#define VPHO_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+namespace vpho {
+extern unsigned long long g_launches;   // kernels launched by this library since load (vpho_launch_count)
+void profile_begin(int tag, cudaStream_t st);   // CUDA-event bracket around one launch when profiling is enabled
+void profile_end(int tag, cudaStream_t st);
+}  // namespace vpho
+#define VPHO_LAUNCH(kern, grid, block, smem, stream, ...) \
+  do { ++::vpho::g_launches; kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); } while (0)
 #define VPHO_CONSTANT __constant__
 namespace vpho {
 // 16-byte asynchronous global->shared copy (LDGSTS) and its group fences
@@ -24,12 +30,23 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #else
 #define VPHO_CONSTANT static
 namespace vpho {
+inline void profile_begin(int, cudaStream_t) {}
+inline void profile_end(int, cudaStream_t) {}
 inline void cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
 inline void cp_async_commit() {}
 template <int N>
 inline void cp_async_wait() {}
 }  // namespace vpho
 #endif
+
+// profiling tags (vpho_profile_collect)
+#define VPHO_TAG_HEAD_GEMM_HAND 0
+#define VPHO_TAG_HEAD_GEMM_OBJ 1
+#define VPHO_TAG_POSE_ENCODER 2
+#define VPHO_TAG_MANO_FULL 3
+#define VPHO_TAG_PHYSICS3 4
+#define VPHO_TAG_HAND_SCORE 5
+#define VPHO_NUM_TAGS 6
 
 #define VPHO_OK 0
 #define VPHO_ERR_INVALID (-1)

@@ -120,12 +120,14 @@ class ScoreBasedModelAgent:
 
     @torch.no_grad()
     def sample(self, data: dict, denoiser: Denoiser, T0: float, init_x: Optional[torch.Tensor] = None,
-               return_inprocess: bool = True):
+               return_inprocess: bool = True, prior: Optional[torch.Tensor] = None):
         """-> (in_process (N, steps, D) float64 [permuted view, as the reference returns it], final (N, D) float64)."""
         device = (data["feat_unique"] if "feat_unique" in data else data["feat"]).device
         D = denoiser.out_dim
         n_rows = int(data["n_rows"]) if "n_rows" in data else int(data["feat"].shape[0])
-        prior = self.prior_fn((n_rows, D), T0).to(device)
+        # `prior` (optional): the prior draw randn*sigma(T0) supplied by the caller ("sampler noise fed from the same
+        # seeded tensor"); otherwise drawn from torch's global CPU generator exactly as the reference does.
+        prior = self.prior_fn((n_rows, D), T0).to(device) if prior is None else prior.to(device)
         x0 = prior if init_x is None else init_x.to(device) + prior      # score_based_model.py:62
         x0 = x0.contiguous().float()
         d2 = dict(data)

@@ -1,0 +1,128 @@
+"""Evaluation hot path of `vpho_net.forward(data, mode='predict')` (lib/model/VPHO.py:228-304) on the CUDA kernels.
+
+`VphoHotPath.predict` takes what the reference's feature extractor produces per image (VPHO.py:112-173: encodings,
+heat-maps, regressed MANO, local forces) plus the dataset fields the hot path reads (dexycb6.py:471-509) and returns
+the same `pd_dt` keys with the same shapes/dtypes.  All arithmetic is in `libvpho_b200.so`; there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import capi
+from .aggregation import Assets, HeadObject, HeadPhysics, HOI_Aggregator
+from .head_mano import HeadMano
+from .score_based_model import Denoiser, ScoreBasedModelAgent
+
+_TENSOR_KEYS = ("encoding_hand", "encoding_obj", "pd_mano_pose", "pd_mano_shape", "hm_hand", "hm_obj", "force_local",
+                "cam_intr_crop_flip", "root_joint_flip", "root_joint", "is_right", "is_grasped", "bbox_hand",
+                "bbox_obj_rect")
+
+
+class VphoHotPath:
+    def __init__(self, mano_model: Dict, anchors: Dict, objects: Dict, denoiser_hand_state: Dict,
+                 denoiser_obj_state: Dict, *, sample_num: int = 100, sampling_steps: int = 50, sample_T0: float = 0.65,
+                 topk_hand: int = 30, topk_obj: int = 10, lib: Optional[capi.Library] = None, debug: bool = False):
+        self.lib = lib or capi.lib()
+        self.sample_num, self.sampling_steps, self.sample_T0 = sample_num, sampling_steps, sample_T0
+        self.topk_hand, self.topk_obj = topk_hand, topk_obj
+        self.head_mano = HeadMano(mano_model, lib=self.lib)
+        self.assets = Assets(anchors, objects, lib=self.lib)
+        self.head_obj = HeadObject(self.assets)
+        self.head_physics = HeadPhysics(self.assets)
+        self.denoiser_hand = Denoiser(denoiser_hand_state, lib=self.lib)
+        self.denoiser_obj = Denoiser(denoiser_obj_state, lib=self.lib)
+        self.score_agent = ScoreBasedModelAgent(sampling_steps=sampling_steps, sample_num=sample_num)
+        self.hoi_aggregator = HOI_Aggregator(self.head_mano, self.assets, debug=debug)
+        self.last_info: dict = {}
+
+    # ---- vpho_net.postprocess_diffusion_hand, branch 'mano_pose' (VPHO.py:306-331) ----
+    def postprocess_diffusion_hand(self, hand_inprocess, hand_final, pd_mano_shape):
+        S = self.sample_num
+        bs = pd_mano_shape.shape[0]
+        dev = hand_final.device
+
+        def to_aa(x6d):
+            x6d = x6d.contiguous().float()
+            n_rot = x6d.numel() // 6
+            aa = torch.empty((n_rot, 3), dtype=torch.float32, device=dev)
+            self.lib.check(self.lib.c.vpho_rot6d_to_axis_angle(capi.ptr(x6d), n_rot, capi.ptr(aa), capi.stream_of(x6d)),
+                           "vpho_rot6d_to_axis_angle")
+            return aa
+
+        hf = to_aa(hand_final).reshape(bs, S, 48)
+        hf = torch.cat((hf, pd_mano_shape[:, None].expand(bs, S, 10)), dim=-1).reshape(-1, 58)
+        hi = None
+        if hand_inprocess is not None:
+            n_in = hand_inprocess.shape[1]
+            # the sampler stores [steps][N][D]; rotations are independent, so convert in storage order and permute after
+            native = hand_inprocess.permute(1, 0, 2)
+            hi = to_aa(native).reshape(n_in, bs, S, 48).permute(1, 2, 0, 3)
+            hi = torch.cat((hi, pd_mano_shape[:, None, None].expand(bs, S, n_in, 10)), dim=-1).reshape(-1, n_in, 58)
+        return hi, hf
+
+    @torch.no_grad()
+    def predict(self, batch: Dict, *, prior_hand: Optional[torch.Tensor] = None, prior_obj: Optional[torch.Tensor] = None,
+                with_inprocess: bool = True) -> Dict:
+        """batch: tensors on the CUDA device (see `to_device`).  prior_* (optional): randn*sigma(T0) draws, (bs*S, 96) and
+        (bs*S, 9); when omitted they are drawn from torch's global CPU generator in the reference's order (hand, object)."""
+        S = self.sample_num
+        enc_h, enc_o = batch["encoding_hand"], batch["encoding_obj"]
+        bs = enc_h.shape[0]
+        pd_mano_pose, pd_mano_shape = batch["pd_mano_pose"], batch["pd_mano_shape"]
+        pd = {"hand_heatmap": batch["hm_hand"], "obj_heatmap": batch["hm_obj"], "force_local": batch["force_local"]}
+
+        xs_h, x_h = self.score_agent.sample({"feat_unique": enc_h, "n_rows": bs * S}, self.denoiser_hand, self.sample_T0,
+                                            return_inprocess=with_inprocess, prior=prior_hand)
+        info_h = dict(self.score_agent.last_info)
+        inproc, final_mano = self.postprocess_diffusion_hand(xs_h, x_h, pd_mano_shape)
+        pd["diff_final_hand_mano"] = final_mano.reshape(bs, S, 58)
+        if with_inprocess:
+            pd["diff_inprocess_hand_mano"] = inproc.reshape(bs, S, -1, 58)
+            # VPHO.py:250: every 10th output point of the first candidate of the first image (visualisation)
+            iv, ij = self.head_mano.get_hand_verts(pose=inproc[0, ::10, :48], shape=inproc[0, ::10, 48:])
+            pd["diff_inprocess_hand_vert"], pd["diff_inprocess_hand_joint"] = iv.reshape(-1, 778, 3), ij.reshape(-1, 21, 3)
+        fv, fj = self.head_mano.get_hand_verts(pose=final_mano[:, :48], shape=final_mano[:, 48:])
+        pd["diff_final_hand_vert"] = fv.reshape(bs, S, 778, 3)
+        pd["diff_final_hand_joint"] = fj.reshape(bs, S, 21, 3)
+
+        xs_o, x_o = self.score_agent.sample({"feat_unique": enc_o, "n_rows": bs * S}, self.denoiser_obj, self.sample_T0,
+                                            return_inprocess=with_inprocess, prior=prior_obj)
+        info_o = dict(self.score_agent.last_info)
+        if with_inprocess:
+            pd["diff_inprocess_obj_6d"] = xs_o.reshape(bs, S, -1, 9)
+        pd["diff_final_obj_6d"] = x_o.reshape(bs, S, 9)
+
+        sel = self.hoi_aggregator(
+            cam_intrinsic=batch["cam_intr_crop_flip"], root_joint_flip=batch["root_joint_flip"],
+            root_joint=batch["root_joint"], is_right=batch["is_right"], force_local=batch["force_local"],
+            is_grasped=batch["is_grasped"], hand_pose_diff=final_mano[:, :48], hand_pose_regression=pd_mano_pose,
+            hand_shape=final_mano[:, 48:], hand_heatmap=batch["hm_hand"], hand_bbox=batch["bbox_hand"],
+            hand_topk=self.topk_hand, obj_pose6d=pd["diff_final_obj_6d"], obj_heatmap=batch["hm_obj"],
+            obj_bbox=batch["bbox_obj_rect"], obj_topk=self.topk_obj,
+            obj_name=batch["obj_id"] if "obj_id" in batch else batch["obj_name"])
+        pd["agg_obj_6d"] = sel["obj_agg_6d"]
+        pd["agg_hand_mano"] = sel["hand_agg_mano"]
+        pd["agg_hand_vert"] = sel["hand_agg_vert"]
+        pd["agg_hand_joint"] = sel["hand_agg_joint"]
+        pd["_sel"] = sel
+        self.last_info = {"hand": info_h, "obj": info_o}
+        return pd
+
+    __call__ = predict
+
+
+def to_device(batch: Dict, device="cuda", non_blocking: bool = True) -> Dict:
+    """Host dict (numpy arrays / tensors) -> tensors on `device`; `obj_name` becomes an int32 id tensor when `obj_id`
+    is present.  Mirrors the `to_device(batch)` step of Trainer.evaluate (train_diff_hand_obj.py:214)."""
+    import numpy as np
+    out = {}
+    for k, v in batch.items():
+        if isinstance(v, np.ndarray):
+            v = torch.from_numpy(v)
+        if isinstance(v, torch.Tensor):
+            out[k] = v.to(device, non_blocking=non_blocking)
+        else:
+            out[k] = v
+    return out

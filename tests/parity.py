@@ -1,0 +1,85 @@
+"""Shared parity helpers for the aggregation / end-to-end tests.
+
+Top-k rule (SURVEY.md §8c ii/iii): indices are compared bit-exactly under the canonical tie-break (value desc, index
+asc).  FP32 scores computed in a different summation order can differ from the oracle's in the last bits; a position
+where the two selections differ is accepted only as a NEAR-TIE: the oracle's own scores of the two candidates involved
+differ by less than `rtol` (relative to the score scale).  Near-ties are counted and reported; anything else fails."""
+from __future__ import annotations
+
+import torch
+
+NEAR_TIE_RTOL = 2e-5
+
+
+def topk_agreement(ours_idx: torch.Tensor, oracle_idx: torch.Tensor, oracle_scores: torch.Tensor, rtol=NEAR_TIE_RTOL):
+    """ours_idx / oracle_idx (..., K) over the candidate axis of oracle_scores (..., C).  Returns (exact, near_tie, bad)
+    counted per list."""
+    K = oracle_idx.shape[-1]
+    oi = ours_idx.reshape(-1, K).long()
+    ri = oracle_idx.reshape(-1, K).long()
+    sc = oracle_scores.reshape(-1, oracle_scores.shape[-1]).double()
+    exact = near = bad = 0
+    for r in range(oi.shape[0]):
+        if torch.equal(oi[r], ri[r]):
+            exact += 1
+            continue
+        scale = sc[r].abs().max().clamp(min=1e-30)
+        diff = (sc[r][oi[r]] - sc[r][ri[r]]).abs() / scale
+        if bool((diff <= rtol).all()):
+            near += 1
+        else:
+            bad += 1
+    return exact, near, bad
+
+
+def hand_level_lists(level_dbg_topk: torch.Tensor, oracle_level: dict, level: int):
+    """(ours (bs, nf, K), oracle (bs, nf, K), oracle scores (bs, nf, 2S)) for one cascade level."""
+    sc, tk = oracle_level["score"], oracle_level["topk"]
+    if sc.dim() == 2:
+        sc, tk = sc[..., None], tk[..., None]
+    nf = sc.shape[-1]
+    return level_dbg_topk[:, :nf].cpu(), tk.permute(0, 2, 1), sc.permute(0, 2, 1)
+
+
+def check_hoi_against_oracle(out: dict, dbg: dict, oracle: dict, *, pos_tol=2e-6, pose_tol=2e-5, obj_tol=1e-6,
+                             cand_tol=0.0):
+    """Stage-wise comparison of one HOI_Aggregator call with the oracle's hoi_aggregate.  Returns a report dict; raises
+    AssertionError on a selection that is not a near-tie, or (for images with only exact selections) on values."""
+    od = oracle["_dbg"]
+    bs = oracle["obj_agg_6d"].shape[0]
+    rep = {"lists": 0, "exact": 0, "near_tie": 0}
+    clean = torch.ones(bs, dtype=torch.bool)      # images whose every selection matched exactly
+
+    def account(ours, ref_idx, ref_sc, name):
+        nl = ours.reshape(-1, ours.shape[-1]).shape[0]
+        per_img = nl // bs
+        for b in range(bs):
+            e, n, bad = topk_agreement(ours.reshape(bs, per_img, -1)[b], ref_idx.reshape(bs, per_img, -1)[b],
+                                       ref_sc.reshape(bs, per_img, -1)[b])
+            assert bad == 0, f"{name}: image {b} selected candidates whose oracle scores are not within the near-tie band"
+            rep["lists"] += e + n
+            rep["exact"] += e
+            rep["near_tie"] += n
+            if n:
+                clean[b] = False
+
+    for lv in range(4):
+        ours, ref_idx, ref_sc = hand_level_lists(dbg["hand_topk"][lv], od["cascade"]["levels"][lv], lv)
+        account(ours, ref_idx, ref_sc, f"hand cascade level {lv}")
+    for i, (nm, snm) in enumerate([("obj_transl_topk", "obj_transl_score"), ("obj_rot_topk", "obj_rot_score"),
+                                   ("phys_topk", "phys_score"), ("heat5_topk", "heat5_score")]):
+        k = od[nm].shape[1]
+        account(dbg["obj_topk"][i, :, :k].cpu()[:, None], od[nm][:, None], od[snm][:, None], nm)
+    account(dbg["finger_topk"].cpu(), od["finger_topk"], od["finger_score"], "hand physics finger top-k")
+    rep["clean_images"] = int(clean.sum())
+    # values, on the images where every selection matched exactly
+    if clean.any():
+        c = clean
+        # recombined candidates are pure gathers of the inputs: bit-identical when the inputs are (cand_tol = 0)
+        assert (out["pose6d_candidate"].cpu()[c] - oracle["pose6d_candidate"][c]).abs().max().item() <= cand_tol
+        for k, tol in (("hand_agg_vert", pos_tol), ("hand_agg_joint", pos_tol), ("agg_obj_vert", pos_tol),
+                       ("hand_agg_mano", pose_tol), ("obj_agg_6d", obj_tol)):
+            err = (out[k].cpu().double()[c] - oracle[k].double()[c]).abs().max().item()
+            rep["err_" + k] = err
+            assert err <= tol, (k, err, tol)
+    return rep

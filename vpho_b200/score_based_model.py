@@ -162,7 +162,7 @@ class ScoreBasedModelAgent:
             raise capi.VphoError("RK45: required step size is less than spacing between numbers")
         if c[4]:
             print("\033[31mWarning: NaN detected in score evaluation. \033[0m")   # score_based_model.py:70
-        self.first_attempts = max(self.first_attempts, c[5])
+        self.first_attempts = max(1, c[5])   # steady state: enqueue exactly what the last batch needed
         if xs is None:
             return None, x
         return xs.permute(1, 0, 2), x

@@ -57,3 +57,19 @@ def fingerprint(*tensors) -> float:
         w = np.cos(np.arange(a.size, dtype=np.float64) * 0.37)
         acc += float((a * w).sum())
     return acc
+
+
+def e2e_priors(kind: str, bs: int, S: int, batch: dict, seed: int):
+    """Prior tensors for the end-to-end tests: 'random' = N(0, sigma(T0)^2) as in the README run; 'clustered' = tight
+    clusters of valid 6D poses around a hidden pose (what a trained sampler converges to)."""
+    from pytorch3d.transforms.rotation_conversions import axis_angle_to_matrix, matrix_to_rotation_6d   # oracle/shims
+    g = torch.Generator().manual_seed(seed)
+    if kind == "random":
+        return torch.randn(bs * S, 96, generator=g) * SIGMA_T0, torch.randn(bs * S, 9, generator=g) * SIGMA_T0
+    T = lambda k: torch.from_numpy(np.asarray(batch[k]))  # noqa: E731
+    true_pose = torch.cat([T("true_wrist"), torch.randn(bs, 45, generator=g) * 0.2], 1)
+    aa = (true_pose[:, None] + torch.randn(bs, S, 48, generator=g) * 0.2).reshape(bs * S, 16, 3)
+    ph = matrix_to_rotation_6d(axis_angle_to_matrix(aa)).reshape(bs * S, 96) * (1 + 0.05 * torch.randn(bs * S, 1, generator=g))
+    rot = T("true_obj_rot")[:, None, :2, :].reshape(bs, 1, 6) + 0.1 * torch.randn(bs, S, 6, generator=g)
+    tr = T("true_obj_trans")[:, None] + 0.02 * torch.randn(bs, S, 3, generator=g)
+    return ph.float().contiguous(), torch.cat([rot, tr], -1).reshape(bs * S, 9).float().contiguous()

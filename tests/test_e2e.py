@@ -23,29 +23,11 @@ from vpho_b200.score_based_model import ve_prior_std
 from vpho_b200.vpho import VphoHotPath, to_device
 
 
-def _rot6d_of_axis_angle(aa):
-    from pytorch3d.transforms.rotation_conversions import axis_angle_to_matrix, matrix_to_rotation_6d
-    return matrix_to_rotation_6d(axis_angle_to_matrix(aa))
-
-
-def _priors(kind, bs, S, batch, seed):
-    g = torch.Generator().manual_seed(seed)
-    if kind == "random":
-        return (torch.randn(bs * S, 96, generator=g) * ve_prior_std(0.65), torch.randn(bs * S, 9, generator=g) * ve_prior_std(0.65))
-    T = lambda k: torch.from_numpy(np.asarray(batch[k]))  # noqa: E731
-    true_pose = torch.cat([T("true_wrist"), torch.randn(bs, 45, generator=g) * 0.2], 1)
-    aa = (true_pose[:, None] + torch.randn(bs, S, 48, generator=g) * 0.2).reshape(bs * S, 16, 3)
-    ph = _rot6d_of_axis_angle(aa).reshape(bs * S, 96) * (1 + 0.05 * torch.randn(bs * S, 1, generator=g))
-    rot = T("true_obj_rot")[:, None, :2, :].reshape(bs, 1, 6) + 0.1 * torch.randn(bs, S, 6, generator=g)
-    tr = T("true_obj_trans")[:, None] + 0.02 * torch.randn(bs, S, 3, generator=g)
-    return ph.float().contiguous(), torch.cat([rot, tr], -1).reshape(bs * S, 9).float().contiguous()
-
-
 def _run(lib, dev, kind, bs, S, Kh, Ko, steps, seed):
     mano, anch, objs = cases.assets()
     batch = syn.make_eval_batch(bs, seed=seed, sample_num=S, mano=mano, objects=objs)
     st_h, st_o = syn.make_denoiser_state("mano_pose", 0), syn.make_denoiser_state("obj", 0)
-    ph, po = _priors(kind, bs, S, batch, seed)
+    ph, po = cases.e2e_priors(kind, bs, S, batch, seed)
     hp = VphoHotPath(mano, anch, objs, st_h, st_o, sample_num=S, sampling_steps=steps, topk_hand=Kh, topk_obj=Ko, lib=lib,
                      debug=True)
     pd = hp.predict(to_device(batch, dev), prior_hand=ph, prior_obj=po)

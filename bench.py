@@ -157,6 +157,7 @@ def workload_config(n_gpus: int):
 def cuda_arm(args, rank: int, world: int, local_rank: int):
     import torch.distributed as dist
     from vpho_b200 import capi
+    from vpho_b200.distributed import gather_records, image_record
     from vpho_b200.vpho import VphoHotPath
 
     torch.cuda.set_device(local_rank)
@@ -191,7 +192,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     def metrics_of(pd):
         # fixed-width per-image record that the final NCCL gather moves (replaces gather_for_metrics,
         # train_diff_hand_obj.py:333-335): fused wrist-relative joints (63) + fused object pose (9)
-        return torch.cat([pd["agg_hand_joint"].reshape(BS, 63), pd["agg_obj_6d"].float()], dim=1)
+        return image_record(pd["agg_hand_joint"], pd["agg_obj_6d"])
 
     def barrier():
         if world > 1:
@@ -210,11 +211,9 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
             ev[i][0].record()
             last = step_fn()
             ev[i][1].record()
-        gathered = None
         if world > 1:
-            m = metrics_of(last)
-            gathered = torch.empty((world,) + tuple(m.shape), dtype=m.dtype, device=dev)
-            dist.all_gather_into_tensor(gathered, m)
+            gathered = gather_records(metrics_of(last), BS * world)     # the only collective of the path
+            assert gathered.shape[0] == BS * world
         barrier()
         wall = time.perf_counter() - wall0
         if profile:

@@ -14,91 +14,45 @@
 //   pose-term  P2 . Wa_p     per candidate per call   (k_head_simt: FP32 register-tiled GEMM, K = 256,
 //                                                      fused bias/ReLU/second ParallelLinear/sigma division)
 // State, stage combinations, error norm and dense output are float64 as in scipy; the network is float32.
-#include "sampler.cuh"
+#include "sampler_device.cuh"
 #include "vpho_b200.h"
 
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace vpho {
 
-// ------------------------------------------------------------------------------------------------------------
-// Dormand-Prince coefficients exactly as scipy/integrate/_ivp/rk.py (class RK45) writes them
-// ------------------------------------------------------------------------------------------------------------
-VPHO_CONSTANT double kC[7] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
-VPHO_CONSTANT double kA[7][6] = {
-    {0, 0, 0, 0, 0, 0},
-    {1.0 / 5, 0, 0, 0, 0, 0},
-    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
-    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
-    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
-    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
-    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};   // row 6 = B (y_new)
-VPHO_CONSTANT double kE[7] = {-71.0 / 57600, 0, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
-VPHO_CONSTANT double kP[7][4] = {
-    {1, -8048581381.0 / 2820520608, 8663915743.0 / 2820520608, -12715105075.0 / 11282082432},
-    {0, 0, 0, 0},
-    {0, 131558114200.0 / 32700410799, -68118460800.0 / 10900136933, 87487479700.0 / 32700410799},
-    {0, -1754552775.0 / 470086768, 14199869525.0 / 1410260304, -10690763975.0 / 1880347072},
-    {0, 127303824393.0 / 49829197408, -318862633887.0 / 49829197408, 701980252875.0 / 199316789632},
-    {0, -282668133.0 / 205662961, 2019193451.0 / 616988883, -1453857185.0 / 822651844},
-    {0, 40617522.0 / 29380423, -110615467.0 / 29380423, 69997945.0 / 29380423}};
+// tcgen05 path (scorenet_tc.cu)
+bool tc_available();
+bool tc_make_map(void* map, const float* base, int rows, int box_rows);
+int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const DenoiserDev& dn,
+                   const SamplerWs& ws, int mode, int s, cudaStream_t st);
 
-constexpr double kSafety = 0.9, kMinFactor = 0.2, kMaxFactor = 10.0, kErrExponent = -0.2;
-constexpr double kSigmaMin = 0.01, kSigmaRatio = 5000.0;   // sigma_max / sigma_min = 50 / 0.01 (sde.py:92-93)
-// sqrt(2 * (log(50) - log(0.01))) evaluated in float64 (torch.tensor(np.float64), sde.py:23)
-constexpr double kSqrt2LogRatio = 4.1272734804992597;
+struct alignas(64) TensorMapBlob { unsigned char b[128]; };
 
 struct DenoiserHost {
   DenoiserDev dev;
   float* blob = nullptr;
+  // tcgen05 head GEMM: K-major hi/lo weight planes [hid][256] and their TMA descriptors
+  bool use_tc = false;
+  float* w_hi = nullptr;
+  float* w_lo = nullptr;
+  TensorMapBlob mapB_hi, mapB_lo, mapA_hi, mapA_lo;
+  const float* mapA_for = nullptr;   // P2hi pointer the cached A maps were built for
+  int mapA_rows = 0;
 };
 
-// ------------------------------------------------------------------------------------------------------------
-// time of an evaluation and the SDE scalars that go with it
-// ------------------------------------------------------------------------------------------------------------
-struct EvalTime {
-  float t32;      // time fed to the network: torch.ones(N,1) * t  -> float32
-  float std32;    // sigma(t32) + 1e-7 in float32 (denoiser.py:78-81)
-  double coef;    // 0.5 * g(t)^2 in float64 (score_based_model.py:84, numpy >= 2 promotion)
-  float g32;      // float32 diffusion for the predictor step (sde_coeff(vec_eps))
-};
-
-__device__ __forceinline__ float sigma_f32(float t32) {
-  // torch: 0.01 * (5000.0 ** t) on a float32 tensor; pow evaluated in double and rounded once
-  float p = (float)pow(5000.0, (double)t32);
-  return __fmul_rn(0.01f, p);
-}
-
-__device__ __forceinline__ EvalTime eval_time(const RkCtrl& c, int mode, int s) {
-  EvalTime e;
-  double t64;
-  if (mode == kModeInit0) t64 = c.T0;
-  else if (mode == kModeInit1) t64 = c.T0 + c.h0 * c.direction;
-  else if (mode == kModeStage) t64 = (s == 6) ? (c.t + c.h) : (c.t + kC[s] * c.h);
-  else if (mode == kModeFinal) t64 = c.eps;
-  else t64 = (double)c.eval_t32;
-  e.t32 = (float)t64;
-  e.std32 = __fadd_rn(sigma_f32(e.t32), 1e-7f);
-  double sigma;
-  if (mode == kModeInit0) sigma = (double)sigma_f32((float)c.T0);          // torch.tensor(python float) is float32
-  else sigma = kSigmaMin * pow(kSigmaRatio, t64);
-  double g = sigma * kSqrt2LogRatio;
-  e.coef = 0.5 * (g * g);
-  e.g32 = __fmul_rn(sigma_f32(e.t32), (float)kSqrt2LogRatio);
-  return e;
-}
-
-// K slot value with the reference's `nan_to_num(score, 0, 0, 0)` applied when that evaluation produced a NaN
-__device__ __forceinline__ double kval(const double* K, const RkCtrl& c, int slot, int n, int i) {
-  double v = K[(size_t)slot * n + i];
-  if (c.nan_stage[slot] && !isfinite(v)) v = 0.0;
-  return v;
-}
-
-__device__ __forceinline__ bool eval_active(const RkCtrl& c, int mode) {
-  if (mode == kModeEval) return true;
-  if (mode == kModeFinal) return c.status == 1;
-  return c.status == 0;
+// round-to-nearest (ties to even) onto the 10-bit TF32 mantissa, result kept in a float container
+__host__ __device__ __forceinline__ float tf32_round(float x) {
+  unsigned u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;
+  u += 0xFFFu + ((u >> 13) & 1u);
+  u &= 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -321,31 +275,31 @@ __global__ void __launch_bounds__(256) k_pose_encoder(DenoiserDev dn, SamplerWs 
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xr[i], wc[j], acc[i][j]);
   }
+  if (ws.P2hi) {
+    // tcgen05 path: row-major (K-major) planes, hi = tf32(p), lo = tf32(p - hi)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p = fmaxf(acc[i][j], 0.f);
+        hi[j] = tf32_round(p);
+        lo[j] = tf32_round(p - hi[j]);
+      }
+      float* dh = ws.P2hi + (size_t)(r0 + 4 * tx + i) * kPDim + 8 * ty;
+      float* dl = ws.P2lo + (size_t)(r0 + 4 * tx + i) * kPDim + 8 * ty;
+      *reinterpret_cast<float4*>(dh) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(dh + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+      *reinterpret_cast<float4*>(dl) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<float4*>(dl + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float4 o = make_float4(fmaxf(acc[0][j], 0.f), fmaxf(acc[1][j], 0.f), fmaxf(acc[2][j], 0.f), fmaxf(acc[3][j], 0.f));
     *reinterpret_cast<float4*>(ws.P2T + (size_t)(8 * ty + j) * ws.Npad + r0 + 4 * tx) = o;
   }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// what happens to one network output element, per evaluation mode
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void emit_score(const SamplerWs& ws, RkCtrl& c, const EvalTime& et, int mode, int s, int i,
-                                           float score) {
-  if (mode == kModeEval) { ws.eval_out[i] = score; return; }
-  if (mode == kModeFinal) {
-    // drift = 0 - diffusion**2 * grad (float32); x = x + drift * ((1-eps)/num_steps)   (score_based_model.py:95-104)
-    const float g2 = __fmul_rn(et.g32, et.g32);
-    const float drift = __fsub_rn(0.f, __fmul_rn(g2, score));
-    const float scale = (float)((1.0 - c.eps) / (double)c.num_steps);
-    c.x_out[i] = __dadd_rn(ws.y[i], (double)__fmul_rn(drift, scale));
-    return;
-  }
-  const int slot = (mode == kModeInit0) ? 0 : (mode == kModeInit1 ? 1 : s);
-  if (isnan(score)) { c.nan_stage[slot] = 1; c.nan_seen = 1; }
-  // drift - 0.5 * diffusion**2 * score, float64 (numpy >= 2 promotion)
-  ws.K[(size_t)slot * c.n + i] = -(et.coef * (double)score);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -649,7 +603,7 @@ __global__ void k_rot6d_to_aa(const float* __restrict__ x6d, int n, float* __res
 // ------------------------------------------------------------------------------------------------------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int n_eval, SamplerWs* ws) {
+static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int n_eval, SamplerWs* ws, bool use_tc = true) {
   const int D = 3 * n_heads, hid = n_heads * kHeadHid;
   const int R = (n_rows + rows_per_feat - 1) / rows_per_feat;
   const int Npad = (int)align_up((size_t)(n_rows > 0 ? n_rows : 1), kRowTile);
@@ -660,6 +614,8 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
   const size_t o_F = take((size_t)R * hid * 4);
   const size_t o_Tt = take((size_t)hid * 4);
   const size_t o_P2T = take((size_t)kPDim * Npad * 4);
+  const size_t o_P2hi = take((size_t)kPDim * Npad * 4);
+  const size_t o_P2lo = take((size_t)kPDim * Npad * 4);
   const size_t o_y = take(n * 8);
   const size_t o_yn = take(n * 8);
   const size_t o_K = take(7 * n * 8);
@@ -671,6 +627,8 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
     ws->F = reinterpret_cast<float*>(b + o_F);
     ws->Tt = reinterpret_cast<float*>(b + o_Tt);
     ws->P2T = reinterpret_cast<float*>(b + o_P2T);
+    ws->P2hi = use_tc ? reinterpret_cast<float*>(b + o_P2hi) : nullptr;
+    ws->P2lo = use_tc ? reinterpret_cast<float*>(b + o_P2lo) : nullptr;
     ws->y = reinterpret_cast<double*>(b + o_y);
     ws->ynew = reinterpret_cast<double*>(b + o_yn);
     ws->K = reinterpret_cast<double*>(b + o_K);
@@ -685,24 +643,37 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
 
 static int red_blocks(int n) { int b = (n + 255) / 256; return b < 1 ? 1 : (b > kMaxRedBlocks ? kMaxRedBlocks : b); }
 
-static int launch_eval(const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, cudaStream_t st) {
+static int launch_eval(DenoiserHost& dh, const SamplerWs& ws, int mode, int s, cudaStream_t st) {
+  const DenoiserDev& dn = dh.dev;
   VPHO_LAUNCH(k_time_term, dim3((dn.hid + 255) / 256), dim3(256), 0, st, dn, ws, mode, s);
   profile_begin(VPHO_TAG_POSE_ENCODER, st);
   VPHO_LAUNCH(k_pose_encoder, dim3(ws.Npad / kPeRows), dim3(256), 0, st, dn, ws, mode, s);
   profile_end(VPHO_TAG_POSE_ENCODER, st);
   const int tag = dn.n_heads >= 16 ? VPHO_TAG_HEAD_GEMM_HAND : VPHO_TAG_HEAD_GEMM_OBJ;
   profile_begin(tag, st);
-  VPHO_LAUNCH(k_head_simt, dim3(ws.Npad / kRowTile, dn.n_heads), dim3(256), 0, st, dn, ws, mode, s);
+  if (ws.P2hi) {
+#ifndef VPHO_EMU
+    if (dh.mapA_for != ws.P2hi || dh.mapA_rows != ws.Npad) {
+      if (!tc_make_map(&dh.mapA_hi, ws.P2hi, ws.Npad, 128) || !tc_make_map(&dh.mapA_lo, ws.P2lo, ws.Npad, 128)) return VPHO_ERR_LAUNCH;
+      dh.mapA_for = ws.P2hi;
+      dh.mapA_rows = ws.Npad;
+    }
+    int rc = tc_launch_head(&dh.mapA_hi, &dh.mapA_lo, &dh.mapB_hi, &dh.mapB_lo, dn, ws, mode, s, st);
+    if (rc) return rc;
+#endif
+  } else {
+    VPHO_LAUNCH(k_head_simt, dim3(ws.Npad / kRowTile, dn.n_heads), dim3(256), 0, st, dn, ws, mode, s);
+  }
   profile_end(tag, st);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }
 
-static int launch_attempts(const DenoiserDev& dn, const SamplerWs& ws, int n, int max_attempts, cudaStream_t st) {
+static int launch_attempts(DenoiserHost& dh, const SamplerWs& ws, int n, int max_attempts, cudaStream_t st) {
   const int rb = red_blocks(n);
   for (int a = 0; a < max_attempts; ++a) {
     for (int s = 1; s <= 6; ++s) {
-      int rc = launch_eval(dn, ws, kModeStage, s, st);
+      int rc = launch_eval(dh, ws, kModeStage, s, st);
       if (rc) return rc;
     }
     VPHO_LAUNCH(k_reduce, dim3(rb), dim3(256), 0, st, ws, (int)kRedErr);
@@ -770,6 +741,34 @@ extern "C" int vpho_denoiser_create(int n_heads, const float* fourier_W, const f
   d.fourier_W = b + o_four; d.Wt = b + o_wt; d.bt = b + o_bt; d.W1 = b + o_w1; d.b1 = b + o_b1; d.W2 = b + o_w2;
   d.b2 = b + o_b2; d.Wa_t = b + o_wat; d.Wa_p = b + o_wap; d.Wa_f = b + o_waf; d.ba = b + o_ba; d.Wb = b + o_wb;
   d.bb = b + o_bb; d.Wa_p_hi = nullptr; d.Wa_p_lo = nullptr;
+#ifndef VPHO_EMU
+  // tcgen05 head GEMM (default).  VPHO_HEAD_GEMM=simt keeps the FP32-SIMT kernel (used to cross-check the two).
+  const char* sel = getenv("VPHO_HEAD_GEMM");
+  const bool want_tc = !(sel && strcmp(sel, "simt") == 0);
+  if (want_tc && tc_available()) {
+    std::vector<float> whi((size_t)hid * kPDim), wlo((size_t)hid * kPDim);
+    for (int nn = 0; nn < n_heads; ++nn)
+      for (int k = 0; k < kPDim; ++k) {
+        const float* src = ha_w + ((size_t)nn * 1408 + 128 + k) * 256;
+        for (int cc = 0; cc < 256; ++cc) {
+          const float w = src[cc], hi = tf32_round(w);
+          whi[((size_t)nn * 256 + cc) * kPDim + k] = hi;
+          wlo[((size_t)nn * 256 + cc) * kPDim + k] = tf32_round(w - hi);
+        }
+      }
+    const size_t bytes = (size_t)hid * kPDim * sizeof(float);
+    if (cudaMalloc((void**)&dh->w_hi, bytes) != cudaSuccess || cudaMalloc((void**)&dh->w_lo, bytes) != cudaSuccess ||
+        cudaMemcpy(dh->w_hi, whi.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(dh->w_lo, wlo.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaFree(dh->w_hi); cudaFree(dh->w_lo); cudaFree(dh->blob); delete dh; return VPHO_ERR_ALLOC;
+    }
+    if (!tc_make_map(&dh->mapB_hi, dh->w_hi, hid, 256) || !tc_make_map(&dh->mapB_lo, dh->w_lo, hid, 256)) {
+      cudaFree(dh->w_hi); cudaFree(dh->w_lo); cudaFree(dh->blob); delete dh; return VPHO_ERR_LAUNCH;
+    }
+    d.Wa_p_hi = dh->w_hi; d.Wa_p_lo = dh->w_lo;
+    dh->use_tc = true;
+  }
+#endif
   *out = dh;
   return VPHO_OK;
 }
@@ -778,13 +777,15 @@ extern "C" int vpho_denoiser_destroy(vpho_denoiser_t h) {
   if (!h) return VPHO_ERR_INVALID;
   DenoiserHost* dh = static_cast<DenoiserHost*>(h);
   cudaFree(dh->blob);
+  if (dh->w_hi) cudaFree(dh->w_hi);
+  if (dh->w_lo) cudaFree(dh->w_lo);
   delete dh;
   return VPHO_OK;
 }
 
 extern "C" size_t vpho_sample_workspace_bytes(int n_heads, int n_rows, int rows_per_feat, int n_eval) {
   if (n_heads <= 0 || n_rows < 0 || rows_per_feat <= 0) return 0;
-  return carve(nullptr, n_heads, n_rows, rows_per_feat, n_eval, nullptr);
+  return carve(nullptr, n_heads, n_rows, rows_per_feat, n_eval, nullptr);   // same size for both head-GEMM paths
 }
 
 extern "C" int vpho_score_eval(vpho_denoiser_t h, const float* x, float t, const float* feat, int n_rows,
@@ -792,15 +793,16 @@ extern "C" int vpho_score_eval(vpho_denoiser_t h, const float* x, float t, const
   if (!h || n_rows < 0 || rows_per_feat <= 0 || !workspace) return VPHO_ERR_INVALID;
   if (n_rows == 0) return VPHO_OK;
   if (!x || !feat || !out) return VPHO_ERR_INVALID;
-  const DenoiserDev& dn = static_cast<DenoiserHost*>(h)->dev;
+  DenoiserHost& dh = *static_cast<DenoiserHost*>(h);
+  const DenoiserDev& dn = dh.dev;
   SamplerWs ws;
-  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, 1, &ws) > workspace_bytes) return VPHO_ERR_INVALID;
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, 1, &ws, dh.use_tc) > workspace_bytes) return VPHO_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   ws.eval_x = x; ws.eval_out = out;
   VPHO_LAUNCH(k_set_eval_time, dim3(1), dim3(1), 0, st, ws, t);
   VPHO_LAUNCH(k_feat_term, dim3(dn.hid / kFtCols, (ws.R + kFtRows - 1) / kFtRows), dim3(256), 0, st, dn, feat, ws.R, ws.F);
   VPHO_CHECK_LAUNCH();
-  return launch_eval(dn, ws, kModeEval, 0, st);
+  return launch_eval(dh, ws, kModeEval, 0, st);
 }
 
 extern "C" int vpho_sample_begin(vpho_denoiser_t h, const float* feat, int n_rows, int rows_per_feat,
@@ -811,9 +813,10 @@ extern "C" int vpho_sample_begin(vpho_denoiser_t h, const float* feat, int n_row
   if (!h || n_rows < 0 || rows_per_feat <= 0 || !workspace || n_eval < 1 || num_steps < 1 || max_attempts < 0)
     return VPHO_ERR_INVALID;
   if (n_rows > 0 && (!feat || !init_x || !x)) return VPHO_ERR_INVALID;
-  const DenoiserDev& dn = static_cast<DenoiserHost*>(h)->dev;
+  DenoiserHost& dh = *static_cast<DenoiserHost*>(h);
+  const DenoiserDev& dn = dh.dev;
   SamplerWs ws;
-  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws) > workspace_bytes) return VPHO_ERR_INVALID;
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws, dh.use_tc) > workspace_bytes) return VPHO_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int n = n_rows * dn.D;
   SampleCfg cfg{T0, eps, rtol, atol, max_step, n_rows, dn.D, n_eval, num_steps, rows_per_feat, t_eval, xs, x, counters};
@@ -824,35 +827,37 @@ extern "C" int vpho_sample_begin(vpho_denoiser_t h, const float* feat, int n_row
   VPHO_LAUNCH(k_init_state, dim3(rb), dim3(256), 0, st, ws, init_x, n);
   VPHO_LAUNCH(k_feat_term, dim3(dn.hid / kFtCols, (ws.R + kFtRows - 1) / kFtRows), dim3(256), 0, st, dn, feat, ws.R, ws.F);
   VPHO_CHECK_LAUNCH();
-  int rc = launch_eval(dn, ws, kModeInit0, 0, st);
+  int rc = launch_eval(dh, ws, kModeInit0, 0, st);
   if (rc) return rc;
   VPHO_LAUNCH(k_reduce, dim3(rb), dim3(256), 0, st, ws, (int)kRedInit0);
-  rc = launch_eval(dn, ws, kModeInit1, 0, st);
+  rc = launch_eval(dh, ws, kModeInit1, 0, st);
   if (rc) return rc;
   VPHO_LAUNCH(k_reduce, dim3(rb), dim3(256), 0, st, ws, (int)kRedInit1);
   VPHO_CHECK_LAUNCH();
-  return launch_attempts(dn, ws, n, max_attempts, st);
+  return launch_attempts(dh, ws, n, max_attempts, st);
 }
 
 extern "C" int vpho_sample_continue(vpho_denoiser_t h, int n_rows, int rows_per_feat, int n_eval, int max_attempts,
                                     void* workspace, size_t workspace_bytes, void* stream) {
   if (!h || n_rows < 0 || rows_per_feat <= 0 || !workspace || max_attempts < 0) return VPHO_ERR_INVALID;
   if (n_rows == 0) return VPHO_OK;
-  const DenoiserDev& dn = static_cast<DenoiserHost*>(h)->dev;
+  DenoiserHost& dh = *static_cast<DenoiserHost*>(h);
+  const DenoiserDev& dn = dh.dev;
   SamplerWs ws;
-  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws) > workspace_bytes) return VPHO_ERR_INVALID;
-  return launch_attempts(dn, ws, n_rows * dn.D, max_attempts, (cudaStream_t)stream);
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws, dh.use_tc) > workspace_bytes) return VPHO_ERR_INVALID;
+  return launch_attempts(dh, ws, n_rows * dn.D, max_attempts, (cudaStream_t)stream);
 }
 
 extern "C" int vpho_sample_finish(vpho_denoiser_t h, int n_rows, int rows_per_feat, int n_eval, void* workspace,
                                   size_t workspace_bytes, void* stream) {
   if (!h || n_rows < 0 || rows_per_feat <= 0 || !workspace) return VPHO_ERR_INVALID;
   if (n_rows == 0) return VPHO_OK;
-  const DenoiserDev& dn = static_cast<DenoiserHost*>(h)->dev;
+  DenoiserHost& dh = *static_cast<DenoiserHost*>(h);
+  const DenoiserDev& dn = dh.dev;
   SamplerWs ws;
-  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws) > workspace_bytes) return VPHO_ERR_INVALID;
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws, dh.use_tc) > workspace_bytes) return VPHO_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = launch_eval(dn, ws, kModeFinal, 0, st);
+  int rc = launch_eval(dh, ws, kModeFinal, 0, st);
   if (rc) return rc;
   VPHO_LAUNCH(k_export, dim3(1), dim3(1), 0, st, ws);
   VPHO_CHECK_LAUNCH();

@@ -75,7 +75,9 @@ struct SamplerWs {
   RkCtrl* ctrl;
   float* F;        // [R][hid]  feat-term + bias, once per sample()
   float* Tt;       // [hid]     time-term of the current evaluation
-  float* P2T;      // [256][Npad] pose features, k-major
+  float* P2T;      // [256][Npad] pose features, k-major (FP32-SIMT head GEMM)
+  float* P2hi;     // [Npad][256] pose features split for 3xTF32, row-major = K-major (tcgen05 head GEMM); nullptr = SIMT
+  float* P2lo;
   double* y;       // [n]
   double* ynew;    // [n]
   double* K;       // [7][n]

@@ -1,0 +1,305 @@
+// Score-network head GEMM on the 5th-generation tensor cores (tcgen05) with FP32-level accuracy by 3xTF32 splitting.
+//
+// Same contract as k_head_simt (sampler.cu): for every 128-candidate row tile and every ParallelLinear head
+//     hidden[128][256] = P2[128][256] . Wa_p[head][256][256]      (lib/model/parallel_linear.py:27-35, K = pose features)
+//     out[row][0..2]   = relu(hidden + F[img] + Tt) . Wb[head] + bb ;  score = out / (sigma(t) + 1e-7)
+// but the contraction runs as  A_hi.B_hi + A_hi.B_lo + A_lo.B_hi  with kind::tf32 UMMA instructions:
+//   * operands staged in shared memory by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, K-major 128-byte rows),
+//     2-stage mbarrier pipeline, one producer lane;
+//   * tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 256, K = 8 per instruction, issued by one elected lane,
+//     FP32 accumulators in TMEM (2 x 256 columns, double-buffered across work items);
+//   * 4 epilogue warps read the accumulator with tcgen05.ld (one candidate row per thread, 32 columns at a time) and
+//     fuse bias / conditioning / time terms, ReLU, the 256 -> 3 second ParallelLinear and the sigma division.
+// Persistent grid: CTA b processes items b, b + gridDim.x, ... of the (head, row tile) list.
+// hi = round_to_nearest_tf32(x), lo = round_to_nearest_tf32(x - hi): the dropped lo.lo term and the TF32 rounding of lo
+// leave a relative error of ~2^-21 per product, i.e. FP32-class accuracy for this K = 256 contraction.
+#include "sampler_device.cuh"
+#include "vpho_b200.h"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace vpho {
+
+constexpr int kTcBM = 128, kTcBN = 256, kTcBK = 32, kTcStages = 2, kTcUmmaK = 8;
+constexpr int kTcABytes = kTcBM * kTcBK * 4;        // 16 KB per operand plane per stage
+constexpr int kTcBBytes = kTcBN * kTcBK * 4;        // 32 KB
+constexpr int kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes;   // 96 KB
+constexpr int kTcThreads = 256;
+constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+
+struct TcSmem {
+  // operand stages first: 1024-byte aligned swizzle atoms
+  unsigned char stage[kTcStages][kTcStageBytes];
+  float wb[2][kTcBN][4];
+  float tt[2][kTcBN];
+  unsigned long long full_bar[kTcStages], empty_bar[kTcStages], tmem_full_bar[2], tmem_empty_bar[2];
+  uint32_t tmem_base;
+};
+
+// -------------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(void* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B operand tile whose rows are 128 bytes: 8-row atoms of 1024 bytes (SBO), LBO unused (= 1)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(const void* smem) {
+  const uint32_t addr = smem_u32(smem);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);            // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                           // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset between 8-row atoms
+  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, DenoiserDev dn, SamplerWs ws,
+          int mode, int s) {
+  RkCtrl& c = *ws.ctrl;
+  if (!eval_active(c, mode)) return;            // uniform across the grid: nothing allocated yet
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = ws.Npad / kTcBM;
+  const int n_items = n_tiles * dn.n_heads;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kTcStages; ++i) { mbar_init(&sm.full_bar[i], 1); mbar_init(&sm.empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full_bar[i], 1); mbar_init(&sm.tmem_empty_bar[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int tile = it % n_tiles, head = it / n_tiles;
+        for (int kc = 0; kc < kPDim / kTcBK; ++kc) {
+          mbar_wait(&sm.empty_bar[stage], phase ^ 1);
+          unsigned char* st = sm.stage[stage];
+          mbar_arrive_expect_tx(&sm.full_bar[stage], kTcStageBytes);
+          tma_load_2d(&tmA_hi, &sm.full_bar[stage], st, kc * kTcBK, tile * kTcBM);
+          tma_load_2d(&tmA_lo, &sm.full_bar[stage], st + kTcABytes, kc * kTcBK, tile * kTcBM);
+          tma_load_2d(&tmB_hi, &sm.full_bar[stage], st + 2 * kTcABytes, kc * kTcBK, head * kTcBN);
+          tma_load_2d(&tmB_lo, &sm.full_bar[stage], st + 2 * kTcABytes + kTcBBytes, kc * kTcBK, head * kTcBN);
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        mbar_wait(&sm.tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTcBN);
+        for (int kc = 0; kc < kPDim / kTcBK; ++kc) {
+          mbar_wait(&sm.full_bar[stage], phase);
+          tc_fence_after();
+          unsigned char* st = sm.stage[stage];
+          const uint64_t a_hi = make_kmajor_sw128_desc(st), a_lo = make_kmajor_sw128_desc(st + kTcABytes);
+          const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * kTcABytes), b_lo = make_kmajor_sw128_desc(st + 2 * kTcABytes + kTcBBytes);
+#pragma unroll
+          for (int k = 0; k < kTcBK / kTcUmmaK; ++k) {
+            const uint64_t adv = (uint64_t)((k * kTcUmmaK * 4) >> 4);     // 32 bytes per K step inside the 128-byte row
+            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, kTcIdesc, (kc | k) != 0 ? 1u : 0u);
+            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, kTcIdesc, 1u);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, kTcIdesc, 1u);
+          }
+          umma_commit(&sm.empty_bar[stage]);          // frees the smem slot once these MMAs have read it
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&sm.tmem_full_bar[acc]);          // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (warps 4..7 own TMEM lanes 32*(warp-4) ..)
+    const int q = warp - 4, te = threadIdx.x - 128;
+    const EvalTime et = eval_time(c, mode, s);
+    const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
+    const int rpf = (mode == kModeEval) ? ws.eval_rpf : c.rows_per_feat;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int tile = it % n_tiles, head = it / n_tiles;
+      const int hc0 = head * kHeadHid;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int col = te + r * 128;
+        sm.tt[acc][col] = ws.Tt[hc0 + col];
+        *reinterpret_cast<float4*>(sm.wb[acc][col]) = __ldg(reinterpret_cast<const float4*>(dn.Wb + (size_t)(hc0 + col) * 4));
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&sm.tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = tile * kTcBM + q * 32 + lane;
+      const bool valid = row < n_rows;
+      const float* Frow = ws.F + (size_t)(valid ? row / rpf : 0) * dn.hid + hc0;
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll 1
+      for (int cb = 0; cb < kTcBN / 32; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTcBN + cb * 32), v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 f4 = __ldg(reinterpret_cast<const float4*>(Frow + cb * 32 + j4 * 4));
+          const float fa[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int col = cb * 32 + j4 * 4 + jj;
+            float hval = (__uint_as_float(v[j4 * 4 + jj]) + fa[jj]) + sm.tt[acc][col];
+            hval = hval > 0.f ? hval : 0.f;
+            const float4 w = *reinterpret_cast<const float4*>(sm.wb[acc][col]);
+            o0 = fmaf(hval, w.x, o0);
+            o1 = fmaf(hval, w.y, o1);
+            o2 = fmaf(hval, w.z, o2);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.tmem_empty_bar[acc]);
+      if (valid) {
+        const float o[3] = {o0, o1, o2};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float out = o[d] + dn.bb[head * 3 + d];
+          emit_score(ws, c, et, mode, s, row * dn.D + head * 3 + d, __fdiv_rn(out, et.std32));
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// -------------------------------------------------------------------------------------------------- host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 2-D K-major f32 tensor [rows][256] -> boxes of {32 k, box_rows}, 128-byte swizzle
+bool tc_make_map(void* map_out, const float* base, int rows, int box_rows) {
+  CUtensorMap* map = static_cast<CUtensorMap*>(map_out);
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)kPDim, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)kPDim * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool tc_available() { return get_encode() != nullptr; }
+
+int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const DenoiserDev& dn,
+                   const SamplerWs& ws, int mode, int s, cudaStream_t st) {
+  static bool attr = false;
+  const int smem = (int)sizeof(TcSmem) + 1024;
+  if (!attr) {
+    if (cudaFuncSetAttribute(k_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return VPHO_ERR_LAUNCH;
+    attr = true;
+  }
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  const int n_items = (ws.Npad / kTcBM) * dn.n_heads;
+  const int grid = n_items < n_sm ? n_items : n_sm;
+  VPHO_LAUNCH(k_head_tc, dim3(grid), dim3(kTcThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
+              *static_cast<const CUtensorMap*>(mapA_lo), *static_cast<const CUtensorMap*>(mapB_hi),
+              *static_cast<const CUtensorMap*>(mapB_lo), dn, ws, mode, s);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
+
+}  // namespace vpho

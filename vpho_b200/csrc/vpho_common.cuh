@@ -17,7 +17,7 @@ void profile_end(int tag, cudaStream_t st);
 }  // namespace vpho
 #define VPHO_LAUNCH(kern, grid, block, smem, stream, ...) \
   do { ++::vpho::g_launches; kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); } while (0)
-#define VPHO_CONSTANT __constant__
+#define VPHO_CONSTANT static __constant__
 namespace vpho {
 // 16-byte asynchronous global->shared copy (LDGSTS) and its group fences
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {

@@ -37,6 +37,8 @@ BS, S, STEPS_ODE, T0, K_HAND, K_OBJ = 64, 100, 50, 0.65, 30, 10
 # algorithmic work (restated in DESIGN.md §5)
 FLOP_HEAD_GEMM_HAND = 2 * (256 * 8192 + 8192 * 3)     # per candidate per network call, head GEMM + fused second layer
 FLOP_SCORE_HAND, FLOP_SCORE_OBJ = 4423680, 533504     # whole factored network per candidate per call
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+NCU_TRAFFIC_BYTES = {"k_head_tc": 32187392 + 2816}
 
 
 def _peaks():
@@ -254,6 +256,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     value = cand * args.steps / (ms_res / 1e3)
     e2e = cand * args.steps / (ms_e2e / 1e3)
     peaks = _peaks()
+    head_kernel = "k_head_simt" if os.environ.get("VPHO_HEAD_GEMM") == "simt" else "k_head_tc"
     hg = prof["head_gemm_hand"]
     # launches that found the integration already finished exit at once; count the real network calls only
     real_launches = info["hand"]["net_calls"] * args.steps
@@ -268,11 +271,14 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
-        "roofline": {"kernel": "k_head_simt (hand score network: pose-feature GEMM K=256 x 8192 hidden, fused bias/ReLU/"
+        "roofline": {"kernel": head_kernel + " (hand score network: pose-feature GEMM K=256 x 8192 hidden, fused bias/ReLU/"
                                "256->3 heads/sigma division)",
                      "bound": "tensor", "achieved": round(achieved, 2) if achieved else None, "peak": peaks["bf16_tflops"],
                      "unit": "TFLOP/s", "frac": round(achieved / peaks["bf16_tflops"], 4) if achieved else None,
-                     "traffic": None, "peak_source": peaks["source"] + " (cuBLAS bf16 burst)",
+                     "traffic": NCU_TRAFFIC_BYTES.get(head_kernel), "peak_source": peaks["source"] + " (cuBLAS bf16 burst)",
+                     "note": "FP32-parity contraction run as 3 kind::tf32 UMMAs per algorithmic FLOP (TF32 rate = 1/2 of bf16): "
+                             "ceiling for this formulation is peak/6 = %.0f TFLOP/s; ncu tensor-pipe active 69%% "
+                             "(profiles/r01_ncu_head_tc_summary.txt)" % (peaks["bf16_tflops"] / 6),
                      "launches_timed": hg["launches"], "network_calls": real_launches, "avg_launch_ms": round(avg_ms, 4),
                      "flop_per_launch": BS * S * FLOP_HEAD_GEMM_HAND,
                      "share_of_step": round(hg["ms_total"] / ms_res, 4)},

@@ -181,14 +181,37 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     def step_resident():
         return hp.predict(resident, prior_hand=resident["prior_hand"], prior_obj=resident["prior_obj"])
 
+    # e2e: inputs live in pinned host memory; every step issues one full H2D copy (the NEXT step's inputs, on a copy
+    # stream, double-buffered -- what a prefetching eval loop does) and one D2H read of the aggregated results.
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_sets = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()} for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    for e in consumed:
+        e.record()
+    e2e_state = {"i": 0}
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            for k, v in host.items():
+                dev_sets[slot][k].copy_(v, non_blocking=True)
+            ready[slot].record(copy_stream)
+
     def step_e2e():
-        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        slot = e2e_state["i"] & 1
+        e2e_state["i"] += 1
+        prefetch(slot ^ 1)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready[slot])
+        d = dev_sets[slot]
         pd = hp.predict(d, prior_hand=d["prior_hand"], prior_obj=d["prior_obj"])
+        consumed[slot].record(cur)
         for k in out_keys:
             if k not in host_out:
                 host_out[k] = torch.empty(pd[k].shape, dtype=pd[k].dtype).pin_memory()
             host_out[k].copy_(pd[k], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        cur.synchronize()
         return pd
 
     def metrics_of(pd):
@@ -239,9 +262,19 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         tot, n = C.c_double(0), C.c_int(0)
         lib.c.vpho_profile_collect(tag, C.byref(tot), C.byref(n))
         prof[name] = {"ms_total": tot.value, "launches": n.value}
+    prefetch(0)
     for _ in range(2):
         step_e2e()
     ms_e2e, wall_e2e, _, _ = timed(step_e2e, args.steps)
+    # stand-alone H2D time of one input set (not overlapped), for reference
+    hs, he = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    hs.record()
+    for k, v in host.items():
+        dev_sets[0][k].copy_(v, non_blocking=True)
+    he.record()
+    torch.cuda.synchronize()
+    h2d_ms = hs.elapsed_time(he)
     if rank == 0:
         clocks.stop_flag.set()
         clocks.join(timeout=2)
@@ -268,7 +301,8 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(world),
         "e2e": {"value": round(e2e, 1), "unit": "candidates/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(ms_e2e / args.steps, 4)},
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(ms_e2e / args.steps, 4),
+                "h2d_ms_alone": round(h2d_ms, 3), "note": "H2D of step i+1 runs on a copy stream while step i computes"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": {"kernel": head_kernel + " (hand score network: pose-feature GEMM K=256 x 8192 hidden, fused bias/ReLU/"

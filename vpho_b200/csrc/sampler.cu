@@ -25,7 +25,10 @@ namespace vpho {
 
 // tcgen05 path (scorenet_tc.cu)
 bool tc_available();
-bool tc_make_map(void* map, const float* base, int rows, int box_rows);
+bool tc_make_map(void* map, const float* base, int rows, int box_rows, int kdim);
+int tc_launch_pose(const void* mapX_hi, const void* mapX_lo, const void* mapW1_hi, const void* mapW1_lo, const void* mapW2_hi,
+                   const void* mapW2_lo, const DenoiserDev& dn,
+                   const SamplerWs& ws, int mode, int s, cudaStream_t st);
 int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const DenoiserDev& dn,
                    const SamplerWs& ws, int mode, int s, cudaStream_t st);
 
@@ -39,6 +42,12 @@ struct DenoiserHost {
   float* w_hi = nullptr;
   float* w_lo = nullptr;
   TensorMapBlob mapB_hi, mapB_lo, mapA_hi, mapA_lo;
+  // tcgen05 pose encoder: K-major hi/lo planes of pose_encoder.0 [256][Kpad1] and pose_encoder.2 [256][256]
+  bool use_tc_pose = false;
+  float* pe_planes = nullptr;
+  TensorMapBlob mapW1_hi, mapW1_lo, mapW2_hi, mapW2_lo, mapX_hi, mapX_lo;
+  const float* mapX_for = nullptr;
+  int mapX_rows = 0;
   const float* mapA_for = nullptr;   // P2hi pointer the cached A maps were built for
   int mapA_rows = 0;
 };
@@ -158,9 +167,8 @@ __global__ void __launch_bounds__(256) k_feat_term(DenoiserDev dn, const float* 
 // ------------------------------------------------------------------------------------------------------------
 // time-term: Fourier embedding -> t_encoder -> Tt[col] = sum_k t_feat[k] Wa_t[k][col]   (one per network call)
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_time_term(DenoiserDev dn, SamplerWs ws, int mode, int s) {
-  const RkCtrl& c = *ws.ctrl;
-  if (!eval_active(c, mode)) return;
+__device__ __forceinline__ void time_term_block(const DenoiserDev& dn, const SamplerWs& ws, const RkCtrl& c, int mode, int s,
+                                                int block) {
   __shared__ float four[kTDim];
   __shared__ float tfeat[kTDim];
   const int tid = threadIdx.x;
@@ -179,12 +187,37 @@ __global__ void __launch_bounds__(256) k_time_term(DenoiserDev dn, SamplerWs ws,
     tfeat[tid] = a > 0.f ? a : 0.f;
   }
   __syncthreads();
-  const int col = blockIdx.x * 256 + tid;
+  const int col = block * 256 + tid;
   if (col < dn.hid) {
     float a = 0.f;
 #pragma unroll 8
     for (int k = 0; k < kTDim; ++k) a = fmaf(tfeat[k], __ldg(dn.Wa_t + (size_t)k * dn.hid + col), a);
     ws.Tt[col] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_time_term(DenoiserDev dn, SamplerWs ws, int mode, int s) {
+  const RkCtrl& c = *ws.ctrl;
+  if (!eval_active(c, mode)) return;
+  time_term_block(dn, ws, c, mode, s, blockIdx.x);
+}
+
+// tcgen05 path: one launch does the time-term (first `nb_time` blocks) and the float64 RK stage combination of every
+// state element into the (hi, lo) TF32 planes of the pose encoder's A operand (remaining blocks), all SMs busy.
+__global__ void __launch_bounds__(256) k_stage_x(DenoiserDev dn, SamplerWs ws, int mode, int s, int nb_time) {
+  const RkCtrl& c = *ws.ctrl;
+  if (!eval_active(c, mode)) return;
+  if ((int)blockIdx.x < nb_time) { time_term_block(dn, ws, c, mode, s, blockIdx.x); return; }
+  const int D = dn.D, Kx = ws.Kx;
+  const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
+  const int total = ws.Npad * Kx;
+  for (int it = (blockIdx.x - nb_time) * 256 + threadIdx.x; it < total; it += (gridDim.x - nb_time) * 256) {
+    const int row = it / Kx, k = it - row * Kx;
+    float x = 0.f;
+    if (k < D) x = (float)stage_input(ws, c, mode, s, row, k, n_rows, D);
+    const float hi = tf32_round(x);
+    ws.Xhi[it] = hi;
+    ws.Xlo[it] = tf32_round(x - hi);
   }
 }
 
@@ -200,30 +233,11 @@ __global__ void __launch_bounds__(256) k_pose_encoder(DenoiserDev dn, SamplerWs 
   __shared__ __align__(16) float xs[kMaxD][kPeRows];
   __shared__ __align__(16) float h1s[kPDim][kPeRows];
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
-  const int D = dn.D, n = c.n, n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
+  const int D = dn.D, n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
   const int r0 = blockIdx.x * kPeRows;
-  const double h = c.h;
   for (int it = tid; it < kPeRows * D; it += 256) {
     const int r = it / D, d = it - r * D;
-    const int row = r0 + r;
-    double v = 0.0;
-    if (row < n_rows) {
-      const int i = row * D + d;
-      if (mode == kModeEval) v = (double)ws.eval_x[i];
-      else {
-        const double y = ws.y[i];
-        if (mode == kModeInit0 || mode == kModeFinal) v = y;
-        else if (mode == kModeInit1) v = __dadd_rn(y, __dmul_rn(c.h0 * c.direction, kval(ws.K, c, 0, n, i)));
-        else {
-          // dy = np.dot(K[:s].T, a[:s]) * h ; y + dy          (rk.py rk_step)
-          double acc = 0.0;
-          const int ns = (s == 6) ? 6 : s;
-          for (int j = 0; j < ns; ++j) acc += kval(ws.K, c, j, n, i) * kA[s][j];
-          v = __dadd_rn(y, __dmul_rn(acc, h));
-          if (s == 6) ws.ynew[i] = v;
-        }
-      }
-    }
+    const double v = stage_input(ws, c, mode, s, r0 + r, d, n_rows, D);
     xs[d][r] = (float)v;
   }
   __syncthreads();
@@ -616,6 +630,9 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
   const size_t o_P2T = take((size_t)kPDim * Npad * 4);
   const size_t o_P2hi = take((size_t)kPDim * Npad * 4);
   const size_t o_P2lo = take((size_t)kPDim * Npad * 4);
+  const int Kx = (D + 31) / 32 * 32;
+  const size_t o_Xhi = take((size_t)Kx * Npad * 4);
+  const size_t o_Xlo = take((size_t)Kx * Npad * 4);
   const size_t o_y = take(n * 8);
   const size_t o_yn = take(n * 8);
   const size_t o_K = take(7 * n * 8);
@@ -629,6 +646,9 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
     ws->P2T = reinterpret_cast<float*>(b + o_P2T);
     ws->P2hi = use_tc ? reinterpret_cast<float*>(b + o_P2hi) : nullptr;
     ws->P2lo = use_tc ? reinterpret_cast<float*>(b + o_P2lo) : nullptr;
+    ws->Xhi = reinterpret_cast<float*>(b + o_Xhi);
+    ws->Xlo = reinterpret_cast<float*>(b + o_Xlo);
+    ws->Kx = Kx;
     ws->y = reinterpret_cast<double*>(b + o_y);
     ws->ynew = reinterpret_cast<double*>(b + o_yn);
     ws->K = reinterpret_cast<double*>(b + o_K);
@@ -645,16 +665,33 @@ static int red_blocks(int n) { int b = (n + 255) / 256; return b < 1 ? 1 : (b > 
 
 static int launch_eval(DenoiserHost& dh, const SamplerWs& ws, int mode, int s, cudaStream_t st) {
   const DenoiserDev& dn = dh.dev;
-  VPHO_LAUNCH(k_time_term, dim3((dn.hid + 255) / 256), dim3(256), 0, st, dn, ws, mode, s);
   profile_begin(VPHO_TAG_POSE_ENCODER, st);
-  VPHO_LAUNCH(k_pose_encoder, dim3(ws.Npad / kPeRows), dim3(256), 0, st, dn, ws, mode, s);
+#ifndef VPHO_EMU
+  if (ws.P2hi && dh.use_tc_pose) {
+    const int nb_time = (dn.hid + 255) / 256;
+    int nb_x = (ws.Npad * ws.Kx + 1023) / 1024;           // ~4 elements per thread
+    if (nb_x > 592) nb_x = 592;
+    VPHO_LAUNCH(k_stage_x, dim3(nb_time + nb_x), dim3(256), 0, st, dn, ws, mode, s, nb_time);
+    if (dh.mapX_for != ws.Xhi || dh.mapX_rows != ws.Npad) {
+      if (!tc_make_map(&dh.mapX_hi, ws.Xhi, ws.Npad, 128, ws.Kx) || !tc_make_map(&dh.mapX_lo, ws.Xlo, ws.Npad, 128, ws.Kx)) return VPHO_ERR_LAUNCH;
+      dh.mapX_for = ws.Xhi;
+      dh.mapX_rows = ws.Npad;
+    }
+    int rc = tc_launch_pose(&dh.mapX_hi, &dh.mapX_lo, &dh.mapW1_hi, &dh.mapW1_lo, &dh.mapW2_hi, &dh.mapW2_lo, dn, ws, mode, s, st);
+    if (rc) return rc;
+  } else
+#endif
+  {
+    VPHO_LAUNCH(k_time_term, dim3((dn.hid + 255) / 256), dim3(256), 0, st, dn, ws, mode, s);
+    VPHO_LAUNCH(k_pose_encoder, dim3(ws.Npad / kPeRows), dim3(256), 0, st, dn, ws, mode, s);
+  }
   profile_end(VPHO_TAG_POSE_ENCODER, st);
   const int tag = dn.n_heads >= 16 ? VPHO_TAG_HEAD_GEMM_HAND : VPHO_TAG_HEAD_GEMM_OBJ;
   profile_begin(tag, st);
   if (ws.P2hi) {
 #ifndef VPHO_EMU
     if (dh.mapA_for != ws.P2hi || dh.mapA_rows != ws.Npad) {
-      if (!tc_make_map(&dh.mapA_hi, ws.P2hi, ws.Npad, 128) || !tc_make_map(&dh.mapA_lo, ws.P2lo, ws.Npad, 128)) return VPHO_ERR_LAUNCH;
+      if (!tc_make_map(&dh.mapA_hi, ws.P2hi, ws.Npad, 128, kPDim) || !tc_make_map(&dh.mapA_lo, ws.P2lo, ws.Npad, 128, kPDim)) return VPHO_ERR_LAUNCH;
       dh.mapA_for = ws.P2hi;
       dh.mapA_rows = ws.Npad;
     }
@@ -762,11 +799,36 @@ extern "C" int vpho_denoiser_create(int n_heads, const float* fourier_W, const f
         cudaMemcpy(dh->w_lo, wlo.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
       cudaFree(dh->w_hi); cudaFree(dh->w_lo); cudaFree(dh->blob); delete dh; return VPHO_ERR_ALLOC;
     }
-    if (!tc_make_map(&dh->mapB_hi, dh->w_hi, hid, 256) || !tc_make_map(&dh->mapB_lo, dh->w_lo, hid, 256)) {
+    if (!tc_make_map(&dh->mapB_hi, dh->w_hi, hid, 256, kPDim) || !tc_make_map(&dh->mapB_lo, dh->w_lo, hid, 256, kPDim)) {
       cudaFree(dh->w_hi); cudaFree(dh->w_lo); cudaFree(dh->blob); delete dh; return VPHO_ERR_LAUNCH;
     }
     d.Wa_p_hi = dh->w_hi; d.Wa_p_lo = dh->w_lo;
     dh->use_tc = true;
+    // pose encoder planes (VPHO_POSE_ENCODER=simt keeps the FP32-SIMT kernel)
+    const char* selp = getenv("VPHO_POSE_ENCODER");
+    if (!(selp && strcmp(selp, "simt") == 0)) {
+      const int kp1 = (D + 31) / 32 * 32;
+      const size_t n1 = (size_t)256 * kp1, n2 = (size_t)256 * 256;
+      std::vector<float> pl(2 * n1 + 2 * n2, 0.f);
+      for (int o = 0; o < 256; ++o) {
+        for (int k = 0; k < D; ++k) {
+          const float w = p1_w[(size_t)o * D + k], hi = tf32_round(w);
+          pl[(size_t)o * kp1 + k] = hi;
+          pl[n1 + (size_t)o * kp1 + k] = tf32_round(w - hi);
+        }
+        for (int k = 0; k < 256; ++k) {
+          const float w = p2_w[(size_t)o * 256 + k], hi = tf32_round(w);
+          pl[2 * n1 + (size_t)o * 256 + k] = hi;
+          pl[2 * n1 + n2 + (size_t)o * 256 + k] = tf32_round(w - hi);
+        }
+      }
+      if (cudaMalloc((void**)&dh->pe_planes, pl.size() * sizeof(float)) == cudaSuccess &&
+          cudaMemcpy(dh->pe_planes, pl.data(), pl.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
+          tc_make_map(&dh->mapW1_hi, dh->pe_planes, 256, 256, kp1) && tc_make_map(&dh->mapW1_lo, dh->pe_planes + n1, 256, 256, kp1) &&
+          tc_make_map(&dh->mapW2_hi, dh->pe_planes + 2 * n1, 256, 256, 256) &&
+          tc_make_map(&dh->mapW2_lo, dh->pe_planes + 2 * n1 + n2, 256, 256, 256))
+        dh->use_tc_pose = true;
+    }
   }
 #endif
   *out = dh;
@@ -779,6 +841,7 @@ extern "C" int vpho_denoiser_destroy(vpho_denoiser_t h) {
   cudaFree(dh->blob);
   if (dh->w_hi) cudaFree(dh->w_hi);
   if (dh->w_lo) cudaFree(dh->w_lo);
+  if (dh->pe_planes) cudaFree(dh->pe_planes);
   delete dh;
   return VPHO_OK;
 }

@@ -78,6 +78,9 @@ struct SamplerWs {
   float* P2T;      // [256][Npad] pose features, k-major (FP32-SIMT head GEMM)
   float* P2hi;     // [Npad][256] pose features split for 3xTF32, row-major = K-major (tcgen05 head GEMM); nullptr = SIMT
   float* P2lo;
+  float* Xhi;      // [Npad][Kx] stage input split for 3xTF32 (Kx = D rounded up to 32), tcgen05 pose encoder only
+  float* Xlo;
+  int Kx;
   double* y;       // [n]
   double* ynew;    // [n]
   double* K;       // [7][n]

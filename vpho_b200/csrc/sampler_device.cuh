@@ -101,4 +101,25 @@ __device__ __forceinline__ void emit_score(const SamplerWs& ws, RkCtrl& c, const
   ws.K[(size_t)slot * c.n + i] = -(et.coef * (double)score);
 }
 
+
+// Input of one network evaluation for element (row, d): the float64 RK combination that scipy hands to `fun`
+// (rk.py rk_step / common.py select_initial_step), or the raw state / stand-alone input.  Returns 0 for padding rows.
+// Side effect: the 7th stage (s == 6) stores y_new.
+__device__ __forceinline__ double stage_input(const SamplerWs& ws, const RkCtrl& c, int mode, int s, int row, int d, int n_rows,
+                                              int D) {
+  if (row >= n_rows) return 0.0;
+  const int i = row * D + d, n = c.n;
+  if (mode == kModeEval) return (double)ws.eval_x[i];
+  const double y = ws.y[i];
+  if (mode == kModeInit0 || mode == kModeFinal) return y;
+  if (mode == kModeInit1) return __dadd_rn(y, __dmul_rn(c.h0 * c.direction, kval(ws.K, c, 0, n, i)));
+  // dy = np.dot(K[:s].T, a[:s]) * h ; y + dy          (rk.py rk_step)
+  double acc = 0.0;
+  const int ns = (s == 6) ? 6 : s;
+  for (int j = 0; j < ns; ++j) acc += kval(ws.K, c, j, n, i) * kA[s][j];
+  const double v = __dadd_rn(y, __dmul_rn(acc, c.h));
+  if (s == 6) ws.ynew[i] = v;
+  return v;
+}
+
 }  // namespace vpho

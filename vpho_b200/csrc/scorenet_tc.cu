@@ -247,6 +247,187 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   }
 }
 
+// =====================================================================================================================
+// Pose encoder on tensor cores: P2 = relu(relu(X.W1 + b1).W2 + b2) for one 128-row tile per CTA, both GEMMs as 3xTF32.
+//   input    X (hi, lo) planes [Npad][Kx] written by k_stage_x (float64 RK stage combination, all SMs), loaded by TMA;
+//   GEMM 1   D1[128x256] (TMEM cols 0..255) = X . W1, W1 (hi, lo) chunks of 32 k streamed by TMA;
+//   re-stage compute warps read D1 32 columns at a time (tcgen05.ld), add b1, ReLU, split, and write the next A operand
+//            chunk of GEMM 2 (double-buffered, reusing the X region) while the MMA lane consumes the previous one;
+//   GEMM 2   D2[128x256] (TMEM cols 256..511) = H1 . W2;  epilogue: + b2, ReLU, split -> P2hi / P2lo (row-major).
+// =====================================================================================================================
+constexpr int kPtMaxK1Chunks = 3;                         // D <= 96
+constexpr int kPtRegionA = kPtMaxK1Chunks * 2 * kTcABytes;   // X hi/lo chunks, later 2 x (H1 hi/lo chunk): 96 KB
+constexpr int kPtStageB = 2 * kTcBBytes;                  // W (hi, lo) chunk: 64 KB
+
+struct PtSmem {
+  unsigned char a[kPtRegionA];
+  unsigned char b[2][kPtStageB];
+  unsigned long long full_bar[2], empty_bar[2], a_full_bar[2], a_empty_bar[2], d1_full_bar, d2_full_bar, x_full_bar;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t sw128_offset(int r, int k) {     // byte offset of element (row r, k) in a [rows][32 f32] tile
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + (k & 3) * 4);
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+          const __grid_constant__ CUtensorMap tmW1_hi, const __grid_constant__ CUtensorMap tmW1_lo,
+          const __grid_constant__ CUtensorMap tmW2_hi, const __grid_constant__ CUtensorMap tmW2_lo, DenoiserDev dn, SamplerWs ws,
+          int mode, int s) {
+  const RkCtrl& c = *ws.ctrl;
+  if (!eval_active(c, mode)) return;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  PtSmem& sm = *reinterpret_cast<PtSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = dn.D, nk1 = (D + kTcBK - 1) / kTcBK;
+  const int r0 = blockIdx.x * kTcBM;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.full_bar[i], 1); mbar_init(&sm.empty_bar[i], 1);
+      mbar_init(&sm.a_full_bar[i], 128); mbar_init(&sm.a_empty_bar[i], 1);
+    }
+    mbar_init(&sm.d1_full_bar, 1); mbar_init(&sm.d2_full_bar, 1); mbar_init(&sm.x_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+  const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      // the whole X tile (A operand of GEMM 1) has a dedicated region: issue it at once
+      mbar_arrive_expect_tx(&sm.x_full_bar, (uint32_t)(nk1 * 2 * kTcABytes));
+      for (int j = 0; j < nk1; ++j) {
+        tma_load_2d(&tmX_hi, &sm.x_full_bar, sm.a + (size_t)j * 2 * kTcABytes, j * kTcBK, r0);
+        tma_load_2d(&tmX_lo, &sm.x_full_bar, sm.a + (size_t)j * 2 * kTcABytes + kTcABytes, j * kTcBK, r0);
+      }
+      for (int j = 0; j < nk1 + 8; ++j) {
+        mbar_wait(&sm.empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&sm.full_bar[stage], kPtStageB);
+        if (j < nk1) {
+          tma_load_2d(&tmW1_hi, &sm.full_bar[stage], sm.b[stage], j * kTcBK, 0);
+          tma_load_2d(&tmW1_lo, &sm.full_bar[stage], sm.b[stage] + kTcBBytes, j * kTcBK, 0);
+        } else {
+          tma_load_2d(&tmW2_hi, &sm.full_bar[stage], sm.b[stage], (j - nk1) * kTcBK, 0);
+          tma_load_2d(&tmW2_lo, &sm.full_bar[stage], sm.b[stage] + kTcBBytes, (j - nk1) * kTcBK, 0);
+        }
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto mma_chunk = [&](uint32_t d_tmem, const unsigned char* a_hi_p, const unsigned char* a_lo_p, bool first) {
+        const uint64_t a_hi = make_kmajor_sw128_desc(a_hi_p), a_lo = make_kmajor_sw128_desc(a_lo_p);
+        const uint64_t b_hi = make_kmajor_sw128_desc(sm.b[stage]), b_lo = make_kmajor_sw128_desc(sm.b[stage] + kTcBBytes);
+#pragma unroll
+        for (int k = 0; k < kTcBK / kTcUmmaK; ++k) {
+          const uint64_t adv = (uint64_t)((k * kTcUmmaK * 4) >> 4);
+          umma_tf32(d_tmem, a_lo + adv, b_hi + adv, kTcIdesc, (first && k == 0) ? 0u : 1u);
+          umma_tf32(d_tmem, a_hi + adv, b_lo + adv, kTcIdesc, 1u);
+          umma_tf32(d_tmem, a_hi + adv, b_hi + adv, kTcIdesc, 1u);
+        }
+      };
+      mbar_wait(&sm.x_full_bar, 0);
+      for (int kc = 0; kc < nk1; ++kc) {
+        mbar_wait(&sm.full_bar[stage], phase);
+        tc_fence_after();
+        const unsigned char* chunk = sm.a + (size_t)kc * 2 * kTcABytes;
+        mma_chunk(d1, chunk, chunk + kTcABytes, kc == 0);
+        umma_commit(&sm.empty_bar[stage]);
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&sm.d1_full_bar);
+      for (int kc = 0; kc < 8; ++kc) {
+        const int ab = kc & 1;
+        mbar_wait(&sm.full_bar[stage], phase);
+        mbar_wait(&sm.a_full_bar[ab], (uint32_t)((kc >> 1) & 1));
+        tc_fence_after();
+        const unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
+        mma_chunk(d2, chunk, chunk + kTcABytes, kc == 0);
+        umma_commit(&sm.empty_bar[stage]);
+        umma_commit(&sm.a_empty_bar[ab]);
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&sm.d2_full_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4, r = q * 32 + lane;          // this thread's row of the tile == its TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    mbar_wait(&sm.d1_full_bar, 0);
+    tc_fence_after();
+    for (int kc = 0; kc < 8; ++kc) {
+      const int ab = kc & 1;
+      mbar_wait(&sm.a_empty_bar[ab], (uint32_t)(((kc >> 1) & 1) ^ 1));
+      uint32_t v[32];
+      tmem_ld32(d1 + lane_addr + (uint32_t)(kc * 32), v);
+      unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 32 + u * 4));
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float hv = fmaxf(__uint_as_float(v[u * 4 + e]) + bb[e], 0.f);
+          hi[e] = tf32_rna(hv);
+          lo[e] = tf32_rna(hv - hi[e]);
+        }
+        const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((u ^ (r & 7)) & 7) << 4));
+        *reinterpret_cast<float4*>(chunk + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(chunk + kTcABytes + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(&sm.a_full_bar[ab]);
+    }
+    mbar_wait(&sm.d2_full_bar, 0);
+    tc_fence_after();
+    float* dh = ws.P2hi + (size_t)(r0 + r) * kPDim;
+    float* dl = ws.P2lo + (size_t)(r0 + r) * kPDim;
+    for (int cb = 0; cb < 8; ++cb) {
+      uint32_t v[32];
+      tmem_ld32(d2 + lane_addr + (uint32_t)(cb * 32), v);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(dn.b2 + cb * 32 + u * 4));
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pv = fmaxf(__uint_as_float(v[u * 4 + e]) + bb[e], 0.f);
+          hi[e] = tf32_rna(pv);
+          lo[e] = tf32_rna(pv - hi[e]);
+        }
+        *reinterpret_cast<float4*>(dh + cb * 32 + u * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(dl + cb * 32 + u * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
 // -------------------------------------------------------------------------------------------------- host side
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -261,13 +442,13 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-// 2-D K-major f32 tensor [rows][256] -> boxes of {32 k, box_rows}, 128-byte swizzle
-bool tc_make_map(void* map_out, const float* base, int rows, int box_rows) {
+// 2-D K-major f32 tensor [rows][kdim] -> boxes of {32 k, box_rows}, 128-byte swizzle
+bool tc_make_map(void* map_out, const float* base, int rows, int box_rows, int kdim) {
   CUtensorMap* map = static_cast<CUtensorMap*>(map_out);
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   if (!enc) return false;
-  cuuint64_t gdim[2] = {(cuuint64_t)kPDim, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)kPDim * 4};
+  cuuint64_t gdim[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)kdim * 4};
   cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
@@ -298,6 +479,23 @@ int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi
   VPHO_LAUNCH(k_head_tc, dim3(grid), dim3(kTcThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
               *static_cast<const CUtensorMap*>(mapA_lo), *static_cast<const CUtensorMap*>(mapB_hi),
               *static_cast<const CUtensorMap*>(mapB_lo), dn, ws, mode, s);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
+
+
+int tc_launch_pose(const void* mapX_hi, const void* mapX_lo, const void* mapW1_hi, const void* mapW1_lo, const void* mapW2_hi,
+                   const void* mapW2_lo, const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, cudaStream_t st) {
+  static bool attr = false;
+  const int smem = (int)sizeof(PtSmem) + 1024;
+  if (!attr) {
+    if (cudaFuncSetAttribute(k_pose_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return VPHO_ERR_LAUNCH;
+    attr = true;
+  }
+  VPHO_LAUNCH(k_pose_tc, dim3(ws.Npad / kTcBM), dim3(kTcThreads), smem, st, *static_cast<const CUtensorMap*>(mapX_hi),
+              *static_cast<const CUtensorMap*>(mapX_lo), *static_cast<const CUtensorMap*>(mapW1_hi),
+              *static_cast<const CUtensorMap*>(mapW1_lo), *static_cast<const CUtensorMap*>(mapW2_hi),
+              *static_cast<const CUtensorMap*>(mapW2_lo), dn, ws, mode, s);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }

@@ -12,19 +12,29 @@ unsigned long long g_launches = 0;
 static bool g_profile = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events[VPHO_NUM_TAGS];
 static cudaEvent_t g_open[VPHO_NUM_TAGS];
+static std::vector<cudaEvent_t> g_pool;     // events are recycled: creating one per launch costs more than the launch
+
+static cudaEvent_t take_event() {
+  if (g_pool.empty()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  cudaEvent_t e = g_pool.back();
+  g_pool.pop_back();
+  return e;
+}
 
 void profile_begin(int tag, cudaStream_t st) {
   if (!g_profile) return;
-  cudaEvent_t e;
-  cudaEventCreate(&e);
+  cudaEvent_t e = take_event();
   cudaEventRecord(e, st);
   g_open[tag] = e;
 }
 
 void profile_end(int tag, cudaStream_t st) {
   if (!g_profile) return;
-  cudaEvent_t e;
-  cudaEventCreate(&e);
+  cudaEvent_t e = take_event();
   cudaEventRecord(e, st);
   g_events[tag].push_back({g_open[tag], e});
 }
@@ -52,8 +62,8 @@ extern "C" int vpho_profile_collect(int tag, double* total_ms, int* n_launches) 
     cudaEventElapsedTime(&ms, pr.first, pr.second);
     tot += ms;
     ++n;
-    cudaEventDestroy(pr.first);
-    cudaEventDestroy(pr.second);
+    g_pool.push_back(pr.first);
+    g_pool.push_back(pr.second);
   }
   g_events[tag].clear();
   *total_ms = tot;

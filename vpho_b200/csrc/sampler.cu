@@ -167,10 +167,14 @@ __global__ void __launch_bounds__(256) k_feat_term(DenoiserDev dn, const float* 
 // ------------------------------------------------------------------------------------------------------------
 // time-term: Fourier embedding -> t_encoder -> Tt[col] = sum_k t_feat[k] Wa_t[k][col]   (one per network call)
 // ------------------------------------------------------------------------------------------------------------
+// One block = 64 output columns of Tt.  The 128-long contraction over t_feat is split over 4 thread groups (32 k each,
+// all loads in flight at once) and summed in a fixed order, so the latency is one L2 round trip instead of 128.
+constexpr int kTtCols = 64;
 __device__ __forceinline__ void time_term_block(const DenoiserDev& dn, const SamplerWs& ws, const RkCtrl& c, int mode, int s,
                                                 int block) {
   __shared__ float four[kTDim];
   __shared__ float tfeat[kTDim];
+  __shared__ float part[4][kTtCols];
   const int tid = threadIdx.x;
   const EvalTime et = eval_time(c, mode, s);
   if (tid < 64) {
@@ -181,19 +185,27 @@ __device__ __forceinline__ void time_term_block(const DenoiserDev& dn, const Sam
   }
   __syncthreads();
   if (tid < kTDim) {
-    float a = 0.f;
-    for (int k = 0; k < kTDim; ++k) a = fmaf(four[k], dn.Wt[k * kTDim + tid], a);
-    a += dn.bt[tid];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < kTDim; k += 4) {
+      a0 = fmaf(four[k + 0], __ldg(dn.Wt + (k + 0) * kTDim + tid), a0);
+      a1 = fmaf(four[k + 1], __ldg(dn.Wt + (k + 1) * kTDim + tid), a1);
+      a2 = fmaf(four[k + 2], __ldg(dn.Wt + (k + 2) * kTDim + tid), a2);
+      a3 = fmaf(four[k + 3], __ldg(dn.Wt + (k + 3) * kTDim + tid), a3);
+    }
+    const float a = ((a0 + a1) + (a2 + a3)) + dn.bt[tid];
     tfeat[tid] = a > 0.f ? a : 0.f;
   }
   __syncthreads();
-  const int col = block * 256 + tid;
+  const int g = tid >> 6, cl = tid & 63, col = block * kTtCols + cl;
+  float a = 0.f;
   if (col < dn.hid) {
-    float a = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < kTDim; ++k) a = fmaf(tfeat[k], __ldg(dn.Wa_t + (size_t)k * dn.hid + col), a);
-    ws.Tt[col] = a;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a = fmaf(tfeat[g * 32 + k], __ldg(dn.Wa_t + (size_t)(g * 32 + k) * dn.hid + col), a);
   }
+  part[g][cl] = a;
+  __syncthreads();
+  if (tid < kTtCols && col < dn.hid) ws.Tt[col] = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
 }
 
 __global__ void __launch_bounds__(256) k_time_term(DenoiserDev dn, SamplerWs ws, int mode, int s) {
@@ -668,7 +680,7 @@ static int launch_eval(DenoiserHost& dh, const SamplerWs& ws, int mode, int s, c
   profile_begin(VPHO_TAG_POSE_ENCODER, st);
 #ifndef VPHO_EMU
   if (ws.P2hi && dh.use_tc_pose) {
-    const int nb_time = (dn.hid + 255) / 256;
+    const int nb_time = (dn.hid + kTtCols - 1) / kTtCols;
     int nb_x = (ws.Npad * ws.Kx + 1023) / 1024;           // ~4 elements per thread
     if (nb_x > 592) nb_x = 592;
     VPHO_LAUNCH(k_stage_x, dim3(nb_time + nb_x), dim3(256), 0, st, dn, ws, mode, s, nb_time);
@@ -682,7 +694,7 @@ static int launch_eval(DenoiserHost& dh, const SamplerWs& ws, int mode, int s, c
   } else
 #endif
   {
-    VPHO_LAUNCH(k_time_term, dim3((dn.hid + 255) / 256), dim3(256), 0, st, dn, ws, mode, s);
+    VPHO_LAUNCH(k_time_term, dim3((dn.hid + kTtCols - 1) / kTtCols), dim3(256), 0, st, dn, ws, mode, s);
     VPHO_LAUNCH(k_pose_encoder, dim3(ws.Npad / kPeRows), dim3(256), 0, st, dn, ws, mode, s);
   }
   profile_end(VPHO_TAG_POSE_ENCODER, st);

@@ -258,7 +258,8 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     ms_res, wall_res, launches, last = timed(step_resident, args.steps, profile=True)
     prof = {}
     for tag, name in ((0, "head_gemm_hand"), (1, "head_gemm_obj"), (2, "pose_encoder"), (3, "mano_skinning"),
-                      (4, "physics3_scan"), (5, "hand_heat_score")):
+                      (4, "physics3_scan"), (5, "hand_heat_score"), (6, "stage_x_time_term"), (7, "feat_term"),
+                      (8, "rk_control"), (9, "hoi_aggregate_total")):
         tot, n = C.c_double(0), C.c_int(0)
         lib.c.vpho_profile_collect(tag, C.byref(tot), C.byref(n))
         prof[name] = {"ms_total": tot.value, "launches": n.value}

@@ -28,7 +28,8 @@ int vpho_version(void);
 /* Bookkeeping for benchmarks: number of kernels this library has launched since it was loaded, and optional CUDA-event
  * brackets around tagged kernels (recorded on the launching stream).  vpho_profile_collect synchronises on the recorded
  * events of `tag`, returns their summed duration and count, and clears them.
- * tags: 0 hand head-GEMM, 1 object head-GEMM, 2 pose encoder, 3 MANO skinning, 4 physics3 scan, 5 hand heat-map scorer */
+ * tags: 0 hand head-GEMM, 1 object head-GEMM, 2 pose encoder (incl. 6), 3 MANO skinning, 4 physics3 scan, 5 hand heat-map
+ * scorer, 6 stage-input + time-term, 7 feat-term, 8 RK error norm / controller / dense output, 9 whole vpho_hoi_aggregate */
 unsigned long long vpho_launch_count(void);
 int vpho_profile_enable(int on);
 int vpho_profile_collect(int tag, double* total_ms, int* n_launches);

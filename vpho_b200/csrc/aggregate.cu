@@ -825,8 +825,9 @@ extern "C" int vpho_hoi_aggregate(vpho_mano_t mano, vpho_assets_t assets, const 
   if (kk > nmax) nmax = kk;
   if (nc > nmax) nmax = nc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (nmax <= 256) return run_hoi<8>(m, as, h, st);
-  if (nmax <= 512) return run_hoi<16>(m, as, h, st);
-  if (nmax <= 1024) return run_hoi<32>(m, as, h, st);
-  return VPHO_ERR_INVALID;
+  if (nmax > 1024) return VPHO_ERR_INVALID;
+  profile_begin(VPHO_TAG_AGGREGATE, st);
+  const int rc = nmax <= 256 ? run_hoi<8>(m, as, h, st) : (nmax <= 512 ? run_hoi<16>(m, as, h, st) : run_hoi<32>(m, as, h, st));
+  profile_end(VPHO_TAG_AGGREGATE, st);
+  return rc;
 }

@@ -683,7 +683,9 @@ static int launch_eval(DenoiserHost& dh, const SamplerWs& ws, int mode, int s, c
     const int nb_time = (dn.hid + kTtCols - 1) / kTtCols;
     int nb_x = (ws.Npad * ws.Kx + 1023) / 1024;           // ~4 elements per thread
     if (nb_x > 592) nb_x = 592;
+    profile_begin(VPHO_TAG_STAGE_X, st);
     VPHO_LAUNCH(k_stage_x, dim3(nb_time + nb_x), dim3(256), 0, st, dn, ws, mode, s, nb_time);
+    profile_end(VPHO_TAG_STAGE_X, st);
     if (dh.mapX_for != ws.Xhi || dh.mapX_rows != ws.Npad) {
       if (!tc_make_map(&dh.mapX_hi, ws.Xhi, ws.Npad, 128, ws.Kx) || !tc_make_map(&dh.mapX_lo, ws.Xlo, ws.Npad, 128, ws.Kx)) return VPHO_ERR_LAUNCH;
       dh.mapX_for = ws.Xhi;
@@ -725,8 +727,10 @@ static int launch_attempts(DenoiserHost& dh, const SamplerWs& ws, int n, int max
       int rc = launch_eval(dh, ws, kModeStage, s, st);
       if (rc) return rc;
     }
+    profile_begin(VPHO_TAG_RK_CONTROL, st);
     VPHO_LAUNCH(k_reduce, dim3(rb), dim3(256), 0, st, ws, (int)kRedErr);
     VPHO_LAUNCH(k_post_step, dim3(rb), dim3(256), 0, st, ws);
+    profile_end(VPHO_TAG_RK_CONTROL, st);
     VPHO_CHECK_LAUNCH();
   }
   return VPHO_OK;
@@ -900,7 +904,9 @@ extern "C" int vpho_sample_begin(vpho_denoiser_t h, const float* feat, int n_row
   if (n_rows == 0) return VPHO_OK;
   const int rb = red_blocks(n);
   VPHO_LAUNCH(k_init_state, dim3(rb), dim3(256), 0, st, ws, init_x, n);
+  profile_begin(VPHO_TAG_FEAT_TERM, st);
   VPHO_LAUNCH(k_feat_term, dim3(dn.hid / kFtCols, (ws.R + kFtRows - 1) / kFtRows), dim3(256), 0, st, dn, feat, ws.R, ws.F);
+  profile_end(VPHO_TAG_FEAT_TERM, st);
   VPHO_CHECK_LAUNCH();
   int rc = launch_eval(dh, ws, kModeInit0, 0, st);
   if (rc) return rc;

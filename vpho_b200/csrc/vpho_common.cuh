@@ -46,7 +46,11 @@ inline void cp_async_wait() {}
 #define VPHO_TAG_MANO_FULL 3
 #define VPHO_TAG_PHYSICS3 4
 #define VPHO_TAG_HAND_SCORE 5
-#define VPHO_NUM_TAGS 6
+#define VPHO_TAG_STAGE_X 6
+#define VPHO_TAG_FEAT_TERM 7
+#define VPHO_TAG_RK_CONTROL 8
+#define VPHO_TAG_AGGREGATE 9
+#define VPHO_NUM_TAGS 10
 
 #define VPHO_OK 0
 #define VPHO_ERR_INVALID (-1)

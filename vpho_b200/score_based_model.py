@@ -100,6 +100,36 @@ def _unique_feat(data: dict, n_rows: int):
     return feat, 1
 
 
+class PendingSample:
+    """Status of one enqueued sample(); `resolve` interprets the controller's counters once they are on the host."""
+
+    def __init__(self, agent, denoiser, counters, n_rows, attempts_enqueued, keep_alive):
+        self.agent, self.denoiser, self.counters, self.n_rows = agent, denoiser, counters, n_rows
+        self.attempts_enqueued = attempts_enqueued
+        self._keep_alive = keep_alive      # inputs read by stream-ordered kernels
+        self.info: dict = {}
+
+    def resolve(self, c=None) -> bool:
+        """True: the integration finished and the outputs are valid.  False: it needs more attempts than were enqueued
+        (the hint is raised; re-issue the sample).  Raises on a failed integration."""
+        if c is None:
+            c = self.counters.cpu().tolist() if self.n_rows else [1, 0, 0, 0, 0, 0, 0, 0]
+        self.info = {"status": c[0], "nfev": c[1], "accepted": c[2], "rejected": c[3], "nan": bool(c[4]),
+                     "attempts": c[5], "net_calls": c[1] + 1}
+        self.agent.last_info = self.info
+        self.denoiser.calls = c[1] + 1
+        if c[0] < 0:
+            raise capi.VphoError("RK45: required step size is less than spacing between numbers")
+        if c[0] == 0:
+            self.denoiser.attempts_hint = max(self.attempts_enqueued, c[5]) + 4
+            return False
+        if c[4]:
+            print("\033[31mWarning: NaN detected in score evaluation. \033[0m")   # score_based_model.py:70
+        # steady state: enqueue what the last batch needed plus one spare attempt (20 no-op launches)
+        self.denoiser.attempts_hint = max(1, c[5]) + (1 if self.agent.spare_attempt else 0)
+        return True
+
+
 class ScoreBasedModelAgent:
     """Drop-in for the evaluation-time methods of the reference's `ScoreBasedModelAgent`."""
 
@@ -112,6 +142,7 @@ class ScoreBasedModelAgent:
         self.sampling_eps = SAMPLING_EPS
         self.T = 1.0
         self.first_attempts = first_attempts
+        self.spare_attempt = False     # VphoHotPath enables it together with deferred status checks
         self.last_info: dict = {}
 
     def prior_fn(self, shape, T):
@@ -120,8 +151,14 @@ class ScoreBasedModelAgent:
 
     @torch.no_grad()
     def sample(self, data: dict, denoiser: Denoiser, T0: float, init_x: Optional[torch.Tensor] = None,
-               return_inprocess: bool = True, prior: Optional[torch.Tensor] = None):
-        """-> (in_process (N, steps, D) float64 [permuted view, as the reference returns it], final (N, D) float64)."""
+               return_inprocess: bool = True, prior: Optional[torch.Tensor] = None, defer_check: bool = False):
+        """-> (in_process (N, steps, D) float64 [permuted view, as the reference returns it], final (N, D) float64).
+
+        The integration runs entirely on the device.  By default the 8-int status word is read back before returning
+        (one host sync) and more RK attempts are enqueued if the controller has not reached t = eps yet.  With
+        `defer_check=True` nothing is read back: a third value, a `PendingSample`, is returned and the caller must call
+        `resolve()` on it once the stream has been synchronised for another reason (VphoHotPath.predict does this once
+        per batch); `resolve()` says whether the outputs are valid or the sample has to be re-issued."""
         device = (data["feat_unique"] if "feat_unique" in data else data["feat"]).device
         D = denoiser.out_dim
         n_rows = int(data["n_rows"]) if "n_rows" in data else int(data["feat"].shape[0])
@@ -140,13 +177,17 @@ class ScoreBasedModelAgent:
         x = torch.empty((n_rows, D), dtype=torch.float64, device=device)
         counters = torch.zeros(8, dtype=torch.int32, device=device)
         stream = capi.stream_of(x0)
+        hint = getattr(denoiser, "attempts_hint", None) or self.first_attempts
         st = lib.c.vpho_sample_begin(denoiser.handle, capi.ptr(feat), n_rows, rpf, capi.ptr(x0), float(T0),
-                                     float(self.sampling_eps), None, n_eval, RTOL, ATOL, MAX_STEP, n_eval,
-                                     self.first_attempts, capi.ptr(xs), capi.ptr(x), capi.ptr(counters), capi.ptr(ws),
-                                     ws.numel(), stream)
+                                     float(self.sampling_eps), None, n_eval, RTOL, ATOL, MAX_STEP, n_eval, hint,
+                                     capi.ptr(xs), capi.ptr(x), capi.ptr(counters), capi.ptr(ws), ws.numel(), stream)
         lib.check(st, "vpho_sample_begin")
         lib.check(lib.c.vpho_sample_finish(denoiser.handle, n_rows, rpf, n_eval, capi.ptr(ws), ws.numel(), stream),
                   "vpho_sample_finish")
+        pending = PendingSample(self, denoiser, counters, n_rows, hint, (feat, x0))
+        xs_view = None if xs is None else xs.permute(1, 0, 2)
+        if defer_check:
+            return xs_view, x, pending
         while True:
             c = counters.cpu().tolist() if n_rows else [1, 0, 0, 0, 0, 0, 0, 0]
             if c[0] != 0:
@@ -155,17 +196,8 @@ class ScoreBasedModelAgent:
                                                  stream), "vpho_sample_continue")
             lib.check(lib.c.vpho_sample_finish(denoiser.handle, n_rows, rpf, n_eval, capi.ptr(ws), ws.numel(), stream),
                       "vpho_sample_finish")
-        self.last_info = {"status": c[0], "nfev": c[1], "accepted": c[2], "rejected": c[3], "nan": bool(c[4]),
-                          "attempts": c[5], "net_calls": c[1] + 1}
-        denoiser.calls = c[1] + 1
-        if c[0] < 0:
-            raise capi.VphoError("RK45: required step size is less than spacing between numbers")
-        if c[4]:
-            print("\033[31mWarning: NaN detected in score evaluation. \033[0m")   # score_based_model.py:70
-        self.first_attempts = max(1, c[5])   # steady state: enqueue exactly what the last batch needed
-        if xs is None:
-            return None, x
-        return xs.permute(1, 0, 2), x
+        pending.resolve(c)
+        return xs_view, x
 
     def get_score(self, data, denoiser):
         return denoiser(data)

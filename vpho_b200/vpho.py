@@ -65,6 +65,28 @@ class VphoHotPath:
     @torch.no_grad()
     def predict(self, batch: Dict, *, prior_hand: Optional[torch.Tensor] = None, prior_obj: Optional[torch.Tensor] = None,
                 with_inprocess: bool = True) -> Dict:
+        """The whole batch is enqueued without a host synchronisation; the two samplers' status words are read once at
+        the end.  If an integration needed more RK attempts than were enqueued (the hint adapts to the previous batch,
+        plus one spare), the batch is re-issued with a larger budget -- rare, and the results are identical."""
+        if prior_hand is None or prior_obj is None:
+            # draw both priors up front, in the reference's order (hand, then object), so a re-issue reuses them
+            from .score_based_model import ve_prior_std
+            S, bs = self.sample_num, batch["encoding_hand"].shape[0]
+            if prior_hand is None:
+                prior_hand = torch.randn(bs * S, self.denoiser_hand.out_dim) * ve_prior_std(self.sample_T0)
+            if prior_obj is None:
+                prior_obj = torch.randn(bs * S, self.denoiser_obj.out_dim) * ve_prior_std(self.sample_T0)
+        self.score_agent.spare_attempt = True
+        for _ in range(8):
+            pd, pend = self._predict_once(batch, prior_hand, prior_obj, with_inprocess)
+            status = torch.stack([p.counters for p in pend]).cpu().tolist()     # the one host sync of the batch
+            ok = [p.resolve(c) for p, c in zip(pend, status)]
+            self.last_info = {"hand": pend[0].info, "obj": pend[1].info}
+            if all(ok):
+                return pd
+        raise capi.VphoError("sampler did not converge within the attempt budget")
+
+    def _predict_once(self, batch: Dict, prior_hand, prior_obj, with_inprocess: bool):
         """batch: tensors on the CUDA device (see `to_device`).  prior_* (optional): randn*sigma(T0) draws, (bs*S, 96) and
         (bs*S, 9); when omitted they are drawn from torch's global CPU generator in the reference's order (hand, object)."""
         S = self.sample_num
@@ -73,9 +95,9 @@ class VphoHotPath:
         pd_mano_pose, pd_mano_shape = batch["pd_mano_pose"], batch["pd_mano_shape"]
         pd = {"hand_heatmap": batch["hm_hand"], "obj_heatmap": batch["hm_obj"], "force_local": batch["force_local"]}
 
-        xs_h, x_h = self.score_agent.sample({"feat_unique": enc_h, "n_rows": bs * S}, self.denoiser_hand, self.sample_T0,
-                                            return_inprocess=with_inprocess, prior=prior_hand)
-        info_h = dict(self.score_agent.last_info)
+        xs_h, x_h, pend_h = self.score_agent.sample({"feat_unique": enc_h, "n_rows": bs * S}, self.denoiser_hand,
+                                                    self.sample_T0, return_inprocess=with_inprocess, prior=prior_hand,
+                                                    defer_check=True)
         inproc, final_mano = self.postprocess_diffusion_hand(xs_h, x_h, pd_mano_shape)
         pd["diff_final_hand_mano"] = final_mano.reshape(bs, S, 58)
         if with_inprocess:
@@ -87,9 +109,9 @@ class VphoHotPath:
         pd["diff_final_hand_vert"] = fv.reshape(bs, S, 778, 3)
         pd["diff_final_hand_joint"] = fj.reshape(bs, S, 21, 3)
 
-        xs_o, x_o = self.score_agent.sample({"feat_unique": enc_o, "n_rows": bs * S}, self.denoiser_obj, self.sample_T0,
-                                            return_inprocess=with_inprocess, prior=prior_obj)
-        info_o = dict(self.score_agent.last_info)
+        xs_o, x_o, pend_o = self.score_agent.sample({"feat_unique": enc_o, "n_rows": bs * S}, self.denoiser_obj,
+                                                    self.sample_T0, return_inprocess=with_inprocess, prior=prior_obj,
+                                                    defer_check=True)
         if with_inprocess:
             pd["diff_inprocess_obj_6d"] = xs_o.reshape(bs, S, -1, 9)
         pd["diff_final_obj_6d"] = x_o.reshape(bs, S, 9)
@@ -107,8 +129,7 @@ class VphoHotPath:
         pd["agg_hand_vert"] = sel["hand_agg_vert"]
         pd["agg_hand_joint"] = sel["hand_agg_joint"]
         pd["_sel"] = sel
-        self.last_info = {"hand": info_h, "obj": info_o}
-        return pd
+        return pd, (pend_h, pend_o)
 
     __call__ = predict
 

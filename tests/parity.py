@@ -9,6 +9,10 @@ from __future__ import annotations
 import torch
 
 NEAR_TIE_RTOL = 2e-5
+# Physics scores are built from anchor->surface distances of ~1 mm measured in camera coordinates (|x| ~ 0.6 m, FP32 ulp
+# 6e-8 m): one ulp of a coordinate is already 6e-5 of such a distance, so any FP32 implementation (including the
+# reference on another device) carries ~1e-4 relative noise in these scores.
+NEAR_TIE_RTOL_PHYSICS = 1e-3
 
 
 def topk_agreement(ours_idx: torch.Tensor, oracle_idx: torch.Tensor, oracle_scores: torch.Tensor, rtol=NEAR_TIE_RTOL):
@@ -50,12 +54,12 @@ def check_hoi_against_oracle(out: dict, dbg: dict, oracle: dict, *, pos_tol=2e-6
     rep = {"lists": 0, "exact": 0, "near_tie": 0}
     clean = torch.ones(bs, dtype=torch.bool)      # images whose every selection matched exactly
 
-    def account(ours, ref_idx, ref_sc, name):
+    def account(ours, ref_idx, ref_sc, name, rtol=NEAR_TIE_RTOL):
         nl = ours.reshape(-1, ours.shape[-1]).shape[0]
         per_img = nl // bs
         for b in range(bs):
             e, n, bad = topk_agreement(ours.reshape(bs, per_img, -1)[b], ref_idx.reshape(bs, per_img, -1)[b],
-                                       ref_sc.reshape(bs, per_img, -1)[b])
+                                       ref_sc.reshape(bs, per_img, -1)[b], rtol)
             assert bad == 0, f"{name}: image {b} selected candidates whose oracle scores are not within the near-tie band"
             rep["lists"] += e + n
             rep["exact"] += e
@@ -69,8 +73,10 @@ def check_hoi_against_oracle(out: dict, dbg: dict, oracle: dict, *, pos_tol=2e-6
     for i, (nm, snm) in enumerate([("obj_transl_topk", "obj_transl_score"), ("obj_rot_topk", "obj_rot_score"),
                                    ("phys_topk", "phys_score"), ("heat5_topk", "heat5_score")]):
         k = od[nm].shape[1]
-        account(dbg["obj_topk"][i, :, :k].cpu()[:, None], od[nm][:, None], od[snm][:, None], nm)
-    account(dbg["finger_topk"].cpu(), od["finger_topk"], od["finger_score"], "hand physics finger top-k")
+        account(dbg["obj_topk"][i, :, :k].cpu()[:, None], od[nm][:, None], od[snm][:, None], nm,
+                NEAR_TIE_RTOL_PHYSICS if nm == "phys_topk" else NEAR_TIE_RTOL)
+    account(dbg["finger_topk"].cpu(), od["finger_topk"], od["finger_score"], "hand physics finger top-k",
+            NEAR_TIE_RTOL_PHYSICS)
     rep["clean_images"] = int(clean.sum())
     # values, on the images where every selection matched exactly
     if clean.any():

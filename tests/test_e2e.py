@@ -54,7 +54,7 @@ def _check(hp, pd, ref, batch, assets, kind):
     loose = kind == "random"
     rep = parity.check_hoi_against_oracle(pd["_sel"], hp.hoi_aggregator.last_debug, ref["_sel"],
                                           pos_tol=5e-4 if loose else 2e-6, pose_tol=1.0 if loose else 5e-5,
-                                          obj_tol=1e-3 if loose else 1e-6, cand_tol=2e-5)
+                                          obj_tol=1e-3 if loose else 1e-5, cand_tol=2e-5)
     if not loose and rep["clean_images"] == bs:
         # final pose error vs a synthetic ground truth (TesterHand MJE/MVE test.py:657-679, ADD test.py:441-442)
         om, oo = O.OracleMano(mano), O.OracleObject(objs)
@@ -101,3 +101,29 @@ def test_e2e_cuda_default_prior_uses_global_cpu_generator(cuda_lib):
     assert torch.equal(pd1["diff_final_hand_mano"], pd2["diff_final_hand_mano"])
     assert torch.equal(pd1["diff_final_obj_6d"], pd2["diff_final_obj_6d"])
     assert torch.equal(pd1["agg_hand_vert"], pd2["agg_hand_vert"])
+
+
+@pytest.mark.gpu
+def test_e2e_cuda_reissues_when_the_attempt_budget_is_too_small(cuda_lib):
+    """Deferred status checks: a batch whose integration needs more RK attempts than were enqueued is re-issued with a
+    larger budget and must give the same answer as a run that had enough from the start."""
+    mano, anch, objs = cases.assets()
+    batch = syn.make_eval_batch(2, seed=7, sample_num=16, mano=mano, objects=objs)
+    st_h, st_o = syn.make_denoiser_state("mano_pose", 0), syn.make_denoiser_state("obj", 0, last_std=3.0)   # stiff object
+    ph, po = cases.e2e_priors("clustered", 2, 16, batch, 7)
+    outs = []
+    for first in (1, 12):
+        hp = VphoHotPath(mano, anch, objs, st_h, st_o, sample_num=16, sampling_steps=7, topk_hand=6, topk_obj=4)
+        hp.score_agent.first_attempts = first
+        pd = hp.predict(to_device(batch, "cuda"), prior_hand=ph, prior_obj=po)
+        assert hp.last_info["obj"]["attempts"] > 1 and hp.last_info["obj"]["status"] == 1
+        outs.append(pd)
+    for k in ("diff_final_obj_6d", "diff_final_hand_mano", "agg_obj_6d", "agg_hand_vert"):
+        assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+@pytest.mark.gpu
+def test_e2e_cuda_single_image_readme_shape(cuda_lib):
+    # BASELINE config 0: batch 1 x 100 samples x 50 steps
+    hp, pd, ref, batch, assets = _run(None, "cuda", "clustered", 1, 100, 30, 10, 50, seed=11)
+    _check(hp, pd, ref, batch, assets, "clustered")

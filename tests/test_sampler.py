@@ -110,3 +110,68 @@ def test_sampler_cuda_readme_batch_runs(cuda_lib):
         _, x = agent.sample({"feat_unique": enc.cuda(), "n_rows": 6400}, den, 0.65, return_inprocess=False)
         outs.append(x)
     assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
+
+
+def _nan_state(head="obj"):
+    st = syn.make_denoiser_state(head, 3, last_std=0.05)
+    st["head.head.2.bias"] = st["head.head.2.bias"].copy()
+    st["head.head.2.bias"][1, 2] = np.nan        # one output dimension of every row becomes NaN
+    return st
+
+
+def _check_nan_semantics(lib, dev):
+    """NaN scores are replaced by 0 inside the ODE right-hand side (score_based_model.py:69-71) but NOT in the final
+    predictor step (:95-104), so the affected dimension keeps its prior value through the integration and ends NaN."""
+    st = _nan_state()
+    den, od = Denoiser(st, lib=lib), O.OracleDenoiser(st)
+    g = torch.Generator().manual_seed(1)
+    feat = torch.relu(torch.randn(6, 1024, generator=g))
+    agent = ScoreBasedModelAgent(sampling_steps=7, sample_num=0)
+    torch.manual_seed(3)
+    xs, x = agent.sample({"feat": feat.to(dev)}, den, 0.65)
+    torch.manual_seed(3)
+    init = torch.randn(6, 9) * ve_prior_std(0.65)
+    xs2, x2, info = O.oracle_sample(od, feat, 0.65, init, 7)
+    assert agent.last_info["nan"] and info["nan"]
+    assert agent.last_info["nfev"] == info["nfev"]
+    xs, x = xs.cpu(), x.cpu()
+    assert torch.equal(torch.isnan(x), torch.isnan(x2)) and torch.isnan(x[:, 5]).all()
+    assert not torch.isnan(xs).any() and not torch.isnan(xs2).any()
+    ok = ~torch.isnan(x2)
+    assert ((x[ok] - x2[ok]).abs() <= 2e-5 * x2[ok].abs().clamp(min=1)).all()
+    assert ((xs - xs2).abs() <= 2e-5 * xs2.abs().clamp(min=1)).all()
+    assert torch.equal(xs[:, -1, 5].float(), init[:, 5])          # the NaN dimension never moved during the ODE
+
+
+def test_sampler_emulated_nan_scores_follow_reference_semantics(emu_lib):
+    _check_nan_semantics(emu_lib, "cpu")
+
+
+@pytest.mark.gpu
+def test_sampler_cuda_nan_scores_follow_reference_semantics(cuda_lib):
+    _check_nan_semantics(None, "cuda")
+
+
+@pytest.mark.gpu
+def test_sampler_cuda_empty_batch(cuda_lib):
+    den = Denoiser(syn.make_denoiser_state("obj", 0))
+    agent = ScoreBasedModelAgent(5, 0)
+    xs, x = agent.sample({"feat": torch.zeros(0, 1024, device="cuda")}, den, 0.65)
+    assert tuple(x.shape) == (0, 9) and tuple(xs.shape) == (0, 5, 9)
+
+
+@pytest.mark.gpu
+def test_sampler_cuda_simt_and_tensor_core_paths_agree(cuda_lib):
+    import os
+    st = syn.make_denoiser_state("mano_pose", 0)
+    os.environ["VPHO_HEAD_GEMM"], os.environ["VPHO_POSE_ENCODER"] = "simt", "simt"
+    d_simt = Denoiser(st)
+    os.environ.pop("VPHO_HEAD_GEMM"), os.environ.pop("VPHO_POSE_ENCODER")
+    d_tc = Denoiser(st)
+    g = torch.Generator().manual_seed(0)
+    enc = torch.relu(torch.randn(5, 1024, generator=g)).cuda()
+    x = (torch.randn(500, 96, generator=g) * 2.5).cuda()
+    for t in (0.65, 0.1):
+        data = {"feat_unique": enc, "sampled_pose": x, "t": torch.full((500, 1), t, device="cuda")}
+        a, b = d_tc(data), d_simt(data)
+        assert ((a - b).norm() / b.norm()).item() < 5e-7        # 3xTF32 keeps FP32-class accuracy

@@ -26,6 +26,8 @@ namespace vpho {
 // tcgen05 path (scorenet_tc.cu)
 bool tc_available();
 bool tc_make_map(void* map, const float* base, int rows, int box_rows, int kdim);
+int tc_launch_feat(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const float* feat,
+                   float* feat_hi, float* feat_lo, const float* ba, float* F, int R, int hid, cudaStream_t st);
 int tc_launch_pose(const void* mapX_hi, const void* mapX_lo, const void* mapW1_hi, const void* mapW1_lo, const void* mapW2_hi,
                    const void* mapW2_lo, const DenoiserDev& dn,
                    const SamplerWs& ws, int mode, int s, cudaStream_t st);
@@ -46,6 +48,12 @@ struct DenoiserHost {
   bool use_tc_pose = false;
   float* pe_planes = nullptr;
   TensorMapBlob mapW1_hi, mapW1_lo, mapW2_hi, mapW2_lo, mapX_hi, mapX_lo;
+  // tcgen05 feat-term: K-major hi/lo planes of the conditioning slice of head.0 [hid][1024]
+  bool use_tc_feat = false;
+  float* wf_planes = nullptr;
+  TensorMapBlob mapWf_hi, mapWf_lo, mapF_hi, mapF_lo;
+  const float* mapF_for = nullptr;
+  int mapF_rows = 0;
   const float* mapX_for = nullptr;
   int mapX_rows = 0;
   const float* mapA_for = nullptr;   // P2hi pointer the cached A maps were built for
@@ -124,26 +132,30 @@ __global__ void k_set_eval_time(SamplerWs ws, float t32) {
 // ------------------------------------------------------------------------------------------------------------
 // feat-term: F[r][col] = sum_k feat[r][k] Wa_f[k][col] + ba[col]       (once per sample(); R = images)
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kFtRows = 32, kFtCols = 128, kFtK = 32;
+constexpr int kFtRows = 32, kFtCols = 128, kFtK = 32, kFtSplit = 4;
 
-__global__ void __launch_bounds__(256) k_feat_term(DenoiserDev dn, const float* __restrict__ feat, int R, float* __restrict__ F) {
+// split-K: blockIdx.z owns K slice [z*256, z*256+256) and writes its partial sums to Fpart[z]; k_feat_sum adds the four
+// partials in a fixed order plus the bias.  FP32 FMA accumulation throughout (the tensor-core variant accumulates with
+// truncation over a 384-instruction chain, which costs ~1 decimal digit on this K = 1024 contraction).
+__global__ void __launch_bounds__(256) k_feat_term(DenoiserDev dn, const float* __restrict__ feat, int R, float* __restrict__ Fpart) {
   __shared__ __align__(16) float fs[kFtK][kFtRows];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int c0 = blockIdx.x * kFtCols, r0 = blockIdx.y * kFtRows;
   const int hid = dn.hid;
+  const int kbeg = blockIdx.z * (kFDim / kFtSplit), kend = kbeg + kFDim / kFtSplit;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < kFDim; k0 += kFtK) {
+  for (int k0 = kbeg; k0 < kend; k0 += kFtK) {
     __syncthreads();
     for (int it = tid; it < kFtK * kFtRows; it += 256) {
       const int r = it / kFtK, k = it % kFtK;
       fs[k][r] = (r0 + r < R) ? feat[(size_t)(r0 + r) * kFDim + k0 + k] : 0.f;
     }
     __syncthreads();
-#pragma unroll 8
+#pragma unroll 16
     for (int k = 0; k < kFtK; ++k) {
       const float4 f = *reinterpret_cast<const float4*>(&fs[k][4 * ty]);
       const float4 w = __ldg(reinterpret_cast<const float4*>(dn.Wa_f + (size_t)(k0 + k) * hid + c0 + 4 * tx));
@@ -154,13 +166,27 @@ __global__ void __launch_bounds__(256) k_feat_term(DenoiserDev dn, const float* 
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(fr[i], wc[j], acc[i][j]);
     }
   }
-  const float4 b = __ldg(reinterpret_cast<const float4*>(dn.ba + c0 + 4 * tx));
+  float* dst = Fpart + (size_t)blockIdx.z * R * hid;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = r0 + 4 * ty + i;
     if (r >= R) continue;
-    float4 o = make_float4(acc[i][0] + b.x, acc[i][1] + b.y, acc[i][2] + b.z, acc[i][3] + b.w);
-    *reinterpret_cast<float4*>(F + (size_t)r * hid + c0 + 4 * tx) = o;
+    *reinterpret_cast<float4*>(dst + (size_t)r * hid + c0 + 4 * tx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
+}
+
+__global__ void k_feat_sum(DenoiserDev dn, const float* __restrict__ Fpart, int R, float* __restrict__ F) {
+  const size_t n4 = (size_t)R * dn.hid / 4, stride = (size_t)R * dn.hid / 4;
+  const float4* p = reinterpret_cast<const float4*>(Fpart);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = p[i], b = p[i + stride], c = p[i + 2 * stride], d = p[i + 3 * stride];
+    const float4 bias = __ldg(reinterpret_cast<const float4*>(dn.ba) + (i % (dn.hid / 4)));
+    float4 o;
+    o.x = ((a.x + b.x) + (c.x + d.x)) + bias.x;
+    o.y = ((a.y + b.y) + (c.y + d.y)) + bias.y;
+    o.z = ((a.z + b.z) + (c.z + d.z)) + bias.z;
+    o.w = ((a.w + b.w) + (c.w + d.w)) + bias.w;
+    reinterpret_cast<float4*>(F)[i] = o;
   }
 }
 
@@ -638,6 +664,7 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t o_ctrl = take(sizeof(RkCtrl));
   const size_t o_F = take((size_t)R * hid * 4);
+  const size_t o_Fpart = take((size_t)4 * R * hid * 4);
   const size_t o_Tt = take((size_t)hid * 4);
   const size_t o_P2T = take((size_t)kPDim * Npad * 4);
   const size_t o_P2hi = take((size_t)kPDim * Npad * 4);
@@ -645,6 +672,9 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
   const int Kx = (D + 31) / 32 * 32;
   const size_t o_Xhi = take((size_t)Kx * Npad * 4);
   const size_t o_Xlo = take((size_t)Kx * Npad * 4);
+  const size_t Rpad = align_up((size_t)(R > 0 ? R : 1), 128);
+  const size_t o_Fhi = take(Rpad * kFDim * 4);
+  const size_t o_Flo = take(Rpad * kFDim * 4);
   const size_t o_y = take(n * 8);
   const size_t o_yn = take(n * 8);
   const size_t o_K = take(7 * n * 8);
@@ -654,6 +684,7 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
     char* b = static_cast<char*>(base);
     ws->ctrl = reinterpret_cast<RkCtrl*>(b + o_ctrl);
     ws->F = reinterpret_cast<float*>(b + o_F);
+    ws->Fpart = reinterpret_cast<float*>(b + o_Fpart);
     ws->Tt = reinterpret_cast<float*>(b + o_Tt);
     ws->P2T = reinterpret_cast<float*>(b + o_P2T);
     ws->P2hi = use_tc ? reinterpret_cast<float*>(b + o_P2hi) : nullptr;
@@ -661,6 +692,8 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
     ws->Xhi = reinterpret_cast<float*>(b + o_Xhi);
     ws->Xlo = reinterpret_cast<float*>(b + o_Xlo);
     ws->Kx = Kx;
+    ws->FeatHi = reinterpret_cast<float*>(b + o_Fhi);
+    ws->FeatLo = reinterpret_cast<float*>(b + o_Flo);
     ws->y = reinterpret_cast<double*>(b + o_y);
     ws->ynew = reinterpret_cast<double*>(b + o_yn);
     ws->K = reinterpret_cast<double*>(b + o_K);
@@ -674,6 +707,32 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
 }
 
 static int red_blocks(int n) { int b = (n + 255) / 256; return b < 1 ? 1 : (b > kMaxRedBlocks ? kMaxRedBlocks : b); }
+
+static int launch_feat_term(DenoiserHost& dh, const SamplerWs& ws, const float* feat, cudaStream_t st) {
+  const DenoiserDev& dn = dh.dev;
+  profile_begin(VPHO_TAG_FEAT_TERM, st);
+#ifndef VPHO_EMU
+  if (dh.use_tc_feat) {
+    const int Rpad = (ws.R + 127) / 128 * 128;
+    if (dh.mapF_for != ws.FeatHi || dh.mapF_rows != Rpad) {
+      if (!tc_make_map(&dh.mapF_hi, ws.FeatHi, Rpad, 128, kFDim) || !tc_make_map(&dh.mapF_lo, ws.FeatLo, Rpad, 128, kFDim)) return VPHO_ERR_LAUNCH;
+      dh.mapF_for = ws.FeatHi;
+      dh.mapF_rows = Rpad;
+    }
+    int rc = tc_launch_feat(&dh.mapF_hi, &dh.mapF_lo, &dh.mapWf_hi, &dh.mapWf_lo, feat, ws.FeatHi, ws.FeatLo, dn.ba, ws.F, ws.R, dn.hid, st);
+    if (rc) return rc;
+  } else
+#endif
+  {
+    VPHO_LAUNCH(k_feat_term, dim3(dn.hid / kFtCols, (ws.R + kFtRows - 1) / kFtRows, kFtSplit), dim3(256), 0, st, dn, feat, ws.R,
+                ws.Fpart);
+    const int n4 = ws.R * dn.hid / 4;
+    VPHO_LAUNCH(k_feat_sum, dim3((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), dim3(256), 0, st, dn, ws.Fpart, ws.R, ws.F);
+  }
+  profile_end(VPHO_TAG_FEAT_TERM, st);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
 
 static int launch_eval(DenoiserHost& dh, const SamplerWs& ws, int mode, int s, cudaStream_t st) {
   const DenoiserDev& dn = dh.dev;
@@ -845,6 +904,25 @@ extern "C" int vpho_denoiser_create(int n_heads, const float* fourier_W, const f
           tc_make_map(&dh->mapW2_lo, dh->pe_planes + 2 * n1 + n2, 256, 256, 256))
         dh->use_tc_pose = true;
     }
+    // feat-term on tensor cores is opt-in (VPHO_FEAT_TERM=tc): see the accuracy note at k_feat_term
+    const char* self = getenv("VPHO_FEAT_TERM");
+    if (self && strcmp(self, "tc") == 0) {
+      const size_t nf = (size_t)hid * kFDim;
+      std::vector<float> pf(2 * nf);
+      for (int nn = 0; nn < n_heads; ++nn)
+        for (int k = 0; k < kFDim; ++k) {
+          const float* src = ha_w + ((size_t)nn * 1408 + 384 + k) * 256;
+          for (int cc = 0; cc < 256; ++cc) {
+            const float w = src[cc], hi = tf32_round(w);
+            pf[((size_t)nn * 256 + cc) * kFDim + k] = hi;
+            pf[nf + ((size_t)nn * 256 + cc) * kFDim + k] = tf32_round(w - hi);
+          }
+        }
+      if (cudaMalloc((void**)&dh->wf_planes, 2 * nf * sizeof(float)) == cudaSuccess &&
+          cudaMemcpy(dh->wf_planes, pf.data(), 2 * nf * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
+          tc_make_map(&dh->mapWf_hi, dh->wf_planes, hid, 256, kFDim) && tc_make_map(&dh->mapWf_lo, dh->wf_planes + nf, hid, 256, kFDim))
+        dh->use_tc_feat = true;
+    }
   }
 #endif
   *out = dh;
@@ -858,6 +936,7 @@ extern "C" int vpho_denoiser_destroy(vpho_denoiser_t h) {
   if (dh->w_hi) cudaFree(dh->w_hi);
   if (dh->w_lo) cudaFree(dh->w_lo);
   if (dh->pe_planes) cudaFree(dh->pe_planes);
+  if (dh->wf_planes) cudaFree(dh->wf_planes);
   delete dh;
   return VPHO_OK;
 }
@@ -879,8 +958,8 @@ extern "C" int vpho_score_eval(vpho_denoiser_t h, const float* x, float t, const
   cudaStream_t st = (cudaStream_t)stream;
   ws.eval_x = x; ws.eval_out = out;
   VPHO_LAUNCH(k_set_eval_time, dim3(1), dim3(1), 0, st, ws, t);
-  VPHO_LAUNCH(k_feat_term, dim3(dn.hid / kFtCols, (ws.R + kFtRows - 1) / kFtRows), dim3(256), 0, st, dn, feat, ws.R, ws.F);
-  VPHO_CHECK_LAUNCH();
+  int rcf = launch_feat_term(dh, ws, feat, st);
+  if (rcf) return rcf;
   return launch_eval(dh, ws, kModeEval, 0, st);
 }
 
@@ -904,11 +983,9 @@ extern "C" int vpho_sample_begin(vpho_denoiser_t h, const float* feat, int n_row
   if (n_rows == 0) return VPHO_OK;
   const int rb = red_blocks(n);
   VPHO_LAUNCH(k_init_state, dim3(rb), dim3(256), 0, st, ws, init_x, n);
-  profile_begin(VPHO_TAG_FEAT_TERM, st);
-  VPHO_LAUNCH(k_feat_term, dim3(dn.hid / kFtCols, (ws.R + kFtRows - 1) / kFtRows), dim3(256), 0, st, dn, feat, ws.R, ws.F);
-  profile_end(VPHO_TAG_FEAT_TERM, st);
-  VPHO_CHECK_LAUNCH();
-  int rc = launch_eval(dh, ws, kModeInit0, 0, st);
+  int rc = launch_feat_term(dh, ws, feat, st);
+  if (rc) return rc;
+  rc = launch_eval(dh, ws, kModeInit0, 0, st);
   if (rc) return rc;
   VPHO_LAUNCH(k_reduce, dim3(rb), dim3(256), 0, st, ws, (int)kRedInit0);
   rc = launch_eval(dh, ws, kModeInit1, 0, st);

@@ -74,6 +74,7 @@ struct RkCtrl {
 struct SamplerWs {
   RkCtrl* ctrl;
   float* F;        // [R][hid]  feat-term + bias, once per sample()
+  float* Fpart;    // [4][R][hid] split-K partial sums of the feat-term
   float* Tt;       // [hid]     time-term of the current evaluation
   float* P2T;      // [256][Npad] pose features, k-major (FP32-SIMT head GEMM)
   float* P2hi;     // [Npad][256] pose features split for 3xTF32, row-major = K-major (tcgen05 head GEMM); nullptr = SIMT
@@ -81,6 +82,8 @@ struct SamplerWs {
   float* Xhi;      // [Npad][Kx] stage input split for 3xTF32 (Kx = D rounded up to 32), tcgen05 pose encoder only
   float* Xlo;
   int Kx;
+  float* FeatHi;   // [Rpad][1024] conditioning features split for 3xTF32 (tcgen05 feat-term), Rpad = R rounded up to 128
+  float* FeatLo;
   double* y;       // [n]
   double* ynew;    // [n]
   double* K;       // [7][n]

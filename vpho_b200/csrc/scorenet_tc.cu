@@ -428,6 +428,129 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
   }
 }
 
+// =====================================================================================================================
+// Feat-term on tensor cores: F[R][hid] = feat[R][1024] . Wa_f + ba, once per sample().  Same TMA / UMMA / TMEM pipeline
+// as k_head_tc with K = 1024 (32 chunks) and a plain store epilogue; rows >= R of the last 128-row tile are zero padding
+// (written by k_split_planes) and never stored.  Work item = (row tile, 256-column tile).
+// =====================================================================================================================
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_feat_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const float* __restrict__ ba,
+          float* __restrict__ F, int R, int hid) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_ct = hid / kTcBN, n_rt = (R + kTcBM - 1) / kTcBM;
+  const int n_items = n_ct * n_rt;
+  constexpr int kChunks = kFDim / kTcBK;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kTcStages; ++i) { mbar_init(&sm.full_bar[i], 1); mbar_init(&sm.empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full_bar[i], 1); mbar_init(&sm.tmem_empty_bar[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int ct = it % n_ct, rt = it / n_ct;
+        for (int kc = 0; kc < kChunks; ++kc) {
+          mbar_wait(&sm.empty_bar[stage], phase ^ 1);
+          unsigned char* st = sm.stage[stage];
+          mbar_arrive_expect_tx(&sm.full_bar[stage], kTcStageBytes);
+          tma_load_2d(&tmA_hi, &sm.full_bar[stage], st, kc * kTcBK, rt * kTcBM);
+          tma_load_2d(&tmA_lo, &sm.full_bar[stage], st + kTcABytes, kc * kTcBK, rt * kTcBM);
+          tma_load_2d(&tmB_hi, &sm.full_bar[stage], st + 2 * kTcABytes, kc * kTcBK, ct * kTcBN);
+          tma_load_2d(&tmB_lo, &sm.full_bar[stage], st + 2 * kTcABytes + kTcBBytes, kc * kTcBK, ct * kTcBN);
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        mbar_wait(&sm.tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTcBN);
+        for (int kc = 0; kc < kChunks; ++kc) {
+          mbar_wait(&sm.full_bar[stage], phase);
+          tc_fence_after();
+          unsigned char* st = sm.stage[stage];
+          const uint64_t a_hi = make_kmajor_sw128_desc(st), a_lo = make_kmajor_sw128_desc(st + kTcABytes);
+          const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * kTcABytes), b_lo = make_kmajor_sw128_desc(st + 2 * kTcABytes + kTcBBytes);
+#pragma unroll
+          for (int k = 0; k < kTcBK / kTcUmmaK; ++k) {
+            const uint64_t adv = (uint64_t)((k * kTcUmmaK * 4) >> 4);
+            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, kTcIdesc, (kc | k) != 0 ? 1u : 0u);
+            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, kTcIdesc, 1u);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, kTcIdesc, 1u);
+          }
+          umma_commit(&sm.empty_bar[stage]);
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&sm.tmem_full_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int ct = it % n_ct, rt = it / n_ct;
+      mbar_wait(&sm.tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = rt * kTcBM + q * 32 + lane;
+      float* dst = F + (size_t)row * hid + ct * kTcBN;
+#pragma unroll 1
+      for (int cb = 0; cb < kTcBN / 32; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTcBN + cb * 32), v);
+        if (row < R) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ba + ct * kTcBN + cb * 32 + u * 4));
+            *reinterpret_cast<float4*>(dst + cb * 32 + u * 4) =
+                make_float4(__uint_as_float(v[u * 4 + 0]) + b4.x, __uint_as_float(v[u * 4 + 1]) + b4.y,
+                            __uint_as_float(v[u * 4 + 2]) + b4.z, __uint_as_float(v[u * 4 + 3]) + b4.w);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// feat -> (hi, lo) TF32 planes for the A operand of k_feat_tc
+__global__ void k_split_planes(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int n_src, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float x = i < n_src ? src[i] : 0.f, h = tf32_rna(x);      // rows beyond R are zero padding of the last tile
+    hi[i] = h;
+    lo[i] = tf32_rna(x - h);
+  }
+}
+
 // -------------------------------------------------------------------------------------------------- host side
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -483,6 +606,24 @@ int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi
   return VPHO_OK;
 }
 
+
+int tc_launch_feat(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const float* feat,
+                   float* feat_hi, float* feat_lo, const float* ba, float* F, int R, int hid, cudaStream_t st) {
+  static bool attr = false;
+  const int smem = (int)sizeof(TcSmem) + 1024;
+  if (!attr) {
+    if (cudaFuncSetAttribute(k_feat_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return VPHO_ERR_LAUNCH;
+    attr = true;
+  }
+  const int n_src = R * kFDim, n = ((R + kTcBM - 1) / kTcBM) * kTcBM * kFDim;
+  VPHO_LAUNCH(k_split_planes, dim3((n + 1023) / 1024), dim3(256), 0, st, feat, feat_hi, feat_lo, n_src, n);
+  const int n_items = (hid / kTcBN) * ((R + kTcBM - 1) / kTcBM);
+  VPHO_LAUNCH(k_feat_tc, dim3(n_items < 148 ? n_items : 148), dim3(kTcThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
+              *static_cast<const CUtensorMap*>(mapA_lo), *static_cast<const CUtensorMap*>(mapB_hi),
+              *static_cast<const CUtensorMap*>(mapB_lo), ba, F, R, hid);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
 
 int tc_launch_pose(const void* mapX_hi, const void* mapX_lo, const void* mapW1_hi, const void* mapW1_lo, const void* mapW2_hi,
                    const void* mapW2_lo, const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, cudaStream_t st) {

@@ -111,6 +111,17 @@ int vpho_object_points(vpho_assets_t h, const float* pose6d, const int32_t* obj_
 int vpho_force_anchors(vpho_assets_t h, const float* verts, const float* force_local, int n, int group,
                        float* force_point, float* force_global, void* stream);
 
+/* Contact scoring of n posed hands against one object point cloud per `group` consecutive hands (BASELINE config 3).
+ * vpho_anchor_contact: nearest distance of each of the 32 force anchors to obj_points [n/group][n_pts][3] (exact
+ * Euclidean, `nn_for_r_memory_save2` lib/model/aggregation.py:1145-1158) -> dist [n][32] (may be NULL) and the per-finger
+ * physics scores -(w * d * |sum f_hat|) summed over the finger's anchors (`select_by_physics`, aggregation.py:553-590)
+ * -> finger_score [n][5] (may be NULL).
+ * vpho_vertex_contact: nearest distance of every MANO vertex, verts [n][778][3] -> dist [n][778]; a dense stress variant
+ * with no counterpart in the reference. */
+int vpho_anchor_contact(const float* force_point, const float* force_global, const float* obj_points, int n, int group,
+                        int n_pts, float* dist, float* finger_score, void* stream);
+int vpho_vertex_contact(const float* verts, const float* obj_points, int n, int group, int n_pts, float* dist, void* stream);
+
 typedef struct {
   int bs;          /* images in this batch                         */
   int S;           /* sample_num: diffusion candidates per image   */

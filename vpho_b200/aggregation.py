@@ -164,3 +164,31 @@ class HOI_Aggregator:
             dbg["obj_score"] = dbg["obj_score"].reshape(4, bs * omax)
             self.last_debug = dbg
         return out
+
+
+def anchor_contact(force_point: torch.Tensor, force_global: torch.Tensor, obj_points: torch.Tensor,
+                   lib: Optional[capi.Library] = None):
+    """Scoring part of `HandAggregator.select_by_physics` (lib/model/aggregation.py:553-590) for posed hands
+    force_point / force_global (G, C, 32, 3) against obj_points (G, P, 3): -> nearest anchor distances (G, C, 32) and
+    per-finger physics scores (G, C, 5)."""
+    lib = lib or capi.lib()
+    G, Cn = force_point.shape[0], force_point.shape[1]
+    fp, fg = force_point.contiguous().float(), force_global.contiguous().float()
+    ov = obj_points.contiguous().float()
+    dist = torch.empty((G, Cn, 32), dtype=torch.float32, device=fp.device)
+    score = torch.empty((G, Cn, 5), dtype=torch.float32, device=fp.device)
+    lib.check(lib.c.vpho_anchor_contact(capi.ptr(fp), capi.ptr(fg), capi.ptr(ov), G * Cn, Cn, ov.shape[1], capi.ptr(dist),
+                                        capi.ptr(score), capi.stream_of(fp)), "vpho_anchor_contact")
+    return dist, score
+
+
+def vertex_contact(verts: torch.Tensor, obj_points: torch.Tensor, lib: Optional[capi.Library] = None):
+    """Dense stress variant: nearest object-point distance of every MANO vertex.  verts (G, C, 778, 3), obj_points
+    (G, P, 3) -> (G, C, 778)."""
+    lib = lib or capi.lib()
+    G, Cn = verts.shape[0], verts.shape[1]
+    v, ov = verts.contiguous().float(), obj_points.contiguous().float()
+    dist = torch.empty((G, Cn, 778), dtype=torch.float32, device=v.device)
+    lib.check(lib.c.vpho_vertex_contact(capi.ptr(v), capi.ptr(ov), G * Cn, Cn, ov.shape[1], capi.ptr(dist),
+                                        capi.stream_of(v)), "vpho_vertex_contact")
+    return dist

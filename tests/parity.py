@@ -54,12 +54,18 @@ def check_hoi_against_oracle(out: dict, dbg: dict, oracle: dict, *, pos_tol=2e-6
     rep = {"lists": 0, "exact": 0, "near_tie": 0}
     clean = torch.ones(bs, dtype=torch.bool)      # images whose every selection matched exactly
 
-    def account(ours, ref_idx, ref_sc, name, rtol=NEAR_TIE_RTOL):
+    def account(ours, ref_idx, ref_sc, name, rtol=NEAR_TIE_RTOL, downstream=False):
+        """downstream=True: this selection ranks candidates that were BUILT from earlier selections (the 31 hand-physics
+        candidates take their DIP parameters from the level-3 top-k lists, aggregation.py:1306-1320).  On an image where
+        an earlier list already differed by a near-tie, the candidate sets themselves differ, so the lists are reported
+        as near-ties without comparing scores."""
         nl = ours.reshape(-1, ours.shape[-1]).shape[0]
         per_img = nl // bs
         for b in range(bs):
             e, n, bad = topk_agreement(ours.reshape(bs, per_img, -1)[b], ref_idx.reshape(bs, per_img, -1)[b],
                                        ref_sc.reshape(bs, per_img, -1)[b], rtol)
+            if downstream and not clean[b]:
+                n, bad = n + bad, 0
             assert bad == 0, f"{name}: image {b} selected candidates whose oracle scores are not within the near-tie band"
             rep["lists"] += e + n
             rep["exact"] += e
@@ -76,7 +82,7 @@ def check_hoi_against_oracle(out: dict, dbg: dict, oracle: dict, *, pos_tol=2e-6
         account(dbg["obj_topk"][i, :, :k].cpu()[:, None], od[nm][:, None], od[snm][:, None], nm,
                 NEAR_TIE_RTOL_PHYSICS if nm == "phys_topk" else NEAR_TIE_RTOL)
     account(dbg["finger_topk"].cpu(), od["finger_topk"], od["finger_score"], "hand physics finger top-k",
-            NEAR_TIE_RTOL_PHYSICS)
+            NEAR_TIE_RTOL_PHYSICS, downstream=True)
     rep["clean_images"] = int(clean.sum())
     # values, on the images where every selection matched exactly
     if clean.any():

@@ -79,8 +79,9 @@ def check_hoi_against_oracle(out: dict, dbg: dict, oracle: dict, *, pos_tol=2e-6
     for i, (nm, snm) in enumerate([("obj_transl_topk", "obj_transl_score"), ("obj_rot_topk", "obj_rot_score"),
                                    ("phys_topk", "phys_score"), ("heat5_topk", "heat5_score")]):
         k = od[nm].shape[1]
+        # the recombined K x K candidates are built from the translation / rotation lists (aggregation.py:1235-1242)
         account(dbg["obj_topk"][i, :, :k].cpu()[:, None], od[nm][:, None], od[snm][:, None], nm,
-                NEAR_TIE_RTOL_PHYSICS if nm == "phys_topk" else NEAR_TIE_RTOL)
+                NEAR_TIE_RTOL_PHYSICS if nm == "phys_topk" else NEAR_TIE_RTOL, downstream=i >= 2)
     account(dbg["finger_topk"].cpu(), od["finger_topk"], od["finger_score"], "hand physics finger top-k",
             NEAR_TIE_RTOL_PHYSICS, downstream=True)
     rep["clean_images"] = int(clean.sum())

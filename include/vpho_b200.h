@@ -122,6 +122,16 @@ int vpho_anchor_contact(const float* force_point, const float* force_global, con
                         int n_pts, float* dist, float* finger_score, void* stream);
 int vpho_vertex_contact(const float* verts, const float* obj_points, int n, int group, int n_pts, float* dist, void* stream);
 
+/* Pseudo-force evaluation (BASELINE config 5): the forward math of one iteration of `ForceOptimizer.optimize_batch`
+ * (lib/engine/force_optimization.py:141-171) for n posed hands.  verts [n][778][3] camera frame; scale [n][32];
+ * weight [n][32][8] (pre-softmax); contact_mask [n][32] u8 or NULL; force_contact [n][32] or NULL; cone_anchor [8][3] the
+ * `HeadPhysics.anchor` buffer with its xy already scaled by the friction coefficient (lib/model/physics.py:549-550,692-698);
+ * gravity, com [n/group][3].  terms [n][4] = {|sum f + g|, (sum f).(-g), |sum (p - CoM) x f|, mean_j (log|c_j/s_j| mask_j)^2};
+ * optional outputs force_local / force_point / force_global [n][32][3]. */
+int vpho_force_eval(vpho_assets_t h, const float* verts, const float* scale, const float* weight, const uint8_t* contact_mask,
+                    const float* force_contact, const float* cone_anchor, const float* gravity, const float* com, int n, int group,
+                    float* terms, float* force_local, float* force_point, float* force_global, void* stream);
+
 typedef struct {
   int bs;          /* images in this batch                         */
   int S;           /* sample_num: diffusion candidates per image   */

@@ -625,6 +625,45 @@ def oracle_predict(batch: dict, den_hand: OracleDenoiser, den_obj: OracleDenoise
     return out
 
 
+def cone_anchor_table(friction_coeff: float = 0.8) -> torch.Tensor:
+    """`HeadPhysics.anchor` (lib/model/physics.py:692-698) with xy scaled as get_local_force does (:549-550)."""
+    num_anchor = 8
+    a = torch.arange(0, 2 * torch.pi, 2 * torch.pi / num_anchor)[:num_anchor]
+    anchor = torch.stack([torch.cos(a), torch.sin(a), torch.ones_like(a)], dim=-1) / num_anchor
+    anchor = anchor.clone()
+    anchor[:, :2] *= friction_coeff
+    return anchor
+
+
+def get_local_force(scale: torch.Tensor, weight: torch.Tensor, friction_coeff: float = 0.8):
+    """HeadPhysics.get_local_force (lib/model/physics.py:546-557)."""
+    scale = torch.abs(scale)
+    weight = torch.softmax(weight, dim=-1)
+    anchor = cone_anchor_table(friction_coeff)[None, :].repeat_interleave(scale.size(-1), dim=0)
+    direction = torch.einsum("...ij,ijk->...ik", weight, anchor)
+    direction = direction / (direction.norm(dim=-1, keepdim=True) + 1e-8)
+    return direction * scale[..., None]
+
+
+def force_eval_terms(anchors: "OracleAnchors", vert3d, scale, weight, contact_mask, force_contact, gravity, com):
+    """Per-sample forward terms of one ForceOptimizer iteration (lib/engine/force_optimization.py:141-171), before the
+    batch means and loss weights: |sum f + g|, (sum f).(-g), |sum (p - CoM) x f|, mean_j (log|c_j/s_j| mask_j)^2.
+    vert3d (n,778,3); scale (n,32); weight (n,32,8); contact_mask (n,32) bool; force_contact (n,32); gravity, com (n,1,3)."""
+    scale = scale * contact_mask
+    force_local = get_local_force(scale, weight)
+    force_point, force_global = anchors.from_local_to_global(force_local, vert3d)
+    resultant = (force_global.sum(1, keepdim=True) + gravity).squeeze(1)
+    t0 = torch.norm(resultant, dim=-1)
+    t1 = torch.einsum("...i,...i->...", force_global.sum(1, keepdim=True), -1 * gravity).squeeze(-1)
+    moment = torch.cross(force_point - com, force_global, dim=-1).sum(1)
+    t2 = torch.norm(moment, dim=-1)
+    scale_norm = scale / (scale.norm(dim=-1, keepdim=True) + 1e-8)
+    fc_norm = force_contact / (force_contact.norm(dim=-1, keepdim=True) + 1e-8)
+    dist = torch.log(torch.abs(fc_norm / (scale_norm + 1e-8)) + 1e-8) * contact_mask
+    t3 = (dist ** 2).mean(dim=-1)
+    return torch.stack([t0, t1, t2, t3], dim=-1), force_local, force_point, force_global
+
+
 def hand_pose_error_mm(pd_joint, gt_joint, pd_vert, gt_vert):
     """MJE / MVE as in TesterHand (lib/engine/test.py:657-679): mean Euclidean distance, metres -> mm."""
     mje = (pd_joint - gt_joint).norm(dim=-1).mean(dim=-1) * 1000

@@ -192,3 +192,34 @@ def vertex_contact(verts: torch.Tensor, obj_points: torch.Tensor, lib: Optional[
     lib.check(lib.c.vpho_vertex_contact(capi.ptr(v), capi.ptr(ov), G * Cn, Cn, ov.shape[1], capi.ptr(dist),
                                         capi.stream_of(v)), "vpho_vertex_contact")
     return dist
+
+
+def cone_anchor_table(friction_coeff: float = 0.8) -> torch.Tensor:
+    """The 8 friction-cone anchors of `HeadPhysics` (lib/model/physics.py:692-698) with xy scaled by the friction
+    coefficient as `get_local_force` does (:549-550); a constant table, built with the same torch ops."""
+    a = torch.arange(0, 2 * torch.pi, 2 * torch.pi / 8)[:8]
+    anchor = torch.stack([torch.cos(a), torch.sin(a), torch.ones_like(a)], dim=-1) / 8
+    anchor[:, :2] *= friction_coeff
+    return anchor.contiguous()
+
+
+def force_eval(assets: Assets, vert3d: torch.Tensor, scale: torch.Tensor, weight: torch.Tensor,
+               contact_mask: Optional[torch.Tensor], force_contact: Optional[torch.Tensor], gravity: torch.Tensor,
+               com: torch.Tensor, return_forces: bool = False):
+    """Forward math of one `ForceOptimizer.optimize_batch` iteration (lib/engine/force_optimization.py:141-171) per posed
+    hand: vert3d (n,778,3), scale (n,32), weight (n,32,8), contact_mask (n,32) bool, force_contact (n,32), gravity / com
+    (n,1,3) or (n,3) -> terms (n,4) [+ force_local, force_point, force_global (n,32,3)]."""
+    lib = assets.lib
+    v = vert3d.reshape(-1, 778, 3).contiguous().float()
+    n, dev = v.shape[0], v.device
+    sc, w = scale.contiguous().float(), weight.contiguous().float()
+    m = None if contact_mask is None else contact_mask.to(torch.uint8).contiguous()
+    fc = None if force_contact is None else force_contact.contiguous().float()
+    g, c = gravity.reshape(n, 3).contiguous().float(), com.reshape(n, 3).contiguous().float()
+    cone = cone_anchor_table().to(dev)
+    terms = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    outs = [torch.empty((n, 32, 3), dtype=torch.float32, device=dev) if return_forces else None for _ in range(3)]
+    lib.check(lib.c.vpho_force_eval(assets.handle, capi.ptr(v), capi.ptr(sc), capi.ptr(w), capi.ptr(m), capi.ptr(fc),
+                                    capi.ptr(cone), capi.ptr(g), capi.ptr(c), n, 1, capi.ptr(terms), capi.ptr(outs[0]),
+                                    capi.ptr(outs[1]), capi.ptr(outs[2]), capi.stream_of(v)), "vpho_force_eval")
+    return (terms, *outs) if return_forces else terms

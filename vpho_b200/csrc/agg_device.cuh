@@ -23,6 +23,12 @@ struct AssetsDev {
   const float* com;     // [n_obj][3]
 };
 
+// host-side handle behind vpho_assets_t
+struct AssetsHost {
+  AssetsDev dev;
+  void* blob = nullptr;
+};
+
 // anchor -> (joint a, joint b) bone used for the frame's y axis (physics_fn.py:127-169 after argsort(label))
 __device__ __forceinline__ void anchor_bone(int j, int& ja, int& jb) {
   const unsigned char t[32][2] = {{0, 1},   {2, 3},   {3, 4},   {3, 4},   {3, 4},   {0, 5},   {0, 1},   {5, 6},

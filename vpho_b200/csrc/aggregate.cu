@@ -23,11 +23,6 @@ int mano_forward_dev(const ManoModelDev& m, const float* pose, const float* shap
                      int n, float* verts, float* joints, cudaStream_t stream);
 const ManoModelDev& mano_model_dev(const void* handle);
 
-struct AssetsHost {
-  AssetsDev dev;
-  void* blob = nullptr;
-};
-
 // everything the aggregation kernels need, passed by value
 struct HoiDev {
   vpho_hoi_args a;

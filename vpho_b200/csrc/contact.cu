@@ -89,9 +89,112 @@ __global__ void __launch_bounds__(kCsThreads) k_vertex_contact(const float* __re
   if (v < kVerts) dist[(size_t)i * kVerts + v] = sqrtf(best);
 }
 
+// Pseudo-force evaluation of one posed hand per CTA (BASELINE config 5): the forward math of one iteration of
+// ForceOptimizer.optimize_batch (lib/engine/force_optimization.py:141-171) -- get_local_force (lib/model/physics.py:546-557:
+// softmax over the 8 friction-cone anchors, normalised direction, |scale|), VERT2ANCHOR frames, from_local_to_global, then
+// per hand: |sum f + g|, (sum f).(-g), |sum (p - CoM) x f| and the contact-distribution term mean_j (log|c_j / s_j| * mask_j)^2.
+__global__ void __launch_bounds__(128) k_force_eval(AssetsDev as, const float* __restrict__ verts, const float* __restrict__ scale,
+                                                    const float* __restrict__ weight, const unsigned char* __restrict__ mask,
+                                                    const float* __restrict__ force_contact, const float* __restrict__ cone,
+                                                    const float* __restrict__ gravity, const float* __restrict__ com, int group,
+                                                    float* __restrict__ terms, float* __restrict__ force_local_out,
+                                                    float* __restrict__ point_out, float* __restrict__ force_out) {
+  __shared__ float j21[21 * 3];
+  __shared__ float s_fp[32][3], s_fg[32][3], s_s[32], s_c[32];
+  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* v = verts + (size_t)i * kVerts * 3;
+  for (int o = warp; o < 63; o += 4) {
+    const int k = o / 3, d = o % 3;
+    float acc = 0.f;
+    for (int vv = lane; vv < kVerts; vv += 32) acc = fmaf(as.v2j[k * kVerts + vv], v[vv * 3 + d], acc);
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+    if (lane == 0) j21[o] = acc;
+  }
+  __syncthreads();
+  if (tid < kAnchors) {
+    const int j = tid;
+    const float m = mask ? (mask[(size_t)i * kAnchors + j] ? 1.f : 0.f) : 1.f;
+    const float sc = scale[(size_t)i * kAnchors + j] * m;                      // scale * contact_mask  (:141)
+    const float* w = weight + ((size_t)i * kAnchors + j) * 8;
+    float mx = w[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) mx = fmaxf(mx, w[k]);
+    float e[8], es = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { e[k] = expf(w[k] - mx); es += e[k]; }
+    float dir[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float wk = e[k] / es;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) dir[d] += wk * cone[k * 3 + d];
+    }
+    const float dn = sqrtf((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]) + 1e-8f;
+    float fl[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) fl[d] = (dir[d] / dn) * fabsf(sc);
+    float pt[3], fg[3];
+    anchor_point_and_force(
+        as, j, [&](int vid, float* out) { out[0] = v[vid * 3 + 0]; out[1] = v[vid * 3 + 1]; out[2] = v[vid * 3 + 2]; }, j21, fl, pt,
+        fg);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      s_fp[j][d] = pt[d]; s_fg[j][d] = fg[d];
+      if (force_local_out) force_local_out[((size_t)i * kAnchors + j) * 3 + d] = fl[d];
+      if (point_out) point_out[((size_t)i * kAnchors + j) * 3 + d] = pt[d];
+      if (force_out) force_out[((size_t)i * kAnchors + j) * 3 + d] = fg[d];
+    }
+    s_s[j] = sc;
+    s_c[j] = force_contact ? force_contact[(size_t)i * kAnchors + j] : 0.f;
+    __syncwarp();
+    if (j == 0) {
+      const float* g = gravity + (size_t)(i / group) * 3;
+      const float* cm = com + (size_t)(i / group) * 3;
+      float F[3] = {0.f, 0.f, 0.f}, M[3] = {0.f, 0.f, 0.f}, ss = 0.f, cs = 0.f;
+      for (int k = 0; k < kAnchors; ++k) {
+        const float arm[3] = {s_fp[k][0] - cm[0], s_fp[k][1] - cm[1], s_fp[k][2] - cm[2]};
+        F[0] += s_fg[k][0]; F[1] += s_fg[k][1]; F[2] += s_fg[k][2];
+        M[0] += arm[1] * s_fg[k][2] - arm[2] * s_fg[k][1];
+        M[1] += arm[2] * s_fg[k][0] - arm[0] * s_fg[k][2];
+        M[2] += arm[0] * s_fg[k][1] - arm[1] * s_fg[k][0];
+        ss += s_s[k] * s_s[k];
+        cs += s_c[k] * s_c[k];
+      }
+      const float r[3] = {F[0] + g[0], F[1] + g[1], F[2] + g[2]};
+      float* o = terms + (size_t)i * 4;
+      o[0] = sqrtf((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]);
+      o[1] = (F[0] * (-1.f * g[0]) + F[1] * (-1.f * g[1])) + F[2] * (-1.f * g[2]);
+      o[2] = sqrtf((M[0] * M[0] + M[1] * M[1]) + M[2] * M[2]);
+      float dsum = 0.f;
+      if (force_contact) {
+        const float sn = sqrtf(ss) + 1e-8f, cn = sqrtf(cs) + 1e-8f;
+        for (int k = 0; k < kAnchors; ++k) {
+          const float mk = mask ? (mask[(size_t)i * kAnchors + k] ? 1.f : 0.f) : 1.f;
+          const float dd = logf(fabsf((s_c[k] / cn) / (s_s[k] / sn + 1e-8f)) + 1e-8f) * mk;
+          dsum += dd * dd;
+        }
+      }
+      o[3] = dsum / (float)kAnchors;
+    }
+  }
+}
+
 }  // namespace vpho
 
 using namespace vpho;
+
+extern "C" int vpho_force_eval(vpho_assets_t h, const float* verts, const float* scale, const float* weight, const uint8_t* contact_mask,
+                               const float* force_contact, const float* cone_anchor, const float* gravity, const float* com, int n,
+                               int group, float* terms, float* force_local, float* force_point, float* force_global, void* stream) {
+  if (!h || n < 0 || group <= 0) return VPHO_ERR_INVALID;
+  if (n == 0) return VPHO_OK;
+  if (!verts || !scale || !weight || !cone_anchor || !gravity || !com || !terms) return VPHO_ERR_INVALID;
+  VPHO_LAUNCH(k_force_eval, dim3(n), dim3(128), 0, (cudaStream_t)stream, static_cast<AssetsHost*>(h)->dev, verts, scale, weight,
+              contact_mask, force_contact, cone_anchor, gravity, com, group, terms, force_local, force_point, force_global);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
 
 extern "C" int vpho_anchor_contact(const float* force_point, const float* force_global, const float* obj_points, int n, int group,
                                    int n_pts, float* dist, float* finger_score, void* stream) {

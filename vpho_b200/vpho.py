@@ -36,6 +36,8 @@ class VphoHotPath:
         self.score_agent = ScoreBasedModelAgent(sampling_steps=sampling_steps, sample_num=sample_num)
         self.hoi_aggregator = HOI_Aggregator(self.head_mano, self.assets, debug=debug)
         self.last_info: dict = {}
+        self.overlap_object_sampler = True
+        self._side_stream = None
 
     # ---- vpho_net.postprocess_diffusion_hand, branch 'mano_pose' (VPHO.py:306-331) ----
     def postprocess_diffusion_hand(self, hand_inprocess, hand_final, pd_mano_shape):
@@ -95,6 +97,23 @@ class VphoHotPath:
         pd_mano_pose, pd_mano_shape = batch["pd_mano_pose"], batch["pd_mano_shape"]
         pd = {"hand_heatmap": batch["hm_hand"], "obj_heatmap": batch["hm_obj"], "force_local": batch["force_local"]}
 
+        # The object sampler is independent of the hand branch: it runs on a side stream and fills the SMs the hand
+        # branch leaves idle (its pose-encoder kernel uses 50 CTAs, the object head GEMM 150 work items).
+        main = torch.cuda.current_stream(enc_h.device) if enc_h.is_cuda else None
+        if main is not None and self.overlap_object_sampler:
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=enc_h.device)
+            side = self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                xs_o, x_o, pend_o = self.score_agent.sample({"feat_unique": enc_o, "n_rows": bs * S}, self.denoiser_obj,
+                                                            self.sample_T0, return_inprocess=with_inprocess,
+                                                            prior=prior_obj, defer_check=True)
+            for t in (xs_o, x_o, pend_o.counters):
+                if t is not None:
+                    t.record_stream(main)
+        else:
+            side = None
         xs_h, x_h, pend_h = self.score_agent.sample({"feat_unique": enc_h, "n_rows": bs * S}, self.denoiser_hand,
                                                     self.sample_T0, return_inprocess=with_inprocess, prior=prior_hand,
                                                     defer_check=True)
@@ -109,9 +128,12 @@ class VphoHotPath:
         pd["diff_final_hand_vert"] = fv.reshape(bs, S, 778, 3)
         pd["diff_final_hand_joint"] = fj.reshape(bs, S, 21, 3)
 
-        xs_o, x_o, pend_o = self.score_agent.sample({"feat_unique": enc_o, "n_rows": bs * S}, self.denoiser_obj,
-                                                    self.sample_T0, return_inprocess=with_inprocess, prior=prior_obj,
-                                                    defer_check=True)
+        if side is None:
+            xs_o, x_o, pend_o = self.score_agent.sample({"feat_unique": enc_o, "n_rows": bs * S}, self.denoiser_obj,
+                                                        self.sample_T0, return_inprocess=with_inprocess, prior=prior_obj,
+                                                        defer_check=True)
+        else:
+            main.wait_stream(side)
         if with_inprocess:
             pd["diff_inprocess_obj_6d"] = xs_o.reshape(bs, S, -1, 9)
         pd["diff_final_obj_6d"] = x_o.reshape(bs, S, 9)

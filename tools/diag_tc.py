@@ -11,7 +11,7 @@ from vpho_b200.score_based_model import Denoiser, ScoreBasedModelAgent  # noqa: 
 
 
 def mk(head, mode):
-    os.environ["VPHO_HEAD_GEMM"] = "simt" if mode == "simt" else "tc"
+    os.environ["VPHO_HEAD_GEMM"] = {"simt": "simt", "tf32": "tf32", "tc_head_only": "tf32"}.get(mode, "tc")
     os.environ["VPHO_POSE_ENCODER"] = "simt" if mode in ("simt", "tc_head_only") else "tc"
     return Denoiser(syn.make_denoiser_state(head, 0))
 
@@ -35,7 +35,7 @@ for head, D in (("obj", 9), ("mano_pose", 96)):
                 line += f" | tc-vs-oracle {((a - o).norm() / o.norm()).item():.3e} simt-vs-oracle {((b - o).norm() / o.norm()).item():.3e}"
             print(line, flush=True)
     enc = torch.relu(torch.randn(64, 1024)).cuda()
-    for name, den in (("tc", d_tc), ("tc_head_only", mk(head, "tc_head_only")), ("simt", d_simt)):
+    for name, den in (("tc (3xFP16 head)", d_tc), ("tf32 (3xTF32 head)", mk(head, "tf32")), ("simt", d_simt)):
         agent = ScoreBasedModelAgent(50, 100)
         data = {"feat_unique": enc, "n_rows": 6400}
         for _ in range(3):

@@ -36,7 +36,10 @@ for scale in (0.01, 0.3):
         st["head.head.0.weight"][:, 384:, :] = 0          # conditioning slice off: the K = 256 pose term is everything
     os.environ["VPHO_HEAD_GEMM"], os.environ["VPHO_POSE_ENCODER"] = "simt", "simt"
     d_simt = Denoiser(st)
-    os.environ.pop("VPHO_HEAD_GEMM"), os.environ.pop("VPHO_POSE_ENCODER")
+    os.environ.pop("VPHO_POSE_ENCODER")
+    os.environ["VPHO_HEAD_GEMM"] = "tf32"
+    d_tf32 = Denoiser(st)
+    os.environ.pop("VPHO_HEAD_GEMM")
     d_tc = Denoiser(st)
     g = torch.Generator().manual_seed(0)
     enc = torch.relu(torch.randn(4, 1024, generator=g))
@@ -44,8 +47,8 @@ for scale in (0.01, 0.3):
     feat = enc[:, None].repeat(1, 100, 1).reshape(-1, 1024)
     for t in (0.65, 0.1):
         data = {"feat_unique": enc.cuda(), "sampled_pose": x.cuda(), "t": torch.full((400, 1), t).cuda()}
-        a, b = d_tc(data).cpu().double(), d_simt(data).cpu().double()
+        a, b, c3 = d_tc(data).cpu().double(), d_simt(data).cpu().double(), d_tf32(data).cpu().double()
         r = f64_network(st, x, t, feat)
         n = r.norm()
-        print(f"pose-weight scale {scale} t={t}: tc-vs-f64 {((a - r).norm() / n).item():.3e}  simt-vs-f64 {((b - r).norm() / n).item():.3e}  "
-              f"tc-vs-simt {((a - b).norm() / n).item():.3e}", flush=True)
+        print(f"pose-weight scale {scale} t={t}: fp16x3-vs-f64 {((a - r).norm() / n).item():.3e}  tf32x3-vs-f64 {((c3 - r).norm() / n).item():.3e}  "
+              f"simt-vs-f64 {((b - r).norm() / n).item():.3e}", flush=True)

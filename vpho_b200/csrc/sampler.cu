@@ -20,19 +20,22 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#ifndef VPHO_EMU
+#include <cuda_fp16.h>
+#endif
 
 namespace vpho {
 
 // tcgen05 path (scorenet_tc.cu)
 bool tc_available();
-bool tc_make_map(void* map, const float* base, int rows, int box_rows, int kdim);
+bool tc_make_map(void* map, const void* base, int rows, int box_rows, int kdim, bool half = false);
 int tc_launch_feat(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const float* feat,
                    float* feat_hi, float* feat_lo, const float* ba, float* F, int R, int hid, cudaStream_t st);
 int tc_launch_pose(const void* mapX_hi, const void* mapX_lo, const void* mapW1_hi, const void* mapW1_lo, const void* mapW2_hi,
                    const void* mapW2_lo, const DenoiserDev& dn,
                    const SamplerWs& ws, int mode, int s, cudaStream_t st);
 int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const DenoiserDev& dn,
-                   const SamplerWs& ws, int mode, int s, cudaStream_t st);
+                   const SamplerWs& ws, int mode, int s, bool half, cudaStream_t st);
 
 struct alignas(64) TensorMapBlob { unsigned char b[128]; };
 
@@ -41,8 +44,12 @@ struct DenoiserHost {
   float* blob = nullptr;
   // tcgen05 head GEMM: K-major hi/lo weight planes [hid][256] and their TMA descriptors
   bool use_tc = false;
+  bool use_f16 = false;              // 3xFP16 head GEMM (needs the tensor-core pose encoder, which writes the FP16 planes)
   float* w_hi = nullptr;
   float* w_lo = nullptr;
+  void* w_half = nullptr;            // [2][hid][256] __half (hi, lo) scaled per head + [n_heads] float un-scale factors
+  TensorMapBlob mapBh_hi, mapBh_lo;
+  bool mapA_half = false;
   TensorMapBlob mapB_hi, mapB_lo, mapA_hi, mapA_lo;
   // tcgen05 pose encoder: K-major hi/lo planes of pose_encoder.0 [256][Kpad1] and pose_encoder.2 [256][256]
   bool use_tc_pose = false;
@@ -655,7 +662,8 @@ __global__ void k_rot6d_to_aa(const float* __restrict__ x6d, int n, float* __res
 // ------------------------------------------------------------------------------------------------------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int n_eval, SamplerWs* ws, bool use_tc = true) {
+static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int n_eval, SamplerWs* ws, bool use_tc = true,
+                    bool use_f16 = false) {
   const int D = 3 * n_heads, hid = n_heads * kHeadHid;
   const int R = (n_rows + rows_per_feat - 1) / rows_per_feat;
   const int Npad = (int)align_up((size_t)(n_rows > 0 ? n_rows : 1), kRowTile);
@@ -669,6 +677,7 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
   const size_t o_P2T = take((size_t)kPDim * Npad * 4);
   const size_t o_P2hi = take((size_t)kPDim * Npad * 4);
   const size_t o_P2lo = take((size_t)kPDim * Npad * 4);
+  const size_t o_P2sc = take((size_t)Npad * 4);
   const int Kx = (D + 31) / 32 * 32;
   const size_t o_Xhi = take((size_t)Kx * Npad * 4);
   const size_t o_Xlo = take((size_t)Kx * Npad * 4);
@@ -689,6 +698,7 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
     ws->P2T = reinterpret_cast<float*>(b + o_P2T);
     ws->P2hi = use_tc ? reinterpret_cast<float*>(b + o_P2hi) : nullptr;
     ws->P2lo = use_tc ? reinterpret_cast<float*>(b + o_P2lo) : nullptr;
+    ws->P2scale = (use_tc && use_f16) ? reinterpret_cast<float*>(b + o_P2sc) : nullptr;
     ws->Xhi = reinterpret_cast<float*>(b + o_Xhi);
     ws->Xlo = reinterpret_cast<float*>(b + o_Xlo);
     ws->Kx = Kx;
@@ -763,12 +773,16 @@ static int launch_eval(DenoiserHost& dh, const SamplerWs& ws, int mode, int s, c
   profile_begin(tag, st);
   if (ws.P2hi) {
 #ifndef VPHO_EMU
-    if (dh.mapA_for != ws.P2hi || dh.mapA_rows != ws.Npad) {
-      if (!tc_make_map(&dh.mapA_hi, ws.P2hi, ws.Npad, 128, kPDim) || !tc_make_map(&dh.mapA_lo, ws.P2lo, ws.Npad, 128, kPDim)) return VPHO_ERR_LAUNCH;
+    const bool half = ws.P2scale != nullptr;
+    if (dh.mapA_for != ws.P2hi || dh.mapA_rows != ws.Npad || dh.mapA_half != half) {
+      if (!tc_make_map(&dh.mapA_hi, ws.P2hi, ws.Npad, 128, kPDim, half) || !tc_make_map(&dh.mapA_lo, ws.P2lo, ws.Npad, 128, kPDim, half))
+        return VPHO_ERR_LAUNCH;
       dh.mapA_for = ws.P2hi;
       dh.mapA_rows = ws.Npad;
+      dh.mapA_half = half;
     }
-    int rc = tc_launch_head(&dh.mapA_hi, &dh.mapA_lo, &dh.mapB_hi, &dh.mapB_lo, dn, ws, mode, s, st);
+    int rc = half ? tc_launch_head(&dh.mapA_hi, &dh.mapA_lo, &dh.mapBh_hi, &dh.mapBh_lo, dn, ws, mode, s, true, st)
+                  : tc_launch_head(&dh.mapA_hi, &dh.mapA_lo, &dh.mapB_hi, &dh.mapB_lo, dn, ws, mode, s, false, st);
     if (rc) return rc;
 #endif
   } else {
@@ -852,7 +866,7 @@ extern "C" int vpho_denoiser_create(int n_heads, const float* fourier_W, const f
   d.n_heads = n_heads; d.D = D; d.hid = hid;
   d.fourier_W = b + o_four; d.Wt = b + o_wt; d.bt = b + o_bt; d.W1 = b + o_w1; d.b1 = b + o_b1; d.W2 = b + o_w2;
   d.b2 = b + o_b2; d.Wa_t = b + o_wat; d.Wa_p = b + o_wap; d.Wa_f = b + o_waf; d.ba = b + o_ba; d.Wb = b + o_wb;
-  d.bb = b + o_bb; d.Wa_p_hi = nullptr; d.Wa_p_lo = nullptr;
+  d.bb = b + o_bb; d.Wa_p_hi = nullptr; d.Wa_p_lo = nullptr; d.Wscale_inv = nullptr;
 #ifndef VPHO_EMU
   // tcgen05 head GEMM (default).  VPHO_HEAD_GEMM=simt keeps the FP32-SIMT kernel (used to cross-check the two).
   const char* sel = getenv("VPHO_HEAD_GEMM");
@@ -904,6 +918,46 @@ extern "C" int vpho_denoiser_create(int n_heads, const float* fourier_W, const f
           tc_make_map(&dh->mapW2_lo, dh->pe_planes + 2 * n1 + n2, 256, 256, 256))
         dh->use_tc_pose = true;
     }
+    // 3xFP16 head GEMM (default when the tensor-core pose encoder is on; VPHO_HEAD_GEMM=tf32 keeps 3xTF32)
+    if (dh->use_tc_pose && !(sel && strcmp(sel, "tf32") == 0)) {
+      const size_t nw = (size_t)hid * kPDim;
+      std::vector<unsigned short> hp(2 * nw);
+      std::vector<float> inv(n_heads, 1.f);
+      for (int nn = 0; nn < n_heads; ++nn) {
+        float mx = 0.f;
+        for (int k = 0; k < kPDim; ++k) {
+          const float* src = ha_w + ((size_t)nn * 1408 + 128 + k) * 256;
+          for (int cc = 0; cc < 256; ++cc) mx = fmaxf(mx, fabsf(src[cc]));
+        }
+        float sc = 1.f;
+        if (mx > 0.f && mx < 3.0e38f) {
+          int e = 0;
+          frexpf(mx, &e);
+          sc = ldexpf(1.f, 14 - e);
+          inv[nn] = ldexpf(1.f, e - 14);
+        }
+        for (int k = 0; k < kPDim; ++k) {
+          const float* src = ha_w + ((size_t)nn * 1408 + 128 + k) * 256;
+          for (int cc = 0; cc < 256; ++cc) {
+            const float w = src[cc] * sc;
+            const __half h = __float2half_rn(w);
+            const __half l = __float2half_rn(w - __half2float(h));
+            hp[((size_t)nn * 256 + cc) * kPDim + k] = __half_as_ushort(h);
+            hp[nw + ((size_t)nn * 256 + cc) * kPDim + k] = __half_as_ushort(l);
+          }
+        }
+      }
+      const size_t bytes = 2 * nw * sizeof(unsigned short) + (size_t)n_heads * sizeof(float);
+      if (cudaMalloc(&dh->w_half, bytes) == cudaSuccess &&
+          cudaMemcpy(dh->w_half, hp.data(), 2 * nw * sizeof(unsigned short), cudaMemcpyHostToDevice) == cudaSuccess &&
+          cudaMemcpy(static_cast<char*>(dh->w_half) + 2 * nw * sizeof(unsigned short), inv.data(), n_heads * sizeof(float),
+                     cudaMemcpyHostToDevice) == cudaSuccess &&
+          tc_make_map(&dh->mapBh_hi, dh->w_half, hid, 256, kPDim, true) &&
+          tc_make_map(&dh->mapBh_lo, static_cast<unsigned short*>(dh->w_half) + nw, hid, 256, kPDim, true)) {
+        d.Wscale_inv = reinterpret_cast<const float*>(static_cast<char*>(dh->w_half) + 2 * nw * sizeof(unsigned short));
+        dh->use_f16 = true;
+      }
+    }
     // feat-term on tensor cores is opt-in (VPHO_FEAT_TERM=tc): see the accuracy note at k_feat_term
     const char* self = getenv("VPHO_FEAT_TERM");
     if (self && strcmp(self, "tc") == 0) {
@@ -937,6 +991,7 @@ extern "C" int vpho_denoiser_destroy(vpho_denoiser_t h) {
   if (dh->w_lo) cudaFree(dh->w_lo);
   if (dh->pe_planes) cudaFree(dh->pe_planes);
   if (dh->wf_planes) cudaFree(dh->wf_planes);
+  if (dh->w_half) cudaFree(dh->w_half);
   delete dh;
   return VPHO_OK;
 }
@@ -954,7 +1009,7 @@ extern "C" int vpho_score_eval(vpho_denoiser_t h, const float* x, float t, const
   DenoiserHost& dh = *static_cast<DenoiserHost*>(h);
   const DenoiserDev& dn = dh.dev;
   SamplerWs ws;
-  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, 1, &ws, dh.use_tc) > workspace_bytes) return VPHO_ERR_INVALID;
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, 1, &ws, dh.use_tc, dh.use_f16) > workspace_bytes) return VPHO_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   ws.eval_x = x; ws.eval_out = out;
   VPHO_LAUNCH(k_set_eval_time, dim3(1), dim3(1), 0, st, ws, t);
@@ -974,7 +1029,7 @@ extern "C" int vpho_sample_begin(vpho_denoiser_t h, const float* feat, int n_row
   DenoiserHost& dh = *static_cast<DenoiserHost*>(h);
   const DenoiserDev& dn = dh.dev;
   SamplerWs ws;
-  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws, dh.use_tc) > workspace_bytes) return VPHO_ERR_INVALID;
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws, dh.use_tc, dh.use_f16) > workspace_bytes) return VPHO_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int n = n_rows * dn.D;
   SampleCfg cfg{T0, eps, rtol, atol, max_step, n_rows, dn.D, n_eval, num_steps, rows_per_feat, t_eval, xs, x, counters};
@@ -1002,7 +1057,7 @@ extern "C" int vpho_sample_continue(vpho_denoiser_t h, int n_rows, int rows_per_
   DenoiserHost& dh = *static_cast<DenoiserHost*>(h);
   const DenoiserDev& dn = dh.dev;
   SamplerWs ws;
-  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws, dh.use_tc) > workspace_bytes) return VPHO_ERR_INVALID;
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws, dh.use_tc, dh.use_f16) > workspace_bytes) return VPHO_ERR_INVALID;
   return launch_attempts(dh, ws, n_rows * dn.D, max_attempts, (cudaStream_t)stream);
 }
 
@@ -1013,7 +1068,7 @@ extern "C" int vpho_sample_finish(vpho_denoiser_t h, int n_rows, int rows_per_fe
   DenoiserHost& dh = *static_cast<DenoiserHost*>(h);
   const DenoiserDev& dn = dh.dev;
   SamplerWs ws;
-  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws, dh.use_tc) > workspace_bytes) return VPHO_ERR_INVALID;
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws, dh.use_tc, dh.use_f16) > workspace_bytes) return VPHO_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = launch_eval(dh, ws, kModeFinal, 0, st);
   if (rc) return rc;

@@ -34,6 +34,7 @@ struct DenoiserDev {
   // 3xTF32 operand images for the tcgen05 path (nullptr when not built)
   const float* Wa_p_hi;    // [n_heads][256 n][256 k]  K-major, hi parts
   const float* Wa_p_lo;
+  const float* Wscale_inv; // [n_heads] exact power-of-two un-scaling of the FP16 weight planes (3xFP16 head GEMM)
 };
 
 enum StageMode : int {
@@ -79,6 +80,7 @@ struct SamplerWs {
   float* P2T;      // [256][Npad] pose features, k-major (FP32-SIMT head GEMM)
   float* P2hi;     // [Npad][256] pose features split for 3xTF32, row-major = K-major (tcgen05 head GEMM); nullptr = SIMT
   float* P2lo;
+  float* P2scale;  // [Npad] per-row un-scaling of the FP16 pose-feature planes (P2hi/P2lo then hold __half); nullptr = TF32
   float* Xhi;      // [Npad][Kx] stage input split for 3xTF32 (Kx = D rounded up to 32), tcgen05 pose encoder only
   float* Xlo;
   int Kx;

@@ -18,6 +18,7 @@
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 
 namespace vpho {
 
@@ -27,6 +28,8 @@ constexpr int kTcBBytes = kTcBN * kTcBK * 4;        // 32 KB
 constexpr int kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes;   // 96 KB
 constexpr int kTcThreads = 256;
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+// FP16 operands (a_format = b_format = 0), FP32 accumulate: same tile, K = 16 per instruction, twice the TF32 rate
+constexpr uint32_t kTcIdescF16 = (1u << 4) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 
 struct TcSmem {
   // operand stages first: 1024-byte aligned swizzle atoms
@@ -77,6 +80,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+template <bool kHalf>
+__device__ __forceinline__ void umma_any(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  if (kHalf) umma_f16(tmem_d, adesc, bdesc, kTcIdescF16, accumulate);
+  else umma_tf32(tmem_d, adesc, bdesc, kTcIdesc, accumulate);
+}
 __device__ __forceinline__ void umma_commit(void* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -107,6 +125,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// kHalf = false: 3xTF32 (operands are float planes, 32 k per 128-byte row, 8 chunks of K = 256).
+// kHalf = true : 3xFP16 (operands are __half planes scaled by exact powers of two so that every row / head peaks in
+//                [2^13, 2^14): hi = half(x s), lo = half(x s - hi), the same 22-bit split as TF32 at twice the MMA rate and
+//                half the operand bytes; 64 k per 128-byte row, 4 chunks; the epilogue undoes the scales).
+template <bool kHalf>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
           const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, DenoiserDev dn, SamplerWs ws,
@@ -118,6 +141,8 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = ws.Npad / kTcBM;
   const int n_items = n_tiles * dn.n_heads;
+  constexpr int kElems = kHalf ? 64 : 32;           // operand elements per 128-byte row
+  constexpr int kChunks = kPDim / kElems;
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kTcStages; ++i) { mbar_init(&sm.full_bar[i], 1); mbar_init(&sm.empty_bar[i], 1); }
@@ -140,14 +165,14 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       uint32_t phase = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const int tile = it % n_tiles, head = it / n_tiles;
-        for (int kc = 0; kc < kPDim / kTcBK; ++kc) {
+        for (int kc = 0; kc < kChunks; ++kc) {
           mbar_wait(&sm.empty_bar[stage], phase ^ 1);
           unsigned char* st = sm.stage[stage];
           mbar_arrive_expect_tx(&sm.full_bar[stage], kTcStageBytes);
-          tma_load_2d(&tmA_hi, &sm.full_bar[stage], st, kc * kTcBK, tile * kTcBM);
-          tma_load_2d(&tmA_lo, &sm.full_bar[stage], st + kTcABytes, kc * kTcBK, tile * kTcBM);
-          tma_load_2d(&tmB_hi, &sm.full_bar[stage], st + 2 * kTcABytes, kc * kTcBK, head * kTcBN);
-          tma_load_2d(&tmB_lo, &sm.full_bar[stage], st + 2 * kTcABytes + kTcBBytes, kc * kTcBK, head * kTcBN);
+          tma_load_2d(&tmA_hi, &sm.full_bar[stage], st, kc * kElems, tile * kTcBM);
+          tma_load_2d(&tmA_lo, &sm.full_bar[stage], st + kTcABytes, kc * kElems, tile * kTcBM);
+          tma_load_2d(&tmB_hi, &sm.full_bar[stage], st + 2 * kTcABytes, kc * kElems, head * kTcBN);
+          tma_load_2d(&tmB_lo, &sm.full_bar[stage], st + 2 * kTcABytes + kTcBBytes, kc * kElems, head * kTcBN);
           if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -161,7 +186,7 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         mbar_wait(&sm.tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTcBN);
-        for (int kc = 0; kc < kPDim / kTcBK; ++kc) {
+        for (int kc = 0; kc < kChunks; ++kc) {
           mbar_wait(&sm.full_bar[stage], phase);
           tc_fence_after();
           unsigned char* st = sm.stage[stage];
@@ -170,9 +195,9 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 #pragma unroll
           for (int k = 0; k < kTcBK / kTcUmmaK; ++k) {
             const uint64_t adv = (uint64_t)((k * kTcUmmaK * 4) >> 4);     // 32 bytes per K step inside the 128-byte row
-            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, kTcIdesc, (kc | k) != 0 ? 1u : 0u);
-            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, kTcIdesc, 1u);
-            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, kTcIdesc, 1u);
+            umma_any<kHalf>(d_tmem, a_lo + adv, b_hi + adv, (kc | k) != 0 ? 1u : 0u);
+            umma_any<kHalf>(d_tmem, a_hi + adv, b_lo + adv, 1u);
+            umma_any<kHalf>(d_tmem, a_hi + adv, b_hi + adv, 1u);
           }
           umma_commit(&sm.empty_bar[stage]);          // frees the smem slot once these MMAs have read it
           if (++stage == kTcStages) { stage = 0; phase ^= 1; }
@@ -204,6 +229,8 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       const int row = tile * kTcBM + q * 32 + lane;
       const bool valid = row < n_rows;
       const float* Frow = ws.F + (size_t)(valid ? row / rpf : 0) * dn.hid + hc0;
+      // exact power-of-two un-scaling of the FP16 operand planes (1 for the TF32 planes)
+      const float unscale = kHalf ? ws.P2scale[row] * dn.Wscale_inv[head] : 1.f;
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #pragma unroll 1
       for (int cb = 0; cb < kTcBN / 32; ++cb) {
@@ -216,7 +243,7 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const int col = cb * 32 + j4 * 4 + jj;
-            float hval = (__uint_as_float(v[j4 * 4 + jj]) + fa[jj]) + sm.tt[acc][col];
+            float hval = (__uint_as_float(v[j4 * 4 + jj]) * unscale + fa[jj]) + sm.tt[acc][col];
             hval = hval > 0.f ? hval : 0.f;
             const float4 w = *reinterpret_cast<const float4*>(sm.wb[acc][col]);
             o0 = fmaf(hval, w.x, o0);
@@ -399,6 +426,48 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
     }
     mbar_wait(&sm.d2_full_bar, 0);
     tc_fence_after();
+    if (ws.P2scale) {
+      // FP16 planes for the head GEMM: pass 1 finds the row maximum of relu(D2 + b2), pass 2 scales by an exact power of
+      // two so the row peaks in [2^13, 2^14) and splits into (hi, lo) halves
+      float rmax = 0.f;
+      for (int cb = 0; cb < 8; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(d2 + lane_addr + (uint32_t)(cb * 32), v);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(dn.b2 + cb * 32 + u * 4));
+          rmax = fmaxf(rmax, fmaxf(fmaxf(__uint_as_float(v[u * 4 + 0]) + b4.x, __uint_as_float(v[u * 4 + 1]) + b4.y),
+                                   fmaxf(__uint_as_float(v[u * 4 + 2]) + b4.z, __uint_as_float(v[u * 4 + 3]) + b4.w)));
+        }
+      }
+      int e = 0;
+      float sc = 1.f, inv = 1.f;
+      if (rmax > 0.f && rmax < 3.0e38f) {
+        frexpf(rmax, &e);                          // rmax = m * 2^e, m in [0.5, 1)
+        sc = ldexpf(1.f, 14 - e);
+        inv = ldexpf(1.f, e - 14);
+      }
+      ws.P2scale[r0 + r] = inv;
+      __half* hh = reinterpret_cast<__half*>(ws.P2hi) + (size_t)(r0 + r) * kPDim;
+      __half* hl = reinterpret_cast<__half*>(ws.P2lo) + (size_t)(r0 + r) * kPDim;
+      for (int cb = 0; cb < 8; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(d2 + lane_addr + (uint32_t)(cb * 32), v);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          __align__(16) __half hi8[8], lo8[8];
+#pragma unroll
+          for (int ee = 0; ee < 8; ++ee) {
+            const float pv = fmaxf(__uint_as_float(v[u * 8 + ee]) + __ldg(dn.b2 + cb * 32 + u * 8 + ee), 0.f) * sc;
+            const __half h = __float2half_rn(pv);
+            hi8[ee] = h;
+            lo8[ee] = __float2half_rn(pv - __half2float(h));
+          }
+          *reinterpret_cast<uint4*>(hh + cb * 32 + u * 8) = *reinterpret_cast<const uint4*>(hi8);
+          *reinterpret_cast<uint4*>(hl + cb * 32 + u * 8) = *reinterpret_cast<const uint4*>(lo8);
+        }
+      }
+    } else {
     float* dh = ws.P2hi + (size_t)(r0 + r) * kPDim;
     float* dl = ws.P2lo + (size_t)(r0 + r) * kPDim;
     for (int cb = 0; cb < 8; ++cb) {
@@ -418,6 +487,7 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
         *reinterpret_cast<float4*>(dh + cb * 32 + u * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<float4*>(dl + cb * 32 + u * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
+    }
     }
   }
   tc_fence_before();
@@ -566,15 +636,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // 2-D K-major f32 tensor [rows][kdim] -> boxes of {32 k, box_rows}, 128-byte swizzle
-bool tc_make_map(void* map_out, const float* base, int rows, int box_rows, int kdim) {
+bool tc_make_map(void* map_out, const void* base, int rows, int box_rows, int kdim, bool half) {
   CUtensorMap* map = static_cast<CUtensorMap*>(map_out);
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   if (!enc) return false;
+  const int esz = half ? 2 : 4;
   cuuint64_t gdim[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)kdim * 4};
-  cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)kdim * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};      // 128-byte rows
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+  CUresult r = enc(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -583,11 +654,13 @@ bool tc_make_map(void* map_out, const float* base, int rows, int box_rows, int k
 bool tc_available() { return get_encode() != nullptr; }
 
 int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const DenoiserDev& dn,
-                   const SamplerWs& ws, int mode, int s, cudaStream_t st) {
+                   const SamplerWs& ws, int mode, int s, bool half, cudaStream_t st) {
   static bool attr = false;
   const int smem = (int)sizeof(TcSmem) + 1024;
   if (!attr) {
-    if (cudaFuncSetAttribute(k_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return VPHO_ERR_LAUNCH;
+    if (cudaFuncSetAttribute(k_head_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_head_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return VPHO_ERR_LAUNCH;
     attr = true;
   }
   static int n_sm = 0;
@@ -599,9 +672,14 @@ int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi
   }
   const int n_items = (ws.Npad / kTcBM) * dn.n_heads;
   const int grid = n_items < n_sm ? n_items : n_sm;
-  VPHO_LAUNCH(k_head_tc, dim3(grid), dim3(kTcThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
-              *static_cast<const CUtensorMap*>(mapA_lo), *static_cast<const CUtensorMap*>(mapB_hi),
-              *static_cast<const CUtensorMap*>(mapB_lo), dn, ws, mode, s);
+  if (half)
+    VPHO_LAUNCH(k_head_tc<true>, dim3(grid), dim3(kTcThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
+                *static_cast<const CUtensorMap*>(mapA_lo), *static_cast<const CUtensorMap*>(mapB_hi),
+                *static_cast<const CUtensorMap*>(mapB_lo), dn, ws, mode, s);
+  else
+    VPHO_LAUNCH(k_head_tc<false>, dim3(grid), dim3(kTcThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
+                *static_cast<const CUtensorMap*>(mapA_lo), *static_cast<const CUtensorMap*>(mapB_hi),
+                *static_cast<const CUtensorMap*>(mapB_lo), dn, ws, mode, s);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }

@@ -170,6 +170,8 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     mano, anchors, objects, batch, prior_h, prior_o, st_h, st_o = make_inputs(BS, seed=rank)
     hp = VphoHotPath(mano, anchors, objects, st_h, st_o, sample_num=S, sampling_steps=STEPS_ODE, sample_T0=T0,
                      topk_hand=K_HAND, topk_obj=K_OBJ)
+    if os.environ.get("VPHO_NO_OVERLAP"):            # diagnostics: serialise the two samplers so per-kernel times are clean
+        hp.overlap_object_sampler = False
     batch["obj_id"] = np.asarray(batch["obj_id"], np.int32)
     host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in batch.items() if isinstance(v, np.ndarray)}
     host["prior_hand"], host["prior_obj"] = prior_h.pin_memory(), prior_o.pin_memory()

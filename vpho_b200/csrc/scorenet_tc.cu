@@ -26,7 +26,9 @@ constexpr int kTcBM = 128, kTcBN = 256, kTcBK = 32, kTcStages = 2, kTcUmmaK = 8;
 constexpr int kTcABytes = kTcBM * kTcBK * 4;        // 16 KB per operand plane per stage
 constexpr int kTcBBytes = kTcBN * kTcBK * 4;        // 32 KB
 constexpr int kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes;   // 96 KB
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 256;        // pose / feat kernels: 4 epilogue warps
+constexpr int kHeadThreads = 384;      // head kernel: 8 epilogue warps
+constexpr int kTcFtImgs = 4;
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 // FP16 operands (a_format = b_format = 0), FP32 accumulate: same tile, K = 16 per instruction, twice the TF32 rate
 constexpr uint32_t kTcIdescF16 = (1u << 4) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
@@ -36,6 +38,8 @@ struct TcSmem {
   unsigned char stage[kTcStages][kTcStageBytes];
   float wb[2][kTcBN][4];
   float tt[2][kTcBN];
+  float part[2][kTcBM][4];      // partial 256->3 sums of the upper column half
+  float ft[2][kTcFtImgs][kTcBN]; // F[img] + Tt of the images a row tile spans
   unsigned long long full_bar[kTcStages], empty_bar[kTcStages], tmem_full_bar[2], tmem_empty_bar[2];
   uint32_t tmem_base;
 };
@@ -113,6 +117,17 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(const void* smem) {
   return d;
 }
 
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
@@ -130,7 +145,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 //                [2^13, 2^14): hi = half(x s), lo = half(x s - hi), the same 22-bit split as TF32 at twice the MMA rate and
 //                half the operand bytes; 64 k per 128-byte row, 4 chunks; the epilogue undoes the scales).
 template <bool kHalf>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kHeadThreads, 1)
 k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
           const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, DenoiserDev dn, SamplerWs ws,
           int mode, int s) {
@@ -146,7 +161,7 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kTcStages; ++i) { mbar_init(&sm.full_bar[i], 1); mbar_init(&sm.empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full_bar[i], 1); mbar_init(&sm.tmem_empty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full_bar[i], 1); mbar_init(&sm.tmem_empty_bar[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -207,8 +222,10 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue (warps 4..7 own TMEM lanes 32*(warp-4) ..)
-    const int q = warp - 4, te = threadIdx.x - 128;
+    // ===================================================== epilogue: 8 warps.  Warp 4+e reads TMEM lanes 32*(e&3).. (its
+    // hardware lane quarter, warp_id % 4) and the 128-column half e>>2 of the accumulator; the two halves of a row are
+    // combined through shared memory in a fixed order (columns 0..127 first).
+    const int e = warp - 4, q = e & 3, half = e >> 2, te = threadIdx.x - 128;
     const EvalTime et = eval_time(c, mode, s);
     const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
     const int rpf = (mode == kModeEval) ? ws.eval_rpf : c.rows_per_feat;
@@ -217,46 +234,77 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int tile = it % n_tiles, head = it / n_tiles;
       const int hc0 = head * kHeadHid;
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int col = te + r * 128;
-        sm.tt[acc][col] = ws.Tt[hc0 + col];
-        *reinterpret_cast<float4*>(sm.wb[acc][col]) = __ldg(reinterpret_cast<const float4*>(dn.Wb + (size_t)(hc0 + col) * 4));
+      // per-item constants in shared memory: Wb, and ft[i][col] = F[img0 + i][col] + Tt[col] for the (at most kTcFtImgs)
+      // images this 128-row tile spans; tiles that span more images read F from global memory instead
+      const int row_lo = tile * kTcBM, row_hi = min(row_lo + kTcBM, n_rows) - 1;
+      const int img0 = row_lo / rpf, n_img = row_hi >= row_lo ? row_hi / rpf - img0 + 1 : 0;
+      const bool ft_smem = n_img <= kTcFtImgs;
+      {
+        const float tt = ws.Tt[hc0 + te];
+        sm.tt[acc][te] = tt;
+        *reinterpret_cast<float4*>(sm.wb[acc][te]) = __ldg(reinterpret_cast<const float4*>(dn.Wb + (size_t)(hc0 + te) * 4));
+        if (ft_smem)
+          for (int i = 0; i < n_img; ++i) sm.ft[acc][i][te] = ws.F[(size_t)(img0 + i) * dn.hid + hc0 + te] + tt;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&sm.tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = tile * kTcBM + q * 32 + lane;
+      const int row = row_lo + q * 32 + lane;
       const bool valid = row < n_rows;
-      const float* Frow = ws.F + (size_t)(valid ? row / rpf : 0) * dn.hid + hc0;
+      const int cbase = half * 128;
+      const int img_l = valid ? row / rpf - img0 : 0;
+      const float* Frow = ws.F + (size_t)(valid ? row / rpf : 0) * dn.hid + hc0 + cbase;
       // exact power-of-two un-scaling of the FP16 operand planes (1 for the TF32 planes)
       const float unscale = kHalf ? ws.P2scale[row] * dn.Wscale_inv[head] : 1.f;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTcBN + cbase);
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-#pragma unroll 1
-      for (int cb = 0; cb < kTcBN / 32; ++cb) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTcBN + cb * 32), v);
+      uint32_t v[2][32];
+      tmem_ld32_nowait(taddr, v[0]);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 f4 = __ldg(reinterpret_cast<const float4*>(Frow + cb * 32 + j4 * 4));
-          const float fa[4] = {f4.x, f4.y, f4.z, f4.w};
+      for (int cb = 0; cb < 4; ++cb) {
+        tmem_wait_ld();
+        if (cb + 1 < 4) tmem_ld32_nowait(taddr + (uint32_t)((cb + 1) * 32), v[(cb + 1) & 1]);     // overlaps the math below
+        const uint32_t* vv = v[cb & 1];
+        if (ft_smem) {
+          const float* ftp = &sm.ft[acc][img_l][cbase + cb * 32];
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int col = cb * 32 + j4 * 4 + jj;
-            float hval = (__uint_as_float(v[j4 * 4 + jj]) * unscale + fa[jj]) + sm.tt[acc][col];
+          for (int j = 0; j < 32; ++j) {
+            float hval = fmaf(__uint_as_float(vv[j]), unscale, ftp[j]);
             hval = hval > 0.f ? hval : 0.f;
-            const float4 w = *reinterpret_cast<const float4*>(sm.wb[acc][col]);
+            const float4 w = *reinterpret_cast<const float4*>(sm.wb[acc][cbase + cb * 32 + j]);
             o0 = fmaf(hval, w.x, o0);
             o1 = fmaf(hval, w.y, o1);
             o2 = fmaf(hval, w.z, o2);
+          }
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 f4 = __ldg(reinterpret_cast<const float4*>(Frow + cb * 32 + j4 * 4));
+            const float4 t4 = *reinterpret_cast<const float4*>(&sm.tt[acc][cbase + cb * 32 + j4 * 4]);
+            const float fa[4] = {f4.x + t4.x, f4.y + t4.y, f4.z + t4.z, f4.w + t4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              float hval = fmaf(__uint_as_float(vv[j4 * 4 + jj]), unscale, fa[jj]);
+              hval = hval > 0.f ? hval : 0.f;
+              const float4 w = *reinterpret_cast<const float4*>(sm.wb[acc][cbase + cb * 32 + j4 * 4 + jj]);
+              o0 = fmaf(hval, w.x, o0);
+              o1 = fmaf(hval, w.y, o1);
+              o2 = fmaf(hval, w.z, o2);
+            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.tmem_empty_bar[acc]);
-      if (valid) {
-        const float o[3] = {o0, o1, o2};
+      if (half == 1) {
+        float* pp = sm.part[acc][q * 32 + lane];
+        pp[0] = o0; pp[1] = o1; pp[2] = o2;
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (half == 0 && valid) {
+        const float* pp = sm.part[acc][q * 32 + lane];
+        const float o[3] = {o0 + pp[0], o1 + pp[1], o2 + pp[2]};
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           const float out = o[d] + dn.bb[head * 3 + d];
@@ -673,11 +721,11 @@ int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi
   const int n_items = (ws.Npad / kTcBM) * dn.n_heads;
   const int grid = n_items < n_sm ? n_items : n_sm;
   if (half)
-    VPHO_LAUNCH(k_head_tc<true>, dim3(grid), dim3(kTcThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
+    VPHO_LAUNCH(k_head_tc<true>, dim3(grid), dim3(kHeadThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
                 *static_cast<const CUtensorMap*>(mapA_lo), *static_cast<const CUtensorMap*>(mapB_hi),
                 *static_cast<const CUtensorMap*>(mapB_lo), dn, ws, mode, s);
   else
-    VPHO_LAUNCH(k_head_tc<false>, dim3(grid), dim3(kTcThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
+    VPHO_LAUNCH(k_head_tc<false>, dim3(grid), dim3(kHeadThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
                 *static_cast<const CUtensorMap*>(mapA_lo), *static_cast<const CUtensorMap*>(mapB_hi),
                 *static_cast<const CUtensorMap*>(mapB_lo), dn, ws, mode, s);
   VPHO_CHECK_LAUNCH();

@@ -209,10 +209,11 @@ __device__ __forceinline__ void time_term_block(const DenoiserDev& dn, const Sam
   __shared__ float tfeat[kTDim];
   __shared__ float part[4][kTtCols];
   const int tid = threadIdx.x;
-  const EvalTime et = eval_time(c, mode, s);
+  const float t32 = (float)eval_t64(c, mode, s);
+  if (block == 0 && tid == 255) ws.ctrl->et = eval_time(c, mode, s);       // read by the head GEMM of this call
   if (tid < 64) {
     // x_proj = t * W * 2 * np.pi in float32, left to right (denoiser.py:29-31)
-    float xp = __fmul_rn(__fmul_rn(__fmul_rn(et.t32, dn.fourier_W[tid]), 2.0f), 3.14159265358979323846f);
+    float xp = __fmul_rn(__fmul_rn(__fmul_rn(t32, dn.fourier_W[tid]), 2.0f), 3.14159265358979323846f);
     four[tid] = (float)sin((double)xp);
     four[64 + tid] = (float)cos((double)xp);
   }
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(256) k_head_simt(DenoiserDev dn, SamplerWs ws,
   const int hid = dn.hid, Npad = ws.Npad;
   const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
   const int rpf = (mode == kModeEval) ? ws.eval_rpf : c.rows_per_feat;
-  const EvalTime et = eval_time(c, mode, s);
+  const EvalTime et = c.et;
 
   int rows[8];
 #pragma unroll
@@ -994,6 +995,18 @@ extern "C" int vpho_denoiser_destroy(vpho_denoiser_t h) {
   if (dh->w_half) cudaFree(dh->w_half);
   delete dh;
   return VPHO_OK;
+}
+
+#ifndef VPHO_EMU
+namespace vpho { int tc_debug_clocks(int enable, unsigned long long* out, int n); }
+#endif
+// Debug only (not declared in the public header): timeline stamps of CTA 0 of the last tensor-core head GEMM launch.
+extern "C" int vpho_debug_tc_clocks(int enable, unsigned long long* out, int n) {
+#ifndef VPHO_EMU
+  return vpho::tc_debug_clocks(enable, out, n);
+#else
+  return VPHO_ERR_INVALID;
+#endif
 }
 
 extern "C" size_t vpho_sample_workspace_bytes(int n_heads, int n_rows, int rows_per_feat, int n_eval) {

@@ -45,6 +45,14 @@ enum StageMode : int {
   kModeEval = 4,    // stand-alone score evaluation (vpho_score_eval)
 };
 
+// time of one network evaluation and the SDE scalars that go with it
+struct EvalTime {
+  float t32;      // time fed to the network: torch.ones(N,1) * t  -> float32
+  float std32;    // sigma(t32) + 1e-7 in float32 (denoiser.py:78-81)
+  double coef;    // 0.5 * g(t)^2 in float64 (score_based_model.py:84, numpy >= 2 promotion)
+  float g32;      // float32 diffusion for the predictor step (sde_coeff(vec_eps))
+};
+
 struct RkCtrl {
   // configuration
   double T0, eps, rtol, atol, max_step;
@@ -66,6 +74,7 @@ struct RkCtrl {
   int nan_stage[8]; // K slot s holds non-finite values that must read as 0 (nan_to_num)
   unsigned int block_counter;
   float eval_t32;   // vpho_score_eval: the time of a stand-alone evaluation
+  EvalTime et;      // scalars of the network call in flight, written by its first kernel (time-term block 0)
   // caller-owned outputs of the running sample()
   double* xs;       // [n_eval][N][D] or nullptr
   double* x_out;    // [N][D]

@@ -36,12 +36,6 @@ constexpr double kSqrt2LogRatio = 4.1272734804992597;
 // ------------------------------------------------------------------------------------------------------------
 // time of an evaluation and the SDE scalars that go with it
 // ------------------------------------------------------------------------------------------------------------
-struct EvalTime {
-  float t32;      // time fed to the network: torch.ones(N,1) * t  -> float32
-  float std32;    // sigma(t32) + 1e-7 in float32 (denoiser.py:78-81)
-  double coef;    // 0.5 * g(t)^2 in float64 (score_based_model.py:84, numpy >= 2 promotion)
-  float g32;      // float32 diffusion for the predictor step (sde_coeff(vec_eps))
-};
 
 __device__ __forceinline__ float sigma_f32(float t32) {
   // torch: 0.01 * (5000.0 ** t) on a float32 tensor; pow evaluated in double and rounded once
@@ -49,14 +43,19 @@ __device__ __forceinline__ float sigma_f32(float t32) {
   return __fmul_rn(0.01f, p);
 }
 
+// float64 time of an evaluation (cheap); eval_time adds the SDE scalars (double pow: expensive on this chip's FP64
+// pipe, so it is evaluated by ONE thread per network call -- the first kernel of the call stores it in ctrl->et)
+__device__ __forceinline__ double eval_t64(const RkCtrl& c, int mode, int s) {
+  if (mode == kModeInit0) return c.T0;
+  if (mode == kModeInit1) return c.T0 + c.h0 * c.direction;
+  if (mode == kModeStage) return (s == 6) ? (c.t + c.h) : (c.t + kC[s] * c.h);
+  if (mode == kModeFinal) return c.eps;
+  return (double)c.eval_t32;
+}
+
 __device__ __forceinline__ EvalTime eval_time(const RkCtrl& c, int mode, int s) {
   EvalTime e;
-  double t64;
-  if (mode == kModeInit0) t64 = c.T0;
-  else if (mode == kModeInit1) t64 = c.T0 + c.h0 * c.direction;
-  else if (mode == kModeStage) t64 = (s == 6) ? (c.t + c.h) : (c.t + kC[s] * c.h);
-  else if (mode == kModeFinal) t64 = c.eps;
-  else t64 = (double)c.eval_t32;
+  const double t64 = eval_t64(c, mode, s);
   e.t32 = (float)t64;
   e.std32 = __fadd_rn(sigma_f32(e.t32), 1e-7f);
   double sigma;

@@ -27,7 +27,7 @@ constexpr int kTcABytes = kTcBM * kTcBK * 4;        // 16 KB per operand plane p
 constexpr int kTcBBytes = kTcBN * kTcBK * 4;        // 32 KB
 constexpr int kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes;   // 96 KB
 constexpr int kTcThreads = 256;        // pose / feat kernels: 4 epilogue warps
-constexpr int kHeadThreads = 384;      // head kernel: 8 epilogue warps
+constexpr int kHeadThreads = 640;      // head kernel: 4 role warps + 2 x 8 epilogue warps
 constexpr int kTcFtImgs = 4;
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 // FP16 operands (a_format = b_format = 0), FP32 accumulate: same tile, K = 16 per instruction, twice the TF32 rate
@@ -43,6 +43,17 @@ struct TcSmem {
   unsigned long long full_bar[kTcStages], empty_bar[kTcStages], tmem_full_bar[2], tmem_empty_bar[2];
   uint32_t tmem_base;
 };
+
+// Optional timeline instrumentation of CTA 0 (vpho_debug_tc_clocks): %globaltimer stamps of the three roles.
+__device__ unsigned long long g_clk[3 * 2048];
+__device__ int g_clk_on = 0;
+__device__ __forceinline__ void clk_stamp(int role, int idx) {
+  if (g_clk_on && blockIdx.x == 0 && idx < 2048) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_clk[role * 2048 + idx] = t;
+  }
+}
 
 // -------------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,11 +72,11 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"      // %2: suspend-time hint, the warp parks
       "@P1 bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* bar, void* dst, int c0, int c1) {
@@ -152,7 +163,8 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   RkCtrl& c = *ws.ctrl;
   if (!eval_active(c, mode)) return;            // uniform across the grid: nothing allocated yet
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align inside the shared window with an offset (an integer round trip would demote every access to a generic load)
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = ws.Npad / kTcBM;
   const int n_items = n_tiles * dn.n_heads;
@@ -176,18 +188,21 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      int stage = 0;
+      int stage = 0, pc = 0;
       uint32_t phase = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const int tile = it % n_tiles, head = it / n_tiles;
         for (int kc = 0; kc < kChunks; ++kc) {
           mbar_wait(&sm.empty_bar[stage], phase ^ 1);
+          clk_stamp(0, 2 * pc);
           unsigned char* st = sm.stage[stage];
           mbar_arrive_expect_tx(&sm.full_bar[stage], kTcStageBytes);
           tma_load_2d(&tmA_hi, &sm.full_bar[stage], st, kc * kElems, tile * kTcBM);
           tma_load_2d(&tmA_lo, &sm.full_bar[stage], st + kTcABytes, kc * kElems, tile * kTcBM);
           tma_load_2d(&tmB_hi, &sm.full_bar[stage], st + 2 * kTcABytes, kc * kElems, head * kTcBN);
           tma_load_2d(&tmB_lo, &sm.full_bar[stage], st + 2 * kTcABytes + kTcBBytes, kc * kElems, head * kTcBN);
+          clk_stamp(0, 2 * pc + 1);
+          ++pc;
           if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -195,14 +210,17 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      int stage = 0, acc = 0;
+      int stage = 0, acc = 0, mc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        clk_stamp(1, mc++);
         mbar_wait(&sm.tmem_empty_bar[acc], acc_phase ^ 1);
+        clk_stamp(1, mc++);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTcBN);
         for (int kc = 0; kc < kChunks; ++kc) {
           mbar_wait(&sm.full_bar[stage], phase);
+          clk_stamp(1, mc++);
           tc_fence_after();
           unsigned char* st = sm.stage[stage];
           const uint64_t a_hi = make_kmajor_sw128_desc(st), a_lo = make_kmajor_sw128_desc(st + kTcABytes);
@@ -215,6 +233,7 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
             umma_any<kHalf>(d_tmem, a_hi + adv, b_hi + adv, 1u);
           }
           umma_commit(&sm.empty_bar[stage]);          // frees the smem slot once these MMAs have read it
+          clk_stamp(1, mc++);
           if (++stage == kTcStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&sm.tmem_full_bar[acc]);          // accumulator complete -> epilogue
@@ -222,86 +241,87 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue: 8 warps.  Warp 4+e reads TMEM lanes 32*(e&3).. (its
-    // hardware lane quarter, warp_id % 4) and the 128-column half e>>2 of the accumulator; the two halves of a row are
-    // combined through shared memory in a fixed order (columns 0..127 first).
-    const int e = warp - 4, q = e & 3, half = e >> 2, te = threadIdx.x - 128;
-    const EvalTime et = eval_time(c, mode, s);
+    // ===================================================== epilogue: two groups of 8 warps.  Group g drains accumulator
+    // buffer g, i.e. every other work item, so the two groups' epilogues overlap each other and the MMAs.  Inside a group
+    // warp e reads TMEM lanes 32*(e&3).. (its hardware lane quarter, warp_id % 4) and the 128-column half (e>>2)&1; the
+    // two partial 256->3 sums of a row are combined through shared memory in a fixed order (low columns first).
+    const int e = warp - 4, q = e & 3, half = (e >> 2) & 1, grp = e >> 3;
+    const int tg = (threadIdx.x - 128) & 255;            // thread index inside the group
+    const EvalTime et = c.et;               // written by the time-term block of this network call
     const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
     const int rpf = (mode == kModeEval) ? ws.eval_rpf : c.rows_per_feat;
-    int acc = 0;
+    int ec = 0, n_it = 0;
     uint32_t acc_phase = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int acc = grp;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n_it) {
+      if ((n_it & 1) != grp) continue;
       const int tile = it % n_tiles, head = it / n_tiles;
       const int hc0 = head * kHeadHid;
+      if (tg == 0 && grp == 0) clk_stamp(2, ec++);
       // per-item constants in shared memory: Wb, and ft[i][col] = F[img0 + i][col] + Tt[col] for the (at most kTcFtImgs)
       // images this 128-row tile spans; tiles that span more images read F from global memory instead
       const int row_lo = tile * kTcBM, row_hi = min(row_lo + kTcBM, n_rows) - 1;
       const int img0 = row_lo / rpf, n_img = row_hi >= row_lo ? row_hi / rpf - img0 + 1 : 0;
       const bool ft_smem = n_img <= kTcFtImgs;
       {
-        const float tt = ws.Tt[hc0 + te];
-        sm.tt[acc][te] = tt;
-        *reinterpret_cast<float4*>(sm.wb[acc][te]) = __ldg(reinterpret_cast<const float4*>(dn.Wb + (size_t)(hc0 + te) * 4));
+        const float tt = ws.Tt[hc0 + tg];
+        sm.tt[acc][tg] = tt;
+        *reinterpret_cast<float4*>(sm.wb[acc][tg]) = __ldg(reinterpret_cast<const float4*>(dn.Wb + (size_t)(hc0 + tg) * 4));
         if (ft_smem)
-          for (int i = 0; i < n_img; ++i) sm.ft[acc][i][te] = ws.F[(size_t)(img0 + i) * dn.hid + hc0 + te] + tt;
+          for (int i = 0; i < n_img; ++i) sm.ft[acc][i][tg] = ws.F[(size_t)(img0 + i) * dn.hid + hc0 + tg] + tt;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(&sm.tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
       const int row = row_lo + q * 32 + lane;
       const bool valid = row < n_rows;
       const int cbase = half * 128;
       const int img_l = valid ? row / rpf - img0 : 0;
       const float* Frow = ws.F + (size_t)(valid ? row / rpf : 0) * dn.hid + hc0 + cbase;
-      // exact power-of-two un-scaling of the FP16 operand planes (1 for the TF32 planes)
+      // exact power-of-two un-scaling of the FP16 operand planes (1 for the TF32 planes); loaded before the waits
       const float unscale = kHalf ? ws.P2scale[row] * dn.Wscale_inv[head] : 1.f;
+      if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 3, 256;" ::: "memory");
+      if (tg == 0 && grp == 0) clk_stamp(2, ec++);
+      mbar_wait(&sm.tmem_full_bar[acc], acc_phase);
+      if (tg == 0 && grp == 0) clk_stamp(2, ec++);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTcBN + cbase);
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-      uint32_t v[2][32];
-      tmem_ld32_nowait(taddr, v[0]);
-#pragma unroll
+      if (tg == 0 && grp == 0) clk_stamp(2, ec++);
+#pragma unroll 1
       for (int cb = 0; cb < 4; ++cb) {
-        tmem_wait_ld();
-        if (cb + 1 < 4) tmem_ld32_nowait(taddr + (uint32_t)((cb + 1) * 32), v[(cb + 1) & 1]);     // overlaps the math below
-        const uint32_t* vv = v[cb & 1];
-        if (ft_smem) {
-          const float* ftp = &sm.ft[acc][img_l][cbase + cb * 32];
+        uint32_t vv[32];
+        tmem_ld32(taddr + (uint32_t)(cb * 32), vv);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float hval = fmaf(__uint_as_float(vv[j]), unscale, ftp[j]);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float fa[4];
+          if (ft_smem) {
+            const float4 f4 = *reinterpret_cast<const float4*>(&sm.ft[acc][img_l][cbase + cb * 32 + j4 * 4]);
+            fa[0] = f4.x; fa[1] = f4.y; fa[2] = f4.z; fa[3] = f4.w;
+          } else {
+            const float4 f4 = __ldg(reinterpret_cast<const float4*>(Frow + cb * 32 + j4 * 4));
+            const float4 t4 = *reinterpret_cast<const float4*>(&sm.tt[acc][cbase + cb * 32 + j4 * 4]);
+            fa[0] = f4.x + t4.x; fa[1] = f4.y + t4.y; fa[2] = f4.z + t4.z; fa[3] = f4.w + t4.w;
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            float hval = fmaf(__uint_as_float(vv[j4 * 4 + jj]), unscale, fa[jj]);
             hval = hval > 0.f ? hval : 0.f;
-            const float4 w = *reinterpret_cast<const float4*>(sm.wb[acc][cbase + cb * 32 + j]);
+            const float4 w = *reinterpret_cast<const float4*>(sm.wb[acc][cbase + cb * 32 + j4 * 4 + jj]);
             o0 = fmaf(hval, w.x, o0);
             o1 = fmaf(hval, w.y, o1);
             o2 = fmaf(hval, w.z, o2);
-          }
-        } else {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 f4 = __ldg(reinterpret_cast<const float4*>(Frow + cb * 32 + j4 * 4));
-            const float4 t4 = *reinterpret_cast<const float4*>(&sm.tt[acc][cbase + cb * 32 + j4 * 4]);
-            const float fa[4] = {f4.x + t4.x, f4.y + t4.y, f4.z + t4.z, f4.w + t4.w};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              float hval = fmaf(__uint_as_float(vv[j4 * 4 + jj]), unscale, fa[jj]);
-              hval = hval > 0.f ? hval : 0.f;
-              const float4 w = *reinterpret_cast<const float4*>(sm.wb[acc][cbase + cb * 32 + j4 * 4 + jj]);
-              o0 = fmaf(hval, w.x, o0);
-              o1 = fmaf(hval, w.y, o1);
-              o2 = fmaf(hval, w.z, o2);
-            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.tmem_empty_bar[acc]);
+      if (tg == 0 && grp == 0) clk_stamp(2, ec++);
       if (half == 1) {
         float* pp = sm.part[acc][q * 32 + lane];
         pp[0] = o0; pp[1] = o1; pp[2] = o2;
       }
-      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (grp == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+      else asm volatile("bar.sync 4, 256;" ::: "memory");
       if (half == 0 && valid) {
         const float* pp = sm.part[acc][q * 32 + lane];
         const float o[3] = {o0 + pp[0], o1 + pp[1], o2 + pp[2]};
@@ -311,7 +331,8 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           emit_score(ws, c, et, mode, s, row * dn.D + head * 3 + d, __fdiv_rn(out, et.std32));
         }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (tg == 0 && grp == 0) clk_stamp(2, ec++);
+      acc_phase ^= 1;
     }
   }
   tc_fence_before();
@@ -359,7 +380,7 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
   const RkCtrl& c = *ws.ctrl;
   if (!eval_active(c, mode)) return;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  PtSmem& sm = *reinterpret_cast<PtSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  PtSmem& sm = *reinterpret_cast<PtSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = dn.D, nk1 = (D + kTcBK - 1) / kTcBK;
   const int r0 = blockIdx.x * kTcBM;
@@ -556,7 +577,8 @@ k_feat_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const float* __restrict__ ba,
           float* __restrict__ F, int R, int hid) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align inside the shared window with an offset (an integer round trip would demote every access to a generic load)
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_ct = hid / kTcBN, n_rt = (R + kTcBM - 1) / kTcBM;
   const int n_items = n_ct * n_rt;
@@ -700,6 +722,16 @@ bool tc_make_map(void* map_out, const void* base, int rows, int box_rows, int kd
 }
 
 bool tc_available() { return get_encode() != nullptr; }
+
+int tc_debug_clocks(int enable, unsigned long long* out, int n) {
+  int on = enable;
+  if (cudaMemcpyToSymbol(g_clk_on, &on, sizeof(int)) != cudaSuccess) return VPHO_ERR_LAUNCH;
+  if (out && n > 0) {
+    if (n > 3 * 2048) n = 3 * 2048;
+    if (cudaMemcpyFromSymbol(out, g_clk, (size_t)n * sizeof(unsigned long long)) != cudaSuccess) return VPHO_ERR_LAUNCH;
+  }
+  return VPHO_OK;
+}
 
 int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const DenoiserDev& dn,
                    const SamplerWs& ws, int mode, int s, bool half, cudaStream_t st) {

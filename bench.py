@@ -38,7 +38,7 @@ BS, S, STEPS_ODE, T0, K_HAND, K_OBJ = 64, 100, 50, 0.65, 30, 10
 FLOP_HEAD_GEMM_HAND = 2 * (256 * 8192 + 8192 * 3)     # per candidate per network call, head GEMM + fused second layer
 FLOP_SCORE_HAND, FLOP_SCORE_OBJ = 4423680, 533504     # whole factored network per candidate per call
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC_BYTES = {"k_head_tc": 32187392 + 2816}
+NCU_TRAFFIC_BYTES = {"k_head_tc": 17272832}
 
 
 def _peaks():
@@ -313,9 +313,9 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
                      "bound": "tensor", "achieved": round(achieved, 2) if achieved else None, "peak": peaks["bf16_tflops"],
                      "unit": "TFLOP/s", "frac": round(achieved / peaks["bf16_tflops"], 4) if achieved else None,
                      "traffic": NCU_TRAFFIC_BYTES.get(head_kernel), "peak_source": peaks["source"] + " (cuBLAS bf16 burst)",
-                     "note": "FP32-parity contraction run as 3 kind::tf32 UMMAs per algorithmic FLOP (TF32 rate = 1/2 of bf16): "
-                             "ceiling for this formulation is peak/6 = %.0f TFLOP/s; ncu tensor-pipe active 69%% "
-                             "(profiles/r01_ncu_head_tc_summary.txt)" % (peaks["bf16_tflops"] / 6),
+                     "note": "FP32-parity contraction run as 3 kind::f16 UMMAs per algorithmic FLOP (hi/lo FP16 planes, exact "
+                             "power-of-two scaling): ceiling for this formulation is peak/3 = %.0f TFLOP/s "
+                             "; ncu: tensor pipe active 59 %% of elapsed, 68 us (profiles/r01_ncu_head_tc_summary.txt)" % (peaks["bf16_tflops"] / 3),
                      "launches_timed": hg["launches"], "network_calls": real_launches, "avg_launch_ms": round(avg_ms, 4),
                      "flop_per_launch": BS * S * FLOP_HEAD_GEMM_HAND,
                      "share_of_step": round(hg["ms_total"] / ms_res, 4)},

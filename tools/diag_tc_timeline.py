@@ -1,4 +1,5 @@
-"""Timeline of CTA 0 of one tensor-core head GEMM launch (producer / MMA issuer / epilogue), from %globaltimer stamps."""
+"""Timeline of CTA 0 of one tensor-core head GEMM launch (producer / MMA issuer / epilogue), from %globaltimer stamps.
+Needs a library built with the stamps compiled in:  VPHO_TC_TIMELINE=1 python -m vpho_b200.build --force"""
 import ctypes as C
 import os
 import sys

@@ -38,6 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
              "-I", os.path.join(ROOT, "include"), "-I", CSRC] + ARCH
     if verbose:
         flags += ["-Xptxas", "-v"]
+    if os.environ.get("VPHO_TC_TIMELINE"):
+        flags += ["-DVPHO_TC_TIMELINE"]
     procs = []
     objs = []
     for s in sources():

@@ -44,15 +44,20 @@ struct TcSmem {
   uint32_t tmem_base;
 };
 
-// Optional timeline instrumentation of CTA 0 (vpho_debug_tc_clocks): %globaltimer stamps of the three roles.
+// Optional timeline instrumentation of CTA 0 (vpho_debug_tc_clocks, tools/diag_tc_timeline.py): %globaltimer stamps of
+// the three roles of the head GEMM.  Compiled in only with -DVPHO_TC_TIMELINE; the default build has no stamps.
 __device__ unsigned long long g_clk[3 * 2048];
 __device__ int g_clk_on = 0;
 __device__ __forceinline__ void clk_stamp(int role, int idx) {
+#ifdef VPHO_TC_TIMELINE
   if (g_clk_on && blockIdx.x == 0 && idx < 2048) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_clk[role * 2048 + idx] = t;
   }
+#else
+  (void)role; (void)idx;
+#endif
 }
 
 // -------------------------------------------------------------------------------------------------- PTX helpers

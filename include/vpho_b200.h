@@ -132,6 +132,14 @@ int vpho_force_eval(vpho_assets_t h, const float* verts, const float* scale, con
                     const float* force_contact, const float* cone_anchor, const float* gravity, const float* com, int n, int group,
                     float* terms, float* force_local, float* force_point, float* force_global, void* stream);
 
+/* Final pose error per image, in millimetres: metrics [n][4] = {MJE, MVE, ADD, ADD-S}.  MJE / MVE: mean Euclidean
+ * joint / vertex distance of `TesterHand` (lib/engine/test.py:657-679); ADD / ADD-S of
+ * `TesterObject.criterion_ADD_REP` (lib/engine/test.py:413-442) on the object's sampled vertices posed by the predicted /
+ * ground-truth 6D poses (rot6d + translation, float64 [n][9]). */
+int vpho_pose_metrics(vpho_assets_t h, const float* pd_joint, const float* gt_joint, const float* pd_vert,
+                      const float* gt_vert, const double* pd_obj6d, const double* gt_obj6d, const int32_t* obj_id, int n,
+                      float* metrics, void* stream);
+
 typedef struct {
   int bs;          /* images in this batch                         */
   int S;           /* sample_num: diffusion candidates per image   */

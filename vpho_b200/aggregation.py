@@ -223,3 +223,19 @@ def force_eval(assets: Assets, vert3d: torch.Tensor, scale: torch.Tensor, weight
                                     capi.ptr(cone), capi.ptr(g), capi.ptr(c), n, 1, capi.ptr(terms), capi.ptr(outs[0]),
                                     capi.ptr(outs[1]), capi.ptr(outs[2]), capi.stream_of(v)), "vpho_force_eval")
     return (terms, *outs) if return_forces else terms
+
+
+def pose_metrics(assets: Assets, pd_joint, gt_joint, pd_vert, gt_vert, pd_obj6d, gt_obj6d, obj_name) -> torch.Tensor:
+    """Per-image final pose error in mm, (n, 4) = MJE, MVE (TesterHand, lib/engine/test.py:657-679), ADD, ADD-S
+    (TesterObject.criterion_ADD_REP, lib/engine/test.py:413-442), computed on the device so that the metric gather is the
+    only traffic leaving the GPU."""
+    lib = assets.lib
+    f = lambda t: t.contiguous().float()   # noqa: E731
+    pj, gj, pv, gv = f(pd_joint), f(gt_joint), f(pd_vert), f(gt_vert)
+    po, go = pd_obj6d.contiguous().double(), gt_obj6d.contiguous().double()
+    n, dev = pj.shape[0], pj.device
+    ids = obj_name if isinstance(obj_name, torch.Tensor) else assets.ids(obj_name, dev)
+    out = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    lib.check(lib.c.vpho_pose_metrics(assets.handle, capi.ptr(pj), capi.ptr(gj), capi.ptr(pv), capi.ptr(gv), capi.ptr(po),
+                                      capi.ptr(go), capi.ptr(ids), n, capi.ptr(out), capi.stream_of(pj)), "vpho_pose_metrics")
+    return out

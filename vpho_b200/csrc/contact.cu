@@ -180,9 +180,103 @@ __global__ void __launch_bounds__(128) k_force_eval(AssetsDev as, const float* _
   }
 }
 
+// Final pose-error metrics of one image per CTA: MJE / MVE of TesterHand (lib/engine/test.py:657-679,
+// mean Euclidean distance, metres -> mm) and ADD / ADD-S of TesterObject.criterion_ADD_REP (test.py:413-442) on the
+// object's sampled vertices.  Deterministic block reductions; ADD-S scans shared-memory tiles of ground-truth points.
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  const int tid = threadIdx.x;
+  red[tid] = v;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (tid < st) red[tid] += red[tid + st];
+    __syncthreads();
+  }
+  const float r = red[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256) k_pose_metrics(AssetsDev as, const float* __restrict__ pd_joint, const float* __restrict__ gt_joint,
+                                                      const float* __restrict__ pd_vert, const float* __restrict__ gt_vert,
+                                                      const double* __restrict__ pd_obj, const double* __restrict__ gt_obj,
+                                                      const int* __restrict__ obj_id, float* __restrict__ out) {
+  __shared__ float red[256];
+  __shared__ float4 tile[256];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float acc = 0.f;
+  if (tid < 21) {
+    const float* p = pd_joint + ((size_t)b * 21 + tid) * 3;
+    const float* g = gt_joint + ((size_t)b * 21 + tid) * 3;
+    const float dx = p[0] - g[0], dy = p[1] - g[1], dz = p[2] - g[2];
+    acc = sqrtf((dx * dx + dy * dy) + dz * dz);
+  }
+  const float mje = block_sum_256(acc, red) / 21.f * 1000.f;
+  acc = 0.f;
+  for (int v = tid; v < kVerts; v += 256) {
+    const float* p = pd_vert + ((size_t)b * kVerts + v) * 3;
+    const float* g = gt_vert + ((size_t)b * kVerts + v) * 3;
+    const float dx = p[0] - g[0], dy = p[1] - g[1], dz = p[2] - g[2];
+    acc += sqrtf((dx * dx + dy * dy) + dz * dz);
+  }
+  const float mve = block_sum_256(acc, red) / (float)kVerts * 1000.f;
+  // object: pose both clouds on the fly (HeadObject semantics, no flip, no root offset)
+  ObjPose pp, pg;
+  const float zero[3] = {0.f, 0.f, 0.f};
+  make_obj_pose(pd_obj + (size_t)b * 9, nullptr, zero, true, pp);
+  make_obj_pose(gt_obj + (size_t)b * 9, nullptr, zero, true, pg);
+  const float* base = as.verts + (size_t)obj_id[b] * as.n_pts * 3;
+  float add = 0.f, adds = 0.f;
+  for (int p0 = 0; p0 < as.n_pts; p0 += 256) {          // this thread's predicted point of the current slab
+    const int i = p0 + tid;
+    float a[3] = {0.f, 0.f, 0.f};
+    if (i < as.n_pts) {
+      float g[3];
+      obj_point(pp, base + (size_t)i * 3, a);
+      obj_point(pg, base + (size_t)i * 3, g);
+      const float dx = a[0] - g[0], dy = a[1] - g[1], dz = a[2] - g[2];
+      add += sqrtf((dx * dx + dy * dy) + dz * dz);
+    }
+    float best = INFINITY;
+    for (int q0 = 0; q0 < as.n_pts; q0 += 256) {
+      __syncthreads();
+      if (q0 + tid < as.n_pts) {
+        float g[3];
+        obj_point(pg, base + (size_t)(q0 + tid) * 3, g);
+        tile[tid] = make_float4(g[0], g[1], g[2], 0.f);
+      }
+      __syncthreads();
+      const int cnt = min(256, as.n_pts - q0);
+#pragma unroll 8
+      for (int q = 0; q < cnt; ++q) {
+        const float4 t = tile[q];
+        const float dx = a[0] - t.x, dy = a[1] - t.y, dz = a[2] - t.z;
+        best = fminf(best, (dx * dx + dy * dy) + dz * dz);
+      }
+    }
+    if (i < as.n_pts) adds += sqrtf(best);
+  }
+  const float add_mm = block_sum_256(add, red) / (float)as.n_pts * 1000.f;
+  const float adds_mm = block_sum_256(adds, red) / (float)as.n_pts * 1000.f;
+  if (tid == 0) {
+    out[(size_t)b * 4 + 0] = mje; out[(size_t)b * 4 + 1] = mve; out[(size_t)b * 4 + 2] = add_mm; out[(size_t)b * 4 + 3] = adds_mm;
+  }
+}
+
 }  // namespace vpho
 
 using namespace vpho;
+
+extern "C" int vpho_pose_metrics(vpho_assets_t h, const float* pd_joint, const float* gt_joint, const float* pd_vert,
+                                 const float* gt_vert, const double* pd_obj6d, const double* gt_obj6d, const int32_t* obj_id, int n,
+                                 float* metrics, void* stream) {
+  if (!h || n < 0) return VPHO_ERR_INVALID;
+  if (n == 0) return VPHO_OK;
+  if (!pd_joint || !gt_joint || !pd_vert || !gt_vert || !pd_obj6d || !gt_obj6d || !obj_id || !metrics) return VPHO_ERR_INVALID;
+  VPHO_LAUNCH(k_pose_metrics, dim3(n), dim3(256), 0, (cudaStream_t)stream, static_cast<AssetsHost*>(h)->dev, pd_joint, gt_joint, pd_vert,
+              gt_vert, pd_obj6d, gt_obj6d, obj_id, metrics);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
 
 extern "C" int vpho_force_eval(vpho_assets_t h, const float* verts, const float* scale, const float* weight, const uint8_t* contact_mask,
                                const float* force_contact, const float* cone_anchor, const float* gravity, const float* com, int n,

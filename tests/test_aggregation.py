@@ -71,6 +71,27 @@ def test_object_points_and_force_anchors_emulated(emu_lib):
     assert (fp - fp2).abs().max().item() < 1e-6 and (fg - fg2).abs().max().item() < 1e-4
 
 
+@pytest.mark.gpu
+def test_object_points_and_force_anchors_cuda(cuda_lib):
+    mano, anch, objs = cases.assets()
+    assets = Assets(anch, objs)
+    ho, oo = HeadObject(assets), O.OracleObject(objs)
+    g = torch.Generator().manual_seed(1)
+    pose = torch.randn(4, 100, 9, generator=g)
+    names = [objs["names"][i] for i in (3, 0, 20, 11)]
+    is_right = torch.tensor([True, False, False, True])
+    for dn in ("keypoint", "verts", "CoM"):
+        b = oo(pose, names, data_name=dn)
+        assert (ho(pose.cuda(), names, data_name=dn).cpu() - b).abs().max().item() < 2e-6
+        a2 = ho(pose.cuda(), names, data_name=dn, is_right=is_right.cuda()).cpu()
+        assert (a2 - oo.flip_pt3d(b.clone(), is_right)).abs().max().item() < 2e-6
+    verts = torch.from_numpy(mano["v_template"])[None].repeat(5, 1, 1) + torch.tensor([0.02, -0.01, 0.6])
+    fl = torch.randn(5, 32, 3, generator=g)
+    fp, fg = HeadPhysics(assets).from_local_to_global(fl.cuda(), verts.cuda())
+    fp2, fg2 = O.OracleAnchors(anch).from_local_to_global(fl, verts)
+    assert (fp.cpu() - fp2).abs().max().item() < 1e-6 and (fg.cpu() - fg2).abs().max().item() < 1e-4
+
+
 def test_topk_ties_follow_index_order(emu_lib):
     # all diffusion candidates identical -> every score ties; the canonical order must be index order 0..K-1
     mano, anch, objs = cases.assets()
@@ -87,7 +108,8 @@ def test_topk_ties_follow_index_order(emu_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("bs,S,Kh,Ko,seed", [(3, 16, 6, 4, 1), (8, 100, 30, 10, 2), (5, 37, 12, 5, 3), (2, 200, 30, 10, 4)])
+@pytest.mark.parametrize("bs,S,Kh,Ko,seed", [(3, 16, 6, 4, 1), (8, 100, 30, 10, 2), (5, 37, 12, 5, 3), (2, 200, 30, 10, 4),
+                                               (1, 300, 64, 16, 5), (2, 5, 5, 3, 6)])
 def test_aggregation_cuda(cuda_lib, bs, S, Kh, Ko, seed):
     out, dbg, ref, _ = _run(None, "cuda", bs, S, Kh, Ko, seed)
     _check_types(out, bs, S, Ko)

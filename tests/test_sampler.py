@@ -175,3 +175,21 @@ def test_sampler_cuda_simt_and_tensor_core_paths_agree(cuda_lib):
         data = {"feat_unique": enc, "sampled_pose": x, "t": torch.full((500, 1), t, device="cuda")}
         a, b = d_tc(data), d_simt(data)
         assert ((a - b).norm() / b.norm()).item() < 5e-7        # 3xTF32 keeps FP32-class accuracy
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,tol", [("sampler_obj", 2e-5), ("sampler_obj_stiff", 2e-4), ("sampler_hand", 2e-5)])
+def test_sampler_cuda_matches_reference_golden(cuda_lib, name, tol):
+    """CUDA sampler against the fixtures minted from the reference's own files (tests/golden, oracle/make_golden.py)."""
+    import os
+    from oracle import cases
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    head, bs, S = str(g["head"]), int(g["bs"]), int(g["S"])
+    st, enc, init = cases.sampler_case(head, bs, S, float(g["last_std"]), int(g["seed"]))
+    assert abs(cases.fingerprint(enc, init) - float(g["fp"])) < 1e-6
+    den = Denoiser(st)
+    agent = ScoreBasedModelAgent(sampling_steps=int(g["steps"]), sample_num=S)
+    xs, x = agent.sample({"feat_unique": enc.cuda(), "n_rows": bs * S}, den, 0.65, prior=init)
+    assert agent.last_info["net_calls"] == int(g["net_calls"])
+    assert (np.abs(x.cpu().numpy() - g["x"]) <= tol * np.maximum(1, np.abs(g["x"]))).all()
+    assert (np.abs(xs.cpu().numpy() - g["xs"]) <= tol * np.maximum(1, np.abs(g["xs"]))).all()

@@ -31,8 +31,11 @@ int vpho_version(void);
  * tags: 0 hand head-GEMM, 1 object head-GEMM, 2 pose encoder (incl. 6), 3 MANO skinning, 4 physics3 scan, 5 hand heat-map
  * scorer, 6 stage-input + time-term, 7 feat-term, 8 RK error norm / controller / dense output, 9 whole vpho_hoi_aggregate */
 unsigned long long vpho_launch_count(void);
-int vpho_profile_enable(int on);
+int vpho_profile_reserve(int n_events);  /* pre-create the event pool (keeps event creation out of timed regions) */
+int vpho_profile_enable(int tag_mask);   /* bit t set: record tag t; 0 = off; -1 = every tag */
 int vpho_profile_collect(int tag, double* total_ms, int* n_launches);
+/* same, and the individual launch durations (ms) of the first `cap` recorded launches in each_ms (HOST pointer) */
+int vpho_profile_collect_list(int tag, double* total_ms, int* n_launches, float* each_ms, int cap);
 
 /* ------------------------------------------------------------------------------------------------ MANO ---- */
 /* Packs the MANO tensors (HOST pointers, float32, manopth layouts: v_template [778][3], shapedirs [778][3][10],

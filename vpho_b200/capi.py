@@ -37,8 +37,10 @@ class HoiArgs(C.Structure):
 _SIGNATURES = {
     "vpho_version": (c_int, []),
     "vpho_launch_count": (C.c_ulonglong, []),
+    "vpho_profile_reserve": (c_int, [c_int]),
     "vpho_profile_enable": (c_int, [c_int]),
     "vpho_profile_collect": (c_int, [c_int, C.POINTER(c_double), C.POINTER(c_int)]),
+    "vpho_profile_collect_list": (c_int, [c_int, C.POINTER(c_double), C.POINTER(c_int), c_void_p, c_int]),
     "vpho_mano_create": (c_int, [c_void_p] * 5 + [C.POINTER(c_void_p)]),
     "vpho_mano_destroy": (c_int, [c_void_p]),
     "vpho_mano_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -144,6 +144,12 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
@@ -377,7 +383,7 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kHeadThreads, 1)
 k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
           const __grid_constant__ CUtensorMap tmW1_hi, const __grid_constant__ CUtensorMap tmW1_lo,
           const __grid_constant__ CUtensorMap tmW2_hi, const __grid_constant__ CUtensorMap tmW2_lo, DenoiserDev dn, SamplerWs ws,
@@ -393,7 +399,7 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.full_bar[i], 1); mbar_init(&sm.empty_bar[i], 1);
-      mbar_init(&sm.a_full_bar[i], 128); mbar_init(&sm.a_empty_bar[i], 1);
+      mbar_init(&sm.a_full_bar[i], 512); mbar_init(&sm.a_empty_bar[i], 1);
     }
     mbar_init(&sm.d1_full_bar, 1); mbar_init(&sm.d2_full_bar, 1); mbar_init(&sm.x_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -470,69 +476,77 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
       umma_commit(&sm.d2_full_bar);
     }
   } else if (warp >= 4) {
-    const int q = warp - 4, r = q * 32 + lane;          // this thread's row of the tile == its TMEM lane
+    // 16 compute warps: warp 4+e owns TMEM lanes 32*(e&3).. (its hardware lane quarter) and column sub-block cs = e>>2
+    const int e = warp - 4, q = e & 3, cs = e >> 2, r = q * 32 + lane;      // r: this thread's row of the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     mbar_wait(&sm.d1_full_bar, 0);
     tc_fence_after();
+    // ---- re-stage relu(D1 + b1) as the A operand of GEMM 2: 8 columns of each 32-column chunk per thread
     for (int kc = 0; kc < 8; ++kc) {
       const int ab = kc & 1;
       mbar_wait(&sm.a_empty_bar[ab], (uint32_t)(((kc >> 1) & 1) ^ 1));
-      uint32_t v[32];
-      tmem_ld32(d1 + lane_addr + (uint32_t)(kc * 32), v);
+      uint32_t v[8];
+      tmem_ld8(d1 + lane_addr + (uint32_t)(kc * 32 + cs * 8), v);
       unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
+      const float4 ba = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 32 + cs * 8));
+      const float4 bb4 = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 32 + cs * 8 + 4));
+      const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb4.x, bb4.y, bb4.z, bb4.w};
+      float hi[8], lo[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 32 + u * 4));
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-        float hi[4], lo[4];
+      for (int j = 0; j < 8; ++j) {
+        const float hv = fmaxf(__uint_as_float(v[j]) + bias[j], 0.f);
+        hi[j] = tf32_rna(hv);
+        lo[j] = tf32_rna(hv - hi[j]);
+      }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float hv = fmaxf(__uint_as_float(v[u * 4 + e]) + bb[e], 0.f);
-          hi[e] = tf32_rna(hv);
-          lo[e] = tf32_rna(hv - hi[e]);
-        }
+      for (int u2 = 0; u2 < 2; ++u2) {
+        const int u = cs * 2 + u2;                       // 16-byte unit inside the 128-byte row
         const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((u ^ (r & 7)) & 7) << 4));
-        *reinterpret_cast<float4*>(chunk + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(chunk + kTcABytes + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<float4*>(chunk + off) = make_float4(hi[u2 * 4 + 0], hi[u2 * 4 + 1], hi[u2 * 4 + 2], hi[u2 * 4 + 3]);
+        *reinterpret_cast<float4*>(chunk + kTcABytes + off) = make_float4(lo[u2 * 4 + 0], lo[u2 * 4 + 1], lo[u2 * 4 + 2], lo[u2 * 4 + 3]);
       }
       fence_proxy_async();
       mbar_arrive(&sm.a_full_bar[ab]);
     }
+    // ---- epilogue: relu(D2 + b2) -> operand planes of the head GEMM, 64 columns per thread
     mbar_wait(&sm.d2_full_bar, 0);
     tc_fence_after();
+    const int c0 = cs * 64;
     if (ws.P2scale) {
-      // FP16 planes for the head GEMM: pass 1 finds the row maximum of relu(D2 + b2), pass 2 scales by an exact power of
-      // two so the row peaks in [2^13, 2^14) and splits into (hi, lo) halves
+      // FP16 planes: the row maximum (over the four column sub-blocks, through shared memory) fixes an exact power-of-two
+      // scale so the row peaks in [2^13, 2^14); then (hi, lo) halves
       float rmax = 0.f;
-      for (int cb = 0; cb < 8; ++cb) {
+#pragma unroll 1
+      for (int cb = 0; cb < 2; ++cb) {
         uint32_t v[32];
-        tmem_ld32(d2 + lane_addr + (uint32_t)(cb * 32), v);
+        tmem_ld32(d2 + lane_addr + (uint32_t)(c0 + cb * 32), v);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(dn.b2 + cb * 32 + u * 4));
-          rmax = fmaxf(rmax, fmaxf(fmaxf(__uint_as_float(v[u * 4 + 0]) + b4.x, __uint_as_float(v[u * 4 + 1]) + b4.y),
-                                   fmaxf(__uint_as_float(v[u * 4 + 2]) + b4.z, __uint_as_float(v[u * 4 + 3]) + b4.w)));
-        }
+        for (int j = 0; j < 32; ++j) rmax = fmaxf(rmax, __uint_as_float(v[j]) + __ldg(dn.b2 + c0 + cb * 32 + j));
       }
-      int e = 0;
+      float* rowmax = reinterpret_cast<float*>(sm.a);      // the A-operand region is free once D2 is complete
+      rowmax[cs * kTcBM + r] = rmax;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      rmax = fmaxf(fmaxf(rowmax[r], rowmax[kTcBM + r]), fmaxf(rowmax[2 * kTcBM + r], rowmax[3 * kTcBM + r]));
+      int ex = 0;
       float sc = 1.f, inv = 1.f;
       if (rmax > 0.f && rmax < 3.0e38f) {
-        frexpf(rmax, &e);                          // rmax = m * 2^e, m in [0.5, 1)
-        sc = ldexpf(1.f, 14 - e);
-        inv = ldexpf(1.f, e - 14);
+        frexpf(rmax, &ex);                         // rmax = m * 2^ex, m in [0.5, 1)
+        sc = ldexpf(1.f, 14 - ex);
+        inv = ldexpf(1.f, ex - 14);
       }
-      ws.P2scale[r0 + r] = inv;
-      __half* hh = reinterpret_cast<__half*>(ws.P2hi) + (size_t)(r0 + r) * kPDim;
-      __half* hl = reinterpret_cast<__half*>(ws.P2lo) + (size_t)(r0 + r) * kPDim;
-      for (int cb = 0; cb < 8; ++cb) {
+      if (cs == 0) ws.P2scale[r0 + r] = inv;
+      __half* hh = reinterpret_cast<__half*>(ws.P2hi) + (size_t)(r0 + r) * kPDim + c0;
+      __half* hl = reinterpret_cast<__half*>(ws.P2lo) + (size_t)(r0 + r) * kPDim + c0;
+#pragma unroll 1
+      for (int cb = 0; cb < 2; ++cb) {
         uint32_t v[32];
-        tmem_ld32(d2 + lane_addr + (uint32_t)(cb * 32), v);
+        tmem_ld32(d2 + lane_addr + (uint32_t)(c0 + cb * 32), v);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           __align__(16) __half hi8[8], lo8[8];
 #pragma unroll
           for (int ee = 0; ee < 8; ++ee) {
-            const float pv = fmaxf(__uint_as_float(v[u * 8 + ee]) + __ldg(dn.b2 + cb * 32 + u * 8 + ee), 0.f) * sc;
+            const float pv = fmaxf(__uint_as_float(v[u * 8 + ee]) + __ldg(dn.b2 + c0 + cb * 32 + u * 8 + ee), 0.f) * sc;
             const __half h = __float2half_rn(pv);
             hi8[ee] = h;
             lo8[ee] = __float2half_rn(pv - __half2float(h));
@@ -542,26 +556,27 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
         }
       }
     } else {
-    float* dh = ws.P2hi + (size_t)(r0 + r) * kPDim;
-    float* dl = ws.P2lo + (size_t)(r0 + r) * kPDim;
-    for (int cb = 0; cb < 8; ++cb) {
-      uint32_t v[32];
-      tmem_ld32(d2 + lane_addr + (uint32_t)(cb * 32), v);
+      float* dh = ws.P2hi + (size_t)(r0 + r) * kPDim + c0;
+      float* dl = ws.P2lo + (size_t)(r0 + r) * kPDim + c0;
+#pragma unroll 1
+      for (int cb = 0; cb < 2; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(d2 + lane_addr + (uint32_t)(c0 + cb * 32), v);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(dn.b2 + cb * 32 + u * 4));
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-        float hi[4], lo[4];
+        for (int u = 0; u < 8; ++u) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(dn.b2 + c0 + cb * 32 + u * 4));
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          float hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float pv = fmaxf(__uint_as_float(v[u * 4 + e]) + bb[e], 0.f);
-          hi[e] = tf32_rna(pv);
-          lo[e] = tf32_rna(pv - hi[e]);
+          for (int ee = 0; ee < 4; ++ee) {
+            const float pv = fmaxf(__uint_as_float(v[u * 4 + ee]) + bb[ee], 0.f);
+            hi[ee] = tf32_rna(pv);
+            lo[ee] = tf32_rna(pv - hi[ee]);
+          }
+          *reinterpret_cast<float4*>(dh + cb * 32 + u * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(dl + cb * 32 + u * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
-        *reinterpret_cast<float4*>(dh + cb * 32 + u * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(dl + cb * 32 + u * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
-    }
     }
   }
   tc_fence_before();
@@ -796,7 +811,7 @@ int tc_launch_pose(const void* mapX_hi, const void* mapX_lo, const void* mapW1_h
     if (cudaFuncSetAttribute(k_pose_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return VPHO_ERR_LAUNCH;
     attr = true;
   }
-  VPHO_LAUNCH(k_pose_tc, dim3(ws.Npad / kTcBM), dim3(kTcThreads), smem, st, *static_cast<const CUtensorMap*>(mapX_hi),
+  VPHO_LAUNCH(k_pose_tc, dim3(ws.Npad / kTcBM), dim3(kHeadThreads), smem, st, *static_cast<const CUtensorMap*>(mapX_hi),
               *static_cast<const CUtensorMap*>(mapX_lo), *static_cast<const CUtensorMap*>(mapW1_hi),
               *static_cast<const CUtensorMap*>(mapW1_lo), *static_cast<const CUtensorMap*>(mapW2_hi),
               *static_cast<const CUtensorMap*>(mapW2_lo), dn, ws, mode, s);

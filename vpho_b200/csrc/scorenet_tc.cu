@@ -413,6 +413,8 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
   const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
+  int sc_ = 1024;                                // timeline stamp slot of this thread (VPHO_TC_TIMELINE builds)
+  if (threadIdx.x == 0) clk_stamp(0, sc_++);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -426,6 +428,7 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
       }
       for (int j = 0; j < nk1 + 8; ++j) {
         mbar_wait(&sm.empty_bar[stage], phase ^ 1);
+        clk_stamp(0, sc_++);
         mbar_arrive_expect_tx(&sm.full_bar[stage], kPtStageB);
         if (j < nk1) {
           tma_load_2d(&tmW1_hi, &sm.full_bar[stage], sm.b[stage], j * kTcBK, 0);
@@ -453,8 +456,10 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
         }
       };
       mbar_wait(&sm.x_full_bar, 0);
+      clk_stamp(1, sc_++);
       for (int kc = 0; kc < nk1; ++kc) {
         mbar_wait(&sm.full_bar[stage], phase);
+        clk_stamp(1, sc_++);
         tc_fence_after();
         const unsigned char* chunk = sm.a + (size_t)kc * 2 * kTcABytes;
         mma_chunk(d1, chunk, chunk + kTcABytes, kc == 0);
@@ -462,10 +467,13 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
         if (++stage == 2) { stage = 0; phase ^= 1; }
       }
       umma_commit(&sm.d1_full_bar);
+      clk_stamp(1, sc_++);
       for (int kc = 0; kc < 8; ++kc) {
         const int ab = kc & 1;
         mbar_wait(&sm.full_bar[stage], phase);
+        clk_stamp(1, sc_++);
         mbar_wait(&sm.a_full_bar[ab], (uint32_t)((kc >> 1) & 1));
+        clk_stamp(1, sc_++);
         tc_fence_after();
         const unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
         mma_chunk(d2, chunk, chunk + kTcABytes, kc == 0);
@@ -474,12 +482,14 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
         if (++stage == 2) { stage = 0; phase ^= 1; }
       }
       umma_commit(&sm.d2_full_bar);
+      clk_stamp(1, sc_++);
     }
   } else if (warp >= 4) {
     // 16 compute warps: warp 4+e owns TMEM lanes 32*(e&3).. (its hardware lane quarter) and column sub-block cs = e>>2
     const int e = warp - 4, q = e & 3, cs = e >> 2, r = q * 32 + lane;      // r: this thread's row of the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     mbar_wait(&sm.d1_full_bar, 0);
+    if (threadIdx.x == 128) clk_stamp(2, sc_++);
     tc_fence_after();
     // ---- re-stage relu(D1 + b1) as the A operand of GEMM 2: 8 columns of each 32-column chunk per thread
     for (int kc = 0; kc < 8; ++kc) {
@@ -507,22 +517,40 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
       }
       fence_proxy_async();
       mbar_arrive(&sm.a_full_bar[ab]);
+      if (threadIdx.x == 128) clk_stamp(2, sc_++);
     }
-    // ---- epilogue: relu(D2 + b2) -> operand planes of the head GEMM, 64 columns per thread
+    // ---- epilogue: relu(D2 + b2) -> operand planes of the head GEMM, 64 columns per thread, ONE pass over TMEM: the
+    // 64 activations stay in registers between the row-maximum exchange and the split
     mbar_wait(&sm.d2_full_bar, 0);
+    if (threadIdx.x == 128) clk_stamp(2, sc_++);
     tc_fence_after();
     const int c0 = cs * 64;
+    float pv[64];
+    {
+      uint32_t v0[32], v1[32];
+      tmem_ld32_nowait(d2 + lane_addr + (uint32_t)c0, v0);
+      tmem_ld32_nowait(d2 + lane_addr + (uint32_t)(c0 + 32), v1);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 ba = __ldg(reinterpret_cast<const float4*>(dn.b2 + c0 + j4 * 4));
+        const float4 bb4 = __ldg(reinterpret_cast<const float4*>(dn.b2 + c0 + 32 + j4 * 4));
+        pv[j4 * 4 + 0] = fmaxf(__uint_as_float(v0[j4 * 4 + 0]) + ba.x, 0.f);
+        pv[j4 * 4 + 1] = fmaxf(__uint_as_float(v0[j4 * 4 + 1]) + ba.y, 0.f);
+        pv[j4 * 4 + 2] = fmaxf(__uint_as_float(v0[j4 * 4 + 2]) + ba.z, 0.f);
+        pv[j4 * 4 + 3] = fmaxf(__uint_as_float(v0[j4 * 4 + 3]) + ba.w, 0.f);
+        pv[32 + j4 * 4 + 0] = fmaxf(__uint_as_float(v1[j4 * 4 + 0]) + bb4.x, 0.f);
+        pv[32 + j4 * 4 + 1] = fmaxf(__uint_as_float(v1[j4 * 4 + 1]) + bb4.y, 0.f);
+        pv[32 + j4 * 4 + 2] = fmaxf(__uint_as_float(v1[j4 * 4 + 2]) + bb4.z, 0.f);
+        pv[32 + j4 * 4 + 3] = fmaxf(__uint_as_float(v1[j4 * 4 + 3]) + bb4.w, 0.f);
+      }
+    }
     if (ws.P2scale) {
       // FP16 planes: the row maximum (over the four column sub-blocks, through shared memory) fixes an exact power-of-two
       // scale so the row peaks in [2^13, 2^14); then (hi, lo) halves
       float rmax = 0.f;
-#pragma unroll 1
-      for (int cb = 0; cb < 2; ++cb) {
-        uint32_t v[32];
-        tmem_ld32(d2 + lane_addr + (uint32_t)(c0 + cb * 32), v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) rmax = fmaxf(rmax, __uint_as_float(v[j]) + __ldg(dn.b2 + c0 + cb * 32 + j));
-      }
+      for (int j = 0; j < 64; ++j) rmax = fmaxf(rmax, pv[j]);
       float* rowmax = reinterpret_cast<float*>(sm.a);      // the A-operand region is free once D2 is complete
       rowmax[cs * kTcBM + r] = rmax;
       asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -535,52 +563,54 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
         inv = ldexpf(1.f, ex - 14);
       }
       if (cs == 0) ws.P2scale[r0 + r] = inv;
-      __half* hh = reinterpret_cast<__half*>(ws.P2hi) + (size_t)(r0 + r) * kPDim + c0;
-      __half* hl = reinterpret_cast<__half*>(ws.P2lo) + (size_t)(r0 + r) * kPDim + c0;
-#pragma unroll 1
-      for (int cb = 0; cb < 2; ++cb) {
-        uint32_t v[32];
-        tmem_ld32(d2 + lane_addr + (uint32_t)(c0 + cb * 32), v);
+      // The tile is a contiguous 64 KB block per plane in global memory.  Lanes own rows, so direct stores would touch 32
+      // different lines per instruction (partial sectors): stage through shared memory (rows padded to 528 bytes:
+      // conflict-free 16-byte stores) and write it out with consecutive threads on consecutive 16-byte units.
+      constexpr int kRowPad = 528, kPlane = kTcBM * kRowPad;
+      unsigned char* ot = sm.a + 2048;               // after the row-max scratch; operand regions a+b are free now
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          __align__(16) __half hi8[8], lo8[8];
+      for (int u = 0; u < 8; ++u) {
+        __align__(16) __half hi8[8], lo8[8];
 #pragma unroll
-          for (int ee = 0; ee < 8; ++ee) {
-            const float pv = fmaxf(__uint_as_float(v[u * 8 + ee]) + __ldg(dn.b2 + c0 + cb * 32 + u * 8 + ee), 0.f) * sc;
-            const __half h = __float2half_rn(pv);
-            hi8[ee] = h;
-            lo8[ee] = __float2half_rn(pv - __half2float(h));
-          }
-          *reinterpret_cast<uint4*>(hh + cb * 32 + u * 8) = *reinterpret_cast<const uint4*>(hi8);
-          *reinterpret_cast<uint4*>(hl + cb * 32 + u * 8) = *reinterpret_cast<const uint4*>(lo8);
+        for (int ee = 0; ee < 8; ++ee) {
+          const float x = pv[u * 8 + ee] * sc;
+          const __half h = __float2half_rn(x);
+          hi8[ee] = h;
+          lo8[ee] = __float2half_rn(x - __half2float(h));
         }
+        *reinterpret_cast<uint4*>(ot + r * kRowPad + (c0 + u * 8) * 2) = *reinterpret_cast<const uint4*>(hi8);
+        *reinterpret_cast<uint4*>(ot + kPlane + r * kRowPad + (c0 + u * 8) * 2) = *reinterpret_cast<const uint4*>(lo8);
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      const int tc = threadIdx.x - 128;
+      unsigned char* ghi = reinterpret_cast<unsigned char*>(ws.P2hi) + (size_t)r0 * kPDim * 2;
+      unsigned char* glo = reinterpret_cast<unsigned char*>(ws.P2lo) + (size_t)r0 * kPDim * 2;
+#pragma unroll 4
+      for (int i = tc; i < 2 * kTcBM * 32; i += 512) {
+        const int plane = i >> 12, j = i & 4095, row = j >> 5, unit = j & 31;
+        const uint4 val = *reinterpret_cast<const uint4*>(ot + plane * kPlane + row * kRowPad + unit * 16);
+        *reinterpret_cast<uint4*>((plane ? glo : ghi) + (size_t)row * 512 + unit * 16) = val;
       }
     } else {
       float* dh = ws.P2hi + (size_t)(r0 + r) * kPDim + c0;
       float* dl = ws.P2lo + (size_t)(r0 + r) * kPDim + c0;
-#pragma unroll 1
-      for (int cb = 0; cb < 2; ++cb) {
-        uint32_t v[32];
-        tmem_ld32(d2 + lane_addr + (uint32_t)(c0 + cb * 32), v);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(dn.b2 + c0 + cb * 32 + u * 4));
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-          float hi[4], lo[4];
+      for (int u = 0; u < 16; ++u) {
+        float hi[4], lo[4];
 #pragma unroll
-          for (int ee = 0; ee < 4; ++ee) {
-            const float pv = fmaxf(__uint_as_float(v[u * 4 + ee]) + bb[ee], 0.f);
-            hi[ee] = tf32_rna(pv);
-            lo[ee] = tf32_rna(pv - hi[ee]);
-          }
-          *reinterpret_cast<float4*>(dh + cb * 32 + u * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(dl + cb * 32 + u * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        for (int ee = 0; ee < 4; ++ee) {
+          hi[ee] = tf32_rna(pv[u * 4 + ee]);
+          lo[ee] = tf32_rna(pv[u * 4 + ee] - hi[ee]);
         }
+        *reinterpret_cast<float4*>(dh + u * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(dl + u * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
   }
+  if (threadIdx.x == 128) clk_stamp(2, sc_++);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) clk_stamp(0, sc_++);
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));

@@ -38,6 +38,7 @@ class VphoHotPath:
         self.last_info: dict = {}
         self.overlap_object_sampler = True
         self._side_stream = None
+        self._side_stream2 = None
 
     # ---- vpho_net.postprocess_diffusion_hand, branch 'mano_pose' (VPHO.py:306-331) ----
     def postprocess_diffusion_hand(self, hand_inprocess, hand_final, pd_mano_shape):
@@ -117,16 +118,40 @@ class VphoHotPath:
         xs_h, x_h, pend_h = self.score_agent.sample({"feat_unique": enc_h, "n_rows": bs * S}, self.denoiser_hand,
                                                     self.sample_T0, return_inprocess=with_inprocess, prior=prior_hand,
                                                     defer_check=True)
-        inproc, final_mano = self.postprocess_diffusion_hand(xs_h, x_h, pd_mano_shape)
+        # The aggregator needs only the final hand poses.  Everything else computed from the hand sampler's output is
+        # output-only (the in-process trajectory for visualisation, the 6400 posed meshes of the candidates): it runs on a
+        # second side stream, concurrently with the aggregation.
+        _, final_mano = self.postprocess_diffusion_hand(None, x_h, pd_mano_shape)
         pd["diff_final_hand_mano"] = final_mano.reshape(bs, S, 58)
-        if with_inprocess:
-            pd["diff_inprocess_hand_mano"] = inproc.reshape(bs, S, -1, 58)
-            # VPHO.py:250: every 10th output point of the first candidate of the first image (visualisation)
-            iv, ij = self.head_mano.get_hand_verts(pose=inproc[0, ::10, :48], shape=inproc[0, ::10, 48:])
-            pd["diff_inprocess_hand_vert"], pd["diff_inprocess_hand_joint"] = iv.reshape(-1, 778, 3), ij.reshape(-1, 21, 3)
-        fv, fj = self.head_mano.get_hand_verts(pose=final_mano[:, :48], shape=final_mano[:, 48:])
-        pd["diff_final_hand_vert"] = fv.reshape(bs, S, 778, 3)
-        pd["diff_final_hand_joint"] = fj.reshape(bs, S, 21, 3)
+
+        def output_only_work():
+            if with_inprocess:
+                inproc, _ = self.postprocess_diffusion_hand(xs_h, x_h, pd_mano_shape)
+                pd["diff_inprocess_hand_mano"] = inproc.reshape(bs, S, -1, 58)
+                # VPHO.py:250: every 10th output point of the first candidate of the first image (visualisation)
+                iv, ij = self.head_mano.get_hand_verts(pose=inproc[0, ::10, :48], shape=inproc[0, ::10, 48:])
+                pd["diff_inprocess_hand_vert"], pd["diff_inprocess_hand_joint"] = iv.reshape(-1, 778, 3), ij.reshape(-1, 21, 3)
+            fv, fj = self.head_mano.get_hand_verts(pose=final_mano[:, :48], shape=final_mano[:, 48:])
+            pd["diff_final_hand_vert"] = fv.reshape(bs, S, 778, 3)
+            pd["diff_final_hand_joint"] = fj.reshape(bs, S, 21, 3)
+
+        side2 = None
+        if main is not None and self.overlap_object_sampler:
+            if self._side_stream2 is None:
+                self._side_stream2 = torch.cuda.Stream(device=enc_h.device)
+            side2 = self._side_stream2
+            side2.wait_stream(main)
+            for t in (xs_h, x_h, final_mano):
+                if t is not None:
+                    t.record_stream(side2)
+            with torch.cuda.stream(side2):
+                output_only_work()
+            for k in ("diff_inprocess_hand_mano", "diff_inprocess_hand_vert", "diff_inprocess_hand_joint",
+                      "diff_final_hand_vert", "diff_final_hand_joint"):
+                if k in pd:
+                    pd[k].record_stream(main)
+        else:
+            output_only_work()
 
         if side is None:
             xs_o, x_o, pend_o = self.score_agent.sample({"feat_unique": enc_o, "n_rows": bs * S}, self.denoiser_obj,
@@ -151,6 +176,8 @@ class VphoHotPath:
         pd["agg_hand_vert"] = sel["hand_agg_vert"]
         pd["agg_hand_joint"] = sel["hand_agg_joint"]
         pd["_sel"] = sel
+        if side2 is not None:
+            main.wait_stream(side2)
         return pd, (pend_h, pend_o)
 
     __call__ = predict

@@ -33,11 +33,21 @@ t0 = min(v for v in np.concatenate([prod, mma, epi]) if v > 0)
 half = os.environ.get("VPHO_HEAD_GEMM") != "tf32"
 ch = 4 if half else 8
 print("chunks per item", ch)
-for item in range(4):
+n_it = 11
+mm = mma[:n_it * (2 + 2 * ch)].reshape(n_it, 2 + 2 * ch) - t0
+wait_empty = (mm[:, 1] - mm[:, 0]).sum()
+wait_full = (mm[:, 2::2] - np.concatenate([mm[:, 1:2], mm[:, 3:-1:2]], axis=1)).sum()
+issue = (mm[:, 3::2] - mm[:, 2::2]).sum()
+print("MMA lane over", n_it, "items: span", mm[-1, -1] - mm[0, 0], "ns; waiting tmem_empty", wait_empty, "ns; waiting full", wait_full,
+      "ns; issuing", issue, "ns")
+print("per item span:", (mm[:, -1] - mm[:, 0]).tolist())
+print("per item wait tmem_empty:", (mm[:, 1] - mm[:, 0]).tolist())
+for item in range(int(os.environ.get("ITEMS", "3"))):
     m = mma[item * (2 + 2 * ch):(item + 1) * (2 + 2 * ch)] - t0
-    e = epi[(item // 2) * 6:(item // 2 + 1) * 6] - t0      # group 0 stamps even items only
+    e = epi[(item // 2) * 10:(item // 2 + 1) * 10] - t0      # group 0 stamps even items only
     p = prod[item * 2 * ch:(item + 1) * 2 * ch] - t0
     print(f"item {item}")
     print("  producer (empty-wait done, issued) per chunk:", p.reshape(-1, 2).tolist())
     print("  mma: start", m[0], "tmem_empty ok", m[1], "per chunk (full ok, committed):", m[2:].reshape(-1, 2).tolist())
-    print("  epilogue: start", e[0], "after bar1", e[1], "tmem_full ok", e[2], "tmem loaded", e[3], "after math+arrive", e[4], "after emit", e[5])
+    print("  epilogue: start", e[0], "after bar1", e[1], "tmem_full ok", e[2], "fenced", e[3], "after each tcgen05.ld", e[4:8].tolist(),
+          "after math+arrive", e[8], "after emit", e[9])

@@ -35,7 +35,7 @@ int tc_launch_pose(const void* mapX_hi, const void* mapX_lo, const void* mapW1_h
                    const void* mapW2_lo, const DenoiserDev& dn,
                    const SamplerWs& ws, int mode, int s, cudaStream_t st);
 int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const DenoiserDev& dn,
-                   const SamplerWs& ws, int mode, int s, bool half, cudaStream_t st);
+                   const SamplerWs& ws, int mode, int s, bool half, int ctas, cudaStream_t st);
 
 struct alignas(64) TensorMapBlob { unsigned char b[128]; };
 
@@ -49,6 +49,8 @@ struct DenoiserHost {
   float* w_lo = nullptr;
   void* w_half = nullptr;            // [2][hid][256] __half (hi, lo) scaled per head + [n_heads] float un-scale factors
   TensorMapBlob mapBh_hi, mapBh_lo;
+  TensorMapBlob mapBp_hi, mapBp_lo;   // same FP16 planes, 128-row boxes: the CTA-pair kernel loads half a head per CTA
+  int pair_min_heads = 8;            // CTA-pair head GEMM from this many heads up (VPHO_HEAD_CTAS=1|2 forces)
   bool mapA_half = false;
   TensorMapBlob mapB_hi, mapB_lo, mapA_hi, mapA_lo;
   // tcgen05 pose encoder: K-major hi/lo planes of pose_encoder.0 [256][Kpad1] and pose_encoder.2 [256][256]
@@ -782,8 +784,10 @@ static int launch_eval(DenoiserHost& dh, const SamplerWs& ws, int mode, int s, c
       dh.mapA_rows = ws.Npad;
       dh.mapA_half = half;
     }
-    int rc = half ? tc_launch_head(&dh.mapA_hi, &dh.mapA_lo, &dh.mapBh_hi, &dh.mapBh_lo, dn, ws, mode, s, true, st)
-                  : tc_launch_head(&dh.mapA_hi, &dh.mapA_lo, &dh.mapB_hi, &dh.mapB_lo, dn, ws, mode, s, false, st);
+    const bool pair = half && dn.n_heads >= dh.pair_min_heads;
+    int rc = pair   ? tc_launch_head(&dh.mapA_hi, &dh.mapA_lo, &dh.mapBp_hi, &dh.mapBp_lo, dn, ws, mode, s, true, 2, st)
+             : half ? tc_launch_head(&dh.mapA_hi, &dh.mapA_lo, &dh.mapBh_hi, &dh.mapBh_lo, dn, ws, mode, s, true, 1, st)
+                    : tc_launch_head(&dh.mapA_hi, &dh.mapA_lo, &dh.mapB_hi, &dh.mapB_lo, dn, ws, mode, s, false, 1, st);
     if (rc) return rc;
 #endif
   } else {
@@ -954,7 +958,12 @@ extern "C" int vpho_denoiser_create(int n_heads, const float* fourier_W, const f
           cudaMemcpy(static_cast<char*>(dh->w_half) + 2 * nw * sizeof(unsigned short), inv.data(), n_heads * sizeof(float),
                      cudaMemcpyHostToDevice) == cudaSuccess &&
           tc_make_map(&dh->mapBh_hi, dh->w_half, hid, 256, kPDim, true) &&
-          tc_make_map(&dh->mapBh_lo, static_cast<unsigned short*>(dh->w_half) + nw, hid, 256, kPDim, true)) {
+          tc_make_map(&dh->mapBh_lo, static_cast<unsigned short*>(dh->w_half) + nw, hid, 256, kPDim, true) &&
+          tc_make_map(&dh->mapBp_hi, dh->w_half, hid, 128, kPDim, true) &&
+          tc_make_map(&dh->mapBp_lo, static_cast<unsigned short*>(dh->w_half) + nw, hid, 128, kPDim, true)) {
+        const char* hc = getenv("VPHO_HEAD_CTAS");
+        if (hc && hc[0] == '1') dh->pair_min_heads = 1 << 30;
+        if (hc && hc[0] == '2') dh->pair_min_heads = 1;
         d.Wscale_inv = reinterpret_cast<const float*>(static_cast<char*>(dh->w_half) + 2 * nw * sizeof(unsigned short));
         dh->use_f16 = true;
       }

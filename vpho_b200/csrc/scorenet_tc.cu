@@ -29,6 +29,7 @@ constexpr int kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes;   // 96 KB
 constexpr int kTcThreads = 256;        // pose / feat kernels: 4 epilogue warps
 constexpr int kHeadThreads = 640;      // head kernel: 4 role warps + 2 x 8 epilogue warps
 constexpr int kTcFtImgs = 4;
+constexpr int kTcMaxStages = 3;      // CTA-pair head GEMM: 3 stages of 64 KB in the same 192 KB
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 // FP16 operands (a_format = b_format = 0), FP32 accumulate: same tile, K = 16 per instruction, twice the TF32 rate
 constexpr uint32_t kTcIdescF16 = (1u << 4) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
@@ -40,7 +41,7 @@ struct TcSmem {
   float tt[2][kTcBN];
   float part[2][kTcBM][4];      // partial 256->3 sums of the upper column half
   float ft[2][kTcFtImgs][kTcBN]; // F[img] + Tt of the images a row tile spans
-  unsigned long long full_bar[kTcStages], empty_bar[kTcStages], tmem_full_bar[2], tmem_empty_bar[2];
+  unsigned long long full_bar[kTcMaxStages], empty_bar[kTcMaxStages], tmem_full_bar[2], tmem_empty_bar[2];
   uint32_t tmem_base;
 };
 
@@ -118,6 +119,63 @@ __device__ __forceinline__ void umma_any(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(void* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+// ---- CTA-pair (cta_group::2) helpers: the two CTAs of a cluster share one UMMA of M = 256
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {      // shared::cluster address of a peer's smem
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default .release.cta: the ordering that matters here (TMEM reads before the next MMA) is carried by tcgen05.wait::ld +
+  // tcgen05.fence::before_thread_sync; a cluster-scope release costs a full memory barrier per arrival
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(void* bar, uint32_t parity) {        // arrivals come from both CTAs
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP_C:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra DONE_C;\n\t"
+      "bra WAIT_LOOP_C;\n\t"
+      "DONE_C:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+// TMA load whose completion bytes are counted on the LEADER CTA's mbarrier (cluster address), data into this CTA's smem
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// completion of the pair's MMAs arrives on the same-offset mbarrier of BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(void* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((unsigned short)3)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -150,6 +208,28 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
@@ -166,7 +246,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // kHalf = true : 3xFP16 (operands are __half planes scaled by exact powers of two so that every row / head peaks in
 //                [2^13, 2^14): hi = half(x s), lo = half(x s - hi), the same 22-bit split as TF32 at twice the MMA rate and
 //                half the operand bytes; 64 k per 128-byte row, 4 chunks; the epilogue undoes the scales).
-template <bool kHalf>
+// kCtas = 2: CTA-pair variant.  The two CTAs of a cluster take the row tiles 2p and 2p + 1 of the same head; each loads its
+//                own A tile and HALF of the head's weight tile (128 of the 256 hidden columns), the leader CTA issues one
+//                tcgen05.mma.cta_group::2 of M = 256 that reads both halves, so the L2 -> SM operand traffic per CTA drops
+//                from 384 KB to 256 KB per work item and the 192 KB of stages hold 3 x 64 KB instead of 2 x 96 KB.
+//                TMA completions of both CTAs are counted on the leader's full barrier; tcgen05.commit multicasts the
+//                "stage free" and "accumulator ready" arrivals to both CTAs; the peer's epilogue warps arrive remotely
+//                on the leader's "accumulator drained" barrier.
+template <bool kHalf, int kCtas>
 __global__ void __launch_bounds__(kHeadThreads, 1)
 k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
           const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, DenoiserDev dn, SamplerWs ws,
@@ -177,55 +264,84 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   // align inside the shared window with an offset (an integer round trip would demote every access to a generic load)
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr bool kPair = kCtas == 2;
+  static_assert(!kPair || kHalf, "the CTA-pair variant is built for the FP16 planes");
+  constexpr int kStages = kPair ? 3 : kTcStages;
+  constexpr int kBHalfBytes = kTcBBytes / kCtas;                   // B plane bytes this CTA stages per K chunk
+  constexpr int kStageBytes = 2 * kTcABytes + 2 * kBHalfBytes;     // 96 KB, or 64 KB per CTA of a pair
+  static_assert(kStages * kStageBytes <= kTcStages * kTcStageBytes, "stages must fit the operand region");
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;           // CTA or CTA pair
+  const int n_units = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int n_tiles = ws.Npad / kTcBM;
-  const int n_items = n_tiles * dn.n_heads;
+  const int n_slots = kPair ? (n_tiles + 1) / 2 : n_tiles;         // row tiles, or pairs of row tiles
+  const int n_items = n_slots * dn.n_heads;
   constexpr int kElems = kHalf ? 64 : 32;           // operand elements per 128-byte row
   constexpr int kChunks = kPDim / kElems;
 
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kTcStages; ++i) { mbar_init(&sm.full_bar[i], 1); mbar_init(&sm.empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full_bar[i], 1); mbar_init(&sm.tmem_empty_bar[i], 8); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full_bar[i], 1); mbar_init(&sm.empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full_bar[i], 1); mbar_init(&sm.tmem_empty_bar[i], 8 * kCtas); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();                // barrier inits visible to the peer before any remote arrive / complete_tx
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
 
   if (warp == 0) {
-    // ===================================================== TMA producer
+    // ===================================================== TMA producer (one lane per CTA)
     if (lane == 0) {
       int stage = 0, pc = 0;
       uint32_t phase = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int tile = it % n_tiles, head = it / n_tiles;
+      for (int it = unit; it < n_items; it += n_units) {
+        const int slot = it % n_slots, head = it / n_slots;
+        const int tile = kPair ? 2 * slot + (int)rank : slot;       // a tile past the end (odd count) loads zeros
+        const int brow = head * kTcBN + (int)rank * (kTcBN / kCtas);
         for (int kc = 0; kc < kChunks; ++kc) {
           mbar_wait(&sm.empty_bar[stage], phase ^ 1);
           clk_stamp(0, 2 * pc);
-          unsigned char* st = sm.stage[stage];
-          mbar_arrive_expect_tx(&sm.full_bar[stage], kTcStageBytes);
-          tma_load_2d(&tmA_hi, &sm.full_bar[stage], st, kc * kElems, tile * kTcBM);
-          tma_load_2d(&tmA_lo, &sm.full_bar[stage], st + kTcABytes, kc * kElems, tile * kTcBM);
-          tma_load_2d(&tmB_hi, &sm.full_bar[stage], st + 2 * kTcABytes, kc * kElems, head * kTcBN);
-          tma_load_2d(&tmB_lo, &sm.full_bar[stage], st + 2 * kTcABytes + kTcBBytes, kc * kElems, head * kTcBN);
+          unsigned char* st = sm.stage[0] + stage * kStageBytes;
+          if (kPair) {
+            if (rank == 0) mbar_arrive_expect_tx(&sm.full_bar[stage], 2 * kStageBytes);
+            const uint32_t lbar = mapa_rank(smem_u32(&sm.full_bar[stage]), 0);
+            tma_load_2d_pair(&tmA_hi, lbar, st, kc * kElems, tile * kTcBM);
+            tma_load_2d_pair(&tmA_lo, lbar, st + kTcABytes, kc * kElems, tile * kTcBM);
+            tma_load_2d_pair(&tmB_hi, lbar, st + 2 * kTcABytes, kc * kElems, brow);
+            tma_load_2d_pair(&tmB_lo, lbar, st + 2 * kTcABytes + kBHalfBytes, kc * kElems, brow);
+          } else {
+            mbar_arrive_expect_tx(&sm.full_bar[stage], kStageBytes);
+            tma_load_2d(&tmA_hi, &sm.full_bar[stage], st, kc * kElems, tile * kTcBM);
+            tma_load_2d(&tmA_lo, &sm.full_bar[stage], st + kTcABytes, kc * kElems, tile * kTcBM);
+            tma_load_2d(&tmB_hi, &sm.full_bar[stage], st + 2 * kTcABytes, kc * kElems, brow);
+            tma_load_2d(&tmB_lo, &sm.full_bar[stage], st + 2 * kTcABytes + kBHalfBytes, kc * kElems, brow);
+          }
           clk_stamp(0, 2 * pc + 1);
           ++pc;
-          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================== MMA issuer (the leader CTA's lane issues for the pair)
+    if (lane == 0 && rank == 0) {
       int stage = 0, acc = 0, mc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      constexpr uint32_t kIdesc = (kHalf ? kTcIdescF16 : kTcIdesc) + (kPair ? ((uint32_t)(kTcBM >> 4) << 24) : 0u);   // M = 128 * kCtas
+      for (int it = unit; it < n_items; it += n_units) {
         clk_stamp(1, mc++);
-        mbar_wait(&sm.tmem_empty_bar[acc], acc_phase ^ 1);
+        if (kPair) mbar_wait_cluster(&sm.tmem_empty_bar[acc], acc_phase ^ 1);
+        else mbar_wait(&sm.tmem_empty_bar[acc], acc_phase ^ 1);
         clk_stamp(1, mc++);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTcBN);
@@ -233,21 +349,32 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           mbar_wait(&sm.full_bar[stage], phase);
           clk_stamp(1, mc++);
           tc_fence_after();
-          unsigned char* st = sm.stage[stage];
+          unsigned char* st = sm.stage[0] + stage * kStageBytes;
           const uint64_t a_hi = make_kmajor_sw128_desc(st), a_lo = make_kmajor_sw128_desc(st + kTcABytes);
-          const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * kTcABytes), b_lo = make_kmajor_sw128_desc(st + 2 * kTcABytes + kTcBBytes);
+          const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * kTcABytes), b_lo = make_kmajor_sw128_desc(st + 2 * kTcABytes + kBHalfBytes);
 #pragma unroll
           for (int k = 0; k < kTcBK / kTcUmmaK; ++k) {
             const uint64_t adv = (uint64_t)((k * kTcUmmaK * 4) >> 4);     // 32 bytes per K step inside the 128-byte row
-            umma_any<kHalf>(d_tmem, a_lo + adv, b_hi + adv, (kc | k) != 0 ? 1u : 0u);
-            umma_any<kHalf>(d_tmem, a_hi + adv, b_lo + adv, 1u);
-            umma_any<kHalf>(d_tmem, a_hi + adv, b_hi + adv, 1u);
+            const uint32_t first = (kc | k) != 0 ? 1u : 0u;
+            if (kPair) {
+              umma_f16_pair(d_tmem, a_lo + adv, b_hi + adv, kIdesc, first);
+              umma_f16_pair(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+              umma_f16_pair(d_tmem, a_hi + adv, b_hi + adv, kIdesc, 1u);
+            } else {
+              umma_any<kHalf>(d_tmem, a_lo + adv, b_hi + adv, first);
+              umma_any<kHalf>(d_tmem, a_hi + adv, b_lo + adv, 1u);
+              umma_any<kHalf>(d_tmem, a_hi + adv, b_hi + adv, 1u);
+            }
           }
-          umma_commit(&sm.empty_bar[stage]);          // frees the smem slot once these MMAs have read it
+          // frees the smem slot (of both CTAs) once these MMAs have read it
+          if (kPair) umma_commit_pair(&sm.empty_bar[stage]);
+          else umma_commit(&sm.empty_bar[stage]);
           clk_stamp(1, mc++);
-          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&sm.tmem_full_bar[acc]);          // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (kPair) umma_commit_pair(&sm.tmem_full_bar[acc]);
+        else umma_commit(&sm.tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -261,35 +388,56 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     const EvalTime et = c.et;               // written by the time-term block of this network call
     const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
     const int rpf = (mode == kModeEval) ? ws.eval_rpf : c.rows_per_feat;
-    int ec = 0, n_it = 0;
+    int ec = 0;
     uint32_t acc_phase = 0;
     const int acc = grp;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n_it) {
-      if ((n_it & 1) != grp) continue;
-      const int tile = it % n_tiles, head = it / n_tiles;
+    const uint32_t drained_bar = kPair ? mapa_rank(smem_u32(&sm.tmem_empty_bar[acc]), 0) : 0u;
+    // Per-item constants of column tg (second-layer weights, time term, conditioning terms of the images the row tile spans)
+    // are fetched one item ahead into registers, so their global-memory latency hides behind the previous item's math.
+    struct ItemConsts { float4 wb; float tt; float f[kTcFtImgs]; };
+    auto item_geometry = [&](int it, int& tile, int& head, int& img0, int& n_img) {
+      const int slot = it % n_slots;
+      head = it / n_slots;
+      tile = kPair ? 2 * slot + (int)rank : slot;
+      const int row_lo = tile * kTcBM, row_hi = min(row_lo + kTcBM, n_rows) - 1;
+      img0 = row_lo / rpf;
+      n_img = row_hi >= row_lo ? row_hi / rpf - img0 + 1 : 0;
+    };
+    auto fetch_consts = [&](int it, ItemConsts& k) {
+      int tile, head, img0, n_img;
+      item_geometry(it, tile, head, img0, n_img);
+      const int col = head * kHeadHid + tg;
+      k.tt = ws.Tt[col];
+      k.wb = __ldg(reinterpret_cast<const float4*>(dn.Wb + (size_t)col * 4));
+#pragma unroll
+      for (int i = 0; i < kTcFtImgs; ++i) k.f[i] = (n_img <= kTcFtImgs && i < n_img) ? ws.F[(size_t)(img0 + i) * dn.hid + col] : 0.f;
+    };
+    const int it_first = unit + grp * n_units, it_step = 2 * n_units;      // group g drains every other item of this CTA
+    ItemConsts kc;
+    if (it_first < n_items) fetch_consts(it_first, kc);
+    for (int it = it_first; it < n_items; it += it_step) {
+      int tile, head, img0, n_img;
+      item_geometry(it, tile, head, img0, n_img);
       const int hc0 = head * kHeadHid;
       if (tg == 0 && grp == 0) clk_stamp(2, ec++);
-      // per-item constants in shared memory: Wb, and ft[i][col] = F[img0 + i][col] + Tt[col] for the (at most kTcFtImgs)
-      // images this 128-row tile spans; tiles that span more images read F from global memory instead
-      const int row_lo = tile * kTcBM, row_hi = min(row_lo + kTcBM, n_rows) - 1;
-      const int img0 = row_lo / rpf, n_img = row_hi >= row_lo ? row_hi / rpf - img0 + 1 : 0;
+      // ft[i][col] = F[img0 + i][col] + Tt[col] for the (at most kTcFtImgs) images this 128-row tile spans; tiles that span
+      // more images read F from global memory instead
+      const int row_lo = tile * kTcBM;
       const bool ft_smem = n_img <= kTcFtImgs;
-      {
-        const float tt = ws.Tt[hc0 + tg];
-        sm.tt[acc][tg] = tt;
-        *reinterpret_cast<float4*>(sm.wb[acc][tg]) = __ldg(reinterpret_cast<const float4*>(dn.Wb + (size_t)(hc0 + tg) * 4));
-        if (ft_smem)
-          for (int i = 0; i < n_img; ++i) sm.ft[acc][i][tg] = ws.F[(size_t)(img0 + i) * dn.hid + hc0 + tg] + tt;
-      }
+      sm.tt[acc][tg] = kc.tt;
+      *reinterpret_cast<float4*>(sm.wb[acc][tg]) = kc.wb;
+#pragma unroll
+      for (int i = 0; i < kTcFtImgs; ++i) sm.ft[acc][i][tg] = kc.f[i] + kc.tt;
       const int row = row_lo + q * 32 + lane;
       const bool valid = row < n_rows;
       const int cbase = half * 128;
       const int img_l = valid ? row / rpf - img0 : 0;
       const float* Frow = ws.F + (size_t)(valid ? row / rpf : 0) * dn.hid + hc0 + cbase;
       // exact power-of-two un-scaling of the FP16 operand planes (1 for the TF32 planes); loaded before the waits
-      const float unscale = kHalf ? ws.P2scale[row] * dn.Wscale_inv[head] : 1.f;
+      const float unscale = kHalf ? (row < ws.Npad ? ws.P2scale[row] : 1.f) * dn.Wscale_inv[head] : 1.f;
       if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
       else asm volatile("bar.sync 3, 256;" ::: "memory");
+      if (it + it_step < n_items) fetch_consts(it + it_step, kc);
       if (tg == 0 && grp == 0) clk_stamp(2, ec++);
       mbar_wait(&sm.tmem_full_bar[acc], acc_phase);
       if (tg == 0 && grp == 0) clk_stamp(2, ec++);
@@ -297,35 +445,69 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTcBN + cbase);
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
       if (tg == 0 && grp == 0) clk_stamp(2, ec++);
-#pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {
-        uint32_t vv[32];
-        tmem_ld32(taddr + (uint32_t)(cb * 32), vv);
+      if (ft_smem) {
+        // hot path: conditioning + time terms of this row's image and the second-layer weights come from shared memory;
+        // the TMEM load of the next 16 columns is in flight while the current 16 are consumed
+        const float* ftp = &sm.ft[acc][img_l][cbase];
+        const float* wbp = &sm.wb[acc][cbase][0];
+        auto consume = [&](const uint32_t (&vv)[16], int cb) {
+          float4 fa[4], w[16];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          float fa[4];
-          if (ft_smem) {
-            const float4 f4 = *reinterpret_cast<const float4*>(&sm.ft[acc][img_l][cbase + cb * 32 + j4 * 4]);
-            fa[0] = f4.x; fa[1] = f4.y; fa[2] = f4.z; fa[3] = f4.w;
-          } else {
-            const float4 f4 = __ldg(reinterpret_cast<const float4*>(Frow + cb * 32 + j4 * 4));
-            const float4 t4 = *reinterpret_cast<const float4*>(&sm.tt[acc][cbase + cb * 32 + j4 * 4]);
-            fa[0] = f4.x + t4.x; fa[1] = f4.y + t4.y; fa[2] = f4.z + t4.z; fa[3] = f4.w + t4.w;
-          }
+          for (int j = 0; j < 4; ++j) fa[j] = *reinterpret_cast<const float4*>(ftp + cb * 16 + j * 4);
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            float hval = fmaf(__uint_as_float(vv[j4 * 4 + jj]), unscale, fa[jj]);
+          for (int j = 0; j < 16; ++j) w[j] = *reinterpret_cast<const float4*>(wbp + (cb * 16 + j) * 4);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float f = (j & 3) == 0 ? fa[j >> 2].x : (j & 3) == 1 ? fa[j >> 2].y : (j & 3) == 2 ? fa[j >> 2].z : fa[j >> 2].w;
+            float hval = fmaf(__uint_as_float(vv[j]), unscale, f);
             hval = hval > 0.f ? hval : 0.f;
-            const float4 w = *reinterpret_cast<const float4*>(sm.wb[acc][cbase + cb * 32 + j4 * 4 + jj]);
-            o0 = fmaf(hval, w.x, o0);
-            o1 = fmaf(hval, w.y, o1);
-            o2 = fmaf(hval, w.z, o2);
+            o0 = fmaf(hval, w[j].x, o0);
+            o1 = fmaf(hval, w[j].y, o1);
+            o2 = fmaf(hval, w[j].z, o2);
+          }
+        };
+        uint32_t va[16], vb[16];
+        tmem_ld16_issue(taddr, va);
+#pragma unroll 1
+        for (int cb = 0; cb < 8; cb += 2) {
+          tmem_ld16_wait(va);
+          tmem_ld16_issue(taddr + (uint32_t)((cb + 1) * 16), vb);
+          consume(va, cb);
+          if (tg == 0 && grp == 0) clk_stamp(2, ec++);
+          tmem_ld16_wait(vb);
+          if (cb + 2 < 8) tmem_ld16_issue(taddr + (uint32_t)((cb + 2) * 16), va);
+          consume(vb, cb + 1);
+        }
+      } else {
+        // a row tile that spans more than kTcFtImgs images (few candidates per image): F from global memory
+#pragma unroll 1
+        for (int cb = 0; cb < 16; ++cb) {
+          uint32_t vv[8];
+          tmem_ld8(taddr + (uint32_t)(cb * 8), vv);
+          if (tg == 0 && grp == 0 && (cb & 3) == 3) clk_stamp(2, ec++);
+#pragma unroll
+          for (int j4 = 0; j4 < 2; ++j4) {
+            const float4 f4 = __ldg(reinterpret_cast<const float4*>(Frow + cb * 8 + j4 * 4));
+            const float4 t4 = *reinterpret_cast<const float4*>(&sm.tt[acc][cbase + cb * 8 + j4 * 4]);
+            const float fa[4] = {f4.x + t4.x, f4.y + t4.y, f4.z + t4.z, f4.w + t4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              float hval = fmaf(__uint_as_float(vv[j4 * 4 + jj]), unscale, fa[jj]);
+              hval = hval > 0.f ? hval : 0.f;
+              const float4 w = *reinterpret_cast<const float4*>(sm.wb[acc][cbase + cb * 8 + j4 * 4 + jj]);
+              o0 = fmaf(hval, w.x, o0);
+              o1 = fmaf(hval, w.y, o1);
+              o2 = fmaf(hval, w.z, o2);
+            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(drained_bar);        // the leader's MMA lane waits for both CTAs' 8 warps
+        else mbar_arrive(&sm.tmem_empty_bar[acc]);
+      }
       if (tg == 0 && grp == 0) clk_stamp(2, ec++);
       if (half == 1) {
         float* pp = sm.part[acc][q * 32 + lane];
@@ -347,10 +529,12 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();                // neither CTA leaves (or frees TMEM) while the pair's MMAs / arrivals are in flight
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
 }
 
@@ -783,13 +967,15 @@ int tc_debug_clocks(int enable, unsigned long long* out, int n) {
   return VPHO_OK;
 }
 
+// ctas = 2 launches the CTA-pair variant (FP16 planes only): mapB_* must then have 128-row boxes.
 int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const DenoiserDev& dn,
-                   const SamplerWs& ws, int mode, int s, bool half, cudaStream_t st) {
+                   const SamplerWs& ws, int mode, int s, bool half, int ctas, cudaStream_t st) {
   static bool attr = false;
   const int smem = (int)sizeof(TcSmem) + 1024;
   if (!attr) {
-    if (cudaFuncSetAttribute(k_head_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_head_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_head_tc<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_head_tc<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_head_tc<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return VPHO_ERR_LAUNCH;
     attr = true;
   }
@@ -800,14 +986,38 @@ int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (n_sm <= 0) n_sm = 148;
   }
-  const int n_items = (ws.Npad / kTcBM) * dn.n_heads;
+  const int n_tiles = ws.Npad / kTcBM;
+  if (ctas == 2) {
+    if (!half) return VPHO_ERR_INVALID;
+    const int n_items = ((n_tiles + 1) / 2) * dn.n_heads;
+    const int pairs = n_items < n_sm / 2 ? n_items : n_sm / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kHeadThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ++g_launches;
+    if (cudaLaunchKernelEx(&cfg, k_head_tc<true, 2>, *static_cast<const CUtensorMap*>(mapA_hi), *static_cast<const CUtensorMap*>(mapA_lo),
+                           *static_cast<const CUtensorMap*>(mapB_hi), *static_cast<const CUtensorMap*>(mapB_lo), dn, ws, mode,
+                           s) != cudaSuccess)
+      return VPHO_ERR_LAUNCH;
+    return VPHO_OK;
+  }
+  const int n_items = n_tiles * dn.n_heads;
   const int grid = n_items < n_sm ? n_items : n_sm;
   if (half)
-    VPHO_LAUNCH(k_head_tc<true>, dim3(grid), dim3(kHeadThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
+    VPHO_LAUNCH((k_head_tc<true, 1>), dim3(grid), dim3(kHeadThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
                 *static_cast<const CUtensorMap*>(mapA_lo), *static_cast<const CUtensorMap*>(mapB_hi),
                 *static_cast<const CUtensorMap*>(mapB_lo), dn, ws, mode, s);
   else
-    VPHO_LAUNCH(k_head_tc<false>, dim3(grid), dim3(kHeadThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
+    VPHO_LAUNCH((k_head_tc<false, 1>), dim3(grid), dim3(kHeadThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
                 *static_cast<const CUtensorMap*>(mapA_lo), *static_cast<const CUtensorMap*>(mapB_hi),
                 *static_cast<const CUtensorMap*>(mapB_lo), dn, ws, mode, s);
   VPHO_CHECK_LAUNCH();

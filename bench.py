@@ -320,6 +320,12 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         tot, n = C.c_double(0), C.c_int(0)
         lib.c.vpho_profile_collect(tag, C.byref(tot), C.byref(n))
         prof[name] = {"ms_total": tot.value, "launches": n.value}
+    # 4) the aggregation stage alone bracketed (tag 9 only: events between its kernels would serialise the
+    #    programmatic-dependent-launch chain the stage normally runs as)
+    timed(step_resident, args.steps, profile=1 << 9)
+    tot, n = C.c_double(0), C.c_int(0)
+    lib.c.vpho_profile_collect(9, C.byref(tot), C.byref(n))
+    prof["hoi_aggregate_total"] = {"ms_total": tot.value, "launches": n.value}
     prefetch(0)
     for _ in range(2):
         step_e2e()

@@ -74,6 +74,8 @@ struct HandScoreSmem {
 // one CTA = TC candidates of one image: joints-only MANO -> projection -> bicubic heat sampling -> finger scores
 template <int TC>
 __global__ void __launch_bounds__(128) k_hand_level_score(ManoModelDev m, HoiDev h, int level) {
+  pdl_wait();          // launched with VPHO_LAUNCH_PDL
+  pdl_trigger();
   VPHO_DYN_SMEM(HandScoreSmem<TC>, sp);
   HandScoreSmem<TC>& s = *sp;
   const int b = blockIdx.y, c0 = blockIdx.x * TC, tid = threadIdx.x, nt = blockDim.x;
@@ -161,8 +163,11 @@ __global__ void __launch_bounds__(128) k_hand_level_score(ManoModelDev m, HoiDev
 // one CTA per image, one warp per finger list: top-k -> weights -> weighted quaternion average -> fused axis-angle
 template <int EL>
 __global__ void __launch_bounds__(160) k_hand_level_fuse(HoiDev h, int level) {
+  pdl_wait();          // launched with VPHO_LAUNCH_PDL
+  pdl_trigger();
   __shared__ float s_val[5][64];
   __shared__ int s_idx[5][64];
+  __shared__ float s_q[5][64][4];
   const int b = blockIdx.x, f = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = h.a.S, K = h.a.topk_hand, n = 2 * S;
   if (level == 0 && f != 0) return;
@@ -181,28 +186,34 @@ __global__ void __launch_bounds__(160) k_hand_level_fuse(HoiDev h, int level) {
       for (int d = 0; d < 3; ++d)
         h.l4[(((size_t)b * K + r) * 5 + f) * 3 + d] = cascade_param(h, b, s_idx[f][r], 3 * jm + d, level);
   }
-  if (lane == 0) {
-    float vsum = 0.f;
-    for (int r = 0; r < K; ++r) vsum += s_val[f][r];
-    float A[16];
+  // signed unit quaternions of the K winners, one candidate per lane (the parameter gathers are independent loads)
+  for (int r = lane; r < K; r += 32) {
+    float aa[3], q[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) A[i] = 0.f;
-    float wsum = 0.f;
+    for (int d = 0; d < 3; ++d) aa[d] = cascade_param(h, b, s_idx[f][r], 3 * jm + d, level);
+    axis_angle_to_quaternion(aa, q);
+    const float sg = q[0] > 0.f ? 1.f : -1.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s_q[f][r][i] = sg * q[i];
+  }
+  __syncwarp();
+  // lane 4 i + j accumulates entry (i, j) of the weighted outer-product sum over the winners in rank order
+  float vsum = 0.f;
+  for (int r = 0; r < K; ++r) vsum += s_val[f][r];
+  float a_ij = 0.f, wsum = 0.f;
+  {
+    const int i = (lane >> 2) & 3, j = lane & 3;
     for (int r = 0; r < K; ++r) {
       const float w = (s_val[f][r] + 1e-8f) / (vsum + 1e-8f);     // aggregation.py:218, 247
-      float aa[3], q[4];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) aa[d] = cascade_param(h, b, s_idx[f][r], 3 * jm + d, level);
-      axis_angle_to_quaternion(aa, q);
-      const float sg = q[0] > 0.f ? 1.f : -1.f;
       wsum += w;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) A[i * 4 + j] += ((sg * q[i]) * (sg * q[j])) * w;
+      a_ij += (s_q[f][r][i] * s_q[f][r][j]) * w;
     }
+    a_ij /= wsum;
+  }
+  float A[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) A[i] /= wsum;
+  for (int i = 0; i < 16; ++i) A[i] = __shfl_sync(0xffffffffu, a_ij, i);
+  if (lane == 0) {
     float qm[4], faa[3];
     sym4_top_eigvec(A, qm);
     quaternion_to_axis_angle(qm, faa);
@@ -224,6 +235,8 @@ __global__ void k_copy_cascade_pose(HoiDev h) {
 __global__ void __launch_bounds__(128) k_force_anchors(AssetsDev as, const float* __restrict__ verts,
                                                        const float* __restrict__ root, const float* __restrict__ force_local,
                                                        int n, int group, float* __restrict__ point, float* __restrict__ force) {
+  pdl_wait();          // launched with VPHO_LAUNCH_PDL
+  pdl_trigger();
   __shared__ float j21[21 * 3];
   const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* v = verts + (size_t)i * kVerts * 3;
@@ -259,6 +272,8 @@ __global__ void __launch_bounds__(128) k_force_anchors(AssetsDev as, const float
 // pose [bs][C][9] f64; transl (optional) [bs][3] f64 replaces every candidate's translation (aggregation.py:1213-1216)
 __global__ void __launch_bounds__(256) k_obj_heat_score(AssetsDev as, HoiDev h, const double* __restrict__ pose,
                                                         const double* __restrict__ transl, int C, float* __restrict__ score) {
+  pdl_wait();          // launched with VPHO_LAUNCH_PDL
+  pdl_trigger();
   __shared__ float hv[8][32];
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 8 + warp;
@@ -285,6 +300,8 @@ __global__ void __launch_bounds__(256) k_obj_heat_score(AssetsDev as, HoiDev h, 
 // step 1 (aggregation.py:1200-1211): top-k on the heat score -> weights -> fused translation (float64)
 template <int EL>
 __global__ void __launch_bounds__(32) k_obj_transl_fuse(HoiDev h) {
+  pdl_wait();          // launched with VPHO_LAUNCH_PDL
+  pdl_trigger();
   __shared__ float s_val[64];
   __shared__ int s_idx[64];
   const int b = blockIdx.x, lane = threadIdx.x;
@@ -308,6 +325,8 @@ __global__ void __launch_bounds__(32) k_obj_transl_fuse(HoiDev h) {
 // step 2 (aggregation.py:1218-1242): top-k rotations under the fused translation -> K x K recombination
 template <int EL>
 __global__ void __launch_bounds__(32) k_obj_recombine(HoiDev h) {
+  pdl_wait();          // launched with VPHO_LAUNCH_PDL
+  pdl_trigger();
   __shared__ float s_val[64];
   __shared__ int s_idx[64];
   const int b = blockIdx.x, lane = threadIdx.x;
@@ -373,6 +392,8 @@ __device__ __forceinline__ void anchor_nearest_scan(int n_pts, const float* anch
 
 // physics3 score of one recombined object candidate (aggregation.py:947-997): grid (kk, bs)
 __global__ void __launch_bounds__(kScanThreads) k_obj_physics3(AssetsDev as, HoiDev h) {
+  pdl_wait();          // launched with VPHO_LAUNCH_PDL
+  pdl_trigger();
   __shared__ float4 tile[kScanThreads];
   __shared__ float red_d2[8 * 32];
   __shared__ int red_arg[8 * 32];
@@ -427,6 +448,8 @@ __global__ void __launch_bounds__(kScanThreads) k_obj_physics3(AssetsDev as, Hoi
 // final object selection + fusion (aggregation.py:1247-1287): one CTA per image
 template <int EL>
 __global__ void __launch_bounds__(256) k_obj_final(AssetsDev as, HoiDev h) {
+  pdl_wait();          // launched with VPHO_LAUNCH_PDL
+  pdl_trigger();
   __shared__ float p_val[64], q_val[64];
   __shared__ int p_idx[64], q_idx[64];
   __shared__ double s_pose[9];
@@ -501,6 +524,8 @@ __global__ void __launch_bounds__(256) k_obj_final(AssetsDev as, HoiDev h) {
 // ------------------------------------------------------------------------------------------------------------
 // candidate poses: cascade-fused pose with the DIP (level-3) parameters of rank r's per-finger winners; last = fused
 __global__ void k_build_phys_pose(HoiDev h) {
+  pdl_wait();          // launched with VPHO_LAUNCH_PDL
+  pdl_trigger();
   const int b = blockIdx.x, K = h.a.topk_hand, nc = h.nc;
   for (int it = threadIdx.x; it < nc * 48; it += blockDim.x) {
     const int r = it / 48, p = it % 48;
@@ -520,6 +545,8 @@ __global__ void k_build_phys_pose(HoiDev h) {
 
 // grid (nc, bs): anchors of candidate (b, r) against the fused object's posed surface -> per-finger scores
 __global__ void __launch_bounds__(kScanThreads) k_hand_phys_score(HoiDev h) {
+  pdl_wait();          // launched with VPHO_LAUNCH_PDL
+  pdl_trigger();
   __shared__ float4 tile[kScanThreads];
   __shared__ float red_d2[8 * 32];
   __shared__ int red_arg[8 * 32];
@@ -564,6 +591,8 @@ __global__ void __launch_bounds__(kScanThreads) k_hand_phys_score(HoiDev h) {
 // one CTA per image, one warp per finger: top-5 candidates -> unweighted quaternion average of PIP and DIP
 template <int EL>
 __global__ void __launch_bounds__(160) k_hand_phys_fuse(HoiDev h) {
+  pdl_wait();          // launched with VPHO_LAUNCH_PDL
+  pdl_trigger();
   __shared__ float s_val[5][64];
   __shared__ int s_idx[5][64];
   const int b = blockIdx.x, f = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -681,46 +710,46 @@ static int run_hoi(const ManoModelDev& m, const AssetsDev& as, const HoiDev& h, 
   for (int level = 0; level < 4; ++level) {
     const int ncand = level == 0 ? 2 * S : S + 1;
     profile_begin(VPHO_TAG_HAND_SCORE, st);
-    VPHO_LAUNCH(k_hand_level_score<TC>, dim3((ncand + TC - 1) / TC, bs), dim3(128), smem, st, m, h, level);
+    VPHO_LAUNCH_PDL(k_hand_level_score<TC>, dim3((ncand + TC - 1) / TC, bs), dim3(128), smem, st, m, h, level);
     profile_end(VPHO_TAG_HAND_SCORE, st);
-    VPHO_LAUNCH(k_hand_level_fuse<EL>, dim3(bs), dim3(160), 0, st, h, level);
+    VPHO_LAUNCH_PDL(k_hand_level_fuse<EL>, dim3(bs), dim3(160), 0, st, h, level);
   }
   VPHO_CHECK_LAUNCH();
   if (a.dbg_cascade_pose) VPHO_LAUNCH(k_copy_cascade_pose, dim3((bs * 48 + 255) / 256), dim3(256), 0, st, h);
   int rc = mano_forward_dev(m, h.fused, a.hand_shape, 48, 10 * S, bs, h.cverts, h.cjoints, st);
   if (rc) return rc;
   // ---- force anchors of the fused hand (aggregation.py:1195-1196)
-  VPHO_LAUNCH(k_force_anchors, dim3(bs), dim3(128), 0, st, as, h.cverts, a.root_joint_flip, a.force_local, bs, 1, h.fpoint,
+  VPHO_LAUNCH_PDL(k_force_anchors, dim3(bs), dim3(128), 0, st, as, h.cverts, a.root_joint_flip, a.force_local, bs, 1, h.fpoint,
               h.fglobal);
   if (a.dbg_force_point) VPHO_LAUNCH(k_copy_f32, dim3((bs * 96 + 255) / 256), dim3(256), 0, st, h.fpoint, a.dbg_force_point, bs * 96);
   if (a.dbg_force_global) VPHO_LAUNCH(k_copy_f32, dim3((bs * 96 + 255) / 256), dim3(256), 0, st, h.fglobal, a.dbg_force_global, bs * 96);
   // ---- object: translation, rotation, recombination (aggregation.py:1200-1242)
   const int omax = S > h.kk ? S : h.kk;
-  VPHO_LAUNCH(k_obj_heat_score, dim3((S + 7) / 8, bs), dim3(256), 0, st, as, h, a.obj_pose6d, (const double*)nullptr, S, h.oscore);
+  VPHO_LAUNCH_PDL(k_obj_heat_score, dim3((S + 7) / 8, bs), dim3(256), 0, st, as, h, a.obj_pose6d, (const double*)nullptr, S, h.oscore);
   if (a.dbg_obj_score) VPHO_LAUNCH(k_copy_f32, dim3((bs * S + 255) / 256), dim3(256), 0, st, h.oscore, a.dbg_obj_score + (size_t)0 * bs * omax, bs * S);
-  VPHO_LAUNCH(k_obj_transl_fuse<EL>, dim3(bs), dim3(32), 0, st, h);
-  VPHO_LAUNCH(k_obj_heat_score, dim3((S + 7) / 8, bs), dim3(256), 0, st, as, h, a.obj_pose6d, (const double*)h.t_fused, S, h.oscore);
+  VPHO_LAUNCH_PDL(k_obj_transl_fuse<EL>, dim3(bs), dim3(32), 0, st, h);
+  VPHO_LAUNCH_PDL(k_obj_heat_score, dim3((S + 7) / 8, bs), dim3(256), 0, st, as, h, a.obj_pose6d, (const double*)h.t_fused, S, h.oscore);
   if (a.dbg_obj_score) VPHO_LAUNCH(k_copy_f32, dim3((bs * S + 255) / 256), dim3(256), 0, st, h.oscore, a.dbg_obj_score + (size_t)1 * bs * omax, bs * S);
-  VPHO_LAUNCH(k_obj_recombine<EL>, dim3(bs), dim3(32), 0, st, h);
+  VPHO_LAUNCH_PDL(k_obj_recombine<EL>, dim3(bs), dim3(32), 0, st, h);
   // ---- object: physics / heat-map selection of the recombined candidates, fusion (aggregation.py:1247-1287)
   profile_begin(VPHO_TAG_PHYSICS3, st);
-  VPHO_LAUNCH(k_obj_physics3, dim3(h.kk, bs), dim3(kScanThreads), 0, st, as, h);
+  VPHO_LAUNCH_PDL(k_obj_physics3, dim3(h.kk, bs), dim3(kScanThreads), 0, st, as, h);
   profile_end(VPHO_TAG_PHYSICS3, st);
-  VPHO_LAUNCH(k_obj_heat_score, dim3((h.kk + 7) / 8, bs), dim3(256), 0, st, as, h, (const double*)a.pose6d_candidate, (const double*)nullptr, h.kk, h.oscore);
+  VPHO_LAUNCH_PDL(k_obj_heat_score, dim3((h.kk + 7) / 8, bs), dim3(256), 0, st, as, h, (const double*)a.pose6d_candidate, (const double*)nullptr, h.kk, h.oscore);
   if (a.dbg_obj_score) {
     VPHO_LAUNCH(k_copy_f32, dim3((bs * h.kk + 255) / 256), dim3(256), 0, st, h.pscore, a.dbg_obj_score + (size_t)2 * bs * omax, bs * h.kk);
     VPHO_LAUNCH(k_copy_f32, dim3((bs * h.kk + 255) / 256), dim3(256), 0, st, h.oscore, a.dbg_obj_score + (size_t)3 * bs * omax, bs * h.kk);
   }
-  VPHO_LAUNCH(k_obj_final<EL>, dim3(bs), dim3(256), 0, st, as, h);
+  VPHO_LAUNCH_PDL(k_obj_final<EL>, dim3(bs), dim3(256), 0, st, as, h);
   VPHO_CHECK_LAUNCH();
   // ---- hand physics refinement (aggregation.py:1306-1337)
-  VPHO_LAUNCH(k_build_phys_pose, dim3(bs), dim3(256), 0, st, h);
+  VPHO_LAUNCH_PDL(k_build_phys_pose, dim3(bs), dim3(256), 0, st, h);
   rc = mano_forward_dev(m, h.ppose, h.pshape, 48, 10, bs * h.nc, h.pverts, h.pjoints, st);
   if (rc) return rc;
-  VPHO_LAUNCH(k_force_anchors, dim3(bs * h.nc), dim3(128), 0, st, as, h.pverts, a.root_joint_flip, a.force_local, bs * h.nc,
+  VPHO_LAUNCH_PDL(k_force_anchors, dim3(bs * h.nc), dim3(128), 0, st, as, h.pverts, a.root_joint_flip, a.force_local, bs * h.nc,
               h.nc, h.ppoint, h.pforce);
-  VPHO_LAUNCH(k_hand_phys_score, dim3(h.nc, bs), dim3(kScanThreads), 0, st, h);
-  VPHO_LAUNCH(k_hand_phys_fuse<EL>, dim3(bs), dim3(160), 0, st, h);
+  VPHO_LAUNCH_PDL(k_hand_phys_score, dim3(h.nc, bs), dim3(kScanThreads), 0, st, h);
+  VPHO_LAUNCH_PDL(k_hand_phys_fuse<EL>, dim3(bs), dim3(160), 0, st, h);
   VPHO_CHECK_LAUNCH();
   return mano_forward_dev(m, a.hand_agg_mano, a.hand_agg_mano + 48, 58, 58, bs, a.hand_agg_vert, a.hand_agg_joint, st);
 }

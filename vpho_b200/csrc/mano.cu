@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(kVChunkPad) mano_forward_kernel(ManoModelDev m
                                                                   const float* __restrict__ shape, int pose_stride,
                                                                   int shape_stride, int n, float* __restrict__ verts,
                                                                   float* __restrict__ joints) {
+  pdl_wait();          // launched with VPHO_LAUNCH_PDL
+  pdl_trigger();
   VPHO_DYN_SMEM(ManoSmem<TC>, sp);
   ManoSmem<TC>& s = *sp;
   const int c0 = blockIdx.x * TC;
@@ -117,7 +119,7 @@ static int launch_mano_forward(const ManoModelDev& m, const float* pose, const f
   }
 #endif
   profile_begin(VPHO_TAG_MANO_FULL, stream);
-  VPHO_LAUNCH(mano_forward_kernel<TC>, grid, dim3(kVChunkPad), smem, stream, m, pose, shape, pose_stride, shape_stride, n, verts,
+  VPHO_LAUNCH_PDL(mano_forward_kernel<TC>, grid, dim3(kVChunkPad), smem, stream, m, pose, shape, pose_stride, shape_stride, n, verts,
               joints);
   profile_end(VPHO_TAG_MANO_FULL, stream);
   VPHO_CHECK_LAUNCH();

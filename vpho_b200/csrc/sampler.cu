@@ -253,6 +253,8 @@ __global__ void __launch_bounds__(256) k_time_term(DenoiserDev dn, SamplerWs ws,
 // tcgen05 path: one launch does the time-term (first `nb_time` blocks) and the float64 RK stage combination of every
 // state element into the (hi, lo) TF32 planes of the pose encoder's A operand (remaining blocks), all SMs busy.
 __global__ void __launch_bounds__(256) k_stage_x(DenoiserDev dn, SamplerWs ws, int mode, int s, int nb_time) {
+  pdl_wait();                 // launched with launch_pdl: nothing of the previous kernel may be read above this line
+  pdl_trigger();
   const RkCtrl& c = *ws.ctrl;
   if (!eval_active(c, mode)) return;
   if ((int)blockIdx.x < nb_time) { time_term_block(dn, ws, c, mode, s, blockIdx.x); return; }
@@ -558,6 +560,8 @@ __device__ void controller(const SamplerWs& ws, RkCtrl& c, int kind, double s0, 
 }
 
 __global__ void __launch_bounds__(256) k_reduce(SamplerWs ws, int kind) {
+  pdl_wait();
+  pdl_trigger();
   RkCtrl& c = *ws.ctrl;
   if (c.status != 0) return;
   __shared__ double sh0[256], sh1[256];
@@ -608,6 +612,8 @@ __global__ void __launch_bounds__(256) k_reduce(SamplerWs ws, int kind) {
 
 // after an accepted step: quartic dense output at the t_eval points inside the step, then roll y <- y_new, f <- f_new
 __global__ void __launch_bounds__(256) k_post_step(SamplerWs ws) {
+  pdl_wait();
+  pdl_trigger();
   RkCtrl& c = *ws.ctrl;
   if (c.status < 0 || !c.accepted_now) return;
   const int n = c.n;
@@ -756,7 +762,7 @@ static int launch_eval(DenoiserHost& dh, const SamplerWs& ws, int mode, int s, c
     int nb_x = (ws.Npad * ws.Kx + 1023) / 1024;           // ~4 elements per thread
     if (nb_x > 592) nb_x = 592;
     profile_begin(VPHO_TAG_STAGE_X, st);
-    VPHO_LAUNCH(k_stage_x, dim3(nb_time + nb_x), dim3(256), 0, st, dn, ws, mode, s, nb_time);
+    VPHO_LAUNCH_PDL(k_stage_x, dim3(nb_time + nb_x), dim3(256), 0, st, dn, ws, mode, s, nb_time);
     profile_end(VPHO_TAG_STAGE_X, st);
     if (dh.mapX_for != ws.Xhi || dh.mapX_rows != ws.Npad) {
       if (!tc_make_map(&dh.mapX_hi, ws.Xhi, ws.Npad, 128, ws.Kx) || !tc_make_map(&dh.mapX_lo, ws.Xlo, ws.Npad, 128, ws.Kx)) return VPHO_ERR_LAUNCH;
@@ -806,8 +812,8 @@ static int launch_attempts(DenoiserHost& dh, const SamplerWs& ws, int n, int max
       if (rc) return rc;
     }
     profile_begin(VPHO_TAG_RK_CONTROL, st);
-    VPHO_LAUNCH(k_reduce, dim3(rb), dim3(256), 0, st, ws, (int)kRedErr);
-    VPHO_LAUNCH(k_post_step, dim3(rb), dim3(256), 0, st, ws);
+    VPHO_LAUNCH_PDL(k_reduce, dim3(rb), dim3(256), 0, st, ws, (int)kRedErr);
+    VPHO_LAUNCH_PDL(k_post_step, dim3(rb), dim3(256), 0, st, ws);
     profile_end(VPHO_TAG_RK_CONTROL, st);
     VPHO_CHECK_LAUNCH();
   }

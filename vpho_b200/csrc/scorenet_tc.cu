@@ -259,7 +259,6 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, DenoiserDev dn, SamplerWs ws,
           int mode, int s) {
   RkCtrl& c = *ws.ctrl;
-  if (!eval_active(c, mode)) return;            // uniform across the grid: nothing allocated yet
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // align inside the shared window with an offset (an integer round trip would demote every access to a generic load)
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -298,8 +297,14 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
+  // launched with launch_pdl: everything above overlaps the tail of the pose-encoder kernel; nothing it (or any earlier
+  // kernel) wrote is read before this point
+  pdl_wait();
+  pdl_trigger();
+  const bool active = eval_active(c, mode);     // uniform across the grid (a skipped RK attempt)
 
-  if (warp == 0) {
+  if (!active) {
+  } else if (warp == 0) {
     // ===================================================== TMA producer (one lane per CTA)
     if (lane == 0) {
       int stage = 0, pc = 0;
@@ -573,7 +578,6 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
           const __grid_constant__ CUtensorMap tmW2_hi, const __grid_constant__ CUtensorMap tmW2_lo, DenoiserDev dn, SamplerWs ws,
           int mode, int s) {
   const RkCtrl& c = *ws.ctrl;
-  if (!eval_active(c, mode)) return;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   PtSmem& sm = *reinterpret_cast<PtSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -598,9 +602,13 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
   const uint32_t tmem_base = sm.tmem_base;
   const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
   int sc_ = 1024;                                // timeline stamp slot of this thread (VPHO_TC_TIMELINE builds)
+  pdl_wait();                 // launched with launch_pdl: the set-up above overlaps the tail of k_stage_x
+  pdl_trigger();
   if (threadIdx.x == 0) clk_stamp(0, sc_++);
+  const bool active = eval_active(c, mode);
 
-  if (warp == 0) {
+  if (!active) {
+  } else if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -987,41 +995,21 @@ int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi
     if (n_sm <= 0) n_sm = 148;
   }
   const int n_tiles = ws.Npad / kTcBM;
+  const CUtensorMap &ah = *static_cast<const CUtensorMap*>(mapA_hi), &al = *static_cast<const CUtensorMap*>(mapA_lo),
+                    &bh = *static_cast<const CUtensorMap*>(mapB_hi), &bl = *static_cast<const CUtensorMap*>(mapB_lo);
+  cudaError_t e;
   if (ctas == 2) {
     if (!half) return VPHO_ERR_INVALID;
     const int n_items = ((n_tiles + 1) / 2) * dn.n_heads;
     const int pairs = n_items < n_sm / 2 ? n_items : n_sm / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(kHeadThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    ++g_launches;
-    if (cudaLaunchKernelEx(&cfg, k_head_tc<true, 2>, *static_cast<const CUtensorMap*>(mapA_hi), *static_cast<const CUtensorMap*>(mapA_lo),
-                           *static_cast<const CUtensorMap*>(mapB_hi), *static_cast<const CUtensorMap*>(mapB_lo), dn, ws, mode,
-                           s) != cudaSuccess)
-      return VPHO_ERR_LAUNCH;
-    return VPHO_OK;
+    e = launch_pdl(k_head_tc<true, 2>, dim3(2 * pairs), dim3(kHeadThreads), smem, st, 2, ah, al, bh, bl, dn, ws, mode, s);
+  } else {
+    const int n_items = n_tiles * dn.n_heads;
+    const int grid = n_items < n_sm ? n_items : n_sm;
+    e = half ? launch_pdl(k_head_tc<true, 1>, dim3(grid), dim3(kHeadThreads), smem, st, 1, ah, al, bh, bl, dn, ws, mode, s)
+             : launch_pdl(k_head_tc<false, 1>, dim3(grid), dim3(kHeadThreads), smem, st, 1, ah, al, bh, bl, dn, ws, mode, s);
   }
-  const int n_items = n_tiles * dn.n_heads;
-  const int grid = n_items < n_sm ? n_items : n_sm;
-  if (half)
-    VPHO_LAUNCH((k_head_tc<true, 1>), dim3(grid), dim3(kHeadThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
-                *static_cast<const CUtensorMap*>(mapA_lo), *static_cast<const CUtensorMap*>(mapB_hi),
-                *static_cast<const CUtensorMap*>(mapB_lo), dn, ws, mode, s);
-  else
-    VPHO_LAUNCH((k_head_tc<false, 1>), dim3(grid), dim3(kHeadThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
-                *static_cast<const CUtensorMap*>(mapA_lo), *static_cast<const CUtensorMap*>(mapB_hi),
-                *static_cast<const CUtensorMap*>(mapB_lo), dn, ws, mode, s);
-  VPHO_CHECK_LAUNCH();
-  return VPHO_OK;
+  return e == cudaSuccess ? VPHO_OK : VPHO_ERR_LAUNCH;
 }
 
 
@@ -1051,11 +1039,11 @@ int tc_launch_pose(const void* mapX_hi, const void* mapX_lo, const void* mapW1_h
     if (cudaFuncSetAttribute(k_pose_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return VPHO_ERR_LAUNCH;
     attr = true;
   }
-  VPHO_LAUNCH(k_pose_tc, dim3(ws.Npad / kTcBM), dim3(kHeadThreads), smem, st, *static_cast<const CUtensorMap*>(mapX_hi),
-              *static_cast<const CUtensorMap*>(mapX_lo), *static_cast<const CUtensorMap*>(mapW1_hi),
-              *static_cast<const CUtensorMap*>(mapW1_lo), *static_cast<const CUtensorMap*>(mapW2_hi),
-              *static_cast<const CUtensorMap*>(mapW2_lo), dn, ws, mode, s);
-  VPHO_CHECK_LAUNCH();
+  if (launch_pdl(k_pose_tc, dim3(ws.Npad / kTcBM), dim3(kHeadThreads), smem, st, 1, *static_cast<const CUtensorMap*>(mapX_hi),
+                 *static_cast<const CUtensorMap*>(mapX_lo), *static_cast<const CUtensorMap*>(mapW1_hi),
+                 *static_cast<const CUtensorMap*>(mapW1_lo), *static_cast<const CUtensorMap*>(mapW2_hi),
+                 *static_cast<const CUtensorMap*>(mapW2_lo), dn, ws, mode, s) != cudaSuccess)
+    return VPHO_ERR_LAUNCH;
   return VPHO_OK;
 }
 

@@ -1,6 +1,7 @@
 // Common definitions for the vpho_b200 sm_100a kernels.
 // The same sources compile under -DVPHO_EMU against tests/emu/cuda_emu.h (test-only SIMT emulator).
 #pragma once
+#include <cstdlib>
 
 #ifndef VPHO_EMU
 #include <cuda_runtime.h>
@@ -18,7 +19,47 @@ void profile_end(int tag, cudaStream_t st);
 #define VPHO_LAUNCH(kern, grid, block, smem, stream, ...) \
   do { ++::vpho::g_launches; kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); } while (0)
 #define VPHO_CONSTANT static __constant__
+// launch with programmatic stream serialization (see launch_pdl): the kernel MUST start with pdl_wait()
+#define VPHO_LAUNCH_PDL(kern, grid, block, smem, stream, ...) \
+  do { if (::vpho::launch_pdl(kern, (grid), (block), (smem), (stream), 1, __VA_ARGS__) != cudaSuccess) return VPHO_ERR_LAUNCH; } while (0)
 namespace vpho {
+// Programmatic dependent launch: a kernel launched with launch_pdl may be scheduled while its predecessor in the stream is
+// still running (after every CTA of the predecessor has executed pdl_trigger or exited).  It must execute pdl_wait() on
+// every path before touching anything an earlier kernel wrote; pdl_wait returns once the predecessor grid has completed and
+// its writes are visible.  VPHO_NO_PDL=1 falls back to plain stream-ordered launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VPHO_NO_PDL"); on = (e && e[0] == '1') ? 0 : 1; }
+  return on == 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = (unsigned)cluster_x;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = (unsigned)na;
+  ++g_launches;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 // 16-byte asynchronous global->shared copy (LDGSTS) and its group fences
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
@@ -29,7 +70,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 }  // namespace vpho
 #else
 #define VPHO_CONSTANT static
+#define VPHO_LAUNCH_PDL VPHO_LAUNCH
 namespace vpho {
+inline void pdl_wait() {}
+inline void pdl_trigger() {}
 inline void profile_begin(int, cudaStream_t) {}
 inline void profile_end(int, cudaStream_t) {}
 inline void cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }

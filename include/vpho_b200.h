@@ -95,6 +95,13 @@ int vpho_sample_finish(vpho_denoiser_t h, int n_rows, int rows_per_feat, int n_e
  * branch 'mano_pose' (lib/model/VPHO.py:318-326).  x6d [n][16][6] f32 -> pose_aa [n][48] f32. */
 int vpho_rot6d_to_axis_angle(const float* x6d, int n_rot, float* aa, void* stream);
 
+/* The whole of `vpho_net.postprocess_diffusion_hand`, branch 'mano_pose' (lib/model/VPHO.py:306-331) in one pass over the
+ * sampler's float64 output: xs [n_steps][n_rows][96] f64 (storage order of vpho_sample_begin's `xs`; n_steps = 1 for the
+ * final state `x`) -> out [n_rows][n_steps][58] f32 = 48 axis-angle parameters (after the float64 -> float32 rounding of
+ * `.float()`) + the 10 regressed shape coefficients of the row's image (shape [n_rows / rows_per_shape][10]). */
+int vpho_postprocess_hand(const double* xs, int n_steps, int n_rows, int rows_per_shape, const float* shape, float* out,
+                          void* stream);
+
 /* ---------------------------------------------------------------------------------- assets / aggregation ---- */
 /* Force-anchor tables (lib/utils/physics_fn.py:121-257, lib/utils/hand_fn.py:427-448) and per-object point tables
  * (lib/model/head_object.py:9-34).  HOST pointers: face_vertex_idx [32][3] int32, anchor_weight [32][2] f32,

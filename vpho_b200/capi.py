@@ -55,6 +55,7 @@ _SIGNATURES = {
     "vpho_sample_continue": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vpho_sample_finish": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vpho_rot6d_to_axis_angle": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "vpho_postprocess_hand": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vpho_assets_create": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                    C.POINTER(c_void_p)]),
     "vpho_assets_destroy": (c_int, [c_void_p]),

@@ -666,6 +666,34 @@ __global__ void k_rot6d_to_aa(const float* __restrict__ x6d, int n, float* __res
   aa[(size_t)i * 3 + 0] = a[0]; aa[(size_t)i * 3 + 1] = a[1]; aa[(size_t)i * 3 + 2] = a[2];
 }
 
+// Fused `postprocess_diffusion_hand` (VPHO.py:306-331): float64 sampler output in storage order [n_steps][n_rows][96]
+// -> float32 MANO vectors [n_rows][n_steps][58] = axis-angle of the 16 joints (the float64 -> float32 rounding of
+// `.float()`, then the same 6D -> matrix -> axis-angle arithmetic as k_rot6d_to_aa) followed by the image's 10 shape
+// coefficients.  One thread per (step, row, slot): slots 0..15 are joints, slot 16 copies the shape.
+__global__ void __launch_bounds__(256) k_postprocess_hand(const double* __restrict__ xs, int n_steps, int n_rows, int rows_per_shape,
+                                                         const float* __restrict__ shape, float* __restrict__ out) {
+  const size_t total = (size_t)n_steps * n_rows * 17;
+  for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (size_t)gridDim.x * blockDim.x) {
+    const int slot = (int)(it % 17);
+    const size_t sr = it / 17;
+    const int row = (int)(sr % n_rows), step = (int)(sr / n_rows);
+    float* dst = out + ((size_t)row * n_steps + step) * 58;
+    if (slot < 16) {
+      const double* src = xs + sr * 96 + slot * 6;
+      float d[6], R[9], a[3];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) d[k] = (float)src[k];
+      rot6d_to_matrix(d, R);
+      matrix_to_axis_angle(R, a);
+      dst[slot * 3 + 0] = a[0]; dst[slot * 3 + 1] = a[1]; dst[slot * 3 + 2] = a[2];
+    } else {
+      const float* sp = shape + (size_t)(row / rows_per_shape) * 10;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) dst[48 + k] = sp[k];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
@@ -1101,6 +1129,20 @@ extern "C" int vpho_sample_finish(vpho_denoiser_t h, int n_rows, int rows_per_fe
   int rc = launch_eval(dh, ws, kModeFinal, 0, st);
   if (rc) return rc;
   VPHO_LAUNCH(k_export, dim3(1), dim3(1), 0, st, ws);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
+
+extern "C" int vpho_postprocess_hand(const double* xs, int n_steps, int n_rows, int rows_per_shape, const float* shape,
+                                     float* out, void* stream) {
+  if (n_steps < 0 || n_rows < 0 || rows_per_shape <= 0) return VPHO_ERR_INVALID;
+  if (n_steps == 0 || n_rows == 0) return VPHO_OK;
+  if (!xs || !shape || !out) return VPHO_ERR_INVALID;
+  const size_t total = (size_t)n_steps * n_rows * 17;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  VPHO_LAUNCH(k_postprocess_hand, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, xs, n_steps, n_rows, rows_per_shape,
+              shape, out);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }

@@ -42,27 +42,27 @@ class VphoHotPath:
 
     # ---- vpho_net.postprocess_diffusion_hand, branch 'mano_pose' (VPHO.py:306-331) ----
     def postprocess_diffusion_hand(self, hand_inprocess, hand_final, pd_mano_shape):
+        """One fused pass per tensor (`vpho_postprocess_hand`): float64 6D rotations -> float32 axis-angle + shape.
+        hand_inprocess: the sampler's (N, steps, 96) permuted view of its [steps][N][96] buffer, or None."""
         S = self.sample_num
         bs = pd_mano_shape.shape[0]
         dev = hand_final.device
+        shape = pd_mano_shape.contiguous().float()
 
-        def to_aa(x6d):
-            x6d = x6d.contiguous().float()
-            n_rot = x6d.numel() // 6
-            aa = torch.empty((n_rot, 3), dtype=torch.float32, device=dev)
-            self.lib.check(self.lib.c.vpho_rot6d_to_axis_angle(capi.ptr(x6d), n_rot, capi.ptr(aa), capi.stream_of(x6d)),
-                           "vpho_rot6d_to_axis_angle")
-            return aa
+        def fused(x64, n_steps, n_rows):
+            out = torch.empty((n_rows, n_steps, 58), dtype=torch.float32, device=dev)
+            self.lib.check(self.lib.c.vpho_postprocess_hand(capi.ptr(x64), n_steps, n_rows, S, capi.ptr(shape), capi.ptr(out),
+                                                            capi.stream_of(x64)), "vpho_postprocess_hand")
+            return out
 
-        hf = to_aa(hand_final).reshape(bs, S, 48)
-        hf = torch.cat((hf, pd_mano_shape[:, None].expand(bs, S, 10)), dim=-1).reshape(-1, 58)
+        hf = fused(hand_final.contiguous().double(), 1, bs * S).reshape(-1, 58)
         hi = None
         if hand_inprocess is not None:
             n_in = hand_inprocess.shape[1]
-            # the sampler stores [steps][N][D]; rotations are independent, so convert in storage order and permute after
-            native = hand_inprocess.permute(1, 0, 2)
-            hi = to_aa(native).reshape(n_in, bs, S, 48).permute(1, 2, 0, 3)
-            hi = torch.cat((hi, pd_mano_shape[:, None, None].expand(bs, S, n_in, 10)), dim=-1).reshape(-1, n_in, 58)
+            native = hand_inprocess.permute(1, 0, 2)              # storage order [steps][N][96]
+            if not native.is_contiguous() or native.dtype != torch.float64:
+                native = native.contiguous().double()
+            hi = fused(native, n_in, bs * S)
         return hi, hf
 
     @torch.no_grad()

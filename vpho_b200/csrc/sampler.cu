@@ -212,7 +212,11 @@ __device__ __forceinline__ void time_term_block(const DenoiserDev& dn, const Sam
   __shared__ float part[4][kTtCols];
   const int tid = threadIdx.x;
   const float t32 = (float)eval_t64(c, mode, s);
-  if (block == 0 && tid == 255) ws.ctrl->et = eval_time(c, mode, s);       // read by the head GEMM of this call
+  if (block == 0 && tid == 255) {
+    const EvalTime et = eval_time(c, mode, s);
+    ws.ctrl->et = et;                                                      // read by the head GEMM of this call
+    if (mode == kModeInit0 || mode == kModeInit1 || mode == kModeStage) ws.ctrl->kcoef[k_slot_of(mode, s)] = et.coef;
+  }
   if (tid < 64) {
     // x_proj = t * W * 2 * np.pi in float32, left to right (denoiser.py:29-31)
     float xp = __fmul_rn(__fmul_rn(__fmul_rn(t32, dn.fourier_W[tid]), 2.0f), 3.14159265358979323846f);
@@ -601,12 +605,21 @@ __global__ void __launch_bounds__(256) k_reduce(SamplerWs ws, int kind) {
     is_last = (prev == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && tid == 0) {
+  if (is_last) {
+    // the last block to finish sums the per-block partials in a fixed order (strided per thread, then the same tree)
     __threadfence();
-    double s0 = 0.0, s1 = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) { s0 += ws.partial[b]; s1 += ws.partial[kMaxRedBlocks + b]; }
-    c.block_counter = 0u;
-    controller(ws, c, kind, s0, s1);
+    double p0 = 0.0, p1 = 0.0;
+    for (int b = tid; b < (int)gridDim.x; b += 256) { p0 += ws.partial[b]; p1 += ws.partial[kMaxRedBlocks + b]; }
+    sh0[tid] = p0; sh1[tid] = p1;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if (tid < st) { sh0[tid] += sh0[tid + st]; sh1[tid] += sh1[tid + st]; }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      c.block_counter = 0u;
+      controller(ws, c, kind, sh0[0], sh1[0]);
+    }
   }
 }
 
@@ -637,7 +650,11 @@ __global__ void __launch_bounds__(256) k_post_step(SamplerWs ws) {
       }
     }
     ws.y[i] = ws.ynew[i];
-    ws.K[i] = kval(ws.K, c, 6, n, i);
+    // f <- f_new (first-same-as-last): slot 0 takes slot 6's scores (its coefficient follows once every block is done);
+    // a value nan_to_num would have zeroed is stored as -0 so that it reads back as the +0 kval returns for it
+    float r = ws.K[(size_t)6 * n + i];
+    if (c.nan_stage[6] && !isfinite(r)) r = -0.f;
+    ws.K[i] = r;
   }
   __shared__ bool is_last;
   __syncthreads();
@@ -648,6 +665,7 @@ __global__ void __launch_bounds__(256) k_post_step(SamplerWs ws) {
     if (is_last) {
       c.block_counter = 0u;
       c.accepted_now = 0;
+      c.kcoef[0] = c.kcoef[6];
       for (int k = 0; k < 7; ++k) c.nan_stage[k] = 0;
     }
   }
@@ -723,7 +741,7 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
   const size_t o_Flo = take(Rpad * kFDim * 4);
   const size_t o_y = take(n * 8);
   const size_t o_yn = take(n * 8);
-  const size_t o_K = take(7 * n * 8);
+  const size_t o_K = take(7 * n * 4);
   const size_t o_part = take((size_t)2 * kMaxRedBlocks * 8);
   const size_t o_te = take((size_t)(n_eval > 0 ? n_eval : 1) * 8);
   if (ws) {
@@ -743,7 +761,7 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
     ws->FeatLo = reinterpret_cast<float*>(b + o_Flo);
     ws->y = reinterpret_cast<double*>(b + o_y);
     ws->ynew = reinterpret_cast<double*>(b + o_yn);
-    ws->K = reinterpret_cast<double*>(b + o_K);
+    ws->K = reinterpret_cast<float*>(b + o_K);
     ws->partial = reinterpret_cast<double*>(b + o_part);
     ws->t_eval = reinterpret_cast<double*>(b + o_te);
     ws->eval_out = nullptr; ws->eval_x = nullptr;

@@ -72,6 +72,7 @@ struct RkCtrl {
   int nfev, n_acc, n_rej, attempts, finished_final;
   int nan_seen;     // any NaN ever produced by the network (score_based_model.py:69-71)
   int nan_stage[8]; // K slot s holds non-finite values that must read as 0 (nan_to_num)
+  double kcoef[8];  // K slot s holds raw float32 scores; its float64 value is -(kcoef[s] * score)  (kval)
   unsigned int block_counter;
   float eval_t32;   // vpho_score_eval: the time of a stand-alone evaluation
   EvalTime et;      // scalars of the network call in flight, written by its first kernel (time-term block 0)
@@ -97,7 +98,7 @@ struct SamplerWs {
   float* FeatLo;
   double* y;       // [n]
   double* ynew;    // [n]
-  double* K;       // [7][n]
+  float* K;        // [7][n] raw network outputs (float32) of the RK stages; see kval for the float64 drift they stand for
   double* partial; // [3][kMaxRedBlocks]
   double* t_eval;  // [n_eval]
   float* eval_out; // vpho_score_eval: output / input / geometry of a stand-alone evaluation

@@ -68,11 +68,15 @@ __device__ __forceinline__ EvalTime eval_time(const RkCtrl& c, int mode, int s) 
 }
 
 // K slot value with the reference's `nan_to_num(score, 0, 0, 0)` applied when that evaluation produced a NaN
-__device__ __forceinline__ double kval(const double* K, const RkCtrl& c, int slot, int n, int i) {
-  double v = K[(size_t)slot * n + i];
+// The slot stores the float32 score; the drift  -0.5 g(t)^2 * score  is formed here in float64 exactly as
+// `drift - 0.5 * diffusion**2 * score` is under numpy >= 2 promotion, so keeping the narrow value in
+// memory halves the K traffic of every RK kernel without changing a bit of the result.
+__device__ __forceinline__ double kval(const float* K, const RkCtrl& c, int slot, int n, int i) {
+  double v = -(c.kcoef[slot] * (double)K[(size_t)slot * n + i]);
   if (c.nan_stage[slot] && !isfinite(v)) v = 0.0;
   return v;
 }
+__device__ __forceinline__ int k_slot_of(int mode, int s) { return (mode == kModeInit0) ? 0 : (mode == kModeInit1 ? 1 : s); }
 
 __device__ __forceinline__ bool eval_active(const RkCtrl& c, int mode) {
   if (mode == kModeEval) return true;
@@ -94,10 +98,9 @@ __device__ __forceinline__ void emit_score(const SamplerWs& ws, RkCtrl& c, const
     c.x_out[i] = __dadd_rn(ws.y[i], (double)__fmul_rn(drift, scale));
     return;
   }
-  const int slot = (mode == kModeInit0) ? 0 : (mode == kModeInit1 ? 1 : s);
+  const int slot = k_slot_of(mode, s);
   if (isnan(score)) { c.nan_stage[slot] = 1; c.nan_seen = 1; }
-  // drift - 0.5 * diffusion**2 * score, float64 (numpy >= 2 promotion)
-  ws.K[(size_t)slot * c.n + i] = -(et.coef * (double)score);
+  ws.K[(size_t)slot * c.n + i] = score;          // read back through kval with kcoef[slot] = et.coef of this call
 }
 
 

@@ -1001,11 +1001,14 @@ int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi
   if (ctas == 2) {
     if (!half) return VPHO_ERR_INVALID;
     const int n_items = ((n_tiles + 1) / 2) * dn.n_heads;
-    const int pairs = n_items < n_sm / 2 ? n_items : n_sm / 2;
+    // the fewest CTA pairs that keep the same number of rounds: SMs left over go to the other sampler's stream
+    const int rounds = (n_items + n_sm / 2 - 1) / (n_sm / 2);
+    const int pairs = (n_items + rounds - 1) / rounds;
     e = launch_pdl(k_head_tc<true, 2>, dim3(2 * pairs), dim3(kHeadThreads), smem, st, 2, ah, al, bh, bl, dn, ws, mode, s);
   } else {
     const int n_items = n_tiles * dn.n_heads;
-    const int grid = n_items < n_sm ? n_items : n_sm;
+    const int rounds = (n_items + n_sm - 1) / n_sm;
+    const int grid = (n_items + rounds - 1) / rounds;       // e.g. 150 items: 75 CTAs x 2 rather than 148 CTAs, 2 of them x 2
     e = half ? launch_pdl(k_head_tc<true, 1>, dim3(grid), dim3(kHeadThreads), smem, st, 1, ah, al, bh, bl, dn, ws, mode, s)
              : launch_pdl(k_head_tc<false, 1>, dim3(grid), dim3(kHeadThreads), smem, st, 1, ah, al, bh, bl, dn, ws, mode, s);
   }

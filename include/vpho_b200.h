@@ -91,6 +91,32 @@ int vpho_sample_continue(vpho_denoiser_t h, int n_rows, int rows_per_feat, int n
 int vpho_sample_finish(vpho_denoiser_t h, int n_rows, int rows_per_feat, int n_eval, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Two samplers in lock-step.  `vpho_net.forward(mode='predict')` integrates the hand ODE and the object ODE of the same
+ * batch back to back (lib/model/VPHO.py:239-262); both issue the same sequence of network calls (2 + 6 per RK attempt
+ * + 1), so the pair entry points serve both integrations with ONE launch per kernel of that sequence -- the object's work
+ * fills the SMs the hand's leaves idle instead of competing for them from another stream.  Each sampler keeps its own
+ * controller, workspace and outputs, and its results are bit-identical to vpho_sample_begin/continue/finish on its own
+ * arguments.  The structure holds exactly the per-sampler arguments of vpho_sample_begin. */
+typedef struct {
+  vpho_denoiser_t denoiser;
+  const float* feat;       /* [ceil(n_rows / rows_per_feat)][1024] */
+  int n_rows, rows_per_feat;
+  const float* init_x;     /* [n_rows][D] prior draw */
+  double T0, eps;
+  const double* t_eval;    /* device, or NULL for linspace(T0, eps, n_eval) */
+  int n_eval;
+  double rtol, atol, max_step;
+  int num_steps;
+  double* xs;              /* [n_eval][n_rows][D] or NULL */
+  double* x;               /* [n_rows][D] */
+  int32_t* counters;       /* [8] status word */
+  void* workspace;
+  size_t workspace_bytes;
+} vpho_sample_args;
+int vpho_sample_pair_begin(const vpho_sample_args* a, const vpho_sample_args* b, int max_attempts, void* stream);
+int vpho_sample_pair_continue(const vpho_sample_args* a, const vpho_sample_args* b, int max_attempts, void* stream);
+int vpho_sample_pair_finish(const vpho_sample_args* a, const vpho_sample_args* b, void* stream);
+
 /* 6D -> axis-angle for the hand finals (+ regressed shape): `vpho_net.postprocess_diffusion_hand`
  * branch 'mano_pose' (lib/model/VPHO.py:318-326).  x6d [n][16][6] f32 -> pose_aa [n][48] f32. */
 int vpho_rot6d_to_axis_angle(const float* x6d, int n_rot, float* aa, void* stream);

@@ -36,6 +36,20 @@ def test_product_loader_refuses_to_run_without_cuda():
 
 def test_hoi_args_struct_matches_header_field_order():
     hdr = open(os.path.join(ROOT, "include", "vpho_b200.h")).read()
-    body = hdr[hdr.index("typedef struct {"):hdr.index("} vpho_hoi_args;")]
+    end = hdr.index("} vpho_hoi_args;")
+    body = hdr[hdr.rindex("typedef struct {", 0, end):end]
     fields = re.findall(r"\b([a-zA-Z_0-9]+);", body)
     assert fields == [f[0] for f in capi.HoiArgs._fields_]
+
+
+def test_sample_args_struct_matches_header_field_order():
+    hdr = open(os.path.join(ROOT, "include", "vpho_b200.h")).read()
+    end = hdr.index("} vpho_sample_args;")
+    body = re.sub(r"/\*.*?\*/", "", hdr[hdr.rindex("typedef struct {", 0, end) + len("typedef struct {"):end], flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        if decl.strip():
+            names = decl.split(",")
+            fields.append(names[0].split()[-1].lstrip("*"))          # "const float* feat" -> feat
+            fields += [n.strip().lstrip("*") for n in names[1:]]      # "int n_rows, rows_per_feat"
+    assert fields == [f[0] for f in capi.SampleArgs._fields_]

@@ -193,3 +193,33 @@ def test_sampler_cuda_matches_reference_golden(cuda_lib, name, tol):
     assert agent.last_info["net_calls"] == int(g["net_calls"])
     assert (np.abs(x.cpu().numpy() - g["x"]) <= tol * np.maximum(1, np.abs(g["x"]))).all()
     assert (np.abs(xs.cpu().numpy() - g["xs"]) <= tol * np.maximum(1, np.abs(g["xs"]))).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bs_a,bs_b,S,std_a,std_b", [(4, 4, 100, 0.05, 0.05), (3, 5, 30, 0.05, 0.5), (2, 1, 7, 0.5, 0.05)])
+def test_sampler_cuda_pair_is_bit_identical_to_separate_samplers(cuda_lib, bs_a, bs_b, S, std_a, std_b):
+    """`sample_pair` (hand and object integrations advanced in lock-step through shared launches, `vpho_sample_pair_*`)
+    must reproduce two separate `sample()` calls bit for bit -- including when one integration needs more RK attempts
+    than the other (stiff scores on one side), odd tile counts and different batch sizes."""
+    den_a, _, enc_a, _, g = _setup("mano_pose", cuda_lib, bs_a, S, std_a, seed=1)
+    den_b, _, enc_b, _, _ = _setup("obj", cuda_lib, bs_b, S, std_b, seed=2)
+    agent = ScoreBasedModelAgent(sampling_steps=20, sample_num=S)
+    pa = torch.randn(bs_a * S, den_a.out_dim, generator=g) * ve_prior_std(0.65)
+    pb = torch.randn(bs_b * S, den_b.out_dim, generator=g) * ve_prior_std(0.65)
+    da = {"feat_unique": enc_a.cuda(), "n_rows": bs_a * S}
+    db = {"feat_unique": enc_b.cuda(), "n_rows": bs_b * S}
+    xs_a, x_a = agent.sample(da, den_a, 0.65, prior=pa)
+    info_a = dict(agent.last_info)
+    xs_b, x_b = agent.sample(db, den_b, 0.65, prior=pb)
+    info_b = dict(agent.last_info)
+    for _ in range(8):
+        (ys_a, y_a, pend_a), (ys_b, y_b, pend_b) = agent.sample_pair(da, den_a, db, den_b, 0.65, prior_a=pa, prior_b=pb)
+        torch.cuda.synchronize()
+        if all([pend_a.resolve(), pend_b.resolve()]):
+            break
+    else:
+        raise AssertionError("pair sampler did not converge")
+    for k in ("nfev", "accepted", "rejected"):
+        assert pend_a.info[k] == info_a[k] and pend_b.info[k] == info_b[k]
+    assert torch.equal(y_a, x_a) and torch.equal(y_b, x_b)
+    assert torch.equal(ys_a, xs_a) and torch.equal(ys_b, xs_b)

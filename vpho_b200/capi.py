@@ -18,6 +18,16 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libvpho_b200.so")
 c_void_p, c_int, c_float, c_double, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t
 
 
+class SampleArgs(C.Structure):
+    """`vpho_sample_args` (include/vpho_b200.h): the per-sampler arguments of vpho_sample_begin."""
+    _fields_ = [
+        ("denoiser", c_void_p), ("feat", c_void_p), ("n_rows", c_int), ("rows_per_feat", c_int), ("init_x", c_void_p),
+        ("T0", c_double), ("eps", c_double), ("t_eval", c_void_p), ("n_eval", c_int),
+        ("rtol", c_double), ("atol", c_double), ("max_step", c_double), ("num_steps", c_int),
+        ("xs", c_void_p), ("x", c_void_p), ("counters", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
 class HoiArgs(C.Structure):
     _fields_ = [
         ("bs", c_int), ("S", c_int), ("topk_hand", c_int), ("topk_obj", c_int), ("phy_topk", c_int),
@@ -54,6 +64,9 @@ _SIGNATURES = {
                                   c_size_t, c_void_p]),
     "vpho_sample_continue": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vpho_sample_finish": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "vpho_sample_pair_begin": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "vpho_sample_pair_continue": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "vpho_sample_pair_finish": (c_int, [c_void_p, c_void_p, c_void_p]),
     "vpho_rot6d_to_axis_angle": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "vpho_postprocess_hand": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vpho_assets_create": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,

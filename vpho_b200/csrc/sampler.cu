@@ -31,11 +31,8 @@ bool tc_available();
 bool tc_make_map(void* map, const void* base, int rows, int box_rows, int kdim, bool half = false);
 int tc_launch_feat(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const float* feat,
                    float* feat_hi, float* feat_lo, const float* ba, float* F, int R, int hid, cudaStream_t st);
-int tc_launch_pose(const void* mapX_hi, const void* mapX_lo, const void* mapW1_hi, const void* mapW1_lo, const void* mapW2_hi,
-                   const void* mapW2_lo, const DenoiserDev& dn,
-                   const SamplerWs& ws, int mode, int s, cudaStream_t st);
-int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const DenoiserDev& dn,
-                   const SamplerWs& ws, int mode, int s, bool half, int ctas, cudaStream_t st);
+int tc_launch_pose(const TcPoseJob* jobs, int n_jobs, int mode, int s, cudaStream_t st);
+int tc_launch_head(const TcHeadJob* jobs, int n_jobs, int mode, int s, bool half, int ctas, cudaStream_t st);
 
 struct alignas(64) TensorMapBlob { unsigned char b[128]; };
 
@@ -256,16 +253,15 @@ __global__ void __launch_bounds__(256) k_time_term(DenoiserDev dn, SamplerWs ws,
 
 // tcgen05 path: one launch does the time-term (first `nb_time` blocks) and the float64 RK stage combination of every
 // state element into the (hi, lo) TF32 planes of the pose encoder's A operand (remaining blocks), all SMs busy.
-__global__ void __launch_bounds__(256) k_stage_x(DenoiserDev dn, SamplerWs ws, int mode, int s, int nb_time) {
-  pdl_wait();                 // launched with launch_pdl: nothing of the previous kernel may be read above this line
-  pdl_trigger();
+__device__ __forceinline__ void stage_x_block(const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, int nb_time, int bid,
+                                              int n_blocks) {
   const RkCtrl& c = *ws.ctrl;
   if (!eval_active(c, mode)) return;
-  if ((int)blockIdx.x < nb_time) { time_term_block(dn, ws, c, mode, s, blockIdx.x); return; }
+  if (bid < nb_time) { time_term_block(dn, ws, c, mode, s, bid); return; }
   const int D = dn.D, Kx = ws.Kx;
   const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
   const int total = ws.Npad * Kx;
-  for (int it = (blockIdx.x - nb_time) * 256 + threadIdx.x; it < total; it += (gridDim.x - nb_time) * 256) {
+  for (int it = (bid - nb_time) * 256 + threadIdx.x; it < total; it += (n_blocks - nb_time) * 256) {
     const int row = it / Kx, k = it - row * Kx;
     float x = 0.f;
     if (k < D) x = (float)stage_input(ws, c, mode, s, row, k, n_rows, D);
@@ -273,6 +269,15 @@ __global__ void __launch_bounds__(256) k_stage_x(DenoiserDev dn, SamplerWs ws, i
     ws.Xhi[it] = hi;
     ws.Xlo[it] = tf32_round(x - hi);
   }
+}
+
+// blocks [0, blocks0) work for job 0, the rest for job 1 (two samplers in lock-step; blocks0 = gridDim.x for one)
+__global__ void __launch_bounds__(256) k_stage_x(DenoiserDev dn0, SamplerWs ws0, DenoiserDev dn1, SamplerWs ws1, int blocks0, int mode,
+                                                int s, int nb_time0, int nb_time1) {
+  pdl_wait();                 // launched with launch_pdl: nothing of the previous kernel may be read above this line
+  pdl_trigger();
+  if ((int)blockIdx.x < blocks0) stage_x_block(dn0, ws0, mode, s, nb_time0, blockIdx.x, blocks0);
+  else stage_x_block(dn1, ws1, mode, s, nb_time1, (int)blockIdx.x - blocks0, (int)gridDim.x - blocks0);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -563,16 +568,14 @@ __device__ void controller(const SamplerWs& ws, RkCtrl& c, int kind, double s0, 
   export_counters(ws, c);
 }
 
-__global__ void __launch_bounds__(256) k_reduce(SamplerWs ws, int kind) {
-  pdl_wait();
-  pdl_trigger();
+__device__ __forceinline__ void reduce_block(const SamplerWs& ws, int kind, int bid, int n_blocks) {
   RkCtrl& c = *ws.ctrl;
   if (c.status != 0) return;
   __shared__ double sh0[256], sh1[256];
   __shared__ bool is_last;
   const int tid = threadIdx.x, n = c.n;
   double a0 = 0.0, a1 = 0.0;
-  for (int i = blockIdx.x * 256 + tid; i < n; i += gridDim.x * 256) {
+  for (int i = bid * 256 + tid; i < n; i += n_blocks * 256) {
     const double y = ws.y[i];
     if (kind == kRedInit0) {
       const double scale = c.atol + fabs(y) * c.rtol;
@@ -598,18 +601,18 @@ __global__ void __launch_bounds__(256) k_reduce(SamplerWs ws, int kind) {
     __syncthreads();
   }
   if (tid == 0) {
-    ws.partial[blockIdx.x] = sh0[0];
-    ws.partial[kMaxRedBlocks + blockIdx.x] = sh1[0];
+    ws.partial[bid] = sh0[0];
+    ws.partial[kMaxRedBlocks + bid] = sh1[0];
     __threadfence();
     const unsigned prev = atomicAdd(&c.block_counter, 1u);
-    is_last = (prev == gridDim.x - 1);
+    is_last = (prev == (unsigned)n_blocks - 1u);
   }
   __syncthreads();
   if (is_last) {
     // the last block to finish sums the per-block partials in a fixed order (strided per thread, then the same tree)
     __threadfence();
     double p0 = 0.0, p1 = 0.0;
-    for (int b = tid; b < (int)gridDim.x; b += 256) { p0 += ws.partial[b]; p1 += ws.partial[kMaxRedBlocks + b]; }
+    for (int b = tid; b < n_blocks; b += 256) { p0 += ws.partial[b]; p1 += ws.partial[kMaxRedBlocks + b]; }
     sh0[tid] = p0; sh1[tid] = p1;
     __syncthreads();
     for (int st = 128; st > 0; st >>= 1) {
@@ -623,16 +626,21 @@ __global__ void __launch_bounds__(256) k_reduce(SamplerWs ws, int kind) {
   }
 }
 
-// after an accepted step: quartic dense output at the t_eval points inside the step, then roll y <- y_new, f <- f_new
-__global__ void __launch_bounds__(256) k_post_step(SamplerWs ws) {
+__global__ void __launch_bounds__(256) k_reduce(SamplerWs ws0, SamplerWs ws1, int blocks0, int kind) {
   pdl_wait();
   pdl_trigger();
+  if ((int)blockIdx.x < blocks0) reduce_block(ws0, kind, blockIdx.x, blocks0);
+  else reduce_block(ws1, kind, (int)blockIdx.x - blocks0, (int)gridDim.x - blocks0);
+}
+
+// after an accepted step: quartic dense output at the t_eval points inside the step, then roll y <- y_new, f <- f_new
+__device__ __forceinline__ void post_step_block(const SamplerWs& ws, int bid, int n_blocks) {
   RkCtrl& c = *ws.ctrl;
   if (c.status < 0 || !c.accepted_now) return;
   const int n = c.n;
   const int lo = c.te_lo, hi = c.te_hi;
   const double h = c.h_done, t_old = c.t_old;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+  for (int i = bid * 256 + threadIdx.x; i < n; i += n_blocks * 256) {
     const double y_old = ws.y[i];
     if (c.xs && hi > lo) {
       double Q[4] = {0, 0, 0, 0};
@@ -661,7 +669,7 @@ __global__ void __launch_bounds__(256) k_post_step(SamplerWs ws) {
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned prev = atomicAdd(&c.block_counter, 1u);
-    is_last = (prev == gridDim.x - 1);
+    is_last = (prev == (unsigned)n_blocks - 1u);
     if (is_last) {
       c.block_counter = 0u;
       c.accepted_now = 0;
@@ -669,6 +677,13 @@ __global__ void __launch_bounds__(256) k_post_step(SamplerWs ws) {
       for (int k = 0; k < 7; ++k) c.nan_stage[k] = 0;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) k_post_step(SamplerWs ws0, SamplerWs ws1, int blocks0) {
+  pdl_wait();
+  pdl_trigger();
+  if ((int)blockIdx.x < blocks0) post_step_block(ws0, blockIdx.x, blocks0);
+  else post_step_block(ws1, (int)blockIdx.x - blocks0, (int)gridDim.x - blocks0);
 }
 
 __global__ void k_export(SamplerWs ws) { export_counters(ws, *ws.ctrl); }
@@ -799,67 +814,132 @@ static int launch_feat_term(DenoiserHost& dh, const SamplerWs& ws, const float* 
   return VPHO_OK;
 }
 
-static int launch_eval(DenoiserHost& dh, const SamplerWs& ws, int mode, int s, cudaStream_t st) {
-  const DenoiserDev& dn = dh.dev;
-  profile_begin(VPHO_TAG_POSE_ENCODER, st);
+// One sampler's state on the host side of a launch; two of them advance in lock-step through the same kernel launches.
+struct SamplerJob { DenoiserHost* dh; SamplerWs ws; int ws_n; /* n_rows * D */ };
+
+static int stage_x_blocks(const DenoiserDev& dn, const SamplerWs& ws, int* nb_time) {
+  *nb_time = (dn.hid + kTtCols - 1) / kTtCols;
+  int nb_x = (ws.Npad * ws.Kx + 1023) / 1024;           // ~4 elements per thread
+  if (nb_x > 592) nb_x = 592;
+  return *nb_time + nb_x;
+}
+
+// One network evaluation of every job: stage input + time term, pose encoder, head GEMM.
+static int launch_eval(SamplerJob* jobs, int n_jobs, int mode, int s, cudaStream_t st) {
 #ifndef VPHO_EMU
-  if (ws.P2hi && dh.use_tc_pose) {
-    const int nb_time = (dn.hid + kTtCols - 1) / kTtCols;
-    int nb_x = (ws.Npad * ws.Kx + 1023) / 1024;           // ~4 elements per thread
-    if (nb_x > 592) nb_x = 592;
-    profile_begin(VPHO_TAG_STAGE_X, st);
-    VPHO_LAUNCH_PDL(k_stage_x, dim3(nb_time + nb_x), dim3(256), 0, st, dn, ws, mode, s, nb_time);
-    profile_end(VPHO_TAG_STAGE_X, st);
-    if (dh.mapX_for != ws.Xhi || dh.mapX_rows != ws.Npad) {
-      if (!tc_make_map(&dh.mapX_hi, ws.Xhi, ws.Npad, 128, ws.Kx) || !tc_make_map(&dh.mapX_lo, ws.Xlo, ws.Npad, 128, ws.Kx)) return VPHO_ERR_LAUNCH;
-      dh.mapX_for = ws.Xhi;
-      dh.mapX_rows = ws.Npad;
+  bool all_tc = true;
+  for (int j = 0; j < n_jobs; ++j) all_tc = all_tc && jobs[j].ws.P2hi && jobs[j].dh->use_tc_pose;
+  // two jobs share launches only on the CTA-pair FP16 path; anything else runs them one after the other
+  if (n_jobs == 2 && !(all_tc && jobs[0].ws.P2scale && jobs[1].ws.P2scale && jobs[0].dh->pair_min_heads < (1 << 30))) {
+    for (int j = 0; j < 2; ++j) {
+      int rc = launch_eval(jobs + j, 1, mode, s, st);
+      if (rc) return rc;
     }
-    int rc = tc_launch_pose(&dh.mapX_hi, &dh.mapX_lo, &dh.mapW1_hi, &dh.mapW1_lo, &dh.mapW2_hi, &dh.mapW2_lo, dn, ws, mode, s, st);
+    return VPHO_OK;
+  }
+  if (all_tc) {
+    SamplerJob& j0 = jobs[0];
+    SamplerJob& j1 = jobs[n_jobs - 1];
+    profile_begin(VPHO_TAG_POSE_ENCODER, st);
+    int nbt0 = 0, nbt1 = 0;
+    const int b0 = stage_x_blocks(j0.dh->dev, j0.ws, &nbt0), b1 = n_jobs > 1 ? stage_x_blocks(j1.dh->dev, j1.ws, &nbt1) : 0;
+    profile_begin(VPHO_TAG_STAGE_X, st);
+    VPHO_LAUNCH_PDL(k_stage_x, dim3(b0 + b1), dim3(256), 0, st, j0.dh->dev, j0.ws, j1.dh->dev, j1.ws, b0, mode, s, nbt0, nbt1);
+    profile_end(VPHO_TAG_STAGE_X, st);
+    TcPoseJob pj[2];
+    TcHeadJob hj[2];
+    bool half = true, pair = n_jobs > 1;
+    for (int j = 0; j < n_jobs; ++j) {
+      DenoiserHost& dh = *jobs[j].dh;
+      const SamplerWs& ws = jobs[j].ws;
+      if (dh.mapX_for != ws.Xhi || dh.mapX_rows != ws.Npad) {
+        if (!tc_make_map(&dh.mapX_hi, ws.Xhi, ws.Npad, 128, ws.Kx) || !tc_make_map(&dh.mapX_lo, ws.Xlo, ws.Npad, 128, ws.Kx)) return VPHO_ERR_LAUNCH;
+        dh.mapX_for = ws.Xhi;
+        dh.mapX_rows = ws.Npad;
+      }
+      const bool h16 = ws.P2scale != nullptr;
+      if (dh.mapA_for != ws.P2hi || dh.mapA_rows != ws.Npad || dh.mapA_half != h16) {
+        if (!tc_make_map(&dh.mapA_hi, ws.P2hi, ws.Npad, 128, kPDim, h16) || !tc_make_map(&dh.mapA_lo, ws.P2lo, ws.Npad, 128, kPDim, h16))
+          return VPHO_ERR_LAUNCH;
+        dh.mapA_for = ws.P2hi;
+        dh.mapA_rows = ws.Npad;
+        dh.mapA_half = h16;
+      }
+      half = half && h16;
+      pair = pair || (h16 && dh.dev.n_heads >= dh.pair_min_heads);
+      pj[j] = TcPoseJob{&dh.mapX_hi, &dh.mapX_lo, &dh.mapW1_hi, &dh.mapW1_lo, &dh.mapW2_hi, &dh.mapW2_lo, &dh.dev, &jobs[j].ws};
+    }
+    for (int j = 0; j < n_jobs; ++j) {
+      DenoiserHost& dh = *jobs[j].dh;
+      hj[j] = pair   ? TcHeadJob{&dh.mapA_hi, &dh.mapA_lo, &dh.mapBp_hi, &dh.mapBp_lo, &dh.dev, &jobs[j].ws}
+              : half ? TcHeadJob{&dh.mapA_hi, &dh.mapA_lo, &dh.mapBh_hi, &dh.mapBh_lo, &dh.dev, &jobs[j].ws}
+                     : TcHeadJob{&dh.mapA_hi, &dh.mapA_lo, &dh.mapB_hi, &dh.mapB_lo, &dh.dev, &jobs[j].ws};
+    }
+    int rc = tc_launch_pose(pj, n_jobs, mode, s, st);
     if (rc) return rc;
-  } else
+    profile_end(VPHO_TAG_POSE_ENCODER, st);
+    const int tag = j0.dh->dev.n_heads >= 16 ? VPHO_TAG_HEAD_GEMM_HAND : VPHO_TAG_HEAD_GEMM_OBJ;
+    profile_begin(tag, st);
+    rc = tc_launch_head(hj, n_jobs, mode, s, half, pair ? 2 : 1, st);
+    if (rc) return rc;
+    profile_end(tag, st);
+    return VPHO_OK;
+  }
 #endif
-  {
+  for (int j = 0; j < n_jobs; ++j) {
+    DenoiserHost& dh = *jobs[j].dh;
+    const DenoiserDev& dn = dh.dev;
+    const SamplerWs& ws = jobs[j].ws;
+    profile_begin(VPHO_TAG_POSE_ENCODER, st);
     VPHO_LAUNCH(k_time_term, dim3((dn.hid + kTtCols - 1) / kTtCols), dim3(256), 0, st, dn, ws, mode, s);
     VPHO_LAUNCH(k_pose_encoder, dim3(ws.Npad / kPeRows), dim3(256), 0, st, dn, ws, mode, s);
-  }
-  profile_end(VPHO_TAG_POSE_ENCODER, st);
-  const int tag = dn.n_heads >= 16 ? VPHO_TAG_HEAD_GEMM_HAND : VPHO_TAG_HEAD_GEMM_OBJ;
-  profile_begin(tag, st);
-  if (ws.P2hi) {
+    profile_end(VPHO_TAG_POSE_ENCODER, st);
+    const int tag = dn.n_heads >= 16 ? VPHO_TAG_HEAD_GEMM_HAND : VPHO_TAG_HEAD_GEMM_OBJ;
+    profile_begin(tag, st);
 #ifndef VPHO_EMU
-    const bool half = ws.P2scale != nullptr;
-    if (dh.mapA_for != ws.P2hi || dh.mapA_rows != ws.Npad || dh.mapA_half != half) {
-      if (!tc_make_map(&dh.mapA_hi, ws.P2hi, ws.Npad, 128, kPDim, half) || !tc_make_map(&dh.mapA_lo, ws.P2lo, ws.Npad, 128, kPDim, half))
-        return VPHO_ERR_LAUNCH;
-      dh.mapA_for = ws.P2hi;
-      dh.mapA_rows = ws.Npad;
-      dh.mapA_half = half;
-    }
-    const bool pair = half && dn.n_heads >= dh.pair_min_heads;
-    int rc = pair   ? tc_launch_head(&dh.mapA_hi, &dh.mapA_lo, &dh.mapBp_hi, &dh.mapBp_lo, dn, ws, mode, s, true, 2, st)
-             : half ? tc_launch_head(&dh.mapA_hi, &dh.mapA_lo, &dh.mapBh_hi, &dh.mapBh_lo, dn, ws, mode, s, true, 1, st)
-                    : tc_launch_head(&dh.mapA_hi, &dh.mapA_lo, &dh.mapB_hi, &dh.mapB_lo, dn, ws, mode, s, false, 1, st);
-    if (rc) return rc;
+    if (ws.P2hi) {
+      // tensor-core head GEMM behind the SIMT pose encoder (VPHO_POSE_ENCODER=simt): 3xTF32 planes, one CTA per item
+      if (dh.mapA_for != ws.P2hi || dh.mapA_rows != ws.Npad || dh.mapA_half) {
+        if (!tc_make_map(&dh.mapA_hi, ws.P2hi, ws.Npad, 128, kPDim, false) || !tc_make_map(&dh.mapA_lo, ws.P2lo, ws.Npad, 128, kPDim, false))
+          return VPHO_ERR_LAUNCH;
+        dh.mapA_for = ws.P2hi;
+        dh.mapA_rows = ws.Npad;
+        dh.mapA_half = false;
+      }
+      TcHeadJob hj{&dh.mapA_hi, &dh.mapA_lo, &dh.mapB_hi, &dh.mapB_lo, &dh.dev, &jobs[j].ws};
+      int rc = tc_launch_head(&hj, 1, mode, s, false, 1, st);
+      if (rc) return rc;
+    } else
 #endif
-  } else {
-    VPHO_LAUNCH(k_head_simt, dim3(ws.Npad / kRowTile, dn.n_heads), dim3(256), 0, st, dn, ws, mode, s);
+    {
+      VPHO_LAUNCH(k_head_simt, dim3(ws.Npad / kRowTile, dn.n_heads), dim3(256), 0, st, dn, ws, mode, s);
+    }
+    profile_end(tag, st);
+    VPHO_CHECK_LAUNCH();
   }
-  profile_end(tag, st);
-  VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }
 
-static int launch_attempts(DenoiserHost& dh, const SamplerWs& ws, int n, int max_attempts, cudaStream_t st) {
-  const int rb = red_blocks(n);
+static int launch_reduce(SamplerJob* jobs, int n_jobs, int kind, cudaStream_t st) {
+  const SamplerWs& w0 = jobs[0].ws;
+  const SamplerWs& w1 = jobs[n_jobs - 1].ws;
+  const int b0 = red_blocks(jobs[0].ws_n), b1 = n_jobs > 1 ? red_blocks(jobs[1].ws_n) : 0;
+  VPHO_LAUNCH_PDL(k_reduce, dim3(b0 + b1), dim3(256), 0, st, w0, w1, b0, kind);
+  return VPHO_OK;
+}
+
+static int launch_attempts(SamplerJob* jobs, int n_jobs, int max_attempts, cudaStream_t st) {
+  const SamplerWs& w0 = jobs[0].ws;
+  const SamplerWs& w1 = jobs[n_jobs - 1].ws;
+  const int b0 = red_blocks(jobs[0].ws_n), b1 = n_jobs > 1 ? red_blocks(jobs[1].ws_n) : 0;
   for (int a = 0; a < max_attempts; ++a) {
     for (int s = 1; s <= 6; ++s) {
-      int rc = launch_eval(dh, ws, kModeStage, s, st);
+      int rc = launch_eval(jobs, n_jobs, kModeStage, s, st);
       if (rc) return rc;
     }
     profile_begin(VPHO_TAG_RK_CONTROL, st);
-    VPHO_LAUNCH_PDL(k_reduce, dim3(rb), dim3(256), 0, st, ws, (int)kRedErr);
-    VPHO_LAUNCH_PDL(k_post_step, dim3(rb), dim3(256), 0, st, ws);
+    VPHO_LAUNCH_PDL(k_reduce, dim3(b0 + b1), dim3(256), 0, st, w0, w1, b0, (int)kRedErr);
+    VPHO_LAUNCH_PDL(k_post_step, dim3(b0 + b1), dim3(256), 0, st, w0, w1, b0);
     profile_end(VPHO_TAG_RK_CONTROL, st);
     VPHO_CHECK_LAUNCH();
   }
@@ -1082,14 +1162,87 @@ extern "C" int vpho_score_eval(vpho_denoiser_t h, const float* x, float t, const
   if (!x || !feat || !out) return VPHO_ERR_INVALID;
   DenoiserHost& dh = *static_cast<DenoiserHost*>(h);
   const DenoiserDev& dn = dh.dev;
-  SamplerWs ws;
-  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, 1, &ws, dh.use_tc, dh.use_f16) > workspace_bytes) return VPHO_ERR_INVALID;
+  SamplerJob job{&dh, {}, n_rows * dn.D};
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, 1, &job.ws, dh.use_tc, dh.use_f16) > workspace_bytes) return VPHO_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  ws.eval_x = x; ws.eval_out = out;
-  VPHO_LAUNCH(k_set_eval_time, dim3(1), dim3(1), 0, st, ws, t);
-  int rcf = launch_feat_term(dh, ws, feat, st);
+  job.ws.eval_x = x; job.ws.eval_out = out;
+  VPHO_LAUNCH(k_set_eval_time, dim3(1), dim3(1), 0, st, job.ws, t);
+  int rcf = launch_feat_term(dh, job.ws, feat, st);
   if (rcf) return rcf;
-  return launch_eval(dh, ws, kModeEval, 0, st);
+  return launch_eval(&job, 1, kModeEval, 0, st);
+}
+
+// validates one sampler's arguments, carves its workspace and (begin only) initialises controller, state and feat-term
+static int prepare_job(const vpho_sample_args* a, bool begin, SamplerJob* job, cudaStream_t st) {
+  if (!a || !a->denoiser || a->n_rows < 0 || a->rows_per_feat <= 0 || !a->workspace) return VPHO_ERR_INVALID;
+  if (begin && (a->n_eval < 1 || a->num_steps < 1)) return VPHO_ERR_INVALID;
+  if (begin && a->n_rows > 0 && (!a->feat || !a->init_x || !a->x)) return VPHO_ERR_INVALID;
+  DenoiserHost& dh = *static_cast<DenoiserHost*>(a->denoiser);
+  const DenoiserDev& dn = dh.dev;
+  job->dh = &dh;
+  job->ws_n = a->n_rows * dn.D;
+  if (carve(a->workspace, dn.n_heads, a->n_rows, a->rows_per_feat, a->n_eval, &job->ws, dh.use_tc, dh.use_f16) > a->workspace_bytes)
+    return VPHO_ERR_INVALID;
+  if (!begin) return VPHO_OK;
+  SampleCfg cfg{a->T0, a->eps, a->rtol, a->atol, a->max_step, a->n_rows, dn.D, a->n_eval, a->num_steps, a->rows_per_feat, a->t_eval,
+                a->xs, a->x, a->counters};
+  VPHO_LAUNCH(k_init_ctrl, dim3(1), dim3(64), 0, st, cfg, job->ws);
+  VPHO_CHECK_LAUNCH();
+  if (a->n_rows == 0) return VPHO_OK;
+  VPHO_LAUNCH(k_init_state, dim3(red_blocks(job->ws_n)), dim3(256), 0, st, job->ws, a->init_x, job->ws_n);
+  return launch_feat_term(dh, job->ws, a->feat, st);
+}
+
+// jobs with no rows drop out; returns the number left (their order is kept)
+static int live_jobs(const vpho_sample_args* const* args, int n_args, bool begin, SamplerJob* jobs, cudaStream_t st, int* rc) {
+  int n = 0;
+  *rc = VPHO_OK;
+  for (int i = 0; i < n_args; ++i) {
+    SamplerJob j{};
+    *rc = prepare_job(args[i], begin, &j, st);
+    if (*rc) return 0;
+    if (args[i]->n_rows > 0) jobs[n++] = j;
+  }
+  return n;
+}
+
+static int sample_begin(const vpho_sample_args* const* args, int n_args, int max_attempts, cudaStream_t st) {
+  if (max_attempts < 0) return VPHO_ERR_INVALID;
+  SamplerJob jobs[2];
+  int rc;
+  const int n = live_jobs(args, n_args, true, jobs, st, &rc);
+  if (rc || n == 0) return rc;
+  rc = launch_eval(jobs, n, kModeInit0, 0, st);
+  if (rc) return rc;
+  rc = launch_reduce(jobs, n, (int)kRedInit0, st);
+  if (rc) return rc;
+  rc = launch_eval(jobs, n, kModeInit1, 0, st);
+  if (rc) return rc;
+  rc = launch_reduce(jobs, n, (int)kRedInit1, st);
+  if (rc) return rc;
+  VPHO_CHECK_LAUNCH();
+  return launch_attempts(jobs, n, max_attempts, st);
+}
+
+static int sample_continue(const vpho_sample_args* const* args, int n_args, int max_attempts, cudaStream_t st) {
+  if (max_attempts < 0) return VPHO_ERR_INVALID;
+  SamplerJob jobs[2];
+  int rc;
+  const int n = live_jobs(args, n_args, false, jobs, st, &rc);
+  if (rc || n == 0) return rc;
+  return launch_attempts(jobs, n, max_attempts, st);
+}
+
+static int sample_finish(const vpho_sample_args* const* args, int n_args, cudaStream_t st) {
+  SamplerJob jobs[2];
+  int rc;
+  const int n = live_jobs(args, n_args, false, jobs, st, &rc);
+  if (rc || n == 0) return rc;
+  rc = launch_eval(jobs, n, kModeFinal, 0, st);
+  if (rc) return rc;
+  for (int j = 0; j < n; ++j) VPHO_LAUNCH(k_export, dim3(1), dim3(1), 0, st, jobs[j].ws);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
 }
 
 extern "C" int vpho_sample_begin(vpho_denoiser_t h, const float* feat, int n_rows, int rows_per_feat,
@@ -1097,58 +1250,46 @@ extern "C" int vpho_sample_begin(vpho_denoiser_t h, const float* feat, int n_row
                                  double rtol, double atol, double max_step, int num_steps, int max_attempts,
                                  double* xs, double* x, int32_t* counters, void* workspace, size_t workspace_bytes,
                                  void* stream) {
-  if (!h || n_rows < 0 || rows_per_feat <= 0 || !workspace || n_eval < 1 || num_steps < 1 || max_attempts < 0)
-    return VPHO_ERR_INVALID;
-  if (n_rows > 0 && (!feat || !init_x || !x)) return VPHO_ERR_INVALID;
-  DenoiserHost& dh = *static_cast<DenoiserHost*>(h);
-  const DenoiserDev& dn = dh.dev;
-  SamplerWs ws;
-  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws, dh.use_tc, dh.use_f16) > workspace_bytes) return VPHO_ERR_INVALID;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int n = n_rows * dn.D;
-  SampleCfg cfg{T0, eps, rtol, atol, max_step, n_rows, dn.D, n_eval, num_steps, rows_per_feat, t_eval, xs, x, counters};
-  VPHO_LAUNCH(k_init_ctrl, dim3(1), dim3(64), 0, st, cfg, ws);
-  VPHO_CHECK_LAUNCH();
-  if (n_rows == 0) return VPHO_OK;
-  const int rb = red_blocks(n);
-  VPHO_LAUNCH(k_init_state, dim3(rb), dim3(256), 0, st, ws, init_x, n);
-  int rc = launch_feat_term(dh, ws, feat, st);
-  if (rc) return rc;
-  rc = launch_eval(dh, ws, kModeInit0, 0, st);
-  if (rc) return rc;
-  VPHO_LAUNCH(k_reduce, dim3(rb), dim3(256), 0, st, ws, (int)kRedInit0);
-  rc = launch_eval(dh, ws, kModeInit1, 0, st);
-  if (rc) return rc;
-  VPHO_LAUNCH(k_reduce, dim3(rb), dim3(256), 0, st, ws, (int)kRedInit1);
-  VPHO_CHECK_LAUNCH();
-  return launch_attempts(dh, ws, n, max_attempts, st);
+  const vpho_sample_args a{h, feat, n_rows, rows_per_feat, init_x, T0, eps, t_eval, n_eval, rtol, atol, max_step, num_steps,
+                           xs, x, counters, workspace, workspace_bytes};
+  const vpho_sample_args* p = &a;
+  return sample_begin(&p, 1, max_attempts, (cudaStream_t)stream);
 }
 
 extern "C" int vpho_sample_continue(vpho_denoiser_t h, int n_rows, int rows_per_feat, int n_eval, int max_attempts,
                                     void* workspace, size_t workspace_bytes, void* stream) {
-  if (!h || n_rows < 0 || rows_per_feat <= 0 || !workspace || max_attempts < 0) return VPHO_ERR_INVALID;
-  if (n_rows == 0) return VPHO_OK;
-  DenoiserHost& dh = *static_cast<DenoiserHost*>(h);
-  const DenoiserDev& dn = dh.dev;
-  SamplerWs ws;
-  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws, dh.use_tc, dh.use_f16) > workspace_bytes) return VPHO_ERR_INVALID;
-  return launch_attempts(dh, ws, n_rows * dn.D, max_attempts, (cudaStream_t)stream);
+  vpho_sample_args a{};
+  a.denoiser = h; a.n_rows = n_rows; a.rows_per_feat = rows_per_feat; a.n_eval = n_eval;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  const vpho_sample_args* p = &a;
+  return sample_continue(&p, 1, max_attempts, (cudaStream_t)stream);
 }
 
 extern "C" int vpho_sample_finish(vpho_denoiser_t h, int n_rows, int rows_per_feat, int n_eval, void* workspace,
                                   size_t workspace_bytes, void* stream) {
-  if (!h || n_rows < 0 || rows_per_feat <= 0 || !workspace) return VPHO_ERR_INVALID;
-  if (n_rows == 0) return VPHO_OK;
-  DenoiserHost& dh = *static_cast<DenoiserHost*>(h);
-  const DenoiserDev& dn = dh.dev;
-  SamplerWs ws;
-  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, n_eval, &ws, dh.use_tc, dh.use_f16) > workspace_bytes) return VPHO_ERR_INVALID;
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc = launch_eval(dh, ws, kModeFinal, 0, st);
-  if (rc) return rc;
-  VPHO_LAUNCH(k_export, dim3(1), dim3(1), 0, st, ws);
-  VPHO_CHECK_LAUNCH();
-  return VPHO_OK;
+  vpho_sample_args a{};
+  a.denoiser = h; a.n_rows = n_rows; a.rows_per_feat = rows_per_feat; a.n_eval = n_eval;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  const vpho_sample_args* p = &a;
+  return sample_finish(&p, 1, (cudaStream_t)stream);
+}
+
+extern "C" int vpho_sample_pair_begin(const vpho_sample_args* a, const vpho_sample_args* b, int max_attempts, void* stream) {
+  if (!a || !b || a->workspace == b->workspace) return VPHO_ERR_INVALID;
+  const vpho_sample_args* p[2] = {a, b};
+  return sample_begin(p, 2, max_attempts, (cudaStream_t)stream);
+}
+
+extern "C" int vpho_sample_pair_continue(const vpho_sample_args* a, const vpho_sample_args* b, int max_attempts, void* stream) {
+  if (!a || !b || a->workspace == b->workspace) return VPHO_ERR_INVALID;
+  const vpho_sample_args* p[2] = {a, b};
+  return sample_continue(p, 2, max_attempts, (cudaStream_t)stream);
+}
+
+extern "C" int vpho_sample_pair_finish(const vpho_sample_args* a, const vpho_sample_args* b, void* stream) {
+  if (!a || !b || a->workspace == b->workspace) return VPHO_ERR_INVALID;
+  const vpho_sample_args* p[2] = {a, b};
+  return sample_finish(p, 2, (cudaStream_t)stream);
 }
 
 extern "C" int vpho_postprocess_hand(const double* xs, int n_steps, int n_rows, int rows_per_shape, const float* shape,

@@ -110,4 +110,8 @@ struct SamplerWs {
 
 constexpr int kMaxRedBlocks = 512;
 
+// one sampler's share of a tensor-core launch (scorenet_tc.cu); two of them = two samplers advancing in lock-step
+struct TcHeadJob { const void *mapA_hi, *mapA_lo, *mapB_hi, *mapB_lo; const DenoiserDev* dn; const SamplerWs* ws; };
+struct TcPoseJob { const void *mapX_hi, *mapX_lo, *mapW1_hi, *mapW1_lo, *mapW2_hi, *mapW2_lo; const DenoiserDev* dn; const SamplerWs* ws; };
+
 }  // namespace vpho

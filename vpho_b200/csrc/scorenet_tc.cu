@@ -253,12 +253,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 //                TMA completions of both CTAs are counted on the leader's full barrier; tcgen05.commit multicasts the
 //                "stage free" and "accumulator ready" arrivals to both CTAs; the peer's epilogue warps arrive remotely
 //                on the leader's "accumulator drained" barrier.
+// Two samplers in lock-step (n_jobs = 2): the hand and the object integrations of one batch issue the same sequence of
+// network calls, so one launch serves both -- job 0's work items followed by job 1's, dealt to the CTAs from opposite ends
+// so that the CTAs with one item fewer of job 0 take job 1's first.  Each job has its own operand maps, weights, workspace
+// and RK controller; a job whose controller is not active in this call (finished, or a skipped attempt) contributes nothing.
 template <bool kHalf, int kCtas>
 __global__ void __launch_bounds__(kHeadThreads, 1)
 k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, DenoiserDev dn, SamplerWs ws,
-          int mode, int s) {
-  RkCtrl& c = *ws.ctrl;
+          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+          const __grid_constant__ CUtensorMap tmA_hi1, const __grid_constant__ CUtensorMap tmA_lo1,
+          const __grid_constant__ CUtensorMap tmB_hi1, const __grid_constant__ CUtensorMap tmB_lo1, DenoiserDev dn0, SamplerWs ws0,
+          DenoiserDev dn1, SamplerWs ws1, int n_jobs, int mode, int s) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // align inside the shared window with an offset (an integer round trip would demote every access to a generic load)
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -272,9 +277,6 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;           // CTA or CTA pair
   const int n_units = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int n_tiles = ws.Npad / kTcBM;
-  const int n_slots = kPair ? (n_tiles + 1) / 2 : n_tiles;         // row tiles, or pairs of row tiles
-  const int n_items = n_slots * dn.n_heads;
   constexpr int kElems = kHalf ? 64 : 32;           // operand elements per 128-byte row
   constexpr int kChunks = kPDim / kElems;
 
@@ -301,41 +303,51 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   // kernel) wrote is read before this point
   pdl_wait();
   pdl_trigger();
-  const bool active = eval_active(c, mode);     // uniform across the grid (a skipped RK attempt)
+  // per job: work items (head, row tile or pair of row tiles) and the first one this CTA / CTA pair takes
+  const bool act0 = eval_active(*ws0.ctrl, mode), act1 = n_jobs > 1 && eval_active(*ws1.ctrl, mode);
+  const int tiles0 = ws0.Npad / kTcBM, tiles1 = ws1.Npad / kTcBM;
+  const int slots0 = kPair ? (tiles0 + 1) / 2 : tiles0, slots1 = kPair ? (tiles1 + 1) / 2 : tiles1;
+  const int items0 = act0 ? slots0 * dn0.n_heads : 0, items1 = act1 ? slots1 * dn1.n_heads : 0;
+  const int first0 = unit, first1 = n_units - 1 - unit;
+  const int cnt0 = items0 > first0 ? (items0 - first0 + n_units - 1) / n_units : 0;     // items of job 0 this CTA takes
 
-  if (!active) {
-  } else if (warp == 0) {
+  if (warp == 0) {
     // ===================================================== TMA producer (one lane per CTA)
     if (lane == 0) {
       int stage = 0, pc = 0;
       uint32_t phase = 0;
-      for (int it = unit; it < n_items; it += n_units) {
-        const int slot = it % n_slots, head = it / n_slots;
-        const int tile = kPair ? 2 * slot + (int)rank : slot;       // a tile past the end (odd count) loads zeros
-        const int brow = head * kTcBN + (int)rank * (kTcBN / kCtas);
-        for (int kc = 0; kc < kChunks; ++kc) {
-          mbar_wait(&sm.empty_bar[stage], phase ^ 1);
-          clk_stamp(0, 2 * pc);
-          unsigned char* st = sm.stage[0] + stage * kStageBytes;
-          if (kPair) {
-            if (rank == 0) mbar_arrive_expect_tx(&sm.full_bar[stage], 2 * kStageBytes);
-            const uint32_t lbar = mapa_rank(smem_u32(&sm.full_bar[stage]), 0);
-            tma_load_2d_pair(&tmA_hi, lbar, st, kc * kElems, tile * kTcBM);
-            tma_load_2d_pair(&tmA_lo, lbar, st + kTcABytes, kc * kElems, tile * kTcBM);
-            tma_load_2d_pair(&tmB_hi, lbar, st + 2 * kTcABytes, kc * kElems, brow);
-            tma_load_2d_pair(&tmB_lo, lbar, st + 2 * kTcABytes + kBHalfBytes, kc * kElems, brow);
-          } else {
-            mbar_arrive_expect_tx(&sm.full_bar[stage], kStageBytes);
-            tma_load_2d(&tmA_hi, &sm.full_bar[stage], st, kc * kElems, tile * kTcBM);
-            tma_load_2d(&tmA_lo, &sm.full_bar[stage], st + kTcABytes, kc * kElems, tile * kTcBM);
-            tma_load_2d(&tmB_hi, &sm.full_bar[stage], st + 2 * kTcABytes, kc * kElems, brow);
-            tma_load_2d(&tmB_lo, &sm.full_bar[stage], st + 2 * kTcABytes + kBHalfBytes, kc * kElems, brow);
+      auto produce = [&](const CUtensorMap* mA_hi, const CUtensorMap* mA_lo, const CUtensorMap* mB_hi, const CUtensorMap* mB_lo,
+                         int n_slots, int n_items, int first) {
+        for (int it = first; it < n_items; it += n_units) {
+          const int slot = it % n_slots, head = it / n_slots;
+          const int tile = kPair ? 2 * slot + (int)rank : slot;       // a tile past the end (odd count) loads zeros
+          const int brow = head * kTcBN + (int)rank * (kTcBN / kCtas);
+          for (int kc = 0; kc < kChunks; ++kc) {
+            mbar_wait(&sm.empty_bar[stage], phase ^ 1);
+            clk_stamp(0, 2 * pc);
+            unsigned char* st = sm.stage[0] + stage * kStageBytes;
+            if (kPair) {
+              if (rank == 0) mbar_arrive_expect_tx(&sm.full_bar[stage], 2 * kStageBytes);
+              const uint32_t lbar = mapa_rank(smem_u32(&sm.full_bar[stage]), 0);
+              tma_load_2d_pair(mA_hi, lbar, st, kc * kElems, tile * kTcBM);
+              tma_load_2d_pair(mA_lo, lbar, st + kTcABytes, kc * kElems, tile * kTcBM);
+              tma_load_2d_pair(mB_hi, lbar, st + 2 * kTcABytes, kc * kElems, brow);
+              tma_load_2d_pair(mB_lo, lbar, st + 2 * kTcABytes + kBHalfBytes, kc * kElems, brow);
+            } else {
+              mbar_arrive_expect_tx(&sm.full_bar[stage], kStageBytes);
+              tma_load_2d(mA_hi, &sm.full_bar[stage], st, kc * kElems, tile * kTcBM);
+              tma_load_2d(mA_lo, &sm.full_bar[stage], st + kTcABytes, kc * kElems, tile * kTcBM);
+              tma_load_2d(mB_hi, &sm.full_bar[stage], st + 2 * kTcABytes, kc * kElems, brow);
+              tma_load_2d(mB_lo, &sm.full_bar[stage], st + 2 * kTcABytes + kBHalfBytes, kc * kElems, brow);
+            }
+            clk_stamp(0, 2 * pc + 1);
+            ++pc;
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          clk_stamp(0, 2 * pc + 1);
-          ++pc;
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-      }
+      };
+      produce(&tmA_hi, &tmA_lo, &tmB_hi, &tmB_lo, slots0, items0, first0);
+      produce(&tmA_hi1, &tmA_lo1, &tmB_hi1, &tmB_lo1, slots1, items1, first1);
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (the leader CTA's lane issues for the pair)
@@ -343,7 +355,8 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       int stage = 0, acc = 0, mc = 0;
       uint32_t phase = 0, acc_phase = 0;
       constexpr uint32_t kIdesc = (kHalf ? kTcIdescF16 : kTcIdesc) + (kPair ? ((uint32_t)(kTcBM >> 4) << 24) : 0u);   // M = 128 * kCtas
-      for (int it = unit; it < n_items; it += n_units) {
+      const int cnt1 = items1 > first1 ? (items1 - first1 + n_units - 1) / n_units : 0;
+      for (int n_it = 0; n_it < cnt0 + cnt1; ++n_it) {          // every item is the same 128 (x2) x 256 x 256 product
         clk_stamp(1, mc++);
         if (kPair) mbar_wait_cluster(&sm.tmem_empty_bar[acc], acc_phase ^ 1);
         else mbar_wait(&sm.tmem_empty_bar[acc], acc_phase ^ 1);
@@ -390,9 +403,6 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     // two partial 256->3 sums of a row are combined through shared memory in a fixed order (low columns first).
     const int e = warp - 4, q = e & 3, half = (e >> 2) & 1, grp = e >> 3;
     const int tg = (threadIdx.x - 128) & 255;            // thread index inside the group
-    const EvalTime et = c.et;               // written by the time-term block of this network call
-    const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
-    const int rpf = (mode == kModeEval) ? ws.eval_rpf : c.rows_per_feat;
     int ec = 0;
     uint32_t acc_phase = 0;
     const int acc = grp;
@@ -400,138 +410,147 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     // Per-item constants of column tg (second-layer weights, time term, conditioning terms of the images the row tile spans)
     // are fetched one item ahead into registers, so their global-memory latency hides behind the previous item's math.
     struct ItemConsts { float4 wb; float tt; float f[kTcFtImgs]; };
-    auto item_geometry = [&](int it, int& tile, int& head, int& img0, int& n_img) {
-      const int slot = it % n_slots;
-      head = it / n_slots;
-      tile = kPair ? 2 * slot + (int)rank : slot;
-      const int row_lo = tile * kTcBM, row_hi = min(row_lo + kTcBM, n_rows) - 1;
-      img0 = row_lo / rpf;
-      n_img = row_hi >= row_lo ? row_hi / rpf - img0 + 1 : 0;
-    };
-    auto fetch_consts = [&](int it, ItemConsts& k) {
-      int tile, head, img0, n_img;
-      item_geometry(it, tile, head, img0, n_img);
-      const int col = head * kHeadHid + tg;
-      k.tt = ws.Tt[col];
-      k.wb = __ldg(reinterpret_cast<const float4*>(dn.Wb + (size_t)col * 4));
+    // `seq0`: position of this job's first item in the CTA's item sequence (group g takes the positions of parity g)
+    auto drain = [&](const DenoiserDev& dn, const SamplerWs& ws, int n_slots, int n_items, int first, int seq0) {
+      RkCtrl& c = *ws.ctrl;
+      const EvalTime et = c.et;               // written by the time-term block of this network call
+      const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
+      const int rpf = (mode == kModeEval) ? ws.eval_rpf : c.rows_per_feat;
+      auto item_geometry = [&](int it, int& tile, int& head, int& img0, int& n_img) {
+        const int slot = it % n_slots;
+        head = it / n_slots;
+        tile = kPair ? 2 * slot + (int)rank : slot;
+        const int row_lo = tile * kTcBM, row_hi = min(row_lo + kTcBM, n_rows) - 1;
+        img0 = row_lo / rpf;
+        n_img = row_hi >= row_lo ? row_hi / rpf - img0 + 1 : 0;
+      };
+      auto fetch_consts = [&](int it, ItemConsts& k) {
+        int tile, head, img0, n_img;
+        item_geometry(it, tile, head, img0, n_img);
+        const int col = head * kHeadHid + tg;
+        k.tt = ws.Tt[col];
+        k.wb = __ldg(reinterpret_cast<const float4*>(dn.Wb + (size_t)col * 4));
 #pragma unroll
-      for (int i = 0; i < kTcFtImgs; ++i) k.f[i] = (n_img <= kTcFtImgs && i < n_img) ? ws.F[(size_t)(img0 + i) * dn.hid + col] : 0.f;
-    };
-    const int it_first = unit + grp * n_units, it_step = 2 * n_units;      // group g drains every other item of this CTA
-    ItemConsts kc;
-    if (it_first < n_items) fetch_consts(it_first, kc);
-    for (int it = it_first; it < n_items; it += it_step) {
-      int tile, head, img0, n_img;
-      item_geometry(it, tile, head, img0, n_img);
-      const int hc0 = head * kHeadHid;
-      if (tg == 0 && grp == 0) clk_stamp(2, ec++);
-      // ft[i][col] = F[img0 + i][col] + Tt[col] for the (at most kTcFtImgs) images this 128-row tile spans; tiles that span
-      // more images read F from global memory instead
-      const int row_lo = tile * kTcBM;
-      const bool ft_smem = n_img <= kTcFtImgs;
-      sm.tt[acc][tg] = kc.tt;
-      *reinterpret_cast<float4*>(sm.wb[acc][tg]) = kc.wb;
+        for (int i = 0; i < kTcFtImgs; ++i) k.f[i] = (n_img <= kTcFtImgs && i < n_img) ? ws.F[(size_t)(img0 + i) * dn.hid + col] : 0.f;
+      };
+      const int it_first = first + (((seq0 & 1) != grp) ? n_units : 0), it_step = 2 * n_units;
+      ItemConsts kc;
+      if (it_first < n_items) fetch_consts(it_first, kc);
+      for (int it = it_first; it < n_items; it += it_step) {
+        int tile, head, img0, n_img;
+        item_geometry(it, tile, head, img0, n_img);
+        const int hc0 = head * kHeadHid;
+        if (tg == 0 && grp == 0) clk_stamp(2, ec++);
+        // ft[i][col] = F[img0 + i][col] + Tt[col] for the (at most kTcFtImgs) images this 128-row tile spans; tiles that span
+        // more images read F from global memory instead
+        const int row_lo = tile * kTcBM;
+        const bool ft_smem = n_img <= kTcFtImgs;
+        sm.tt[acc][tg] = kc.tt;
+        *reinterpret_cast<float4*>(sm.wb[acc][tg]) = kc.wb;
 #pragma unroll
-      for (int i = 0; i < kTcFtImgs; ++i) sm.ft[acc][i][tg] = kc.f[i] + kc.tt;
-      const int row = row_lo + q * 32 + lane;
-      const bool valid = row < n_rows;
-      const int cbase = half * 128;
-      const int img_l = valid ? row / rpf - img0 : 0;
-      const float* Frow = ws.F + (size_t)(valid ? row / rpf : 0) * dn.hid + hc0 + cbase;
-      // exact power-of-two un-scaling of the FP16 operand planes (1 for the TF32 planes); loaded before the waits
-      const float unscale = kHalf ? (row < ws.Npad ? ws.P2scale[row] : 1.f) * dn.Wscale_inv[head] : 1.f;
-      if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-      else asm volatile("bar.sync 3, 256;" ::: "memory");
-      if (it + it_step < n_items) fetch_consts(it + it_step, kc);
-      if (tg == 0 && grp == 0) clk_stamp(2, ec++);
-      mbar_wait(&sm.tmem_full_bar[acc], acc_phase);
-      if (tg == 0 && grp == 0) clk_stamp(2, ec++);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTcBN + cbase);
-      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-      if (tg == 0 && grp == 0) clk_stamp(2, ec++);
-      if (ft_smem) {
-        // hot path: conditioning + time terms of this row's image and the second-layer weights come from shared memory;
-        // the TMEM load of the next 16 columns is in flight while the current 16 are consumed
-        const float* ftp = &sm.ft[acc][img_l][cbase];
-        const float* wbp = &sm.wb[acc][cbase][0];
-        auto consume = [&](const uint32_t (&vv)[16], int cb) {
-          float4 fa[4], w[16];
+        for (int i = 0; i < kTcFtImgs; ++i) sm.ft[acc][i][tg] = kc.f[i] + kc.tt;
+        const int row = row_lo + q * 32 + lane;
+        const bool valid = row < n_rows;
+        const int cbase = half * 128;
+        const int img_l = valid ? row / rpf - img0 : 0;
+        const float* Frow = ws.F + (size_t)(valid ? row / rpf : 0) * dn.hid + hc0 + cbase;
+        // exact power-of-two un-scaling of the FP16 operand planes (1 for the TF32 planes); loaded before the waits
+        const float unscale = kHalf ? (row < ws.Npad ? ws.P2scale[row] : 1.f) * dn.Wscale_inv[head] : 1.f;
+        if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (it + it_step < n_items) fetch_consts(it + it_step, kc);
+        if (tg == 0 && grp == 0) clk_stamp(2, ec++);
+        mbar_wait(&sm.tmem_full_bar[acc], acc_phase);
+        if (tg == 0 && grp == 0) clk_stamp(2, ec++);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTcBN + cbase);
+        float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+        if (tg == 0 && grp == 0) clk_stamp(2, ec++);
+        if (ft_smem) {
+          // hot path: conditioning + time terms of this row's image and the second-layer weights come from shared memory;
+          // the TMEM load of the next 16 columns is in flight while the current 16 are consumed
+          const float* ftp = &sm.ft[acc][img_l][cbase];
+          const float* wbp = &sm.wb[acc][cbase][0];
+          auto consume = [&](const uint32_t (&vv)[16], int cb) {
+            float4 fa[4], w[16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) fa[j] = *reinterpret_cast<const float4*>(ftp + cb * 16 + j * 4);
+            for (int j = 0; j < 4; ++j) fa[j] = *reinterpret_cast<const float4*>(ftp + cb * 16 + j * 4);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] = *reinterpret_cast<const float4*>(wbp + (cb * 16 + j) * 4);
+            for (int j = 0; j < 16; ++j) w[j] = *reinterpret_cast<const float4*>(wbp + (cb * 16 + j) * 4);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float f = (j & 3) == 0 ? fa[j >> 2].x : (j & 3) == 1 ? fa[j >> 2].y : (j & 3) == 2 ? fa[j >> 2].z : fa[j >> 2].w;
-            float hval = fmaf(__uint_as_float(vv[j]), unscale, f);
-            hval = hval > 0.f ? hval : 0.f;
-            o0 = fmaf(hval, w[j].x, o0);
-            o1 = fmaf(hval, w[j].y, o1);
-            o2 = fmaf(hval, w[j].z, o2);
-          }
-        };
-        uint32_t va[16], vb[16];
-        tmem_ld16_issue(taddr, va);
-#pragma unroll 1
-        for (int cb = 0; cb < 8; cb += 2) {
-          tmem_ld16_wait(va);
-          tmem_ld16_issue(taddr + (uint32_t)((cb + 1) * 16), vb);
-          consume(va, cb);
-          if (tg == 0 && grp == 0) clk_stamp(2, ec++);
-          tmem_ld16_wait(vb);
-          if (cb + 2 < 8) tmem_ld16_issue(taddr + (uint32_t)((cb + 2) * 16), va);
-          consume(vb, cb + 1);
-        }
-      } else {
-        // a row tile that spans more than kTcFtImgs images (few candidates per image): F from global memory
-#pragma unroll 1
-        for (int cb = 0; cb < 16; ++cb) {
-          uint32_t vv[8];
-          tmem_ld8(taddr + (uint32_t)(cb * 8), vv);
-          if (tg == 0 && grp == 0 && (cb & 3) == 3) clk_stamp(2, ec++);
-#pragma unroll
-          for (int j4 = 0; j4 < 2; ++j4) {
-            const float4 f4 = __ldg(reinterpret_cast<const float4*>(Frow + cb * 8 + j4 * 4));
-            const float4 t4 = *reinterpret_cast<const float4*>(&sm.tt[acc][cbase + cb * 8 + j4 * 4]);
-            const float fa[4] = {f4.x + t4.x, f4.y + t4.y, f4.z + t4.z, f4.w + t4.w};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              float hval = fmaf(__uint_as_float(vv[j4 * 4 + jj]), unscale, fa[jj]);
+            for (int j = 0; j < 16; ++j) {
+              const float f = (j & 3) == 0 ? fa[j >> 2].x : (j & 3) == 1 ? fa[j >> 2].y : (j & 3) == 2 ? fa[j >> 2].z : fa[j >> 2].w;
+              float hval = fmaf(__uint_as_float(vv[j]), unscale, f);
               hval = hval > 0.f ? hval : 0.f;
-              const float4 w = *reinterpret_cast<const float4*>(sm.wb[acc][cbase + cb * 8 + j4 * 4 + jj]);
-              o0 = fmaf(hval, w.x, o0);
-              o1 = fmaf(hval, w.y, o1);
-              o2 = fmaf(hval, w.z, o2);
+              o0 = fmaf(hval, w[j].x, o0);
+              o1 = fmaf(hval, w[j].y, o1);
+              o2 = fmaf(hval, w[j].z, o2);
+            }
+          };
+          uint32_t va[16], vb[16];
+          tmem_ld16_issue(taddr, va);
+#pragma unroll 1
+          for (int cb = 0; cb < 8; cb += 2) {
+            tmem_ld16_wait(va);
+            tmem_ld16_issue(taddr + (uint32_t)((cb + 1) * 16), vb);
+            consume(va, cb);
+            if (tg == 0 && grp == 0) clk_stamp(2, ec++);
+            tmem_ld16_wait(vb);
+            if (cb + 2 < 8) tmem_ld16_issue(taddr + (uint32_t)((cb + 2) * 16), va);
+            consume(vb, cb + 1);
+          }
+        } else {
+          // a row tile that spans more than kTcFtImgs images (few candidates per image): F from global memory
+#pragma unroll 1
+          for (int cb = 0; cb < 16; ++cb) {
+            uint32_t vv[8];
+            tmem_ld8(taddr + (uint32_t)(cb * 8), vv);
+            if (tg == 0 && grp == 0 && (cb & 3) == 3) clk_stamp(2, ec++);
+#pragma unroll
+            for (int j4 = 0; j4 < 2; ++j4) {
+              const float4 f4 = __ldg(reinterpret_cast<const float4*>(Frow + cb * 8 + j4 * 4));
+              const float4 t4 = *reinterpret_cast<const float4*>(&sm.tt[acc][cbase + cb * 8 + j4 * 4]);
+              const float fa[4] = {f4.x + t4.x, f4.y + t4.y, f4.z + t4.z, f4.w + t4.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                float hval = fmaf(__uint_as_float(vv[j4 * 4 + jj]), unscale, fa[jj]);
+                hval = hval > 0.f ? hval : 0.f;
+                const float4 w = *reinterpret_cast<const float4*>(sm.wb[acc][cbase + cb * 8 + j4 * 4 + jj]);
+                o0 = fmaf(hval, w.x, o0);
+                o1 = fmaf(hval, w.y, o1);
+                o2 = fmaf(hval, w.z, o2);
+              }
             }
           }
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (kPair) mbar_arrive_cluster(drained_bar);        // the leader's MMA lane waits for both CTAs' 8 warps
-        else mbar_arrive(&sm.tmem_empty_bar[acc]);
-      }
-      if (tg == 0 && grp == 0) clk_stamp(2, ec++);
-      if (half == 1) {
-        float* pp = sm.part[acc][q * 32 + lane];
-        pp[0] = o0; pp[1] = o1; pp[2] = o2;
-      }
-      if (grp == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
-      else asm volatile("bar.sync 4, 256;" ::: "memory");
-      if (half == 0 && valid) {
-        const float* pp = sm.part[acc][q * 32 + lane];
-        const float o[3] = {o0 + pp[0], o1 + pp[1], o2 + pp[2]};
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const float out = o[d] + dn.bb[head * 3 + d];
-          emit_score(ws, c, et, mode, s, row * dn.D + head * 3 + d, __fdiv_rn(out, et.std32));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair) mbar_arrive_cluster(drained_bar);        // the leader's MMA lane waits for both CTAs' 8 warps
+          else mbar_arrive(&sm.tmem_empty_bar[acc]);
         }
+        if (tg == 0 && grp == 0) clk_stamp(2, ec++);
+        if (half == 1) {
+          float* pp = sm.part[acc][q * 32 + lane];
+          pp[0] = o0; pp[1] = o1; pp[2] = o2;
+        }
+        if (grp == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+        else asm volatile("bar.sync 4, 256;" ::: "memory");
+        if (half == 0 && valid) {
+          const float* pp = sm.part[acc][q * 32 + lane];
+          const float o[3] = {o0 + pp[0], o1 + pp[1], o2 + pp[2]};
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const float out = o[d] + dn.bb[head * 3 + d];
+            emit_score(ws, c, et, mode, s, row * dn.D + head * 3 + d, __fdiv_rn(out, et.std32));
+          }
+        }
+        if (tg == 0 && grp == 0) clk_stamp(2, ec++);
+        acc_phase ^= 1;
       }
-      if (tg == 0 && grp == 0) clk_stamp(2, ec++);
-      acc_phase ^= 1;
-    }
+    };
+    if (items0 > 0) drain(dn0, ws0, slots0, items0, first0, 0);
+    if (items1 > 0) drain(dn1, ws1, slots1, items1, first1, cnt0);
   }
   tc_fence_before();
   if (kPair) cluster_sync_all();                // neither CTA leaves (or frees TMEM) while the pair's MMAs / arrivals are in flight
@@ -572,17 +591,15 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kHeadThreads, 1)
-k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
-          const __grid_constant__ CUtensorMap tmW1_hi, const __grid_constant__ CUtensorMap tmW1_lo,
-          const __grid_constant__ CUtensorMap tmW2_hi, const __grid_constant__ CUtensorMap tmW2_lo, DenoiserDev dn, SamplerWs ws,
-          int mode, int s) {
+__device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CUtensorMap* tmX_lo, const CUtensorMap* tmW1_hi,
+                                             const CUtensorMap* tmW1_lo, const CUtensorMap* tmW2_hi, const CUtensorMap* tmW2_lo,
+                                             const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, int tile) {
   const RkCtrl& c = *ws.ctrl;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   PtSmem& sm = *reinterpret_cast<PtSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = dn.D, nk1 = (D + kTcBK - 1) / kTcBK;
-  const int r0 = blockIdx.x * kTcBM;
+  const int r0 = tile * kTcBM;
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -615,19 +632,19 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
       // the whole X tile (A operand of GEMM 1) has a dedicated region: issue it at once
       mbar_arrive_expect_tx(&sm.x_full_bar, (uint32_t)(nk1 * 2 * kTcABytes));
       for (int j = 0; j < nk1; ++j) {
-        tma_load_2d(&tmX_hi, &sm.x_full_bar, sm.a + (size_t)j * 2 * kTcABytes, j * kTcBK, r0);
-        tma_load_2d(&tmX_lo, &sm.x_full_bar, sm.a + (size_t)j * 2 * kTcABytes + kTcABytes, j * kTcBK, r0);
+        tma_load_2d(tmX_hi, &sm.x_full_bar, sm.a + (size_t)j * 2 * kTcABytes, j * kTcBK, r0);
+        tma_load_2d(tmX_lo, &sm.x_full_bar, sm.a + (size_t)j * 2 * kTcABytes + kTcABytes, j * kTcBK, r0);
       }
       for (int j = 0; j < nk1 + 8; ++j) {
         mbar_wait(&sm.empty_bar[stage], phase ^ 1);
         clk_stamp(0, sc_++);
         mbar_arrive_expect_tx(&sm.full_bar[stage], kPtStageB);
         if (j < nk1) {
-          tma_load_2d(&tmW1_hi, &sm.full_bar[stage], sm.b[stage], j * kTcBK, 0);
-          tma_load_2d(&tmW1_lo, &sm.full_bar[stage], sm.b[stage] + kTcBBytes, j * kTcBK, 0);
+          tma_load_2d(tmW1_hi, &sm.full_bar[stage], sm.b[stage], j * kTcBK, 0);
+          tma_load_2d(tmW1_lo, &sm.full_bar[stage], sm.b[stage] + kTcBBytes, j * kTcBK, 0);
         } else {
-          tma_load_2d(&tmW2_hi, &sm.full_bar[stage], sm.b[stage], (j - nk1) * kTcBK, 0);
-          tma_load_2d(&tmW2_lo, &sm.full_bar[stage], sm.b[stage] + kTcBBytes, (j - nk1) * kTcBK, 0);
+          tma_load_2d(tmW2_hi, &sm.full_bar[stage], sm.b[stage], (j - nk1) * kTcBK, 0);
+          tma_load_2d(tmW2_lo, &sm.full_bar[stage], sm.b[stage] + kTcBBytes, (j - nk1) * kTcBK, 0);
         }
         if (++stage == 2) { stage = 0; phase ^= 1; }
       }
@@ -809,6 +826,19 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
   }
 }
 
+// One CTA per 128-row tile; with two samplers in lock-step the grid holds job 0's tiles followed by job 1's.
+__global__ void __launch_bounds__(kHeadThreads, 1)
+k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+          const __grid_constant__ CUtensorMap tmW1_hi, const __grid_constant__ CUtensorMap tmW1_lo,
+          const __grid_constant__ CUtensorMap tmW2_hi, const __grid_constant__ CUtensorMap tmW2_lo,
+          const __grid_constant__ CUtensorMap tmX_hi1, const __grid_constant__ CUtensorMap tmX_lo1,
+          const __grid_constant__ CUtensorMap tmW1_hi1, const __grid_constant__ CUtensorMap tmW1_lo1,
+          const __grid_constant__ CUtensorMap tmW2_hi1, const __grid_constant__ CUtensorMap tmW2_lo1, DenoiserDev dn0, SamplerWs ws0,
+          DenoiserDev dn1, SamplerWs ws1, int tiles0, int mode, int s) {
+  if ((int)blockIdx.x < tiles0) pose_tc_tile(&tmX_hi, &tmX_lo, &tmW1_hi, &tmW1_lo, &tmW2_hi, &tmW2_lo, dn0, ws0, mode, s, blockIdx.x);
+  else pose_tc_tile(&tmX_hi1, &tmX_lo1, &tmW1_hi1, &tmW1_lo1, &tmW2_hi1, &tmW2_lo1, dn1, ws1, mode, s, (int)blockIdx.x - tiles0);
+}
+
 // =====================================================================================================================
 // Feat-term on tensor cores: F[R][hid] = feat[R][1024] . Wa_f + ba, once per sample().  Same TMA / UMMA / TMEM pipeline
 // as k_head_tc with K = 1024 (32 chunks) and a plain store epilogue; rows >= R of the last 128-row tile are zero padding
@@ -975,9 +1005,9 @@ int tc_debug_clocks(int enable, unsigned long long* out, int n) {
   return VPHO_OK;
 }
 
-// ctas = 2 launches the CTA-pair variant (FP16 planes only): mapB_* must then have 128-row boxes.
-int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const DenoiserDev& dn,
-                   const SamplerWs& ws, int mode, int s, bool half, int ctas, cudaStream_t st) {
+// ctas = 2 launches the CTA-pair variant (FP16 planes only): mapB_* must then have 128-row boxes.  n_jobs = 2 serves two
+// samplers in lock-step with one launch (see k_head_tc).
+int tc_launch_head(const TcHeadJob* jobs, int n_jobs, int mode, int s, bool half, int ctas, cudaStream_t st) {
   static bool attr = false;
   const int smem = (int)sizeof(TcSmem) + 1024;
   if (!attr) {
@@ -994,24 +1024,32 @@ int tc_launch_head(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (n_sm <= 0) n_sm = 148;
   }
-  const int n_tiles = ws.Npad / kTcBM;
-  const CUtensorMap &ah = *static_cast<const CUtensorMap*>(mapA_hi), &al = *static_cast<const CUtensorMap*>(mapA_lo),
-                    &bh = *static_cast<const CUtensorMap*>(mapB_hi), &bl = *static_cast<const CUtensorMap*>(mapB_lo);
-  cudaError_t e;
-  if (ctas == 2) {
-    if (!half) return VPHO_ERR_INVALID;
-    const int n_items = ((n_tiles + 1) / 2) * dn.n_heads;
-    // the fewest CTA pairs that keep the same number of rounds: SMs left over go to the other sampler's stream
-    const int rounds = (n_items + n_sm / 2 - 1) / (n_sm / 2);
-    const int pairs = (n_items + rounds - 1) / rounds;
-    e = launch_pdl(k_head_tc<true, 2>, dim3(2 * pairs), dim3(kHeadThreads), smem, st, 2, ah, al, bh, bl, dn, ws, mode, s);
-  } else {
-    const int n_items = n_tiles * dn.n_heads;
-    const int rounds = (n_items + n_sm - 1) / n_sm;
-    const int grid = (n_items + rounds - 1) / rounds;       // e.g. 150 items: 75 CTAs x 2 rather than 148 CTAs, 2 of them x 2
-    e = half ? launch_pdl(k_head_tc<true, 1>, dim3(grid), dim3(kHeadThreads), smem, st, 1, ah, al, bh, bl, dn, ws, mode, s)
-             : launch_pdl(k_head_tc<false, 1>, dim3(grid), dim3(kHeadThreads), smem, st, 1, ah, al, bh, bl, dn, ws, mode, s);
+  if (n_jobs < 1 || n_jobs > 2 || (ctas == 2 && !half)) return VPHO_ERR_INVALID;
+  const TcHeadJob& j0 = jobs[0];
+  const TcHeadJob& j1 = jobs[n_jobs - 1];
+  int n_items = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    const int n_tiles = jobs[j].ws->Npad / kTcBM;
+    n_items += (ctas == 2 ? (n_tiles + 1) / 2 : n_tiles) * jobs[j].dn->n_heads;
   }
+  // the fewest CTAs (CTA pairs) that keep the same number of rounds: SMs left over go to other streams
+  const int units_max = n_sm / ctas;
+  const int rounds = (n_items + units_max - 1) / units_max;
+  const int units = (n_items + rounds - 1) / rounds;       // e.g. 150 items: 75 CTAs x 2 rather than 148 CTAs, 2 of them x 2
+  auto M = [](const void* p) -> const CUtensorMap& { return *static_cast<const CUtensorMap*>(p); };
+  cudaError_t e;
+  if (ctas == 2)
+    e = launch_pdl(k_head_tc<true, 2>, dim3(2 * units), dim3(kHeadThreads), smem, st, 2, M(j0.mapA_hi), M(j0.mapA_lo), M(j0.mapB_hi),
+                   M(j0.mapB_lo), M(j1.mapA_hi), M(j1.mapA_lo), M(j1.mapB_hi), M(j1.mapB_lo), *j0.dn, *j0.ws, *j1.dn, *j1.ws, n_jobs,
+                   mode, s);
+  else if (half)
+    e = launch_pdl(k_head_tc<true, 1>, dim3(units), dim3(kHeadThreads), smem, st, 1, M(j0.mapA_hi), M(j0.mapA_lo), M(j0.mapB_hi),
+                   M(j0.mapB_lo), M(j1.mapA_hi), M(j1.mapA_lo), M(j1.mapB_hi), M(j1.mapB_lo), *j0.dn, *j0.ws, *j1.dn, *j1.ws, n_jobs,
+                   mode, s);
+  else
+    e = launch_pdl(k_head_tc<false, 1>, dim3(units), dim3(kHeadThreads), smem, st, 1, M(j0.mapA_hi), M(j0.mapA_lo), M(j0.mapB_hi),
+                   M(j0.mapB_lo), M(j1.mapA_hi), M(j1.mapA_lo), M(j1.mapB_hi), M(j1.mapB_lo), *j0.dn, *j0.ws, *j1.dn, *j1.ws, n_jobs,
+                   mode, s);
   return e == cudaSuccess ? VPHO_OK : VPHO_ERR_LAUNCH;
 }
 
@@ -1034,18 +1072,21 @@ int tc_launch_feat(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi
   return VPHO_OK;
 }
 
-int tc_launch_pose(const void* mapX_hi, const void* mapX_lo, const void* mapW1_hi, const void* mapW1_lo, const void* mapW2_hi,
-                   const void* mapW2_lo, const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, cudaStream_t st) {
+int tc_launch_pose(const TcPoseJob* jobs, int n_jobs, int mode, int s, cudaStream_t st) {
   static bool attr = false;
   const int smem = (int)sizeof(PtSmem) + 1024;
   if (!attr) {
     if (cudaFuncSetAttribute(k_pose_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return VPHO_ERR_LAUNCH;
     attr = true;
   }
-  if (launch_pdl(k_pose_tc, dim3(ws.Npad / kTcBM), dim3(kHeadThreads), smem, st, 1, *static_cast<const CUtensorMap*>(mapX_hi),
-                 *static_cast<const CUtensorMap*>(mapX_lo), *static_cast<const CUtensorMap*>(mapW1_hi),
-                 *static_cast<const CUtensorMap*>(mapW1_lo), *static_cast<const CUtensorMap*>(mapW2_hi),
-                 *static_cast<const CUtensorMap*>(mapW2_lo), dn, ws, mode, s) != cudaSuccess)
+  if (n_jobs < 1 || n_jobs > 2) return VPHO_ERR_INVALID;
+  const TcPoseJob& j0 = jobs[0];
+  const TcPoseJob& j1 = jobs[n_jobs - 1];
+  const int tiles0 = j0.ws->Npad / kTcBM, tiles1 = n_jobs > 1 ? j1.ws->Npad / kTcBM : 0;
+  auto M = [](const void* p) -> const CUtensorMap& { return *static_cast<const CUtensorMap*>(p); };
+  if (launch_pdl(k_pose_tc, dim3(tiles0 + tiles1), dim3(kHeadThreads), smem, st, 1, M(j0.mapX_hi), M(j0.mapX_lo), M(j0.mapW1_hi),
+                 M(j0.mapW1_lo), M(j0.mapW2_hi), M(j0.mapW2_lo), M(j1.mapX_hi), M(j1.mapX_lo), M(j1.mapW1_hi), M(j1.mapW1_lo),
+                 M(j1.mapW2_hi), M(j1.mapW2_lo), *j0.dn, *j0.ws, *j1.dn, *j1.ws, tiles0, mode, s) != cudaSuccess)
     return VPHO_ERR_LAUNCH;
   return VPHO_OK;
 }

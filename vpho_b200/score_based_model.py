@@ -199,5 +199,45 @@ class ScoreBasedModelAgent:
         pending.resolve(c)
         return xs_view, x
 
+    @torch.no_grad()
+    def sample_pair(self, data_a: dict, denoiser_a: Denoiser, data_b: dict, denoiser_b: Denoiser, T0: float,
+                    return_inprocess: bool = True, prior_a: Optional[torch.Tensor] = None,
+                    prior_b: Optional[torch.Tensor] = None):
+        """The two `sample()` calls of `vpho_net.forward(mode='predict')` (hand, then object: VPHO.py:239-262) advanced in
+        lock-step through shared kernel launches (`vpho_sample_pair_*`).  Priors are drawn in the reference's order
+        (a, then b).  Always deferred: -> ((xs_a, x_a, pending_a), (xs_b, x_b, pending_b)); results are bit-identical
+        to two separate `sample(..., defer_check=True)` calls."""
+        jobs = []
+        for data, den, prior in ((data_a, denoiser_a, prior_a), (data_b, denoiser_b, prior_b)):
+            device = (data["feat_unique"] if "feat_unique" in data else data["feat"]).device
+            D = den.out_dim
+            n_rows = int(data["n_rows"]) if "n_rows" in data else int(data["feat"].shape[0])
+            prior = self.prior_fn((n_rows, D), T0).to(device) if prior is None else prior.to(device)
+            x0 = prior.contiguous().float()
+            d2 = dict(data)
+            d2.setdefault("sample_num", self.sample_num)
+            feat, rpf = _unique_feat(d2, n_rows)
+            n_eval = self.sampling_steps
+            ws = den.workspace(n_rows, rpf, n_eval, device)
+            xs = torch.empty((n_eval, n_rows, D), dtype=torch.float64, device=device) if return_inprocess else None
+            x = torch.empty((n_rows, D), dtype=torch.float64, device=device)
+            counters = torch.zeros(8, dtype=torch.int32, device=device)
+            args = capi.SampleArgs(den.handle, capi.ptr(feat), n_rows, rpf, capi.ptr(x0), float(T0), float(self.sampling_eps),
+                                   None, n_eval, RTOL, ATOL, MAX_STEP, n_eval, capi.ptr(xs), capi.ptr(x), capi.ptr(counters),
+                                   capi.ptr(ws), ws.numel())
+            jobs.append((den, args, xs, x, counters, n_rows, (feat, x0, ws)))
+        lib = denoiser_a.lib
+        stream = capi.stream_of(jobs[0][3])
+        hint = max((getattr(j[0], "attempts_hint", None) or self.first_attempts) for j in jobs)
+        import ctypes as C
+        pa, pb = C.byref(jobs[0][1]), C.byref(jobs[1][1])
+        lib.check(lib.c.vpho_sample_pair_begin(pa, pb, hint, stream), "vpho_sample_pair_begin")
+        lib.check(lib.c.vpho_sample_pair_finish(pa, pb, stream), "vpho_sample_pair_finish")
+        out = []
+        for den, args, xs, x, counters, n_rows, keep in jobs:
+            pending = PendingSample(self, den, counters, n_rows, hint, keep)
+            out.append((None if xs is None else xs.permute(1, 0, 2), x, pending))
+        return out[0], out[1]
+
     def get_score(self, data, denoiser):
         return denoiser(data)

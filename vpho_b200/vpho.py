@@ -8,6 +8,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import os
+
 import torch
 
 from . import capi
@@ -39,6 +41,7 @@ class VphoHotPath:
         self.overlap_object_sampler = True
         self._side_stream = None
         self._side_stream2 = None
+        self.pair_samplers = os.environ.get("VPHO_PAIR_SAMPLERS", "1") != "0"
 
     # ---- vpho_net.postprocess_diffusion_hand, branch 'mano_pose' (VPHO.py:306-331) ----
     def postprocess_diffusion_hand(self, hand_inprocess, hand_final, pd_mano_shape):
@@ -98,26 +101,32 @@ class VphoHotPath:
         pd_mano_pose, pd_mano_shape = batch["pd_mano_pose"], batch["pd_mano_shape"]
         pd = {"hand_heatmap": batch["hm_hand"], "obj_heatmap": batch["hm_obj"], "force_local": batch["force_local"]}
 
-        # The object sampler is independent of the hand branch: it runs on a side stream and fills the SMs the hand
-        # branch leaves idle (its pose-encoder kernel uses 50 CTAs, the object head GEMM 150 work items).
+        # The hand and the object integrations issue the same sequence of network calls: they advance in lock-step
+        # through shared kernel launches (`sample_pair`), the object's work items filling the SMs the hand's leave idle.
         main = torch.cuda.current_stream(enc_h.device) if enc_h.is_cuda else None
-        if main is not None and self.overlap_object_sampler:
-            if self._side_stream is None:
-                self._side_stream = torch.cuda.Stream(device=enc_h.device)
-            side = self._side_stream
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                xs_o, x_o, pend_o = self.score_agent.sample({"feat_unique": enc_o, "n_rows": bs * S}, self.denoiser_obj,
-                                                            self.sample_T0, return_inprocess=with_inprocess,
-                                                            prior=prior_obj, defer_check=True)
-            for t in (xs_o, x_o, pend_o.counters):
-                if t is not None:
-                    t.record_stream(main)
+        side = None
+        paired = main is not None and self.overlap_object_sampler and self.pair_samplers
+        if paired:
+            (xs_h, x_h, pend_h), (xs_o, x_o, pend_o) = self.score_agent.sample_pair(
+                {"feat_unique": enc_h, "n_rows": bs * S}, self.denoiser_hand, {"feat_unique": enc_o, "n_rows": bs * S},
+                self.denoiser_obj, self.sample_T0, return_inprocess=with_inprocess, prior_a=prior_hand, prior_b=prior_obj)
         else:
-            side = None
-        xs_h, x_h, pend_h = self.score_agent.sample({"feat_unique": enc_h, "n_rows": bs * S}, self.denoiser_hand,
-                                                    self.sample_T0, return_inprocess=with_inprocess, prior=prior_hand,
-                                                    defer_check=True)
+            # fallback: the object sampler on a side stream (VPHO_PAIR_SAMPLERS=0), or after the hand's on the same stream
+            if main is not None and self.overlap_object_sampler:
+                if self._side_stream is None:
+                    self._side_stream = torch.cuda.Stream(device=enc_h.device)
+                side = self._side_stream
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    xs_o, x_o, pend_o = self.score_agent.sample({"feat_unique": enc_o, "n_rows": bs * S}, self.denoiser_obj,
+                                                                self.sample_T0, return_inprocess=with_inprocess,
+                                                                prior=prior_obj, defer_check=True)
+                for t in (xs_o, x_o, pend_o.counters):
+                    if t is not None:
+                        t.record_stream(main)
+            xs_h, x_h, pend_h = self.score_agent.sample({"feat_unique": enc_h, "n_rows": bs * S}, self.denoiser_hand,
+                                                        self.sample_T0, return_inprocess=with_inprocess, prior=prior_hand,
+                                                        defer_check=True)
         # The aggregator needs only the final hand poses.  Everything else computed from the hand sampler's output is
         # output-only (the in-process trajectory for visualisation, the 6400 posed meshes of the candidates): it runs on a
         # second side stream, concurrently with the aggregation.
@@ -153,7 +162,9 @@ class VphoHotPath:
         else:
             output_only_work()
 
-        if side is None:
+        if paired:
+            pass
+        elif side is None:
             xs_o, x_o, pend_o = self.score_agent.sample({"feat_unique": enc_o, "n_rows": bs * S}, self.denoiser_obj,
                                                         self.sample_T0, return_inprocess=with_inprocess, prior=prior_obj,
                                                         defer_check=True)

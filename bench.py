@@ -36,6 +36,7 @@ sys.path.insert(0, ROOT)
 BS, S, STEPS_ODE, T0, K_HAND, K_OBJ = 64, 100, 50, 0.65, 30, 10
 # algorithmic work (restated in DESIGN.md §5)
 FLOP_HEAD_GEMM_HAND = 2 * (256 * 8192 + 8192 * 3)     # per candidate per network call, head GEMM + fused second layer
+FLOP_HEAD_GEMM_OBJ = 2 * (256 * 768 + 768 * 3)        # same for the object denoiser (3 heads of 256 hidden units)
 FLOP_SCORE_HAND, FLOP_SCORE_OBJ = 4423680, 533504     # whole factored network per candidate per call
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
 NCU_TRAFFIC_BYTES = {"k_head_tc": 17272832}
@@ -360,7 +361,11 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     real_launches = info["hand"]["net_calls"] * args.steps
     real = each[-real_launches:] if each.size >= real_launches else each
     avg_ms = float(np.median(real)) if real.size else 0.0
-    achieved = BS * S * FLOP_HEAD_GEMM_HAND / (avg_ms * 1e-3) / 1e12 if hg["launches"] else None
+    # with the two samplers in lock-step (default) one launch serves the hand's AND the object's head GEMM
+    paired = os.environ.get("VPHO_PAIR_SAMPLERS", "1") != "0" and os.environ.get("VPHO_NO_OVERLAP") is None \
+        and head_kernel == "k_head_tc"
+    flop_launch = BS * S * (FLOP_HEAD_GEMM_HAND + (FLOP_HEAD_GEMM_OBJ if paired else 0))
+    achieved = flop_launch / (avg_ms * 1e-3) / 1e12 if hg["launches"] else None
     line = {
         "metric": "hand-object pose candidates scored/sec", "value": round(value, 1), "unit": "candidates/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_res / args.steps, 4),
@@ -371,8 +376,9 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
                 "h2d_ms_alone": round(h2d_ms, 3), "note": "H2D of step i+1 runs on a copy stream while step i computes"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary([windows[0], windows[-1]]),
-        "roofline": {"kernel": head_kernel + " (hand score network: pose-feature GEMM K=256 x 8192 hidden, fused bias/ReLU/"
-                               "256->3 heads/sigma division)",
+        "roofline": {"kernel": head_kernel + " (score-network head GEMM: pose features K=256 x 8192 hidden units of the hand "
+                               "denoiser" + (" + 768 of the object denoiser, one launch" if paired else "") +
+                               ", fused bias/ReLU/256->3 heads/sigma division)",
                      "bound": "tensor", "achieved": round(achieved, 2) if achieved else None, "peak": peaks["bf16_tflops"],
                      "unit": "TFLOP/s", "frac": round(achieved / peaks["bf16_tflops"], 4) if achieved else None,
                      "traffic": NCU_TRAFFIC_BYTES.get(head_kernel), "peak_source": peaks["source"] + " (cuBLAS bf16 burst)",
@@ -381,7 +387,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
                              "; ncu: tensor pipe active 59 %% of elapsed, 68 us (profiles/r01_ncu_head_tc_summary.txt)" % (peaks["bf16_tflops"] / 3),
                      "launches_timed": hg["launches"], "network_calls": real_launches, "avg_launch_ms": round(avg_ms, 4),
                      "avg_is": "median over the real launches of a second pass of the same K steps (%.4f ms/step)" % (ms_roof / args.steps),
-                     "flop_per_launch": BS * S * FLOP_HEAD_GEMM_HAND,
+                     "flop_per_launch": flop_launch,
                      "share_of_step": round(avg_ms * info["hand"]["net_calls"] / (ms_res / args.steps), 4)},
         "kernel_ms_per_step": {k: round(v["ms_total"] / args.steps, 4) for k, v in prof.items()},
         "sampler": {"hand_net_calls": info["hand"]["net_calls"], "obj_net_calls": info["obj"]["net_calls"],

@@ -30,3 +30,25 @@ for _ in range(20):
     tot.append((t2 - t0) * 1e3)
     del pd
 print(f"host enqueue of one step: median {np.median(enq):.2f} ms (min {min(enq):.2f}); enqueue + device: median {np.median(tot):.2f} ms")
+
+# back-to-back steps without the per-step status read (what a one-step-lookahead evaluation loop achieves): the host runs
+# ahead of the device, so the device never waits for Python between steps
+for depth in (1, 2):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    pending = []
+    e0.record()
+    for i in range(n):
+        pending.append(hp._predict_once(res, ph, po, True))
+        if len(pending) >= depth:
+            pd, pend = pending.pop(0)
+            st = torch.stack([p.counters for p in pend]).cpu()
+            del pd
+    while pending:
+        pd, pend = pending.pop(0)
+        st = torch.stack([p.counters for p in pend]).cpu()
+        del pd
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"lookahead depth {depth}: {e0.elapsed_time(e1) / n:.3f} ms per step")

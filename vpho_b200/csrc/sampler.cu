@@ -143,10 +143,12 @@ constexpr int kFtRows = 32, kFtCols = 128, kFtK = 32, kFtSplit = 4;
 // split-K: blockIdx.z owns K slice [z*256, z*256+256) and writes its partial sums to Fpart[z]; k_feat_sum adds the four
 // partials in a fixed order plus the bias.  FP32 FMA accumulation throughout (the tensor-core variant accumulates with
 // truncation over a 384-instruction chain, which costs ~1 decimal digit on this K = 1024 contraction).
-__global__ void __launch_bounds__(256) k_feat_term(DenoiserDev dn, const float* __restrict__ feat, int R, float* __restrict__ Fpart) {
+__device__ __forceinline__ void feat_term_block(const DenoiserDev& dn, const float* __restrict__ feat, int R, float* __restrict__ Fpart,
+                                                int bx) {
   __shared__ __align__(16) float fs[kFtK][kFtRows];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int c0 = blockIdx.x * kFtCols, r0 = blockIdx.y * kFtRows;
+  const int c0 = bx * kFtCols, r0 = blockIdx.y * kFtRows;
+  if (r0 >= R) return;
   const int hid = dn.hid;
   const int kbeg = blockIdx.z * (kFDim / kFtSplit), kend = kbeg + kFDim / kFtSplit;
   float acc[4][4];
@@ -179,6 +181,15 @@ __global__ void __launch_bounds__(256) k_feat_term(DenoiserDev dn, const float* 
     if (r >= R) continue;
     *reinterpret_cast<float4*>(dst + (size_t)r * hid + c0 + 4 * tx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   }
+}
+
+// grid.x: column blocks of job 0 followed by those of job 1 (two samplers begun together; xb0 = gridDim.x for one job);
+// grid.y covers the larger row count
+__global__ void __launch_bounds__(256) k_feat_term(DenoiserDev dn0, const float* __restrict__ feat0, int R0, float* __restrict__ Fpart0,
+                                                  DenoiserDev dn1, const float* __restrict__ feat1, int R1, float* __restrict__ Fpart1,
+                                                  int xb0) {
+  if ((int)blockIdx.x < xb0) feat_term_block(dn0, feat0, R0, Fpart0, blockIdx.x);
+  else feat_term_block(dn1, feat1, R1, Fpart1, (int)blockIdx.x - xb0);
 }
 
 __global__ void k_feat_sum(DenoiserDev dn, const float* __restrict__ Fpart, int R, float* __restrict__ F) {
@@ -805,7 +816,7 @@ static int launch_feat_term(DenoiserHost& dh, const SamplerWs& ws, const float* 
 #endif
   {
     VPHO_LAUNCH(k_feat_term, dim3(dn.hid / kFtCols, (ws.R + kFtRows - 1) / kFtRows, kFtSplit), dim3(256), 0, st, dn, feat, ws.R,
-                ws.Fpart);
+                ws.Fpart, dn, feat, ws.R, ws.Fpart, dn.hid / kFtCols);
     const int n4 = ws.R * dn.hid / 4;
     VPHO_LAUNCH(k_feat_sum, dim3((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), dim3(256), 0, st, dn, ws.Fpart, ws.R, ws.F);
   }
@@ -1173,7 +1184,7 @@ extern "C" int vpho_score_eval(vpho_denoiser_t h, const float* x, float t, const
 }
 
 // validates one sampler's arguments, carves its workspace and (begin only) initialises controller, state and feat-term
-static int prepare_job(const vpho_sample_args* a, bool begin, SamplerJob* job, cudaStream_t st) {
+static int prepare_job(const vpho_sample_args* a, bool begin, SamplerJob* job, cudaStream_t st, bool defer_feat = false) {
   if (!a || !a->denoiser || a->n_rows < 0 || a->rows_per_feat <= 0 || !a->workspace) return VPHO_ERR_INVALID;
   if (begin && (a->n_eval < 1 || a->num_steps < 1)) return VPHO_ERR_INVALID;
   if (begin && a->n_rows > 0 && (!a->feat || !a->init_x || !a->x)) return VPHO_ERR_INVALID;
@@ -1190,6 +1201,7 @@ static int prepare_job(const vpho_sample_args* a, bool begin, SamplerJob* job, c
   VPHO_CHECK_LAUNCH();
   if (a->n_rows == 0) return VPHO_OK;
   VPHO_LAUNCH(k_init_state, dim3(red_blocks(job->ws_n)), dim3(256), 0, st, job->ws, a->init_x, job->ws_n);
+  if (defer_feat) return VPHO_OK;
   return launch_feat_term(dh, job->ws, a->feat, st);
 }
 
@@ -1197,11 +1209,31 @@ static int prepare_job(const vpho_sample_args* a, bool begin, SamplerJob* job, c
 static int live_jobs(const vpho_sample_args* const* args, int n_args, bool begin, SamplerJob* jobs, cudaStream_t st, int* rc) {
   int n = 0;
   *rc = VPHO_OK;
+  // two samplers begun together share one split-K feat-term launch (each alone is a latency-bound ~60 us kernel)
+  bool both = begin && n_args == 2;
+  for (int i = 0; both && i < 2; ++i)
+    both = args[i] && args[i]->denoiser && args[i]->n_rows > 0 && !static_cast<DenoiserHost*>(args[i]->denoiser)->use_tc_feat;
+  const float* feats[2] = {nullptr, nullptr};
   for (int i = 0; i < n_args; ++i) {
     SamplerJob j{};
-    *rc = prepare_job(args[i], begin, &j, st);
+    *rc = prepare_job(args[i], begin, &j, st, both);
     if (*rc) return 0;
-    if (args[i]->n_rows > 0) jobs[n++] = j;
+    if (args[i]->n_rows > 0) { feats[n] = args[i]->feat; jobs[n++] = j; }
+  }
+  if (both && n == 2) {
+    const DenoiserDev &d0 = jobs[0].dh->dev, &d1 = jobs[1].dh->dev;
+    const SamplerWs &w0 = jobs[0].ws, &w1 = jobs[1].ws;
+    const int rmax = w0.R > w1.R ? w0.R : w1.R;
+    profile_begin(VPHO_TAG_FEAT_TERM, st);
+    VPHO_LAUNCH(k_feat_term, dim3((d0.hid + d1.hid) / kFtCols, (rmax + kFtRows - 1) / kFtRows, kFtSplit), dim3(256), 0, st, d0, feats[0],
+                w0.R, w0.Fpart, d1, feats[1], w1.R, w1.Fpart, d0.hid / kFtCols);
+    for (int j = 0; j < 2; ++j) {
+      const int n4 = jobs[j].ws.R * jobs[j].dh->dev.hid / 4;
+      VPHO_LAUNCH(k_feat_sum, dim3((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), dim3(256), 0, st, jobs[j].dh->dev, jobs[j].ws.Fpart,
+                  jobs[j].ws.R, jobs[j].ws.F);
+    }
+    profile_end(VPHO_TAG_FEAT_TERM, st);
+    if (cudaGetLastError() != cudaSuccess) { *rc = VPHO_ERR_LAUNCH; return 0; }
   }
   return n;
 }

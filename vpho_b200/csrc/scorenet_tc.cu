@@ -264,6 +264,16 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           const __grid_constant__ CUtensorMap tmA_hi1, const __grid_constant__ CUtensorMap tmA_lo1,
           const __grid_constant__ CUtensorMap tmB_hi1, const __grid_constant__ CUtensorMap tmB_lo1, DenoiserDev dn0, SamplerWs ws0,
           DenoiserDev dn1, SamplerWs ws1, int n_jobs, int mode, int s) {
+  // A skipped RK attempt (spare launches behind a finished integration) leaves before any set-up.  Reading the status
+  // word ahead of pdl_wait is safe as a one-way hint: it is written by k_reduce, which has completed before the kernel
+  // that triggered this launch passed its own pdl_wait, and it never returns to "running" within a sample; a stale
+  // "running" only sends us down the normal path, which checks again after the wait.  The wait itself is still executed
+  // so that the launch chain stays transitively ordered.
+  if (!eval_active(*ws0.ctrl, mode) && !(n_jobs > 1 && eval_active(*ws1.ctrl, mode))) {
+    pdl_trigger();
+    pdl_wait();
+    return;
+  }
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // align inside the shared window with an offset (an integer round trip would demote every access to a generic load)
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -595,6 +605,11 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
                                              const CUtensorMap* tmW1_lo, const CUtensorMap* tmW2_hi, const CUtensorMap* tmW2_lo,
                                              const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, int tile) {
   const RkCtrl& c = *ws.ctrl;
+  if (!eval_active(c, mode)) {           // one-way hint ahead of the wait, see k_head_tc
+    pdl_trigger();
+    pdl_wait();
+    return;
+  }
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   PtSmem& sm = *reinterpret_cast<PtSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

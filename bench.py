@@ -39,7 +39,7 @@ FLOP_HEAD_GEMM_HAND = 2 * (256 * 8192 + 8192 * 3)     # per candidate per networ
 FLOP_HEAD_GEMM_OBJ = 2 * (256 * 768 + 768 * 3)        # same for the object denoiser (3 heads of 256 hidden units)
 FLOP_SCORE_HAND, FLOP_SCORE_OBJ = 4423680, 533504     # whole factored network per candidate per call
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC_BYTES = {"k_head_tc": 17272832}
+NCU_TRAFFIC_BYTES = {"k_head_tc": 24889600}
 
 
 def _peaks():
@@ -383,8 +383,9 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
                      "unit": "TFLOP/s", "frac": round(achieved / peaks["bf16_tflops"], 4) if achieved else None,
                      "traffic": NCU_TRAFFIC_BYTES.get(head_kernel), "peak_source": peaks["source"] + " (cuBLAS bf16 burst)",
                      "note": "FP32-parity contraction run as 3 kind::f16 UMMAs per algorithmic FLOP (hi/lo FP16 planes, exact "
-                             "power-of-two scaling): ceiling for this formulation is peak/3 = %.0f TFLOP/s "
-                             "; ncu: tensor pipe active 59 %% of elapsed, 68 us (profiles/r01_ncu_head_tc_summary.txt)" % (peaks["bf16_tflops"] / 3),
+                             "power-of-two scaling), i.e. the tensor pipe does 3x the algorithmic work: the measured bf16 "
+                             "peak / 3 = %.0f TFLOP/s; ncu: tensor pipe active 73 %% of elapsed, 83 %% of active cycles "
+                             "(profiles/r01_ncu_head_tc_summary.txt)" % (peaks["bf16_tflops"] / 3),
                      "launches_timed": hg["launches"], "network_calls": real_launches, "avg_launch_ms": round(avg_ms, 4),
                      "avg_is": "median over the real launches of a second pass of the same K steps (%.4f ms/step)" % (ms_roof / args.steps),
                      "flop_per_launch": flop_launch,

@@ -453,6 +453,7 @@ __global__ void __launch_bounds__(256) k_obj_final(AssetsDev as, HoiDev h) {
   __shared__ float p_val[64], q_val[64];
   __shared__ int p_idx[64], q_idx[64];
   __shared__ double s_pose[9];
+  __shared__ double s_q[64][4], s_t[64][3];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kk = h.kk, K5 = h.a.phy_topk;
   if (warp == 0) warp_topk<EL>(kk, K5, [&](int i) { return h.pscore[(size_t)b * kk + i]; }, p_val, p_idx, lane);
@@ -462,9 +463,21 @@ __global__ void __launch_bounds__(256) k_obj_final(AssetsDev as, HoiDev h) {
     h.a.dbg_obj_topk[((size_t)2 * h.a.bs + b) * max(h.a.topk_obj, K5) + tid] = p_idx[tid];
     h.a.dbg_obj_topk[((size_t)3 * h.a.bs + b) * max(h.a.topk_obj, K5) + tid] = q_idx[tid];
   }
-  if (tid == 0) {
-    const bool grasped = h.a.is_grasped[b] != 0;
+  // signed quaternions of the K5 winners, one candidate per thread (float64: rot6d -> matrix -> quaternion)
+  const bool grasped = h.a.is_grasped[b] != 0;
+  const double* cand = h.a.pose6d_candidate + (size_t)b * kk * 9;
+  if (tid < K5) {
     const int* idx = grasped ? p_idx : q_idx;
+    const double* p = cand + (size_t)idx[tid] * 9;
+    double R[9], q[4];
+    rot6d_to_matrix(p, R);
+    matrix_to_quaternion(R, q);
+    const double sg = q[0] > 0.0 ? 1.0 : -1.0;
+    for (int i = 0; i < 4; ++i) s_q[tid][i] = sg * q[i];
+    for (int d = 0; d < 3; ++d) s_t[tid][d] = p[6 + d];
+  }
+  __syncthreads();
+  if (tid == 0) {
     float w[64];
     if (grasped) {
       // weight = ones / ones.sum()   (aggregation.py:990-991)
@@ -477,21 +490,15 @@ __global__ void __launch_bounds__(256) k_obj_final(AssetsDev as, HoiDev h) {
       for (int r = 0; r < K5; ++r) w[r] = (q_val[r] + 1e-8f) / (vs + 1e-8f);
     }
     // fuse_topk (aggregation.py:729-740): float64 poses, float32 weights
-    const double* cand = h.a.pose6d_candidate + (size_t)b * kk * 9;
     double tr[3] = {0, 0, 0};
     double A[16];
     for (int i = 0; i < 16; ++i) A[i] = 0.0;
     float wsum = 0.f;
     for (int r = 0; r < K5; ++r) {
-      const double* p = cand + (size_t)idx[r] * 9;
-      for (int d = 0; d < 3; ++d) tr[d] += p[6 + d] * (double)w[r];
-      double R[9], q[4];
-      rot6d_to_matrix(p, R);
-      matrix_to_quaternion(R, q);
-      const double sg = q[0] > 0.0 ? 1.0 : -1.0;
+      for (int d = 0; d < 3; ++d) tr[d] += s_t[r][d] * (double)w[r];
       wsum += w[r];
       for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) A[i * 4 + j] += ((sg * q[i]) * (sg * q[j])) * (double)w[r];
+        for (int j = 0; j < 4; ++j) A[i * 4 + j] += (s_q[r][i] * s_q[r][j]) * (double)w[r];
     }
     for (int i = 0; i < 16; ++i) A[i] /= (double)wsum;
     double qm[4], Rm[9];
@@ -706,6 +713,32 @@ static int run_hoi(const ManoModelDev& m, const AssetsDev& as, const HoiDev& h, 
     attr_set = true;
   }
 #endif
+  // The object's translation / rotation selection and the K x K recombination do not depend on the hand: they run on a
+  // library-owned side stream next to the hand cascade and are joined before the physics score of the recombined poses.
+  cudaStream_t so = st;
+#ifndef VPHO_EMU
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (!side) {
+    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
+      return VPHO_ERR_ALLOC;
+  }
+  if (cudaEventRecord(ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(side, ev_fork, 0) != cudaSuccess) return VPHO_ERR_LAUNCH;
+  so = side;
+#endif
+  // ---- object: translation, rotation, recombination (aggregation.py:1200-1242)
+  const int omax = S > h.kk ? S : h.kk;
+  VPHO_LAUNCH_PDL(k_obj_heat_score, dim3((S + 7) / 8, bs), dim3(256), 0, so, as, h, a.obj_pose6d, (const double*)nullptr, S, h.oscore);
+  if (a.dbg_obj_score) VPHO_LAUNCH(k_copy_f32, dim3((bs * S + 255) / 256), dim3(256), 0, so, h.oscore, a.dbg_obj_score + (size_t)0 * bs * omax, bs * S);
+  VPHO_LAUNCH_PDL(k_obj_transl_fuse<EL>, dim3(bs), dim3(32), 0, so, h);
+  VPHO_LAUNCH_PDL(k_obj_heat_score, dim3((S + 7) / 8, bs), dim3(256), 0, so, as, h, a.obj_pose6d, (const double*)h.t_fused, S, h.oscore);
+  if (a.dbg_obj_score) VPHO_LAUNCH(k_copy_f32, dim3((bs * S + 255) / 256), dim3(256), 0, so, h.oscore, a.dbg_obj_score + (size_t)1 * bs * omax, bs * S);
+  VPHO_LAUNCH_PDL(k_obj_recombine<EL>, dim3(bs), dim3(32), 0, so, h);
+#ifndef VPHO_EMU
+  if (cudaEventRecord(ev_join, side) != cudaSuccess) return VPHO_ERR_LAUNCH;
+#endif
   // ---- hand heat-map cascade (aggregation.py:115-178)
   for (int level = 0; level < 4; ++level) {
     const int ncand = level == 0 ? 2 * S : S + 1;
@@ -723,14 +756,9 @@ static int run_hoi(const ManoModelDev& m, const AssetsDev& as, const HoiDev& h, 
               h.fglobal);
   if (a.dbg_force_point) VPHO_LAUNCH(k_copy_f32, dim3((bs * 96 + 255) / 256), dim3(256), 0, st, h.fpoint, a.dbg_force_point, bs * 96);
   if (a.dbg_force_global) VPHO_LAUNCH(k_copy_f32, dim3((bs * 96 + 255) / 256), dim3(256), 0, st, h.fglobal, a.dbg_force_global, bs * 96);
-  // ---- object: translation, rotation, recombination (aggregation.py:1200-1242)
-  const int omax = S > h.kk ? S : h.kk;
-  VPHO_LAUNCH_PDL(k_obj_heat_score, dim3((S + 7) / 8, bs), dim3(256), 0, st, as, h, a.obj_pose6d, (const double*)nullptr, S, h.oscore);
-  if (a.dbg_obj_score) VPHO_LAUNCH(k_copy_f32, dim3((bs * S + 255) / 256), dim3(256), 0, st, h.oscore, a.dbg_obj_score + (size_t)0 * bs * omax, bs * S);
-  VPHO_LAUNCH_PDL(k_obj_transl_fuse<EL>, dim3(bs), dim3(32), 0, st, h);
-  VPHO_LAUNCH_PDL(k_obj_heat_score, dim3((S + 7) / 8, bs), dim3(256), 0, st, as, h, a.obj_pose6d, (const double*)h.t_fused, S, h.oscore);
-  if (a.dbg_obj_score) VPHO_LAUNCH(k_copy_f32, dim3((bs * S + 255) / 256), dim3(256), 0, st, h.oscore, a.dbg_obj_score + (size_t)1 * bs * omax, bs * S);
-  VPHO_LAUNCH_PDL(k_obj_recombine<EL>, dim3(bs), dim3(32), 0, st, h);
+#ifndef VPHO_EMU
+  if (cudaStreamWaitEvent(st, ev_join, 0) != cudaSuccess) return VPHO_ERR_LAUNCH;
+#endif
   // ---- object: physics / heat-map selection of the recombined candidates, fusion (aggregation.py:1247-1287)
   profile_begin(VPHO_TAG_PHYSICS3, st);
   VPHO_LAUNCH_PDL(k_obj_physics3, dim3(h.kk, bs), dim3(kScanThreads), 0, st, as, h);

@@ -176,6 +176,13 @@ int vpho_pose_metrics(vpho_assets_t h, const float* pd_joint, const float* gt_jo
                       const float* gt_vert, const double* pd_obj6d, const double* gt_obj6d, const int32_t* obj_id, int n,
                       float* metrics, void* stream);
 
+/* Procrustes-aligned hand errors per image, in millimetres: metrics [n][23] = {PA-MJE, PA-MVE, JE[21]} of
+ * `TesterHand.criterion_MJE_PAMJE` (lib/engine/test.py:657-679): the prediction is aligned to the ground truth by the
+ * similarity transform of `rigid_align_AtoB` (lib/utils/transform_fn.py:43-66; SVD of the 3x3 cross-covariance, reflection
+ * fix, scale = sum(s) / var) before the mean joint / vertex distance is taken; JE are the unaligned per-joint errors. */
+int vpho_hand_pa_metrics(const float* pd_joint, const float* gt_joint, const float* pd_vert, const float* gt_vert, int n,
+                         float* metrics, void* stream);
+
 typedef struct {
   int bs;          /* images in this batch                         */
   int S;           /* sample_num: diffusion candidates per image   */

@@ -671,6 +671,35 @@ def hand_pose_error_mm(pd_joint, gt_joint, pd_vert, gt_vert):
     return mje, mve
 
 
+def rigid_align_AtoB(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """Similarity Procrustes alignment of A onto B, `rigid_transform_3D_AtoB` + `rigid_align_AtoB`
+    (lib/utils/transform_fn.py:43-66), statement by statement in the dtype of the inputs."""
+    n, dim = A.shape
+    centroid_A = np.mean(A, axis=0)
+    centroid_B = np.mean(B, axis=0)
+    H = np.dot(np.transpose(A - centroid_A), B - centroid_B) / n
+    U, s, V = np.linalg.svd(H)
+    R = np.dot(np.transpose(V), np.transpose(U))
+    if np.linalg.det(R) < 0:
+        s[-1] = -s[-1]
+        V[2] = -V[2]
+        R = np.dot(np.transpose(V), np.transpose(U))
+    varP = np.var(A, axis=0).sum()
+    c = 1 / varP * np.sum(s)
+    t = -np.dot(c * R, np.transpose(centroid_A)) + np.transpose(centroid_B)
+    return np.transpose(np.dot(c * R, np.transpose(A))) + t
+
+
+def hand_pa_error_mm(pd_joint, gt_joint, pd_vert, gt_vert):
+    """PA-MJE / PA-MVE and the per-joint errors JE of `TesterHand.criterion_MJE_PAMJE` (lib/engine/test.py:657-679):
+    -> (pa_mje (n,), pa_mve (n,), je (n, 21)) in mm."""
+    pj, gj, pv, gv = (np.asarray(t, np.float32) for t in (pd_joint, gt_joint, pd_vert, gt_vert))
+    pa_mje = np.stack([np.linalg.norm(gj[i] - rigid_align_AtoB(pj[i], gj[i]), axis=-1).mean(-1) for i in range(pj.shape[0])])
+    pa_mve = np.stack([np.linalg.norm(gv[i] - rigid_align_AtoB(pv[i], gv[i]), axis=-1).mean(-1) for i in range(pv.shape[0])])
+    je = np.linalg.norm(gj - pj, axis=-1)
+    return pa_mje * 1000, pa_mve * 1000, je * 1000
+
+
 def object_add_mm(obj: OracleObject, pd_6d, gt_6d, obj_name):
     """ADD / ADD-S of TesterObject.criterion_ADD_REP (lib/engine/test.py:413-442) on the sampled vertices."""
     pv = obj(pd_6d.float(), obj_name, data_name="verts")

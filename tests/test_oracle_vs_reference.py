@@ -59,3 +59,13 @@ def test_mano_and_aggregation_bit_identical(ref):
     o = O.hoi_aggregate(O.OracleMano(mano), O.OracleObject(objs), O.OracleAnchors(anch), **cases.clone_kw(kw))
     for k in ("obj_agg_6d", "pose6d_candidate", "agg_obj_vert", "hand_agg_mano", "hand_agg_vert", "hand_agg_joint"):
         assert r[k].dtype == o[k].dtype and torch.equal(r[k], o[k]), k
+
+
+def test_procrustes_alignment_bit_identical(ref):
+    """oracle.rigid_align_AtoB vs the reference's lib/utils/transform_fn.py:43-66 (used by TesterHand's PA metrics)"""
+    rng = np.random.default_rng(3)
+    for n in (21, 778):
+        for dt in (np.float32, np.float64):
+            B = rng.normal(size=(n, 3)).astype(dt) * 0.05
+            A = (B @ np.linalg.qr(rng.normal(size=(3, 3)))[0].astype(dt)) * dt(1.3) + rng.normal(size=(n, 3)).astype(dt) * dt(0.004)
+            assert np.array_equal(O.rigid_align_AtoB(A.copy(), B.copy()), ref.transform_fn.rigid_align_AtoB(A.copy(), B.copy()))

@@ -225,6 +225,19 @@ def force_eval(assets: Assets, vert3d: torch.Tensor, scale: torch.Tensor, weight
     return (terms, *outs) if return_forces else terms
 
 
+def hand_pa_metrics(pd_joint, gt_joint, pd_vert, gt_vert, lib=None) -> torch.Tensor:
+    """Per-image Procrustes-aligned hand errors in mm, (n, 23) = PA-MJE, PA-MVE, JE[21]
+    (TesterHand.criterion_MJE_PAMJE, lib/engine/test.py:657-679; rigid_align_AtoB, lib/utils/transform_fn.py:43-66)."""
+    lib = lib or capi.lib()
+    f = lambda t: t.contiguous().float()   # noqa: E731
+    pj, gj, pv, gv = f(pd_joint), f(gt_joint), f(pd_vert), f(gt_vert)
+    n = pj.shape[0]
+    out = torch.empty((n, 23), dtype=torch.float32, device=pj.device)
+    lib.check(lib.c.vpho_hand_pa_metrics(capi.ptr(pj), capi.ptr(gj), capi.ptr(pv), capi.ptr(gv), n, capi.ptr(out),
+                                         capi.stream_of(pj)), "vpho_hand_pa_metrics")
+    return out
+
+
 def pose_metrics(assets: Assets, pd_joint, gt_joint, pd_vert, gt_vert, pd_obj6d, gt_obj6d, obj_name) -> torch.Tensor:
     """Per-image final pose error in mm, (n, 4) = MJE, MVE (TesterHand, lib/engine/test.py:657-679), ADD, ADD-S
     (TesterObject.criterion_ADD_REP, lib/engine/test.py:413-442), computed on the device so that the metric gather is the

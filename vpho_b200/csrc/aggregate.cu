@@ -346,6 +346,31 @@ __global__ void __launch_bounds__(32) k_obj_recombine(HoiDev h) {
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
 
+#ifndef VPHO_EMU
+// packed FP32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): each half is an ordinary IEEE single-precision operation
+__device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long sub_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+#endif
+
 // pts(i, out[3]) yields posed point i; results (min squared distance, first arg-min) of the 32 anchors land in
 // s_d2[0..32), s_arg[0..32) (shared) after the call.  All kScanThreads threads of the CTA must call it.
 template <typename PtFn>
@@ -356,6 +381,39 @@ __device__ __forceinline__ void anchor_nearest_scan(int n_pts, const float* anch
   float best = INFINITY;
   int arg = 0;
   const float ax = anchor[0], ay = anchor[1], az = anchor[2];
+#ifndef VPHO_EMU
+  // Packed-FP32 scan: the tile is kept as three coordinate planes and two points are handled per instruction
+  // (FADD2 / FMUL2 / FFMA2).  Every lane of a pair performs exactly the scalar sequence of the loop below,
+  // d2 = fma(dz, dz, fma(dx, dx, dy * dy)), so distances, ties and the first arg-min are unchanged.  Slots past the last
+  // point hold a far-away coordinate: they can never win against the real points that precede them in a warp's slice.
+  float* tx = reinterpret_cast<float*>(tile);
+  float* ty = tx + kScanThreads;
+  float* tz = ty + kScanThreads;
+  const unsigned long long A = pack_f32x2(ax, ax), B = pack_f32x2(ay, ay), C = pack_f32x2(az, az);
+  for (int p0 = 0; p0 < n_pts; p0 += kScanThreads) {
+    __syncthreads();
+    {
+      float o[3] = {1e18f, 1e18f, 1e18f};
+      if (p0 + tid < n_pts) pts(p0 + tid, o);
+      tx[tid] = o[0]; ty[tid] = o[1]; tz[tid] = o[2];
+    }
+    __syncthreads();
+    const int base = warp * 32;
+    if (n_pts - p0 - base <= 0) continue;
+#pragma unroll 4
+    for (int q = 0; q < 32; q += 2) {
+      const unsigned long long X = *reinterpret_cast<const unsigned long long*>(tx + base + q);
+      const unsigned long long Y = *reinterpret_cast<const unsigned long long*>(ty + base + q);
+      const unsigned long long Z = *reinterpret_cast<const unsigned long long*>(tz + base + q);
+      const unsigned long long dx = sub_f32x2(A, X), dy = sub_f32x2(B, Y), dz = sub_f32x2(C, Z);
+      const unsigned long long d = fma_f32x2(dz, dz, fma_f32x2(dx, dx, mul_f32x2(dy, dy)));
+      float d0, d1;
+      unpack_f32x2(d, d0, d1);
+      if (d0 < best) { best = d0; arg = p0 + base + q; }
+      if (d1 < best) { best = d1; arg = p0 + base + q + 1; }
+    }
+  }
+#else
   for (int p0 = 0; p0 < n_pts; p0 += kScanThreads) {
     __syncthreads();
     {
@@ -373,6 +431,7 @@ __device__ __forceinline__ void anchor_nearest_scan(int n_pts, const float* anch
       if (d2 < best) { best = d2; arg = p0 + base + q; }
     }
   }
+#endif
   red_d2[warp * 32 + lane] = best;
   red_arg[warp * 32 + lane] = arg;
   __syncthreads();

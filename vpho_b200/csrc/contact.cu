@@ -262,6 +262,165 @@ __global__ void __launch_bounds__(256) k_pose_metrics(AssetsDev as, const float*
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Procrustes-aligned hand errors: PA-MJE / PA-MVE and the per-joint errors of TesterHand.criterion_MJE_PAMJE
+// (lib/engine/test.py:657-679) with rigid_align_AtoB (lib/utils/transform_fn.py:43-66): similarity transform
+// (c, R, t) = argmin |c R A + t - B| from the SVD of the 3x3 cross-covariance.  One CTA per image; float64 moments with
+// fixed-order block reductions; the SVD is taken from the Jacobi eigen-decomposition of H^T H by one thread.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_256d(double v, double* red) {
+  const int tid = threadIdx.x;
+  red[tid] = v;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (tid < st) red[tid] += red[tid + st];
+    __syncthreads();
+  }
+  const double r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// eigen-decomposition of a symmetric 3x3 (row-major M): eigenvalues w descending, eigenvectors in the COLUMNS of V
+__device__ void sym3_eig(const double* M, double* w, double* V) {
+  double a[9];
+  for (int i = 0; i < 9; ++i) { a[i] = M[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    const double off = a[1] * a[1] + a[2] * a[2] + a[5] * a[5];
+    if (off <= 1e-300) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = a[p * 3 + q];
+        if (fabs(apq) <= 1e-300) continue;
+        const double theta = (a[q * 3 + q] - a[p * 3 + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; ++k) {          // A <- A J
+          const double akp = a[k * 3 + p], akq = a[k * 3 + q];
+          a[k * 3 + p] = c * akp - sn * akq;
+          a[k * 3 + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {          // A <- J^T A
+          const double apk = a[p * 3 + k], aqk = a[q * 3 + k];
+          a[p * 3 + k] = c * apk - sn * aqk;
+          a[q * 3 + k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {          // V <- V J
+          const double vkp = V[k * 3 + p], vkq = V[k * 3 + q];
+          V[k * 3 + p] = c * vkp - sn * vkq;
+          V[k * 3 + q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  w[0] = a[0]; w[1] = a[4]; w[2] = a[8];
+  for (int i = 0; i < 2; ++i)                   // sort descending (columns follow)
+    for (int j = 0; j < 2 - i; ++j)
+      if (w[j] < w[j + 1]) {
+        const double tw = w[j]; w[j] = w[j + 1]; w[j + 1] = tw;
+        for (int k = 0; k < 3; ++k) { const double tv = V[k * 3 + j]; V[k * 3 + j] = V[k * 3 + j + 1]; V[k * 3 + j + 1] = tv; }
+      }
+}
+
+// similarity transform of the point set A [n][3] onto B: fills T[12] = {c R (row-major 3x3), t}
+__device__ void procrustes_256(const float* __restrict__ A, const float* __restrict__ B, int n, double* red, double* T /*shared [12]*/) {
+  const int tid = threadIdx.x;
+  double ca[3], cb[3];
+  for (int d = 0; d < 3; ++d) {
+    double sa = 0.0, sb = 0.0;
+    for (int i = tid; i < n; i += 256) { sa += (double)A[i * 3 + d]; sb += (double)B[i * 3 + d]; }
+    ca[d] = block_sum_256d(sa, red) / n;
+    cb[d] = block_sum_256d(sb, red) / n;
+  }
+  double H[9], var = 0.0;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      double acc = 0.0;
+      for (int i = tid; i < n; i += 256) acc += ((double)A[i * 3 + r] - ca[r]) * ((double)B[i * 3 + c] - cb[c]);
+      H[r * 3 + c] = block_sum_256d(acc, red) / n;          // H = (A - cA)^T (B - cB) / n
+    }
+  for (int d = 0; d < 3; ++d) {
+    double acc = 0.0;
+    for (int i = tid; i < n; i += 256) { const double x = (double)A[i * 3 + d] - ca[d]; acc += x * x; }
+    var += block_sum_256d(acc, red) / n;                    // np.var(A, axis=0).sum()
+  }
+  if (tid == 0) {
+    // H = U S V^T.  Eigen-decompose H^T H = V S^2 V^T, make V right-handed, u_i = H v_i / s_i, u_3 = u_1 x u_2; the
+    // reflection case of the reference (det(V U^T) < 0 -> negate the last singular value) is the sign of det(H).
+    double M[9], w[3], V[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) M[r * 3 + c] = (H[0 * 3 + r] * H[0 * 3 + c] + H[1 * 3 + r] * H[1 * 3 + c]) + H[2 * 3 + r] * H[2 * 3 + c];
+    sym3_eig(M, w, V);
+    double v[3][3], u[3][3], sv[3];
+    for (int i = 0; i < 3; ++i)
+      for (int k = 0; k < 3; ++k) v[i][k] = V[k * 3 + i];
+    v[2][0] = v[0][1] * v[1][2] - v[0][2] * v[1][1];         // v3 = v1 x v2
+    v[2][1] = v[0][2] * v[1][0] - v[0][0] * v[1][2];
+    v[2][2] = v[0][0] * v[1][1] - v[0][1] * v[1][0];
+    for (int i = 0; i < 3; ++i) sv[i] = sqrt(w[i] > 0.0 ? w[i] : 0.0);
+    for (int i = 0; i < 2; ++i) {
+      double hv[3], nrm = 0.0;
+      for (int r = 0; r < 3; ++r) { hv[r] = (H[r * 3 + 0] * v[i][0] + H[r * 3 + 1] * v[i][1]) + H[r * 3 + 2] * v[i][2]; nrm += hv[r] * hv[r]; }
+      nrm = sqrt(nrm);
+      for (int r = 0; r < 3; ++r) u[i][r] = nrm > 0.0 ? hv[r] / nrm : (r == i ? 1.0 : 0.0);
+    }
+    u[2][0] = u[0][1] * u[1][2] - u[0][2] * u[1][1];         // u3 = u1 x u2
+    u[2][1] = u[0][2] * u[1][0] - u[0][0] * u[1][2];
+    u[2][2] = u[0][0] * u[1][1] - u[0][1] * u[1][0];
+    const double det = H[0] * (H[4] * H[8] - H[5] * H[7]) - H[1] * (H[3] * H[8] - H[5] * H[6]) + H[2] * (H[3] * H[7] - H[4] * H[6]);
+    const double dsg = det < 0.0 ? -1.0 : 1.0;
+    const double scale = ((sv[0] + sv[1]) + dsg * sv[2]) / var;          // c = sum(s) / var(A)
+    // R = V U^T with both bases right-handed: for det(H) < 0 this IS the reference's "flip the last singular pair"
+    // rotation (its own u_3 is then -(u_1 x u_2)); only the scale sees the sign
+    double R[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) R[r * 3 + c] = (v[0][r] * u[0][c] + v[1][r] * u[1][c]) + v[2][r] * u[2][c];
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) T[r * 3 + c] = scale * R[r * 3 + c];
+      T[9 + r] = cb[r] - ((T[r * 3 + 0] * ca[0] + T[r * 3 + 1] * ca[1]) + T[r * 3 + 2] * ca[2]);      // t = cB - c R cA
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double aligned_error(const float* a, const float* b, const double* T) {
+  double e2 = 0.0;
+  for (int r = 0; r < 3; ++r) {
+    const double x = ((T[r * 3 + 0] * (double)a[0] + T[r * 3 + 1] * (double)a[1]) + T[r * 3 + 2] * (double)a[2]) + T[9 + r];
+    const double d = (double)b[r] - x;
+    e2 += d * d;
+  }
+  return sqrt(e2);
+}
+
+// out [n][23] = {PA-MJE, PA-MVE, JE[21]} in mm
+__global__ void __launch_bounds__(256) k_hand_pa_metrics(const float* __restrict__ pd_joint, const float* __restrict__ gt_joint,
+                                                         const float* __restrict__ pd_vert, const float* __restrict__ gt_vert,
+                                                         float* __restrict__ out) {
+  __shared__ double red[256];
+  __shared__ double T[12];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* pj = pd_joint + (size_t)b * 21 * 3;
+  const float* gj = gt_joint + (size_t)b * 21 * 3;
+  const float* pv = pd_vert + (size_t)b * kVerts * 3;
+  const float* gv = gt_vert + (size_t)b * kVerts * 3;
+  if (tid < 21) {
+    const float dx = gj[tid * 3 + 0] - pj[tid * 3 + 0], dy = gj[tid * 3 + 1] - pj[tid * 3 + 1], dz = gj[tid * 3 + 2] - pj[tid * 3 + 2];
+    out[(size_t)b * 23 + 2 + tid] = sqrtf((dx * dx + dy * dy) + dz * dz) * 1000.f;
+  }
+  procrustes_256(pj, gj, 21, red, T);
+  double e = tid < 21 ? aligned_error(pj + tid * 3, gj + tid * 3, T) : 0.0;
+  const double pa_mje = block_sum_256d(e, red) / 21.0;
+  procrustes_256(pv, gv, kVerts, red, T);
+  e = 0.0;
+  for (int i = tid; i < kVerts; i += 256) e += aligned_error(pv + i * 3, gv + i * 3, T);
+  const double pa_mve = block_sum_256d(e, red) / (double)kVerts;
+  if (tid == 0) {
+    out[(size_t)b * 23 + 0] = (float)(pa_mje * 1000.0);
+    out[(size_t)b * 23 + 1] = (float)(pa_mve * 1000.0);
+  }
+}
+
 }  // namespace vpho
 
 using namespace vpho;
@@ -274,6 +433,16 @@ extern "C" int vpho_pose_metrics(vpho_assets_t h, const float* pd_joint, const f
   if (!pd_joint || !gt_joint || !pd_vert || !gt_vert || !pd_obj6d || !gt_obj6d || !obj_id || !metrics) return VPHO_ERR_INVALID;
   VPHO_LAUNCH(k_pose_metrics, dim3(n), dim3(256), 0, (cudaStream_t)stream, static_cast<AssetsHost*>(h)->dev, pd_joint, gt_joint, pd_vert,
               gt_vert, pd_obj6d, gt_obj6d, obj_id, metrics);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
+
+extern "C" int vpho_hand_pa_metrics(const float* pd_joint, const float* gt_joint, const float* pd_vert, const float* gt_vert, int n,
+                                    float* metrics, void* stream) {
+  if (n < 0) return VPHO_ERR_INVALID;
+  if (n == 0) return VPHO_OK;
+  if (!pd_joint || !gt_joint || !pd_vert || !gt_vert || !metrics) return VPHO_ERR_INVALID;
+  VPHO_LAUNCH(k_hand_pa_metrics, dim3(n), dim3(256), 0, (cudaStream_t)stream, pd_joint, gt_joint, pd_vert, gt_vert, metrics);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }

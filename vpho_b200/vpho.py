@@ -42,6 +42,8 @@ class VphoHotPath:
         self._side_stream = None
         self._side_stream2 = None
         self.pair_samplers = os.environ.get("VPHO_PAIR_SAMPLERS", "1") != "0"
+        self._agg_stream = None
+        self.aggregate_priority = os.environ.get("VPHO_AGG_PRIORITY", "1") != "0"
 
     # ---- vpho_net.postprocess_diffusion_hand, branch 'mano_pose' (VPHO.py:306-331) ----
     def postprocess_diffusion_hand(self, hand_inprocess, hand_final, pd_mano_shape):
@@ -174,14 +176,32 @@ class VphoHotPath:
             pd["diff_inprocess_obj_6d"] = xs_o.reshape(bs, S, -1, 9)
         pd["diff_final_obj_6d"] = x_o.reshape(bs, S, 9)
 
-        sel = self.hoi_aggregator(
-            cam_intrinsic=batch["cam_intr_crop_flip"], root_joint_flip=batch["root_joint_flip"],
-            root_joint=batch["root_joint"], is_right=batch["is_right"], force_local=batch["force_local"],
-            is_grasped=batch["is_grasped"], hand_pose_diff=final_mano[:, :48], hand_pose_regression=pd_mano_pose,
-            hand_shape=final_mano[:, 48:], hand_heatmap=batch["hm_hand"], hand_bbox=batch["bbox_hand"],
-            hand_topk=self.topk_hand, obj_pose6d=pd["diff_final_obj_6d"], obj_heatmap=batch["hm_obj"],
-            obj_bbox=batch["bbox_obj_rect"], obj_topk=self.topk_obj,
-            obj_name=batch["obj_id"] if "obj_id" in batch else batch["obj_name"])
+        def aggregate():
+            return self.hoi_aggregator(
+                cam_intrinsic=batch["cam_intr_crop_flip"], root_joint_flip=batch["root_joint_flip"],
+                root_joint=batch["root_joint"], is_right=batch["is_right"], force_local=batch["force_local"],
+                is_grasped=batch["is_grasped"], hand_pose_diff=final_mano[:, :48], hand_pose_regression=pd_mano_pose,
+                hand_shape=final_mano[:, 48:], hand_heatmap=batch["hm_hand"], hand_bbox=batch["bbox_hand"],
+                hand_topk=self.topk_hand, obj_pose6d=pd["diff_final_obj_6d"], obj_heatmap=batch["hm_obj"],
+                obj_bbox=batch["bbox_obj_rect"], obj_topk=self.topk_obj,
+                obj_name=batch["obj_id"] if "obj_id" in batch else batch["obj_name"])
+
+        # The aggregation is a chain of short kernels on the critical path; the output-only stream floods the GPU with
+        # the 6400 candidate meshes at the same time.  Running the chain on a high-priority stream lets its CTAs be
+        # placed ahead of the pending mesh CTAs whenever SM slots free up.
+        if side2 is not None and self.aggregate_priority:
+            if self._agg_stream is None:
+                self._agg_stream = torch.cuda.Stream(device=enc_h.device, priority=-1)
+            hs = self._agg_stream
+            hs.wait_stream(main)
+            with torch.cuda.stream(hs):
+                sel = aggregate()
+            main.wait_stream(hs)
+            for v in sel.values():
+                if torch.is_tensor(v):
+                    v.record_stream(main)
+        else:
+            sel = aggregate()
         pd["agg_obj_6d"] = sel["obj_agg_6d"]
         pd["agg_hand_mano"] = sel["hand_agg_mano"]
         pd["agg_hand_vert"] = sel["hand_agg_vert"]

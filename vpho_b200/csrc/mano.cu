@@ -17,15 +17,6 @@ struct ManoModelHost {
   float* blob = nullptr;
 };
 
-// the blended rest-pose vertices of the TC candidates are parked in shared memory between the blend and the skinning
-// loop, so that the latter can stay rolled: fully unrolled it is ~5000 straight-line instructions executed once per
-// thread and a fifth of the kernel's stall samples are instruction-fetch misses
-template <int TC>
-struct ManoFwdSmem {
-  ManoSmem<TC> mano;
-  float stage[TC * 3][kVChunkPad];
-};
-
 template <int TC>
 __global__ void __launch_bounds__(kVChunkPad) mano_forward_kernel(ManoModelDev m, const float* __restrict__ pose,
                                                                   const float* __restrict__ shape, int pose_stride,
@@ -33,8 +24,8 @@ __global__ void __launch_bounds__(kVChunkPad) mano_forward_kernel(ManoModelDev m
                                                                   float* __restrict__ joints) {
   pdl_wait();          // launched with VPHO_LAUNCH_PDL
   pdl_trigger();
-  VPHO_DYN_SMEM(ManoFwdSmem<TC>, sp);
-  ManoSmem<TC>& s = sp->mano;
+  VPHO_DYN_SMEM(ManoSmem<TC>, sp);
+  ManoSmem<TC>& s = *sp;
   const int c0 = blockIdx.x * TC;
   const int chunk = blockIdx.y;
   const int tid = threadIdx.x;
@@ -99,14 +90,9 @@ __global__ void __launch_bounds__(kVChunkPad) mano_forward_kernel(ManoModelDev m
     if (v == tip_vertex(t)) tip = t;
 #pragma unroll
   for (int c = 0; c < TC; ++c) {
-    sp->stage[c * 3 + 0][tid] = acc[c][0]; sp->stage[c * 3 + 1][tid] = acc[c][1]; sp->stage[c * 3 + 2][tid] = acc[c][2];
-  }
-  const int nc = min(TC, n - c0);
-#pragma unroll 2
-  for (int c = 0; c < nc; ++c) {
-    const float vp[3] = {sp->stage[c * 3 + 0][tid], sp->stage[c * 3 + 1][tid], sp->stage[c * 3 + 2][tid]};
+    if (c0 + c >= n) break;
     float o[3];
-    mano_skin_point<TC>(s, c, w, vp, o);
+    mano_skin_point<TC>(s, c, w, acc[c], o);
 #pragma unroll
     for (int d = 0; d < 3; ++d) o[d] = mano_center_scale(o[d], s.G[c][0][d * 4 + 3]);
     if (verts) {
@@ -124,7 +110,7 @@ template <int TC>
 static int launch_mano_forward(const ManoModelDev& m, const float* pose, const float* shape, int pose_stride,
                                int shape_stride, int n, float* verts, float* joints, cudaStream_t stream) {
   dim3 grid((n + TC - 1) / TC, kNumVChunks);
-  const size_t smem = sizeof(ManoFwdSmem<TC>);
+  const size_t smem = sizeof(ManoSmem<TC>);
 #ifndef VPHO_EMU
   static bool attr_set = false;
   if (!attr_set) {

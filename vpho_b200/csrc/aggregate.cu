@@ -30,7 +30,6 @@ struct HoiDev {
   int kk;            // recombined object candidates per image = topk_obj^2
   int n_pts;
   // workspace
-  unsigned int* done;  // [bs][8] per-image arrival counters of the merged score + fuse launches (zero between calls)
   float* hscore;     // [bs][2S][5]
   float* fused;      // [bs][48]   cascade-fused pose (levels written as they are fused)
   float* l4;         // [bs][topk_hand][5][3]  level-3 axis-angles of the per-finger top-k (aggregation.py:1310)
@@ -74,7 +73,9 @@ struct HandScoreSmem {
 
 // one CTA = TC candidates of one image: joints-only MANO -> projection -> bicubic heat sampling -> finger scores
 template <int TC>
-__device__ __forceinline__ void hand_level_score_tile(const ManoModelDev& m, const HoiDev& h, int level) {
+__global__ void __launch_bounds__(128) k_hand_level_score(ManoModelDev m, HoiDev h, int level) {
+  pdl_wait();          // launched with VPHO_LAUNCH_PDL
+  pdl_trigger();
   VPHO_DYN_SMEM(HandScoreSmem<TC>, sp);
   HandScoreSmem<TC>& s = *sp;
   const int b = blockIdx.y, c0 = blockIdx.x * TC, tid = threadIdx.x, nt = blockDim.x;
@@ -159,33 +160,19 @@ __device__ __forceinline__ void hand_level_score_tile(const ManoModelDev& m, con
   }
 }
 
-template <int TC>
-__global__ void __launch_bounds__(128) k_hand_level_score(ManoModelDev m, HoiDev h, int level) {
+// one CTA per image, one warp per finger list: top-k -> weights -> weighted quaternion average -> fused axis-angle
+template <int EL>
+__global__ void __launch_bounds__(160) k_hand_level_fuse(HoiDev h, int level) {
   pdl_wait();          // launched with VPHO_LAUNCH_PDL
   pdl_trigger();
-  hand_level_score_tile<TC>(m, h, level);
-}
-
-// one CTA per image, one warp per finger list: top-k -> weights -> weighted quaternion average -> fused axis-angle
-// the scores may have been written by other CTAs of the same launch (merged score + fuse kernel): bypass L1
-__device__ __forceinline__ float load_score(const float* p) {
-#ifndef VPHO_EMU
-  return __ldcg(p);
-#else
-  return *p;
-#endif
-}
-
-template <int EL>
-__device__ __forceinline__ void hand_level_fuse_image(const HoiDev& h, int level, int b) {
   __shared__ float s_val[5][64];
   __shared__ int s_idx[5][64];
   __shared__ float s_q[5][64][4];
-  const int f = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x, f = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = h.a.S, K = h.a.topk_hand, n = 2 * S;
-  if (f > 4 || (level == 0 && f != 0)) return;
+  if (level == 0 && f != 0) return;
   const float* sc = h.hscore + (size_t)b * n * 5;
-  auto value_of = [&](int i) { return load_score(sc + (size_t)((level > 0 && i > S) ? S : i) * 5 + (level == 0 ? 0 : f)); };
+  auto value_of = [&](int i) { return sc[(size_t)((level > 0 && i > S) ? S : i) * 5 + (level == 0 ? 0 : f)]; };
   warp_topk<EL>(n, K, value_of, s_val[f], s_idx[f], lane);
   if (h.a.dbg_hand_score) {
     for (int i = lane; i < n; i += 32)
@@ -233,35 +220,6 @@ __device__ __forceinline__ void hand_level_fuse_image(const HoiDev& h, int level
 #pragma unroll
     for (int d = 0; d < 3; ++d) h.fused[b * 48 + 3 * jm + d] = faa[d];
   }
-}
-
-template <int EL>
-__global__ void __launch_bounds__(160) k_hand_level_fuse(HoiDev h, int level) {
-  pdl_wait();          // launched with VPHO_LAUNCH_PDL
-  pdl_trigger();
-  hand_level_fuse_image<EL>(h, level, blockIdx.x);
-}
-
-// Score + fuse of one cascade level in ONE launch: the CTA that finishes an image's last score tile (per-image arrival
-// counter) fuses that image, so the 64 short per-image fusions overlap the other images' score tiles instead of forming a
-// separate, nearly empty launch.  5 warps per CTA (one per finger list in the fusion).
-template <int TC, int EL>
-__global__ void __launch_bounds__(160) k_hand_level(ManoModelDev m, HoiDev h, int level) {
-  pdl_wait();          // launched with VPHO_LAUNCH_PDL
-  pdl_trigger();
-  hand_level_score_tile<TC>(m, h, level);
-  __shared__ bool last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(&h.done[blockIdx.y * 8 + level], 1u);
-    last = (prev == gridDim.x - 1);
-    if (last) h.done[blockIdx.y * 8 + level] = 0u;          // ready for the next call
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  hand_level_fuse_image<EL>(h, level, blockIdx.y);
 }
 
 __global__ void k_copy_cascade_pose(HoiDev h) {
@@ -787,7 +745,7 @@ static size_t hoi_carve(void* base, int bs, int S, int Kh, int Ko, int n_pts, Ho
                o_pverts = take((size_t)bs * nc * kVerts * 3 * 4), o_pjoints = take((size_t)bs * nc * 63 * 4),
                o_ppoint = take((size_t)bs * nc * 96 * 4), o_pforce = take((size_t)bs * nc * 96 * 4),
                o_fscore = take((size_t)bs * 5 * nc * 4), o_ocom = take((size_t)bs * 3 * 4),
-               o_pshape = take((size_t)bs * nc * 10 * 4), o_done = take((size_t)bs * 8 * 4);
+               o_pshape = take((size_t)bs * nc * 10 * 4);
   if (h) {
     char* p = static_cast<char*>(base);
     h->nc = nc; h->kk = kk; h->n_pts = n_pts;
@@ -797,7 +755,6 @@ static size_t hoi_carve(void* base, int bs, int S, int Kh, int Ko, int n_pts, Ho
     h->t_topk = (int*)(p + o_ttopk); h->t_fused = (double*)(p + o_tfused); h->ppose = (float*)(p + o_ppose);
     h->pverts = (float*)(p + o_pverts); h->pjoints = (float*)(p + o_pjoints); h->ppoint = (float*)(p + o_ppoint);
     h->pforce = (float*)(p + o_pforce); h->fscore = (float*)(p + o_fscore); h->ocom = (float*)(p + o_ocom); h->pshape = (float*)(p + o_pshape);
-    h->done = (unsigned int*)(p + o_done);
   }
   return off;
 }
@@ -812,7 +769,6 @@ static int run_hoi(const ManoModelDev& m, const AssetsDev& as, const HoiDev& h, 
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_hand_level_score<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_hand_level<TC, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
 #endif
@@ -843,19 +799,9 @@ static int run_hoi(const ManoModelDev& m, const AssetsDev& as, const HoiDev& h, 
   if (cudaEventRecord(ev_join, side) != cudaSuccess) return VPHO_ERR_LAUNCH;
 #endif
   // ---- hand heat-map cascade (aggregation.py:115-178)
-  static const bool merged = [] { const char* e = getenv("VPHO_AGG_MERGE"); return e && e[0] == '1'; }();
-  if (merged) {
-    // the counters are zero between calls (the last CTA of an image resets its own); the workspace arrives uninitialised
-    if (cudaMemsetAsync(h.done, 0, (size_t)bs * 8 * sizeof(unsigned int), st) != cudaSuccess) return VPHO_ERR_LAUNCH;
-  }
   for (int level = 0; level < 4; ++level) {
     const int ncand = level == 0 ? 2 * S : S + 1;
     profile_begin(VPHO_TAG_HAND_SCORE, st);
-    if (merged) {
-      VPHO_LAUNCH_PDL((k_hand_level<TC, EL>), dim3((ncand + TC - 1) / TC, bs), dim3(160), smem, st, m, h, level);
-      profile_end(VPHO_TAG_HAND_SCORE, st);
-      continue;
-    }
     VPHO_LAUNCH_PDL(k_hand_level_score<TC>, dim3((ncand + TC - 1) / TC, bs), dim3(128), smem, st, m, h, level);
     profile_end(VPHO_TAG_HAND_SCORE, st);
     VPHO_LAUNCH_PDL(k_hand_level_fuse<EL>, dim3(bs), dim3(160), 0, st, h, level);

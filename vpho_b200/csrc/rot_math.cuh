@@ -137,13 +137,18 @@ __device__ __forceinline__ void sym4_top_eigvec(T* A, T* q) {
   const T tiny = sizeof(T) == 8 ? T(1e-300) : T(1e-37);
   for (int sweep = 0; sweep < 30; ++sweep) {
     T off = T(0), diag = T(0);
+#pragma unroll
     for (int p = 0; p < 4; ++p) {
       diag += A[p * 4 + p] * A[p * 4 + p];
+#pragma unroll
       for (int r = p + 1; r < 4; ++r) off += A[p * 4 + r] * A[p * 4 + r];
     }
     const T epsq = sizeof(T) == 8 ? T(1e-32) : T(1e-15);
     if (off <= epsq * diag || off < tiny) break;
+    // p, r, k loops fully unrolled: A and V stay in registers (rolled, their dynamic indexing puts them in local memory)
+#pragma unroll
     for (int p = 0; p < 3; ++p)
+#pragma unroll
       for (int r = p + 1; r < 4; ++r) {
         T apq = A[p * 4 + r];
         if (v_abs(apq) < tiny) continue;
@@ -151,16 +156,19 @@ __device__ __forceinline__ void sym4_top_eigvec(T* A, T* q) {
         T tau = (aqq - app) / (T(2) * apq);
         T t = (tau >= T(0) ? T(1) : T(-1)) / (v_abs(tau) + v_sqrt(T(1) + tau * tau));
         T c = T(1) / v_sqrt(T(1) + t * t), s = t * c;
+#pragma unroll
         for (int k = 0; k < 4; ++k) {   // columns p, r of A
           T akp = A[k * 4 + p], akq = A[k * 4 + r];
           A[k * 4 + p] = c * akp - s * akq;
           A[k * 4 + r] = s * akp + c * akq;
         }
+#pragma unroll
         for (int k = 0; k < 4; ++k) {   // rows p, r of A
           T apk = A[p * 4 + k], aqk = A[r * 4 + k];
           A[p * 4 + k] = c * apk - s * aqk;
           A[r * 4 + k] = s * apk + c * aqk;
         }
+#pragma unroll
         for (int k = 0; k < 4; ++k) {
           T vkp = V[k * 4 + p], vkq = V[k * 4 + r];
           V[k * 4 + p] = c * vkp - s * vkq;
@@ -168,11 +176,19 @@ __device__ __forceinline__ void sym4_top_eigvec(T* A, T* q) {
         }
       }
   }
-  int best = 0;
+  // arg-max of the diagonal (first maximum) selected without dynamic indexing
+  T bv = A[0];
+  T vb[4] = {V[0], V[4], V[8], V[12]};
+#pragma unroll
   for (int i = 1; i < 4; ++i)
-    if (A[i * 4 + i] > A[best * 4 + best]) best = i;
-  T sgn = V[0 * 4 + best] > T(0) ? T(1) : T(-1);   // ((q_w > 0) - 0.5) * 2
-  for (int k = 0; k < 4; ++k) q[k] = sgn * V[k * 4 + best];
+    if (A[i * 4 + i] > bv) {
+      bv = A[i * 4 + i];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) vb[k] = V[k * 4 + i];
+    }
+  T sgn = vb[0] > T(0) ? T(1) : T(-1);   // ((q_w > 0) - 0.5) * 2
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = sgn * vb[k];
 }
 
 // average_quaternion over n quaternions (stride given) with optional weights (nullptr = ones).

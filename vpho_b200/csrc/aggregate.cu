@@ -232,7 +232,7 @@ __global__ void k_copy_cascade_pose(HoiDev h) {
 // ------------------------------------------------------------------------------------------------------------
 // verts [n][778][3] wrist-centred; root [n/group][3] is added first (vert_cam = vert + root_joint_flip);
 // force_local [n/group][32][3]; outputs point/force [n][32][3]
-__global__ void __launch_bounds__(128) k_force_anchors(AssetsDev as, const float* __restrict__ verts,
+__global__ void __launch_bounds__(256) k_force_anchors(AssetsDev as, const float* __restrict__ verts,
                                                        const float* __restrict__ root, const float* __restrict__ force_local,
                                                        int n, int group, float* __restrict__ point, float* __restrict__ force) {
   pdl_wait();          // launched with VPHO_LAUNCH_PDL
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(128) k_force_anchors(AssetsDev as, const float
   float r[3] = {0.f, 0.f, 0.f};
   if (root) { r[0] = root[(i / group) * 3 + 0]; r[1] = root[(i / group) * 3 + 1]; r[2] = root[(i / group) * 3 + 2]; }
   // joints = vert2joint . vert_cam   (hand_fn.py:436-448)
-  for (int o = warp; o < 63; o += 4) {
+  for (int o = warp; o < 63; o += (int)(blockDim.x >> 5)) {
     const int k = o / 3, d = o % 3;
     float acc = 0.f;
     for (int vv = lane; vv < kVerts; vv += 32) acc = fmaf(as.v2j[k * kVerts + vv], v[vv * 3 + d] + r[d], acc);
@@ -811,7 +811,7 @@ static int run_hoi(const ManoModelDev& m, const AssetsDev& as, const HoiDev& h, 
   int rc = mano_forward_dev(m, h.fused, a.hand_shape, 48, 10 * S, bs, h.cverts, h.cjoints, st);
   if (rc) return rc;
   // ---- force anchors of the fused hand (aggregation.py:1195-1196)
-  VPHO_LAUNCH_PDL(k_force_anchors, dim3(bs), dim3(128), 0, st, as, h.cverts, a.root_joint_flip, a.force_local, bs, 1, h.fpoint,
+  VPHO_LAUNCH_PDL(k_force_anchors, dim3(bs), dim3(256), 0, st, as, h.cverts, a.root_joint_flip, a.force_local, bs, 1, h.fpoint,
               h.fglobal);
   if (a.dbg_force_point) VPHO_LAUNCH(k_copy_f32, dim3((bs * 96 + 255) / 256), dim3(256), 0, st, h.fpoint, a.dbg_force_point, bs * 96);
   if (a.dbg_force_global) VPHO_LAUNCH(k_copy_f32, dim3((bs * 96 + 255) / 256), dim3(256), 0, st, h.fglobal, a.dbg_force_global, bs * 96);
@@ -833,7 +833,7 @@ static int run_hoi(const ManoModelDev& m, const AssetsDev& as, const HoiDev& h, 
   VPHO_LAUNCH_PDL(k_build_phys_pose, dim3(bs), dim3(256), 0, st, h);
   rc = mano_forward_dev(m, h.ppose, h.pshape, 48, 10, bs * h.nc, h.pverts, h.pjoints, st);
   if (rc) return rc;
-  VPHO_LAUNCH_PDL(k_force_anchors, dim3(bs * h.nc), dim3(128), 0, st, as, h.pverts, a.root_joint_flip, a.force_local, bs * h.nc,
+  VPHO_LAUNCH_PDL(k_force_anchors, dim3(bs * h.nc), dim3(256), 0, st, as, h.pverts, a.root_joint_flip, a.force_local, bs * h.nc,
               h.nc, h.ppoint, h.pforce);
   VPHO_LAUNCH_PDL(k_hand_phys_score, dim3(h.nc, bs), dim3(kScanThreads), 0, st, h);
   VPHO_LAUNCH_PDL(k_hand_phys_fuse<EL>, dim3(bs), dim3(160), 0, st, h);
@@ -901,7 +901,7 @@ extern "C" int vpho_force_anchors(vpho_assets_t h, const float* verts, const flo
   if (!h || n < 0 || group <= 0) return VPHO_ERR_INVALID;
   if (n == 0) return VPHO_OK;
   if (!verts || !force_local || !force_point || !force_global) return VPHO_ERR_INVALID;
-  VPHO_LAUNCH(k_force_anchors, dim3(n), dim3(128), 0, (cudaStream_t)stream, static_cast<AssetsHost*>(h)->dev, verts,
+  VPHO_LAUNCH(k_force_anchors, dim3(n), dim3(256), 0, (cudaStream_t)stream, static_cast<AssetsHost*>(h)->dev, verts,
               (const float*)nullptr, force_local, n, group, force_point, force_global);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;

@@ -138,10 +138,11 @@ __global__ void k_set_eval_time(SamplerWs ws, float t32) {
 // ------------------------------------------------------------------------------------------------------------
 // feat-term: F[r][col] = sum_k feat[r][k] Wa_f[k][col] + ba[col]       (once per sample(); R = images)
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kFtRows = 32, kFtCols = 128, kFtK = 32, kFtSplit = 4;
+constexpr int kFtRows = 32, kFtCols = 128, kFtK = 32, kFtSplit = 8;
 
-// split-K: blockIdx.z owns K slice [z*256, z*256+256) and writes its partial sums to Fpart[z]; k_feat_sum adds the four
-// partials in a fixed order plus the bias.  FP32 FMA accumulation throughout (the tensor-core variant accumulates with
+// split-K: blockIdx.z owns K slice [z*128, z*128+128) and writes its partial sums to Fpart[z]; k_feat_sum adds the eight
+// partials in a fixed order plus the bias (8 slices: the kernel is a chain of dependent global-load rounds, and 4 rounds
+// per CTA instead of 8 nearly halve its latency).  FP32 FMA accumulation throughout (the tensor-core variant accumulates with
 // truncation over a 384-instruction chain, which costs ~1 decimal digit on this K = 1024 contraction).
 __device__ __forceinline__ void feat_term_block(const DenoiserDev& dn, const float* __restrict__ feat, int R, float* __restrict__ Fpart,
                                                 int bx) {
@@ -193,16 +194,19 @@ __global__ void __launch_bounds__(256) k_feat_term(DenoiserDev dn0, const float*
 }
 
 __global__ void k_feat_sum(DenoiserDev dn, const float* __restrict__ Fpart, int R, float* __restrict__ F) {
+  static_assert(kFtSplit == 8, "the fixed summation tree below is written for 8 partials");
   const size_t n4 = (size_t)R * dn.hid / 4, stride = (size_t)R * dn.hid / 4;
   const float4* p = reinterpret_cast<const float4*>(Fpart);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 a = p[i], b = p[i + stride], c = p[i + 2 * stride], d = p[i + 3 * stride];
+    float4 q[kFtSplit];
+#pragma unroll
+    for (int z = 0; z < kFtSplit; ++z) q[z] = p[i + z * stride];
     const float4 bias = __ldg(reinterpret_cast<const float4*>(dn.ba) + (i % (dn.hid / 4)));
-    float4 o;
-    o.x = ((a.x + b.x) + (c.x + d.x)) + bias.x;
-    o.y = ((a.y + b.y) + (c.y + d.y)) + bias.y;
-    o.z = ((a.z + b.z) + (c.z + d.z)) + bias.z;
-    o.w = ((a.w + b.w) + (c.w + d.w)) + bias.w;
+    float4 o;          // fixed tree: ((p0 + p1) + (p2 + p3)) + ((p4 + p5) + (p6 + p7)), then the bias
+    o.x = (((q[0].x + q[1].x) + (q[2].x + q[3].x)) + ((q[4].x + q[5].x) + (q[6].x + q[7].x))) + bias.x;
+    o.y = (((q[0].y + q[1].y) + (q[2].y + q[3].y)) + ((q[4].y + q[5].y) + (q[6].y + q[7].y))) + bias.y;
+    o.z = (((q[0].z + q[1].z) + (q[2].z + q[3].z)) + ((q[4].z + q[5].z) + (q[6].z + q[7].z))) + bias.z;
+    o.w = (((q[0].w + q[1].w) + (q[2].w + q[3].w)) + ((q[4].w + q[5].w) + (q[6].w + q[7].w))) + bias.w;
     reinterpret_cast<float4*>(F)[i] = o;
   }
 }
@@ -753,7 +757,7 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t o_ctrl = take(sizeof(RkCtrl));
   const size_t o_F = take((size_t)R * hid * 4);
-  const size_t o_Fpart = take((size_t)4 * R * hid * 4);
+  const size_t o_Fpart = take((size_t)8 * R * hid * 4);      // kFtSplit partial sums
   const size_t o_Tt = take((size_t)hid * 4);
   const size_t o_P2T = take((size_t)kPDim * Npad * 4);
   const size_t o_P2hi = take((size_t)kPDim * Npad * 4);

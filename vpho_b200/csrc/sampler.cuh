@@ -85,7 +85,7 @@ struct RkCtrl {
 struct SamplerWs {
   RkCtrl* ctrl;
   float* F;        // [R][hid]  feat-term + bias, once per sample()
-  float* Fpart;    // [4][R][hid] split-K partial sums of the feat-term
+  float* Fpart;    // [8][R][hid] split-K partial sums of the feat-term
   float* Tt;       // [hid]     time-term of the current evaluation
   float* P2T;      // [256][Npad] pose features, k-major (FP32-SIMT head GEMM)
   float* P2hi;     // [Npad][256] pose features split for 3xTF32, row-major = K-major (tcgen05 head GEMM); nullptr = SIMT

@@ -763,7 +763,7 @@ template <int EL>
 static int run_hoi(const ManoModelDev& m, const AssetsDev& as, const HoiDev& h, cudaStream_t st) {
   const vpho_hoi_args& a = h.a;
   const int bs = a.bs, S = a.S;
-  constexpr int TC = 8;
+  constexpr int TC = 4;
   const size_t smem = sizeof(HandScoreSmem<TC>);
 #ifndef VPHO_EMU
   static bool attr_set = false;

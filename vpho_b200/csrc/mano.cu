@@ -130,7 +130,8 @@ static int launch_mano_forward(const ManoModelDev& m, const float* pose, const f
 int mano_forward_dev(const ManoModelDev& m, const float* pose, const float* shape, int pose_stride, int shape_stride,
                      int n, float* verts, float* joints, cudaStream_t stream) {
   if (n <= 0) return VPHO_OK;
-  if (n >= 148 * 8) return launch_mano_forward<16>(m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream);
+  if (n >= 148 * 32) return launch_mano_forward<16>(m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream);
+  if (n >= 148 * 4) return launch_mano_forward<8>(m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream);
   return launch_mano_forward<4>(m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream);
 }
 

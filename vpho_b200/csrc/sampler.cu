@@ -54,6 +54,8 @@ struct DenoiserHost {
   bool use_tc_pose = false;
   float* pe_planes = nullptr;
   TensorMapBlob mapW1_hi, mapW1_lo, mapW2_hi, mapW2_lo, mapX_hi, mapX_lo;
+  void* w2_half = nullptr;           // [2][256][256] __half (hi, lo) planes of pose_encoder.2 scaled by a power of two
+  TensorMapBlob mapW2h_hi, mapW2h_lo;
   // tcgen05 feat-term: K-major hi/lo planes of the conditioning slice of head.0 [hid][1024]
   bool use_tc_feat = false;
   float* wf_planes = nullptr;
@@ -882,7 +884,9 @@ static int launch_eval(SamplerJob* jobs, int n_jobs, int mode, int s, cudaStream
       }
       half = half && h16;
       pair = pair || (h16 && dh.dev.n_heads >= dh.pair_min_heads);
-      pj[j] = TcPoseJob{&dh.mapX_hi, &dh.mapX_lo, &dh.mapW1_hi, &dh.mapW1_lo, &dh.mapW2_hi, &dh.mapW2_lo, &dh.dev, &jobs[j].ws};
+      const bool g2h = dh.dev.W2scale_inv > 0.f;
+      pj[j] = TcPoseJob{&dh.mapX_hi, &dh.mapX_lo, &dh.mapW1_hi, &dh.mapW1_lo, g2h ? &dh.mapW2h_hi : &dh.mapW2_hi,
+                        g2h ? &dh.mapW2h_lo : &dh.mapW2_lo, &dh.dev, &jobs[j].ws};
     }
     for (int j = 0; j < n_jobs; ++j) {
       DenoiserHost& dh = *jobs[j].dh;
@@ -1018,7 +1022,7 @@ extern "C" int vpho_denoiser_create(int n_heads, const float* fourier_W, const f
   d.n_heads = n_heads; d.D = D; d.hid = hid;
   d.fourier_W = b + o_four; d.Wt = b + o_wt; d.bt = b + o_bt; d.W1 = b + o_w1; d.b1 = b + o_b1; d.W2 = b + o_w2;
   d.b2 = b + o_b2; d.Wa_t = b + o_wat; d.Wa_p = b + o_wap; d.Wa_f = b + o_waf; d.ba = b + o_ba; d.Wb = b + o_wb;
-  d.bb = b + o_bb; d.Wa_p_hi = nullptr; d.Wa_p_lo = nullptr; d.Wscale_inv = nullptr;
+  d.bb = b + o_bb; d.Wa_p_hi = nullptr; d.Wa_p_lo = nullptr; d.Wscale_inv = nullptr; d.W2scale_inv = 0.f;
 #ifndef VPHO_EMU
   // tcgen05 head GEMM (default).  VPHO_HEAD_GEMM=simt keeps the FP32-SIMT kernel (used to cross-check the two).
   const char* sel = getenv("VPHO_HEAD_GEMM");
@@ -1114,6 +1118,34 @@ extern "C" int vpho_denoiser_create(int n_heads, const float* fourier_W, const f
         d.Wscale_inv = reinterpret_cast<const float*>(static_cast<char*>(dh->w_half) + 2 * nw * sizeof(unsigned short));
         dh->use_f16 = true;
       }
+      // FP16 planes of the second pose-encoder layer (one power-of-two scale for the matrix): its GEMM is 72 % of the pose
+      // kernel's tensor work and runs at twice the TF32 rate on half the bytes (VPHO_POSE_GEMM2=tf32 keeps 3xTF32)
+      const char* selg = getenv("VPHO_POSE_GEMM2");
+      if (dh->use_f16 && !(selg && strcmp(selg, "tf32") == 0)) {
+        float mx = 0.f;
+        for (size_t i = 0; i < (size_t)256 * 256; ++i) mx = fmaxf(mx, fabsf(p2_w[i]));
+        float sc = 1.f, inv2 = 1.f;
+        if (mx > 0.f && mx < 3.0e38f) {
+          int e = 0;
+          frexpf(mx, &e);
+          sc = ldexpf(1.f, 14 - e);
+          inv2 = ldexpf(1.f, e - 14);
+        }
+        const size_t n2h = (size_t)256 * 256;
+        std::vector<unsigned short> w2(2 * n2h);
+        for (int o = 0; o < 256; ++o)
+          for (int k = 0; k < 256; ++k) {
+            const float w = p2_w[(size_t)o * 256 + k] * sc;
+            const __half h = __float2half_rn(w);
+            w2[(size_t)o * 256 + k] = __half_as_ushort(h);
+            w2[n2h + (size_t)o * 256 + k] = __half_as_ushort(__float2half_rn(w - __half2float(h)));
+          }
+        if (cudaMalloc(&dh->w2_half, w2.size() * sizeof(unsigned short)) == cudaSuccess &&
+            cudaMemcpy(dh->w2_half, w2.data(), w2.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) == cudaSuccess &&
+            tc_make_map(&dh->mapW2h_hi, dh->w2_half, 256, 256, 256, true) &&
+            tc_make_map(&dh->mapW2h_lo, static_cast<unsigned short*>(dh->w2_half) + n2h, 256, 256, 256, true))
+          d.W2scale_inv = inv2;
+      }
     }
     // feat-term on tensor cores is opt-in (VPHO_FEAT_TERM=tc): see the accuracy note at k_feat_term
     const char* self = getenv("VPHO_FEAT_TERM");
@@ -1147,6 +1179,7 @@ extern "C" int vpho_denoiser_destroy(vpho_denoiser_t h) {
   if (dh->w_hi) cudaFree(dh->w_hi);
   if (dh->w_lo) cudaFree(dh->w_lo);
   if (dh->pe_planes) cudaFree(dh->pe_planes);
+  if (dh->w2_half) cudaFree(dh->w2_half);
   if (dh->wf_planes) cudaFree(dh->wf_planes);
   if (dh->w_half) cudaFree(dh->w_half);
   delete dh;

@@ -35,6 +35,7 @@ struct DenoiserDev {
   const float* Wa_p_hi;    // [n_heads][256 n][256 k]  K-major, hi parts
   const float* Wa_p_lo;
   const float* Wscale_inv; // [n_heads] exact power-of-two un-scaling of the FP16 weight planes (3xFP16 head GEMM)
+  float W2scale_inv;       // > 0: the second pose-encoder GEMM runs on FP16 planes of W2 scaled by 1 / W2scale_inv (power of two)
 };
 
 enum StageMode : int {

@@ -615,6 +615,10 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = dn.D, nk1 = (D + kTcBK - 1) / kTcBK;
   const int r0 = tile * kTcBM;
+  // GEMM 2 on FP16 planes (dn.W2scale_inv > 0): 4 chunks of 64 k, kind::f16, H1 re-staged as (hi, lo) halves scaled per row;
+  // otherwise 8 chunks of 32 k, kind::tf32.  Either way a chunk is 128-byte rows: 16 KB per A plane, 32 KB per B plane.
+  const bool g2h = dn.W2scale_inv > 0.f;
+  const int nk2 = g2h ? 4 : 8, kel2 = g2h ? 64 : 32;
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -650,7 +654,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
         tma_load_2d(tmX_hi, &sm.x_full_bar, sm.a + (size_t)j * 2 * kTcABytes, j * kTcBK, r0);
         tma_load_2d(tmX_lo, &sm.x_full_bar, sm.a + (size_t)j * 2 * kTcABytes + kTcABytes, j * kTcBK, r0);
       }
-      for (int j = 0; j < nk1 + 8; ++j) {
+      for (int j = 0; j < nk1 + nk2; ++j) {
         mbar_wait(&sm.empty_bar[stage], phase ^ 1);
         clk_stamp(0, sc_++);
         mbar_arrive_expect_tx(&sm.full_bar[stage], kPtStageB);
@@ -658,8 +662,8 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
           tma_load_2d(tmW1_hi, &sm.full_bar[stage], sm.b[stage], j * kTcBK, 0);
           tma_load_2d(tmW1_lo, &sm.full_bar[stage], sm.b[stage] + kTcBBytes, j * kTcBK, 0);
         } else {
-          tma_load_2d(tmW2_hi, &sm.full_bar[stage], sm.b[stage], (j - nk1) * kTcBK, 0);
-          tma_load_2d(tmW2_lo, &sm.full_bar[stage], sm.b[stage] + kTcBBytes, (j - nk1) * kTcBK, 0);
+          tma_load_2d(tmW2_hi, &sm.full_bar[stage], sm.b[stage], (j - nk1) * kel2, 0);
+          tma_load_2d(tmW2_lo, &sm.full_bar[stage], sm.b[stage] + kTcBBytes, (j - nk1) * kel2, 0);
         }
         if (++stage == 2) { stage = 0; phase ^= 1; }
       }
@@ -692,7 +696,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
       }
       umma_commit(&sm.d1_full_bar);
       clk_stamp(1, sc_++);
-      for (int kc = 0; kc < 8; ++kc) {
+      for (int kc = 0; kc < nk2; ++kc) {
         const int ab = kc & 1;
         mbar_wait(&sm.full_bar[stage], phase);
         clk_stamp(1, sc_++);
@@ -700,6 +704,17 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
         clk_stamp(1, sc_++);
         tc_fence_after();
         const unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
+        if (g2h) {
+          const uint64_t a_hi = make_kmajor_sw128_desc(chunk), a_lo = make_kmajor_sw128_desc(chunk + kTcABytes);
+          const uint64_t b_hi = make_kmajor_sw128_desc(sm.b[stage]), b_lo = make_kmajor_sw128_desc(sm.b[stage] + kTcBBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                    // 4 x K16 inside the 128-byte row
+            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+            umma_f16(d2, a_lo + adv, b_hi + adv, kTcIdescF16, (kc == 0 && k == 0) ? 0u : 1u);
+            umma_f16(d2, a_hi + adv, b_lo + adv, kTcIdescF16, 1u);
+            umma_f16(d2, a_hi + adv, b_hi + adv, kTcIdescF16, 1u);
+          }
+        } else
         mma_chunk(d2, chunk, chunk + kTcABytes, kc == 0);
         umma_commit(&sm.empty_bar[stage]);
         umma_commit(&sm.a_empty_bar[ab]);
@@ -715,33 +730,93 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
     mbar_wait(&sm.d1_full_bar, 0);
     if (threadIdx.x == 128) clk_stamp(2, sc_++);
     tc_fence_after();
+    float d2_unscale = 1.f;                        // undoes the operand scaling of GEMM 2 (FP16 planes only)
+    if (g2h) {
+      // ---- re-stage relu(D1 + b1) as FP16 (hi, lo) planes: this thread owns 16 columns of each 64-column chunk.  The 64
+      // activations stay in registers between the row-maximum exchange (power-of-two row scale, peak in [2^13, 2^14)) and
+      // the split, as in the epilogue below.
+      float hv[64];
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        uint32_t v[16];
+        tmem_ld16(d1 + lane_addr + (uint32_t)(kc * 64 + cs * 16), v);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 64 + cs * 16 + j4 * 4));
+          hv[kc * 16 + j4 * 4 + 0] = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + bv.x, 0.f);
+          hv[kc * 16 + j4 * 4 + 1] = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + bv.y, 0.f);
+          hv[kc * 16 + j4 * 4 + 2] = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + bv.z, 0.f);
+          hv[kc * 16 + j4 * 4 + 3] = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + bv.w, 0.f);
+        }
+      }
+      float rmax = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) rmax = fmaxf(rmax, hv[j]);
+      float* rowmax = reinterpret_cast<float*>(sm.a + 2 * 2 * kTcABytes);      // third X chunk: free once D1 is complete
+      rowmax[cs * kTcBM + r] = rmax;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      rmax = fmaxf(fmaxf(rowmax[r], rowmax[kTcBM + r]), fmaxf(rowmax[2 * kTcBM + r], rowmax[3 * kTcBM + r]));
+      float sc = 1.f, inv = 1.f;
+      if (rmax > 0.f && rmax < 3.0e38f) {
+        int ex = 0;
+        frexpf(rmax, &ex);
+        sc = ldexpf(1.f, 14 - ex);
+        inv = ldexpf(1.f, ex - 14);
+      }
+      d2_unscale = inv * dn.W2scale_inv;
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        const int ab = kc & 1;
+        mbar_wait(&sm.a_empty_bar[ab], (uint32_t)(((kc >> 1) & 1) ^ 1));
+        unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
+#pragma unroll
+        for (int u2 = 0; u2 < 2; ++u2) {
+          __align__(16) __half hi8[8], lo8[8];
+#pragma unroll
+          for (int ee = 0; ee < 8; ++ee) {
+            const float x = hv[kc * 16 + u2 * 8 + ee] * sc;
+            const __half h = __float2half_rn(x);
+            hi8[ee] = h;
+            lo8[ee] = __float2half_rn(x - __half2float(h));
+          }
+          const int u = cs * 2 + u2;                     // 16-byte unit (8 halves) inside the 128-byte row
+          const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((u ^ (r & 7)) & 7) << 4));
+          *reinterpret_cast<uint4*>(chunk + off) = *reinterpret_cast<const uint4*>(hi8);
+          *reinterpret_cast<uint4*>(chunk + kTcABytes + off) = *reinterpret_cast<const uint4*>(lo8);
+        }
+        fence_proxy_async();
+        mbar_arrive(&sm.a_full_bar[ab]);
+        if (threadIdx.x == 128) clk_stamp(2, sc_++);
+      }
+    } else {
     // ---- re-stage relu(D1 + b1) as the A operand of GEMM 2: 8 columns of each 32-column chunk per thread
-    for (int kc = 0; kc < 8; ++kc) {
-      const int ab = kc & 1;
-      mbar_wait(&sm.a_empty_bar[ab], (uint32_t)(((kc >> 1) & 1) ^ 1));
-      uint32_t v[8];
-      tmem_ld8(d1 + lane_addr + (uint32_t)(kc * 32 + cs * 8), v);
-      unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
-      const float4 ba = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 32 + cs * 8));
-      const float4 bb4 = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 32 + cs * 8 + 4));
-      const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb4.x, bb4.y, bb4.z, bb4.w};
-      float hi[8], lo[8];
+      for (int kc = 0; kc < 8; ++kc) {
+        const int ab = kc & 1;
+        mbar_wait(&sm.a_empty_bar[ab], (uint32_t)(((kc >> 1) & 1) ^ 1));
+        uint32_t v[8];
+        tmem_ld8(d1 + lane_addr + (uint32_t)(kc * 32 + cs * 8), v);
+        unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
+        const float4 ba = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 32 + cs * 8));
+        const float4 bb4 = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 32 + cs * 8 + 4));
+        const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb4.x, bb4.y, bb4.z, bb4.w};
+        float hi[8], lo[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float hv = fmaxf(__uint_as_float(v[j]) + bias[j], 0.f);
-        hi[j] = tf32_rna(hv);
-        lo[j] = tf32_rna(hv - hi[j]);
-      }
+        for (int j = 0; j < 8; ++j) {
+          const float hv = fmaxf(__uint_as_float(v[j]) + bias[j], 0.f);
+          hi[j] = tf32_rna(hv);
+          lo[j] = tf32_rna(hv - hi[j]);
+        }
 #pragma unroll
-      for (int u2 = 0; u2 < 2; ++u2) {
-        const int u = cs * 2 + u2;                       // 16-byte unit inside the 128-byte row
-        const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((u ^ (r & 7)) & 7) << 4));
-        *reinterpret_cast<float4*>(chunk + off) = make_float4(hi[u2 * 4 + 0], hi[u2 * 4 + 1], hi[u2 * 4 + 2], hi[u2 * 4 + 3]);
-        *reinterpret_cast<float4*>(chunk + kTcABytes + off) = make_float4(lo[u2 * 4 + 0], lo[u2 * 4 + 1], lo[u2 * 4 + 2], lo[u2 * 4 + 3]);
+        for (int u2 = 0; u2 < 2; ++u2) {
+          const int u = cs * 2 + u2;                       // 16-byte unit inside the 128-byte row
+          const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((u ^ (r & 7)) & 7) << 4));
+          *reinterpret_cast<float4*>(chunk + off) = make_float4(hi[u2 * 4 + 0], hi[u2 * 4 + 1], hi[u2 * 4 + 2], hi[u2 * 4 + 3]);
+          *reinterpret_cast<float4*>(chunk + kTcABytes + off) = make_float4(lo[u2 * 4 + 0], lo[u2 * 4 + 1], lo[u2 * 4 + 2], lo[u2 * 4 + 3]);
+        }
+        fence_proxy_async();
+        mbar_arrive(&sm.a_full_bar[ab]);
+        if (threadIdx.x == 128) clk_stamp(2, sc_++);
       }
-      fence_proxy_async();
-      mbar_arrive(&sm.a_full_bar[ab]);
-      if (threadIdx.x == 128) clk_stamp(2, sc_++);
     }
     // ---- epilogue: relu(D2 + b2) -> operand planes of the head GEMM, 64 columns per thread, ONE pass over TMEM: the
     // 64 activations stay in registers between the row-maximum exchange and the split
@@ -759,14 +834,14 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
       for (int j4 = 0; j4 < 8; ++j4) {
         const float4 ba = __ldg(reinterpret_cast<const float4*>(dn.b2 + c0 + j4 * 4));
         const float4 bb4 = __ldg(reinterpret_cast<const float4*>(dn.b2 + c0 + 32 + j4 * 4));
-        pv[j4 * 4 + 0] = fmaxf(__uint_as_float(v0[j4 * 4 + 0]) + ba.x, 0.f);
-        pv[j4 * 4 + 1] = fmaxf(__uint_as_float(v0[j4 * 4 + 1]) + ba.y, 0.f);
-        pv[j4 * 4 + 2] = fmaxf(__uint_as_float(v0[j4 * 4 + 2]) + ba.z, 0.f);
-        pv[j4 * 4 + 3] = fmaxf(__uint_as_float(v0[j4 * 4 + 3]) + ba.w, 0.f);
-        pv[32 + j4 * 4 + 0] = fmaxf(__uint_as_float(v1[j4 * 4 + 0]) + bb4.x, 0.f);
-        pv[32 + j4 * 4 + 1] = fmaxf(__uint_as_float(v1[j4 * 4 + 1]) + bb4.y, 0.f);
-        pv[32 + j4 * 4 + 2] = fmaxf(__uint_as_float(v1[j4 * 4 + 2]) + bb4.z, 0.f);
-        pv[32 + j4 * 4 + 3] = fmaxf(__uint_as_float(v1[j4 * 4 + 3]) + bb4.w, 0.f);
+        pv[j4 * 4 + 0] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 0]), d2_unscale, ba.x), 0.f);
+        pv[j4 * 4 + 1] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 1]), d2_unscale, ba.y), 0.f);
+        pv[j4 * 4 + 2] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 2]), d2_unscale, ba.z), 0.f);
+        pv[j4 * 4 + 3] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 3]), d2_unscale, ba.w), 0.f);
+        pv[32 + j4 * 4 + 0] = fmaxf(fmaf(__uint_as_float(v1[j4 * 4 + 0]), d2_unscale, bb4.x), 0.f);
+        pv[32 + j4 * 4 + 1] = fmaxf(fmaf(__uint_as_float(v1[j4 * 4 + 1]), d2_unscale, bb4.y), 0.f);
+        pv[32 + j4 * 4 + 2] = fmaxf(fmaf(__uint_as_float(v1[j4 * 4 + 2]), d2_unscale, bb4.z), 0.f);
+        pv[32 + j4 * 4 + 3] = fmaxf(fmaf(__uint_as_float(v1[j4 * 4 + 3]), d2_unscale, bb4.w), 0.f);
       }
     }
     if (ws.P2scale) {

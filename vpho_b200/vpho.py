@@ -72,7 +72,7 @@ class VphoHotPath:
 
     @torch.no_grad()
     def predict(self, batch: Dict, *, prior_hand: Optional[torch.Tensor] = None, prior_obj: Optional[torch.Tensor] = None,
-                with_inprocess: bool = True) -> Dict:
+                with_inprocess: bool = True, prefetch=None) -> Dict:
         """The whole batch is enqueued without a host synchronisation; the two samplers' status words are read once at
         the end.  If an integration needed more RK attempts than were enqueued (the hint adapts to the previous batch,
         plus one spare), the batch is re-issued with a larger budget -- rare, and the results are identical."""
@@ -87,6 +87,11 @@ class VphoHotPath:
         self.score_agent.spare_attempt = True
         for _ in range(8):
             pd, pend = self._predict_once(batch, prior_hand, prior_obj, with_inprocess)
+            if prefetch is not None:
+                # caller hook, run once after the batch is enqueued and before the host blocks on its status: the place
+                # to issue the next batch's host-to-device copies on another stream
+                prefetch()
+                prefetch = None
             status = torch.stack([p.counters for p in pend]).cpu().tolist()     # the one host sync of the batch
             ok = [p.resolve(c) for p, c in zip(pend, status)]
             self.last_info = {"hand": pend[0].info, "obj": pend[1].info}

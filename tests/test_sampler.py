@@ -223,3 +223,32 @@ def test_sampler_cuda_pair_is_bit_identical_to_separate_samplers(cuda_lib, bs_a,
         assert pend_a.info[k] == info_a[k] and pend_b.info[k] == info_b[k]
     assert torch.equal(y_a, x_a) and torch.equal(y_b, x_b)
     assert torch.equal(ys_a, xs_a) and torch.equal(ys_b, xs_b)
+
+
+def test_sampler_emulated_pair_matches_separate_and_tolerates_an_empty_job(emu_lib):
+    """host logic of `vpho_sample_pair_*` on the CPU emulator (the error-norm / post-step kernels serve both jobs there
+    too): bit-identical to separate samplers; a job without rows drops out"""
+    S = 5
+    den_a, _, enc_a, _, g = _setup("obj", emu_lib, 2, S, 0.05, seed=3)
+    den_b, _, enc_b, _, _ = _setup("obj", emu_lib, 1, S, 0.5, seed=4)
+    agent = ScoreBasedModelAgent(sampling_steps=6, sample_num=S)
+    pa = torch.randn(2 * S, den_a.out_dim, generator=g) * ve_prior_std(0.65)
+    pb = torch.randn(1 * S, den_b.out_dim, generator=g) * ve_prior_std(0.65)
+    da, db = {"feat_unique": enc_a, "n_rows": 2 * S}, {"feat_unique": enc_b, "n_rows": S}
+    xs_a, x_a = agent.sample(da, den_a, 0.65, prior=pa)
+    xs_b, x_b = agent.sample(db, den_b, 0.65, prior=pb)
+    for _ in range(8):
+        (ys_a, y_a, pend_a), (ys_b, y_b, pend_b) = agent.sample_pair(da, den_a, db, den_b, 0.65, prior_a=pa, prior_b=pb)
+        if all([pend_a.resolve(), pend_b.resolve()]):
+            break
+    else:
+        raise AssertionError("pair sampler did not converge")
+    assert torch.equal(y_a, x_a) and torch.equal(y_b, x_b) and torch.equal(ys_a, xs_a) and torch.equal(ys_b, xs_b)
+    # second job empty
+    empty = {"feat_unique": enc_b[:0], "n_rows": 0}
+    for _ in range(8):
+        (zs_a, z_a, pend_a), (zs_e, z_e, pend_e) = agent.sample_pair(da, den_a, empty, den_b, 0.65, prior_a=pa,
+                                                                     prior_b=pb[:0])
+        if all([pend_a.resolve(), pend_e.resolve()]):
+            break
+    assert torch.equal(z_a, x_a) and z_e.shape == (0, den_b.out_dim)

@@ -228,7 +228,7 @@ __device__ __forceinline__ void time_term_block(const DenoiserDev& dn, const Sam
   const float t32 = (float)eval_t64(c, mode, s);
   if (block == 0 && tid == 255) {
     const EvalTime et = eval_time(c, mode, s);
-    ws.ctrl->et = et;                                                      // read by the head GEMM of this call
+    ws.ctrl->et[tt_slot(mode, s)] = et;                                    // read by the head GEMM of that call
     if (mode == kModeInit0 || mode == kModeInit1 || mode == kModeStage) ws.ctrl->kcoef[k_slot_of(mode, s)] = et.coef;
   }
   if (tid < 64) {
@@ -259,7 +259,8 @@ __device__ __forceinline__ void time_term_block(const DenoiserDev& dn, const Sam
   }
   part[g][cl] = a;
   __syncthreads();
-  if (tid < kTtCols && col < dn.hid) ws.Tt[col] = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+  if (tid < kTtCols && col < dn.hid)
+    ws.Tt[(size_t)tt_slot(mode, s) * dn.hid + col] = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
 }
 
 __global__ void __launch_bounds__(256) k_time_term(DenoiserDev dn, SamplerWs ws, int mode, int s) {
@@ -274,7 +275,15 @@ __device__ __forceinline__ void stage_x_block(const DenoiserDev& dn, const Sampl
                                               int n_blocks) {
   const RkCtrl& c = *ws.ctrl;
   if (!eval_active(c, mode)) return;
-  if (bid < nb_time) { time_term_block(dn, ws, c, mode, s, bid); return; }
+  if (bid < nb_time) {
+    // The times of all six stages of an RK attempt are known once the attempt has begun (t + c_s h), so the first stage's
+    // launch computes all six time terms (six groups of column blocks) and stages 2..6 launch none: their critical path
+    // is the stage input alone.
+    const int per = (dn.hid + kTtCols - 1) / kTtCols;
+    if (mode == kModeStage) time_term_block(dn, ws, c, mode, 1 + bid / per, bid % per);
+    else time_term_block(dn, ws, c, mode, s, bid);
+    return;
+  }
   const int D = dn.D, Kx = ws.Kx;
   const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
   const int total = ws.Npad * Kx;
@@ -409,7 +418,7 @@ __global__ void __launch_bounds__(256) k_head_simt(DenoiserDev dn, SamplerWs ws,
   const int hid = dn.hid, Npad = ws.Npad;
   const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
   const int rpf = (mode == kModeEval) ? ws.eval_rpf : c.rows_per_feat;
-  const EvalTime et = c.et;
+  const EvalTime et = c.et[tt_slot(mode, s)];
 
   int rows[8];
 #pragma unroll
@@ -461,7 +470,7 @@ __global__ void __launch_bounds__(256) k_head_simt(DenoiserDev dn, SamplerWs ws,
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
       const int cb = c0 + jj * 64 + 4 * tx;
-      const float4 tt = *reinterpret_cast<const float4*>(ws.Tt + cb);
+      const float4 tt = *reinterpret_cast<const float4*>(ws.Tt + (size_t)tt_slot(mode, s) * dn.hid + cb);
       const float tta[4] = {tt.x, tt.y, tt.z, tt.w};
       float4 wb[4];
 #pragma unroll
@@ -760,7 +769,7 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
   const size_t o_ctrl = take(sizeof(RkCtrl));
   const size_t o_F = take((size_t)R * hid * 4);
   const size_t o_Fpart = take((size_t)8 * R * hid * 4);      // kFtSplit partial sums
-  const size_t o_Tt = take((size_t)hid * 4);
+  const size_t o_Tt = take((size_t)7 * hid * 4);
   const size_t o_P2T = take((size_t)kPDim * Npad * 4);
   const size_t o_P2hi = take((size_t)kPDim * Npad * 4);
   const size_t o_P2lo = take((size_t)kPDim * Npad * 4);
@@ -834,8 +843,9 @@ static int launch_feat_term(DenoiserHost& dh, const SamplerWs& ws, const float* 
 // One sampler's state on the host side of a launch; two of them advance in lock-step through the same kernel launches.
 struct SamplerJob { DenoiserHost* dh; SamplerWs ws; int ws_n; /* n_rows * D */ };
 
-static int stage_x_blocks(const DenoiserDev& dn, const SamplerWs& ws, int* nb_time) {
-  *nb_time = (dn.hid + kTtCols - 1) / kTtCols;
+static int stage_x_blocks(const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, int* nb_time) {
+  const int per = (dn.hid + kTtCols - 1) / kTtCols;
+  *nb_time = mode == kModeStage ? (s == 1 ? 6 * per : 0) : per;      // see stage_x_block
   int nb_x = (ws.Npad * ws.Kx + 1023) / 1024;           // ~4 elements per thread
   if (nb_x > 592) nb_x = 592;
   return *nb_time + nb_x;
@@ -859,7 +869,8 @@ static int launch_eval(SamplerJob* jobs, int n_jobs, int mode, int s, cudaStream
     SamplerJob& j1 = jobs[n_jobs - 1];
     profile_begin(VPHO_TAG_POSE_ENCODER, st);
     int nbt0 = 0, nbt1 = 0;
-    const int b0 = stage_x_blocks(j0.dh->dev, j0.ws, &nbt0), b1 = n_jobs > 1 ? stage_x_blocks(j1.dh->dev, j1.ws, &nbt1) : 0;
+    const int b0 = stage_x_blocks(j0.dh->dev, j0.ws, mode, s, &nbt0),
+              b1 = n_jobs > 1 ? stage_x_blocks(j1.dh->dev, j1.ws, mode, s, &nbt1) : 0;
     profile_begin(VPHO_TAG_STAGE_X, st);
     VPHO_LAUNCH_PDL(k_stage_x, dim3(b0 + b1), dim3(256), 0, st, j0.dh->dev, j0.ws, j1.dh->dev, j1.ws, b0, mode, s, nbt0, nbt1);
     profile_end(VPHO_TAG_STAGE_X, st);

@@ -76,7 +76,8 @@ struct RkCtrl {
   double kcoef[8];  // K slot s holds raw float32 scores; its float64 value is -(kcoef[s] * score)  (kval)
   unsigned int block_counter;
   float eval_t32;   // vpho_score_eval: the time of a stand-alone evaluation
-  EvalTime et;      // scalars of the network call in flight, written by its first kernel (time-term block 0)
+  EvalTime et[8];   // scalars of a network call, by time-term slot (tt_slot): RK stage s uses slot s, every other mode slot 0;
+                    // an attempt's six slots are filled together by the first stage's kernel
   // caller-owned outputs of the running sample()
   double* xs;       // [n_eval][N][D] or nullptr
   double* x_out;    // [N][D]
@@ -87,7 +88,7 @@ struct SamplerWs {
   RkCtrl* ctrl;
   float* F;        // [R][hid]  feat-term + bias, once per sample()
   float* Fpart;    // [8][R][hid] split-K partial sums of the feat-term
-  float* Tt;       // [hid]     time-term of the current evaluation
+  float* Tt;       // [7][hid]  time-term by slot (tt_slot): the six stages of an RK attempt are computed together
   float* P2T;      // [256][Npad] pose features, k-major (FP32-SIMT head GEMM)
   float* P2hi;     // [Npad][256] pose features split for 3xTF32, row-major = K-major (tcgen05 head GEMM); nullptr = SIMT
   float* P2lo;

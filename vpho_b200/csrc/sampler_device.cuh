@@ -76,6 +76,8 @@ __device__ __forceinline__ double kval(const float* K, const RkCtrl& c, int slot
   if (c.nan_stage[slot] && !isfinite(v)) v = 0.0;
   return v;
 }
+// time-term / EvalTime slot of a network call: the stage index inside an RK attempt, 0 for the other modes
+__device__ __forceinline__ int tt_slot(int mode, int s) { return mode == kModeStage ? s : 0; }
 __device__ __forceinline__ int k_slot_of(int mode, int s) { return (mode == kModeInit0) ? 0 : (mode == kModeInit1 ? 1 : s); }
 
 __device__ __forceinline__ bool eval_active(const RkCtrl& c, int mode) {

@@ -423,7 +423,7 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     // `seq0`: position of this job's first item in the CTA's item sequence (group g takes the positions of parity g)
     auto drain = [&](const DenoiserDev& dn, const SamplerWs& ws, int n_slots, int n_items, int first, int seq0) {
       RkCtrl& c = *ws.ctrl;
-      const EvalTime et = c.et;               // written by the time-term block of this network call
+      const EvalTime et = c.et[tt_slot(mode, s)];          // written by the time-term block of this call (or of the attempt's first)
       const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
       const int rpf = (mode == kModeEval) ? ws.eval_rpf : c.rows_per_feat;
       auto item_geometry = [&](int it, int& tile, int& head, int& img0, int& n_img) {
@@ -438,7 +438,7 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         int tile, head, img0, n_img;
         item_geometry(it, tile, head, img0, n_img);
         const int col = head * kHeadHid + tg;
-        k.tt = ws.Tt[col];
+        k.tt = ws.Tt[(size_t)tt_slot(mode, s) * dn.hid + col];
         k.wb = __ldg(reinterpret_cast<const float4*>(dn.Wb + (size_t)col * 4));
 #pragma unroll
         for (int i = 0; i < kTcFtImgs; ++i) k.f[i] = (n_img <= kTcFtImgs && i < n_img) ? ws.F[(size_t)(img0 + i) * dn.hid + col] : 0.f;

@@ -546,7 +546,7 @@ __device__ void begin_attempt(RkCtrl& c, bool new_step) {
   c.t_new = t_new;
 }
 
-__device__ void controller(const SamplerWs& ws, RkCtrl& c, int kind, double s0, double s1) {
+__device__ void controller(const SamplerWs& ws, RkCtrl& c, int kind, double s0, double s1, int te_count) {
   const double sqrt_n = sqrt((double)c.n);     // x.size ** 0.5
   if (kind == kRedInit0) {
     c.nfev = 1;
@@ -576,8 +576,10 @@ __device__ void controller(const SamplerWs& ws, RkCtrl& c, int kind, double s0, 
       c.t = c.t_new;
       c.n_acc += 1;
       c.accepted_now = 1;
-      int hi = c.te_next;
-      while (hi < c.n_eval && ws.t_eval[hi] >= c.t) ++hi;      // ivp.py: searchsorted(side='left') on reversed t_eval
+      // ivp.py: searchsorted(side='left') on reversed t_eval.  `te_count` = number of output times from te_next on that are
+      // >= t_new, counted by the whole block beforehand (t_eval is sorted): a serial scan here is a chain of up to 17
+      // dependent global loads per accepted step
+      int hi = c.te_next + te_count;
       c.te_lo = c.te_next; c.te_hi = hi; c.te_next = hi;
       if (c.direction * (c.t - c.eps) >= 0) c.status = 1;
       else begin_attempt(c, true);
@@ -645,9 +647,19 @@ __device__ __forceinline__ void reduce_block(const SamplerWs& ws, int kind, int 
       if (tid < st) { sh0[tid] += sh0[tid + st]; sh1[tid] += sh1[tid + st]; }
       __syncthreads();
     }
+    // output times inside the step that is about to be judged (used only if it is accepted)
+    __shared__ int s_cnt;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    if (kind == kRedErr) {
+      int mine = 0;
+      for (int e = c.te_next + tid; e < c.n_eval; e += 256) mine += (ws.t_eval[e] >= c.t_new) ? 1 : 0;
+      if (mine) atomicAdd(&s_cnt, mine);
+    }
+    __syncthreads();
     if (tid == 0) {
       c.block_counter = 0u;
-      controller(ws, c, kind, sh0[0], sh1[0]);
+      controller(ws, c, kind, sh0[0], sh1[0], s_cnt);
     }
   }
 }

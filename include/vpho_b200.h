@@ -112,6 +112,8 @@ typedef struct {
   int32_t* counters;       /* [8] status word */
   void* workspace;
   size_t workspace_bytes;
+  float* xs_f32;           /* optional [n_eval][n_rows][D]: the dense output rounded to float32, i.e. what the predict branch keeps
+                            * of it (`.float()`, lib/model/VPHO.py:243); `xs` may then be NULL and no float64 copy is written */
 } vpho_sample_args;
 int vpho_sample_pair_begin(const vpho_sample_args* a, const vpho_sample_args* b, int max_attempts, void* stream);
 int vpho_sample_pair_continue(const vpho_sample_args* a, const vpho_sample_args* b, int max_attempts, void* stream);
@@ -127,6 +129,9 @@ int vpho_rot6d_to_axis_angle(const float* x6d, int n_rot, float* aa, void* strea
  * `.float()`) + the 10 regressed shape coefficients of the row's image (shape [n_rows / rows_per_shape][10]). */
 int vpho_postprocess_hand(const double* xs, int n_steps, int n_rows, int rows_per_shape, const float* shape, float* out,
                           void* stream);
+/* Same for a float32 trajectory (vpho_sample_args.xs_f32). */
+int vpho_postprocess_hand_f32(const float* xs, int n_steps, int n_rows, int rows_per_shape, const float* shape, float* out,
+                              void* stream);
 
 /* ---------------------------------------------------------------------------------- assets / aggregation ---- */
 /* Force-anchor tables (lib/utils/physics_fn.py:121-257, lib/utils/hand_fn.py:427-448) and per-object point tables

@@ -61,5 +61,9 @@ def test_postprocess_matches_composed_path(cuda_lib):
     lib.check(lib.c.vpho_rot6d_to_axis_angle(capi.ptr(x32), T * n * 16, capi.ptr(aa), capi.stream_of(x32)), "aa")
     comp = torch.cat((aa.reshape(T, n, 48).permute(1, 0, 2), shape.repeat_interleave(4, 0)[:, None].expand(n, T, 10)), -1)
     assert torch.equal(out, comp)
+    # float32 trajectory in: same result as the float64 one after `.float()`
+    out32 = torch.empty_like(out)
+    lib.check(lib.c.vpho_postprocess_hand_f32(capi.ptr(x32), T, n, 4, capi.ptr(shape), capi.ptr(out32), capi.stream_of(x32)), "pp32")
+    assert torch.equal(out32, out)
     # empty inputs are accepted
     lib.check(lib.c.vpho_postprocess_hand(None, 0, 0, 4, None, None, None), "empty")

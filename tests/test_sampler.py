@@ -223,6 +223,13 @@ def test_sampler_cuda_pair_is_bit_identical_to_separate_samplers(cuda_lib, bs_a,
         assert pend_a.info[k] == info_a[k] and pend_b.info[k] == info_b[k]
     assert torch.equal(y_a, x_a) and torch.equal(y_b, x_b)
     assert torch.equal(ys_a, xs_a) and torch.equal(ys_b, xs_b)
+    for _ in range(8):
+        (fs_a, f_a, pend_a), (fs_b, f_b, pend_b) = agent.sample_pair(da, den_a, db, den_b, 0.65, prior_a=pa, prior_b=pb,
+                                                                     inprocess_float32=(True, False))
+        torch.cuda.synchronize()
+        if all([pend_a.resolve(), pend_b.resolve()]):
+            break
+    assert fs_a.dtype == torch.float32 and torch.equal(fs_a, xs_a.float()) and torch.equal(fs_b, xs_b) and torch.equal(f_a, x_a)
 
 
 def test_sampler_emulated_pair_matches_separate_and_tolerates_an_empty_job(emu_lib):
@@ -244,6 +251,13 @@ def test_sampler_emulated_pair_matches_separate_and_tolerates_an_empty_job(emu_l
     else:
         raise AssertionError("pair sampler did not converge")
     assert torch.equal(y_a, x_a) and torch.equal(y_b, x_b) and torch.equal(ys_a, xs_a) and torch.equal(ys_b, xs_b)
+    # float32 trajectory of one job (`vpho_sample_args.xs_f32`): exactly `.float()` of the float64 one
+    for _ in range(8):
+        (fs_a, f_a, pend_a), (fs_b, f_b, pend_b) = agent.sample_pair(da, den_a, db, den_b, 0.65, prior_a=pa, prior_b=pb,
+                                                                     inprocess_float32=(True, False))
+        if all([pend_a.resolve(), pend_b.resolve()]):
+            break
+    assert fs_a.dtype == torch.float32 and torch.equal(fs_a, xs_a.float()) and torch.equal(fs_b, xs_b) and torch.equal(f_a, x_a)
     # second job empty
     empty = {"feat_unique": enc_b[:0], "n_rows": 0}
     for _ in range(8):

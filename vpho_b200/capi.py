@@ -25,6 +25,7 @@ class SampleArgs(C.Structure):
         ("T0", c_double), ("eps", c_double), ("t_eval", c_void_p), ("n_eval", c_int),
         ("rtol", c_double), ("atol", c_double), ("max_step", c_double), ("num_steps", c_int),
         ("xs", c_void_p), ("x", c_void_p), ("counters", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("xs_f32", c_void_p),
     ]
 
 
@@ -69,6 +70,7 @@ _SIGNATURES = {
     "vpho_sample_pair_finish": (c_int, [c_void_p, c_void_p, c_void_p]),
     "vpho_rot6d_to_axis_angle": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "vpho_postprocess_hand": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "vpho_postprocess_hand_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vpho_assets_create": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                    C.POINTER(c_void_p)]),
     "vpho_assets_destroy": (c_int, [c_void_p]),

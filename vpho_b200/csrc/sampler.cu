@@ -88,6 +88,7 @@ struct SampleCfg {
   int n_rows, D, n_eval, num_steps, rows_per_feat;
   const double* t_eval_in;   // device pointer or nullptr (= numpy.linspace(T0, eps, n_eval))
   double* xs;
+  float* xs32;
   double* x_out;
   int32_t* counters;
 };
@@ -120,7 +121,7 @@ __global__ void k_init_ctrl(SampleCfg cfg, SamplerWs ws) {
     for (int k = 0; k < 8; ++k) c.nan_stage[k] = 0;
     c.block_counter = 0u;
     c.eval_t32 = 0.f;
-    c.xs = cfg.xs; c.x_out = cfg.x_out; c.counters = cfg.counters;
+    c.xs = cfg.xs; c.xs32 = cfg.xs32; c.x_out = cfg.x_out; c.counters = cfg.counters;
     if (c.counters) for (int k = 0; k < 8; ++k) c.counters[k] = 0;
   }
 }
@@ -680,7 +681,7 @@ __device__ __forceinline__ void post_step_block(const SamplerWs& ws, int bid, in
   const double h = c.h_done, t_old = c.t_old;
   for (int i = bid * 256 + threadIdx.x; i < n; i += n_blocks * 256) {
     const double y_old = ws.y[i];
-    if (c.xs && hi > lo) {
+    if ((c.xs || c.xs32) && hi > lo) {
       double Q[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int j = 0; j < 7; ++j) {
@@ -692,7 +693,9 @@ __device__ __forceinline__ void post_step_block(const SamplerWs& ws, int bid, in
         const double x = (ws.t_eval[e] - t_old) / h;
         const double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x;      // np.cumprod
         const double dot = ((Q[0] * p1 + Q[1] * p2) + Q[2] * p3) + Q[3] * p4;
-        c.xs[(size_t)e * n + i] = __dadd_rn(__dmul_rn(h, dot), y_old);
+        const double v = __dadd_rn(__dmul_rn(h, dot), y_old);
+        if (c.xs) c.xs[(size_t)e * n + i] = v;
+        if (c.xs32) c.xs32[(size_t)e * n + i] = (float)v;          // the `.float()` the predict branch applies (VPHO.py:243)
       }
     }
     ws.y[i] = ws.ynew[i];
@@ -741,7 +744,8 @@ __global__ void k_rot6d_to_aa(const float* __restrict__ x6d, int n, float* __res
 // -> float32 MANO vectors [n_rows][n_steps][58] = axis-angle of the 16 joints (the float64 -> float32 rounding of
 // `.float()`, then the same 6D -> matrix -> axis-angle arithmetic as k_rot6d_to_aa) followed by the image's 10 shape
 // coefficients.  One thread per (step, row, slot): slots 0..15 are joints, slot 16 copies the shape.
-__global__ void __launch_bounds__(256) k_postprocess_hand(const double* __restrict__ xs, int n_steps, int n_rows, int rows_per_shape,
+template <typename TIn>
+__global__ void __launch_bounds__(256) k_postprocess_hand(const TIn* __restrict__ xs, int n_steps, int n_rows, int rows_per_shape,
                                                          const float* __restrict__ shape, float* __restrict__ out) {
   const size_t total = (size_t)n_steps * n_rows * 17;
   for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (size_t)gridDim.x * blockDim.x) {
@@ -750,7 +754,7 @@ __global__ void __launch_bounds__(256) k_postprocess_hand(const double* __restri
     const int row = (int)(sr % n_rows), step = (int)(sr / n_rows);
     float* dst = out + ((size_t)row * n_steps + step) * 58;
     if (slot < 16) {
-      const double* src = xs + sr * 96 + slot * 6;
+      const TIn* src = xs + sr * 96 + slot * 6;
       float d[6], R[9], a[3];
 #pragma unroll
       for (int k = 0; k < 6; ++k) d[k] = (float)src[k];
@@ -1256,7 +1260,7 @@ static int prepare_job(const vpho_sample_args* a, bool begin, SamplerJob* job, c
     return VPHO_ERR_INVALID;
   if (!begin) return VPHO_OK;
   SampleCfg cfg{a->T0, a->eps, a->rtol, a->atol, a->max_step, a->n_rows, dn.D, a->n_eval, a->num_steps, a->rows_per_feat, a->t_eval,
-                a->xs, a->x, a->counters};
+                a->xs, a->xs_f32, a->x, a->counters};
   VPHO_LAUNCH(k_init_ctrl, dim3(1), dim3(64), 0, st, cfg, job->ws);
   VPHO_CHECK_LAUNCH();
   if (a->n_rows == 0) return VPHO_OK;
@@ -1343,7 +1347,7 @@ extern "C" int vpho_sample_begin(vpho_denoiser_t h, const float* feat, int n_row
                                  double* xs, double* x, int32_t* counters, void* workspace, size_t workspace_bytes,
                                  void* stream) {
   const vpho_sample_args a{h, feat, n_rows, rows_per_feat, init_x, T0, eps, t_eval, n_eval, rtol, atol, max_step, num_steps,
-                           xs, x, counters, workspace, workspace_bytes};
+                           xs, x, counters, workspace, workspace_bytes, nullptr};
   const vpho_sample_args* p = &a;
   return sample_begin(&p, 1, max_attempts, (cudaStream_t)stream);
 }
@@ -1384,18 +1388,28 @@ extern "C" int vpho_sample_pair_finish(const vpho_sample_args* a, const vpho_sam
   return sample_finish(p, 2, (cudaStream_t)stream);
 }
 
-extern "C" int vpho_postprocess_hand(const double* xs, int n_steps, int n_rows, int rows_per_shape, const float* shape,
-                                     float* out, void* stream) {
+template <typename TIn>
+static int postprocess_hand(const TIn* xs, int n_steps, int n_rows, int rows_per_shape, const float* shape, float* out, void* stream) {
   if (n_steps < 0 || n_rows < 0 || rows_per_shape <= 0) return VPHO_ERR_INVALID;
   if (n_steps == 0 || n_rows == 0) return VPHO_OK;
   if (!xs || !shape || !out) return VPHO_ERR_INVALID;
   const size_t total = (size_t)n_steps * n_rows * 17;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 64) blocks = 148 * 64;
-  VPHO_LAUNCH(k_postprocess_hand, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, xs, n_steps, n_rows, rows_per_shape,
+  VPHO_LAUNCH(k_postprocess_hand<TIn>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, xs, n_steps, n_rows, rows_per_shape,
               shape, out);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
+}
+
+extern "C" int vpho_postprocess_hand(const double* xs, int n_steps, int n_rows, int rows_per_shape, const float* shape,
+                                     float* out, void* stream) {
+  return postprocess_hand(xs, n_steps, n_rows, rows_per_shape, shape, out, stream);
+}
+
+extern "C" int vpho_postprocess_hand_f32(const float* xs, int n_steps, int n_rows, int rows_per_shape, const float* shape,
+                                         float* out, void* stream) {
+  return postprocess_hand(xs, n_steps, n_rows, rows_per_shape, shape, out, stream);
 }
 
 extern "C" int vpho_rot6d_to_axis_angle(const float* x6d, int n_rot, float* aa, void* stream) {

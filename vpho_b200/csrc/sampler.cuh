@@ -80,6 +80,7 @@ struct RkCtrl {
                     // an attempt's six slots are filled together by the first stage's kernel
   // caller-owned outputs of the running sample()
   double* xs;       // [n_eval][N][D] or nullptr
+  float* xs32;      // the same dense output rounded to float32 (`.float()`), or nullptr
   double* x_out;    // [N][D]
   int32_t* counters;
 };

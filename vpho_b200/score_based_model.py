@@ -202,13 +202,15 @@ class ScoreBasedModelAgent:
     @torch.no_grad()
     def sample_pair(self, data_a: dict, denoiser_a: Denoiser, data_b: dict, denoiser_b: Denoiser, T0: float,
                     return_inprocess: bool = True, prior_a: Optional[torch.Tensor] = None,
-                    prior_b: Optional[torch.Tensor] = None):
+                    prior_b: Optional[torch.Tensor] = None, inprocess_float32=(False, False)):
         """The two `sample()` calls of `vpho_net.forward(mode='predict')` (hand, then object: VPHO.py:239-262) advanced in
         lock-step through shared kernel launches (`vpho_sample_pair_*`).  Priors are drawn in the reference's order
         (a, then b).  Always deferred: -> ((xs_a, x_a, pending_a), (xs_b, x_b, pending_b)); results are bit-identical
-        to two separate `sample(..., defer_check=True)` calls."""
+        to two separate `sample(..., defer_check=True)` calls.  `inprocess_float32[i]`: return sampler i's trajectory
+        already rounded to float32 (what `vpho_net` keeps of the hand's: `.float()`, VPHO.py:243) -- no float64 copy is
+        written."""
         jobs = []
-        for data, den, prior in ((data_a, denoiser_a, prior_a), (data_b, denoiser_b, prior_b)):
+        for (data, den, prior), f32 in zip(((data_a, denoiser_a, prior_a), (data_b, denoiser_b, prior_b)), inprocess_float32):
             device = (data["feat_unique"] if "feat_unique" in data else data["feat"]).device
             D = den.out_dim
             n_rows = int(data["n_rows"]) if "n_rows" in data else int(data["feat"].shape[0])
@@ -219,12 +221,13 @@ class ScoreBasedModelAgent:
             feat, rpf = _unique_feat(d2, n_rows)
             n_eval = self.sampling_steps
             ws = den.workspace(n_rows, rpf, n_eval, device)
-            xs = torch.empty((n_eval, n_rows, D), dtype=torch.float64, device=device) if return_inprocess else None
+            xs = (torch.empty((n_eval, n_rows, D), dtype=torch.float32 if f32 else torch.float64, device=device)
+                  if return_inprocess else None)
             x = torch.empty((n_rows, D), dtype=torch.float64, device=device)
             counters = torch.zeros(8, dtype=torch.int32, device=device)
             args = capi.SampleArgs(den.handle, capi.ptr(feat), n_rows, rpf, capi.ptr(x0), float(T0), float(self.sampling_eps),
-                                   None, n_eval, RTOL, ATOL, MAX_STEP, n_eval, capi.ptr(xs), capi.ptr(x), capi.ptr(counters),
-                                   capi.ptr(ws), ws.numel())
+                                   None, n_eval, RTOL, ATOL, MAX_STEP, n_eval, capi.ptr(None if f32 else xs), capi.ptr(x),
+                                   capi.ptr(counters), capi.ptr(ws), ws.numel(), capi.ptr(xs if f32 else None))
             jobs.append((den, args, xs, x, counters, n_rows, (feat, x0, ws)))
         lib = denoiser_a.lib
         stream = capi.stream_of(jobs[0][3])

@@ -54,10 +54,11 @@ class VphoHotPath:
         dev = hand_final.device
         shape = pd_mano_shape.contiguous().float()
 
-        def fused(x64, n_steps, n_rows):
+        def fused(x, n_steps, n_rows):
             out = torch.empty((n_rows, n_steps, 58), dtype=torch.float32, device=dev)
-            self.lib.check(self.lib.c.vpho_postprocess_hand(capi.ptr(x64), n_steps, n_rows, S, capi.ptr(shape), capi.ptr(out),
-                                                            capi.stream_of(x64)), "vpho_postprocess_hand")
+            fn = self.lib.c.vpho_postprocess_hand_f32 if x.dtype == torch.float32 else self.lib.c.vpho_postprocess_hand
+            self.lib.check(fn(capi.ptr(x), n_steps, n_rows, S, capi.ptr(shape), capi.ptr(out), capi.stream_of(x)),
+                           "vpho_postprocess_hand")
             return out
 
         hf = fused(hand_final.contiguous().double(), 1, bs * S).reshape(-1, 58)
@@ -65,7 +66,7 @@ class VphoHotPath:
         if hand_inprocess is not None:
             n_in = hand_inprocess.shape[1]
             native = hand_inprocess.permute(1, 0, 2)              # storage order [steps][N][96]
-            if not native.is_contiguous() or native.dtype != torch.float64:
+            if not native.is_contiguous() or native.dtype not in (torch.float64, torch.float32):
                 native = native.contiguous().double()
             hi = fused(native, n_in, bs * S)
         return hi, hf
@@ -116,7 +117,8 @@ class VphoHotPath:
         if paired:
             (xs_h, x_h, pend_h), (xs_o, x_o, pend_o) = self.score_agent.sample_pair(
                 {"feat_unique": enc_h, "n_rows": bs * S}, self.denoiser_hand, {"feat_unique": enc_o, "n_rows": bs * S},
-                self.denoiser_obj, self.sample_T0, return_inprocess=with_inprocess, prior_a=prior_hand, prior_b=prior_obj)
+                self.denoiser_obj, self.sample_T0, return_inprocess=with_inprocess, prior_a=prior_hand, prior_b=prior_obj,
+                inprocess_float32=(True, False))      # the hand trajectory is only ever used as float32 (VPHO.py:243)
         else:
             # fallback: the object sampler on a side stream (VPHO_PAIR_SAMPLERS=0), or after the hand's on the same stream
             if main is not None and self.overlap_object_sampler:

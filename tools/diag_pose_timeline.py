@@ -30,7 +30,10 @@ buf = np.zeros(3 * 2048, np.uint64)
 fn(0, buf.ctypes.data, buf.size)
 prod, mma, comp = (buf[i * 2048 + 1024:(i + 1) * 2048].astype(np.int64) for i in range(3))
 t0 = prod[0]
-print("producer: start 0; empty-wait done per chunk:", (prod[1:12] - t0).tolist(), "kernel end:", int(prod[12] - t0))
+# default build: GEMM 1 = 3 chunks of 32 k (3xTF32), GEMM 2 = 4 chunks of 64 k (3xFP16); VPHO_POSE_GEMM2=tf32: 8 chunks
+n2 = 8 if os.environ.get("VPHO_POSE_GEMM2") == "tf32" else 4
+print("producer: start 0; empty-wait done per chunk:", (prod[1:4 + n2] - t0).tolist(), "kernel end:", int(prod[4 + n2] - t0))
 print("mma: x ready", int(mma[0] - t0), "gemm1 full-ok:", (mma[1:4] - t0).tolist(), "d1 committed", int(mma[4] - t0))
-print("mma gemm2 (W ok, A ok) per chunk:", (mma[5:21] - t0).reshape(-1, 2).tolist(), "d2 committed", int(mma[21] - t0))
-print("compute: d1 seen", int(comp[0] - t0), "restaged chunks:", (comp[1:9] - t0).tolist(), "d2 seen", int(comp[9] - t0), "done", int(comp[10] - t0))
+print("mma gemm2 (W ok, A ok) per chunk:", (mma[5:5 + 2 * n2] - t0).reshape(-1, 2).tolist(), "d2 committed", int(mma[5 + 2 * n2] - t0))
+print("compute: d1 seen", int(comp[0] - t0), "restaged chunks:", (comp[1:1 + n2] - t0).tolist(), "d2 seen", int(comp[1 + n2] - t0),
+      "done", int(comp[2 + n2] - t0))

@@ -1,4 +1,6 @@
-"""Times one sample() of each denoiser at the README shape (bs 64 x 100 candidates, 50 output points) with CUDA
+"""NOTE: this times the BLOCKING stand-alone `sample()` (a host read of the status word inside every call, attempts issued
+in two rounds); the predict path uses the deferred, paired form -- see tools/graph_probe.py / bench.py for that.
+Times one sample() of each denoiser at the README shape (bs 64 x 100 candidates, 50 output points) with CUDA
 events and reports achieved FLOP/s on the factored-minimum FLOP count of SURVEY.md §8d."""
 import json
 import os

@@ -727,6 +727,18 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
     // 16 compute warps: warp 4+e owns TMEM lanes 32*(e&3).. (its hardware lane quarter) and column sub-block cs = e>>2
     const int e = warp - 4, q = e & 3, cs = e >> 2, r = q * 32 + lane;      // r: this thread's row of the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    // first-layer bias of this thread's 64 columns, fetched while GEMM 1 runs (its global-load latency would otherwise sit
+    // between "D1 complete" and the first re-staged chunk)
+    float hv[64];
+    if (g2h) {
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc)
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 64 + cs * 16 + j4 * 4));
+          hv[kc * 16 + j4 * 4 + 0] = bv.x; hv[kc * 16 + j4 * 4 + 1] = bv.y; hv[kc * 16 + j4 * 4 + 2] = bv.z; hv[kc * 16 + j4 * 4 + 3] = bv.w;
+        }
+    }
     mbar_wait(&sm.d1_full_bar, 0);
     if (threadIdx.x == 128) clk_stamp(2, sc_++);
     tc_fence_after();
@@ -735,20 +747,18 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
       // ---- re-stage relu(D1 + b1) as FP16 (hi, lo) planes: this thread owns 16 columns of each 64-column chunk.  The 64
       // activations stay in registers between the row-maximum exchange (power-of-two row scale, peak in [2^13, 2^14)) and
       // the split, as in the epilogue below.
-      float hv[64];
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
         uint32_t v[16];
         tmem_ld16(d1 + lane_addr + (uint32_t)(kc * 64 + cs * 16), v);
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 64 + cs * 16 + j4 * 4));
-          hv[kc * 16 + j4 * 4 + 0] = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + bv.x, 0.f);
-          hv[kc * 16 + j4 * 4 + 1] = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + bv.y, 0.f);
-          hv[kc * 16 + j4 * 4 + 2] = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + bv.z, 0.f);
-          hv[kc * 16 + j4 * 4 + 3] = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + bv.w, 0.f);
-        }
+        for (int j = 0; j < 16; ++j) hv[kc * 16 + j] = fmaxf(__uint_as_float(v[j]) + hv[kc * 16 + j], 0.f);
       }
+      // second-layer bias into shared memory for the epilogue (the third X chunk is free once D1 is complete; ordered by
+      // the row-maximum barrier below)
+      float* b2s = reinterpret_cast<float*>(sm.a + 2 * 2 * kTcABytes + 4 * kTcBM * sizeof(float));
+      if (threadIdx.x - 128 < 64)
+        *reinterpret_cast<float4*>(b2s + (threadIdx.x - 128) * 4) = __ldg(reinterpret_cast<const float4*>(dn.b2) + (threadIdx.x - 128));
       float rmax = 0.f;
 #pragma unroll
       for (int j = 0; j < 64; ++j) rmax = fmaxf(rmax, hv[j]);
@@ -830,10 +840,12 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
       tmem_ld32_nowait(d2 + lane_addr + (uint32_t)c0, v0);
       tmem_ld32_nowait(d2 + lane_addr + (uint32_t)(c0 + 32), v1);
       tmem_wait_ld();
+      const float* b2s = reinterpret_cast<const float*>(sm.a + 2 * 2 * kTcABytes + 4 * kTcBM * sizeof(float));
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 ba = __ldg(reinterpret_cast<const float4*>(dn.b2 + c0 + j4 * 4));
-        const float4 bb4 = __ldg(reinterpret_cast<const float4*>(dn.b2 + c0 + 32 + j4 * 4));
+        const float4 ba = g2h ? *reinterpret_cast<const float4*>(b2s + c0 + j4 * 4) : __ldg(reinterpret_cast<const float4*>(dn.b2 + c0 + j4 * 4));
+        const float4 bb4 = g2h ? *reinterpret_cast<const float4*>(b2s + c0 + 32 + j4 * 4)
+                               : __ldg(reinterpret_cast<const float4*>(dn.b2 + c0 + 32 + j4 * 4));
         pv[j4 * 4 + 0] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 0]), d2_unscale, ba.x), 0.f);
         pv[j4 * 4 + 1] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 1]), d2_unscale, ba.y), 0.f);
         pv[j4 * 4 + 2] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 2]), d2_unscale, ba.z), 0.f);

@@ -241,14 +241,20 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         cur = torch.cuda.current_stream()
         cur.wait_event(ready[slot])
         d = dev_sets[slot]
-        # enqueue this step's compute first, then issue the next step's H2D copies (copy stream): the ~15 copy calls cost
-        # host time that is better spent while the GPU is already busy
-        pd = hp.predict(d, prior_hand=d["prior_hand"], prior_obj=d["prior_obj"], prefetch=lambda: prefetch(slot ^ 1))
+        # enqueue this step's compute first; the result read-back and the next step's H2D copies (~20 copy calls of host
+        # time) are issued from predict's hook while the GPU is already busy
+        def enqueued(pd_, issue):
+            # device -> host read of the step's results, stream-ordered behind the aggregation (complete when predict's
+            # status read returns); then, once per step, the next step's H2D copies on the copy stream
+            for k in out_keys:
+                if k not in host_out:
+                    host_out[k] = torch.empty(pd_[k].shape, dtype=pd_[k].dtype).pin_memory()
+                host_out[k].copy_(pd_[k], non_blocking=True)
+            if issue == 0:
+                prefetch(slot ^ 1)
+
+        pd = hp.predict(d, prior_hand=d["prior_hand"], prior_obj=d["prior_obj"], prefetch=enqueued)
         consumed[slot].record(cur)
-        for k in out_keys:
-            if k not in host_out:
-                host_out[k] = torch.empty(pd[k].shape, dtype=pd[k].dtype).pin_memory()
-            host_out[k].copy_(pd[k], non_blocking=True)
         cur.synchronize()
         return pd
 

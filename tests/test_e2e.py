@@ -116,8 +116,11 @@ def test_e2e_cuda_reissues_when_the_attempt_budget_is_too_small(cuda_lib):
         hp = VphoHotPath(mano, anch, objs, st_h, st_o, sample_num=16, sampling_steps=7, topk_hand=6, topk_obj=4)
         hp.score_agent.first_attempts = first
         calls = []
-        pd = hp.predict(to_device(batch, "cuda"), prior_hand=ph, prior_obj=po, prefetch=lambda: calls.append(1))
-        assert len(calls) == 1          # the prefetch hook runs once per batch, re-issues included
+        pd = hp.predict(to_device(batch, "cuda"), prior_hand=ph, prior_obj=po,
+                        prefetch=lambda pd_, issue: calls.append((issue, pd_["agg_obj_6d"])))
+        # the hook runs after every enqueue (issue 0, 1, ... for re-issues) with that issue's outputs
+        assert [c[0] for c in calls] == list(range(len(calls))) and len(calls) >= 1
+        assert (len(calls) > 1) == (first == 1) and calls[-1][1] is pd["agg_obj_6d"]
         assert hp.last_info["obj"]["attempts"] > 1 and hp.last_info["obj"]["status"] == 1
         outs.append(pd)
     for k in ("diff_final_obj_6d", "diff_final_hand_mano", "agg_obj_6d", "agg_hand_vert"):

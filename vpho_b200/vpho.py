@@ -86,13 +86,16 @@ class VphoHotPath:
             if prior_obj is None:
                 prior_obj = torch.randn(bs * S, self.denoiser_obj.out_dim) * ve_prior_std(self.sample_T0)
         self.score_agent.spare_attempt = True
+        issue = 0
         for _ in range(8):
             pd, pend = self._predict_once(batch, prior_hand, prior_obj, with_inprocess)
             if prefetch is not None:
-                # caller hook, run once after the batch is enqueued and before the host blocks on its status: the place
-                # to issue the next batch's host-to-device copies on another stream
-                prefetch()
-                prefetch = None
+                # caller hook `prefetch(pd, issue)`, run after the batch is enqueued and before the host blocks on its
+                # status: the place to enqueue device-to-host reads of `pd` (stream-ordered behind the aggregation, complete
+                # when predict returns) and, for issue == 0, the next batch's host-to-device copies on another stream.
+                # A re-issued batch (issue > 0, rare) calls it again with the new outputs.
+                prefetch(pd, issue)
+            issue += 1
             status = torch.stack([p.counters for p in pend]).cpu().tolist()     # the one host sync of the batch
             ok = [p.resolve(c) for p, c in zip(pend, status)]
             self.last_info = {"hand": pend[0].info, "obj": pend[1].info}

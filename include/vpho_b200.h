@@ -58,6 +58,15 @@ int vpho_mano_forward(vpho_mano_t h, const float* pose, const float* shape, int 
 int vpho_denoiser_create(int n_heads, const float* fourier_W, const float* t_w, const float* t_b, const float* p1_w,
                          const float* p1_b, const float* p2_w, const float* p2_b, const float* ha_w,
                          const float* ha_b, const float* hb_w, const float* hb_b, vpho_denoiser_t* out);
+/* Same with an explicit numerical path, fixed for the life of the handle:
+ *   flags = 0                          tcgen05 tensor-core path (3xTF32 / 3xFP16 splitting, FP32-class accuracy).  Every
+ *                                      operand plane and TMA descriptor it needs is REQUIRED: if one cannot be built the
+ *                                      call returns VPHO_ERR_ALLOC / VPHO_ERR_LAUNCH -- it never degrades to another path.
+ *   flags = VPHO_DENOISER_STRICT_FP32  FP32 SIMT kernels only (cross-check of the tensor-core kernels). */
+#define VPHO_DENOISER_STRICT_FP32 1
+int vpho_denoiser_create_ex(int n_heads, const float* fourier_W, const float* t_w, const float* t_b, const float* p1_w,
+                            const float* p1_b, const float* p2_w, const float* p2_b, const float* ha_w,
+                            const float* ha_b, const float* hb_w, const float* hb_b, int flags, vpho_denoiser_t* out);
 int vpho_denoiser_destroy(vpho_denoiser_t h);
 
 /* One score-network evaluation: out[N][D] = denoiser(x[N][D], t, feat) / (sigma(t)+1e-7), t a single float shared

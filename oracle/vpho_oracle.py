@@ -74,6 +74,30 @@ def anchor_skeleton_table() -> np.ndarray:
     return sk[np.argsort(np.asarray(label))]
 
 
+# Geometry dtype of the scoring / aggregation stage.  The reference casts the (float64) object poses to float32 before any
+# geometry (`pose6d.clone().float()`, aggregation.py:753,958,1282).  `float64_shadow()` switches those casts -- and the
+# MANO / object / anchor tables -- to float64: the SAME algorithm evaluated without FP32 rounding.  It is used only to
+# measure how far the reference's own FP32 result sits from the exact one (tests/test_headline_parity.py), i.e. to
+# derive the parity tolerance of ill-conditioned cases instead of choosing it.
+_GEOM = [torch.float32]
+
+
+def _geom(x: torch.Tensor) -> torch.Tensor:
+    return x.to(_GEOM[0])
+
+
+class float64_shadow:
+    def __enter__(self):
+        _GEOM.append(torch.float64)
+        _GEOM[0] = torch.float64
+        return self
+
+    def __exit__(self, *exc):
+        _GEOM.pop()
+        _GEOM[0] = torch.float32
+        return False
+
+
 def canonical_topk(x: torch.Tensor, k: int, dim: int = 1):
     """torch.topk with the canonical tie-break (value desc, index asc) -- oracle rule (ii)."""
     order = torch.sort(-x, dim=dim, stable=True)[1]
@@ -181,10 +205,12 @@ def oracle_sample(den: OracleDenoiser, feat: torch.Tensor, T0: float, init_x: to
 class OracleMano:
     """HeadMano.get_hand_verts (lib/model/head_mano.py:78-87) over the manopth restatement (oracle/shims)."""
 
-    def __init__(self, model: Dict[str, np.ndarray]):
+    def __init__(self, model: Dict[str, np.ndarray], dtype=torch.float32):
         _mano_shim.set_model(model)
         self.layer = _mano_shim.ManoLayer(ncomps=45, center_idx=0, flat_hand_mean=True, side="right",
                                           mano_root="", use_pca=False)
+        if dtype != torch.float32:          # float64 shadow: the model tensors themselves stay the float32 values
+            self.layer = self.layer.to(dtype)
         self.calls = 0
 
     def __call__(self, pose: torch.Tensor, shape: torch.Tensor):
@@ -215,12 +241,12 @@ def postprocess_diffusion_hand(hand_final: torch.Tensor, pd_mano_shape: torch.Te
 class OracleObject:
     """HeadObject.forward / flip_pt3d (lib/model/head_object.py:36-67)."""
 
-    def __init__(self, tables: Dict[str, object]):
+    def __init__(self, tables: Dict[str, object], dtype=torch.float32):
         self.names = list(tables["names"])
         self.tab = {
-            "keypoint": torch.as_tensor(np.asarray(tables["kpt3d"])).float(),
-            "verts": torch.as_tensor(np.asarray(tables["verts_sampled"])).float(),
-            "CoM": torch.as_tensor(np.asarray(tables["CoM"])).float()[:, None],
+            "keypoint": torch.as_tensor(np.asarray(tables["kpt3d"])).float().to(dtype),
+            "verts": torch.as_tensor(np.asarray(tables["verts_sampled"])).float().to(dtype),
+            "CoM": torch.as_tensor(np.asarray(tables["CoM"])).float()[:, None].to(dtype),
         }
 
     def __call__(self, pose: torch.Tensor, name: Sequence[str], data_name: str = "keypoint"):
@@ -244,12 +270,12 @@ class OracleAnchors:
     """ForceAnchor.__call__ + Vert2Joint (lib/utils/physics_fn.py:224-257, lib/utils/hand_fn.py:427-448) and
     from_local_to_global (lib/model/physics.py:362-371)."""
 
-    def __init__(self, anchors: Dict[str, np.ndarray]):
+    def __init__(self, anchors: Dict[str, np.ndarray], dtype=torch.float32):
         self.face = torch.as_tensor(np.asarray(anchors["face_vertex_idx"]).reshape(-1)).long()
         aw = np.asarray(anchors["anchor_weight"], np.float64)
         aw = np.concatenate([np.ones((aw.shape[0], 1)), aw], axis=1)
-        self.anchor_weight = torch.from_numpy(aw).float()
-        self.vert2joint = torch.as_tensor(np.asarray(anchors["vert2joint"])).float()
+        self.anchor_weight = torch.from_numpy(aw).float().to(dtype)
+        self.vert2joint = torch.as_tensor(np.asarray(anchors["vert2joint"])).float().to(dtype)
         self.skel = torch.as_tensor(anchor_skeleton_table()).long()
 
     def points_and_frames(self, vertices: torch.Tensor):
@@ -404,7 +430,7 @@ def hand_cascade(mano: OracleMano, pose_diff, pose_regression, shape, root_joint
 # ---------------------------------------------------------------------------------------------------------
 def obj_heat_topk(obj: OracleObject, pose6d, root_joint, obj_name, cam, heatmap, bbox, k, is_right):
     """ObjectAggregator.select_topk_object_by_heatmap (lib/model/aggregation.py:742-780)."""
-    p = pose6d.clone().float()
+    p = _geom(pose6d.clone())
     p[..., 6:] = p[..., 6:] + root_joint.unsqueeze(1)
     pts = obj(p, obj_name)
     pts = obj.flip_pt3d(pts, is_right)
@@ -435,7 +461,7 @@ def obj_fuse_topk(topk, pose6d, weight=None):
 def obj_physics3_topk(obj: OracleObject, pose6d, root_joint, obj_name, is_right, force_point, force_global, k):
     """ObjectAggregator.select_topk_object_by_physics3 (lib/model/aggregation.py:947-997); the two cdist passes of
     cdist_memory_save / nn_for_r_memory_save (:1115-1142) are kept as in the reference."""
-    p = pose6d.clone().float()
+    p = _geom(pose6d.clone())
     p[..., 6:] = p[..., 6:] + root_joint.unsqueeze(1)
     ov = obj.flip_pt3d(obj(p, obj_name, data_name="verts"), is_right)
     oc = obj.flip_pt3d(obj(p, obj_name, data_name="CoM"), is_right)
@@ -543,7 +569,7 @@ def hoi_aggregate(mano: OracleMano, obj: OracleObject, anchors: OracleAnchors, *
     new_w[ung] = h_w[ung]
     pose6d_fused = obj_fuse_topk(new_topk, cand, new_w)
 
-    p = pose6d_fused.clone().float()
+    p = _geom(pose6d_fused.clone())
     p[..., 6:] = p[..., 6:] + root_joint
     ov = obj.flip_pt3d(obj(p, obj_name, data_name="verts"), is_right)
     oc = obj.flip_pt3d(obj(p, obj_name, data_name="CoM"), is_right)

@@ -104,3 +104,70 @@ def check_hoi_against_oracle(out: dict, dbg: dict, oracle: dict, *, pos_tol=2e-6
             rep["err_" + k] = err
             assert err <= tol, (k, err, tol)
     return rep
+
+
+def check_hoi_derived(out: dict, dbg: dict, oracle: dict, floor: dict, *, c: float = 10.0, base: dict = None):
+    """Stage-wise comparison with tolerances DERIVED from the oracle's own rounding-noise floor (tests/sensitivity.py)
+    instead of chosen per regime.
+
+    Selections: every top-k list must equal the oracle's under the canonical tie-break, or differ only by near-ties (the
+    oracle's own scores of the swapped candidates within the near-tie band).  Once a list of an image differs, the
+    candidates ranked by that image's later lists are no longer the same sets, so those lists are reported, not judged.
+    Values: for every image whose selections ALL match exactly, each output must be within
+    max(c * floor[key][image], base[key]) of the oracle's, where floor is the deviation of the oracle's float64 / +-1-ulp
+    shadow runs from the plain FP32 oracle on that image.  Returns the report (always; the caller asserts `violations`)."""
+    base = base or {"hand_agg_vert": 2e-6, "hand_agg_joint": 2e-6, "agg_obj_vert": 2e-6, "hand_agg_mano": 5e-5, "obj_agg_6d": 1e-5}
+    od = oracle["_dbg"]
+    bs = oracle["obj_agg_6d"].shape[0]
+    rep = {"images": bs, "lists": 0, "exact": 0, "near_tie": 0, "not_judged": 0, "bad": 0, "bad_lists": []}
+    clean = torch.ones(bs, dtype=torch.bool)
+
+    def account(ours, ref_idx, ref_sc, name, rtol=NEAR_TIE_RTOL):
+        nl = ours.reshape(-1, ours.shape[-1]).shape[0]
+        per_img = nl // bs
+        for b in range(bs):
+            e, n, bad = topk_agreement(ours.reshape(bs, per_img, -1)[b], ref_idx.reshape(bs, per_img, -1)[b],
+                                       ref_sc.reshape(bs, per_img, -1)[b], rtol)
+            rep["lists"] += e + n + bad
+            rep["exact"] += e
+            if not clean[b]:
+                rep["not_judged"] += n + bad        # built from an earlier differing selection
+            else:
+                rep["near_tie"] += n
+                rep["bad"] += bad
+                if bad:
+                    rep["bad_lists"].append((name, b))
+            if n or bad:
+                clean[b] = False
+
+    for lv in range(4):
+        ours, ref_idx, ref_sc = hand_level_lists(dbg["hand_topk"][lv], od["cascade"]["levels"][lv], lv)
+        account(ours, ref_idx, ref_sc, f"hand cascade level {lv}")
+    hand_clean = clean.clone()
+    clean = torch.ones(bs, dtype=torch.bool)         # the object's first two selections do not depend on the hand
+    for i, (nm, snm) in enumerate([("obj_transl_topk", "obj_transl_score"), ("obj_rot_topk", "obj_rot_score")]):
+        k = od[nm].shape[1]
+        account(dbg["obj_topk"][i, :, :k].cpu()[:, None], od[nm][:, None], od[snm][:, None], nm)
+    clean &= hand_clean                               # physics3 ranks the recombined poses against the fused hand's anchors
+    for i, (nm, snm) in ((2, ("phys_topk", "phys_score")), (3, ("heat5_topk", "heat5_score"))):
+        k = od[nm].shape[1]
+        account(dbg["obj_topk"][i, :, :k].cpu()[:, None], od[nm][:, None], od[snm][:, None], nm,
+                NEAR_TIE_RTOL_PHYSICS if nm == "phys_topk" else NEAR_TIE_RTOL)
+    account(dbg["finger_topk"].cpu(), od["finger_topk"], od["finger_score"], "hand physics finger top-k", NEAR_TIE_RTOL_PHYSICS)
+    rep["clean_images"] = int(clean.sum())
+    rep["clean_mask"] = clean.tolist()
+    rep["violations"] = []
+    rep["values"] = {}
+    for k in ("hand_agg_vert", "hand_agg_joint", "agg_obj_vert", "hand_agg_mano", "obj_agg_6d"):
+        d = (out[k].cpu().double() - oracle[k].double()).abs()
+        err = d.reshape(bs, -1).amax(dim=1)
+        tol = torch.clamp(c * floor[k].double(), min=base[k])
+        rep["values"][k] = {"err_clean": err[clean].tolist(), "floor_clean": floor[k][clean].tolist(),
+                            "err_max_clean": float(err[clean].max()) if clean.any() else None,
+                            "err_median_all": float(err.median()), "floor_median_all": float(floor[k].double().median())}
+        for b in torch.nonzero(clean & (err > tol)).reshape(-1).tolist():
+            rep["violations"].append((k, b, float(err[b]), float(tol[b])))
+    if clean.any():
+        cand_err = (out["pose6d_candidate"].cpu()[clean] - oracle["pose6d_candidate"][clean]).abs().max().item()
+        rep["pose6d_candidate_err_clean"] = cand_err
+    return rep

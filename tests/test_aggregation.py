@@ -92,19 +92,55 @@ def test_object_points_and_force_anchors_cuda(cuda_lib):
     assert (fp.cpu() - fp2).abs().max().item() < 1e-6 and (fg.cpu() - fg2).abs().max().item() < 1e-4
 
 
-def test_topk_ties_follow_index_order(emu_lib):
-    # all diffusion candidates identical -> every score ties; the canonical order must be index order 0..K-1
+def _ties(lib, dev, bs, S, Kh, Ko):
+    """All diffusion candidates of an image identical (and equal to the regression pose) -> every score of every list
+    ties exactly; the canonical order (value desc, index asc) must then return index order 0..K-1 everywhere, and a
+    partial tie (two distinct groups) must keep index order inside each group."""
     mano, anch, objs = cases.assets()
-    kw, _, _ = cases.aggregate_case(1, 16, 3)
-    kw["hand_pose_diff"] = kw["hand_pose_diff"][:1].repeat(16, 1)
-    kw["hand_pose_regression"] = kw["hand_pose_diff"][:1].clone()
-    kw["obj_pose6d"] = kw["obj_pose6d"][:, :1].repeat(1, 16, 1)
-    kw.update(hand_topk=6, obj_topk=4)
-    agg = HOI_Aggregator(HeadMano(mano, lib=emu_lib), Assets(anch, objs, lib=emu_lib), debug=True)
-    agg(**kw)
-    d = agg.last_debug
-    assert d["hand_topk"][0, 0, 0].tolist() == list(range(6))
-    assert d["obj_topk"][0, 0, :4].tolist() == list(range(4)) and d["obj_topk"][1, 0, :4].tolist() == list(range(4))
+    kw, _, _ = cases.aggregate_case(bs, S, 3)
+    pd = kw["hand_pose_diff"].reshape(bs, S, 48)
+    kw["hand_pose_diff"] = pd[:, :1].repeat(1, S, 1).reshape(-1, 48)
+    kw["hand_pose_regression"] = pd[:, 0].clone()
+    kw["obj_pose6d"] = kw["obj_pose6d"][:, :1].repeat(1, S, 1)
+    kw.update(hand_topk=Kh, obj_topk=Ko)
+    agg = HOI_Aggregator(HeadMano(mano, lib=lib), Assets(anch, objs, lib=lib), debug=True)
+    agg(**{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()})
+    d = {k: v.cpu() for k, v in agg.last_debug.items()}
+    for b in range(bs):
+        for lv in range(4):
+            for f in range(1 if lv == 0 else 5):
+                assert d["hand_topk"][lv, b, f].tolist() == list(range(Kh)), (lv, b, f)
+        assert d["obj_topk"][0, b, :Ko].tolist() == list(range(Ko)) and d["obj_topk"][1, b, :Ko].tolist() == list(range(Ko))
+        assert d["obj_topk"][3, b, :5].tolist() == list(range(5))          # heat-map ranking of the K x K identical poses
+        for f in range(5):
+            # candidates 0..Kh-1 carry the identical top-k DIP parameters (exact ties); candidate Kh (the FUSED parameters,
+            # a quaternion average that is not bit-identical to its inputs) may rank anywhere
+            dup = [i for i in d["finger_topk"][b, f].tolist() if i != Kh]
+            assert dup == list(range(len(dup))), (b, f, d["finger_topk"][b, f].tolist())
+    # two groups: odd candidates get a second pose; whichever group scores higher comes first, in index order
+    pd2 = pd[:, :1].repeat(1, S, 1)
+    pd2[:, 1::2] = pd[:, 1:2]
+    kw["hand_pose_diff"] = pd2.reshape(-1, 48)
+    agg(**{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()})
+    tk = agg.last_debug["hand_topk"].cpu()[0, :, 0, :Kh]
+    sc = agg.last_debug["hand_score"].cpu()[0, :, :, 0]
+    for b in range(bs):
+        order = tk[b].tolist()
+        vals = sc[b][tk[b].long()]
+        assert bool((vals[:-1] >= vals[1:]).all())
+        for i in range(len(order) - 1):
+            if vals[i] == vals[i + 1]:
+                assert order[i] < order[i + 1], (b, order)
+
+
+def test_topk_ties_follow_index_order(emu_lib):
+    _ties(emu_lib, "cpu", 1, 16, 6, 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bs,S,Kh,Ko", [(2, 16, 6, 4), (3, 100, 30, 10)])
+def test_topk_ties_follow_index_order_cuda(cuda_lib, bs, S, Kh, Ko):
+    _ties(None, "cuda", bs, S, Kh, Ko)
 
 
 @pytest.mark.gpu

@@ -162,11 +162,8 @@ def test_sampler_cuda_empty_batch(cuda_lib):
 
 @pytest.mark.gpu
 def test_sampler_cuda_simt_and_tensor_core_paths_agree(cuda_lib):
-    import os
     st = syn.make_denoiser_state("mano_pose", 0)
-    os.environ["VPHO_HEAD_GEMM"], os.environ["VPHO_POSE_ENCODER"] = "simt", "simt"
-    d_simt = Denoiser(st)
-    os.environ.pop("VPHO_HEAD_GEMM"), os.environ.pop("VPHO_POSE_ENCODER")
+    d_simt = Denoiser(st, strict_fp32=True)          # VPHO_DENOISER_STRICT_FP32: the FP32 SIMT kernels
     d_tc = Denoiser(st)
     g = torch.Generator().manual_seed(0)
     enc = torch.relu(torch.randn(5, 1024, generator=g)).cuda()

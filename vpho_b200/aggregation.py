@@ -46,7 +46,20 @@ class Assets:
         except Exception:
             pass
 
-    def ids(self, names: Sequence[str], device) -> torch.Tensor:
+    def ids(self, names, device) -> torch.Tensor:
+        """Object ids as the contiguous int32 device tensor the kernels read (`const int32_t*`).  `names`: a sequence of
+        object names, or integer ids as a list / numpy array / tensor of any integer dtype.  Ids that live on the host are
+        range-checked here; ids already on the device are converted without a host sync and clamped by the kernels."""
+        if isinstance(names, torch.Tensor):
+            if names.dtype in (torch.float16, torch.float32, torch.float64, torch.bool):
+                raise capi.VphoError(f"object ids must be integers, got {names.dtype}")
+            if not names.is_cuda and names.numel() and (int(names.min()) < 0 or int(names.max()) >= self.n_obj):
+                raise capi.VphoError(f"object id out of range [0, {self.n_obj})")
+            return names.to(device=device, dtype=torch.int32).contiguous()
+        if isinstance(names, np.ndarray):
+            return self.ids(torch.from_numpy(np.ascontiguousarray(names)), device)
+        if len(names) and not isinstance(names[0], str):
+            return self.ids(torch.as_tensor(list(names)), device)
         return torch.tensor([self.names.index(n) for n in names], dtype=torch.int32, device=device)
 
 
@@ -63,7 +76,7 @@ class HeadObject:
         bs = lead[0]
         p = pose.reshape(bs, -1, 9).contiguous().float()
         Cn = p.shape[1]
-        ids = name if isinstance(name, torch.Tensor) else a.ids(name, p.device)
+        ids = a.ids(name, p.device)
         which = self._WHICH[data_name]
         V = (27, a.n_pts, 1)[which]
         out = torch.empty((bs, Cn, V, 3), dtype=torch.float32, device=p.device)
@@ -127,7 +140,7 @@ class HOI_Aggregator:
             force_local=f32(kw["force_local"]), pose_diff=hand_pose_diff, pose_reg=f32(kw["hand_pose_regression"]),
             shape=f32(kw["hand_shape"]).reshape(-1, 10), hm_h=f32(kw["hand_heatmap"]), bb_h=f32(kw["hand_bbox"]),
             obj_pose=obj_pose, hm_o=f32(kw["obj_heatmap"]), bb_o=f32(kw["obj_bbox"]),
-            obj_id=kw["obj_name"] if isinstance(kw["obj_name"], torch.Tensor) else a.ids(kw["obj_name"], dev))
+            obj_id=a.ids(kw["obj_name"], dev))
         assert hold["hm_h"].shape == (bs, 21, 64, 64) and hold["hm_o"].shape == (bs, 27, 64, 64)
         kk, nc, omax = Ko * Ko, Kh + 1, max(S, Ko * Ko)
         out = dict(
@@ -150,7 +163,7 @@ class HOI_Aggregator:
         args = capi.HoiArgs(
             bs, S, Kh, Ko, PHY_TOPK, P(hold["cam"]), P(hold["rjf"]), P(hold["rj"]), P(hold["is_right"]),
             P(hold["is_grasped"]), P(hold["force_local"]), P(hold["pose_diff"]), P(hold["pose_reg"]), P(hold["shape"]),
-            P(hold["hm_h"]), P(hold["bb_h"]), P(hold["obj_pose"]), P(hold["hm_o"]), P(hold["bb_o"]), P(hold["obj_id"]),
+            P(hold["hm_h"]), P(hold["bb_h"]), P(hold["obj_pose"]), P(hold["hm_o"]), P(hold["bb_o"]), P(hold["obj_id"], torch.int32),
             P(out["obj_agg_6d"]), P(out["pose6d_candidate"]), P(out["agg_obj_vert"]), P(out["hand_agg_mano"]),
             P(out["hand_agg_vert"]), P(out["hand_agg_joint"]),
             P(dbg.get("hand_score")), P(dbg.get("hand_topk")), P(dbg.get("cascade_pose")), P(dbg.get("obj_score")),
@@ -247,7 +260,7 @@ def pose_metrics(assets: Assets, pd_joint, gt_joint, pd_vert, gt_vert, pd_obj6d,
     pj, gj, pv, gv = f(pd_joint), f(gt_joint), f(pd_vert), f(gt_vert)
     po, go = pd_obj6d.contiguous().double(), gt_obj6d.contiguous().double()
     n, dev = pj.shape[0], pj.device
-    ids = obj_name if isinstance(obj_name, torch.Tensor) else assets.ids(obj_name, dev)
+    ids = assets.ids(obj_name, dev)
     out = torch.empty((n, 4), dtype=torch.float32, device=dev)
     lib.check(lib.c.vpho_pose_metrics(assets.handle, capi.ptr(pj), capi.ptr(gj), capi.ptr(pv), capi.ptr(gv), capi.ptr(po),
                                       capi.ptr(go), capi.ptr(ids), n, capi.ptr(out), capi.stream_of(pj)), "vpho_pose_metrics")

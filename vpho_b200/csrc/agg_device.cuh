@@ -23,10 +23,21 @@ struct AssetsDev {
   const float* com;     // [n_obj][3]
 };
 
+// An object id outside [0, n_obj) (a caller bug the host mirror rejects for host-side ids) must never index the tables out
+// of bounds: device-resident ids are clamped here.
+__device__ __forceinline__ int obj_index(const AssetsDev& as, int id) { return id < 0 ? 0 : (id >= as.n_obj ? as.n_obj - 1 : id); }
+
 // host-side handle behind vpho_assets_t
 struct AssetsHost {
   AssetsDev dev;
   void* blob = nullptr;
+#ifndef VPHO_EMU
+  // Side stream + fork/join events of the aggregation (object branch beside the hand cascade): owned by the handle, created
+  // on the device that was current in vpho_assets_create.  One aggregation in flight per handle.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int device = -1;
+#endif
 };
 
 // anchor -> (joint a, joint b) bone used for the frame's y axis (physics_fn.py:127-169 after argsort(label))

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) k_obj_heat_score(AssetsDev as, HoiDev h, 
   float v = 0.f;
   if (lane < kKpts) {
     float pt[3], gx, gy;
-    obj_point(op, as.kpt + ((size_t)h.a.obj_id[b] * kKpts + lane) * 3, pt);
+    obj_point(op, as.kpt + ((size_t)obj_index(as, h.a.obj_id[b]) * kKpts + lane) * 3, pt);
     project_to_grid(h.a.cam_intrinsic + (size_t)b * 9, h.a.obj_bbox + (size_t)b * 4, pt[0], pt[1], pt[2], gx, gy);
     v = bicubic_sample64(h.a.obj_heatmap + ((size_t)b * kKpts + lane) * kHm * kHm, gx, gy);
   }
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kScanThreads) k_obj_physics3(AssetsDev as, Hoi
   ObjPose op;
   make_obj_pose(h.a.pose6d_candidate + ((size_t)b * h.kk + c) * 9, nullptr, h.a.root_joint + (size_t)b * 3,
                 h.a.is_right[b] != 0, op);
-  const float* base_pts = as.verts + (size_t)h.a.obj_id[b] * as.n_pts * 3;
+  const float* base_pts = as.verts + (size_t)obj_index(as, h.a.obj_id[b]) * as.n_pts * 3;
   float anchor[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) anchor[d] = h.fpoint[((size_t)b * kAnchors + lane) * 3 + d];
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(kScanThreads) k_obj_physics3(AssetsDev as, Hoi
     const float dist = sqrtf(s_d2[j]);
     float vstar[3], com[3];
     pts(s_arg[j], vstar);
-    obj_point(op, as.com + (size_t)h.a.obj_id[b] * 3, com);
+    obj_point(op, as.com + (size_t)obj_index(as, h.a.obj_id[b]) * 3, com);
     float r[3], fdir[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) { r[d] = (anchor[d] - vstar[d]) - com[d]; fdir[d] = fg[d] / fn; }
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(256) k_obj_final(AssetsDev as, HoiDev h) {
   // posed surface + centre of mass of the fused object (aggregation.py:1282-1287)
   ObjPose op;
   make_obj_pose(s_pose, nullptr, h.a.root_joint + (size_t)b * 3, h.a.is_right[b] != 0, op);
-  const float* base_pts = as.verts + (size_t)h.a.obj_id[b] * as.n_pts * 3;
+  const float* base_pts = as.verts + (size_t)obj_index(as, h.a.obj_id[b]) * as.n_pts * 3;
   for (int i = tid; i < as.n_pts; i += blockDim.x) {
     float o[3];
     obj_point(op, base_pts + (size_t)i * 3, o);
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(256) k_obj_final(AssetsDev as, HoiDev h) {
   }
   if (tid == 0) {
     float o[3];
-    obj_point(op, as.com + (size_t)h.a.obj_id[b] * 3, o);
+    obj_point(op, as.com + (size_t)obj_index(as, h.a.obj_id[b]) * 3, o);
     h.ocom[b * 3 + 0] = o[0]; h.ocom[b * 3 + 1] = o[1]; h.ocom[b * 3 + 2] = o[2];
   }
 }
@@ -716,8 +716,8 @@ __global__ void k_object_points(AssetsDev as, const float* __restrict__ pose6d, 
   rot6d_to_matrix(d6, op.R);
   op.t[0] = p[6]; op.t[1] = p[7]; op.t[2] = p[8];
   op.flip = flip && is_right && !is_right[b];
-  const float* tab = which == 0 ? as.kpt + (size_t)obj_id[b] * kKpts * 3
-                                : (which == 1 ? as.verts + (size_t)obj_id[b] * as.n_pts * 3 : as.com + (size_t)obj_id[b] * 3);
+  const float* tab = which == 0 ? as.kpt + (size_t)obj_index(as, obj_id[b]) * kKpts * 3
+                                : (which == 1 ? as.verts + (size_t)obj_index(as, obj_id[b]) * as.n_pts * 3 : as.com + (size_t)obj_index(as, obj_id[b]) * 3);
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
     float o[3];
     obj_point(op, tab + (size_t)v * 3, o);
@@ -760,31 +760,49 @@ static size_t hoi_carve(void* base, int bs, int S, int Kh, int Ko, int n_pts, Ho
 }
 
 template <int EL>
-static int run_hoi(const ManoModelDev& m, const AssetsDev& as, const HoiDev& h, cudaStream_t st) {
+static int run_hoi_enqueue(const ManoModelDev& m, AssetsHost& ah, const HoiDev& h, cudaStream_t st, bool* forked);
+
+// Error paths between the fork and the join must not leave side-stream work un-joined while the caller frees or reuses
+// the workspace: whatever happens, the caller's stream waits for the side stream before this returns.
+template <int EL>
+static int run_hoi(const ManoModelDev& m, AssetsHost& ah, const HoiDev& h, cudaStream_t st) {
+  bool forked = false;
+  const int rc = run_hoi_enqueue<EL>(m, ah, h, st, &forked);
+#ifndef VPHO_EMU
+  if (rc != VPHO_OK && forked) {
+    if (cudaEventRecord(ah.ev_join, ah.side) == cudaSuccess) cudaStreamWaitEvent(st, ah.ev_join, 0);
+  }
+#endif
+  return rc;
+}
+
+template <int EL>
+static int run_hoi_enqueue(const ManoModelDev& m, AssetsHost& ah, const HoiDev& h, cudaStream_t st, bool* forked) {
+  const AssetsDev& as = ah.dev;
   const vpho_hoi_args& a = h.a;
   const int bs = a.bs, S = a.S;
   constexpr int TC = 4;
   const size_t smem = sizeof(HandScoreSmem<TC>);
 #ifndef VPHO_EMU
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_hand_level_score<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != ah.device) return VPHO_ERR_INVALID;      // handle belongs to another device
+    static bool attr_set[64] = {};
+    if (dev < 64 && !attr_set[dev]) {
+      if (cudaFuncSetAttribute(k_hand_level_score<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return VPHO_ERR_LAUNCH;
+      attr_set[dev] = true;
+    }
   }
 #endif
   // The object's translation / rotation selection and the K x K recombination do not depend on the hand: they run on a
   // library-owned side stream next to the hand cascade and are joined before the physics score of the recombined poses.
   cudaStream_t so = st;
 #ifndef VPHO_EMU
-  static cudaStream_t side = nullptr;
-  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  if (!side) {
-    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
-      return VPHO_ERR_ALLOC;
-  }
+  cudaStream_t side = ah.side;
+  cudaEvent_t ev_fork = ah.ev_fork, ev_join = ah.ev_join;
   if (cudaEventRecord(ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(side, ev_fork, 0) != cudaSuccess) return VPHO_ERR_LAUNCH;
+  *forked = true;
   so = side;
 #endif
   // ---- object: translation, rotation, recombination (aggregation.py:1200-1242)
@@ -817,6 +835,7 @@ static int run_hoi(const ManoModelDev& m, const AssetsDev& as, const HoiDev& h, 
   if (a.dbg_force_global) VPHO_LAUNCH(k_copy_f32, dim3((bs * 96 + 255) / 256), dim3(256), 0, st, h.fglobal, a.dbg_force_global, bs * 96);
 #ifndef VPHO_EMU
   if (cudaStreamWaitEvent(st, ev_join, 0) != cudaSuccess) return VPHO_ERR_LAUNCH;
+  *forked = false;           // joined
 #endif
   // ---- object: physics / heat-map selection of the recombined candidates, fusion (aggregation.py:1247-1287)
   profile_begin(VPHO_TAG_PHYSICS3, st);
@@ -867,6 +886,16 @@ extern "C" int vpho_assets_create(const int32_t* face_vertex_idx, const float* a
   AssetsHost* ah = new AssetsHost();
   if (cudaMalloc(&ah->blob, off) != cudaSuccess) { delete ah; return VPHO_ERR_ALLOC; }
   if (cudaMemcpy(ah->blob, hbuf.data(), off, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(ah->blob); delete ah; return VPHO_ERR_ALLOC; }
+#ifndef VPHO_EMU
+  if (cudaGetDevice(&ah->device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ah->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ah->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ah->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    if (ah->ev_fork) cudaEventDestroy(ah->ev_fork);
+    if (ah->side) cudaStreamDestroy(ah->side);
+    cudaFree(ah->blob); delete ah; return VPHO_ERR_ALLOC;
+  }
+#endif
   char* b = static_cast<char*>(ah->blob);
   ah->dev.face = (const int*)(b + o_face); ah->dev.aw = (const float*)(b + o_aw); ah->dev.v2j = (const float*)(b + o_v2j);
   ah->dev.n_obj = n_obj; ah->dev.n_pts = n_pts;
@@ -878,6 +907,11 @@ extern "C" int vpho_assets_create(const int32_t* face_vertex_idx, const float* a
 extern "C" int vpho_assets_destroy(vpho_assets_t h) {
   if (!h) return VPHO_ERR_INVALID;
   AssetsHost* ah = static_cast<AssetsHost*>(h);
+#ifndef VPHO_EMU
+  if (ah->side) { cudaStreamSynchronize(ah->side); cudaStreamDestroy(ah->side); }
+  if (ah->ev_fork) cudaEventDestroy(ah->ev_fork);
+  if (ah->ev_join) cudaEventDestroy(ah->ev_join);
+#endif
   cudaFree(ah->blob);
   delete ah;
   return VPHO_OK;
@@ -916,7 +950,8 @@ extern "C" int vpho_hoi_aggregate(vpho_mano_t mano, vpho_assets_t assets, const 
                                   size_t workspace_bytes, void* stream) {
   if (!mano || !assets || !args || !workspace) return VPHO_ERR_INVALID;
   const vpho_hoi_args& a = *args;
-  const AssetsDev& as = static_cast<AssetsHost*>(assets)->dev;
+  AssetsHost& ah = *static_cast<AssetsHost*>(assets);
+  const AssetsDev& as = ah.dev;
   if (a.bs < 0 || a.S <= 0) return VPHO_ERR_INVALID;
   if (a.bs == 0) return VPHO_OK;
   const int nc = a.topk_hand + 1, kk = a.topk_obj * a.topk_obj;
@@ -938,7 +973,7 @@ extern "C" int vpho_hoi_aggregate(vpho_mano_t mano, vpho_assets_t assets, const 
   cudaStream_t st = (cudaStream_t)stream;
   if (nmax > 1024) return VPHO_ERR_INVALID;
   profile_begin(VPHO_TAG_AGGREGATE, st);
-  const int rc = nmax <= 256 ? run_hoi<8>(m, as, h, st) : (nmax <= 512 ? run_hoi<16>(m, as, h, st) : run_hoi<32>(m, as, h, st));
+  const int rc = nmax <= 256 ? run_hoi<8>(m, ah, h, st) : (nmax <= 512 ? run_hoi<16>(m, ah, h, st) : run_hoi<32>(m, ah, h, st));
   profile_end(VPHO_TAG_AGGREGATE, st);
   return rc;
 }

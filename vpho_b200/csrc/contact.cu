@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256) k_pose_metrics(AssetsDev as, const float*
   const float zero[3] = {0.f, 0.f, 0.f};
   make_obj_pose(pd_obj + (size_t)b * 9, nullptr, zero, true, pp);
   make_obj_pose(gt_obj + (size_t)b * 9, nullptr, zero, true, pg);
-  const float* base = as.verts + (size_t)obj_id[b] * as.n_pts * 3;
+  const float* base = as.verts + (size_t)obj_index(as, obj_id[b]) * as.n_pts * 3;
   float add = 0.f, adds = 0.f;
   for (int p0 = 0; p0 < as.n_pts; p0 += 256) {          // this thread's predicted point of the current slab
     const int i = p0 + tid;

@@ -112,10 +112,15 @@ static int launch_mano_forward(const ManoModelDev& m, const float* pose, const f
   dim3 grid((n + TC - 1) / TC, kNumVChunks);
   const size_t smem = sizeof(ManoSmem<TC>);
 #ifndef VPHO_EMU
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(mano_forward_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+  {
+    int dev = 0;
+    static bool attr_set[64] = {};                   // function attributes are per device
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return VPHO_ERR_LAUNCH;
+    if (!attr_set[dev]) {
+      if (cudaFuncSetAttribute(mano_forward_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return VPHO_ERR_LAUNCH;
+      attr_set[dev] = true;
+    }
   }
 #endif
   profile_begin(VPHO_TAG_MANO_FULL, stream);

@@ -29,39 +29,28 @@ namespace vpho {
 // tcgen05 path (scorenet_tc.cu)
 bool tc_available();
 bool tc_make_map(void* map, const void* base, int rows, int box_rows, int kdim, bool half = false);
-int tc_launch_feat(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const float* feat,
-                   float* feat_hi, float* feat_lo, const float* ba, float* F, int R, int hid, cudaStream_t st);
 int tc_launch_pose(const TcPoseJob* jobs, int n_jobs, int mode, int s, cudaStream_t st);
-int tc_launch_head(const TcHeadJob* jobs, int n_jobs, int mode, int s, bool half, int ctas, cudaStream_t st);
+int tc_launch_head(const TcHeadJob* jobs, int n_jobs, int mode, int s, int ctas, cudaStream_t st);
 
 struct alignas(64) TensorMapBlob { unsigned char b[128]; };
 
 struct DenoiserHost {
   DenoiserDev dev;
   float* blob = nullptr;
-  // tcgen05 head GEMM: K-major hi/lo weight planes [hid][256] and their TMA descriptors
+  // Exactly one numerical path per handle, fixed at creation (vpho_denoiser_create_ex):
+  //   tensor-core (default): tcgen05 pose encoder (3xTF32 + 3xFP16) feeding the 3xFP16 head GEMM;
+  //   strict FP32 (VPHO_DENOISER_STRICT_FP32, and the only path of the CPU emulator build): SIMT kernels.
   bool use_tc = false;
-  bool use_f16 = false;              // 3xFP16 head GEMM (needs the tensor-core pose encoder, which writes the FP16 planes)
-  float* w_hi = nullptr;
-  float* w_lo = nullptr;
-  void* w_half = nullptr;            // [2][hid][256] __half (hi, lo) scaled per head + [n_heads] float un-scale factors
-  TensorMapBlob mapBh_hi, mapBh_lo;
-  TensorMapBlob mapBp_hi, mapBp_lo;   // same FP16 planes, 128-row boxes: the CTA-pair kernel loads half a head per CTA
-  int pair_min_heads = 8;            // CTA-pair head GEMM from this many heads up (VPHO_HEAD_CTAS=1|2 forces)
-  bool mapA_half = false;
-  TensorMapBlob mapB_hi, mapB_lo, mapA_hi, mapA_lo;
-  // tcgen05 pose encoder: K-major hi/lo planes of pose_encoder.0 [256][Kpad1] and pose_encoder.2 [256][256]
-  bool use_tc_pose = false;
+  void* w_half = nullptr;            // [2][hid][256] __half (hi, lo) head weights scaled per head + [n_heads] float un-scale factors
+  TensorMapBlob mapBh_hi, mapBh_lo;   // 256-row boxes: single-CTA head GEMM (a stand-alone sampler with few heads)
+  TensorMapBlob mapBp_hi, mapBp_lo;   // same planes, 128-row boxes: the CTA-pair kernel loads half a head per CTA
+  int pair_min_heads = 8;            // CTA-pair head GEMM from this many heads up (and always for two samplers in lock-step)
+  TensorMapBlob mapA_hi, mapA_lo;
+  // tcgen05 pose encoder: K-major TF32 hi/lo planes of pose_encoder.0 [256][Kpad1], FP16 hi/lo planes of pose_encoder.2
   float* pe_planes = nullptr;
-  TensorMapBlob mapW1_hi, mapW1_lo, mapW2_hi, mapW2_lo, mapX_hi, mapX_lo;
+  TensorMapBlob mapW1_hi, mapW1_lo, mapX_hi, mapX_lo;
   void* w2_half = nullptr;           // [2][256][256] __half (hi, lo) planes of pose_encoder.2 scaled by a power of two
   TensorMapBlob mapW2h_hi, mapW2h_lo;
-  // tcgen05 feat-term: K-major hi/lo planes of the conditioning slice of head.0 [hid][1024]
-  bool use_tc_feat = false;
-  float* wf_planes = nullptr;
-  TensorMapBlob mapWf_hi, mapWf_lo, mapF_hi, mapF_lo;
-  const float* mapF_for = nullptr;
-  int mapF_rows = 0;
   const float* mapX_for = nullptr;
   int mapX_rows = 0;
   const float* mapA_for = nullptr;   // P2hi pointer the cached A maps were built for
@@ -374,26 +363,6 @@ __global__ void __launch_bounds__(256) k_pose_encoder(DenoiserDev dn, SamplerWs 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xr[i], wc[j], acc[i][j]);
-  }
-  if (ws.P2hi) {
-    // tcgen05 path: row-major (K-major) planes, hi = tf32(p), lo = tf32(p - hi)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float hi[8], lo[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float p = fmaxf(acc[i][j], 0.f);
-        hi[j] = tf32_round(p);
-        lo[j] = tf32_round(p - hi[j]);
-      }
-      float* dh = ws.P2hi + (size_t)(r0 + 4 * tx + i) * kPDim + 8 * ty;
-      float* dl = ws.P2lo + (size_t)(r0 + 4 * tx + i) * kPDim + 8 * ty;
-      *reinterpret_cast<float4*>(dh) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<float4*>(dh + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-      *reinterpret_cast<float4*>(dl) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-      *reinterpret_cast<float4*>(dl + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
-    }
-    return;
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -774,8 +743,7 @@ __global__ void __launch_bounds__(256) k_postprocess_hand(const TIn* __restrict_
 // ------------------------------------------------------------------------------------------------------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int n_eval, SamplerWs* ws, bool use_tc = true,
-                    bool use_f16 = false) {
+static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int n_eval, SamplerWs* ws, bool use_tc = true) {
   const int D = 3 * n_heads, hid = n_heads * kHeadHid;
   const int R = (n_rows + rows_per_feat - 1) / rows_per_feat;
   const int Npad = (int)align_up((size_t)(n_rows > 0 ? n_rows : 1), kRowTile);
@@ -786,16 +754,13 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
   const size_t o_F = take((size_t)R * hid * 4);
   const size_t o_Fpart = take((size_t)8 * R * hid * 4);      // kFtSplit partial sums
   const size_t o_Tt = take((size_t)7 * hid * 4);
+  // pose features: [256][Npad] float (strict-FP32 SIMT path) or two [Npad][256] __half planes + per-row scales (tensor cores);
+  // the workspace size does not depend on the path (same bytes either way)
   const size_t o_P2T = take((size_t)kPDim * Npad * 4);
-  const size_t o_P2hi = take((size_t)kPDim * Npad * 4);
-  const size_t o_P2lo = take((size_t)kPDim * Npad * 4);
   const size_t o_P2sc = take((size_t)Npad * 4);
   const int Kx = (D + 31) / 32 * 32;
   const size_t o_Xhi = take((size_t)Kx * Npad * 4);
   const size_t o_Xlo = take((size_t)Kx * Npad * 4);
-  const size_t Rpad = align_up((size_t)(R > 0 ? R : 1), 128);
-  const size_t o_Fhi = take(Rpad * kFDim * 4);
-  const size_t o_Flo = take(Rpad * kFDim * 4);
   const size_t o_y = take(n * 8);
   const size_t o_yn = take(n * 8);
   const size_t o_K = take(7 * n * 4);
@@ -807,15 +772,13 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
     ws->F = reinterpret_cast<float*>(b + o_F);
     ws->Fpart = reinterpret_cast<float*>(b + o_Fpart);
     ws->Tt = reinterpret_cast<float*>(b + o_Tt);
-    ws->P2T = reinterpret_cast<float*>(b + o_P2T);
-    ws->P2hi = use_tc ? reinterpret_cast<float*>(b + o_P2hi) : nullptr;
-    ws->P2lo = use_tc ? reinterpret_cast<float*>(b + o_P2lo) : nullptr;
-    ws->P2scale = (use_tc && use_f16) ? reinterpret_cast<float*>(b + o_P2sc) : nullptr;
+    ws->P2T = use_tc ? nullptr : reinterpret_cast<float*>(b + o_P2T);
+    ws->P2hi = use_tc ? reinterpret_cast<float*>(b + o_P2T) : nullptr;
+    ws->P2lo = use_tc ? reinterpret_cast<float*>(b + o_P2T + (size_t)kPDim * Npad * 2) : nullptr;
+    ws->P2scale = use_tc ? reinterpret_cast<float*>(b + o_P2sc) : nullptr;
     ws->Xhi = reinterpret_cast<float*>(b + o_Xhi);
     ws->Xlo = reinterpret_cast<float*>(b + o_Xlo);
     ws->Kx = Kx;
-    ws->FeatHi = reinterpret_cast<float*>(b + o_Fhi);
-    ws->FeatLo = reinterpret_cast<float*>(b + o_Flo);
     ws->y = reinterpret_cast<double*>(b + o_y);
     ws->ynew = reinterpret_cast<double*>(b + o_yn);
     ws->K = reinterpret_cast<float*>(b + o_K);
@@ -833,24 +796,10 @@ static int red_blocks(int n) { int b = (n + 255) / 256; return b < 1 ? 1 : (b > 
 static int launch_feat_term(DenoiserHost& dh, const SamplerWs& ws, const float* feat, cudaStream_t st) {
   const DenoiserDev& dn = dh.dev;
   profile_begin(VPHO_TAG_FEAT_TERM, st);
-#ifndef VPHO_EMU
-  if (dh.use_tc_feat) {
-    const int Rpad = (ws.R + 127) / 128 * 128;
-    if (dh.mapF_for != ws.FeatHi || dh.mapF_rows != Rpad) {
-      if (!tc_make_map(&dh.mapF_hi, ws.FeatHi, Rpad, 128, kFDim) || !tc_make_map(&dh.mapF_lo, ws.FeatLo, Rpad, 128, kFDim)) return VPHO_ERR_LAUNCH;
-      dh.mapF_for = ws.FeatHi;
-      dh.mapF_rows = Rpad;
-    }
-    int rc = tc_launch_feat(&dh.mapF_hi, &dh.mapF_lo, &dh.mapWf_hi, &dh.mapWf_lo, feat, ws.FeatHi, ws.FeatLo, dn.ba, ws.F, ws.R, dn.hid, st);
-    if (rc) return rc;
-  } else
-#endif
-  {
-    VPHO_LAUNCH(k_feat_term, dim3(dn.hid / kFtCols, (ws.R + kFtRows - 1) / kFtRows, kFtSplit), dim3(256), 0, st, dn, feat, ws.R,
-                ws.Fpart, dn, feat, ws.R, ws.Fpart, dn.hid / kFtCols);
-    const int n4 = ws.R * dn.hid / 4;
-    VPHO_LAUNCH(k_feat_sum, dim3((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), dim3(256), 0, st, dn, ws.Fpart, ws.R, ws.F);
-  }
+  VPHO_LAUNCH(k_feat_term, dim3(dn.hid / kFtCols, (ws.R + kFtRows - 1) / kFtRows, kFtSplit), dim3(256), 0, st, dn, feat, ws.R,
+              ws.Fpart, dn, feat, ws.R, ws.Fpart, dn.hid / kFtCols);
+  const int n4 = ws.R * dn.hid / 4;
+  VPHO_LAUNCH(k_feat_sum, dim3((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), dim3(256), 0, st, dn, ws.Fpart, ws.R, ws.F);
   profile_end(VPHO_TAG_FEAT_TERM, st);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
@@ -870,11 +819,10 @@ static int stage_x_blocks(const DenoiserDev& dn, const SamplerWs& ws, int mode, 
 // One network evaluation of every job: stage input + time term, pose encoder, head GEMM.
 static int launch_eval(SamplerJob* jobs, int n_jobs, int mode, int s, cudaStream_t st) {
 #ifndef VPHO_EMU
-  bool all_tc = true;
-  for (int j = 0; j < n_jobs; ++j) all_tc = all_tc && jobs[j].ws.P2hi && jobs[j].dh->use_tc_pose;
-  // two jobs share launches only on the CTA-pair FP16 path; anything else runs them one after the other
-  if (n_jobs == 2 && !(all_tc && jobs[0].ws.P2scale && jobs[1].ws.P2scale && jobs[0].dh->pair_min_heads < (1 << 30))) {
-    for (int j = 0; j < 2; ++j) {
+  bool any_tc = false, all_tc = true;
+  for (int j = 0; j < n_jobs; ++j) { any_tc = any_tc || jobs[j].dh->use_tc; all_tc = all_tc && jobs[j].dh->use_tc; }
+  if (any_tc && !all_tc) {         // a tensor-core and a strict-FP32 handle do not share launches
+    for (int j = 0; j < n_jobs; ++j) {
       int rc = launch_eval(jobs + j, 1, mode, s, st);
       if (rc) return rc;
     }
@@ -892,7 +840,7 @@ static int launch_eval(SamplerJob* jobs, int n_jobs, int mode, int s, cudaStream
     profile_end(VPHO_TAG_STAGE_X, st);
     TcPoseJob pj[2];
     TcHeadJob hj[2];
-    bool half = true, pair = n_jobs > 1;
+    bool pair = n_jobs > 1;
     for (int j = 0; j < n_jobs; ++j) {
       DenoiserHost& dh = *jobs[j].dh;
       const SamplerWs& ws = jobs[j].ws;
@@ -901,37 +849,32 @@ static int launch_eval(SamplerJob* jobs, int n_jobs, int mode, int s, cudaStream
         dh.mapX_for = ws.Xhi;
         dh.mapX_rows = ws.Npad;
       }
-      const bool h16 = ws.P2scale != nullptr;
-      if (dh.mapA_for != ws.P2hi || dh.mapA_rows != ws.Npad || dh.mapA_half != h16) {
-        if (!tc_make_map(&dh.mapA_hi, ws.P2hi, ws.Npad, 128, kPDim, h16) || !tc_make_map(&dh.mapA_lo, ws.P2lo, ws.Npad, 128, kPDim, h16))
+      if (dh.mapA_for != ws.P2hi || dh.mapA_rows != ws.Npad) {
+        if (!tc_make_map(&dh.mapA_hi, ws.P2hi, ws.Npad, 128, kPDim, true) || !tc_make_map(&dh.mapA_lo, ws.P2lo, ws.Npad, 128, kPDim, true))
           return VPHO_ERR_LAUNCH;
         dh.mapA_for = ws.P2hi;
         dh.mapA_rows = ws.Npad;
-        dh.mapA_half = h16;
       }
-      half = half && h16;
-      pair = pair || (h16 && dh.dev.n_heads >= dh.pair_min_heads);
-      const bool g2h = dh.dev.W2scale_inv > 0.f;
-      pj[j] = TcPoseJob{&dh.mapX_hi, &dh.mapX_lo, &dh.mapW1_hi, &dh.mapW1_lo, g2h ? &dh.mapW2h_hi : &dh.mapW2_hi,
-                        g2h ? &dh.mapW2h_lo : &dh.mapW2_lo, &dh.dev, &jobs[j].ws};
+      pair = pair || dh.dev.n_heads >= dh.pair_min_heads;
+      pj[j] = TcPoseJob{&dh.mapX_hi, &dh.mapX_lo, &dh.mapW1_hi, &dh.mapW1_lo, &dh.mapW2h_hi, &dh.mapW2h_lo, &dh.dev, &jobs[j].ws};
     }
     for (int j = 0; j < n_jobs; ++j) {
       DenoiserHost& dh = *jobs[j].dh;
-      hj[j] = pair   ? TcHeadJob{&dh.mapA_hi, &dh.mapA_lo, &dh.mapBp_hi, &dh.mapBp_lo, &dh.dev, &jobs[j].ws}
-              : half ? TcHeadJob{&dh.mapA_hi, &dh.mapA_lo, &dh.mapBh_hi, &dh.mapBh_lo, &dh.dev, &jobs[j].ws}
-                     : TcHeadJob{&dh.mapA_hi, &dh.mapA_lo, &dh.mapB_hi, &dh.mapB_lo, &dh.dev, &jobs[j].ws};
+      hj[j] = pair ? TcHeadJob{&dh.mapA_hi, &dh.mapA_lo, &dh.mapBp_hi, &dh.mapBp_lo, &dh.dev, &jobs[j].ws}
+                   : TcHeadJob{&dh.mapA_hi, &dh.mapA_lo, &dh.mapBh_hi, &dh.mapBh_lo, &dh.dev, &jobs[j].ws};
     }
     int rc = tc_launch_pose(pj, n_jobs, mode, s, st);
     if (rc) return rc;
     profile_end(VPHO_TAG_POSE_ENCODER, st);
     const int tag = j0.dh->dev.n_heads >= 16 ? VPHO_TAG_HEAD_GEMM_HAND : VPHO_TAG_HEAD_GEMM_OBJ;
     profile_begin(tag, st);
-    rc = tc_launch_head(hj, n_jobs, mode, s, half, pair ? 2 : 1, st);
+    rc = tc_launch_head(hj, n_jobs, mode, s, pair ? 2 : 1, st);
     if (rc) return rc;
     profile_end(tag, st);
     return VPHO_OK;
   }
 #endif
+  // strict-FP32 SIMT path (cross-check of the tensor-core kernels; the CPU emulator build)
   for (int j = 0; j < n_jobs; ++j) {
     DenoiserHost& dh = *jobs[j].dh;
     const DenoiserDev& dn = dh.dev;
@@ -942,24 +885,7 @@ static int launch_eval(SamplerJob* jobs, int n_jobs, int mode, int s, cudaStream
     profile_end(VPHO_TAG_POSE_ENCODER, st);
     const int tag = dn.n_heads >= 16 ? VPHO_TAG_HEAD_GEMM_HAND : VPHO_TAG_HEAD_GEMM_OBJ;
     profile_begin(tag, st);
-#ifndef VPHO_EMU
-    if (ws.P2hi) {
-      // tensor-core head GEMM behind the SIMT pose encoder (VPHO_POSE_ENCODER=simt): 3xTF32 planes, one CTA per item
-      if (dh.mapA_for != ws.P2hi || dh.mapA_rows != ws.Npad || dh.mapA_half) {
-        if (!tc_make_map(&dh.mapA_hi, ws.P2hi, ws.Npad, 128, kPDim, false) || !tc_make_map(&dh.mapA_lo, ws.P2lo, ws.Npad, 128, kPDim, false))
-          return VPHO_ERR_LAUNCH;
-        dh.mapA_for = ws.P2hi;
-        dh.mapA_rows = ws.Npad;
-        dh.mapA_half = false;
-      }
-      TcHeadJob hj{&dh.mapA_hi, &dh.mapA_lo, &dh.mapB_hi, &dh.mapB_lo, &dh.dev, &jobs[j].ws};
-      int rc = tc_launch_head(&hj, 1, mode, s, false, 1, st);
-      if (rc) return rc;
-    } else
-#endif
-    {
-      VPHO_LAUNCH(k_head_simt, dim3(ws.Npad / kRowTile, dn.n_heads), dim3(256), 0, st, dn, ws, mode, s);
-    }
+    VPHO_LAUNCH(k_head_simt, dim3(ws.Npad / kRowTile, dn.n_heads), dim3(256), 0, st, dn, ws, mode, s);
     profile_end(tag, st);
     VPHO_CHECK_LAUNCH();
   }
@@ -996,12 +922,115 @@ static int launch_attempts(SamplerJob* jobs, int n_jobs, int max_attempts, cudaS
 
 using namespace vpho;
 
-extern "C" int vpho_denoiser_create(int n_heads, const float* fourier_W, const float* t_w, const float* t_b,
-                                    const float* p1_w, const float* p1_b, const float* p2_w, const float* p2_b,
-                                    const float* ha_w, const float* ha_b, const float* hb_w, const float* hb_b,
-                                    vpho_denoiser_t* out) {
+static void free_denoiser(DenoiserHost* dh) {
+  if (!dh) return;
+  if (dh->blob) cudaFree(dh->blob);
+  if (dh->pe_planes) cudaFree(dh->pe_planes);
+  if (dh->w2_half) cudaFree(dh->w2_half);
+  if (dh->w_half) cudaFree(dh->w_half);
+  delete dh;
+}
+
+#ifndef VPHO_EMU
+// power-of-two scale that brings `mx` into [2^13, 2^14) (exact in FP16 hi/lo splitting) and its inverse
+static void pow2_scale(float mx, float* sc, float* inv) {
+  *sc = 1.f; *inv = 1.f;
+  if (mx > 0.f && mx < 3.0e38f) {
+    int e = 0;
+    frexpf(mx, &e);
+    *sc = ldexpf(1.f, 14 - e);
+    *inv = ldexpf(1.f, e - 14);
+  }
+}
+
+// Operand planes + TMA descriptors of the tensor-core path.  Every resource is REQUIRED: a failure is reported to the
+// caller (no silent change of numerical path).
+static int build_tc_planes(DenoiserHost* dh, int n_heads, const float* p1_w, const float* p2_w, const float* ha_w) {
+  DenoiserDev& d = dh->dev;
+  const int D = d.D, hid = d.hid;
+  if (!tc_available()) return VPHO_ERR_LAUNCH;       // driver without cuTensorMapEncodeTiled
+  // pose_encoder.0: TF32 (hi, lo) planes [256][Kpad1]
+  const int kp1 = (D + 31) / 32 * 32;
+  const size_t n1 = (size_t)256 * kp1;
+  std::vector<float> pl(2 * n1, 0.f);
+  for (int o = 0; o < 256; ++o)
+    for (int k = 0; k < D; ++k) {
+      const float w = p1_w[(size_t)o * D + k], hi = tf32_round(w);
+      pl[(size_t)o * kp1 + k] = hi;
+      pl[n1 + (size_t)o * kp1 + k] = tf32_round(w - hi);
+    }
+  if (cudaMalloc((void**)&dh->pe_planes, pl.size() * sizeof(float)) != cudaSuccess) return VPHO_ERR_ALLOC;
+  if (cudaMemcpy(dh->pe_planes, pl.data(), pl.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return VPHO_ERR_ALLOC;
+  if (!tc_make_map(&dh->mapW1_hi, dh->pe_planes, 256, 256, kp1) || !tc_make_map(&dh->mapW1_lo, dh->pe_planes + n1, 256, 256, kp1))
+    return VPHO_ERR_LAUNCH;
+  // pose_encoder.2: FP16 (hi, lo) planes [256][256], one power-of-two scale for the matrix
+  {
+    float mx = 0.f, sc, inv2;
+    for (size_t i = 0; i < (size_t)256 * 256; ++i) mx = fmaxf(mx, fabsf(p2_w[i]));
+    pow2_scale(mx, &sc, &inv2);
+    const size_t n2h = (size_t)256 * 256;
+    std::vector<unsigned short> w2(2 * n2h);
+    for (int o = 0; o < 256; ++o)
+      for (int k = 0; k < 256; ++k) {
+        const float w = p2_w[(size_t)o * 256 + k] * sc;
+        const __half h = __float2half_rn(w);
+        w2[(size_t)o * 256 + k] = __half_as_ushort(h);
+        w2[n2h + (size_t)o * 256 + k] = __half_as_ushort(__float2half_rn(w - __half2float(h)));
+      }
+    if (cudaMalloc(&dh->w2_half, w2.size() * sizeof(unsigned short)) != cudaSuccess) return VPHO_ERR_ALLOC;
+    if (cudaMemcpy(dh->w2_half, w2.data(), w2.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess) return VPHO_ERR_ALLOC;
+    if (!tc_make_map(&dh->mapW2h_hi, dh->w2_half, 256, 256, 256, true) ||
+        !tc_make_map(&dh->mapW2h_lo, static_cast<unsigned short*>(dh->w2_half) + n2h, 256, 256, 256, true))
+      return VPHO_ERR_LAUNCH;
+    d.W2scale_inv = inv2;
+  }
+  // head.0 pose slice: FP16 (hi, lo) planes [hid][256] K-major, one power-of-two scale per head
+  {
+    const size_t nw = (size_t)hid * kPDim;
+    std::vector<unsigned short> hp(2 * nw);
+    std::vector<float> inv(n_heads, 1.f);
+    for (int nn = 0; nn < n_heads; ++nn) {
+      float mx = 0.f, sc;
+      for (int k = 0; k < kPDim; ++k) {
+        const float* src = ha_w + ((size_t)nn * 1408 + 128 + k) * 256;
+        for (int cc = 0; cc < 256; ++cc) mx = fmaxf(mx, fabsf(src[cc]));
+      }
+      pow2_scale(mx, &sc, &inv[nn]);
+      for (int k = 0; k < kPDim; ++k) {
+        const float* src = ha_w + ((size_t)nn * 1408 + 128 + k) * 256;
+        for (int cc = 0; cc < 256; ++cc) {
+          const float w = src[cc] * sc;
+          const __half h = __float2half_rn(w);
+          const __half l = __float2half_rn(w - __half2float(h));
+          hp[((size_t)nn * 256 + cc) * kPDim + k] = __half_as_ushort(h);
+          hp[nw + ((size_t)nn * 256 + cc) * kPDim + k] = __half_as_ushort(l);
+        }
+      }
+    }
+    const size_t bytes = 2 * nw * sizeof(unsigned short) + (size_t)n_heads * sizeof(float);
+    if (cudaMalloc(&dh->w_half, bytes) != cudaSuccess) return VPHO_ERR_ALLOC;
+    if (cudaMemcpy(dh->w_half, hp.data(), 2 * nw * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(static_cast<char*>(dh->w_half) + 2 * nw * sizeof(unsigned short), inv.data(), n_heads * sizeof(float),
+                   cudaMemcpyHostToDevice) != cudaSuccess)
+      return VPHO_ERR_ALLOC;
+    if (!tc_make_map(&dh->mapBh_hi, dh->w_half, hid, 256, kPDim, true) ||
+        !tc_make_map(&dh->mapBh_lo, static_cast<unsigned short*>(dh->w_half) + nw, hid, 256, kPDim, true) ||
+        !tc_make_map(&dh->mapBp_hi, dh->w_half, hid, 128, kPDim, true) ||
+        !tc_make_map(&dh->mapBp_lo, static_cast<unsigned short*>(dh->w_half) + nw, hid, 128, kPDim, true))
+      return VPHO_ERR_LAUNCH;
+    d.Wscale_inv = reinterpret_cast<const float*>(static_cast<char*>(dh->w_half) + 2 * nw * sizeof(unsigned short));
+  }
+  dh->use_tc = true;
+  return VPHO_OK;
+}
+#endif
+
+extern "C" int vpho_denoiser_create_ex(int n_heads, const float* fourier_W, const float* t_w, const float* t_b,
+                                       const float* p1_w, const float* p1_b, const float* p2_w, const float* p2_b,
+                                       const float* ha_w, const float* ha_b, const float* hb_w, const float* hb_b,
+                                       int flags, vpho_denoiser_t* out) {
   if (n_heads <= 0 || 3 * n_heads > kMaxD || !fourier_W || !t_w || !t_b || !p1_w || !p1_b || !p2_w || !p2_b || !ha_w ||
-      !ha_b || !hb_w || !hb_b || !out)
+      !ha_b || !hb_w || !hb_b || !out || (flags & ~VPHO_DENOISER_STRICT_FP32))
     return VPHO_ERR_INVALID;
   const int D = 3 * n_heads, hid = n_heads * kHeadHid;
   const size_t n_four = 64, n_wt = 128 * 128, n_bt = 128, n_w1 = (size_t)D * 256, n_b1 = 256, n_w2 = 256 * 256,
@@ -1040,176 +1069,34 @@ extern "C" int vpho_denoiser_create(int n_heads, const float* fourier_W, const f
   for (int i = 0; i < D; ++i) h[o_bb + i] = hb_b[i];
 
   DenoiserHost* dh = new DenoiserHost();
-  if (cudaMalloc((void**)&dh->blob, off * sizeof(float)) != cudaSuccess) { delete dh; return VPHO_ERR_ALLOC; }
-  if (cudaMemcpy(dh->blob, h.data(), off * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
-    cudaFree(dh->blob); delete dh; return VPHO_ERR_ALLOC;
-  }
+  if (cudaMalloc((void**)&dh->blob, off * sizeof(float)) != cudaSuccess) { dh->blob = nullptr; free_denoiser(dh); return VPHO_ERR_ALLOC; }
+  if (cudaMemcpy(dh->blob, h.data(), off * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { free_denoiser(dh); return VPHO_ERR_ALLOC; }
   const float* b = dh->blob;
   DenoiserDev& d = dh->dev;
   d.n_heads = n_heads; d.D = D; d.hid = hid;
   d.fourier_W = b + o_four; d.Wt = b + o_wt; d.bt = b + o_bt; d.W1 = b + o_w1; d.b1 = b + o_b1; d.W2 = b + o_w2;
   d.b2 = b + o_b2; d.Wa_t = b + o_wat; d.Wa_p = b + o_wap; d.Wa_f = b + o_waf; d.ba = b + o_ba; d.Wb = b + o_wb;
-  d.bb = b + o_bb; d.Wa_p_hi = nullptr; d.Wa_p_lo = nullptr; d.Wscale_inv = nullptr; d.W2scale_inv = 0.f;
+  d.bb = b + o_bb; d.Wscale_inv = nullptr; d.W2scale_inv = 0.f;
 #ifndef VPHO_EMU
-  // tcgen05 head GEMM (default).  VPHO_HEAD_GEMM=simt keeps the FP32-SIMT kernel (used to cross-check the two).
-  const char* sel = getenv("VPHO_HEAD_GEMM");
-  const bool want_tc = !(sel && strcmp(sel, "simt") == 0);
-  if (want_tc && tc_available()) {
-    std::vector<float> whi((size_t)hid * kPDim), wlo((size_t)hid * kPDim);
-    for (int nn = 0; nn < n_heads; ++nn)
-      for (int k = 0; k < kPDim; ++k) {
-        const float* src = ha_w + ((size_t)nn * 1408 + 128 + k) * 256;
-        for (int cc = 0; cc < 256; ++cc) {
-          const float w = src[cc], hi = tf32_round(w);
-          whi[((size_t)nn * 256 + cc) * kPDim + k] = hi;
-          wlo[((size_t)nn * 256 + cc) * kPDim + k] = tf32_round(w - hi);
-        }
-      }
-    const size_t bytes = (size_t)hid * kPDim * sizeof(float);
-    if (cudaMalloc((void**)&dh->w_hi, bytes) != cudaSuccess || cudaMalloc((void**)&dh->w_lo, bytes) != cudaSuccess ||
-        cudaMemcpy(dh->w_hi, whi.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(dh->w_lo, wlo.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
-      cudaFree(dh->w_hi); cudaFree(dh->w_lo); cudaFree(dh->blob); delete dh; return VPHO_ERR_ALLOC;
-    }
-    if (!tc_make_map(&dh->mapB_hi, dh->w_hi, hid, 256, kPDim) || !tc_make_map(&dh->mapB_lo, dh->w_lo, hid, 256, kPDim)) {
-      cudaFree(dh->w_hi); cudaFree(dh->w_lo); cudaFree(dh->blob); delete dh; return VPHO_ERR_LAUNCH;
-    }
-    d.Wa_p_hi = dh->w_hi; d.Wa_p_lo = dh->w_lo;
-    dh->use_tc = true;
-    // pose encoder planes (VPHO_POSE_ENCODER=simt keeps the FP32-SIMT kernel)
-    const char* selp = getenv("VPHO_POSE_ENCODER");
-    if (!(selp && strcmp(selp, "simt") == 0)) {
-      const int kp1 = (D + 31) / 32 * 32;
-      const size_t n1 = (size_t)256 * kp1, n2 = (size_t)256 * 256;
-      std::vector<float> pl(2 * n1 + 2 * n2, 0.f);
-      for (int o = 0; o < 256; ++o) {
-        for (int k = 0; k < D; ++k) {
-          const float w = p1_w[(size_t)o * D + k], hi = tf32_round(w);
-          pl[(size_t)o * kp1 + k] = hi;
-          pl[n1 + (size_t)o * kp1 + k] = tf32_round(w - hi);
-        }
-        for (int k = 0; k < 256; ++k) {
-          const float w = p2_w[(size_t)o * 256 + k], hi = tf32_round(w);
-          pl[2 * n1 + (size_t)o * 256 + k] = hi;
-          pl[2 * n1 + n2 + (size_t)o * 256 + k] = tf32_round(w - hi);
-        }
-      }
-      if (cudaMalloc((void**)&dh->pe_planes, pl.size() * sizeof(float)) == cudaSuccess &&
-          cudaMemcpy(dh->pe_planes, pl.data(), pl.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
-          tc_make_map(&dh->mapW1_hi, dh->pe_planes, 256, 256, kp1) && tc_make_map(&dh->mapW1_lo, dh->pe_planes + n1, 256, 256, kp1) &&
-          tc_make_map(&dh->mapW2_hi, dh->pe_planes + 2 * n1, 256, 256, 256) &&
-          tc_make_map(&dh->mapW2_lo, dh->pe_planes + 2 * n1 + n2, 256, 256, 256))
-        dh->use_tc_pose = true;
-    }
-    // 3xFP16 head GEMM (default when the tensor-core pose encoder is on; VPHO_HEAD_GEMM=tf32 keeps 3xTF32)
-    if (dh->use_tc_pose && !(sel && strcmp(sel, "tf32") == 0)) {
-      const size_t nw = (size_t)hid * kPDim;
-      std::vector<unsigned short> hp(2 * nw);
-      std::vector<float> inv(n_heads, 1.f);
-      for (int nn = 0; nn < n_heads; ++nn) {
-        float mx = 0.f;
-        for (int k = 0; k < kPDim; ++k) {
-          const float* src = ha_w + ((size_t)nn * 1408 + 128 + k) * 256;
-          for (int cc = 0; cc < 256; ++cc) mx = fmaxf(mx, fabsf(src[cc]));
-        }
-        float sc = 1.f;
-        if (mx > 0.f && mx < 3.0e38f) {
-          int e = 0;
-          frexpf(mx, &e);
-          sc = ldexpf(1.f, 14 - e);
-          inv[nn] = ldexpf(1.f, e - 14);
-        }
-        for (int k = 0; k < kPDim; ++k) {
-          const float* src = ha_w + ((size_t)nn * 1408 + 128 + k) * 256;
-          for (int cc = 0; cc < 256; ++cc) {
-            const float w = src[cc] * sc;
-            const __half h = __float2half_rn(w);
-            const __half l = __float2half_rn(w - __half2float(h));
-            hp[((size_t)nn * 256 + cc) * kPDim + k] = __half_as_ushort(h);
-            hp[nw + ((size_t)nn * 256 + cc) * kPDim + k] = __half_as_ushort(l);
-          }
-        }
-      }
-      const size_t bytes = 2 * nw * sizeof(unsigned short) + (size_t)n_heads * sizeof(float);
-      if (cudaMalloc(&dh->w_half, bytes) == cudaSuccess &&
-          cudaMemcpy(dh->w_half, hp.data(), 2 * nw * sizeof(unsigned short), cudaMemcpyHostToDevice) == cudaSuccess &&
-          cudaMemcpy(static_cast<char*>(dh->w_half) + 2 * nw * sizeof(unsigned short), inv.data(), n_heads * sizeof(float),
-                     cudaMemcpyHostToDevice) == cudaSuccess &&
-          tc_make_map(&dh->mapBh_hi, dh->w_half, hid, 256, kPDim, true) &&
-          tc_make_map(&dh->mapBh_lo, static_cast<unsigned short*>(dh->w_half) + nw, hid, 256, kPDim, true) &&
-          tc_make_map(&dh->mapBp_hi, dh->w_half, hid, 128, kPDim, true) &&
-          tc_make_map(&dh->mapBp_lo, static_cast<unsigned short*>(dh->w_half) + nw, hid, 128, kPDim, true)) {
-        const char* hc = getenv("VPHO_HEAD_CTAS");
-        if (hc && hc[0] == '1') dh->pair_min_heads = 1 << 30;
-        if (hc && hc[0] == '2') dh->pair_min_heads = 1;
-        d.Wscale_inv = reinterpret_cast<const float*>(static_cast<char*>(dh->w_half) + 2 * nw * sizeof(unsigned short));
-        dh->use_f16 = true;
-      }
-      // FP16 planes of the second pose-encoder layer (one power-of-two scale for the matrix): its GEMM is 72 % of the pose
-      // kernel's tensor work and runs at twice the TF32 rate on half the bytes (VPHO_POSE_GEMM2=tf32 keeps 3xTF32)
-      const char* selg = getenv("VPHO_POSE_GEMM2");
-      if (dh->use_f16 && !(selg && strcmp(selg, "tf32") == 0)) {
-        float mx = 0.f;
-        for (size_t i = 0; i < (size_t)256 * 256; ++i) mx = fmaxf(mx, fabsf(p2_w[i]));
-        float sc = 1.f, inv2 = 1.f;
-        if (mx > 0.f && mx < 3.0e38f) {
-          int e = 0;
-          frexpf(mx, &e);
-          sc = ldexpf(1.f, 14 - e);
-          inv2 = ldexpf(1.f, e - 14);
-        }
-        const size_t n2h = (size_t)256 * 256;
-        std::vector<unsigned short> w2(2 * n2h);
-        for (int o = 0; o < 256; ++o)
-          for (int k = 0; k < 256; ++k) {
-            const float w = p2_w[(size_t)o * 256 + k] * sc;
-            const __half h = __float2half_rn(w);
-            w2[(size_t)o * 256 + k] = __half_as_ushort(h);
-            w2[n2h + (size_t)o * 256 + k] = __half_as_ushort(__float2half_rn(w - __half2float(h)));
-          }
-        if (cudaMalloc(&dh->w2_half, w2.size() * sizeof(unsigned short)) == cudaSuccess &&
-            cudaMemcpy(dh->w2_half, w2.data(), w2.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) == cudaSuccess &&
-            tc_make_map(&dh->mapW2h_hi, dh->w2_half, 256, 256, 256, true) &&
-            tc_make_map(&dh->mapW2h_lo, static_cast<unsigned short*>(dh->w2_half) + n2h, 256, 256, 256, true))
-          d.W2scale_inv = inv2;
-      }
-    }
-    // feat-term on tensor cores is opt-in (VPHO_FEAT_TERM=tc): see the accuracy note at k_feat_term
-    const char* self = getenv("VPHO_FEAT_TERM");
-    if (self && strcmp(self, "tc") == 0) {
-      const size_t nf = (size_t)hid * kFDim;
-      std::vector<float> pf(2 * nf);
-      for (int nn = 0; nn < n_heads; ++nn)
-        for (int k = 0; k < kFDim; ++k) {
-          const float* src = ha_w + ((size_t)nn * 1408 + 384 + k) * 256;
-          for (int cc = 0; cc < 256; ++cc) {
-            const float w = src[cc], hi = tf32_round(w);
-            pf[((size_t)nn * 256 + cc) * kFDim + k] = hi;
-            pf[nf + ((size_t)nn * 256 + cc) * kFDim + k] = tf32_round(w - hi);
-          }
-        }
-      if (cudaMalloc((void**)&dh->wf_planes, 2 * nf * sizeof(float)) == cudaSuccess &&
-          cudaMemcpy(dh->wf_planes, pf.data(), 2 * nf * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
-          tc_make_map(&dh->mapWf_hi, dh->wf_planes, hid, 256, kFDim) && tc_make_map(&dh->mapWf_lo, dh->wf_planes + nf, hid, 256, kFDim))
-        dh->use_tc_feat = true;
-    }
+  if (!(flags & VPHO_DENOISER_STRICT_FP32)) {
+    const int rc = build_tc_planes(dh, n_heads, p1_w, p2_w, ha_w);
+    if (rc != VPHO_OK) { free_denoiser(dh); return rc; }
   }
 #endif
   *out = dh;
   return VPHO_OK;
 }
 
+extern "C" int vpho_denoiser_create(int n_heads, const float* fourier_W, const float* t_w, const float* t_b,
+                                    const float* p1_w, const float* p1_b, const float* p2_w, const float* p2_b,
+                                    const float* ha_w, const float* ha_b, const float* hb_w, const float* hb_b,
+                                    vpho_denoiser_t* out) {
+  return vpho_denoiser_create_ex(n_heads, fourier_W, t_w, t_b, p1_w, p1_b, p2_w, p2_b, ha_w, ha_b, hb_w, hb_b, 0, out);
+}
+
 extern "C" int vpho_denoiser_destroy(vpho_denoiser_t h) {
   if (!h) return VPHO_ERR_INVALID;
-  DenoiserHost* dh = static_cast<DenoiserHost*>(h);
-  cudaFree(dh->blob);
-  if (dh->w_hi) cudaFree(dh->w_hi);
-  if (dh->w_lo) cudaFree(dh->w_lo);
-  if (dh->pe_planes) cudaFree(dh->pe_planes);
-  if (dh->w2_half) cudaFree(dh->w2_half);
-  if (dh->wf_planes) cudaFree(dh->wf_planes);
-  if (dh->w_half) cudaFree(dh->w_half);
-  delete dh;
+  free_denoiser(static_cast<DenoiserHost*>(h));
   return VPHO_OK;
 }
 
@@ -1238,7 +1125,7 @@ extern "C" int vpho_score_eval(vpho_denoiser_t h, const float* x, float t, const
   DenoiserHost& dh = *static_cast<DenoiserHost*>(h);
   const DenoiserDev& dn = dh.dev;
   SamplerJob job{&dh, {}, n_rows * dn.D};
-  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, 1, &job.ws, dh.use_tc, dh.use_f16) > workspace_bytes) return VPHO_ERR_INVALID;
+  if (carve(workspace, dn.n_heads, n_rows, rows_per_feat, 1, &job.ws, dh.use_tc) > workspace_bytes) return VPHO_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   job.ws.eval_x = x; job.ws.eval_out = out;
   VPHO_LAUNCH(k_set_eval_time, dim3(1), dim3(1), 0, st, job.ws, t);
@@ -1256,7 +1143,7 @@ static int prepare_job(const vpho_sample_args* a, bool begin, SamplerJob* job, c
   const DenoiserDev& dn = dh.dev;
   job->dh = &dh;
   job->ws_n = a->n_rows * dn.D;
-  if (carve(a->workspace, dn.n_heads, a->n_rows, a->rows_per_feat, a->n_eval, &job->ws, dh.use_tc, dh.use_f16) > a->workspace_bytes)
+  if (carve(a->workspace, dn.n_heads, a->n_rows, a->rows_per_feat, a->n_eval, &job->ws, dh.use_tc) > a->workspace_bytes)
     return VPHO_ERR_INVALID;
   if (!begin) return VPHO_OK;
   SampleCfg cfg{a->T0, a->eps, a->rtol, a->atol, a->max_step, a->n_rows, dn.D, a->n_eval, a->num_steps, a->rows_per_feat, a->t_eval,
@@ -1276,7 +1163,7 @@ static int live_jobs(const vpho_sample_args* const* args, int n_args, bool begin
   // two samplers begun together share one split-K feat-term launch (each alone is a latency-bound ~60 us kernel)
   bool both = begin && n_args == 2;
   for (int i = 0; both && i < 2; ++i)
-    both = args[i] && args[i]->denoiser && args[i]->n_rows > 0 && !static_cast<DenoiserHost*>(args[i]->denoiser)->use_tc_feat;
+    both = args[i] && args[i]->denoiser && args[i]->n_rows > 0;
   const float* feats[2] = {nullptr, nullptr};
   for (int i = 0; i < n_args; ++i) {
     SamplerJob j{};

@@ -31,11 +31,8 @@ struct DenoiserDev {
   const float* ba;         // [hid]
   const float* Wb;         // [hid][4]            head.2.weight[n][c][0..2], padded to float4
   const float* bb;         // [D]
-  // 3xTF32 operand images for the tcgen05 path (nullptr when not built)
-  const float* Wa_p_hi;    // [n_heads][256 n][256 k]  K-major, hi parts
-  const float* Wa_p_lo;
   const float* Wscale_inv; // [n_heads] exact power-of-two un-scaling of the FP16 weight planes (3xFP16 head GEMM)
-  float W2scale_inv;       // > 0: the second pose-encoder GEMM runs on FP16 planes of W2 scaled by 1 / W2scale_inv (power of two)
+  float W2scale_inv;       // the second pose-encoder GEMM runs on FP16 planes of W2 scaled by 1 / W2scale_inv (power of two)
 };
 
 enum StageMode : int {
@@ -91,14 +88,12 @@ struct SamplerWs {
   float* Fpart;    // [8][R][hid] split-K partial sums of the feat-term
   float* Tt;       // [7][hid]  time-term by slot (tt_slot): the six stages of an RK attempt are computed together
   float* P2T;      // [256][Npad] pose features, k-major (FP32-SIMT head GEMM)
-  float* P2hi;     // [Npad][256] pose features split for 3xTF32, row-major = K-major (tcgen05 head GEMM); nullptr = SIMT
-  float* P2lo;
-  float* P2scale;  // [Npad] per-row un-scaling of the FP16 pose-feature planes (P2hi/P2lo then hold __half); nullptr = TF32
+  float* P2hi;     // [Npad][256] __half (hi, lo) planes of the pose features scaled per row, row-major = K-major (tcgen05
+  float* P2lo;     // head GEMM); nullptr on the strict-FP32 SIMT path
+  float* P2scale;  // [Npad] exact power-of-two un-scaling of each row of the FP16 planes; nullptr on the SIMT path
   float* Xhi;      // [Npad][Kx] stage input split for 3xTF32 (Kx = D rounded up to 32), tcgen05 pose encoder only
   float* Xlo;
   int Kx;
-  float* FeatHi;   // [Rpad][1024] conditioning features split for 3xTF32 (tcgen05 feat-term), Rpad = R rounded up to 128
-  float* FeatLo;
   double* y;       // [n]
   double* ynew;    // [n]
   float* K;        // [7][n] raw network outputs (float32) of the RK stages; see kval for the float64 drift they stand for

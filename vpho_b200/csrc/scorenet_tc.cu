@@ -1,18 +1,18 @@
-// Score-network head GEMM on the 5th-generation tensor cores (tcgen05) with FP32-level accuracy by 3xTF32 splitting.
+// Score network on the 5th-generation tensor cores (tcgen05) with FP32-class accuracy by operand splitting.
 //
-// Same contract as k_head_simt (sampler.cu): for every 128-candidate row tile and every ParallelLinear head
+// Head GEMM (k_head_tc), same contract as k_head_simt (sampler.cu): for every 128-candidate row tile and ParallelLinear head
 //     hidden[128][256] = P2[128][256] . Wa_p[head][256][256]      (lib/model/parallel_linear.py:27-35, K = pose features)
 //     out[row][0..2]   = relu(hidden + F[img] + Tt) . Wb[head] + bb ;  score = out / (sigma(t) + 1e-7)
-// but the contraction runs as  A_hi.B_hi + A_hi.B_lo + A_lo.B_hi  with kind::tf32 UMMA instructions:
+// with the contraction run as  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  on FP16 (hi, lo) planes (kind::f16 UMMA):
+//   * operands are scaled by exact powers of two so that every candidate row / head peaks in [2^13, 2^14):
+//     hi = half(x s), lo = half(x s - hi) is a 22-bit split; the dropped lo.lo term leaves ~2^-21 per product;
 //   * operands staged in shared memory by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B, K-major 128-byte rows),
-//     2-stage mbarrier pipeline, one producer lane;
-//   * tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 256, K = 8 per instruction, issued by one elected lane,
-//     FP32 accumulators in TMEM (2 x 256 columns, double-buffered across work items);
-//   * 4 epilogue warps read the accumulator with tcgen05.ld (one candidate row per thread, 32 columns at a time) and
-//     fuse bias / conditioning / time terms, ReLU, the 256 -> 3 second ParallelLinear and the sigma division.
-// Persistent grid: CTA b processes items b, b + gridDim.x, ... of the (head, row tile) list.
-// hi = round_to_nearest_tf32(x), lo = round_to_nearest_tf32(x - hi): the dropped lo.lo term and the TF32 rounding of lo
-// leave a relative error of ~2^-21 per product, i.e. FP32-class accuracy for this K = 256 contraction.
+//     mbarrier pipeline, one producer lane;
+//   * tcgen05.mma issued by one elected lane, FP32 accumulators in TMEM (2 x 256 columns, double-buffered across items);
+//   * epilogue warps read the accumulator with tcgen05.ld (one candidate row per thread) and fuse the un-scaling,
+//     bias / conditioning / time terms, ReLU, the 256 -> 3 second ParallelLinear and the sigma division.
+// Persistent grid: CTA (pair) b processes items b, b + n_units, ... of the (head, row tile) list.
+// Pose encoder (k_pose_tc): D -> 256 -> 256 ReLU MLP per 128-row tile, GEMM 1 as 3xTF32, GEMM 2 as 3xFP16.
 #include "sampler_device.cuh"
 #include "vpho_b200.h"
 
@@ -29,6 +29,7 @@ constexpr int kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes;   // 96 KB
 constexpr int kTcThreads = 256;        // pose / feat kernels: 4 epilogue warps
 constexpr int kHeadThreads = 640;      // head kernel: 4 role warps + 2 x 8 epilogue warps
 constexpr int kTcFtImgs = 4;
+constexpr int kMaxDevices = 64;       // per-device caches of function attributes
 constexpr int kTcMaxStages = 3;      // CTA-pair head GEMM: 3 stages of 64 KB in the same 192 KB
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 // FP16 operands (a_format = b_format = 0), FP32 accumulate: same tile, K = 16 per instruction, twice the TF32 rate
@@ -110,11 +111,6 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
-}
-template <bool kHalf>
-__device__ __forceinline__ void umma_any(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  if (kHalf) umma_f16(tmem_d, adesc, bdesc, kTcIdescF16, accumulate);
-  else umma_tf32(tmem_d, adesc, bdesc, kTcIdesc, accumulate);
 }
 __device__ __forceinline__ void umma_commit(void* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -242,10 +238,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// kHalf = false: 3xTF32 (operands are float planes, 32 k per 128-byte row, 8 chunks of K = 256).
-// kHalf = true : 3xFP16 (operands are __half planes scaled by exact powers of two so that every row / head peaks in
-//                [2^13, 2^14): hi = half(x s), lo = half(x s - hi), the same 22-bit split as TF32 at twice the MMA rate and
-//                half the operand bytes; 64 k per 128-byte row, 4 chunks; the epilogue undoes the scales).
+// Operands are __half planes (64 k per 128-byte row, 4 chunks of K = 256); the epilogue undoes the power-of-two scales.
 // kCtas = 2: CTA-pair variant.  The two CTAs of a cluster take the row tiles 2p and 2p + 1 of the same head; each loads its
 //                own A tile and HALF of the head's weight tile (128 of the 256 hidden columns), the leader CTA issues one
 //                tcgen05.mma.cta_group::2 of M = 256 that reads both halves, so the L2 -> SM operand traffic per CTA drops
@@ -257,7 +250,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // network calls, so one launch serves both -- job 0's work items followed by job 1's, dealt to the CTAs from opposite ends
 // so that the CTAs with one item fewer of job 0 take job 1's first.  Each job has its own operand maps, weights, workspace
 // and RK controller; a job whose controller is not active in this call (finished, or a skipped attempt) contributes nothing.
-template <bool kHalf, int kCtas>
+template <int kCtas>
 __global__ void __launch_bounds__(kHeadThreads, 1)
 k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
           const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -279,7 +272,6 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool kPair = kCtas == 2;
-  static_assert(!kPair || kHalf, "the CTA-pair variant is built for the FP16 planes");
   constexpr int kStages = kPair ? 3 : kTcStages;
   constexpr int kBHalfBytes = kTcBBytes / kCtas;                   // B plane bytes this CTA stages per K chunk
   constexpr int kStageBytes = 2 * kTcABytes + 2 * kBHalfBytes;     // 96 KB, or 64 KB per CTA of a pair
@@ -287,7 +279,7 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;           // CTA or CTA pair
   const int n_units = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  constexpr int kElems = kHalf ? 64 : 32;           // operand elements per 128-byte row
+  constexpr int kElems = 64;           // __half operand elements per 128-byte row
   constexpr int kChunks = kPDim / kElems;
 
   if (warp == 1 && lane == 0) {
@@ -364,7 +356,7 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     if (lane == 0 && rank == 0) {
       int stage = 0, acc = 0, mc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      constexpr uint32_t kIdesc = (kHalf ? kTcIdescF16 : kTcIdesc) + (kPair ? ((uint32_t)(kTcBM >> 4) << 24) : 0u);   // M = 128 * kCtas
+      constexpr uint32_t kIdesc = kTcIdescF16 + (kPair ? ((uint32_t)(kTcBM >> 4) << 24) : 0u);   // M = 128 * kCtas
       const int cnt1 = items1 > first1 ? (items1 - first1 + n_units - 1) / n_units : 0;
       for (int n_it = 0; n_it < cnt0 + cnt1; ++n_it) {          // every item is the same 128 (x2) x 256 x 256 product
         clk_stamp(1, mc++);
@@ -389,9 +381,9 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
               umma_f16_pair(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
               umma_f16_pair(d_tmem, a_hi + adv, b_hi + adv, kIdesc, 1u);
             } else {
-              umma_any<kHalf>(d_tmem, a_lo + adv, b_hi + adv, first);
-              umma_any<kHalf>(d_tmem, a_hi + adv, b_lo + adv, 1u);
-              umma_any<kHalf>(d_tmem, a_hi + adv, b_hi + adv, 1u);
+              umma_f16(d_tmem, a_lo + adv, b_hi + adv, kIdesc, first);
+              umma_f16(d_tmem, a_hi + adv, b_lo + adv, kIdesc, 1u);
+              umma_f16(d_tmem, a_hi + adv, b_hi + adv, kIdesc, 1u);
             }
           }
           // frees the smem slot (of both CTAs) once these MMAs have read it
@@ -464,8 +456,8 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         const int cbase = half * 128;
         const int img_l = valid ? row / rpf - img0 : 0;
         const float* Frow = ws.F + (size_t)(valid ? row / rpf : 0) * dn.hid + hc0 + cbase;
-        // exact power-of-two un-scaling of the FP16 operand planes (1 for the TF32 planes); loaded before the waits
-        const float unscale = kHalf ? (row < ws.Npad ? ws.P2scale[row] : 1.f) * dn.Wscale_inv[head] : 1.f;
+        // exact power-of-two un-scaling of the FP16 operand planes; loaded before the waits
+        const float unscale = (row < ws.Npad ? ws.P2scale[row] : 1.f) * dn.Wscale_inv[head];
         if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
         else asm volatile("bar.sync 3, 256;" ::: "memory");
         if (it + it_step < n_items) fetch_consts(it + it_step, kc);
@@ -615,10 +607,9 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = dn.D, nk1 = (D + kTcBK - 1) / kTcBK;
   const int r0 = tile * kTcBM;
-  // GEMM 2 on FP16 planes (dn.W2scale_inv > 0): 4 chunks of 64 k, kind::f16, H1 re-staged as (hi, lo) halves scaled per row;
-  // otherwise 8 chunks of 32 k, kind::tf32.  Either way a chunk is 128-byte rows: 16 KB per A plane, 32 KB per B plane.
-  const bool g2h = dn.W2scale_inv > 0.f;
-  const int nk2 = g2h ? 4 : 8, kel2 = g2h ? 64 : 32;
+  // GEMM 2 on FP16 planes: 4 chunks of 64 k, kind::f16, H1 re-staged as (hi, lo) halves scaled per row.  A chunk is 128-byte
+  // rows: 16 KB per A plane, 32 KB per B plane.
+  constexpr int nk2 = 4, kel2 = 64;
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -704,7 +695,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
         clk_stamp(1, sc_++);
         tc_fence_after();
         const unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
-        if (g2h) {
+        {
           const uint64_t a_hi = make_kmajor_sw128_desc(chunk), a_lo = make_kmajor_sw128_desc(chunk + kTcABytes);
           const uint64_t b_hi = make_kmajor_sw128_desc(sm.b[stage]), b_lo = make_kmajor_sw128_desc(sm.b[stage] + kTcBBytes);
 #pragma unroll
@@ -714,8 +705,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
             umma_f16(d2, a_hi + adv, b_lo + adv, kTcIdescF16, 1u);
             umma_f16(d2, a_hi + adv, b_hi + adv, kTcIdescF16, 1u);
           }
-        } else
-        mma_chunk(d2, chunk, chunk + kTcABytes, kc == 0);
+        }
         umma_commit(&sm.empty_bar[stage]);
         umma_commit(&sm.a_empty_bar[ab]);
         if (++stage == 2) { stage = 0; phase ^= 1; }
@@ -730,7 +720,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
     // first-layer bias of this thread's 64 columns, fetched while GEMM 1 runs (its global-load latency would otherwise sit
     // between "D1 complete" and the first re-staged chunk)
     float hv[64];
-    if (g2h) {
+    {
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc)
 #pragma unroll
@@ -742,8 +732,8 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
     mbar_wait(&sm.d1_full_bar, 0);
     if (threadIdx.x == 128) clk_stamp(2, sc_++);
     tc_fence_after();
-    float d2_unscale = 1.f;                        // undoes the operand scaling of GEMM 2 (FP16 planes only)
-    if (g2h) {
+    float d2_unscale = 1.f;                        // undoes the operand scaling of GEMM 2
+    {
       // ---- re-stage relu(D1 + b1) as FP16 (hi, lo) planes: this thread owns 16 columns of each 64-column chunk.  The 64
       // activations stay in registers between the row-maximum exchange (power-of-two row scale, peak in [2^13, 2^14)) and
       // the split, as in the epilogue below.
@@ -798,35 +788,6 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
         mbar_arrive(&sm.a_full_bar[ab]);
         if (threadIdx.x == 128) clk_stamp(2, sc_++);
       }
-    } else {
-    // ---- re-stage relu(D1 + b1) as the A operand of GEMM 2: 8 columns of each 32-column chunk per thread
-      for (int kc = 0; kc < 8; ++kc) {
-        const int ab = kc & 1;
-        mbar_wait(&sm.a_empty_bar[ab], (uint32_t)(((kc >> 1) & 1) ^ 1));
-        uint32_t v[8];
-        tmem_ld8(d1 + lane_addr + (uint32_t)(kc * 32 + cs * 8), v);
-        unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
-        const float4 ba = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 32 + cs * 8));
-        const float4 bb4 = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 32 + cs * 8 + 4));
-        const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb4.x, bb4.y, bb4.z, bb4.w};
-        float hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float hv = fmaxf(__uint_as_float(v[j]) + bias[j], 0.f);
-          hi[j] = tf32_rna(hv);
-          lo[j] = tf32_rna(hv - hi[j]);
-        }
-#pragma unroll
-        for (int u2 = 0; u2 < 2; ++u2) {
-          const int u = cs * 2 + u2;                       // 16-byte unit inside the 128-byte row
-          const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((u ^ (r & 7)) & 7) << 4));
-          *reinterpret_cast<float4*>(chunk + off) = make_float4(hi[u2 * 4 + 0], hi[u2 * 4 + 1], hi[u2 * 4 + 2], hi[u2 * 4 + 3]);
-          *reinterpret_cast<float4*>(chunk + kTcABytes + off) = make_float4(lo[u2 * 4 + 0], lo[u2 * 4 + 1], lo[u2 * 4 + 2], lo[u2 * 4 + 3]);
-        }
-        fence_proxy_async();
-        mbar_arrive(&sm.a_full_bar[ab]);
-        if (threadIdx.x == 128) clk_stamp(2, sc_++);
-      }
     }
     // ---- epilogue: relu(D2 + b2) -> operand planes of the head GEMM, 64 columns per thread, ONE pass over TMEM: the
     // 64 activations stay in registers between the row-maximum exchange and the split
@@ -843,9 +804,8 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
       const float* b2s = reinterpret_cast<const float*>(sm.a + 2 * 2 * kTcABytes + 4 * kTcBM * sizeof(float));
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 ba = g2h ? *reinterpret_cast<const float4*>(b2s + c0 + j4 * 4) : __ldg(reinterpret_cast<const float4*>(dn.b2 + c0 + j4 * 4));
-        const float4 bb4 = g2h ? *reinterpret_cast<const float4*>(b2s + c0 + 32 + j4 * 4)
-                               : __ldg(reinterpret_cast<const float4*>(dn.b2 + c0 + 32 + j4 * 4));
+        const float4 ba = *reinterpret_cast<const float4*>(b2s + c0 + j4 * 4);
+        const float4 bb4 = *reinterpret_cast<const float4*>(b2s + c0 + 32 + j4 * 4);
         pv[j4 * 4 + 0] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 0]), d2_unscale, ba.x), 0.f);
         pv[j4 * 4 + 1] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 1]), d2_unscale, ba.y), 0.f);
         pv[j4 * 4 + 2] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 2]), d2_unscale, ba.z), 0.f);
@@ -856,7 +816,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
         pv[32 + j4 * 4 + 3] = fmaxf(fmaf(__uint_as_float(v1[j4 * 4 + 3]), d2_unscale, bb4.w), 0.f);
       }
     }
-    if (ws.P2scale) {
+    {
       // FP16 planes: the row maximum (over the four column sub-blocks, through shared memory) fixes an exact power-of-two
       // scale so the row peaks in [2^13, 2^14); then (hi, lo) halves
       float rmax = 0.f;
@@ -902,20 +862,6 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
         const uint4 val = *reinterpret_cast<const uint4*>(ot + plane * kPlane + row * kRowPad + unit * 16);
         *reinterpret_cast<uint4*>((plane ? glo : ghi) + (size_t)row * 512 + unit * 16) = val;
       }
-    } else {
-      float* dh = ws.P2hi + (size_t)(r0 + r) * kPDim + c0;
-      float* dl = ws.P2lo + (size_t)(r0 + r) * kPDim + c0;
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        float hi[4], lo[4];
-#pragma unroll
-        for (int ee = 0; ee < 4; ++ee) {
-          hi[ee] = tf32_rna(pv[u * 4 + ee]);
-          lo[ee] = tf32_rna(pv[u * 4 + ee] - hi[ee]);
-        }
-        *reinterpret_cast<float4*>(dh + u * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(dl + u * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-      }
     }
   }
   if (threadIdx.x == 128) clk_stamp(2, sc_++);
@@ -939,130 +885,6 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
           DenoiserDev dn1, SamplerWs ws1, int tiles0, int mode, int s) {
   if ((int)blockIdx.x < tiles0) pose_tc_tile(&tmX_hi, &tmX_lo, &tmW1_hi, &tmW1_lo, &tmW2_hi, &tmW2_lo, dn0, ws0, mode, s, blockIdx.x);
   else pose_tc_tile(&tmX_hi1, &tmX_lo1, &tmW1_hi1, &tmW1_lo1, &tmW2_hi1, &tmW2_lo1, dn1, ws1, mode, s, (int)blockIdx.x - tiles0);
-}
-
-// =====================================================================================================================
-// Feat-term on tensor cores: F[R][hid] = feat[R][1024] . Wa_f + ba, once per sample().  Same TMA / UMMA / TMEM pipeline
-// as k_head_tc with K = 1024 (32 chunks) and a plain store epilogue; rows >= R of the last 128-row tile are zero padding
-// (written by k_split_planes) and never stored.  Work item = (row tile, 256-column tile).
-// =====================================================================================================================
-__global__ void __launch_bounds__(kTcThreads, 1)
-k_feat_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const float* __restrict__ ba,
-          float* __restrict__ F, int R, int hid) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // align inside the shared window with an offset (an integer round trip would demote every access to a generic load)
-  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_ct = hid / kTcBN, n_rt = (R + kTcBM - 1) / kTcBM;
-  const int n_items = n_ct * n_rt;
-  constexpr int kChunks = kFDim / kTcBK;
-
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kTcStages; ++i) { mbar_init(&sm.full_bar[i], 1); mbar_init(&sm.empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full_bar[i], 1); mbar_init(&sm.tmem_empty_bar[i], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = sm.tmem_base;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int ct = it % n_ct, rt = it / n_ct;
-        for (int kc = 0; kc < kChunks; ++kc) {
-          mbar_wait(&sm.empty_bar[stage], phase ^ 1);
-          unsigned char* st = sm.stage[stage];
-          mbar_arrive_expect_tx(&sm.full_bar[stage], kTcStageBytes);
-          tma_load_2d(&tmA_hi, &sm.full_bar[stage], st, kc * kTcBK, rt * kTcBM);
-          tma_load_2d(&tmA_lo, &sm.full_bar[stage], st + kTcABytes, kc * kTcBK, rt * kTcBM);
-          tma_load_2d(&tmB_hi, &sm.full_bar[stage], st + 2 * kTcABytes, kc * kTcBK, ct * kTcBN);
-          tma_load_2d(&tmB_lo, &sm.full_bar[stage], st + 2 * kTcABytes + kTcBBytes, kc * kTcBK, ct * kTcBN);
-          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        mbar_wait(&sm.tmem_empty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTcBN);
-        for (int kc = 0; kc < kChunks; ++kc) {
-          mbar_wait(&sm.full_bar[stage], phase);
-          tc_fence_after();
-          unsigned char* st = sm.stage[stage];
-          const uint64_t a_hi = make_kmajor_sw128_desc(st), a_lo = make_kmajor_sw128_desc(st + kTcABytes);
-          const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * kTcABytes), b_lo = make_kmajor_sw128_desc(st + 2 * kTcABytes + kTcBBytes);
-#pragma unroll
-          for (int k = 0; k < kTcBK / kTcUmmaK; ++k) {
-            const uint64_t adv = (uint64_t)((k * kTcUmmaK * 4) >> 4);
-            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, kTcIdesc, (kc | k) != 0 ? 1u : 0u);
-            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, kTcIdesc, 1u);
-            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, kTcIdesc, 1u);
-          }
-          umma_commit(&sm.empty_bar[stage]);
-          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(&sm.tmem_full_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else if (warp >= 4) {
-    const int q = warp - 4;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const int ct = it % n_ct, rt = it / n_ct;
-      mbar_wait(&sm.tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      const int row = rt * kTcBM + q * 32 + lane;
-      float* dst = F + (size_t)row * hid + ct * kTcBN;
-#pragma unroll 1
-      for (int cb = 0; cb < kTcBN / 32; ++cb) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTcBN + cb * 32), v);
-        if (row < R) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ba + ct * kTcBN + cb * 32 + u * 4));
-            *reinterpret_cast<float4*>(dst + cb * 32 + u * 4) =
-                make_float4(__uint_as_float(v[u * 4 + 0]) + b4.x, __uint_as_float(v[u * 4 + 1]) + b4.y,
-                            __uint_as_float(v[u * 4 + 2]) + b4.z, __uint_as_float(v[u * 4 + 3]) + b4.w);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.tmem_empty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
-  }
-}
-
-// feat -> (hi, lo) TF32 planes for the A operand of k_feat_tc
-__global__ void k_split_planes(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int n_src, int n) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float x = i < n_src ? src[i] : 0.f, h = tf32_rna(x);      // rows beyond R are zero padding of the last tile
-    hi[i] = h;
-    lo[i] = tf32_rna(x - h);
-  }
 }
 
 // -------------------------------------------------------------------------------------------------- host side
@@ -1107,26 +929,25 @@ int tc_debug_clocks(int enable, unsigned long long* out, int n) {
   return VPHO_OK;
 }
 
-// ctas = 2 launches the CTA-pair variant (FP16 planes only): mapB_* must then have 128-row boxes.  n_jobs = 2 serves two
-// samplers in lock-step with one launch (see k_head_tc).
-int tc_launch_head(const TcHeadJob* jobs, int n_jobs, int mode, int s, bool half, int ctas, cudaStream_t st) {
-  static bool attr = false;
+// ctas = 2 launches the CTA-pair variant: mapB_* must then have 128-row boxes.  n_jobs = 2 serves two samplers in
+// lock-step with one launch (see k_head_tc).  Per-device state (function attributes, SM count) is looked up per device.
+int tc_launch_head(const TcHeadJob* jobs, int n_jobs, int mode, int s, int ctas, cudaStream_t st) {
   const int smem = (int)sizeof(TcSmem) + 1024;
-  if (!attr) {
-    if (cudaFuncSetAttribute(k_head_tc<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_head_tc<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-        cudaFuncSetAttribute(k_head_tc<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return VPHO_ERR_LAUNCH;
+  static bool attr[kMaxDevices] = {};
+  static int n_sm_of[kMaxDevices] = {};
+  if (!attr[dev]) {
+    if (cudaFuncSetAttribute(k_head_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaFuncSetAttribute(k_head_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return VPHO_ERR_LAUNCH;
-    attr = true;
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    n_sm_of[dev] = n > 0 ? n : 148;
+    attr[dev] = true;
   }
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (n_sm <= 0) n_sm = 148;
-  }
-  if (n_jobs < 1 || n_jobs > 2 || (ctas == 2 && !half)) return VPHO_ERR_INVALID;
+  const int n_sm = n_sm_of[dev];
+  if (n_jobs < 1 || n_jobs > 2 || (ctas != 1 && ctas != 2)) return VPHO_ERR_INVALID;
   const TcHeadJob& j0 = jobs[0];
   const TcHeadJob& j1 = jobs[n_jobs - 1];
   int n_items = 0;
@@ -1141,45 +962,24 @@ int tc_launch_head(const TcHeadJob* jobs, int n_jobs, int mode, int s, bool half
   auto M = [](const void* p) -> const CUtensorMap& { return *static_cast<const CUtensorMap*>(p); };
   cudaError_t e;
   if (ctas == 2)
-    e = launch_pdl(k_head_tc<true, 2>, dim3(2 * units), dim3(kHeadThreads), smem, st, 2, M(j0.mapA_hi), M(j0.mapA_lo), M(j0.mapB_hi),
-                   M(j0.mapB_lo), M(j1.mapA_hi), M(j1.mapA_lo), M(j1.mapB_hi), M(j1.mapB_lo), *j0.dn, *j0.ws, *j1.dn, *j1.ws, n_jobs,
-                   mode, s);
-  else if (half)
-    e = launch_pdl(k_head_tc<true, 1>, dim3(units), dim3(kHeadThreads), smem, st, 1, M(j0.mapA_hi), M(j0.mapA_lo), M(j0.mapB_hi),
+    e = launch_pdl(k_head_tc<2>, dim3(2 * units), dim3(kHeadThreads), smem, st, 2, M(j0.mapA_hi), M(j0.mapA_lo), M(j0.mapB_hi),
                    M(j0.mapB_lo), M(j1.mapA_hi), M(j1.mapA_lo), M(j1.mapB_hi), M(j1.mapB_lo), *j0.dn, *j0.ws, *j1.dn, *j1.ws, n_jobs,
                    mode, s);
   else
-    e = launch_pdl(k_head_tc<false, 1>, dim3(units), dim3(kHeadThreads), smem, st, 1, M(j0.mapA_hi), M(j0.mapA_lo), M(j0.mapB_hi),
+    e = launch_pdl(k_head_tc<1>, dim3(units), dim3(kHeadThreads), smem, st, 1, M(j0.mapA_hi), M(j0.mapA_lo), M(j0.mapB_hi),
                    M(j0.mapB_lo), M(j1.mapA_hi), M(j1.mapA_lo), M(j1.mapB_hi), M(j1.mapB_lo), *j0.dn, *j0.ws, *j1.dn, *j1.ws, n_jobs,
                    mode, s);
   return e == cudaSuccess ? VPHO_OK : VPHO_ERR_LAUNCH;
 }
 
-
-int tc_launch_feat(const void* mapA_hi, const void* mapA_lo, const void* mapB_hi, const void* mapB_lo, const float* feat,
-                   float* feat_hi, float* feat_lo, const float* ba, float* F, int R, int hid, cudaStream_t st) {
-  static bool attr = false;
-  const int smem = (int)sizeof(TcSmem) + 1024;
-  if (!attr) {
-    if (cudaFuncSetAttribute(k_feat_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return VPHO_ERR_LAUNCH;
-    attr = true;
-  }
-  const int n_src = R * kFDim, n = ((R + kTcBM - 1) / kTcBM) * kTcBM * kFDim;
-  VPHO_LAUNCH(k_split_planes, dim3((n + 1023) / 1024), dim3(256), 0, st, feat, feat_hi, feat_lo, n_src, n);
-  const int n_items = (hid / kTcBN) * ((R + kTcBM - 1) / kTcBM);
-  VPHO_LAUNCH(k_feat_tc, dim3(n_items < 148 ? n_items : 148), dim3(kTcThreads), smem, st, *static_cast<const CUtensorMap*>(mapA_hi),
-              *static_cast<const CUtensorMap*>(mapA_lo), *static_cast<const CUtensorMap*>(mapB_hi),
-              *static_cast<const CUtensorMap*>(mapB_lo), ba, F, R, hid);
-  VPHO_CHECK_LAUNCH();
-  return VPHO_OK;
-}
-
 int tc_launch_pose(const TcPoseJob* jobs, int n_jobs, int mode, int s, cudaStream_t st) {
-  static bool attr = false;
   const int smem = (int)sizeof(PtSmem) + 1024;
-  if (!attr) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return VPHO_ERR_LAUNCH;
+  static bool attr[kMaxDevices] = {};
+  if (!attr[dev]) {
     if (cudaFuncSetAttribute(k_pose_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return VPHO_ERR_LAUNCH;
-    attr = true;
+    attr[dev] = true;
   }
   if (n_jobs < 1 || n_jobs > 2) return VPHO_ERR_INVALID;
   const TcPoseJob& j0 = jobs[0];

@@ -33,7 +33,11 @@ def ve_prior_std(T: float) -> float:
 class Denoiser:
     """Packed score network on the device.  `state` uses the reference's state-dict keys (denoiser.py:33-66)."""
 
-    def __init__(self, state: Dict[str, object], lib: Optional[capi.Library] = None):
+    STRICT_FP32 = 1      # VPHO_DENOISER_STRICT_FP32 (include/vpho_b200.h)
+
+    def __init__(self, state: Dict[str, object], lib: Optional[capi.Library] = None, strict_fp32: bool = False):
+        """strict_fp32: FP32 SIMT kernels instead of the tcgen05 path (used to cross-check the tensor-core kernels).  The
+        path is fixed at creation; creation FAILS when the tensor-core resources cannot be built (no silent downgrade)."""
         self.lib = lib or capi.lib()
         arrs = []
         for k in _KEYS:
@@ -46,8 +50,9 @@ class Denoiser:
         self.n_heads = n
         self.out_dim = 3 * n
         h = C.c_void_p()
-        self.lib.check(self.lib.c.vpho_denoiser_create(n, *[capi.host_ptr(a) for a in arrs], C.byref(h)),
-                       "vpho_denoiser_create")
+        self.lib.check(self.lib.c.vpho_denoiser_create_ex(n, *[capi.host_ptr(a) for a in arrs],
+                                                         self.STRICT_FP32 if strict_fp32 else 0, C.byref(h)),
+                       "vpho_denoiser_create_ex")
         self.handle = h
         self._ws: Dict[tuple, torch.Tensor] = {}
         self.calls = 0   # network evaluations issued by the last sample() (nfev + 1)
@@ -121,13 +126,30 @@ class PendingSample:
         if c[0] < 0:
             raise capi.VphoError("RK45: required step size is less than spacing between numbers")
         if c[0] == 0:
-            self.denoiser.attempts_hint = max(self.attempts_enqueued, c[5]) + 4
+            if getattr(self, "pair", None) is None:     # stand-alone deferred sample(): the caller re-issues with a larger budget
+                self.denoiser.attempts_hint = max(self.attempts_enqueued, c[5]) + 4
             return False
         if c[4]:
             print("\033[31mWarning: NaN detected in score evaluation. \033[0m")   # score_based_model.py:70
         # steady state: enqueue what the last batch needed plus one spare attempt (20 no-op launches)
         self.denoiser.attempts_hint = max(1, c[5]) + (1 if self.agent.spare_attempt else 0)
         return True
+
+
+class PendingPair:
+    """Two samplers advancing in lock-step on the same workspaces.  `advance(n)` enqueues `n` more RK attempts for both
+    (`vpho_sample_pair_continue`; a finished integration ignores them) followed by the final predictor step
+    (`vpho_sample_pair_finish`, which runs only for an integration that has reached t = eps)."""
+
+    def __init__(self, lib, args_a, args_b, pendings):
+        self.lib, self.args_a, self.args_b, self.pendings = lib, args_a, args_b, pendings
+
+    def advance(self, attempts: int, stream) -> None:
+        pa, pb = C.byref(self.args_a), C.byref(self.args_b)
+        self.lib.check(self.lib.c.vpho_sample_pair_continue(pa, pb, int(attempts), stream), "vpho_sample_pair_continue")
+        self.lib.check(self.lib.c.vpho_sample_pair_finish(pa, pb, stream), "vpho_sample_pair_finish")
+        for p in self.pendings:
+            p.attempts_enqueued += int(attempts)
 
 
 class ScoreBasedModelAgent:
@@ -223,7 +245,9 @@ class ScoreBasedModelAgent:
             ws = den.workspace(n_rows, rpf, n_eval, device)
             xs = (torch.empty((n_eval, n_rows, D), dtype=torch.float32 if f32 else torch.float64, device=device)
                   if return_inprocess else None)
-            x = torch.empty((n_rows, D), dtype=torch.float64, device=device)
+            # zeros, not empty: the final predictor step writes `x` only once the integration has reached t = eps, and
+            # the speculative downstream work of `VphoHotPath.predict` must never consume uninitialised memory
+            x = torch.zeros((n_rows, D), dtype=torch.float64, device=device)
             counters = torch.zeros(8, dtype=torch.int32, device=device)
             args = capi.SampleArgs(den.handle, capi.ptr(feat), n_rows, rpf, capi.ptr(x0), float(T0), float(self.sampling_eps),
                                    None, n_eval, RTOL, ATOL, MAX_STEP, n_eval, capi.ptr(None if f32 else xs), capi.ptr(x),
@@ -232,7 +256,6 @@ class ScoreBasedModelAgent:
         lib = denoiser_a.lib
         stream = capi.stream_of(jobs[0][3])
         hint = max((getattr(j[0], "attempts_hint", None) or self.first_attempts) for j in jobs)
-        import ctypes as C
         pa, pb = C.byref(jobs[0][1]), C.byref(jobs[1][1])
         lib.check(lib.c.vpho_sample_pair_begin(pa, pb, hint, stream), "vpho_sample_pair_begin")
         lib.check(lib.c.vpho_sample_pair_finish(pa, pb, stream), "vpho_sample_pair_finish")
@@ -240,6 +263,8 @@ class ScoreBasedModelAgent:
         for den, args, xs, x, counters, n_rows, keep in jobs:
             pending = PendingSample(self, den, counters, n_rows, hint, keep)
             out.append((None if xs is None else xs.permute(1, 0, 2), x, pending))
+        pair = PendingPair(lib, jobs[0][1], jobs[1][1], (out[0][2], out[1][2]))
+        out[0][2].pair = out[1][2].pair = pair
         return out[0], out[1]
 
     def get_score(self, data, denoiser):

@@ -8,8 +8,6 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
-import os
-
 import torch
 
 from . import capi
@@ -38,12 +36,8 @@ class VphoHotPath:
         self.score_agent = ScoreBasedModelAgent(sampling_steps=sampling_steps, sample_num=sample_num)
         self.hoi_aggregator = HOI_Aggregator(self.head_mano, self.assets, debug=debug)
         self.last_info: dict = {}
-        self.overlap_object_sampler = True
-        self._side_stream = None
         self._side_stream2 = None
-        self.pair_samplers = os.environ.get("VPHO_PAIR_SAMPLERS", "1") != "0"
         self._agg_stream = None
-        self.aggregate_priority = os.environ.get("VPHO_AGG_PRIORITY", "1") != "0"
 
     # ---- vpho_net.postprocess_diffusion_hand, branch 'mano_pose' (VPHO.py:306-331) ----
     def postprocess_diffusion_hand(self, hand_inprocess, hand_final, pd_mano_shape):
@@ -74,11 +68,14 @@ class VphoHotPath:
     @torch.no_grad()
     def predict(self, batch: Dict, *, prior_hand: Optional[torch.Tensor] = None, prior_obj: Optional[torch.Tensor] = None,
                 with_inprocess: bool = True, prefetch=None) -> Dict:
-        """The whole batch is enqueued without a host synchronisation; the two samplers' status words are read once at
-        the end.  If an integration needed more RK attempts than were enqueued (the hint adapts to the previous batch,
-        plus one spare), the batch is re-issued with a larger budget -- rare, and the results are identical."""
+        """The whole batch (both samplers, MANO, scoring, aggregation) is enqueued without a host synchronisation and the
+        two samplers' status words are read once at the end.  The number of RK attempts enqueued up front adapts to the
+        previous batch (what it needed plus one spare).  If an integration needed more, it is CONTINUED on the same
+        workspaces (`vpho_sample_pair_continue` + `_finish`, as the reference's solve_ivp simply keeps stepping) until both
+        controllers report completion -- there is no attempt cap -- and only then is the downstream work enqueued again on
+        the now valid samples.  Results are identical either way."""
         if prior_hand is None or prior_obj is None:
-            # draw both priors up front, in the reference's order (hand, then object), so a re-issue reuses them
+            # draw both priors up front, in the reference's order (hand, then object)
             from .score_based_model import ve_prior_std
             S, bs = self.sample_num, batch["encoding_hand"].shape[0]
             if prior_hand is None:
@@ -86,62 +83,54 @@ class VphoHotPath:
             if prior_obj is None:
                 prior_obj = torch.randn(bs * S, self.denoiser_obj.out_dim) * ve_prior_std(self.sample_T0)
         self.score_agent.spare_attempt = True
+        S = self.sample_num
+        enc_h, enc_o = batch["encoding_hand"], batch["encoding_obj"]
+        bs = enc_h.shape[0]
+        # The hand and the object integrations issue the same sequence of network calls: they advance in lock-step
+        # through shared kernel launches (`sample_pair`), the object's work items filling the SMs the hand's leave idle.
+        samples = self.score_agent.sample_pair(
+            {"feat_unique": enc_h, "n_rows": bs * S}, self.denoiser_hand, {"feat_unique": enc_o, "n_rows": bs * S},
+            self.denoiser_obj, self.sample_T0, return_inprocess=with_inprocess, prior_a=prior_hand, prior_b=prior_obj,
+            inprocess_float32=(True, False))      # the hand trajectory is only ever used as float32 (VPHO.py:243)
+        pend = (samples[0][2], samples[1][2])
         issue = 0
-        for _ in range(8):
-            pd, pend = self._predict_once(batch, prior_hand, prior_obj, with_inprocess)
+        while True:
+            pd = self._downstream(batch, samples, with_inprocess)      # speculative on the first pass
             if prefetch is not None:
                 # caller hook `prefetch(pd, issue)`, run after the batch is enqueued and before the host blocks on its
                 # status: the place to enqueue device-to-host reads of `pd` (stream-ordered behind the aggregation, complete
                 # when predict returns) and, for issue == 0, the next batch's host-to-device copies on another stream.
-                # A re-issued batch (issue > 0, rare) calls it again with the new outputs.
+                # When the samplers had to be continued (issue > 0, rare) it is called again with the new outputs.
                 prefetch(pd, issue)
             issue += 1
-            status = torch.stack([p.counters for p in pend]).cpu().tolist()     # the one host sync of the batch
-            ok = [p.resolve(c) for p, c in zip(pend, status)]
-            self.last_info = {"hand": pend[0].info, "obj": pend[1].info}
-            if all(ok):
+            done = self._await(pend)                                   # the one host sync of the batch
+            if done:
                 return pd
-        raise capi.VphoError("sampler did not converge within the attempt budget")
+            # slow path: keep stepping both integrations until they finish, then redo the downstream work once
+            stream = capi.stream_of(samples[0][1])
+            while not done:
+                pend[0].pair.advance(4, stream)
+                done = self._await(pend)
 
-    def _predict_once(self, batch: Dict, prior_hand, prior_obj, with_inprocess: bool):
-        """batch: tensors on the CUDA device (see `to_device`).  prior_* (optional): randn*sigma(T0) draws, (bs*S, 96) and
-        (bs*S, 9); when omitted they are drawn from torch's global CPU generator in the reference's order (hand, object)."""
+    def _await(self, pend) -> bool:
+        status = torch.stack([p.counters for p in pend]).cpu().tolist()
+        ok = [p.resolve(c) for p, c in zip(pend, status)]
+        self.last_info = {"hand": pend[0].info, "obj": pend[1].info}
+        return all(ok)
+
+    def _downstream(self, batch: Dict, samples, with_inprocess: bool) -> Dict:
+        """Everything after the two `sample()` calls of the predict branch (VPHO.py:243-304).  batch: tensors on the CUDA
+        device (see `to_device`)."""
         S = self.sample_num
-        enc_h, enc_o = batch["encoding_hand"], batch["encoding_obj"]
+        (xs_h, x_h, _), (xs_o, x_o, _) = samples
+        enc_h = batch["encoding_hand"]
         bs = enc_h.shape[0]
         pd_mano_pose, pd_mano_shape = batch["pd_mano_pose"], batch["pd_mano_shape"]
         pd = {"hand_heatmap": batch["hm_hand"], "obj_heatmap": batch["hm_obj"], "force_local": batch["force_local"]}
-
-        # The hand and the object integrations issue the same sequence of network calls: they advance in lock-step
-        # through shared kernel launches (`sample_pair`), the object's work items filling the SMs the hand's leave idle.
         main = torch.cuda.current_stream(enc_h.device) if enc_h.is_cuda else None
-        side = None
-        paired = main is not None and self.overlap_object_sampler and self.pair_samplers
-        if paired:
-            (xs_h, x_h, pend_h), (xs_o, x_o, pend_o) = self.score_agent.sample_pair(
-                {"feat_unique": enc_h, "n_rows": bs * S}, self.denoiser_hand, {"feat_unique": enc_o, "n_rows": bs * S},
-                self.denoiser_obj, self.sample_T0, return_inprocess=with_inprocess, prior_a=prior_hand, prior_b=prior_obj,
-                inprocess_float32=(True, False))      # the hand trajectory is only ever used as float32 (VPHO.py:243)
-        else:
-            # fallback: the object sampler on a side stream (VPHO_PAIR_SAMPLERS=0), or after the hand's on the same stream
-            if main is not None and self.overlap_object_sampler:
-                if self._side_stream is None:
-                    self._side_stream = torch.cuda.Stream(device=enc_h.device)
-                side = self._side_stream
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    xs_o, x_o, pend_o = self.score_agent.sample({"feat_unique": enc_o, "n_rows": bs * S}, self.denoiser_obj,
-                                                                self.sample_T0, return_inprocess=with_inprocess,
-                                                                prior=prior_obj, defer_check=True)
-                for t in (xs_o, x_o, pend_o.counters):
-                    if t is not None:
-                        t.record_stream(main)
-            xs_h, x_h, pend_h = self.score_agent.sample({"feat_unique": enc_h, "n_rows": bs * S}, self.denoiser_hand,
-                                                        self.sample_T0, return_inprocess=with_inprocess, prior=prior_hand,
-                                                        defer_check=True)
         # The aggregator needs only the final hand poses.  Everything else computed from the hand sampler's output is
         # output-only (the in-process trajectory for visualisation, the 6400 posed meshes of the candidates): it runs on a
-        # second side stream, concurrently with the aggregation.
+        # side stream, concurrently with the aggregation.
         _, final_mano = self.postprocess_diffusion_hand(None, x_h, pd_mano_shape)
         pd["diff_final_hand_mano"] = final_mano.reshape(bs, S, 58)
 
@@ -157,7 +146,7 @@ class VphoHotPath:
             pd["diff_final_hand_joint"] = fj.reshape(bs, S, 21, 3)
 
         side2 = None
-        if main is not None and self.overlap_object_sampler:
+        if main is not None:
             if self._side_stream2 is None:
                 self._side_stream2 = torch.cuda.Stream(device=enc_h.device)
             side2 = self._side_stream2
@@ -174,14 +163,6 @@ class VphoHotPath:
         else:
             output_only_work()
 
-        if paired:
-            pass
-        elif side is None:
-            xs_o, x_o, pend_o = self.score_agent.sample({"feat_unique": enc_o, "n_rows": bs * S}, self.denoiser_obj,
-                                                        self.sample_T0, return_inprocess=with_inprocess, prior=prior_obj,
-                                                        defer_check=True)
-        else:
-            main.wait_stream(side)
         if with_inprocess:
             pd["diff_inprocess_obj_6d"] = xs_o.reshape(bs, S, -1, 9)
         pd["diff_final_obj_6d"] = x_o.reshape(bs, S, 9)
@@ -199,7 +180,7 @@ class VphoHotPath:
         # The aggregation is a chain of short kernels on the critical path; the output-only stream floods the GPU with
         # the 6400 candidate meshes at the same time.  Running the chain on a high-priority stream lets its CTAs be
         # placed ahead of the pending mesh CTAs whenever SM slots free up.
-        if side2 is not None and self.aggregate_priority:
+        if side2 is not None:
             if self._agg_stream is None:
                 self._agg_stream = torch.cuda.Stream(device=enc_h.device, priority=-1)
             hs = self._agg_stream
@@ -219,7 +200,7 @@ class VphoHotPath:
         pd["_sel"] = sel
         if side2 is not None:
             main.wait_stream(side2)
-        return pd, (pend_h, pend_o)
+        return pd
 
     __call__ = predict
 
@@ -233,6 +214,8 @@ def to_device(batch: Dict, device="cuda", non_blocking: bool = True) -> Dict:
         if isinstance(v, np.ndarray):
             v = torch.from_numpy(v)
         if isinstance(v, torch.Tensor):
+            if k == "obj_id":
+                v = v.to(torch.int32)          # the kernels read `const int32_t*`
             out[k] = v.to(device, non_blocking=non_blocking)
         else:
             out[k] = v

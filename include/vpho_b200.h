@@ -190,6 +190,30 @@ int vpho_pose_metrics(vpho_assets_t h, const float* pd_joint, const float* gt_jo
                       const float* gt_vert, const double* pd_obj6d, const double* gt_obj6d, const int32_t* obj_id, int n,
                       float* metrics, void* stream);
 
+/* The whole per-image row of `TesterHand.__call__` (lib/engine/test.py:589-654), in millimetres:
+ * metrics [n][25] = {MJE, PA_MJE, MVE, PAMVE, JE[21]} for one prediction per image. */
+int vpho_hand_metrics(const float* pd_joint, const float* gt_joint, const float* pd_vert, const float* gt_vert, int n,
+                      float* metrics, void* stream);
+
+/* Object-pose metrics of `TesterObject` (lib/engine/test.py:196-584) per (image, candidate), on the device -- what
+ * Trainer.evaluate computes from `diff_final_obj_rt` / `agg_obj_rt` on the host (lib/engine/train_diff_hand_obj.py:249-257).
+ * Tables (HOST pointers): bbox3d [n_obj][8][3] and diameter [n_obj] (YCB_MESHES[name]['bbox3d' / 'diameter']), the padded
+ * symmetry transforms of TesterObject.__init__ (test.py:208-232) sym_R [n_obj][sym_k][3][3], sym_t [n_obj][sym_k][3] in
+ * metres, sym_count [n_obj] (may be NULL), and the cloud of the F-score / Chamfer terms fverts [n_obj][n_fpts][3]
+ * (NULL: the assets' sampled surface, as `verts_sampled`).
+ * vpho_object_metrics: pd_rt [n][C][3][4], gt_rt [n][3][4] float64 ([R | t] rows), obj_id [n], cam_intr [n][3][3] ->
+ * out [n][C][VPHO_OBJ_METRIC_COLS] float64 = MCE, OCE, MCE2, SMCE, ADD, ADD-S (m), REP (px), CD (m),
+ * FSCORE@{2,5,10 mm, 2,5,10 cm}, ADD01d, ADDS01d, REP5 (0/1).  Replaces criterion_MCE_OCE :354-375, criterion_SMCE
+ * :377-399, criterion_MCE2 :401-417, criterion_ADD_REP :419-451, criterion_FSCORE :453-503, cal_ADD01d / cal_REP5 :505-521. */
+#define VPHO_OBJ_METRIC_COLS 17
+typedef void* vpho_objmetrics_t;
+int vpho_objmetrics_create(int n_obj, const float* bbox3d, const float* diameter, int sym_k, const double* sym_R,
+                           const double* sym_t, const int32_t* sym_count, int n_fpts, const float* fverts,
+                           vpho_objmetrics_t* out);
+int vpho_objmetrics_destroy(vpho_objmetrics_t h);
+int vpho_object_metrics(vpho_assets_t assets, vpho_objmetrics_t tables, const double* pd_rt, const double* gt_rt,
+                        const int32_t* obj_id, const float* cam_intr, int n, int C, double* out, void* stream);
+
 /* Procrustes-aligned hand errors per image, in millimetres: metrics [n][23] = {PA-MJE, PA-MVE, JE[21]} of
  * `TesterHand.criterion_MJE_PAMJE` (lib/engine/test.py:657-679): the prediction is aligned to the ground truth by the
  * similarity transform of `rigid_align_AtoB` (lib/utils/transform_fn.py:43-66; SVD of the 3x3 cross-covariance, reflection

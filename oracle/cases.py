@@ -73,3 +73,20 @@ def e2e_priors(kind: str, bs: int, S: int, batch: dict, seed: int):
     rot = T("true_obj_rot")[:, None, :2, :].reshape(bs, 1, 6) + 0.1 * torch.randn(bs, S, 6, generator=g)
     tr = T("true_obj_trans")[:, None] + 0.02 * torch.randn(bs, S, 3, generator=g)
     return ph.float().contiguous(), torch.cat([rot, tr], -1).reshape(bs * S, 9).float().contiguous()
+
+
+def object_metric_case(n: int = 6, C: int = 5, seed: int = 11):
+    """Seeded inputs of the object-metric fixture: ground-truth poses in front of the camera, candidates scattered around
+    them from near-exact to far off (so every F-score threshold and both 0.1-diameter flags see both outcomes)."""
+    from scipy.spatial.transform import Rotation as Rot
+    rng = np.random.default_rng(seed)
+    R_gt = Rot.random(n, random_state=int(rng.integers(1 << 30))).as_matrix()
+    t_gt = rng.normal(size=(n, 3)) * 0.05 + np.array([0.02, -0.03, 0.6])
+    gt = np.concatenate([R_gt, t_gt[..., None]], -1)
+    spread = np.array([1e-3, 0.02, 0.1, 0.4, 1.5])[:C]
+    d = Rot.from_rotvec((rng.normal(size=(n, C, 3)) * spread[None, :, None]).reshape(-1, 3)).as_matrix().reshape(n, C, 3, 3)
+    tt = t_gt[:, None] + rng.normal(size=(n, C, 3)) * (spread[None, :, None] * 0.05)
+    pd = np.concatenate([d @ R_gt[:, None], tt[..., None]], -1)
+    ids = np.array([0, 1, 2, 5, 20, 8][:n], np.int32)
+    K = np.tile(np.array([[600.0, 0, 128], [0, 610.0, 126], [0, 0, 1]], np.float32), (n, 1, 1))
+    return {"pd_rt": pd, "gt_rt": gt, "obj_id": ids, "cam_intr": K}

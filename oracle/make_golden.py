@@ -29,11 +29,43 @@ from oracle.reference_loader import load_reference  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
+def object_metrics_fixture(ref, objs):
+    """TesterObject's own criteria (lib/engine/test.py:354-521), called per image exactly as TesterObject.__call__ does
+    (:250-279), on seeded poses.  `.cuda()` is a no-op here (no GPU in the build container) and torch.cdist runs in the
+    exact mode (oracle rule 0)."""
+    inp = cases.object_metric_case()
+    T = ref.tester_object
+    names = [objs["names"][i] for i in inp["obj_id"]]
+    _cuda, _cd = torch.Tensor.cuda, torch.cdist
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.cdist = lambda a, b, p=2.0, compute_mode=None: _cd(a, b, p=p, compute_mode="donot_use_mm_for_euclid_dist")
+    rows = []
+    try:
+        for i, nm in enumerate(names):
+            pd, gt, K = inp["pd_rt"][i], inp["gt_rt"][i], inp["cam_intr"][i]
+            mce, oce = T.criterion_MCE_OCE(pd, gt, nm)
+            smce = T.criterion_SMCE(pd, gt, nm)
+            mce2 = np.array([T.criterion_MCE2(pd[c], gt, nm) for c in range(pd.shape[0])]).reshape(-1)
+            add, adds, rep = T.criterion_ADD_REP(pd, gt, nm, K)
+            fs, cd = T.criterion_FSCORE(pd, gt, nm)
+            a01, s01 = T.cal_ADD01d(add, adds, nm)
+            rows.append(np.stack([mce, oce, mce2, smce, add, adds, rep, cd] +
+                                 [fs[k] for k in ("FSCORE@2mm", "FSCORE@5mm", "FSCORE@10mm", "FSCORE@2cm", "FSCORE@5cm", "FSCORE@10cm")] +
+                                 [a01, s01, T.cal_REP5(rep)], -1).astype(np.float64))
+    finally:
+        torch.Tensor.cuda, torch.cdist = _cuda, _cd
+    np.savez_compressed(os.path.join(OUT, "object_metrics.npz"), metrics=np.stack(rows), fp=cases.fingerprint(inp["pd_rt"], inp["gt_rt"]))
+    print("object_metrics", np.stack(rows).shape)
+
+
 def main():
     torch.set_num_threads(8)
     mano, anch, objs = cases.assets()
     ref = load_reference(mano, anch, objs)
     os.makedirs(OUT, exist_ok=True)
+    object_metrics_fixture(ref, objs)
+    if "--only-object-metrics" in sys.argv:
+        return
     _, marg, sde_fn, eps, T = ref.sde.init_sde("ve")
     agent = ref.sbm.ScoreBasedModelAgent()
 

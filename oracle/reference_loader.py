@@ -9,7 +9,8 @@ What is shimmed: `ipdb`, `pytorch3d.transforms`, `pytorch3d.ops
 (oracle/shims/*), a fake `lib.dataset.base` exposing `YCB_MESHES`, `sys.argv` for lib/configs/args.py, and
 a temporary CWD holding synthetic `asset/ours/vert2joint.pkl` + `asset/2021_CVPR_CPF/anchor/*`.
 Files executed verbatim from the reference: lib/model/{sde,parallel_linear,denoiser,score_based_model,
-aggregation,head_mano,head_object,physics}.py, lib/utils/{hand_fn,physics_fn,transform_fn}.py, lib/configs/args.py.
+aggregation,head_mano,head_object,physics}.py, lib/utils/{hand_fn,physics_fn,transform_fn}.py, lib/configs/args.py,
+lib/engine/test.py (TesterObject, with a synthetic asset/2023_NIPS_DeepSimHO/assets_models_info.json).
 """
 from __future__ import annotations
 
@@ -60,13 +61,23 @@ def load_reference(mano: dict, anchors: dict, objects: dict, *, sample_num=100, 
             pickle.dump({}, f)
         os.chdir(tmp)
 
+        # tables TesterObject reads (lib/engine/test.py:196-232): box corners, diameter, symmetry info (synthetic)
+        import json
+        from oracle.object_metrics import synthetic_metric_tables
+        mt = synthetic_metric_tables(objects)
+        os.makedirs(os.path.join(tmp, "asset", "2023_NIPS_DeepSimHO"))
+        with open(os.path.join(tmp, "asset", "2023_NIPS_DeepSimHO", "assets_models_info.json"), "w") as f:
+            json.dump({str(i + 1): mi for i, mi in enumerate(mt["model_info"])}, f)
         base = types.ModuleType("lib.dataset.base")
         ycb = {}
         for i, n in enumerate(objects["names"]):
             ycb[n] = {"kpt3d": np.asarray(objects["kpt3d"][i]), "shift": np.eye(4)[:3],
                       "verts_sampled": np.asarray(objects["verts_sampled"][i]),
-                      "CoM": np.asarray(objects["CoM"][i]), "verts": np.asarray(objects["verts_sampled"][i])}
+                      "CoM": np.asarray(objects["CoM"][i]), "verts": np.asarray(objects["verts_sampled"][i]),
+                      "bbox3d": np.asarray(mt["bbox3d"][i]), "diameter": float(mt["diameter"][i])}
         base.YCB_MESHES = ycb
+        base.YCB_CLASSES = {i + 1: n for i, n in enumerate(objects["names"])}
+        base.YCB_ID = {n: i + 1 for i, n in enumerate(objects["names"])}
         sys.modules["lib.dataset.base"] = base
 
         import manopth.manolayer as shim_mano  # noqa: E402  (oracle/shims)
@@ -83,11 +94,13 @@ def load_reference(mano: dict, anchors: dict, objects: dict, *, sample_num=100, 
         import lib.utils.hand_fn as ref_hand_fn
         import lib.utils.physics_fn as ref_physics_fn
         from lib.configs.args import cfg
+        import lib.engine.test as ref_test                # TesterObject / TesterHand (reads the json above at construction)
+        tester_object = ref_test.TesterObject()
     finally:
         os.chdir(cwd)
         sys.argv = argv
     _loaded = SimpleNamespace(sde=ref_sde, denoiser=ref_denoiser, sbm=ref_sbm, head_mano=ref_head_mano,
                               head_object=ref_head_object, physics=ref_physics, aggregation=ref_aggregation,
                               transform_fn=ref_transform_fn, hand_fn=ref_hand_fn, physics_fn=ref_physics_fn,
-                              cfg=cfg, asset_dir=tmp)
+                              cfg=cfg, asset_dir=tmp, test=ref_test, tester_object=tester_object, metric_tables=mt)
     return _loaded

@@ -265,3 +265,68 @@ def pose_metrics(assets: Assets, pd_joint, gt_joint, pd_vert, gt_vert, pd_obj6d,
     lib.check(lib.c.vpho_pose_metrics(assets.handle, capi.ptr(pj), capi.ptr(gj), capi.ptr(pv), capi.ptr(gv), capi.ptr(po),
                                       capi.ptr(go), capi.ptr(ids), n, capi.ptr(out), capi.stream_of(pj)), "vpho_pose_metrics")
     return out
+
+
+OBJ_METRIC_COLS = ("MCE", "OCE", "MCE2", "SMCE", "ADD", "ADDS", "REP", "CD", "FSCORE@2mm", "FSCORE@5mm", "FSCORE@10mm",
+                   "FSCORE@2cm", "FSCORE@5cm", "FSCORE@10cm", "ADD01d", "ADDS01d", "REP5")
+
+
+class ObjectMetrics:
+    """`TesterObject` (lib/engine/test.py:196-584) on the device: every per-candidate object metric of the reference's
+    evaluate loop in one launch.  tables: bbox3d (n_obj,8,3), diameter (n_obj,), sym_R (n_obj,K,3,3), sym_t (n_obj,K,3)
+    [metres, already padded with identities as TesterObject.__init__ does], optional sym_count, optional `verts`
+    (n_obj,Q,3) for the F-score / Chamfer terms (default: the assets' sampled surface)."""
+
+    def __init__(self, assets: Assets, tables: Dict[str, np.ndarray]):
+        self.assets, self.lib = assets, assets.lib
+        box = np.ascontiguousarray(tables["bbox3d"], dtype=np.float32).reshape(assets.n_obj, 8, 3)
+        diam = np.ascontiguousarray(tables["diameter"], dtype=np.float32).reshape(assets.n_obj)
+        sR = np.ascontiguousarray(tables["sym_R"], dtype=np.float64)
+        K = sR.shape[1]
+        st = np.ascontiguousarray(tables["sym_t"], dtype=np.float64).reshape(assets.n_obj, K, 3)
+        cnt = tables.get("sym_count")
+        cnt = None if cnt is None else np.ascontiguousarray(cnt, dtype=np.int32)
+        fv = tables.get("verts_full")
+        fv = None if fv is None else np.ascontiguousarray(fv, dtype=np.float32)
+        h = C.c_void_p()
+        self.lib.check(self.lib.c.vpho_objmetrics_create(
+            assets.n_obj, capi.host_ptr(box), capi.host_ptr(diam), K, capi.host_ptr(sR), capi.host_ptr(st),
+            None if cnt is None else capi.host_ptr(cnt), 0 if fv is None else fv.shape[1],
+            None if fv is None else capi.host_ptr(fv), C.byref(h)), "vpho_objmetrics_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.c.vpho_objmetrics_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def __call__(self, pd_rt: torch.Tensor, gt_rt: torch.Tensor, obj_name, cam_intr: torch.Tensor) -> torch.Tensor:
+        """pd_rt (n, C, 3, 4) or (n, 3, 4), gt_rt (n, 3, 4), cam_intr (n, 3, 3) -> (n, C, 17) float64 (`OBJ_METRIC_COLS`)."""
+        squeeze = pd_rt.dim() == 3
+        pd = (pd_rt[:, None] if squeeze else pd_rt).contiguous().double()
+        gt = gt_rt.contiguous().double()
+        n, Cn, dev = pd.shape[0], pd.shape[1], pd.device
+        K = cam_intr.contiguous().float()
+        ids = self.assets.ids(obj_name, dev)
+        out = torch.empty((n, Cn, len(OBJ_METRIC_COLS)), dtype=torch.float64, device=dev)
+        self.lib.check(self.lib.c.vpho_object_metrics(self.assets.handle, self.handle, capi.ptr(pd), capi.ptr(gt),
+                                                      capi.ptr(ids, torch.int32), capi.ptr(K), n, Cn, capi.ptr(out),
+                                                      capi.stream_of(pd)), "vpho_object_metrics")
+        return out[:, 0] if squeeze else out
+
+
+def obj_6d_to_rt(pose6d: torch.Tensor, root_joint: torch.Tensor) -> torch.Tensor:
+    """`Trainer.__postprocess_obj_rt` (lib/engine/train_diff_hand_obj.py:593-596): (bs, ..., 9) rot6d + translation ->
+    (bs, ..., 3, 4) [R | t + root_joint]; tensor glue in the input dtype (Gram-Schmidt of pytorch3d's
+    rotation_6d_to_matrix)."""
+    a1, a2 = pose6d[..., :3], pose6d[..., 3:6]
+    b1 = torch.nn.functional.normalize(a1, dim=-1)
+    b2 = torch.nn.functional.normalize(a2 - (b1 * a2).sum(-1, keepdim=True) * b1, dim=-1)
+    b3 = torch.cross(b1, b2, dim=-1)
+    R = torch.stack((b1, b2, b3), dim=-2)
+    rj = root_joint.reshape(root_joint.shape[0], *([1] * (pose6d.dim() - 2)), 3).to(pose6d.dtype)
+    t = pose6d[..., 6:] + rj
+    return torch.cat([R, t[..., None]], dim=-1)

@@ -82,6 +82,11 @@ _SIGNATURES = {
     "vpho_vertex_contact": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vpho_force_eval": (c_int, [c_void_p] * 9 + [c_int, c_int] + [c_void_p] * 5),
     "vpho_pose_metrics": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p]),
+    "vpho_hand_metrics": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_void_p]),
+    "vpho_objmetrics_create": (c_int, [c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                       C.POINTER(c_void_p)]),
+    "vpho_objmetrics_destroy": (c_int, [c_void_p]),
+    "vpho_object_metrics": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "vpho_hand_pa_metrics": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_void_p]),
     "vpho_hoi_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vpho_hoi_aggregate": (c_int, [c_void_p, c_void_p, C.POINTER(HoiArgs), c_void_p, c_size_t, c_void_p]),

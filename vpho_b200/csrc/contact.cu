@@ -393,20 +393,38 @@ __device__ __forceinline__ double aligned_error(const float* a, const float* b, 
   return sqrt(e2);
 }
 
-// out [n][23] = {PA-MJE, PA-MVE, JE[21]} in mm
+// full = 0: out [n][23] = {PA-MJE, PA-MVE, JE[21]} in mm;  full = 1: out [n][25] = {MJE, PA-MJE, MVE, PA-MVE, JE[21]}, the whole
+// per-image row of TesterHand.__call__ (lib/engine/test.py:589-654)
 __global__ void __launch_bounds__(256) k_hand_pa_metrics(const float* __restrict__ pd_joint, const float* __restrict__ gt_joint,
                                                          const float* __restrict__ pd_vert, const float* __restrict__ gt_vert,
-                                                         float* __restrict__ out) {
+                                                         float* __restrict__ out, int full) {
   __shared__ double red[256];
   __shared__ double T[12];
   const int b = blockIdx.x, tid = threadIdx.x;
+  const int W = full ? 25 : 23, o_je = full ? 4 : 2, o_pamje = full ? 1 : 0, o_pamve = full ? 3 : 1;
   const float* pj = pd_joint + (size_t)b * 21 * 3;
   const float* gj = gt_joint + (size_t)b * 21 * 3;
   const float* pv = pd_vert + (size_t)b * kVerts * 3;
   const float* gv = gt_vert + (size_t)b * kVerts * 3;
+  double je = 0.0;
   if (tid < 21) {
     const float dx = gj[tid * 3 + 0] - pj[tid * 3 + 0], dy = gj[tid * 3 + 1] - pj[tid * 3 + 1], dz = gj[tid * 3 + 2] - pj[tid * 3 + 2];
-    out[(size_t)b * 23 + 2 + tid] = sqrtf((dx * dx + dy * dy) + dz * dz) * 1000.f;
+    const float d = sqrtf((dx * dx + dy * dy) + dz * dz);
+    out[(size_t)b * W + o_je + tid] = d * 1000.f;
+    je = (double)d;
+  }
+  if (full) {
+    const double mje = block_sum_256d(je, red) / 21.0;
+    double ve = 0.0;
+    for (int i = tid; i < kVerts; i += 256) {
+      const float dx = gv[i * 3 + 0] - pv[i * 3 + 0], dy = gv[i * 3 + 1] - pv[i * 3 + 1], dz = gv[i * 3 + 2] - pv[i * 3 + 2];
+      ve += (double)sqrtf((dx * dx + dy * dy) + dz * dz);
+    }
+    const double mve = block_sum_256d(ve, red) / (double)kVerts;
+    if (tid == 0) {
+      out[(size_t)b * W + 0] = (float)(mje * 1000.0);
+      out[(size_t)b * W + 2] = (float)(mve * 1000.0);
+    }
   }
   procrustes_256(pj, gj, 21, red, T);
   double e = tid < 21 ? aligned_error(pj + tid * 3, gj + tid * 3, T) : 0.0;
@@ -416,8 +434,8 @@ __global__ void __launch_bounds__(256) k_hand_pa_metrics(const float* __restrict
   for (int i = tid; i < kVerts; i += 256) e += aligned_error(pv + i * 3, gv + i * 3, T);
   const double pa_mve = block_sum_256d(e, red) / (double)kVerts;
   if (tid == 0) {
-    out[(size_t)b * 23 + 0] = (float)(pa_mje * 1000.0);
-    out[(size_t)b * 23 + 1] = (float)(pa_mve * 1000.0);
+    out[(size_t)b * W + o_pamje] = (float)(pa_mje * 1000.0);
+    out[(size_t)b * W + o_pamve] = (float)(pa_mve * 1000.0);
   }
 }
 
@@ -442,7 +460,17 @@ extern "C" int vpho_hand_pa_metrics(const float* pd_joint, const float* gt_joint
   if (n < 0) return VPHO_ERR_INVALID;
   if (n == 0) return VPHO_OK;
   if (!pd_joint || !gt_joint || !pd_vert || !gt_vert || !metrics) return VPHO_ERR_INVALID;
-  VPHO_LAUNCH(k_hand_pa_metrics, dim3(n), dim3(256), 0, (cudaStream_t)stream, pd_joint, gt_joint, pd_vert, gt_vert, metrics);
+  VPHO_LAUNCH(k_hand_pa_metrics, dim3(n), dim3(256), 0, (cudaStream_t)stream, pd_joint, gt_joint, pd_vert, gt_vert, metrics, 0);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
+
+extern "C" int vpho_hand_metrics(const float* pd_joint, const float* gt_joint, const float* pd_vert, const float* gt_vert, int n,
+                                 float* metrics, void* stream) {
+  if (n < 0) return VPHO_ERR_INVALID;
+  if (n == 0) return VPHO_OK;
+  if (!pd_joint || !gt_joint || !pd_vert || !gt_vert || !metrics) return VPHO_ERR_INVALID;
+  VPHO_LAUNCH(k_hand_pa_metrics, dim3(n), dim3(256), 0, (cudaStream_t)stream, pd_joint, gt_joint, pd_vert, gt_vert, metrics, 1);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }

@@ -1,0 +1,303 @@
+// Object-pose evaluation metrics on the device: the step right after the hot path in Trainer.evaluate
+// (lib/engine/train_diff_hand_obj.py:236-259), `TesterObject` of lib/engine/test.py:196-584, per (image, candidate):
+//   MCE / OCE        criterion_MCE_OCE  test.py:354-375   box corners, float64
+//   SMCE             criterion_SMCE     test.py:377-399   min over the object's symmetry transforms, float64
+//   MCE2             criterion_MCE2     test.py:401-417 -> compute_obj_metrics_dexycb :155-193, axis-aligned boxes, float32
+//   ADD / ADD-S / REP criterion_ADD_REP test.py:419-451   float32 distances of the float64-posed clouds, float64 projection
+//   F-score x6 / CD  criterion_FSCORE   test.py:453-503
+//   ADD01d / ADDS01d / REP5             test.py:505-521
+// With these on the device the reference's evaluate loop needs nothing but the per-image metric rows from the GPU (today:
+// numpy on the host plus a `.cuda()` round trip per image).  One CTA per (candidate, image); nearest-point scans stage
+// tiles of the other cloud in shared memory as k_pose_metrics does.
+#include "agg_device.cuh"
+#include "vpho_b200.h"
+
+#include <cstring>
+#include <vector>
+
+namespace vpho {
+
+constexpr int kMetricCols = VPHO_OBJ_METRIC_COLS;
+
+struct ObjMetricDev {
+  int n_obj, sym_k, n_fpts;
+  const float* bbox3d;     // [n_obj][8][3]
+  const float* diameter;   // [n_obj]
+  const double* sym_R;     // [n_obj][K][9]
+  const double* sym_t;     // [n_obj][K][3] metres
+  const int* sym_count;    // [n_obj] transforms that are not identity padding (padding is harmless: it repeats the identity)
+  const float* fverts;     // [n_obj][n_fpts][3] cloud of the F-score / Chamfer terms (nullptr: the assets' sampled surface)
+};
+
+struct ObjMetricHost {
+  ObjMetricDev dev;
+  void* blob = nullptr;
+};
+
+__device__ __forceinline__ double block_sum_d(double v, double* red) {
+  const int tid = threadIdx.x;
+  red[tid] = v;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (tid < st) red[tid] += red[tid + st];
+    __syncthreads();
+  }
+  const double r = red[0];
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_min_f(float v, float* red, bool want_max) {
+  const int tid = threadIdx.x;
+  red[tid] = v;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (tid < st) red[tid] = want_max ? fmaxf(red[tid], red[tid + st]) : fminf(red[tid], red[tid + st]);
+    __syncthreads();
+  }
+  const float r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// p R^T + t in float64 (numpy einsum "ni,...ij->...nj" with the transposed rotation, then + t)
+__device__ __forceinline__ void pose_point_d(const double* rt, const float* p, double* out) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    out[j] = (((double)p[0] * rt[j * 4 + 0] + (double)p[1] * rt[j * 4 + 1]) + (double)p[2] * rt[j * 4 + 2]) + rt[j * 4 + 3];
+}
+
+// nearest-point scan: every thread owns the points a[slab] of cloud A (posed by rtA) and scans all of cloud B (posed by rtB)
+// through shared-memory tiles; `consume(i, d)` receives the distance of point i.
+template <typename F>
+__device__ __forceinline__ void nearest_scan(const float* base, int n_pts, const double* rtA, const double* rtB, float4* tile, F consume) {
+  const int tid = threadIdx.x;
+  for (int p0 = 0; p0 < n_pts; p0 += 256) {
+    const int i = p0 + tid;
+    float a[3] = {0.f, 0.f, 0.f};
+    if (i < n_pts) {
+      double ad[3];
+      pose_point_d(rtA, base + (size_t)i * 3, ad);
+      a[0] = (float)ad[0]; a[1] = (float)ad[1]; a[2] = (float)ad[2];
+    }
+    float best = INFINITY;
+    for (int q0 = 0; q0 < n_pts; q0 += 256) {
+      __syncthreads();
+      if (q0 + tid < n_pts) {
+        double g[3];
+        pose_point_d(rtB, base + (size_t)(q0 + tid) * 3, g);
+        tile[tid] = make_float4((float)g[0], (float)g[1], (float)g[2], 0.f);
+      }
+      __syncthreads();
+      const int cnt = min(256, n_pts - q0);
+#pragma unroll 8
+      for (int q = 0; q < cnt; ++q) {
+        const float4 t = tile[q];
+        const float dx = a[0] - t.x, dy = a[1] - t.y, dz = a[2] - t.z;
+        best = fminf(best, (dx * dx + dy * dy) + dz * dz);
+      }
+    }
+    if (i < n_pts) consume(i, sqrtf(best));
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_object_metrics(AssetsDev as, ObjMetricDev mt, const double* __restrict__ pd_rt,
+                                                        const double* __restrict__ gt_rt, const int* __restrict__ obj_id,
+                                                        const float* __restrict__ cam_intr, int C, double* __restrict__ out) {
+  __shared__ double red[256];
+  __shared__ float redf[256];
+  __shared__ float4 tile[256];
+  __shared__ double s_pd[12], s_gt[12], s_pdbox[8][3], s_gtbox[8][3];
+  const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int o = obj_index(as, obj_id[b]);
+  if (tid < 12) {
+    s_pd[tid] = pd_rt[((size_t)b * C + c) * 12 + tid];
+    s_gt[tid] = gt_rt[(size_t)b * 12 + tid];
+  }
+  __syncthreads();
+  double* row = out + ((size_t)b * C + c) * kMetricCols;
+  // ---- box corners: MCE, OCE
+  const float* box = mt.bbox3d + (size_t)o * 24;
+  double dcorner = 0.0;
+  if (tid < 8) {
+    pose_point_d(s_pd, box + tid * 3, s_pdbox[tid]);
+    pose_point_d(s_gt, box + tid * 3, s_gtbox[tid]);
+    const double dx = s_pdbox[tid][0] - s_gtbox[tid][0], dy = s_pdbox[tid][1] - s_gtbox[tid][1], dz = s_pdbox[tid][2] - s_gtbox[tid][2];
+    dcorner = sqrt((dx * dx + dy * dy) + dz * dz);
+  }
+  const double mce = block_sum_d(dcorner, red) / 8.0;
+  if (tid == 0) {
+    double pc[3] = {0, 0, 0}, gc[3] = {0, 0, 0};
+    for (int k = 0; k < 8; ++k)
+      for (int d = 0; d < 3; ++d) { pc[d] += s_pdbox[k][d]; gc[d] += s_gtbox[k][d]; }
+    const double dx = pc[0] / 8.0 - gc[0] / 8.0, dy = pc[1] / 8.0 - gc[1] / 8.0, dz = pc[2] / 8.0 - gc[2] / 8.0;
+    row[0] = mce;
+    row[1] = sqrt((dx * dx + dy * dy) + dz * dz);
+  }
+  // ---- SMCE: symmetric copies of the box posed by the ground truth; thread k takes transforms k, k+256, ...
+  {
+    double best = INFINITY;
+    for (int k = tid; k < mt.sym_k; k += 256) {
+      const double* sR = mt.sym_R + ((size_t)o * mt.sym_k + k) * 9;
+      const double* st = mt.sym_t + ((size_t)o * mt.sym_k + k) * 3;
+      double acc = 0.0;
+      for (int n = 0; n < 8; ++n) {
+        const float* p = box + n * 3;
+        double sp[3], g[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          sp[j] = (((double)p[0] * sR[j * 3 + 0] + (double)p[1] * sR[j * 3 + 1]) + (double)p[2] * sR[j * 3 + 2]) + st[j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) g[j] = ((sp[0] * s_gt[j * 4 + 0] + sp[1] * s_gt[j * 4 + 1]) + sp[2] * s_gt[j * 4 + 2]) + s_gt[j * 4 + 3];
+        const double dx = s_pdbox[n][0] - g[0], dy = s_pdbox[n][1] - g[1], dz = s_pdbox[n][2] - g[2];
+        acc += sqrt((dx * dx + dy * dy) + dz * dz);
+      }
+      best = fmin(best, acc / 8.0);
+    }
+    red[tid] = best;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if (tid < st) red[tid] = fmin(red[tid], red[tid + st]);
+      __syncthreads();
+    }
+    if (tid == 0) row[3] = red[0];
+    __syncthreads();
+  }
+  // ---- sampled surface: ADD, REP, axis-aligned boxes (MCE2), then ADD-S
+  const float* base = as.verts + (size_t)o * as.n_pts * 3;
+  const int P = as.n_pts;
+  double add = 0.0, rep = 0.0;
+  float mn_p[3] = {INFINITY, INFINITY, INFINITY}, mx_p[3] = {-INFINITY, -INFINITY, -INFINITY};
+  float mn_g[3] = {INFINITY, INFINITY, INFINITY}, mx_g[3] = {-INFINITY, -INFINITY, -INFINITY};
+  double Kd[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Kd[k] = (double)cam_intr[(size_t)b * 9 + k];
+  for (int i = tid; i < P; i += 256) {
+    double pdv[3], gtv[3];
+    pose_point_d(s_pd, base + (size_t)i * 3, pdv);
+    pose_point_d(s_gt, base + (size_t)i * 3, gtv);
+    const float pf[3] = {(float)pdv[0], (float)pdv[1], (float)pdv[2]}, gf[3] = {(float)gtv[0], (float)gtv[1], (float)gtv[2]};
+    const float dx = pf[0] - gf[0], dy = pf[1] - gf[1], dz = pf[2] - gf[2];
+    add += (double)sqrtf((dx * dx + dy * dy) + dz * dz);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      mn_p[d] = fminf(mn_p[d], pf[d]); mx_p[d] = fmaxf(mx_p[d], pf[d]);
+      mn_g[d] = fminf(mn_g[d], gf[d]); mx_g[d] = fmaxf(mx_g[d], gf[d]);
+    }
+    // pixel coordinates  K v / (v_z + 1e-7)  in float64
+    double pu[2], gu[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      pu[j] = ((pdv[0] * Kd[j * 3 + 0] + pdv[1] * Kd[j * 3 + 1]) + pdv[2] * Kd[j * 3 + 2]) / (pdv[2] + 1e-7);
+      gu[j] = ((gtv[0] * Kd[j * 3 + 0] + gtv[1] * Kd[j * 3 + 1]) + gtv[2] * Kd[j * 3 + 2]) / (gtv[2] + 1e-7);
+    }
+    const double ux = pu[0] - gu[0], uy = pu[1] - gu[1];
+    rep += sqrt(ux * ux + uy * uy);
+  }
+  const double add_m = block_sum_d(add, red) / (double)P;
+  const double rep_px = block_sum_d(rep, red) / (double)P;
+  float bp[2][3], bg[2][3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    bp[0][d] = block_min_f(mn_p[d], redf, false); bp[1][d] = block_min_f(mx_p[d], redf, true);
+    bg[0][d] = block_min_f(mn_g[d], redf, false); bg[1][d] = block_min_f(mx_g[d], redf, true);
+  }
+  double adds = 0.0;
+  nearest_scan(base, P, s_pd, s_gt, tile, [&](int, float d) { adds += (double)d; });
+  const double adds_m = block_sum_d(adds, red) / (double)P;
+  if (tid == 0) {
+    // the 8 corners of compute_obj_metrics_dexycb: (x, y, z) picks min (0) or max (1) by these index rows
+    const int cx[8] = {0, 1, 0, 0, 1, 0, 1, 1}, cy[8] = {0, 0, 1, 0, 1, 1, 0, 1}, cz[8] = {0, 0, 0, 1, 0, 1, 1, 1};
+    float acc = 0.f;
+    for (int k = 0; k < 8; ++k) {
+      const float dx = bp[cx[k]][0] - bg[cx[k]][0], dy = bp[cy[k]][1] - bg[cy[k]][1], dz = bp[cz[k]][2] - bg[cz[k]][2];
+      acc += sqrtf((dx * dx + dy * dy) + dz * dz);
+    }
+    row[2] = (double)(acc / 8.f);
+    row[4] = (double)(float)add_m;
+    row[5] = (double)(float)adds_m;
+    row[6] = rep_px;
+    const float diam = mt.diameter[o];
+    row[14] = ((float)add_m <= diam * 0.1f) ? 1.0 : 0.0;
+    row[15] = ((float)adds_m <= diam * 0.1f) ? 1.0 : 0.0;
+    row[16] = (rep_px < 5.0) ? 1.0 : 0.0;
+  }
+  // ---- F-score / Chamfer on the F-score cloud, both directions
+  const float* fbase = mt.fverts ? mt.fverts + (size_t)o * mt.n_fpts * 3 : base;
+  const int Q = mt.fverts ? mt.n_fpts : P;
+  const float th[6] = {0.002f, 0.005f, 0.010f, 0.020f, 0.050f, 0.100f};
+  double s_pg = 0.0, s_gp = 0.0;
+  int hit_pg[6] = {0, 0, 0, 0, 0, 0}, hit_gp[6] = {0, 0, 0, 0, 0, 0};
+  nearest_scan(fbase, Q, s_pd, s_gt, tile, [&](int, float d) {
+    s_pg += (double)d;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hit_pg[k] += d < th[k] ? 1 : 0;
+  });
+  nearest_scan(fbase, Q, s_gt, s_pd, tile, [&](int, float d) {
+    s_gp += (double)d;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hit_gp[k] += d < th[k] ? 1 : 0;
+  });
+  const double m_pg = block_sum_d(s_pg, red) / (double)Q, m_gp = block_sum_d(s_gp, red) / (double)Q;
+  if (tid == 0) row[7] = (double)(0.5f * ((float)m_pg + (float)m_gp));
+  for (int k = 0; k < 6; ++k) {
+    const double np_ = block_sum_d((double)hit_pg[k], red), ng_ = block_sum_d((double)hit_gp[k], red);
+    if (tid == 0) {
+      const float prec = (float)np_ / (float)Q, rec = (float)ng_ / (float)Q;
+      row[8 + k] = (double)((2.f * prec * rec) / (prec + rec + 1e-6f));
+    }
+  }
+}
+
+}  // namespace vpho
+
+using namespace vpho;
+
+extern "C" int vpho_objmetrics_create(int n_obj, const float* bbox3d, const float* diameter, int sym_k, const double* sym_R,
+                                      const double* sym_t, const int32_t* sym_count, int n_fpts, const float* fverts,
+                                      vpho_objmetrics_t* out) {
+  if (n_obj <= 0 || !bbox3d || !diameter || sym_k <= 0 || !sym_R || !sym_t || !out || (fverts && n_fpts <= 0)) return VPHO_ERR_INVALID;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
+  const size_t o_box = take((size_t)n_obj * 24 * 4), o_diam = take((size_t)n_obj * 4), o_R = take((size_t)n_obj * sym_k * 9 * 8),
+               o_t = take((size_t)n_obj * sym_k * 3 * 8), o_cnt = take((size_t)n_obj * 4),
+               o_fv = take(fverts ? (size_t)n_obj * n_fpts * 3 * 4 : 0);
+  std::vector<char> h(off, 0);
+  memcpy(h.data() + o_box, bbox3d, (size_t)n_obj * 24 * 4);
+  memcpy(h.data() + o_diam, diameter, (size_t)n_obj * 4);
+  memcpy(h.data() + o_R, sym_R, (size_t)n_obj * sym_k * 9 * 8);
+  memcpy(h.data() + o_t, sym_t, (size_t)n_obj * sym_k * 3 * 8);
+  if (sym_count) memcpy(h.data() + o_cnt, sym_count, (size_t)n_obj * 4);
+  if (fverts) memcpy(h.data() + o_fv, fverts, (size_t)n_obj * n_fpts * 3 * 4);
+  ObjMetricHost* mh = new ObjMetricHost();
+  if (cudaMalloc(&mh->blob, off) != cudaSuccess) { delete mh; return VPHO_ERR_ALLOC; }
+  if (cudaMemcpy(mh->blob, h.data(), off, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(mh->blob); delete mh; return VPHO_ERR_ALLOC; }
+  char* b = static_cast<char*>(mh->blob);
+  mh->dev.n_obj = n_obj; mh->dev.sym_k = sym_k; mh->dev.n_fpts = n_fpts;
+  mh->dev.bbox3d = (const float*)(b + o_box); mh->dev.diameter = (const float*)(b + o_diam);
+  mh->dev.sym_R = (const double*)(b + o_R); mh->dev.sym_t = (const double*)(b + o_t); mh->dev.sym_count = (const int*)(b + o_cnt);
+  mh->dev.fverts = fverts ? (const float*)(b + o_fv) : nullptr;
+  *out = mh;
+  return VPHO_OK;
+}
+
+extern "C" int vpho_objmetrics_destroy(vpho_objmetrics_t h) {
+  if (!h) return VPHO_ERR_INVALID;
+  ObjMetricHost* mh = static_cast<ObjMetricHost*>(h);
+  cudaFree(mh->blob);
+  delete mh;
+  return VPHO_OK;
+}
+
+extern "C" int vpho_object_metrics(vpho_assets_t assets, vpho_objmetrics_t tables, const double* pd_rt, const double* gt_rt,
+                                   const int32_t* obj_id, const float* cam_intr, int n, int C, double* out, void* stream) {
+  if (!assets || !tables || n < 0 || C < 0) return VPHO_ERR_INVALID;
+  if (n == 0 || C == 0) return VPHO_OK;
+  if (!pd_rt || !gt_rt || !obj_id || !cam_intr || !out) return VPHO_ERR_INVALID;
+  const AssetsDev& as = static_cast<AssetsHost*>(assets)->dev;
+  const ObjMetricDev& mt = static_cast<ObjMetricHost*>(tables)->dev;
+  if (mt.n_obj != as.n_obj) return VPHO_ERR_INVALID;
+  VPHO_LAUNCH(k_object_metrics, dim3(C, n), dim3(256), 0, (cudaStream_t)stream, as, mt, pd_rt, gt_rt, obj_id, cam_intr, C, out);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}

@@ -316,3 +316,26 @@ def make_eval_batch(bs: int, seed: int = 0, sample_num: int = 100,
     out["force_local"] = (d * scale[..., None]).astype(f32)
     out["sample_num"] = sample_num
     return out
+
+
+def make_eval_ground_truth(batch: Dict[str, object], head_mano, objects: Dict[str, object]):
+    """Ground-truth fields `Trainer.evaluate` reads from the dataset (gt_joint, gt_hand_vert, gt_obj_rt, cam_intr;
+    lib/engine/train_diff_hand_obj.py:236-257) for a synthetic batch: the hidden "true" wrist pose with flat fingers posed
+    by the MANO layer, and the hidden object pose, both in the un-flipped camera frame.  `head_mano`: the product's
+    `HeadMano` (the meshes are made by the same CUDA layer; this runs outside any timed region)."""
+    import torch
+    bs = len(batch["obj_name"])
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    T = lambda k: torch.from_numpy(np.asarray(batch[k])).to(dev)     # noqa: E731
+    pose = torch.cat([T("true_wrist").float(), torch.zeros(bs, 45, device=dev)], 1)
+    v, j = head_mano.get_hand_verts(pose=pose, shape=T("pd_mano_shape").float())
+    is_right = T("is_right").bool()
+    sign = torch.where(is_right, 1.0, -1.0)[:, None]
+    root = T("root_joint").float()
+    v, j = v.clone(), j.clone()
+    v[..., 0] *= sign
+    j[..., 0] *= sign
+    gt_rt = torch.cat([T("true_obj_rot").double(), (T("true_obj_trans").double() + root.double())[..., None]], -1)
+    K = T("cam_intr_crop_flip").float()
+    return {"gt_joint": j + root[:, None], "gt_hand_vert": v + root[:, None], "gt_obj_rt": gt_rt, "cam_intr": K}
+

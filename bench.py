@@ -1,24 +1,31 @@
 """Benchmark of the VPHO evaluation hot path (BASELINE.json metric: hand-object pose candidates scored per second).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the whole hot path (hand + object ODE sampling with 50 output points, MANO, visual and physical
-scoring, top-30 / top-10 selection, aggregation) over one batch of 64 synthetic DexYCB-shaped images x 100 candidates
-per GPU (BASELINE config 2; with N GPUs this is config 4: 64 images per GPU, sharded by image, weak scaling).
-
-  value  : candidates/s over all ranks, inputs resident in HBM, per-step CUDA events (max over ranks)
-  e2e    : the same through `VphoHotPath.predict` fed from pinned HOST buffers, H2D of every input and D2H of the
-           aggregated results inside the timed region
-  --impl reference : the CPU oracle restatement of the reference (oracle/vpho_oracle.py, validated bit-exact against the
-           reference's own files in the build container) on the box's host cores -- the reference has no compiled code
-           on this path and /root/reference does not travel to the GPU box.
+--config 2 (default; BASELINE configs[1], and configs[3] when launched on N GPUs): one "step" = one pass of the whole hot
+  path (hand + object ODE sampling with 50 output points, MANO, visual and physical scoring, top-30 / top-10 selection,
+  aggregation) over one batch of 64 synthetic DexYCB-shaped images x 100 candidates per GPU, sharded by image.
+    value    : candidates/s over all ranks, inputs resident in HBM, per-step CUDA events (max over ranks)
+    e2e      : the same through `VphoHotPath.predict` fed from pinned HOST buffers; H2D of every input, the on-device
+               evaluation record (TesterHand / TesterObject metrics) and D2H of that record + the aggregated poses inside
+               the timed region
+    roofline : dominant kernel (score-network head GEMM) against the measured tensor peak
+    stages   : per-stage time from a SERIALISED pass (no programmatic dependent launch, no side streams: isolated kernel
+               durations from CUDA events on the launching stream), algorithmic work, fraction of the bounding roofline
+--config 1 : BASELINE configs[0] (batch 1 x 100 x 50) on the GPU, with the CPU reference beside it.
+--config 3 : MANO LBS + contact microbench, 4 candidate counts x 3 object-point counts (BASELINE configs[2]).
+--config 5 : pseudo-force contact evaluation over 64 x 100 candidates + physics3 against 8192-point clouds (configs[4]).
+--impl reference : the CPU oracle restatement of the reference (oracle/vpho_oracle.py, bit-identical to the reference's own
+  files in the build container) on the box's host cores, same workload -- the reference has no compiled code on this path
+  and /root/reference does not travel to the GPU box.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import glob
 import json
 import os
 import statistics
@@ -34,20 +41,40 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BS, S, STEPS_ODE, T0, K_HAND, K_OBJ = 64, 100, 50, 0.65, 30, 10
-# algorithmic work (restated in DESIGN.md §5)
+# algorithmic work (restated in DESIGN.md §4-5)
 FLOP_HEAD_GEMM_HAND = 2 * (256 * 8192 + 8192 * 3)     # per candidate per network call, head GEMM + fused second layer
 FLOP_HEAD_GEMM_OBJ = 2 * (256 * 768 + 768 * 3)        # same for the object denoiser (3 heads of 256 hidden units)
 FLOP_SCORE_HAND, FLOP_SCORE_OBJ = 4423680, 533504     # whole factored network per candidate per call
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC_BYTES = {"k_head_tc": 24889600}
+FLOP_FEAT_TERM_PER_IMAGE = 2 * 1024 * (8192 + 768)    # conditioning term, once per image per sample()
+MANO_BYTES, MANO_FLOP = 9820, 1176000                 # per candidate with vertices materialised
+PAIR_FLOP = 8                                         # per (anchor, object point) distance pair
+TRAJ_BYTES = 96 * 4 + 58 * 4                          # trajectory post-processing per (row, output point): f32 6D in, MANO vector out
+METRIC = "hand-object pose candidates scored/sec"
 
 
-def _peaks():
+def _peaks(lib=None):
+    """Roofline denominators: the driver-written MEASURED_PEAKS.json (HBM copy bandwidth, cuBLAS bf16) and, measured here by
+    the library's own microbenchmarks at the clock a short kernel runs at, FP32 FMA and FP16 UMMA throughput."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    out = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": None, "source": "fallback (B200_PROFILING.md)"}
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+        out.update(hbm_gbs=d.get("hbm_gbs", out["hbm_gbs"]), bf16_tflops=d.get("bf16_tflops", out["bf16_tflops"]),
+                   bf16_tflops_sustained=d.get("bf16_tflops_sustained"), source="MEASURED_PEAKS.json")
+    if lib is not None:
+        a, b = C.c_float(0), C.c_float(0)
+        if lib.c.vpho_measure_peaks(C.byref(a), C.byref(b), 5, None) == 0:
+            out["fp32_fma_tflops"], out["f16_umma_tflops"] = round(a.value, 2), round(b.value, 1)
+    return out
+
+
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each profiled kernel, from the committed summary of the
+    `ncu --set full` captures (profiles/*_ncu_traffic.json, written by tools/ncu_summarize.py); newest round wins."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    if not files:
+        return {}, None
+    return json.load(open(files[-1])), os.path.basename(files[-1])
 
 
 class ClockSampler(threading.Thread):
@@ -113,18 +140,26 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def make_inputs(bs: int, seed: int):
+def make_inputs(bs: int, seed: int, n_pts: int = 2048):
     from vpho_b200 import synthetic as syn
     from vpho_b200.score_based_model import ve_prior_std
     mano = syn.make_mano_model()
     anchors = syn.make_anchor_assets(mano)
-    objects = syn.make_object_tables()
+    objects = syn.make_object_tables(n_verts=n_pts) if n_pts != 2048 else syn.make_object_tables()
     batch = syn.make_eval_batch(bs, seed=seed, sample_num=S, mano=mano, objects=objects)
     g = torch.Generator().manual_seed(1000 + seed)
     prior_h = torch.randn(bs * S, 96, generator=g) * ve_prior_std(T0)
     prior_o = torch.randn(bs * S, 9, generator=g) * ve_prior_std(T0)
     st_h, st_o = syn.make_denoiser_state("mano_pose", 0), syn.make_denoiser_state("obj", 0)
     return mano, anchors, objects, batch, prior_h, prior_o, st_h, st_o
+
+
+def workload_config(n_gpus: int, bs: int = BS):
+    return {"workload": f"vpho_net eval hot path, batch {bs} images/GPU x sample_num {S} x {STEPS_ODE} ODE output points, "
+                        f"topk_hand {K_HAND} / topk_obj {K_OBJ}, T0 {T0}, random-init weights, synthetic DexYCB-shaped input",
+            "images_per_gpu": bs, "candidates_per_step_per_gpu": bs * S, "sharding": f"by image, {n_gpus} rank(s)",
+            "l2": "no explicit flush: one step streams ~0.5 GB (trajectory 123 MB + its post-processed form 74 MB, candidate "
+                  "meshes 60 MB, heat-maps 50 MB, weights 52 MB, RK state 44 MB) through the 126 MB L2"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -146,70 +181,78 @@ def run_oracle(bs: int, seed: int, timing=None):
 
 
 def reference_arm(args, rank: int):
+    """The reference's CPU implementation of the path on ALL host cores, on the SAME workload as our arm: the full
+    64-image batch per step (RK45's step controller couples the batch, so a smaller batch is a different computation).
+    A step takes ~10-20 s; the run is bounded to ~4 minutes by timing fewer steps than asked when necessary (reported)."""
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
-    budget = 150.0
-    probe = run_oracle(8, 0)
-    t_probe, _ = probe()          # includes first-call overheads
-    t_probe, _ = probe()
-    per_img = t_probe / 8
-    total_steps = args.steps + args.warmup
-    bs_ref = int(budget / max(total_steps, 1) / per_img) // 8 * 8
-    bs_ref = max(8, min(BS, bs_ref))
-    step = run_oracle(bs_ref, 0) if bs_ref != 8 else probe
-    for _ in range(args.warmup):
+    bs = 1 if args.config == 1 else BS
+    step = run_oracle(bs, 0)
+    budget = 240.0
+    t_first, out = step()                      # warm-up (first-call overheads)
+    warm_done = 1
+    while warm_done < args.warmup and (warm_done + 1) * t_first < 0.25 * budget:
         step()
-    times = [step()[0] for _ in range(args.steps)]
+        warm_done += 1
+    n_timed = max(1, min(args.steps, int((budget - warm_done * t_first) / max(t_first, 1e-3))))
+    times = [step()[0] for _ in range(n_timed)]
     tot = sum(times)
-    value = bs_ref * S * args.steps / tot
-    sample = f"{bs_ref} images x {S} candidates per step (bounded sample of the {BS}-image batch), {args.steps} steps"
+    value = bs * S * n_timed / tot
+    sample = (f"the full workload: {bs} images x {S} candidates per step; {n_timed} timed step(s) of the {args.steps} asked "
+              f"and {warm_done} warm-up step(s) of the {args.warmup} asked, bounded to ~{budget:.0f} s of CPU work")
     line = {
-        "impl": "reference", "metric": "hand-object pose candidates scored/sec", "value": round(value, 2),
-        "unit": "candidates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(tot / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "candidates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "steps_timed": n_timed, "warmup_done": warm_done,
+        "ms_per_step": round(tot / n_timed * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": round(value, 2), "unit": "candidates/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.gpus, bs),
+        "cpu_baseline": {"value": round(value, 2), "unit": "candidates/s", "cores": cores, "kind": "port", "sample": sample,
+                         "net_calls": out["_info"]["hand"]["net_calls"]},
         "e2e": {"value": round(value, 2), "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "CPU oracle restatement of the reference's PyTorch/scipy path (bit-exact vs the reference's own files in "
-                "the build container); torch threads = all host cores",
+        "note": "CPU oracle restatement of the reference's PyTorch/scipy path (bit-identical to the reference's own files in "
+                "the build container); torch threads = all host cores.  ONE CPU process on rank 0: at --gpus N > 1 this line "
+                "is still one host running one 64-image batch, so a ratio against the N-GPU line compares N GPUs with one "
+                "CPU process (not a like-for-like scaling figure)",
+        "comparable_n_gpus": 1,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus: int):
-    return {"workload": f"vpho_net eval hot path, batch {BS} images/GPU x sample_num {S} x {STEPS_ODE} ODE output points, "
-                        f"topk_hand {K_HAND} / topk_obj {K_OBJ}, T0 {T0}, random-init weights, synthetic DexYCB-shaped input",
-            "images_per_gpu": BS, "candidates_per_step_per_gpu": BS * S, "sharding": f"by image, {n_gpus} rank(s)",
-            "l2": "no explicit flush: one step streams ~0.6 GB (xs 245 MB, verts 60 MB, heat-maps 50 MB, weights 52 MB, RK "
-                  "state 44 MB) through the 126 MB L2"}
+# ---------------------------------------------------------------------------------------------------------------------
+# CUDA arm, configs 1 / 2 / 4
+# ---------------------------------------------------------------------------------------------------------------------
+TAGS = ((0, "head_gemm"), (1, "head_gemm_single"), (2, "stage_input_plus_pose_encoder"), (3, "mano_skinning"), (4, "physics3_scan"),
+        (5, "hand_heat_score"), (6, "stage_input_time_term"), (7, "feat_term"), (8, "rk_control"), (9, "hoi_aggregate_total"),
+        (10, "hand_physics_scan"), (11, "trajectory_postprocess"))
 
 
-# ---------------------------------------------------------------------------------------------------------------------
-# CUDA arm
-# ---------------------------------------------------------------------------------------------------------------------
 def cuda_arm(args, rank: int, world: int, local_rank: int):
     import torch.distributed as dist
     from vpho_b200 import capi
-    from vpho_b200.distributed import gather_records, image_record
+    from vpho_b200 import synthetic as syn
+    from vpho_b200.distributed import gather_records
+    from vpho_b200.evaluation import EvalRecorder
     from vpho_b200.vpho import VphoHotPath
 
+    bs = 1 if args.config == 1 else BS
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = capi.lib()       # raises when the CUDA library is missing: there is no fallback
-    mano, anchors, objects, batch, prior_h, prior_o, st_h, st_o = make_inputs(BS, seed=rank)
+    mano, anchors, objects, batch, prior_h, prior_o, st_h, st_o = make_inputs(bs, seed=rank)
     hp = VphoHotPath(mano, anchors, objects, st_h, st_o, sample_num=S, sampling_steps=STEPS_ODE, sample_T0=T0,
                      topk_hand=K_HAND, topk_obj=K_OBJ)
-    if os.environ.get("VPHO_NO_OVERLAP"):            # diagnostics: serialise the two samplers so per-kernel times are clean
-        hp.overlap_object_sampler = False
+    recorder = EvalRecorder(hp.assets, syn.make_metric_tables(objects))
+    gt = syn.make_eval_ground_truth(batch, hp.head_mano, objects)
     batch["obj_id"] = np.asarray(batch["obj_id"], np.int32)
     host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in batch.items() if isinstance(v, np.ndarray)}
     host["prior_hand"], host["prior_obj"] = prior_h.pin_memory(), prior_o.pin_memory()
+    for k, v in gt.items():                      # ground truth of the metric step travels with the batch, as in the reference
+        host[k] = v.cpu().pin_memory()
     h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
     resident = {k: v.to(dev) for k, v in host.items()}
     out_keys = ("agg_obj_6d", "agg_hand_mano", "agg_hand_vert", "agg_hand_joint")
@@ -219,14 +262,15 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         return hp.predict(resident, prior_hand=resident["prior_hand"], prior_obj=resident["prior_obj"])
 
     # e2e: inputs live in pinned host memory; every step issues one full H2D copy (the NEXT step's inputs, on a copy
-    # stream, double-buffered -- what a prefetching eval loop does) and one D2H read of the aggregated results.
+    # stream, double-buffered -- what a prefetching eval loop does), computes the evaluation record on the device and
+    # reads the record and the aggregated poses back.
     copy_stream = torch.cuda.Stream(device=dev)
     dev_sets = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()} for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     for e in consumed:
         e.record()
-    e2e_state = {"i": 0}
+    e2e_state = {"i": 0, "record": None}
 
     def prefetch(slot):
         with torch.cuda.stream(copy_stream):
@@ -241,15 +285,18 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         cur = torch.cuda.current_stream()
         cur.wait_event(ready[slot])
         d = dev_sets[slot]
-        # enqueue this step's compute first; the result read-back and the next step's H2D copies (~20 copy calls of host
-        # time) are issued from predict's hook while the GPU is already busy
+
         def enqueued(pd_, issue):
-            # device -> host read of the step's results, stream-ordered behind the aggregation (complete when predict's
-            # status read returns); then, once per step, the next step's H2D copies on the copy stream
-            for k in out_keys:
+            # metric step on the device (TesterHand / TesterObject rows), then the device -> host reads, all stream-ordered
+            # behind the aggregation (complete when predict's status read returns); then, once per step, the next step's
+            # H2D copies on the copy stream
+            rec = recorder(pd_, d)
+            e2e_state["record"] = rec
+            outs = dict({k: pd_[k] for k in out_keys}, eval_record=rec)
+            for k, t in outs.items():
                 if k not in host_out:
-                    host_out[k] = torch.empty(pd_[k].shape, dtype=pd_[k].dtype).pin_memory()
-                host_out[k].copy_(pd_[k], non_blocking=True)
+                    host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                host_out[k].copy_(t, non_blocking=True)
             if issue == 0:
                 prefetch(slot ^ 1)
 
@@ -258,17 +305,14 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         cur.synchronize()
         return pd
 
-    def metrics_of(pd):
-        # fixed-width per-image record that the final NCCL gather moves (replaces gather_for_metrics,
-        # train_diff_hand_obj.py:333-335): fused wrist-relative joints (63) + fused object pose (9)
-        return image_record(pd["agg_hand_joint"], pd["agg_obj_6d"])
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps, profile=0):
+    windows = []
+
+    def timed(step_fn, steps, profile=0, gather=False):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         l0 = lib.c.vpho_launch_count()
@@ -282,9 +326,12 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
             last = None              # release the previous step's outputs first: same footprint as the warm-up steps
             last = step_fn()
             ev[i][1].record()
-        if world > 1:
-            gathered = gather_records(metrics_of(last), BS * world)     # the only collective of the path
-            assert gathered.shape[0] == BS * world
+        if world > 1 and gather:
+            # the only collective of the path: the per-image evaluation rows (replaces gather_for_metrics,
+            # train_diff_hand_obj.py:333-335)
+            rec = e2e_state["record"] if e2e_state["record"] is not None else recorder(last, resident)
+            gathered = gather_records(rec, bs * world)
+            assert gathered.shape == (bs * world, recorder.width)
         barrier()
         wall = time.perf_counter() - wall0
         windows[-1][1] = wall0 + wall
@@ -293,51 +340,58 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         launches = lib.c.vpho_launch_count() - l0
         per_step = [a.elapsed_time(b) for a, b in ev]
         ms = sum(per_step)
-        if os.environ.get("VPHO_BENCH_VERBOSE") and rank == 0:
-            sys.stderr.write("per-step ms: " + " ".join(f"{x:.2f}" for x in per_step) + "\n")
         t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         del last
         return t[0].item(), t[1].item(), launches
 
+    def collect(tag, cap=0):
+        tot, n = C.c_double(0), C.c_int(0)
+        each = np.zeros(max(cap, 1), np.float32)
+        lib.c.vpho_profile_collect_list(tag, C.byref(tot), C.byref(n), each.ctypes.data if cap else None, cap)
+        return tot.value, n.value, each[:min(n.value, cap)]
+
     # the sampler thread starts before the warm-up steps so that its first (slow) driver queries stay out of the timed
     # regions; only samples that fall inside a timed window are reported
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    windows = []
-    lib.c.vpho_profile_reserve(min(2 * 600 * args.steps + 1024, 200000))
+    lib.c.vpho_profile_reserve(min(2 * 700 * args.steps + 1024, 200000))
+    peaks = _peaks(lib) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    # 1) the timed region (`value`): K steps, no library instrumentation at all;
-    # 2) the same K steps again with the dominant kernel (tag 0, hand head GEMM) bracketed by CUDA events on its launching
-    #    stream -> roofline (median launch duration: a single driver hiccup must not move it);
-    # 3) once more with every tag -> per-kernel breakdown.
+    # 1) the timed region (`value`): K steps, no library instrumentation at all
     ms_res, wall_res, launches = timed(step_resident, args.steps)
+    # 2) the same K steps with the dominant kernel (tag 0, head GEMM) bracketed by CUDA events on its launching stream ->
+    #    roofline (median launch duration: a single driver hiccup must not move it)
     ms_roof, _, _ = timed(step_resident, args.steps, profile=1)
-    hg_tot, hg_n = C.c_double(0), C.c_int(0)
-    each = np.zeros(64 * args.steps + 64, np.float32)
-    lib.c.vpho_profile_collect_list(0, C.byref(hg_tot), C.byref(hg_n), each.ctypes.data, each.size)
-    each = np.sort(each[:min(hg_n.value, each.size)])
-    timed(step_resident, args.steps, profile=-1)
-    prof = {}
-    for tag, name in ((0, "head_gemm_hand"), (1, "head_gemm_obj"), (2, "pose_encoder"), (3, "mano_skinning"),
-                      (4, "physics3_scan"), (5, "hand_heat_score"), (6, "stage_x_time_term"), (7, "feat_term"),
-                      (8, "rk_control"), (9, "hoi_aggregate_total")):
-        tot, n = C.c_double(0), C.c_int(0)
-        lib.c.vpho_profile_collect(tag, C.byref(tot), C.byref(n))
-        prof[name] = {"ms_total": tot.value, "launches": n.value}
-    # 4) the aggregation stage alone bracketed (tag 9 only: events between its kernels would serialise the
-    #    programmatic-dependent-launch chain the stage normally runs as)
+    _, hg_n, each = collect(0, 64 * args.steps + 64)
+    each = np.sort(each)
+    # 3) the aggregation stage alone bracketed, still overlapped (events between its kernels would serialise its chain)
     timed(step_resident, args.steps, profile=1 << 9)
-    tot, n = C.c_double(0), C.c_int(0)
-    lib.c.vpho_profile_collect(9, C.byref(tot), C.byref(n))
-    prof["hoi_aggregate_total"] = {"ms_total": tot.value, "launches": n.value}
+    agg_overlapped_ms, _, _ = collect(9)
+    # 4) SERIALISED pass: programmatic dependent launch off, no side streams, every tagged kernel bracketed -> isolated
+    #    per-kernel durations that add up (the overlapped step is shorter than their sum)
+    lib.c.vpho_set_pdl(0)
+    hp.serialize = True
+    step_resident()
+    ms_serial, _, _ = timed(step_resident, args.steps, profile=-1)
+    prof = {}
+    mano_each = None
+    for tag, name in TAGS:
+        tot, n, ea = collect(tag, 16 * args.steps if tag == 3 else 0)
+        prof[name] = {"ms_per_step": tot / args.steps, "launches_per_step": n / args.steps}
+        if tag == 3:
+            mano_each = ea
+    lib.c.vpho_set_pdl(1)
+    hp.serialize = False
+    step_resident()
+    # 5) end to end from pinned host buffers
     prefetch(0)
     for _ in range(2):
         step_e2e()
-    ms_e2e, wall_e2e, _ = timed(step_e2e, args.steps)
+    ms_e2e, wall_e2e, _ = timed(step_e2e, args.steps, gather=True)
     # stand-alone H2D time of one input set (not overlapped), for reference
     hs, he = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -357,63 +411,292 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         if world > 1:
             dist.destroy_process_group()
         return
-    cand = BS * S * world
+    cand = bs * S * world
+    step_ms = ms_res / args.steps
     value = cand * args.steps / (ms_res / 1e3)
     e2e = cand * args.steps / (ms_e2e / 1e3)
-    peaks = _peaks()
-    head_kernel = "k_head_simt" if os.environ.get("VPHO_HEAD_GEMM") == "simt" else "k_head_tc"
-    hg = {"ms_total": hg_tot.value, "launches": hg_n.value}
-    # launches that found the integration already finished exit at once (spare attempt): keep the real network calls,
-    # i.e. the `real_launches` longest ones, and take their median
-    real_launches = info["hand"]["net_calls"] * args.steps
+    net_calls = info["hand"]["net_calls"]
+    traffic, traffic_file = _ncu_traffic()
+    # ---- roofline of the dominant kernel.  Launches that found the integration already finished exit at once (spare
+    # attempt): keep the real network calls, i.e. the `real_launches` longest ones, and take their median
+    real_launches = net_calls * args.steps
     real = each[-real_launches:] if each.size >= real_launches else each
     avg_ms = float(np.median(real)) if real.size else 0.0
-    # with the two samplers in lock-step (default) one launch serves the hand's AND the object's head GEMM
-    paired = os.environ.get("VPHO_PAIR_SAMPLERS", "1") != "0" and os.environ.get("VPHO_NO_OVERLAP") is None \
-        and head_kernel == "k_head_tc"
-    flop_launch = BS * S * (FLOP_HEAD_GEMM_HAND + (FLOP_HEAD_GEMM_OBJ if paired else 0))
-    achieved = flop_launch / (avg_ms * 1e-3) / 1e12 if hg["launches"] else None
+    flop_launch = bs * S * (FLOP_HEAD_GEMM_HAND + FLOP_HEAD_GEMM_OBJ)       # one launch serves both denoisers
+    achieved = flop_launch / (avg_ms * 1e-3) / 1e12 if avg_ms else None
+    f16_peak = peaks.get("f16_umma_tflops")
+    roofline = {
+        "kernel": "k_head_tc (score-network head GEMM: pose features K=256 x 8192 hidden units of the hand denoiser + 768 of "
+                  "the object denoiser in one launch, fused bias/ReLU/256->3 heads/sigma division)",
+        "bound": "tensor", "achieved": round(achieved, 2) if achieved else None, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+        "frac": round(achieved / peaks["bf16_tflops"], 4) if achieved else None,
+        "traffic": traffic.get("k_head_tc"), "traffic_source": traffic_file,
+        "peak_source": peaks["source"] + " (cuBLAS bf16 burst)",
+        "note": "FP32-parity contraction run as 3 kind::f16 UMMAs per algorithmic FLOP (hi/lo FP16 planes, exact power-of-two "
+                "scaling): the tensor pipe executes 3x `achieved`.  Measured here with the library's own back-to-back UMMA "
+                "kernel at the clock a short kernel runs at: %s TFLOP/s kind::f16 -> executed / measured-f16 = %s" %
+                (f16_peak, round(3 * achieved / f16_peak, 3) if achieved and f16_peak else None),
+        "launches_timed": hg_n, "network_calls": real_launches, "avg_launch_ms": round(avg_ms, 4),
+        "avg_is": "median over the real launches of a second pass of the same K steps (%.4f ms/step)" % (ms_roof / args.steps),
+        "flop_per_launch": flop_launch, "share_of_step": round(avg_ms * net_calls / step_ms, 4)}
+    # ---- stages (serialised pass).  Algorithmic work per step:
+    P = lambda k: prof[k]["ms_per_step"]   # noqa: E731
+    n_pts = objects["verts_sampled"].shape[1]
+    score_ms = P("head_gemm") + P("head_gemm_single") + P("stage_input_plus_pose_encoder") + P("feat_term") + P("rk_control")
+    score_flop = net_calls * bs * S * (FLOP_SCORE_HAND + FLOP_SCORE_OBJ) + bs * FLOP_FEAT_TERM_PER_IMAGE
+    # MANO with vertices: the finals (bs*S candidates) are the largest launch of the step; the rest are the aggregator's
+    mano_finals_ms = float(np.sort(mano_each)[-args.steps:].mean()) if mano_each is not None and mano_each.size >= args.steps else None
+    mano_other = bs * (1 + (K_HAND + 1) + 1)
+    contact_ms = P("physics3_scan") + P("hand_physics_scan")
+    contact_pairs = bs * (32 * n_pts * K_OBJ * K_OBJ + (K_HAND + 1) * 32 * n_pts)
+    traj_ms = P("trajectory_postprocess")
+    agg_rest_ms = P("hoi_aggregate_total") - contact_ms - (P("mano_skinning") - (mano_finals_ms or 0.0))
+    fp32_peak = peaks.get("fp32_fma_tflops")
+
+    def frac(x, peak):
+        return round(x / peak, 4) if (x is not None and peak) else None
+    st_score = score_flop / (score_ms * 1e-3) / 1e12 if score_ms else None
+    st_mano = bs * S * MANO_BYTES / (mano_finals_ms * 1e-3) / 1e9 if mano_finals_ms else None
+    st_contact = contact_pairs * PAIR_FLOP / (contact_ms * 1e-3) / 1e12 if contact_ms else None
+    st_traj = (bs * S * STEPS_ODE * TRAJ_BYTES + bs * S * TRAJ_BYTES) / (traj_ms * 1e-3) / 1e9 if traj_ms else None
+    stages = [
+        {"stage": "score network (both samplers: stage input, pose encoder, head GEMM, feat-term, RK control / dense output)",
+         "ms": round(score_ms, 4), "bound": "tensor", "work": score_flop, "work_unit": "FLOP (factored minimum, SURVEY §8d)",
+         "achieved": round(st_score, 2) if st_score else None, "unit": "TFLOP/s", "peak": peaks["bf16_tflops"],
+         "frac": frac(st_score, peaks["bf16_tflops"]), "network_calls": net_calls,
+         "kernels": {k: round(P(k), 4) for k in ("head_gemm", "stage_input_plus_pose_encoder", "stage_input_time_term", "feat_term", "rk_control")}},
+        {"stage": "MANO with vertices materialised (the bs*S candidate meshes)", "ms": round(mano_finals_ms, 4) if mano_finals_ms else None,
+         "bound": "hbm", "work": bs * S * MANO_BYTES, "work_unit": "bytes (9820 per candidate)",
+         "achieved": round(st_mano, 1) if st_mano else None, "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": frac(st_mano, peaks["hbm_gbs"])},
+        {"stage": "contact scans (physics3 over K_obj^2 recombined poses + hand physics over K_hand+1 hands)", "ms": round(contact_ms, 4),
+         "bound": "fp32", "work": contact_pairs * PAIR_FLOP, "work_unit": "FLOP (8 per anchor-point pair)",
+         "achieved": round(st_contact, 2) if st_contact else None, "unit": "TFLOP/s", "peak": fp32_peak,
+         "peak_source": "vpho_measure_peaks (back-to-back FFMA on every SM)", "frac": frac(st_contact, fp32_peak)},
+        {"stage": "trajectory post-processing (6D -> axis-angle of all 50 output points; output-only)", "ms": round(traj_ms, 4),
+         "bound": "hbm", "work": bs * S * (STEPS_ODE + 1) * TRAJ_BYTES, "work_unit": "bytes",
+         "achieved": round(st_traj, 1) if st_traj else None, "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": frac(st_traj, peaks["hbm_gbs"])},
+        {"stage": "visual scoring / top-k / fusion / small MANO calls of the aggregation (%d joints-only + %d full forwards)" %
+                  (bs * (2 * S + 3 * (S + 1)), mano_other), "ms": round(agg_rest_ms, 4), "bound": "latency", "frac": None,
+         "kernels": {"hand_heat_score": round(P("hand_heat_score"), 4), "hoi_aggregate_total": round(P("hoi_aggregate_total"), 4),
+                     "hoi_aggregate_total_overlapped": round(agg_overlapped_ms / args.steps, 4)}},
+    ]
+    with_roof = [s for s in stages if s.get("frac") is not None and s.get("ms")]
+    t_roof = sum(s["ms"] for s in with_roof)
+    t_all = sum(s["ms"] for s in stages if s.get("ms"))
+    e2e_frac = sum(s["frac"] * s["ms"] for s in with_roof) / t_roof if t_roof else None
     line = {
-        "metric": "hand-object pose candidates scored/sec", "value": round(value, 1), "unit": "candidates/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_res / args.steps, 4),
+        "metric": METRIC, "value": round(value, 1), "unit": "candidates/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(step_ms, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(world),
+        "config": workload_config(world, bs),
         "e2e": {"value": round(e2e, 1), "unit": "candidates/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(ms_e2e / args.steps, 4),
-                "h2d_ms_alone": round(h2d_ms, 3), "note": "H2D of step i+1 runs on a copy stream while step i computes"},
+                "h2d_ms_alone": round(h2d_ms, 3),
+                "note": "H2D of step i+1 runs on a copy stream while step i computes; the timed region also computes the "
+                        "per-image evaluation record (TesterHand / TesterObject metrics, %d float64 columns) on the device and "
+                        "reads it back with the aggregated poses" % recorder.width + ("; the final NCCL gather of the records "
+                        "is inside the timed region" if world > 1 else "")},
         "gpu_launches": int(launches),
         "clocks": clocks.summary([windows[0], windows[-1]]),
-        "roofline": {"kernel": head_kernel + " (score-network head GEMM: pose features K=256 x 8192 hidden units of the hand "
-                               "denoiser" + (" + 768 of the object denoiser, one launch" if paired else "") +
-                               ", fused bias/ReLU/256->3 heads/sigma division)",
-                     "bound": "tensor", "achieved": round(achieved, 2) if achieved else None, "peak": peaks["bf16_tflops"],
-                     "unit": "TFLOP/s", "frac": round(achieved / peaks["bf16_tflops"], 4) if achieved else None,
-                     "traffic": NCU_TRAFFIC_BYTES.get(head_kernel), "peak_source": peaks["source"] + " (cuBLAS bf16 burst)",
-                     "note": "FP32-parity contraction run as 3 kind::f16 UMMAs per algorithmic FLOP (hi/lo FP16 planes, exact "
-                             "power-of-two scaling), i.e. the tensor pipe does 3x the algorithmic work: the measured bf16 "
-                             "peak / 3 = %.0f TFLOP/s; ncu: tensor pipe active 73 %% of elapsed, 83 %% of active cycles "
-                             "(profiles/r01_ncu_head_tc_summary.txt)" % (peaks["bf16_tflops"] / 3),
-                     "launches_timed": hg["launches"], "network_calls": real_launches, "avg_launch_ms": round(avg_ms, 4),
-                     "avg_is": "median over the real launches of a second pass of the same K steps (%.4f ms/step)" % (ms_roof / args.steps),
-                     "flop_per_launch": flop_launch,
-                     "share_of_step": round(avg_ms * info["hand"]["net_calls"] / (ms_res / args.steps), 4)},
-        "kernel_ms_per_step": {k: round(v["ms_total"] / args.steps, 4) for k, v in prof.items()},
-        "sampler": {"hand_net_calls": info["hand"]["net_calls"], "obj_net_calls": info["obj"]["net_calls"],
+        "roofline": roofline,
+        "stages": stages,
+        "stages_summary": {"serialised_ms_per_step": round(ms_serial / args.steps, 4), "sum_of_stage_ms": round(t_all, 4),
+                           "overlapped_ms_per_step": round(step_ms, 4),
+                           "time_weighted_roofline_frac": round(e2e_frac, 4) if e2e_frac is not None else None,
+                           "share_of_serialised_step_with_a_roofline": round(t_roof / (ms_serial / args.steps), 4),
+                           "how": "serialised pass: vpho_set_pdl(0), one stream, every tagged kernel bracketed by CUDA events"},
+        "peaks": peaks,
+        "sampler": {"hand_net_calls": net_calls, "obj_net_calls": info["obj"]["net_calls"],
                     "hand_attempts": info["hand"]["attempts"], "rejected": info["hand"]["rejected"] + info["obj"]["rejected"]},
         "wall_ms_per_step": round(wall_res / args.steps, 4),
     }
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         tm = {}
-        step = run_oracle(BS, 0, timing=tm)
+        step = run_oracle(bs, 0, timing=tm)
+        step()                                   # warm (first-call overheads of torch / scipy)
         t, out = step()
-        line["cpu_baseline"] = {"value": round(BS * S / t, 2), "unit": "candidates/s", "cores": torch.get_num_threads(),
-                                "kind": "port", "sample": f"one full step ({BS} images x {S} candidates), single cold run, "
-                                f"{t:.1f} s", "split_s": {k: round(v, 2) for k, v in tm.items()},
+        line["cpu_baseline"] = {"value": round(bs * S / t, 2), "unit": "candidates/s", "cores": torch.get_num_threads(),
+                                "kind": "port", "sample": f"one full step ({bs} images x {S} candidates) after one warm step, {t:.1f} s",
+                                "split_s": {k: round(v, 2) for k, v in tm.items()},
                                 "net_calls": out["_info"]["hand"]["net_calls"]}
+        if bs != 1:
+            s1 = run_oracle(1, 0)
+            s1()
+            t1 = statistics.median([s1()[0] for _ in range(5)])
+            line["cpu_baseline"]["config1_bs1"] = {"value": round(S / t1, 2), "unit": "candidates/s",
+                                                   "sample": "BASELINE configs[0]: batch 1 x 100 x 50, median of 5 warm runs"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# config 3: MANO LBS + contact microbench; config 5: pseudo-force evaluation
+# ---------------------------------------------------------------------------------------------------------------------
+def _timed(fn, reps=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return statistics.median([a.elapsed_time(b) for a, b in ev])
+
+
+def config3_arm(args):
+    """candidates in {6400, 25600, 102400, 409600} x object points in {2048, 4096, 8192}:
+    (a) LBS, vertices materialised (HBM roofline: 9820 algorithmic bytes per candidate);
+    (b) LBS + 32 force anchors + anchor contact scoring (the reference's semantics, aggregation.py:553-590);
+    (c) dense 778-vertex x object-point nearest distance (stress superset; 8 FLOP per pair, FP32 CUDA cores).
+    Inputs of every case are far larger than L2 from 25 600 candidates up (verts alone: 239 MB)."""
+    from vpho_b200 import capi
+    from vpho_b200 import synthetic as syn
+    from vpho_b200.aggregation import Assets, HeadPhysics, anchor_contact, vertex_contact
+    from vpho_b200.head_mano import HeadMano
+    lib = capi.lib()
+    peaks = _peaks(lib)
+    mano = syn.make_mano_model()
+    anch, objs = syn.make_anchor_assets(mano), syn.make_object_tables()
+    hm, phys = HeadMano(mano), HeadPhysics(Assets(anch, objs))
+    Cn = 100
+    results = []
+    clocks = ClockSampler(0)
+    clocks.start()
+    t0 = time.perf_counter()
+    head = None
+    for n in (6400, 25600, 102400, 409600):
+        G = n // Cn
+        g = torch.Generator(device="cuda").manual_seed(n)
+        pose = torch.randn(n, 48, device="cuda", generator=g) * 0.4
+        shape = torch.randn(n, 10, device="cuda", generator=g)
+        root = torch.tensor([0.03, -0.02, 0.6], device="cuda")
+        fl = torch.rand(G, Cn, 32, 3, device="cuda", generator=g) * 0.3
+        verts = torch.empty((n, 778, 3), device="cuda")
+        joints = torch.empty((n, 21, 3), device="cuda")
+
+        def lbs():
+            lib.check(lib.c.vpho_mano_forward(hm.handle, capi.ptr(pose), capi.ptr(shape), n, capi.ptr(verts), capi.ptr(joints),
+                                              capi.stream_of(pose)), "vpho_mano_forward")
+        ms = _timed(lbs, reps=args.steps, warm=max(args.warmup, 3))
+        row = {"case": "a_lbs_verts", "candidates": n, "ms": round(ms, 4), "GBps": round(n * MANO_BYTES / ms / 1e6, 1),
+               "frac_hbm": round(n * MANO_BYTES / ms / 1e6 / peaks["hbm_gbs"], 4), "TFLOPs": round(n * MANO_FLOP / ms / 1e9, 2)}
+        results.append(row)
+        if n == 6400:
+            head = row
+        for Pn in (2048, 4096, 8192):
+            obj = root + torch.tensor([0.07, 0.0, 0.02], device="cuda") + 0.05 * torch.randn(G, Pn, 3, device="cuda", generator=g)
+            vc = verts.view(G, Cn, 778, 3)
+
+            def fused():
+                lbs()
+                fp, fgl = phys.from_local_to_global(fl, vc)      # verts are wrist-centred here: geometry-only timing
+                anchor_contact(fp, fgl, obj)
+            ms_b = _timed(fused, reps=args.steps, warm=3)
+            results.append({"case": "b_lbs_anchor_contact", "candidates": n, "points": Pn, "ms": round(ms_b, 4),
+                            "cand_per_s": round(n / ms_b * 1e3), "Gpairs_per_s": round(n * 32 * Pn / ms_b / 1e6, 1)})
+            ms_c = _timed(lambda: vertex_contact(vc, obj), reps=3, warm=1)
+            tf = n * 778 * Pn * PAIR_FLOP / ms_c / 1e9
+            results.append({"case": "c_dense_vertex_contact", "candidates": n, "points": Pn, "ms": round(ms_c, 3),
+                            "Gpairs_per_s": round(n * 778 * Pn / ms_c / 1e6, 1), "TFLOPs_8_per_pair": round(tf, 2),
+                            "frac_fp32": round(tf / peaks["fp32_fma_tflops"], 4) if peaks.get("fp32_fma_tflops") else None})
+        del pose, shape, fl, verts, joints
+        torch.cuda.empty_cache()
+    clocks.stop_flag.set()
+    clocks.join(timeout=2)
+    traffic, traffic_file = _ncu_traffic()
+    line = {"metric": "MANO LBS candidates/sec (vertices materialised), 6400 candidates", "value": round(6400 / head["ms"] * 1e3, 1),
+            "unit": "candidates/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: MANO LBS + hand-object contact scoring microbench, candidates "
+                                   "{6400, 25600, 102400, 409600} x object points {2048, 4096, 8192}",
+                       "l2": "inputs larger than L2 from 25 600 candidates up; the 6400-candidate case (60 MB of vertices) is the "
+                             "shape the hot path runs"},
+            "roofline": {"kernel": "mano_forward (blend shapes + pose correctives + LBS, vertices written)", "bound": "hbm",
+                         "achieved": head["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": head["frac_hbm"],
+                         "traffic": traffic.get("mano_forward"), "traffic_source": traffic_file},
+            "results": results, "peaks": peaks, "clocks": clocks.summary([(t0, time.perf_counter())]),
+            "gpu_launches": int(lib.c.vpho_launch_count())}
+    print(json.dumps(line), flush=True)
+
+
+def config5_arm(args):
+    """BASELINE configs[4]: the forward terms of one ForceOptimizer.optimize_batch iteration
+    (lib/engine/force_optimization.py:141-171) for 64 x 100 posed hands, and the physics3 object score
+    (lib/model/aggregation.py:947-997) of 64 x 100 recombined poses against dense 8192-point object clouds."""
+    from vpho_b200 import capi
+    from vpho_b200 import synthetic as syn
+    from vpho_b200.aggregation import Assets, HOI_Aggregator, force_eval
+    from vpho_b200.head_mano import HeadMano
+    lib = capi.lib()
+    peaks = _peaks(lib)
+    n_pts = 8192
+    mano, anchors, objects, batch, prior_h, prior_o, st_h, st_o = make_inputs(BS, 0, n_pts=n_pts)
+    hm, assets = HeadMano(mano), Assets(anchors, objects)
+    n = BS * S
+    g = torch.Generator(device="cuda").manual_seed(0)
+    pose = torch.randn(n, 48, device="cuda", generator=g) * 0.3
+    shape = torch.randn(n, 10, device="cuda", generator=g)
+    verts, _ = hm.get_hand_verts(pose=pose, shape=shape)
+    verts = verts + torch.tensor([0.02, -0.01, 0.6], device="cuda")
+    scale = torch.randn(n, 32, device="cuda", generator=g)
+    weight = torch.randn(n, 32, 8, device="cuda", generator=g)
+    mask = torch.rand(n, 32, device="cuda", generator=g) < 0.5
+    fc = torch.rand(n, 32, device="cuda", generator=g)
+    grav = torch.tensor([0.0, -9.8, 0.0], device="cuda").repeat(n, 1)
+    com = verts.mean(1)
+    clocks = ClockSampler(0)
+    clocks.start()
+    t0 = time.perf_counter()
+    ms_force = _timed(lambda: force_eval(assets, verts, scale, weight, mask, fc, grav, com), reps=args.steps, warm=max(args.warmup, 3))
+    # physics3 at K_obj = 10 -> 100 recombined poses per image, 8192 points: through the aggregator (its physics3 kernel is tagged)
+    kw = dict(cam_intrinsic=batch["cam_intr_crop_flip"], root_joint_flip=batch["root_joint_flip"], root_joint=batch["root_joint"],
+              is_right=batch["is_right"], force_local=batch["force_local"], is_grasped=batch["is_grasped"],
+              hand_pose_regression=batch["pd_mano_pose"], hand_heatmap=batch["hm_hand"], hand_bbox=batch["bbox_hand"],
+              obj_heatmap=batch["hm_obj"], obj_bbox=batch["bbox_obj_rect"])
+    kw = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in kw.items()}
+    kw.update(hand_pose_diff=pose, hand_shape=shape, hand_topk=K_HAND, obj_topk=K_OBJ,
+              obj_pose6d=torch.randn(BS, S, 9, device="cuda", generator=g, dtype=torch.float64) * 0.05,
+              obj_name=np.asarray(batch["obj_id"], np.int32))
+    agg = HOI_Aggregator(hm, assets)
+    for _ in range(3):
+        agg(**kw)
+    torch.cuda.synchronize()
+    lib.c.vpho_profile_reserve(4096)
+    lib.c.vpho_set_pdl(0)
+    lib.c.vpho_profile_enable(1 << 4)
+    for _ in range(args.steps):
+        agg(**kw)
+    torch.cuda.synchronize()
+    lib.c.vpho_profile_enable(0)
+    lib.c.vpho_set_pdl(1)
+    tot, cnt = C.c_double(0), C.c_int(0)
+    lib.c.vpho_profile_collect(4, C.byref(tot), C.byref(cnt))
+    ms_phys = tot.value / max(cnt.value, 1)
+    clocks.stop_flag.set()
+    clocks.join(timeout=2)
+    pairs = BS * K_OBJ * K_OBJ * 32 * n_pts
+    tf = pairs * PAIR_FLOP / ms_phys / 1e9
+    line = {"metric": "pseudo-force contact evaluations/sec (force_optim.py forward terms, 64x100 candidates)",
+            "value": round(n / ms_force * 1e3, 1), "unit": "candidates/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_force, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[4]: force_optim.py pseudo-force contact evaluation over 64x100 candidates "
+                                   "+ physics3 score of 64x100 poses against 8192-point object clouds",
+                       "l2": "hand meshes 60 MB per pass; the 8192-point clouds are posed on the fly (98 KB per object table)"},
+            "force_eval": {"ms": round(ms_force, 4), "candidates": n, "bytes": n * (778 * 3 * 4 + 32 * 4 * 10),
+                           "GBps": round(n * (778 * 3 * 4 + 32 * 4 * 10) / ms_force / 1e6, 1),
+                           "frac_hbm": round(n * (778 * 3 * 4 + 32 * 4 * 10) / ms_force / 1e6 / peaks["hbm_gbs"], 4)},
+            "roofline": {"kernel": "k_obj_physics3 (32 anchors x 8192 on-the-fly posed points x 100 poses per image)", "bound": "fp32",
+                         "achieved": round(tf, 2), "peak": peaks.get("fp32_fma_tflops"), "unit": "TFLOP/s",
+                         "frac": round(tf / peaks["fp32_fma_tflops"], 4) if peaks.get("fp32_fma_tflops") else None,
+                         "traffic": None, "avg_launch_ms": round(ms_phys, 4), "pairs_per_launch": pairs,
+                         "peak_source": "vpho_measure_peaks (back-to-back FFMA on every SM)"},
+            "peaks": peaks, "clocks": clocks.summary([(t0, time.perf_counter())]), "gpu_launches": int(lib.c.vpho_launch_count())}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -422,8 +705,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.config == 4:
+        args.config = 2          # config 4 is config 2 launched on N GPUs
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -432,6 +718,11 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    if args.config in (3, 5):
+        if rank == 0:
+            torch.cuda.set_device(local_rank)
+            (config3_arm if args.config == 3 else config5_arm)(args)
+        return
     cuda_arm(args, rank, world, local_rank)
 
 

@@ -25,11 +25,21 @@ typedef void* vpho_assets_t;    /* force-anchor tables + object point tables  */
 
 int vpho_version(void);
 
+/* Measured peaks of THIS device at the clock a short kernel runs at, in TFLOP/s: back-to-back FP32 FMAs on every SM (the
+ * bound of the contact scans) and back-to-back tcgen05 kind::f16 UMMAs M128 N256 K16 with FP32 accumulation on every SM
+ * (the bound of the 3xFP16 score network).  Best of `reps` launches, timed with CUDA events on `stream`. */
+int vpho_measure_peaks(float* fp32_fma_tflops, float* f16_umma_tflops, int reps, void* stream);
+
+/* Programmatic dependent launch (kernel N+1's prologue overlapping kernel N's tail) is on by default; 0 turns it off so that
+ * per-kernel CUDA-event brackets measure isolated durations (bench.py's serialised breakdown pass). */
+int vpho_set_pdl(int enabled);
+
 /* Bookkeeping for benchmarks: number of kernels this library has launched since it was loaded, and optional CUDA-event
  * brackets around tagged kernels (recorded on the launching stream).  vpho_profile_collect synchronises on the recorded
  * events of `tag`, returns their summed duration and count, and clears them.
  * tags: 0 hand head-GEMM, 1 object head-GEMM, 2 pose encoder (incl. 6), 3 MANO skinning, 4 physics3 scan, 5 hand heat-map
- * scorer, 6 stage-input + time-term, 7 feat-term, 8 RK error norm / controller / dense output, 9 whole vpho_hoi_aggregate */
+ * scorer, 6 stage-input + time-term, 7 feat-term, 8 RK error norm / controller / dense output, 9 whole vpho_hoi_aggregate,
+ * 10 hand-physics contact scan, 11 trajectory post-processing (6D -> axis-angle) */
 unsigned long long vpho_launch_count(void);
 int vpho_profile_reserve(int n_events);  /* pre-create the event pool (keeps event creation out of timed regions) */
 int vpho_profile_enable(int tag_mask);   /* bit t set: record tag t; 0 = off; -1 = every tag */

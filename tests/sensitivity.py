@@ -52,22 +52,51 @@ def run_oracle(assets, kw: dict, dtype=torch.float32) -> dict:
     return O.hoi_aggregate(O.OracleMano(mano), O.OracleObject(objs), O.OracleAnchors(anch), **kw)
 
 
+# score arrays behind each family of top-k lists (names as tests/parity.py reports them)
+SCORE_OF = {"obj_transl_topk": "obj_transl_score", "obj_rot_topk": "obj_rot_score", "phys_topk": "phys_score",
+            "heat5_topk": "heat5_score", "hand physics finger top-k": "finger_score"}
+
+
+def _score_arrays(res: dict) -> Dict[str, torch.Tensor]:
+    od = res["_dbg"]
+    out = {f"hand cascade level {lv}": od["cascade"]["levels"][lv]["score"] for lv in range(4)}
+    out.update({name: od[key] for name, key in SCORE_OF.items()})
+    return out
+
+
+def _score_dev(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """per image: largest change of any candidate's score, relative to the image's score scale (as topk_agreement scales)"""
+    bs = a.shape[0]
+    a, b = a.double().reshape(bs, -1), b.double().reshape(bs, -1)
+    return (a - b).abs().amax(dim=1) / b.abs().amax(dim=1).clamp(min=1e-30)
+
+
 def oracle_sensitivity(assets, kw: dict, ref: dict, n_ulp: int = 3, seed: int = 0) -> Dict[str, torch.Tensor]:
     """ref = run_oracle(assets, kw).  -> {key: (bs,) float64 noise floor of the reference's own result}, plus
-    '_runs': the individual shadow deviations, for the report."""
+    '_runs': the individual shadow deviations (for the report), '_f64': the float64 shadow's outputs, and '_score_dev':
+    {list family: (bs,)} how far the reference's OWN candidate scores move between the shadow runs (every cascade level after
+    the first ranks candidates whose parent joints were fused by the levels before, so the scores inherit the rounding
+    noise of those fusions): the derived near-tie band of that family's top-k lists."""
     runs: List[Dict[str, torch.Tensor]] = []
+    base_scores = _score_arrays(ref)
+    devs = {k: [] for k in base_scores}
+
+    def account(res):
+        runs.append({k: _per_image(res[k], ref[k]) for k in KEYS})
+        for k, v in _score_arrays(res).items():
+            devs[k].append(_score_dev(v, base_scores[k]))
     sh = run_oracle(assets, kw, torch.float64)
-    runs.append({k: _per_image(sh[k], ref[k]) for k in KEYS})
+    account(sh)
     g = torch.Generator().manual_seed(1234 + seed)
     for _ in range(n_ulp):
         kp = cases.clone_kw(kw)
         for k in ("hand_pose_diff", "hand_pose_regression", "obj_pose6d", "hand_heatmap", "obj_heatmap"):
             kp[k] = _ulp_perturb(kp[k], g)
-        pr = run_oracle(assets, kp)
-        runs.append({k: _per_image(pr[k], ref[k]) for k in KEYS})
+        account(run_oracle(assets, kp))
     floor = {k: torch.stack([r[k] for r in runs]).amax(dim=0) for k in KEYS}
     floor["_runs"] = runs
     floor["_f64"] = sh
+    floor["_score_dev"] = {k: torch.stack(v).amax(dim=0) for k, v in devs.items()}
     return floor
 
 

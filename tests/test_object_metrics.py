@@ -65,6 +65,17 @@ def test_object_metrics_oracle_matches_reference_fixture():
     assert tables["sym_R"].shape[1] == 628          # identity x 314 continuous steps x one discrete half-turn (object 5)
 
 
+def test_product_symmetry_tables_equal_the_oracle_tables():
+    # vpho_b200.evaluation.symmetry_tables (what a user feeds ObjectMetrics) vs the oracle restatement, itself checked
+    # against TesterObject.R / .t of the reference in the build container (oracle/make_golden.py)
+    from vpho_b200 import synthetic as syn
+    mano, anch, objs = cases.assets()
+    a, b = syn.make_metric_tables(objs), OM.synthetic_metric_tables(objs)
+    assert np.abs(a["sym_R"] - b["sym_R"]).max() < 1e-15 and np.abs(a["sym_t"] - b["sym_t"]).max() < 1e-18
+    assert np.array_equal(a["sym_count"], b["sym_count"]) and np.array_equal(a["bbox3d"], b["bbox3d"])
+    assert np.array_equal(a["diameter"], b["diameter"])
+
+
 def test_object_metrics_emulated(emu_lib):
     inp = cases.object_metric_case()
     small = {k: v[:2, :2] if k == "pd_rt" else v[:2] for k, v in inp.items()}      # the emulator is slow: 2 images x 2 candidates

@@ -48,6 +48,8 @@ class HoiArgs(C.Structure):
 _SIGNATURES = {
     "vpho_version": (c_int, []),
     "vpho_launch_count": (C.c_ulonglong, []),
+    "vpho_measure_peaks": (c_int, [C.POINTER(c_float), C.POINTER(c_float), c_int, c_void_p]),
+    "vpho_set_pdl": (c_int, [c_int]),
     "vpho_profile_reserve": (c_int, [c_int]),
     "vpho_profile_enable": (c_int, [c_int]),
     "vpho_profile_collect": (c_int, [c_int, C.POINTER(c_double), C.POINTER(c_int)]),

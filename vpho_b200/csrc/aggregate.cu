@@ -799,10 +799,14 @@ static int run_hoi_enqueue(const ManoModelDev& m, AssetsHost& ah, const HoiDev& 
   // library-owned side stream next to the hand cascade and are joined before the physics score of the recombined poses.
   cudaStream_t so = st;
 #ifndef VPHO_EMU
-  cudaStream_t side = ah.side;
+  // vpho_set_pdl(0) (bench.py's serialised per-kernel pass) also keeps the object branch on the caller's stream
+  const bool fork = pdl_enabled();
+  cudaStream_t side = fork ? ah.side : st;
   cudaEvent_t ev_fork = ah.ev_fork, ev_join = ah.ev_join;
-  if (cudaEventRecord(ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(side, ev_fork, 0) != cudaSuccess) return VPHO_ERR_LAUNCH;
-  *forked = true;
+  if (fork) {
+    if (cudaEventRecord(ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(side, ev_fork, 0) != cudaSuccess) return VPHO_ERR_LAUNCH;
+    *forked = true;
+  }
   so = side;
 #endif
   // ---- object: translation, rotation, recombination (aggregation.py:1200-1242)
@@ -814,7 +818,7 @@ static int run_hoi_enqueue(const ManoModelDev& m, AssetsHost& ah, const HoiDev& 
   if (a.dbg_obj_score) VPHO_LAUNCH(k_copy_f32, dim3((bs * S + 255) / 256), dim3(256), 0, so, h.oscore, a.dbg_obj_score + (size_t)1 * bs * omax, bs * S);
   VPHO_LAUNCH_PDL(k_obj_recombine<EL>, dim3(bs), dim3(32), 0, so, h);
 #ifndef VPHO_EMU
-  if (cudaEventRecord(ev_join, side) != cudaSuccess) return VPHO_ERR_LAUNCH;
+  if (fork && cudaEventRecord(ev_join, side) != cudaSuccess) return VPHO_ERR_LAUNCH;
 #endif
   // ---- hand heat-map cascade (aggregation.py:115-178)
   for (int level = 0; level < 4; ++level) {
@@ -834,7 +838,7 @@ static int run_hoi_enqueue(const ManoModelDev& m, AssetsHost& ah, const HoiDev& 
   if (a.dbg_force_point) VPHO_LAUNCH(k_copy_f32, dim3((bs * 96 + 255) / 256), dim3(256), 0, st, h.fpoint, a.dbg_force_point, bs * 96);
   if (a.dbg_force_global) VPHO_LAUNCH(k_copy_f32, dim3((bs * 96 + 255) / 256), dim3(256), 0, st, h.fglobal, a.dbg_force_global, bs * 96);
 #ifndef VPHO_EMU
-  if (cudaStreamWaitEvent(st, ev_join, 0) != cudaSuccess) return VPHO_ERR_LAUNCH;
+  if (fork && cudaStreamWaitEvent(st, ev_join, 0) != cudaSuccess) return VPHO_ERR_LAUNCH;
   *forked = false;           // joined
 #endif
   // ---- object: physics / heat-map selection of the recombined candidates, fusion (aggregation.py:1247-1287)
@@ -854,7 +858,9 @@ static int run_hoi_enqueue(const ManoModelDev& m, AssetsHost& ah, const HoiDev& 
   if (rc) return rc;
   VPHO_LAUNCH_PDL(k_force_anchors, dim3(bs * h.nc), dim3(256), 0, st, as, h.pverts, a.root_joint_flip, a.force_local, bs * h.nc,
               h.nc, h.ppoint, h.pforce);
+  profile_begin(VPHO_TAG_HAND_PHYS, st);
   VPHO_LAUNCH_PDL(k_hand_phys_score, dim3(h.nc, bs), dim3(kScanThreads), 0, st, h);
+  profile_end(VPHO_TAG_HAND_PHYS, st);
   VPHO_LAUNCH_PDL(k_hand_phys_fuse<EL>, dim3(bs), dim3(160), 0, st, h);
   VPHO_CHECK_LAUNCH();
   return mano_forward_dev(m, a.hand_agg_mano, a.hand_agg_mano + 48, 58, 58, bs, a.hand_agg_vert, a.hand_agg_joint, st);

@@ -43,7 +43,19 @@ void profile_end(int tag, cudaStream_t st) {
 
 using namespace vpho;
 
-extern "C" int vpho_version(void) { return 100; }
+namespace vpho { int tc_measure_peaks(float* fp32_tflops, float* f16_tflops, int reps, cudaStream_t st); }
+
+extern "C" int vpho_version(void) { return 200; }
+
+extern "C" int vpho_measure_peaks(float* fp32_fma_tflops, float* f16_umma_tflops, int reps, void* stream) {
+  if (!fp32_fma_tflops || !f16_umma_tflops || reps < 1) return VPHO_ERR_INVALID;
+  return vpho::tc_measure_peaks(fp32_fma_tflops, f16_umma_tflops, reps, (cudaStream_t)stream);
+}
+
+extern "C" int vpho_set_pdl(int enabled) {
+  vpho::pdl_override() = enabled ? 1 : 0;
+  return VPHO_OK;
+}
 
 extern "C" unsigned long long vpho_launch_count(void) { return g_launches; }
 

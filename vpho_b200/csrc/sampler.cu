@@ -1283,8 +1283,10 @@ static int postprocess_hand(const TIn* xs, int n_steps, int n_rows, int rows_per
   const size_t total = (size_t)n_steps * n_rows * 17;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 64) blocks = 148 * 64;
+  profile_begin(VPHO_TAG_POSTPROCESS, (cudaStream_t)stream);
   VPHO_LAUNCH(k_postprocess_hand<TIn>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, xs, n_steps, n_rows, rows_per_shape,
               shape, out);
+  profile_end(VPHO_TAG_POSTPROCESS, (cudaStream_t)stream);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }

@@ -887,6 +887,109 @@ k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CU
   else pose_tc_tile(&tmX_hi1, &tmX_lo1, &tmW1_hi1, &tmW1_lo1, &tmW2_hi1, &tmW2_lo1, dn1, ws1, mode, s, (int)blockIdx.x - tiles0);
 }
 
+// =====================================================================================================================
+// Measured peaks for the rooflines bench.py reports ("TF32/FP32-SIMT peaks to be measured the same way on the
+// box"): back-to-back FP32 FMAs on every SM, and back-to-back kind::f16 UMMAs (M128 N256 K16, operands resident in shared
+// memory, FP32 accumulate in TMEM) on every SM -- the rates the contact scans and the 3xFP16 score network are bounded by at
+// the clock a short kernel actually runs at.
+// =====================================================================================================================
+__global__ void __launch_bounds__(1024) k_peak_fp32(float* sink, int iters) {
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = (float)(threadIdx.x + j) * 1e-3f;
+  const float b = 1.0000001f, c = 1e-9f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], b, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += a[j];
+  if (s == 123.456f) sink[0] = s;        // never true: keeps the chain alive
+}
+
+constexpr int kPeakSmem = 120 * 1024;    // more than half an SM's shared memory: one CTA per SM
+__global__ void __launch_bounds__(128, 1) k_peak_umma_f16(int n_groups) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* a = base;                       // [128 rows][64 half]  16 KB, K-major SWIZZLE_128B
+  unsigned char* b = base + kTcABytes;           // [256 rows][64 half]  32 KB
+  __shared__ unsigned long long bar;
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < (kTcABytes + kTcBBytes) / 16; i += blockDim.x) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 1 && lane == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 1 && lane == 0) {
+    const uint64_t ad = make_kmajor_sw128_desc(a), bd = make_kmajor_sw128_desc(b);
+    for (int g = 0; g < n_groups; ++g) {
+      const uint32_t d = tmem_base + (uint32_t)((g & 1) * kTcBN);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {               // 4 x K16 inside the 128-byte rows
+        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+        umma_f16(d, ad + adv, bd + adv, kTcIdescF16, (g > 1 || k > 0) ? 1u : 0u);
+      }
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// -> TFLOP/s of each (best of `reps` timed launches after a warm-up one), measured with CUDA events on `st`
+int tc_measure_peaks(float* fp32_tflops, float* f16_tflops, int reps, cudaStream_t st) {
+  int dev = 0, n_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return VPHO_ERR_LAUNCH;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (n_sm <= 0) n_sm = 148;
+  if (cudaFuncSetAttribute(k_peak_umma_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, kPeakSmem) != cudaSuccess) return VPHO_ERR_LAUNCH;
+  float* sink = nullptr;
+  if (cudaMalloc((void**)&sink, 256) != cudaSuccess) return VPHO_ERR_ALLOC;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 1 << 15, n_groups = 1 << 13;
+  float best32 = 1e30f, best16 = 1e30f;
+  for (int r = 0; r <= reps; ++r) {
+    float ms = 0.f;
+    cudaEventRecord(e0, st);
+    k_peak_fp32<<<2 * n_sm, 1024, 0, st>>>(sink, iters);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best32) best32 = ms;
+    cudaEventRecord(e0, st);
+    k_peak_umma_f16<<<n_sm, 128, kPeakSmem, st>>>(n_groups);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best16) best16 = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  if (cudaGetLastError() != cudaSuccess) return VPHO_ERR_LAUNCH;
+  *fp32_tflops = (float)((double)2 * n_sm * 1024.0 * iters * 8 * 2 / (best32 * 1e-3) / 1e12);
+  *f16_tflops = (float)((double)n_sm * n_groups * 4.0 * (2.0 * kTcBM * kTcBN * 16) / (best16 * 1e-3) / 1e12);
+  return VPHO_OK;
+}
+
 // -------------------------------------------------------------------------------------------------- host side
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;

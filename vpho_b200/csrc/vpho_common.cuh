@@ -29,11 +29,12 @@ namespace vpho {
 // its writes are visible.  VPHO_NO_PDL=1 falls back to plain stream-ordered launches.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-inline bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("VPHO_NO_PDL"); on = (e && e[0] == '1') ? 0 : 1; }
-  return on == 1;
+// programmatic dependent launch is on by default; vpho_set_pdl(0) turns it off (bench.py's serialised per-kernel pass)
+inline int& pdl_override() {
+  static int v = 1;
+  return v;
 }
+inline bool pdl_enabled() { return pdl_override() == 1; }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -94,7 +95,9 @@ inline void cp_async_wait() {}
 #define VPHO_TAG_FEAT_TERM 7
 #define VPHO_TAG_RK_CONTROL 8
 #define VPHO_TAG_AGGREGATE 9
-#define VPHO_NUM_TAGS 10
+#define VPHO_TAG_HAND_PHYS 10
+#define VPHO_TAG_POSTPROCESS 11
+#define VPHO_NUM_TAGS 12
 
 #define VPHO_OK 0
 #define VPHO_ERR_INVALID (-1)

@@ -23,6 +23,46 @@ from .aggregation import OBJ_METRIC_COLS, Assets, ObjectMetrics, obj_6d_to_rt
 HAND_COLS = ["MJE", "PA_MJE", "MVE", "PAMVE"] + [f"MJE_{i}" for i in range(21)]
 
 
+def symmetry_tables(model_infos, max_sym_disc_step: float = 0.01):
+    """The padded symmetry-transform tables `TesterObject.__init__` builds from assets_models_info.json
+    (lib/engine/test.py:205-232 with get_symmetry_transformations :97-152): per object the identity and its discrete
+    symmetries, each composed with the continuous symmetries discretised into ceil(pi / max_sym_disc_step) rotations about
+    the given axis; shorter lists are padded with identities; translations millimetres -> metres.
+    -> sym_R (N, K, 3, 3), sym_t (N, K, 3) float64, sym_count (N,) int32  (inputs of `ObjectMetrics`)."""
+    import math
+    import numpy as np
+
+    def about_axis(angle, axis):
+        a = np.asarray(axis[:3], np.float64)
+        a = a / math.sqrt(float(a @ a))
+        c, s = math.cos(angle), math.sin(angle)
+        skew = np.array([[0.0, -a[2], a[1]], [a[2], 0.0, -a[0]], [-a[1], a[0], 0.0]])
+        return np.diag([c, c, c]) + np.outer(a, a) * (1.0 - c) + skew * s
+
+    per = []
+    for info in model_infos:
+        discrete = [(np.eye(3), np.zeros(3))]
+        for sym in info.get("symmetries_discrete", []):
+            m = np.asarray(sym, np.float64).reshape(4, 4)
+            discrete.append((m[:3, :3], m[:3, 3]))
+        continuous = []
+        for sym in info.get("symmetries_continuous", []):
+            off = np.asarray(sym["offset"], np.float64).reshape(3)
+            n_steps = int(np.ceil(np.pi / max_sym_disc_step))
+            for i in range(1, n_steps):
+                R = about_axis(i * (2.0 * np.pi / n_steps), sym["axis"])
+                continuous.append((R, off - R @ off))
+        combos = [(Rc @ Rd, Rc @ td + tc) for Rd, td in discrete for Rc, tc in continuous] if continuous else discrete
+        per.append(combos)
+    K = max(len(c) for c in per)
+    sym_R = np.tile(np.eye(3), (len(per), K, 1, 1))
+    sym_t = np.zeros((len(per), K, 3))
+    for i, combos in enumerate(per):
+        for k, (R, t) in enumerate(combos):
+            sym_R[i, k], sym_t[i, k] = R, t / 1000.0
+    return sym_R, sym_t, np.asarray([len(c) for c in per], np.int32)
+
+
 def postprocess_hand_vert(vert: torch.Tensor, root_joint: torch.Tensor, is_right: torch.Tensor) -> torch.Tensor:
     """`Trainer.__postprocess_hand_vert` (train_diff_hand_obj.py:598-602): un-flip left hands, add the root joint.
     vert (bs, ..., V, 3) wrist-relative in the flipped frame -> camera frame.  Returns a new tensor."""

@@ -339,3 +339,28 @@ def make_eval_ground_truth(batch: Dict[str, object], head_mano, objects: Dict[st
     K = T("cam_intr_crop_flip").float()
     return {"gt_joint": j + root[:, None], "gt_hand_vert": v + root[:, None], "gt_obj_rt": gt_rt, "cam_intr": K}
 
+
+def make_metric_tables(objects: Dict[str, object]) -> Dict[str, object]:
+    """Synthetic stand-ins for what `TesterObject` reads per object (lib/engine/test.py:196-232): YCB_MESHES[name]['bbox3d'
+    / 'diameter'] and asset/2023_NIPS_DeepSimHO/assets_models_info.json -- box corners and diagonal of the sampled surface and
+    a mix of symmetry classes (none / one discrete half-turn / a continuous axis / both)."""
+    from .evaluation import symmetry_tables
+    verts = np.asarray(objects["verts_sampled"], np.float64)
+    N = verts.shape[0]
+    lo, hi = verts.min(1), verts.max(1)
+    corners = np.array([[(hi if (c >> a) & 1 else lo)[:, a] for a in range(3)] for c in range(8)])     # (8, 3, N)
+    diameter = np.sqrt(((hi - lo) ** 2).sum(-1))
+    infos = []
+    for i in range(N):
+        mi = {"diameter": float(diameter[i] * 1000)}
+        if i % 3 == 1:
+            mi["symmetries_discrete"] = [[-1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]]
+        if i % 3 == 2:
+            mi["symmetries_continuous"] = [{"axis": [0, 0, 1], "offset": [0, 0, 0]}]
+        if i % 6 == 5:
+            mi["symmetries_discrete"] = [[1, 0, 0, 0, 0, -1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1]]
+        infos.append(mi)
+    sR, st, cnt = symmetry_tables(infos)
+    return {"bbox3d": np.transpose(corners, (2, 0, 1)).astype(np.float32), "diameter": diameter.astype(np.float32),
+            "sym_R": sR, "sym_t": st, "sym_count": cnt, "model_info": infos}
+

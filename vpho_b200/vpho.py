@@ -38,6 +38,9 @@ class VphoHotPath:
         self.last_info: dict = {}
         self._side_stream2 = None
         self._agg_stream = None
+        # True: everything on the caller's stream (no output-only side stream, no high-priority aggregation stream);
+        # bench.py's serialised per-kernel pass uses it together with vpho_set_pdl(0).  Results are identical.
+        self.serialize = False
 
     # ---- vpho_net.postprocess_diffusion_hand, branch 'mano_pose' (VPHO.py:306-331) ----
     def postprocess_diffusion_hand(self, hand_inprocess, hand_final, pd_mano_shape):
@@ -146,7 +149,7 @@ class VphoHotPath:
             pd["diff_final_hand_joint"] = fj.reshape(bs, S, 21, 3)
 
         side2 = None
-        if main is not None:
+        if main is not None and not self.serialize:
             if self._side_stream2 is None:
                 self._side_stream2 = torch.cuda.Stream(device=enc_h.device)
             side2 = self._side_stream2

@@ -265,16 +265,19 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     # stream, double-buffered -- what a prefetching eval loop does), computes the evaluation record on the device and
     # reads the record and the aggregated poses back.
     copy_stream = torch.cuda.Stream(device=dev)
+    eval_stream = torch.cuda.Stream(device=dev)          # the metric step of batch i runs beside the samplers of batch i+1
     dev_sets = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()} for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    for e in consumed:
-        e.record()
+    consumed = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]     # by the compute stream, by the eval stream
+    for pair in consumed:
+        for e in pair:
+            e.record()
     e2e_state = {"i": 0, "record": None}
 
     def prefetch(slot):
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])
+            for e in consumed[slot]:
+                copy_stream.wait_event(e)
             for k, v in host.items():
                 dev_sets[slot][k].copy_(v, non_blocking=True)
             ready[slot].record(copy_stream)
@@ -287,21 +290,30 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         d = dev_sets[slot]
 
         def enqueued(pd_, issue):
-            # metric step on the device (TesterHand / TesterObject rows), then the device -> host reads, all stream-ordered
-            # behind the aggregation (complete when predict's status read returns); then, once per step, the next step's
-            # H2D copies on the copy stream
-            rec = recorder(pd_, d)
-            e2e_state["record"] = rec
-            outs = dict({k: pd_[k] for k in out_keys}, eval_record=rec)
-            for k, t in outs.items():
-                if k not in host_out:
-                    host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-                host_out[k].copy_(t, non_blocking=True)
+            # metric step on the device (TesterHand / TesterObject rows) and the device -> host reads of the record and the
+            # aggregated poses, stream-ordered behind the aggregation on the eval stream (they overlap the next batch's
+            # samplers; everything is complete before the timed region ends); then, once per step, the next step's H2D
+            # copies on the copy stream
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(eval_stream):
+                eval_stream.wait_event(done)
+                used = [pd_[k] for k in out_keys] + [pd_["diff_final_hand_joint"], pd_["diff_final_hand_vert"], pd_["diff_final_obj_6d"]]
+                for t in used:
+                    t.record_stream(eval_stream)
+                rec = recorder(pd_, d)
+                e2e_state["record"] = rec
+                outs = dict({k: pd_[k] for k in out_keys}, eval_record=rec)
+                for k, t in outs.items():
+                    if k not in host_out:
+                        host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                    host_out[k].copy_(t, non_blocking=True)
+                consumed[slot][1].record(eval_stream)
             if issue == 0:
                 prefetch(slot ^ 1)
 
         pd = hp.predict(d, prior_hand=d["prior_hand"], prior_obj=d["prior_obj"], prefetch=enqueued)
-        consumed[slot].record(cur)
+        consumed[slot][0].record(cur)
         cur.synchronize()
         return pd
 
@@ -329,6 +341,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         if world > 1 and gather:
             # the only collective of the path: the per-image evaluation rows (replaces gather_for_metrics,
             # train_diff_hand_obj.py:333-335)
+            torch.cuda.current_stream().wait_stream(eval_stream)
             rec = e2e_state["record"] if e2e_state["record"] is not None else recorder(last, resident)
             gathered = gather_records(rec, bs * world)
             assert gathered.shape == (bs * world, recorder.width)

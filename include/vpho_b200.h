@@ -59,6 +59,11 @@ int vpho_mano_destroy(vpho_mano_t h);
  * metres, wrist-centred.  Replaces `HeadMano.get_hand_verts` (lib/model/head_mano.py:78-87). */
 int vpho_mano_forward(vpho_mano_t h, const float* pose, const float* shape, int n, float* verts, float* joints,
                       void* stream);
+/* Same with an explicit numerical path: flags = 0 is vpho_mano_forward (tcgen05 blend when vertices are materialised);
+ * VPHO_MANO_STRICT_FP32 runs the FP32 SIMT kernel (cross-check of the tensor-core kernel; also what joints-only calls use). */
+#define VPHO_MANO_STRICT_FP32 1
+int vpho_mano_forward_ex(vpho_mano_t h, const float* pose, const float* shape, int n, float* verts, float* joints, int flags,
+                         void* stream);
 
 /* --------------------------------------------------------------------------------------------- sampler ---- */
 /* Packs a BaseDenoiser state dict (HOST pointers, float32, reference layouts -- lib/model/denoiser.py:33-66,

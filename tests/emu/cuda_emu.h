@@ -38,7 +38,8 @@ struct dim3 {
 struct float2 { float x, y; };
 struct float3 { float x, y, z; };
 struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
-struct double2 { double x, y; };
+struct __attribute__((aligned(16))) double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 struct int2 { int x, y; };
 struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
@@ -55,6 +56,7 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n); return *p ? cudaSuccess : cudaErrorInvalidValue; }

@@ -146,7 +146,16 @@ def check_hoi_derived(out: dict, dbg: dict, oracle: dict, floor: dict, *, c: flo
                 rep["near_tie"] += n
                 rep["bad"] += bad
                 if bad:
-                    rep["bad_lists"].append((name, b))
+                    # how wide a band would have accepted it (largest oracle-score gap of a swapped pair), vs the derived one
+                    oi = ours.reshape(bs, per_img, -1)[b].long()
+                    ri = ref_idx.reshape(bs, per_img, -1)[b].long()
+                    sc = ref_sc.reshape(bs, per_img, -1)[b].double()
+                    need = 0.0
+                    for r in range(per_img):
+                        scale = sc[r].abs().max().clamp(min=1e-30)
+                        need = max(need, float(((sc[r][oi[r]] - sc[r][ri[r]]).abs() / scale).max()))
+                    rep["bad_lists"].append((name, b, {"needed_band": need, "derived_band": float(band[b]),
+                                                       "oracle_score_dev": None if dev is None else float(dev[b])}))
             if n or bad:
                 clean[b] = False
 

@@ -24,8 +24,13 @@ def _check(hm, om, n, dev, seed, scale=0.5):
     assert _rel(v.cpu(), v2) < REL_TOL and _rel(j.cpu(), j2) < REL_TOL
     # per-element: relative to the hand's size (~0.1 m) so wrist-centred zeros do not blow up the ratio
     assert (v.cpu() - v2).abs().max().item() < 1e-5 * 0.2
+    # joints only (no vertices): the FP32 SIMT path.  The 16 kinematic joints are the same arithmetic on both paths; the 5
+    # fingertips are vertices, which the full path blends on tensor cores (3xFP16 split, FP32 accumulate)
     _, j3 = hm.get_hand_verts(pose=p.to(dev), shape=s.to(dev), need_verts=False)
-    assert torch.equal(j3, j)
+    tips = [4, 8, 12, 16, 20]
+    kin = [i for i in range(21) if i not in tips]
+    assert torch.equal(j3[:, kin], j[:, kin])
+    assert (j3[:, tips] - j[:, tips]).abs().max().item() < 1e-6 if n else True
 
 
 def test_mano_emulated_kernel(assets, emu_lib):
@@ -48,6 +53,21 @@ def test_mano_zero_pose_is_template(assets, emu_lib):
 def test_mano_cuda(assets, cuda_lib, n):
     hm, om = HeadMano(assets["mano"]), O.OracleMano(assets["mano"])
     _check(hm, om, n, "cuda", seed=n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 200, 1984, 6400])
+def test_mano_cuda_tensor_core_blend_matches_the_fp32_kernel(assets, cuda_lib, n):
+    """tcgen05 blend (3xFP16 operand split) vs the strict FP32 SIMT kernel (VPHO_MANO_STRICT_FP32) on the same inputs:
+    every candidate count exercises a different grid split (candidate tiles of 64 x vertex-tile groups)."""
+    hm = HeadMano(assets["mano"])
+    g = torch.Generator().manual_seed(n)
+    p = (torch.randn(n, 48, generator=g) * 0.7).cuda()
+    s = (torch.randn(n, 10, generator=g) * 1.5).cuda()
+    v1, j1 = hm.get_hand_verts(pose=p, shape=s)
+    v2, j2 = hm.get_hand_verts(pose=p, shape=s, strict_fp32=True)
+    assert (v1 - v2).abs().max().item() < 5e-7 and (j1 - j2).abs().max().item() < 5e-7
+    assert _rel(v1, v2) < 2e-6
 
 
 @pytest.mark.gpu

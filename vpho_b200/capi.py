@@ -57,6 +57,7 @@ _SIGNATURES = {
     "vpho_mano_create": (c_int, [c_void_p] * 5 + [C.POINTER(c_void_p)]),
     "vpho_mano_destroy": (c_int, [c_void_p]),
     "vpho_mano_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "vpho_mano_forward_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "vpho_denoiser_create": (c_int, [c_int] + [c_void_p] * 11 + [C.POINTER(c_void_p)]),
     "vpho_denoiser_create_ex": (c_int, [c_int] + [c_void_p] * 11 + [c_int, C.POINTER(c_void_p)]),
     "vpho_denoiser_destroy": (c_int, [c_void_p]),

@@ -17,6 +17,14 @@ struct ManoModelHost {
   float* blob = nullptr;
 };
 
+#ifndef VPHO_EMU
+// tensor-core layer (mano_tc.cu)
+int mano_tc_create(const float* v_template, const float* shapedirs, const float* posedirs, const float* weights, void** out);
+void mano_tc_destroy(void* h);
+int mano_tc_forward(const void* h, const ManoModelDev& m, const float* pose, const float* shape, int pose_stride, int shape_stride,
+                    int n, float* verts, float* joints, cudaStream_t stream);
+#endif
+
 template <int TC>
 __global__ void __launch_bounds__(kVChunkPad) mano_forward_kernel(ManoModelDev m, const float* __restrict__ pose,
                                                                   const float* __restrict__ shape, int pose_stride,
@@ -132,9 +140,14 @@ static int launch_mano_forward(const ManoModelDev& m, const float* pose, const f
 }
 
 // pose/shape rows may be strided (elements) so callers can pick e.g. candidate 0 of every image without a gather
+// Vertices materialised: the tcgen05 kernel (mano_tc.cu).  Joints only (verts == nullptr), the explicit FP32 cross-check
+// (simt = true) and the CPU emulator build: the SIMT kernel above.
 int mano_forward_dev(const ManoModelDev& m, const float* pose, const float* shape, int pose_stride, int shape_stride,
-                     int n, float* verts, float* joints, cudaStream_t stream) {
+                     int n, float* verts, float* joints, cudaStream_t stream, bool simt) {
   if (n <= 0) return VPHO_OK;
+#ifndef VPHO_EMU
+  if (verts && !simt) return mano_tc_forward(m.tc_host, m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream);
+#endif
   if (n >= 148 * 32) return launch_mano_forward<16>(m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream);
   if (n >= 148 * 4) return launch_mano_forward<8>(m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream);
   return launch_mano_forward<4>(m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream);
@@ -205,6 +218,16 @@ extern "C" int vpho_mano_create(const float* v_template, const float* shapedirs,
   mh->dev.tip_dirs = mh->dev.J_shapedirs + n_js;
   mh->dev.tip_template = mh->dev.tip_dirs + n_td;
   mh->dev.tip_weights = mh->dev.tip_template + n_tt;
+  mh->dev.tc_host = nullptr;
+#ifndef VPHO_EMU
+  {
+    // the tensor-core layer is the product path: if its planes or TMA descriptors cannot be built the creation FAILS
+    void* tc = nullptr;
+    const int rc = mano_tc_create(v_template, shapedirs, posedirs, weights, &tc);
+    if (rc != VPHO_OK) { cudaFree(mh->blob); delete mh; return rc; }
+    mh->dev.tc_host = tc;
+  }
+#endif
   *out = mh;
   return VPHO_OK;
 }
@@ -212,16 +235,24 @@ extern "C" int vpho_mano_create(const float* v_template, const float* shapedirs,
 extern "C" int vpho_mano_destroy(vpho_mano_t h) {
   if (!h) return VPHO_ERR_INVALID;
   ManoModelHost* mh = static_cast<ManoModelHost*>(h);
+#ifndef VPHO_EMU
+  mano_tc_destroy(const_cast<void*>(mh->dev.tc_host));
+#endif
   cudaFree(mh->blob);
   delete mh;
   return VPHO_OK;
 }
 
-extern "C" int vpho_mano_forward(vpho_mano_t h, const float* pose, const float* shape, int n, float* verts,
-                                 float* joints, void* stream) {
-  if (!h || n < 0) return VPHO_ERR_INVALID;
+extern "C" int vpho_mano_forward_ex(vpho_mano_t h, const float* pose, const float* shape, int n, float* verts,
+                                    float* joints, int flags, void* stream) {
+  if (!h || n < 0 || (flags & ~VPHO_MANO_STRICT_FP32)) return VPHO_ERR_INVALID;
   if (n == 0) return VPHO_OK;
   if (!pose || !shape || !joints) return VPHO_ERR_INVALID;
   return mano_forward_dev(static_cast<ManoModelHost*>(h)->dev, pose, shape, 48, 10, n, verts, joints,
-                          (cudaStream_t)stream);
+                          (cudaStream_t)stream, (flags & VPHO_MANO_STRICT_FP32) != 0);
+}
+
+extern "C" int vpho_mano_forward(vpho_mano_t h, const float* pose, const float* shape, int n, float* verts,
+                                 float* joints, void* stream) {
+  return vpho_mano_forward_ex(h, pose, shape, n, verts, joints, 0, stream);
 }

@@ -21,6 +21,7 @@ struct ManoModelDev {
   const float* tip_dirs;      // [5][3][145]       blend rows of the 5 fingertip vertices
   const float* tip_template;  // [5][3]
   const float* tip_weights;   // [5][16]
+  const void* tc_host;        // HOST pointer (opaque on the device): tables + TMA descriptors of the tensor-core kernel (mano_tc.cu)
 };
 
 // kinematic joint j (manopth order) -> slot in the 21-joint output; fingertip t -> slot

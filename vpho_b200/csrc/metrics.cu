@@ -7,8 +7,9 @@
 //   F-score x6 / CD  criterion_FSCORE   test.py:453-503
 //   ADD01d / ADDS01d / REP5             test.py:505-521
 // With these on the device the reference's evaluate loop needs nothing but the per-image metric rows from the GPU (today:
-// numpy on the host plus a `.cuda()` round trip per image).  One CTA per (candidate, image); nearest-point scans stage
-// tiles of the other cloud in shared memory as k_pose_metrics does.
+// numpy on the host plus a `.cuda()` round trip per image).  The O(P^2) nearest-point scans are split over 8 CTAs per
+// (candidate, image), tiles of the other cloud staged in shared memory; a second kernel adds the partial sums in a fixed
+// order and computes the O(P) metrics.
 #include "agg_device.cuh"
 #include "vpho_b200.h"
 
@@ -18,6 +19,9 @@
 namespace vpho {
 
 constexpr int kMetricCols = VPHO_OBJ_METRIC_COLS;
+constexpr int kMT = 256;           // threads per CTA
+constexpr int kSplit = 8;          // CTAs sharing the nearest-point scans of one (candidate, image): each owns 1/8 of the points
+constexpr int kPartCols = 16;      // partial sums per split: ADD-S, pd->gt, gt->pd distance sums, 6 + 6 threshold hit counts
 
 struct ObjMetricDev {
   int n_obj, sym_k, n_fpts;
@@ -32,13 +36,15 @@ struct ObjMetricDev {
 struct ObjMetricHost {
   ObjMetricDev dev;
   void* blob = nullptr;
+  double* part = nullptr;      // [rows][kSplit][kPartCols] partial sums of the scans, grown on demand
+  size_t part_rows = 0;
 };
 
 __device__ __forceinline__ double block_sum_d(double v, double* red) {
   const int tid = threadIdx.x;
   red[tid] = v;
   __syncthreads();
-  for (int st = 128; st > 0; st >>= 1) {
+  for (int st = kMT / 2; st > 0; st >>= 1) {
     if (tid < st) red[tid] += red[tid + st];
     __syncthreads();
   }
@@ -50,7 +56,7 @@ __device__ __forceinline__ float block_min_f(float v, float* red, bool want_max)
   const int tid = threadIdx.x;
   red[tid] = v;
   __syncthreads();
-  for (int st = 128; st > 0; st >>= 1) {
+  for (int st = kMT / 2; st > 0; st >>= 1) {
     if (tid < st) red[tid] = want_max ? fmaxf(red[tid], red[tid + st]) : fminf(red[tid], red[tid + st]);
     __syncthreads();
   }
@@ -66,21 +72,22 @@ __device__ __forceinline__ void pose_point_d(const double* rt, const float* p, d
     out[j] = (((double)p[0] * rt[j * 4 + 0] + (double)p[1] * rt[j * 4 + 1]) + (double)p[2] * rt[j * 4 + 2]) + rt[j * 4 + 3];
 }
 
-// nearest-point scan: every thread owns the points a[slab] of cloud A (posed by rtA) and scans all of cloud B (posed by rtB)
-// through shared-memory tiles; `consume(i, d)` receives the distance of point i.
+// nearest-point scan: every thread owns points of cloud A (posed by rtA) in [own_lo, own_hi) and scans all of cloud B (posed
+// by rtB) through shared-memory tiles; `consume(i, d)` receives the distance of point i.
 template <typename F>
-__device__ __forceinline__ void nearest_scan(const float* base, int n_pts, const double* rtA, const double* rtB, float4* tile, F consume) {
+__device__ __forceinline__ void nearest_scan(const float* base, int n_pts, int own_lo, int own_hi, const double* rtA, const double* rtB,
+                                             float4* tile, F consume) {
   const int tid = threadIdx.x;
-  for (int p0 = 0; p0 < n_pts; p0 += 256) {
+  for (int p0 = own_lo; p0 < own_hi; p0 += kMT) {
     const int i = p0 + tid;
     float a[3] = {0.f, 0.f, 0.f};
-    if (i < n_pts) {
+    if (i < own_hi) {
       double ad[3];
       pose_point_d(rtA, base + (size_t)i * 3, ad);
       a[0] = (float)ad[0]; a[1] = (float)ad[1]; a[2] = (float)ad[2];
     }
     float best = INFINITY;
-    for (int q0 = 0; q0 < n_pts; q0 += 256) {
+    for (int q0 = 0; q0 < n_pts; q0 += kMT) {
       __syncthreads();
       if (q0 + tid < n_pts) {
         double g[3];
@@ -88,7 +95,7 @@ __device__ __forceinline__ void nearest_scan(const float* base, int n_pts, const
         tile[tid] = make_float4((float)g[0], (float)g[1], (float)g[2], 0.f);
       }
       __syncthreads();
-      const int cnt = min(256, n_pts - q0);
+      const int cnt = min(kMT, n_pts - q0);
 #pragma unroll 8
       for (int q = 0; q < cnt; ++q) {
         const float4 t = tile[q];
@@ -96,17 +103,69 @@ __device__ __forceinline__ void nearest_scan(const float* base, int n_pts, const
         best = fminf(best, (dx * dx + dy * dy) + dz * dz);
       }
     }
-    if (i < n_pts) consume(i, sqrtf(best));
+    if (i < own_hi) consume(i, sqrtf(best));
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_object_metrics(AssetsDev as, ObjMetricDev mt, const double* __restrict__ pd_rt,
+// The O(P^2) part: ADD-S and the two directions of the F-score / Chamfer cloud, each CTA owning 1 / kSplit of the points.
+// Partial sums go to part[(b C + c) kSplit + split][kPartCols]; k_object_metrics adds them in split order (deterministic).
+__global__ void __launch_bounds__(kMT) k_object_metrics_scan(AssetsDev as, ObjMetricDev mt, const double* __restrict__ pd_rt,
+                                                             const double* __restrict__ gt_rt, const int* __restrict__ obj_id, int C,
+                                                             double* __restrict__ part) {
+  __shared__ double red[kMT];
+  __shared__ float4 tile[kMT];
+  __shared__ double s_pd[12], s_gt[12];
+  const int split = blockIdx.x, c = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+  const int o = obj_index(as, obj_id[b]);
+  if (tid < 12) {
+    s_pd[tid] = pd_rt[((size_t)b * C + c) * 12 + tid];
+    s_gt[tid] = gt_rt[(size_t)b * 12 + tid];
+  }
+  __syncthreads();
+  double* out = part + (((size_t)b * C + c) * kSplit + split) * kPartCols;
+  const float* base = as.verts + (size_t)o * as.n_pts * 3;
+  const int P = as.n_pts;
+  auto range = [&](int n, int& lo, int& hi) {
+    const int per = (n + kSplit - 1) / kSplit;
+    lo = min(n, split * per);
+    hi = min(n, lo + per);
+  };
+  int lo, hi;
+  range(P, lo, hi);
+  double adds = 0.0;
+  nearest_scan(base, P, lo, hi, s_pd, s_gt, tile, [&](int, float d) { adds += (double)d; });
+  const double adds_s = block_sum_d(adds, red);
+  const float* fbase = mt.fverts ? mt.fverts + (size_t)o * mt.n_fpts * 3 : base;
+  const int Q = mt.fverts ? mt.n_fpts : P;
+  range(Q, lo, hi);
+  const float th[6] = {0.002f, 0.005f, 0.010f, 0.020f, 0.050f, 0.100f};
+  double s_pg = 0.0, s_gp = 0.0;
+  int hit_pg[6] = {0, 0, 0, 0, 0, 0}, hit_gp[6] = {0, 0, 0, 0, 0, 0};
+  nearest_scan(fbase, Q, lo, hi, s_pd, s_gt, tile, [&](int, float d) {
+    s_pg += (double)d;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hit_pg[k] += d < th[k] ? 1 : 0;
+  });
+  nearest_scan(fbase, Q, lo, hi, s_gt, s_pd, tile, [&](int, float d) {
+    s_gp += (double)d;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) hit_gp[k] += d < th[k] ? 1 : 0;
+  });
+  const double t_pg = block_sum_d(s_pg, red), t_gp = block_sum_d(s_gp, red);
+  if (tid == 0) { out[0] = adds_s; out[1] = t_pg; out[2] = t_gp; }
+  for (int k = 0; k < 6; ++k) {
+    const double np_ = block_sum_d((double)hit_pg[k], red), ng_ = block_sum_d((double)hit_gp[k], red);
+    if (tid == 0) { out[3 + k] = np_; out[9 + k] = ng_; }
+  }
+}
+
+__global__ void __launch_bounds__(kMT) k_object_metrics(AssetsDev as, ObjMetricDev mt, const double* __restrict__ pd_rt,
                                                         const double* __restrict__ gt_rt, const int* __restrict__ obj_id,
-                                                        const float* __restrict__ cam_intr, int C, double* __restrict__ out) {
-  __shared__ double red[256];
-  __shared__ float redf[256];
-  __shared__ float4 tile[256];
+                                                        const float* __restrict__ cam_intr, int C, const double* __restrict__ part,
+                                                        double* __restrict__ out) {
+  __shared__ double red[kMT];
+  __shared__ float redf[kMT];
   __shared__ double s_pd[12], s_gt[12], s_pdbox[8][3], s_gtbox[8][3];
   const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int o = obj_index(as, obj_id[b]);
@@ -137,7 +196,7 @@ __global__ void __launch_bounds__(256) k_object_metrics(AssetsDev as, ObjMetricD
   // ---- SMCE: symmetric copies of the box posed by the ground truth; thread k takes transforms k, k+256, ...
   {
     double best = INFINITY;
-    for (int k = tid; k < mt.sym_k; k += 256) {
+    for (int k = tid; k < mt.sym_k; k += kMT) {
       const double* sR = mt.sym_R + ((size_t)o * mt.sym_k + k) * 9;
       const double* st = mt.sym_t + ((size_t)o * mt.sym_k + k) * 3;
       double acc = 0.0;
@@ -156,7 +215,7 @@ __global__ void __launch_bounds__(256) k_object_metrics(AssetsDev as, ObjMetricD
     }
     red[tid] = best;
     __syncthreads();
-    for (int st = 128; st > 0; st >>= 1) {
+    for (int st = kMT / 2; st > 0; st >>= 1) {
       if (tid < st) red[tid] = fmin(red[tid], red[tid + st]);
       __syncthreads();
     }
@@ -172,7 +231,7 @@ __global__ void __launch_bounds__(256) k_object_metrics(AssetsDev as, ObjMetricD
   double Kd[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) Kd[k] = (double)cam_intr[(size_t)b * 9 + k];
-  for (int i = tid; i < P; i += 256) {
+  for (int i = tid; i < P; i += kMT) {
     double pdv[3], gtv[3];
     pose_point_d(s_pd, base + (size_t)i * 3, pdv);
     pose_point_d(s_gt, base + (size_t)i * 3, gtv);
@@ -202,9 +261,14 @@ __global__ void __launch_bounds__(256) k_object_metrics(AssetsDev as, ObjMetricD
     bp[0][d] = block_min_f(mn_p[d], redf, false); bp[1][d] = block_min_f(mx_p[d], redf, true);
     bg[0][d] = block_min_f(mn_g[d], redf, false); bg[1][d] = block_min_f(mx_g[d], redf, true);
   }
-  double adds = 0.0;
-  nearest_scan(base, P, s_pd, s_gt, tile, [&](int, float d) { adds += (double)d; });
-  const double adds_m = block_sum_d(adds, red) / (double)P;
+  // the scans' partial sums, in split order
+  const double* pp = part + ((size_t)b * C + c) * kSplit * kPartCols;
+  double tot[kPartCols];
+  for (int k = 0; k < kPartCols; ++k) {
+    tot[k] = 0.0;
+    for (int sp = 0; sp < kSplit; ++sp) tot[k] += pp[sp * kPartCols + k];
+  }
+  const double adds_m = tot[0] / (double)P;
   if (tid == 0) {
     // the 8 corners of compute_obj_metrics_dexycb: (x, y, z) picks min (0) or max (1) by these index rows
     const int cx[8] = {0, 1, 0, 0, 1, 0, 1, 1}, cy[8] = {0, 0, 1, 0, 1, 1, 0, 1}, cz[8] = {0, 0, 0, 1, 0, 1, 1, 1};
@@ -221,29 +285,12 @@ __global__ void __launch_bounds__(256) k_object_metrics(AssetsDev as, ObjMetricD
     row[14] = ((float)add_m <= diam * 0.1f) ? 1.0 : 0.0;
     row[15] = ((float)adds_m <= diam * 0.1f) ? 1.0 : 0.0;
     row[16] = (rep_px < 5.0) ? 1.0 : 0.0;
-  }
-  // ---- F-score / Chamfer on the F-score cloud, both directions
-  const float* fbase = mt.fverts ? mt.fverts + (size_t)o * mt.n_fpts * 3 : base;
-  const int Q = mt.fverts ? mt.n_fpts : P;
-  const float th[6] = {0.002f, 0.005f, 0.010f, 0.020f, 0.050f, 0.100f};
-  double s_pg = 0.0, s_gp = 0.0;
-  int hit_pg[6] = {0, 0, 0, 0, 0, 0}, hit_gp[6] = {0, 0, 0, 0, 0, 0};
-  nearest_scan(fbase, Q, s_pd, s_gt, tile, [&](int, float d) {
-    s_pg += (double)d;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) hit_pg[k] += d < th[k] ? 1 : 0;
-  });
-  nearest_scan(fbase, Q, s_gt, s_pd, tile, [&](int, float d) {
-    s_gp += (double)d;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) hit_gp[k] += d < th[k] ? 1 : 0;
-  });
-  const double m_pg = block_sum_d(s_pg, red) / (double)Q, m_gp = block_sum_d(s_gp, red) / (double)Q;
-  if (tid == 0) row[7] = (double)(0.5f * ((float)m_pg + (float)m_gp));
-  for (int k = 0; k < 6; ++k) {
-    const double np_ = block_sum_d((double)hit_pg[k], red), ng_ = block_sum_d((double)hit_gp[k], red);
-    if (tid == 0) {
-      const float prec = (float)np_ / (float)Q, rec = (float)ng_ / (float)Q;
+    // F-score / Chamfer on the F-score cloud, both directions
+    const int Q = mt.fverts ? mt.n_fpts : P;
+    const double m_pg = tot[1] / (double)Q, m_gp = tot[2] / (double)Q;
+    row[7] = (double)(0.5f * ((float)m_pg + (float)m_gp));
+    for (int k = 0; k < 6; ++k) {
+      const float prec = (float)tot[3 + k] / (float)Q, rec = (float)tot[9 + k] / (float)Q;
       row[8 + k] = (double)((2.f * prec * rec) / (prec + rec + 1e-6f));
     }
   }
@@ -284,6 +331,7 @@ extern "C" int vpho_objmetrics_create(int n_obj, const float* bbox3d, const floa
 extern "C" int vpho_objmetrics_destroy(vpho_objmetrics_t h) {
   if (!h) return VPHO_ERR_INVALID;
   ObjMetricHost* mh = static_cast<ObjMetricHost*>(h);
+  if (mh->part) cudaFree(mh->part);
   cudaFree(mh->blob);
   delete mh;
   return VPHO_OK;
@@ -297,7 +345,17 @@ extern "C" int vpho_object_metrics(vpho_assets_t assets, vpho_objmetrics_t table
   const AssetsDev& as = static_cast<AssetsHost*>(assets)->dev;
   const ObjMetricDev& mt = static_cast<ObjMetricHost*>(tables)->dev;
   if (mt.n_obj != as.n_obj) return VPHO_ERR_INVALID;
-  VPHO_LAUNCH(k_object_metrics, dim3(C, n), dim3(256), 0, (cudaStream_t)stream, as, mt, pd_rt, gt_rt, obj_id, cam_intr, C, out);
+  ObjMetricHost* mh = static_cast<ObjMetricHost*>(tables);
+  const size_t rows = (size_t)n * C;
+  if (rows > mh->part_rows) {
+    // grow the partial-sum workspace (rare: only when a larger batch than ever before arrives); earlier launches may still
+    // be reading the old one
+    if (mh->part) { cudaDeviceSynchronize(); cudaFree(mh->part); mh->part = nullptr; mh->part_rows = 0; }
+    if (cudaMalloc((void**)&mh->part, rows * kSplit * kPartCols * sizeof(double)) != cudaSuccess) return VPHO_ERR_ALLOC;
+    mh->part_rows = rows;
+  }
+  VPHO_LAUNCH(k_object_metrics_scan, dim3(kSplit, C, n), dim3(kMT), 0, (cudaStream_t)stream, as, mt, pd_rt, gt_rt, obj_id, C, mh->part);
+  VPHO_LAUNCH(k_object_metrics, dim3(C, n), dim3(kMT), 0, (cudaStream_t)stream, as, mt, pd_rt, gt_rt, obj_id, cam_intr, C, mh->part, out);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }

@@ -48,26 +48,12 @@ struct DenoiserHost {
   TensorMapBlob mapA_hi, mapA_lo;
   // tcgen05 pose encoder: K-major TF32 hi/lo planes of pose_encoder.0 [256][Kpad1], FP16 hi/lo planes of pose_encoder.2
   float* pe_planes = nullptr;
-  TensorMapBlob mapW1_hi, mapW1_lo, mapX_hi, mapX_lo;
+  TensorMapBlob mapW1_hi, mapW1_lo;
   void* w2_half = nullptr;           // [2][256][256] __half (hi, lo) planes of pose_encoder.2 scaled by a power of two
   TensorMapBlob mapW2h_hi, mapW2h_lo;
-  const float* mapX_for = nullptr;
-  int mapX_rows = 0;
   const float* mapA_for = nullptr;   // P2hi pointer the cached A maps were built for
   int mapA_rows = 0;
 };
-
-// round-to-nearest (ties to even) onto the 10-bit TF32 mantissa, result kept in a float container
-__host__ __device__ __forceinline__ float tf32_round(float x) {
-  unsigned u;
-  memcpy(&u, &x, 4);
-  if ((u & 0x7F800000u) == 0x7F800000u) return x;
-  u += 0xFFFu + ((u >> 13) & 1u);
-  u &= 0xFFFFE000u;
-  float r;
-  memcpy(&r, &u, 4);
-  return r;
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // controller set-up
@@ -203,97 +189,30 @@ __global__ void k_feat_sum(DenoiserDev dn, const float* __restrict__ Fpart, int 
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// time-term: Fourier embedding -> t_encoder -> Tt[col] = sum_k t_feat[k] Wa_t[k][col]   (one per network call)
-// ------------------------------------------------------------------------------------------------------------
-// One block = 64 output columns of Tt.  The 128-long contraction over t_feat is split over 4 thread groups (32 k each,
-// all loads in flight at once) and summed in a fixed order, so the latency is one L2 round trip instead of 128.
-constexpr int kTtCols = 64;
-__device__ __forceinline__ void time_term_block(const DenoiserDev& dn, const SamplerWs& ws, const RkCtrl& c, int mode, int s,
-                                                int block) {
-  __shared__ float four[kTDim];
-  __shared__ float tfeat[kTDim];
-  __shared__ float part[4][kTtCols];
-  const int tid = threadIdx.x;
-  const float t32 = (float)eval_t64(c, mode, s);
-  if (block == 0 && tid == 255) {
-    const EvalTime et = eval_time(c, mode, s);
-    ws.ctrl->et[tt_slot(mode, s)] = et;                                    // read by the head GEMM of that call
-    if (mode == kModeInit0 || mode == kModeInit1 || mode == kModeStage) ws.ctrl->kcoef[k_slot_of(mode, s)] = et.coef;
-  }
-  if (tid < 64) {
-    // x_proj = t * W * 2 * np.pi in float32, left to right (denoiser.py:29-31)
-    float xp = __fmul_rn(__fmul_rn(__fmul_rn(t32, dn.fourier_W[tid]), 2.0f), 3.14159265358979323846f);
-    four[tid] = (float)sin((double)xp);
-    four[64 + tid] = (float)cos((double)xp);
-  }
-  __syncthreads();
-  if (tid < kTDim) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < kTDim; k += 4) {
-      a0 = fmaf(four[k + 0], __ldg(dn.Wt + (k + 0) * kTDim + tid), a0);
-      a1 = fmaf(four[k + 1], __ldg(dn.Wt + (k + 1) * kTDim + tid), a1);
-      a2 = fmaf(four[k + 2], __ldg(dn.Wt + (k + 2) * kTDim + tid), a2);
-      a3 = fmaf(four[k + 3], __ldg(dn.Wt + (k + 3) * kTDim + tid), a3);
-    }
-    const float a = ((a0 + a1) + (a2 + a3)) + dn.bt[tid];
-    tfeat[tid] = a > 0.f ? a : 0.f;
-  }
-  __syncthreads();
-  const int g = tid >> 6, cl = tid & 63, col = block * kTtCols + cl;
-  float a = 0.f;
-  if (col < dn.hid) {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) a = fmaf(tfeat[g * 32 + k], __ldg(dn.Wa_t + (size_t)(g * 32 + k) * dn.hid + col), a);
-  }
-  part[g][cl] = a;
-  __syncthreads();
-  if (tid < kTtCols && col < dn.hid)
-    ws.Tt[(size_t)tt_slot(mode, s) * dn.hid + col] = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
-}
-
 __global__ void __launch_bounds__(256) k_time_term(DenoiserDev dn, SamplerWs ws, int mode, int s) {
   const RkCtrl& c = *ws.ctrl;
   if (!eval_active(c, mode)) return;
   time_term_block(dn, ws, c, mode, s, blockIdx.x);
 }
 
-// tcgen05 path: one launch does the time-term (first `nb_time` blocks) and the float64 RK stage combination of every
-// state element into the (hi, lo) TF32 planes of the pose encoder's A operand (remaining blocks), all SMs busy.
-__device__ __forceinline__ void stage_x_block(const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, int nb_time, int bid,
-                                              int n_blocks) {
+// tcgen05 path: the time terms of a network call.  The times of all six stages of an RK attempt are known once the attempt
+// has begun (t + c_s h), so the first stage's launch computes all six (six groups of column blocks) and stages 2..6 launch
+// nothing: their critical path is the fused stage-input + pose-encoder kernel alone (k_pose_tc).
+__device__ __forceinline__ void time_terms_block(const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, int bid) {
   const RkCtrl& c = *ws.ctrl;
   if (!eval_active(c, mode)) return;
-  if (bid < nb_time) {
-    // The times of all six stages of an RK attempt are known once the attempt has begun (t + c_s h), so the first stage's
-    // launch computes all six time terms (six groups of column blocks) and stages 2..6 launch none: their critical path
-    // is the stage input alone.
-    const int per = (dn.hid + kTtCols - 1) / kTtCols;
-    if (mode == kModeStage) time_term_block(dn, ws, c, mode, 1 + bid / per, bid % per);
-    else time_term_block(dn, ws, c, mode, s, bid);
-    return;
-  }
-  const int D = dn.D, Kx = ws.Kx;
-  const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
-  const int total = ws.Npad * Kx;
-  for (int it = (bid - nb_time) * 256 + threadIdx.x; it < total; it += (n_blocks - nb_time) * 256) {
-    const int row = it / Kx, k = it - row * Kx;
-    float x = 0.f;
-    if (k < D) x = (float)stage_input(ws, c, mode, s, row, k, n_rows, D);
-    const float hi = tf32_round(x);
-    ws.Xhi[it] = hi;
-    ws.Xlo[it] = tf32_round(x - hi);
-  }
+  const int per = (dn.hid + kTtCols - 1) / kTtCols;
+  if (mode == kModeStage) time_term_block(dn, ws, c, mode, 1 + bid / per, bid % per);
+  else time_term_block(dn, ws, c, mode, s, bid);
 }
 
 // blocks [0, blocks0) work for job 0, the rest for job 1 (two samplers in lock-step; blocks0 = gridDim.x for one)
-__global__ void __launch_bounds__(256) k_stage_x(DenoiserDev dn0, SamplerWs ws0, DenoiserDev dn1, SamplerWs ws1, int blocks0, int mode,
-                                                int s, int nb_time0, int nb_time1) {
+__global__ void __launch_bounds__(256) k_time_terms(DenoiserDev dn0, SamplerWs ws0, DenoiserDev dn1, SamplerWs ws1, int blocks0, int mode,
+                                                   int s) {
   pdl_wait();                 // launched with launch_pdl: nothing of the previous kernel may be read above this line
   pdl_trigger();
-  if ((int)blockIdx.x < blocks0) stage_x_block(dn0, ws0, mode, s, nb_time0, blockIdx.x, blocks0);
-  else stage_x_block(dn1, ws1, mode, s, nb_time1, (int)blockIdx.x - blocks0, (int)gridDim.x - blocks0);
+  if ((int)blockIdx.x < blocks0) time_terms_block(dn0, ws0, mode, s, blockIdx.x);
+  else time_terms_block(dn1, ws1, mode, s, (int)blockIdx.x - blocks0);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -758,9 +677,6 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
   // the workspace size does not depend on the path (same bytes either way)
   const size_t o_P2T = take((size_t)kPDim * Npad * 4);
   const size_t o_P2sc = take((size_t)Npad * 4);
-  const int Kx = (D + 31) / 32 * 32;
-  const size_t o_Xhi = take((size_t)Kx * Npad * 4);
-  const size_t o_Xlo = take((size_t)Kx * Npad * 4);
   const size_t o_y = take(n * 8);
   const size_t o_yn = take(n * 8);
   const size_t o_K = take(7 * n * 4);
@@ -776,9 +692,6 @@ static size_t carve(void* base, int n_heads, int n_rows, int rows_per_feat, int 
     ws->P2hi = use_tc ? reinterpret_cast<float*>(b + o_P2T) : nullptr;
     ws->P2lo = use_tc ? reinterpret_cast<float*>(b + o_P2T + (size_t)kPDim * Npad * 2) : nullptr;
     ws->P2scale = use_tc ? reinterpret_cast<float*>(b + o_P2sc) : nullptr;
-    ws->Xhi = reinterpret_cast<float*>(b + o_Xhi);
-    ws->Xlo = reinterpret_cast<float*>(b + o_Xlo);
-    ws->Kx = Kx;
     ws->y = reinterpret_cast<double*>(b + o_y);
     ws->ynew = reinterpret_cast<double*>(b + o_yn);
     ws->K = reinterpret_cast<float*>(b + o_K);
@@ -808,12 +721,10 @@ static int launch_feat_term(DenoiserHost& dh, const SamplerWs& ws, const float* 
 // One sampler's state on the host side of a launch; two of them advance in lock-step through the same kernel launches.
 struct SamplerJob { DenoiserHost* dh; SamplerWs ws; int ws_n; /* n_rows * D */ };
 
-static int stage_x_blocks(const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, int* nb_time) {
+// column blocks of the time-term kernel for this call (0: nothing to launch)
+static int time_blocks(const DenoiserDev& dn, int mode, int s) {
   const int per = (dn.hid + kTtCols - 1) / kTtCols;
-  *nb_time = mode == kModeStage ? (s == 1 ? 6 * per : 0) : per;      // see stage_x_block
-  int nb_x = (ws.Npad * ws.Kx + 1023) / 1024;           // ~4 elements per thread
-  if (nb_x > 592) nb_x = 592;
-  return *nb_time + nb_x;
+  return mode == kModeStage ? (s == 1 ? 6 * per : 0) : per;      // see k_time_terms
 }
 
 // One network evaluation of every job: stage input + time term, pose encoder, head GEMM.
@@ -832,23 +743,18 @@ static int launch_eval(SamplerJob* jobs, int n_jobs, int mode, int s, cudaStream
     SamplerJob& j0 = jobs[0];
     SamplerJob& j1 = jobs[n_jobs - 1];
     profile_begin(VPHO_TAG_POSE_ENCODER, st);
-    int nbt0 = 0, nbt1 = 0;
-    const int b0 = stage_x_blocks(j0.dh->dev, j0.ws, mode, s, &nbt0),
-              b1 = n_jobs > 1 ? stage_x_blocks(j1.dh->dev, j1.ws, mode, s, &nbt1) : 0;
-    profile_begin(VPHO_TAG_STAGE_X, st);
-    VPHO_LAUNCH_PDL(k_stage_x, dim3(b0 + b1), dim3(256), 0, st, j0.dh->dev, j0.ws, j1.dh->dev, j1.ws, b0, mode, s, nbt0, nbt1);
-    profile_end(VPHO_TAG_STAGE_X, st);
+    const int b0 = time_blocks(j0.dh->dev, mode, s), b1 = n_jobs > 1 ? time_blocks(j1.dh->dev, mode, s) : 0;
+    if (b0 + b1 > 0) {
+      profile_begin(VPHO_TAG_STAGE_X, st);
+      VPHO_LAUNCH_PDL(k_time_terms, dim3(b0 + b1), dim3(256), 0, st, j0.dh->dev, j0.ws, j1.dh->dev, j1.ws, b0, mode, s);
+      profile_end(VPHO_TAG_STAGE_X, st);
+    }
     TcPoseJob pj[2];
     TcHeadJob hj[2];
     bool pair = n_jobs > 1;
     for (int j = 0; j < n_jobs; ++j) {
       DenoiserHost& dh = *jobs[j].dh;
       const SamplerWs& ws = jobs[j].ws;
-      if (dh.mapX_for != ws.Xhi || dh.mapX_rows != ws.Npad) {
-        if (!tc_make_map(&dh.mapX_hi, ws.Xhi, ws.Npad, 128, ws.Kx) || !tc_make_map(&dh.mapX_lo, ws.Xlo, ws.Npad, 128, ws.Kx)) return VPHO_ERR_LAUNCH;
-        dh.mapX_for = ws.Xhi;
-        dh.mapX_rows = ws.Npad;
-      }
       if (dh.mapA_for != ws.P2hi || dh.mapA_rows != ws.Npad) {
         if (!tc_make_map(&dh.mapA_hi, ws.P2hi, ws.Npad, 128, kPDim, true) || !tc_make_map(&dh.mapA_lo, ws.P2lo, ws.Npad, 128, kPDim, true))
           return VPHO_ERR_LAUNCH;
@@ -856,7 +762,7 @@ static int launch_eval(SamplerJob* jobs, int n_jobs, int mode, int s, cudaStream
         dh.mapA_rows = ws.Npad;
       }
       pair = pair || dh.dev.n_heads >= dh.pair_min_heads;
-      pj[j] = TcPoseJob{&dh.mapX_hi, &dh.mapX_lo, &dh.mapW1_hi, &dh.mapW1_lo, &dh.mapW2h_hi, &dh.mapW2h_lo, &dh.dev, &jobs[j].ws};
+      pj[j] = TcPoseJob{&dh.mapW1_hi, &dh.mapW1_lo, &dh.mapW2h_hi, &dh.mapW2h_lo, &dh.dev, &jobs[j].ws};
     }
     for (int j = 0; j < n_jobs; ++j) {
       DenoiserHost& dh = *jobs[j].dh;

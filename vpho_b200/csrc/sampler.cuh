@@ -91,9 +91,6 @@ struct SamplerWs {
   float* P2hi;     // [Npad][256] __half (hi, lo) planes of the pose features scaled per row, row-major = K-major (tcgen05
   float* P2lo;     // head GEMM); nullptr on the strict-FP32 SIMT path
   float* P2scale;  // [Npad] exact power-of-two un-scaling of each row of the FP16 planes; nullptr on the SIMT path
-  float* Xhi;      // [Npad][Kx] stage input split for 3xTF32 (Kx = D rounded up to 32), tcgen05 pose encoder only
-  float* Xlo;
-  int Kx;
   double* y;       // [n]
   double* ynew;    // [n]
   float* K;        // [7][n] raw network outputs (float32) of the RK stages; see kval for the float64 drift they stand for
@@ -110,6 +107,6 @@ constexpr int kMaxRedBlocks = 512;
 
 // one sampler's share of a tensor-core launch (scorenet_tc.cu); two of them = two samplers advancing in lock-step
 struct TcHeadJob { const void *mapA_hi, *mapA_lo, *mapB_hi, *mapB_lo; const DenoiserDev* dn; const SamplerWs* ws; };
-struct TcPoseJob { const void *mapX_hi, *mapX_lo, *mapW1_hi, *mapW1_lo, *mapW2_hi, *mapW2_lo; const DenoiserDev* dn; const SamplerWs* ws; };
+struct TcPoseJob { const void *mapW1_hi, *mapW1_lo, *mapW2_hi, *mapW2_lo; const DenoiserDev* dn; const SamplerWs* ws; };
 
 }  // namespace vpho

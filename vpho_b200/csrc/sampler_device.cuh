@@ -4,6 +4,8 @@
 #pragma once
 #include "sampler.cuh"
 
+#include <cstring>
+
 namespace vpho {
 
 // ------------------------------------------------------------------------------------------------------------
@@ -125,5 +127,139 @@ __device__ __forceinline__ double stage_input(const SamplerWs& ws, const RkCtrl&
   if (s == 6) ws.ynew[i] = v;
   return v;
 }
+
+// The same stage input for FOUR consecutive elements i..i+3 (i a multiple of 4, D a multiple of 4), with the controller
+// scalars read once (`StageScalars`) and the K slots / state read as 16-byte vectors.  Operation for operation the arithmetic
+// of stage_input / kval above -- the fused pose-encoder kernel calls this 6 times per thread per network call, where the
+// scalar form spends its time re-reading the controller words.
+struct StageScalars {
+  double kc[6];     // kcoef of the K slots that enter the combination
+  double a[6];      // their Dormand-Prince weights kA[s][j]
+  double h;         // step (h0 * direction for the second initial-step evaluation)
+  int nanf[6];
+  int ns;           // slots that enter (0: the input is the state itself)
+};
+__device__ __forceinline__ StageScalars stage_scalars(const RkCtrl& c, int mode, int s) {
+  StageScalars q;
+  q.ns = 0;
+  q.h = 0.0;
+  if (mode == kModeInit1) { q.ns = 1; q.h = c.h0 * c.direction; }
+  if (mode == kModeStage) { q.ns = (s == 6) ? 6 : s; q.h = c.h; }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    q.kc[j] = j < q.ns ? c.kcoef[j] : 0.0;
+    q.nanf[j] = j < q.ns ? c.nan_stage[j] : 0;
+    q.a[j] = mode == kModeStage ? kA[s][j] : 1.0;
+  }
+  return q;
+}
+__device__ __forceinline__ void stage_input4(const SamplerWs& ws, const StageScalars& q, int mode, int s, int i, int n, float* out) {
+  if (mode == kModeEval) {
+    const float4 x = *reinterpret_cast<const float4*>(ws.eval_x + i);
+    out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = x.w;
+    return;
+  }
+  const double2 y01 = *reinterpret_cast<const double2*>(ws.y + i), y23 = *reinterpret_cast<const double2*>(ws.y + i + 2);
+  const double y[4] = {y01.x, y01.y, y23.x, y23.y};
+  if (q.ns == 0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[e] = (float)y[e];
+    return;
+  }
+  float4 kv[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+    if (j < q.ns) kv[j] = *reinterpret_cast<const float4*>(ws.K + (size_t)j * n + i);
+  double v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (mode == kModeInit1) {
+      const float k0 = e == 0 ? kv[0].x : e == 1 ? kv[0].y : e == 2 ? kv[0].z : kv[0].w;
+      double kvv = -(q.kc[0] * (double)k0);
+      if (q.nanf[0] && !isfinite(kvv)) kvv = 0.0;
+      v[e] = __dadd_rn(y[e], __dmul_rn(q.h, kvv));
+    } else {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (j < q.ns) {
+          const float kj = e == 0 ? kv[j].x : e == 1 ? kv[j].y : e == 2 ? kv[j].z : kv[j].w;
+          double kvv = -(q.kc[j] * (double)kj);
+          if (q.nanf[j] && !isfinite(kvv)) kvv = 0.0;
+          acc += kvv * q.a[j];
+        }
+      v[e] = __dadd_rn(y[e], __dmul_rn(acc, q.h));
+    }
+    out[e] = (float)v[e];
+  }
+  if (mode == kModeStage && s == 6) {
+    *reinterpret_cast<double2*>(ws.ynew + i) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(ws.ynew + i + 2) = make_double2(v[2], v[3]);
+  }
+}
+
+// round-to-nearest (ties to even) onto the 10-bit TF32 mantissa, result kept in a float container
+__host__ __device__ __forceinline__ float tf32_round(float x) {
+  unsigned u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;
+  u += 0xFFFu + ((u >> 13) & 1u);
+  u &= 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// time-term: Fourier embedding -> t_encoder -> Tt[col] = sum_k t_feat[k] Wa_t[k][col]   (one per network call)
+// ------------------------------------------------------------------------------------------------------------
+// One block = 64 output columns of Tt.  The 128-long contraction over t_feat is split over 4 thread groups (32 k each,
+// all loads in flight at once) and summed in a fixed order, so the latency is one L2 round trip instead of 128.
+constexpr int kTtCols = 64;
+__device__ __forceinline__ void time_term_block(const DenoiserDev& dn, const SamplerWs& ws, const RkCtrl& c, int mode, int s,
+                                                int block) {
+  __shared__ float four[kTDim];
+  __shared__ float tfeat[kTDim];
+  __shared__ float part[4][kTtCols];
+  const int tid = threadIdx.x;
+  const float t32 = (float)eval_t64(c, mode, s);
+  if (block == 0 && tid == 255) {
+    const EvalTime et = eval_time(c, mode, s);
+    ws.ctrl->et[tt_slot(mode, s)] = et;                                    // read by the head GEMM of that call
+    if (mode == kModeInit0 || mode == kModeInit1 || mode == kModeStage) ws.ctrl->kcoef[k_slot_of(mode, s)] = et.coef;
+  }
+  if (tid < 64) {
+    // x_proj = t * W * 2 * np.pi in float32, left to right (denoiser.py:29-31)
+    float xp = __fmul_rn(__fmul_rn(__fmul_rn(t32, dn.fourier_W[tid]), 2.0f), 3.14159265358979323846f);
+    four[tid] = (float)sin((double)xp);
+    four[64 + tid] = (float)cos((double)xp);
+  }
+  __syncthreads();
+  if (tid < kTDim) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < kTDim; k += 4) {
+      a0 = fmaf(four[k + 0], __ldg(dn.Wt + (k + 0) * kTDim + tid), a0);
+      a1 = fmaf(four[k + 1], __ldg(dn.Wt + (k + 1) * kTDim + tid), a1);
+      a2 = fmaf(four[k + 2], __ldg(dn.Wt + (k + 2) * kTDim + tid), a2);
+      a3 = fmaf(four[k + 3], __ldg(dn.Wt + (k + 3) * kTDim + tid), a3);
+    }
+    const float a = ((a0 + a1) + (a2 + a3)) + dn.bt[tid];
+    tfeat[tid] = a > 0.f ? a : 0.f;
+  }
+  __syncthreads();
+  const int g = tid >> 6, cl = tid & 63, col = block * kTtCols + cl;
+  float a = 0.f;
+  if (col < dn.hid) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a = fmaf(tfeat[g * 32 + k], __ldg(dn.Wa_t + (size_t)(g * 32 + k) * dn.hid + col), a);
+  }
+  part[g][cl] = a;
+  __syncthreads();
+  if (tid < kTtCols && col < dn.hid)
+    ws.Tt[(size_t)tt_slot(mode, s) * dn.hid + col] = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+}
+
 
 }  // namespace vpho

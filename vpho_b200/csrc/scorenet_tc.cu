@@ -14,6 +14,7 @@
 // Persistent grid: CTA (pair) b processes items b, b + n_units, ... of the (head, row tile) list.
 // Pose encoder (k_pose_tc): D -> 256 -> 256 ReLU MLP per 128-row tile, GEMM 1 as 3xTF32, GEMM 2 as 3xFP16.
 #include "sampler_device.cuh"
+#include "tc_ptx.cuh"
 #include "vpho_b200.h"
 
 #include <cuda.h>
@@ -26,11 +27,10 @@ constexpr int kTcBM = 128, kTcBN = 256, kTcBK = 32, kTcStages = 2, kTcUmmaK = 8;
 constexpr int kTcABytes = kTcBM * kTcBK * 4;        // 16 KB per operand plane per stage
 constexpr int kTcBBytes = kTcBN * kTcBK * 4;        // 32 KB
 constexpr int kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes;   // 96 KB
-constexpr int kTcThreads = 256;        // pose / feat kernels: 4 epilogue warps
+constexpr int kTcMaxStages = 3;      // CTA-pair head GEMM: 3 stages of 64 KB in the same 192 KB
 constexpr int kHeadThreads = 640;      // head kernel: 4 role warps + 2 x 8 epilogue warps
 constexpr int kTcFtImgs = 4;
 constexpr int kMaxDevices = 64;       // per-device caches of function attributes
-constexpr int kTcMaxStages = 3;      // CTA-pair head GEMM: 3 stages of 64 KB in the same 192 KB
 constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 // FP16 operands (a_format = b_format = 0), FP32 accumulate: same tile, K = 16 per instruction, twice the TF32 rate
 constexpr uint32_t kTcIdescF16 = (1u << 4) | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
@@ -60,182 +60,6 @@ __device__ __forceinline__ void clk_stamp(int role, int idx) {
 #else
   (void)role; (void)idx;
 #endif
-}
-
-// -------------------------------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(void* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"      // %2: suspend-time hint, the warp parks
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* bar, void* dst, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                   smem_u32(dst)),
-               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(void* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// ---- CTA-pair (cta_group::2) helpers: the two CTAs of a cluster share one UMMA of M = 256
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {      // shared::cluster address of a peer's smem
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  // default .release.cta: the ordering that matters here (TMEM reads before the next MMA) is carried by tcgen05.wait::ld +
-  // tcgen05.fence::before_thread_sync; a cluster-scope release costs a full memory barrier per arrival
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(void* bar, uint32_t parity) {        // arrivals come from both CTAs
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP_C:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1, %2;\n\t"
-      "@P1 bra DONE_C;\n\t"
-      "bra WAIT_LOOP_C;\n\t"
-      "DONE_C:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
-      : "memory");
-}
-// TMA load whose completion bytes are counted on the LEADER CTA's mbarrier (cluster address), data into this CTA's smem
-__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-// completion of the pair's MMAs arrives on the same-offset mbarrier of BOTH CTAs
-__device__ __forceinline__ void umma_commit_pair(void* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((unsigned short)3)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B operand tile whose rows are 128 bytes: 8-row atoms of 1024 bytes (SBO), LBO unused (= 1)
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(const void* smem) {
-  const uint32_t addr = smem_u32(smem);
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);            // start address, 16-byte units
-  d |= (uint64_t)1 << 16;                           // leading byte offset (ignored for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset between 8-row atoms
-  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
-  return d;
-}
-
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
-      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&v)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
-               :
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
-      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 // Operands are __half planes (64 k per 128-byte row, 4 chunks of K = 256); the epilogue undoes the power-of-two scales.
@@ -566,7 +390,8 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 
 // =====================================================================================================================
 // Pose encoder on tensor cores: P2 = relu(relu(X.W1 + b1).W2 + b2) for one 128-row tile per CTA, both GEMMs as 3xTF32.
-//   input    X (hi, lo) planes [Npad][Kx] written by k_stage_x (float64 RK stage combination, all SMs), loaded by TMA;
+//   input    X = the float64 RK stage combination of the tile's state elements, formed by the compute warps and written as
+//            (hi, lo) TF32 planes straight into the swizzled A operand (no stage-input kernel, no global round trip);
 //   GEMM 1   D1[128x256] (TMEM cols 0..255) = X . W1, W1 (hi, lo) chunks of 32 k streamed by TMA;
 //   re-stage compute warps read D1 32 columns at a time (tcgen05.ld), add b1, ReLU, split, and write the next A operand
 //            chunk of GEMM 2 (double-buffered, reusing the X region) while the MMA lane consumes the previous one;
@@ -591,11 +416,10 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CUtensorMap* tmX_lo, const CUtensorMap* tmW1_hi,
-                                             const CUtensorMap* tmW1_lo, const CUtensorMap* tmW2_hi, const CUtensorMap* tmW2_lo,
-                                             const DenoiserDev& dn, const SamplerWs& ws, int mode, int s, int tile) {
+__device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const CUtensorMap* tmW1_lo, const CUtensorMap* tmW2_hi,
+                                             const CUtensorMap* tmW2_lo, const DenoiserDev& dn, const SamplerWs& ws, int mode, int s,
+                                             int tile) {
   const RkCtrl& c = *ws.ctrl;
   if (!eval_active(c, mode)) {           // one-way hint ahead of the wait, see k_head_tc
     pdl_trigger();
@@ -616,7 +440,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
       mbar_init(&sm.full_bar[i], 1); mbar_init(&sm.empty_bar[i], 1);
       mbar_init(&sm.a_full_bar[i], 512); mbar_init(&sm.a_empty_bar[i], 1);
     }
-    mbar_init(&sm.d1_full_bar, 1); mbar_init(&sm.d2_full_bar, 1); mbar_init(&sm.x_full_bar, 1);
+    mbar_init(&sm.d1_full_bar, 1); mbar_init(&sm.d2_full_bar, 1); mbar_init(&sm.x_full_bar, 512);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -639,12 +463,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // the whole X tile (A operand of GEMM 1) has a dedicated region: issue it at once
-      mbar_arrive_expect_tx(&sm.x_full_bar, (uint32_t)(nk1 * 2 * kTcABytes));
-      for (int j = 0; j < nk1; ++j) {
-        tma_load_2d(tmX_hi, &sm.x_full_bar, sm.a + (size_t)j * 2 * kTcABytes, j * kTcBK, r0);
-        tma_load_2d(tmX_lo, &sm.x_full_bar, sm.a + (size_t)j * 2 * kTcABytes + kTcABytes, j * kTcBK, r0);
-      }
+      // (the X tile, A operand of GEMM 1, is written into its dedicated region by the compute warps)
       for (int j = 0; j < nk1 + nk2; ++j) {
         mbar_wait(&sm.empty_bar[stage], phase ^ 1);
         clk_stamp(0, sc_++);
@@ -717,6 +536,43 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
     // 16 compute warps: warp 4+e owns TMEM lanes 32*(e&3).. (its hardware lane quarter) and column sub-block cs = e>>2
     const int e = warp - 4, q = e & 3, cs = e >> 2, r = q * 32 + lane;      // r: this thread's row of the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    // ---- stage input: the float64 RK stage combination of every state element of this tile (what scipy hands to `fun`,
+    // stage_input), rounded to float32 and split into the (hi, lo) TF32 planes of GEMM 1's A operand, straight into the
+    // SWIZZLE_128B chunks (32 k per 128-byte row).  One thread = one 16-byte unit (4 consecutive k of a row); consecutive
+    // threads take consecutive units, so the K-slot reads are coalesced.  Rows past the end and k >= D are zero.
+    {
+      const int tcx = threadIdx.x - 128;                       // 0..511
+      const int upr = nk1 * (kTcBK / 4);                       // 16-byte units per row
+      const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
+      const bool vec = (D & 3) == 0;                           // 16-byte aligned rows: vector loads, scalars hoisted
+      const StageScalars q4 = stage_scalars(c, mode, s);
+      const int n_state = (mode == kModeEval) ? n_rows * D : c.n;
+#pragma unroll 2
+      for (int u = tcx; u < kTcBM * upr; u += 512) {
+        const int rr = u / upr, kq = u - rr * upr;
+        float x4[4] = {0.f, 0.f, 0.f, 0.f}, hi4[4], lo4[4];
+        if (vec) {
+          if (r0 + rr < n_rows && 4 * kq < D) stage_input4(ws, q4, mode, s, (r0 + rr) * D + 4 * kq, n_state, x4);
+        } else {
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const int k = 4 * kq + e4;
+            x4[e4] = k < D ? (float)stage_input(ws, c, mode, s, r0 + rr, k, n_rows, D) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+          hi4[e4] = tf32_round(x4[e4]);
+          lo4[e4] = tf32_round(x4[e4] - hi4[e4]);
+        }
+        unsigned char* chunk = sm.a + (size_t)(kq >> 3) * 2 * kTcABytes;
+        const uint32_t off = (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128 + ((((kq & 7) ^ (rr & 7)) & 7) << 4));
+        *reinterpret_cast<float4*>(chunk + off) = make_float4(hi4[0], hi4[1], hi4[2], hi4[3]);
+        *reinterpret_cast<float4*>(chunk + kTcABytes + off) = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(&sm.x_full_bar);
+    }
     // first-layer bias of this thread's 64 columns, fetched while GEMM 1 runs (its global-load latency would otherwise sit
     // between "D1 complete" and the first re-staged chunk)
     float hv[64];
@@ -876,15 +732,13 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmX_hi, const CU
 
 // One CTA per 128-row tile; with two samplers in lock-step the grid holds job 0's tiles followed by job 1's.
 __global__ void __launch_bounds__(kHeadThreads, 1)
-k_pose_tc(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
-          const __grid_constant__ CUtensorMap tmW1_hi, const __grid_constant__ CUtensorMap tmW1_lo,
+k_pose_tc(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_constant__ CUtensorMap tmW1_lo,
           const __grid_constant__ CUtensorMap tmW2_hi, const __grid_constant__ CUtensorMap tmW2_lo,
-          const __grid_constant__ CUtensorMap tmX_hi1, const __grid_constant__ CUtensorMap tmX_lo1,
           const __grid_constant__ CUtensorMap tmW1_hi1, const __grid_constant__ CUtensorMap tmW1_lo1,
           const __grid_constant__ CUtensorMap tmW2_hi1, const __grid_constant__ CUtensorMap tmW2_lo1, DenoiserDev dn0, SamplerWs ws0,
           DenoiserDev dn1, SamplerWs ws1, int tiles0, int mode, int s) {
-  if ((int)blockIdx.x < tiles0) pose_tc_tile(&tmX_hi, &tmX_lo, &tmW1_hi, &tmW1_lo, &tmW2_hi, &tmW2_lo, dn0, ws0, mode, s, blockIdx.x);
-  else pose_tc_tile(&tmX_hi1, &tmX_lo1, &tmW1_hi1, &tmW1_lo1, &tmW2_hi1, &tmW2_lo1, dn1, ws1, mode, s, (int)blockIdx.x - tiles0);
+  if ((int)blockIdx.x < tiles0) pose_tc_tile(&tmW1_hi, &tmW1_lo, &tmW2_hi, &tmW2_lo, dn0, ws0, mode, s, blockIdx.x);
+  else pose_tc_tile(&tmW1_hi1, &tmW1_lo1, &tmW2_hi1, &tmW2_lo1, dn1, ws1, mode, s, (int)blockIdx.x - tiles0);
 }
 
 // =====================================================================================================================
@@ -1089,9 +943,9 @@ int tc_launch_pose(const TcPoseJob* jobs, int n_jobs, int mode, int s, cudaStrea
   const TcPoseJob& j1 = jobs[n_jobs - 1];
   const int tiles0 = j0.ws->Npad / kTcBM, tiles1 = n_jobs > 1 ? j1.ws->Npad / kTcBM : 0;
   auto M = [](const void* p) -> const CUtensorMap& { return *static_cast<const CUtensorMap*>(p); };
-  if (launch_pdl(k_pose_tc, dim3(tiles0 + tiles1), dim3(kHeadThreads), smem, st, 1, M(j0.mapX_hi), M(j0.mapX_lo), M(j0.mapW1_hi),
-                 M(j0.mapW1_lo), M(j0.mapW2_hi), M(j0.mapW2_lo), M(j1.mapX_hi), M(j1.mapX_lo), M(j1.mapW1_hi), M(j1.mapW1_lo),
-                 M(j1.mapW2_hi), M(j1.mapW2_lo), *j0.dn, *j0.ws, *j1.dn, *j1.ws, tiles0, mode, s) != cudaSuccess)
+  if (launch_pdl(k_pose_tc, dim3(tiles0 + tiles1), dim3(kHeadThreads), smem, st, 1, M(j0.mapW1_hi), M(j0.mapW1_lo), M(j0.mapW2_hi),
+                 M(j0.mapW2_lo), M(j1.mapW1_hi), M(j1.mapW1_lo), M(j1.mapW2_hi), M(j1.mapW2_lo), *j0.dn, *j0.ws, *j1.dn, *j1.ws,
+                 tiles0, mode, s) != cudaSuccess)
     return VPHO_ERR_LAUNCH;
   return VPHO_OK;
 }

@@ -45,9 +45,11 @@ class HeadMano:
         need_verts = kwargs.get("need_verts", True)
         verts = torch.empty((n, 778, 3), dtype=torch.float32, device=pose.device) if need_verts else None
         joints = torch.empty((n, 21, 3), dtype=torch.float32, device=pose.device)
-        st = self.lib.c.vpho_mano_forward(self.handle, capi.ptr(pose), capi.ptr(shape), n, capi.ptr(verts),
-                                          capi.ptr(joints), capi.stream_of(pose))
-        self.lib.check(st, "vpho_mano_forward")
+        # strict_fp32=True: the FP32 SIMT kernel instead of the tcgen05 blend (VPHO_MANO_STRICT_FP32; cross-checks only)
+        flags = 1 if kwargs.get("strict_fp32", False) else 0
+        st = self.lib.c.vpho_mano_forward_ex(self.handle, capi.ptr(pose), capi.ptr(shape), n, capi.ptr(verts),
+                                             capi.ptr(joints), flags, capi.stream_of(pose))
+        self.lib.check(st, "vpho_mano_forward_ex")
         return verts, joints
 
     __call__ = get_hand_verts

@@ -62,6 +62,7 @@ int vpho_mano_forward(vpho_mano_t h, const float* pose, const float* shape, int 
 /* Same with an explicit numerical path: flags = 0 is vpho_mano_forward (tcgen05 blend when vertices are materialised);
  * VPHO_MANO_STRICT_FP32 runs the FP32 SIMT kernel (cross-check of the tensor-core kernel; also what joints-only calls use). */
 #define VPHO_MANO_STRICT_FP32 1
+#define VPHO_MANO_DEBUG_BLEND 2   /* diagnostics: verts receives the blended rest pose (template + shape + pose correctives) */
 int vpho_mano_forward_ex(vpho_mano_t h, const float* pose, const float* shape, int n, float* verts, float* joints, int flags,
                          void* stream);
 

@@ -20,7 +20,7 @@
 namespace vpho {
 
 int mano_forward_dev(const ManoModelDev& m, const float* pose, const float* shape, int pose_stride, int shape_stride,
-                     int n, float* verts, float* joints, cudaStream_t stream, bool simt = false);
+                     int n, float* verts, float* joints, cudaStream_t stream, bool simt = false, int debug_blend = 0);
 const ManoModelDev& mano_model_dev(const void* handle);
 
 // everything the aggregation kernels need, passed by value

@@ -64,11 +64,11 @@ __global__ void __launch_bounds__(kCsThreads) k_anchor_contact(const float* __re
   }
 }
 
-// grid (ceil(778/256), n): nearest object point of every vertex of candidate blockIdx.y
+// grid (n, ceil(778/256)): nearest object point of every vertex of candidate blockIdx.x (x: up to 2^31 - 1 candidates)
 __global__ void __launch_bounds__(kCsThreads) k_vertex_contact(const float* __restrict__ verts, const float* __restrict__ obj,
                                                                 int n_pts, int group, float* __restrict__ dist) {
   __shared__ float4 tile[kCsThreads];
-  const int i = blockIdx.y, v = blockIdx.x * kCsThreads + threadIdx.x;
+  const int i = blockIdx.x, v = blockIdx.y * kCsThreads + threadIdx.x;
   const float* ov = obj + (size_t)(i / group) * n_pts * 3;
   float x = 0.f, y = 0.f, z = 0.f;
   if (v < kVerts) { x = verts[((size_t)i * kVerts + v) * 3]; y = verts[((size_t)i * kVerts + v) * 3 + 1]; z = verts[((size_t)i * kVerts + v) * 3 + 2]; }
@@ -502,7 +502,7 @@ extern "C" int vpho_vertex_contact(const float* verts, const float* obj_points, 
   if (n < 0 || group <= 0 || n_pts <= 0) return VPHO_ERR_INVALID;
   if (n == 0) return VPHO_OK;
   if (!verts || !obj_points || !dist) return VPHO_ERR_INVALID;
-  VPHO_LAUNCH(k_vertex_contact, dim3((kVerts + kCsThreads - 1) / kCsThreads, n), dim3(kCsThreads), 0, (cudaStream_t)stream, verts,
+  VPHO_LAUNCH(k_vertex_contact, dim3(n, (kVerts + kCsThreads - 1) / kCsThreads), dim3(kCsThreads), 0, (cudaStream_t)stream, verts,
               obj_points, n_pts, group, dist);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;

@@ -22,7 +22,7 @@ struct ManoModelHost {
 int mano_tc_create(const float* v_template, const float* shapedirs, const float* posedirs, const float* weights, void** out);
 void mano_tc_destroy(void* h);
 int mano_tc_forward(const void* h, const ManoModelDev& m, const float* pose, const float* shape, int pose_stride, int shape_stride,
-                    int n, float* verts, float* joints, cudaStream_t stream);
+                    int n, float* verts, float* joints, cudaStream_t stream, int debug_blend);
 #endif
 
 template <int TC>
@@ -143,10 +143,10 @@ static int launch_mano_forward(const ManoModelDev& m, const float* pose, const f
 // Vertices materialised: the tcgen05 kernel (mano_tc.cu).  Joints only (verts == nullptr), the explicit FP32 cross-check
 // (simt = true) and the CPU emulator build: the SIMT kernel above.
 int mano_forward_dev(const ManoModelDev& m, const float* pose, const float* shape, int pose_stride, int shape_stride,
-                     int n, float* verts, float* joints, cudaStream_t stream, bool simt) {
+                     int n, float* verts, float* joints, cudaStream_t stream, bool simt, int debug_blend) {
   if (n <= 0) return VPHO_OK;
 #ifndef VPHO_EMU
-  if (verts && !simt) return mano_tc_forward(m.tc_host, m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream);
+  if (verts && !simt) return mano_tc_forward(m.tc_host, m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream, debug_blend);
 #endif
   if (n >= 148 * 32) return launch_mano_forward<16>(m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream);
   if (n >= 148 * 4) return launch_mano_forward<8>(m, pose, shape, pose_stride, shape_stride, n, verts, joints, stream);
@@ -245,11 +245,11 @@ extern "C" int vpho_mano_destroy(vpho_mano_t h) {
 
 extern "C" int vpho_mano_forward_ex(vpho_mano_t h, const float* pose, const float* shape, int n, float* verts,
                                     float* joints, int flags, void* stream) {
-  if (!h || n < 0 || (flags & ~VPHO_MANO_STRICT_FP32)) return VPHO_ERR_INVALID;
+  if (!h || n < 0 || (flags & ~(VPHO_MANO_STRICT_FP32 | VPHO_MANO_DEBUG_BLEND))) return VPHO_ERR_INVALID;
   if (n == 0) return VPHO_OK;
   if (!pose || !shape || !joints) return VPHO_ERR_INVALID;
   return mano_forward_dev(static_cast<ManoModelHost*>(h)->dev, pose, shape, 48, 10, n, verts, joints,
-                          (cudaStream_t)stream, (flags & VPHO_MANO_STRICT_FP32) != 0);
+                          (cudaStream_t)stream, (flags & VPHO_MANO_STRICT_FP32) != 0, (flags & VPHO_MANO_DEBUG_BLEND) ? 1 : 0);
 }
 
 extern "C" int vpho_mano_forward(vpho_mano_t h, const float* pose, const float* shape, int n, float* verts,

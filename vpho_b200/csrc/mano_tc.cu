@@ -75,7 +75,7 @@ static_assert(sizeof(MtScratch) <= kMtStages * kMtStage, "set-up scratch must fi
 __global__ void __launch_bounds__(kMtThreads, 1)
 k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CUtensorMap tmD_lo, ManoModelDev m, ManoTcDev t,
           const float* __restrict__ pose, const float* __restrict__ shape, int pose_stride, int shape_stride, int n,
-          float* __restrict__ verts, float* __restrict__ joints, int vt_per_cta) {
+          float* __restrict__ verts, float* __restrict__ joints, int vt_per_cta, int debug_blend) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   MtSmem& sm = *reinterpret_cast<MtSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   MtScratch& sc = *reinterpret_cast<MtScratch*>(sm.stage[0]);
@@ -216,8 +216,9 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
       int st = 0;
       uint32_t phase = 0;
       for (int vt = vt_lo; vt < vt_hi; ++vt)
-        for (int d = 0; d < 3; ++d)
+        for (int dd = 0; dd < 3; ++dd)
           for (int ch = 0; ch < kMtChunks; ++ch) {
+            const int d = dd;
             mbar_wait(&sm.empty[st], phase ^ 1);
             mbar_arrive_expect_tx(&sm.full[st], kMtStage);
             tma_load_2d(&tmD_hi, &sm.full[st], sm.stage[st], ch * 64, d * kMtVPad + vt * 128);
@@ -234,7 +235,8 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
       for (int vt = vt_lo; vt < vt_hi; ++vt) {
         mbar_wait(&sm.tmem_empty[buf], acc_phase ^ 1);
         tc_fence_after();
-        for (int d = 0; d < 3; ++d) {
+        for (int dd = 0; dd < 3; ++dd) {
+          const int d = dd;
           const uint32_t dcol = tmem_base + (uint32_t)(buf * 3 * kMtNC + d * kMtNC);
           for (int ch = 0; ch < kMtChunks; ++ch) {
             mbar_wait(&sm.full[st], phase);
@@ -267,65 +269,91 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
       const int v0 = vt * 128 + q * 32, v = v0 + lane;
       const bool vvalid = v < kVerts;
       const int nv = min(32, kVerts - v0);               // vertices of this warp that exist (<= 0: none)
-      // per-vertex constants
-      float tp[3] = {0.f, 0.f, 0.f}, w4[4] = {0.f, 0.f, 0.f, 0.f};
+      // per-vertex constants: rest-pose template and the 16 skinning weights.  A vertex with at most 4 non-zero weights
+      // (real MANO assets) takes the sparse path when the whole warp can; otherwise the dense sum over the 16 joints
+      float tp[3] = {0.f, 0.f, 0.f}, w16[16];
       unsigned jpack = 0;
       int nnz = 0, tip = -1;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w16[j] = 0.f;
       if (vvalid) {
         tp[0] = t.tmpl[v]; tp[1] = t.tmpl[kMtVPad + v]; tp[2] = t.tmpl[2 * kMtVPad + v];
         nnz = t.nz_n[v];
         jpack = t.nz_j[v];
-        const float4 ww = *reinterpret_cast<const float4*>(t.nz_w + (size_t)v * 4);
-        w4[0] = ww.x; w4[1] = ww.y; w4[2] = ww.z; w4[3] = ww.w;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 ww = *reinterpret_cast<const float4*>(t.w_dense + (size_t)v * 16 + j4 * 4);
+          w16[j4 * 4 + 0] = ww.x; w16[j4 * 4 + 1] = ww.y; w16[j4 * 4 + 2] = ww.z; w16[j4 * 4 + 3] = ww.w;
+        }
 #pragma unroll
         for (int tt = 0; tt < 5; ++tt)
           if (v == tip_vertex(tt)) tip = tt;
       }
+      const bool sparse = __all_sync(0xffffffffu, nnz <= 4);
+      float ws4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (sparse) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = (int)((jpack >> (4 * i)) & 15u);
+          float wj = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) wj = jj == j ? w16[jj] : wj;
+          ws4[i] = i < nnz ? wj : 0.f;
+        }
+      }
       mbar_wait(&sm.tmem_full[buf], acc_phase);
       tc_fence_after();
-      uint32_t ax[16], ay[16], az[16];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 3 * kMtNC + cg * 16);
-      tmem_ld16_issue(taddr, ax);
-      tmem_ld16_issue(taddr + kMtNC, ay);
-      tmem_ld16_issue(taddr + 2 * kMtNC, az);
-      tmem_ld16_wait(ax);          // (the register operands keep the compiler from using the values before the wait)
-      tmem_ld16_wait(ay);
-      tmem_ld16_wait(az);
-      // the accumulators are in registers: the buffer can be refilled while this warp skins
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.tmem_empty[buf]);
-      if (nv > 0) {
+      const uint32_t dstep = (uint32_t)kMtNC;
 #pragma unroll 1
-        for (int cc = 0; cc < 16; ++cc) {
-          const int c = cg * 16 + cc;
+      for (int h8 = 0; h8 < 2; ++h8) {
+        uint32_t ax[8], ay[8], az[8];
+        tmem_ld8x3(taddr + h8 * 8, taddr + dstep + h8 * 8, taddr + 2 * dstep + h8 * 8, ax, ay, az);
+        if (h8 == 1) {
+          // the accumulators are in registers: the buffer can be refilled while this warp skins
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.tmem_empty[buf]);
+        }
+        if (nv <= 0) continue;
+        // fully unrolled: the accumulator arrays must be indexed statically (they live in registers filled by the asm above)
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          const int c = cg * 16 + h8 * 8 + cc;
           if (c0 + c >= n) break;                          // uniform across the warp
           const float un = sm.center[c][3] * t.dirs_inv;
           const float vp[3] = {fmaf(__uint_as_float(ax[cc]), un, tp[0]), fmaf(__uint_as_float(ay[cc]), un, tp[1]),
                                fmaf(__uint_as_float(az[cc]), un, tp[2])};
-          float T[12];
+          // T = sum_j w_j A_j as six packed FP32 pairs (FFMA2; each half is the scalar fmaf of mano_skin_point)
+          unsigned long long T2[6];
 #pragma unroll
-          for (int i = 0; i < 12; ++i) T[i] = 0.f;
+          for (int i = 0; i < 6; ++i) T2[i] = 0ull;
           auto add_joint = [&](int j, float wj) {
-            const float4* a4 = reinterpret_cast<const float4*>(sm.A[c][j]);
-            const float4 a0 = a4[0], a1 = a4[1], a2 = a4[2];
-            T[0] = fmaf(wj, a0.x, T[0]); T[1] = fmaf(wj, a0.y, T[1]); T[2] = fmaf(wj, a0.z, T[2]); T[3] = fmaf(wj, a0.w, T[3]);
-            T[4] = fmaf(wj, a1.x, T[4]); T[5] = fmaf(wj, a1.y, T[5]); T[6] = fmaf(wj, a1.z, T[6]); T[7] = fmaf(wj, a1.w, T[7]);
-            T[8] = fmaf(wj, a2.x, T[8]); T[9] = fmaf(wj, a2.y, T[9]); T[10] = fmaf(wj, a2.z, T[10]); T[11] = fmaf(wj, a2.w, T[11]);
+            const ulonglong2* a2 = reinterpret_cast<const ulonglong2*>(sm.A[c][j]);
+            const ulonglong2 a0 = a2[0], a1 = a2[1], a2v = a2[2];
+            const unsigned long long w2 = f32x2_pack(wj, wj);
+            T2[0] = f32x2_fma(w2, a0.x, T2[0]); T2[1] = f32x2_fma(w2, a0.y, T2[1]);
+            T2[2] = f32x2_fma(w2, a1.x, T2[2]); T2[3] = f32x2_fma(w2, a1.y, T2[3]);
+            T2[4] = f32x2_fma(w2, a2v.x, T2[4]); T2[5] = f32x2_fma(w2, a2v.y, T2[5]);
           };
-          if (nnz <= 4) {
+          if (sparse) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              if (i < nnz) add_joint((int)((jpack >> (4 * i)) & 15u), w4[i]);
-          } else if (vvalid) {
-            for (int j = 0; j < 16; ++j) add_joint(j, t.w_dense[(size_t)v * 16 + j]);
+              if (i < nnz) add_joint((int)((jpack >> (4 * i)) & 15u), ws4[i]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) add_joint(j, w16[j]);
           }
+          float T[12];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) f32x2_unpack(T2[i], T[2 * i], T[2 * i + 1]);
           float o[3];
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
             const float raw = ((T[r * 4 + 0] * vp[0] + T[r * 4 + 1] * vp[1]) + T[r * 4 + 2] * vp[2]) + T[r * 4 + 3];
             o[r] = mano_center_scale(raw, sm.center[c][r]);
           }
+          if (debug_blend) { o[0] = vp[0]; o[1] = vp[1]; o[2] = vp[2]; }      // VPHO_MANO_DEBUG_BLEND: the blended rest pose
           ob[lane * 3 + 0] = o[0]; ob[lane * 3 + 1] = o[1]; ob[lane * 3 + 2] = o[2];
           if (tip >= 0) {
             float* dst = joints + ((size_t)(c0 + c) * 21 + tip_to_21(tip)) * 3;
@@ -433,7 +461,7 @@ void mano_tc_destroy(void* h) {
 }
 
 int mano_tc_forward(const void* h, const ManoModelDev& m, const float* pose, const float* shape, int pose_stride, int shape_stride,
-                    int n, float* verts, float* joints, cudaStream_t stream) {
+                    int n, float* verts, float* joints, cudaStream_t stream, int debug_blend) {
   const ManoTcHost* th = static_cast<const ManoTcHost*>(h);
   const int smem = (int)sizeof(MtSmem) + 1024;
   int dev = 0, n_sm = 148;
@@ -455,7 +483,7 @@ int mano_tc_forward(const void* h, const ManoModelDev& m, const float* pose, con
   profile_begin(VPHO_TAG_MANO_FULL, stream);
   if (launch_pdl(k_mano_tc, dim3(nb, gy), dim3(kMtThreads), smem, stream, 1, *reinterpret_cast<const CUtensorMap*>(th->map_hi),
                  *reinterpret_cast<const CUtensorMap*>(th->map_lo), m, th->dev, pose, shape, pose_stride, shape_stride, n, verts, joints,
-                 vt_per_cta) != cudaSuccess)
+                 vt_per_cta, debug_blend) != cudaSuccess)
     return VPHO_ERR_LAUNCH;
   profile_end(VPHO_TAG_MANO_FULL, stream);
   return VPHO_OK;

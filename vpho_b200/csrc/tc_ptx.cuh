@@ -185,6 +185,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Three 8-column TMEM loads (one per accumulator) and the wait in ONE asm statement: the destination registers are only
+// defined once the statement is over, so the compiler cannot copy them while the asynchronous loads are still in flight
+// (with separate issue / wait statements and several loads outstanding, a register move scheduled in between reads a
+// stale value).
+__device__ __forceinline__ void tmem_ld8x3(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t (&a)[8], uint32_t (&b)[8], uint32_t (&c)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%24];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%25];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16, %17, %18, %19, %20, %21, %22, %23}, [%26];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(b[0]), "=r"(b[1]),
+        "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]),
+        "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7])
+      : "r"(t0), "r"(t1), "r"(t2)
+      : "memory");
+}
+
+// packed FP32 pairs (sm_100 FFMA2): each half is an ordinary IEEE single-precision fused multiply-add
+__device__ __forceinline__ unsigned long long f32x2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 // host: 2-D K-major tensor [rows][kdim] (float32 or __half) -> TMA boxes of {128 bytes of k, box_rows}, 128-byte swizzle
 bool tc_make_map(void* map_out, const void* base, int rows, int box_rows, int kdim, bool half);
 bool tc_available();

@@ -198,6 +198,20 @@ int vpho_force_eval(vpho_assets_t h, const float* verts, const float* scale, con
                     const float* force_contact, const float* cone_anchor, const float* gravity, const float* com, int n, int group,
                     float* terms, float* force_local, float* force_point, float* force_global, void* stream);
 
+/* `ForceOptimizer.optimize_batch` for one batch (lib/engine/force_optimization.py:110-207): n_iter iterations (reference 3000)
+ * of the two AdamW optimisers (:33-37; lr, betas (0.9, 0.999), eps 1e-8, weight decay 0.01) over scale [n][32] (initialised
+ * 0.05) and weight [n][32][8] (0): gravity loss on the weights for the first switch_iter iterations (reference 300), then
+ * force + moment + contact-distribution loss on both (:150-176), with an analytic backward pass, in ONE persistent kernel.
+ * verts [n][778][3], force_contact [n][32], gravity / com [n][3] in the flipped frame (:134-137); cone_anchor [8][3] as
+ * for vpho_force_eval.  Out: the parameters after the last step; force_local / force_global [n][32][3] of the last
+ * iteration's forward pass, zeroed for hands with is_grasped == 0 (:191-194; NULL: none); losses [n_iter][5] =
+ * {loss, force, gravity, moment, dist} (optional).  The optimiser state starts fresh (the reference's first batch). */
+size_t vpho_force_optimize_workspace_bytes(int n);
+int vpho_force_optimize(vpho_assets_t h, const float* verts, const float* force_contact, const float* gravity, const float* com,
+                        const uint8_t* is_grasped, const float* cone_anchor, int n, int n_iter, int switch_iter, float lr,
+                        float* scale, float* weight, float* force_local, float* force_global, float* losses, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* Final pose error per image, in millimetres: metrics [n][4] = {MJE, MVE, ADD, ADD-S}.  MJE / MVE: mean Euclidean
  * joint / vertex distance of `TesterHand` (lib/engine/test.py:657-679); ADD / ADD-S of
  * `TesterObject.criterion_ADD_REP` (lib/engine/test.py:413-442) on the object's sampled vertices posed by the predicted /

@@ -733,3 +733,56 @@ def object_add_mm(obj: OracleObject, pd_6d, gt_6d, obj_name):
     add = (pv - gv).norm(dim=-1).mean(dim=-1) * 1000
     adds = torch.stack([exact_cdist(pv[i], gv[i]).min(dim=-1)[0].mean() for i in range(pv.shape[0])]) * 1000
     return add, adds
+
+
+def force_optimize(anchors: "OracleAnchors", vert3d, force_contact, gravity, com, n_iter: int = 3000, switch_iter: int = 300,
+                   lr: float = 1e-3, trace: bool = False):
+    """ForceOptimizer.optimize_batch for ONE batch (lib/engine/force_optimization.py:110-207), autograd + torch.optim.AdamW
+    exactly as the reference builds them (get_optimizer :33-37: two AdamW optimisers, betas (0.9, 0.999), eps 1e-8,
+    lr 1e-3, default weight decay; init_param :42-44: scale 0.05, weight 0).  Inputs already in the flipped frame
+    (:134-137).  Returns the parameters after the last step and the forces of the last iteration's forward pass (what the
+    reference saves, :185-206), plus the loss trace when asked."""
+    from torch import nn, optim
+    bs = vert3d.shape[0]
+    contact_mask = force_contact > 0.1
+    scale_p = nn.Parameter(torch.ones(bs, 32) * 0.05)
+    weight_p = nn.Parameter(torch.zeros(bs, 32, 8))
+    opt1 = optim.AdamW([weight_p], betas=(0.9, 0.999), eps=1e-8, lr=lr)
+    opt2 = optim.AdamW([scale_p, weight_p], betas=(0.9, 0.999), eps=1e-8, lr=lr)
+    gravity = gravity.reshape(bs, 1, 3)
+    com = com.reshape(bs, 1, 3)
+    losses = []
+    force_local = force_global = None
+    for i in range(n_iter):
+        scale = scale_p.clone() * contact_mask
+        weight = weight_p.clone()
+        force_local = get_local_force(scale, weight)
+        force_point, force_global = anchors.from_local_to_global(force_local, vert3d)
+        resultant = (force_global.sum(1, keepdim=True) + gravity).squeeze(1)
+        force_loss = torch.norm(resultant, dim=-1).mean()
+        sum_weight = force_loss.detach()
+        resultant2 = force_global.sum(1, keepdim=True)
+        cos_proj = torch.einsum("...i,...i->...", resultant2, -1 * gravity)
+        gravity_loss = F.mse_loss(cos_proj, torch.ones_like(cos_proj))
+        moment = torch.cross(force_point - com, force_global, dim=-1).sum(1)
+        moment_loss = torch.norm(moment, dim=-1).mean() * 30
+        moment_loss = moment_loss / (100 * sum_weight ** 2 + 1e-8)
+        scale_norm = scale / (scale.norm(dim=-1, keepdim=True).detach() + 1e-8).detach()
+        fc_norm = force_contact / (force_contact.norm(dim=-1, keepdim=True).detach() + 1e-8)
+        dist = torch.log(torch.abs(fc_norm / (scale_norm + 1e-8)) + 1e-8) * contact_mask
+        dist_loss = (dist ** 2).mean() * 0.1
+        dist_loss = dist_loss / (1000 * sum_weight ** 2 + 1e-8)
+        if i < switch_iter:
+            loss, opt = gravity_loss, opt1
+        else:
+            loss, opt = force_loss + moment_loss + dist_loss, opt2
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        if trace:
+            losses.append([float(x.detach()) for x in (loss, force_loss, gravity_loss, moment_loss, dist_loss)])
+    out = {"scale": scale_p.detach().clone(), "weight": weight_p.detach().clone(), "force_local": force_local.detach(),
+           "force_global": force_global.detach()}
+    if trace:
+        out["losses"] = torch.tensor(losses)
+    return out

@@ -238,6 +238,33 @@ def force_eval(assets: Assets, vert3d: torch.Tensor, scale: torch.Tensor, weight
     return (terms, *outs) if return_forces else terms
 
 
+def force_optimize(assets: Assets, vert3d: torch.Tensor, force_contact: torch.Tensor, gravity: torch.Tensor, com: torch.Tensor,
+                   is_grasped: Optional[torch.Tensor] = None, n_iter: int = 3000, switch_iter: int = 300, lr: float = 1e-3,
+                   return_losses: bool = False):
+    """`ForceOptimizer.optimize_batch` for one batch (lib/engine/force_optimization.py:110-207) in one persistent kernel.
+    vert3d (n,778,3), force_contact (n,32), gravity / com (n,3) or (n,1,3), already in the flipped frame (:134-137).
+    -> dict(scale (n,32), weight (n,32,8), force_local, force_global (n,32,3) [, losses (n_iter,5)])."""
+    lib = assets.lib
+    v = vert3d.reshape(-1, 778, 3).contiguous().float()
+    n, dev = v.shape[0], v.device
+    fc = force_contact.contiguous().float()
+    g, c = gravity.reshape(n, 3).contiguous().float(), com.reshape(n, 3).contiguous().float()
+    ig = None if is_grasped is None else is_grasped.to(torch.uint8).contiguous()
+    cone = cone_anchor_table().to(dev)
+    out = dict(scale=torch.empty((n, 32), dtype=torch.float32, device=dev), weight=torch.empty((n, 32, 8), dtype=torch.float32, device=dev),
+               force_local=torch.empty((n, 32, 3), dtype=torch.float32, device=dev),
+               force_global=torch.empty((n, 32, 3), dtype=torch.float32, device=dev))
+    losses = torch.empty((n_iter, 5), dtype=torch.float32, device=dev) if return_losses else None
+    ws = torch.empty(max(int(lib.c.vpho_force_optimize_workspace_bytes(n)), 256), dtype=torch.uint8, device=dev)
+    lib.check(lib.c.vpho_force_optimize(assets.handle, capi.ptr(v), capi.ptr(fc), capi.ptr(g), capi.ptr(c), capi.ptr(ig), capi.ptr(cone),
+                                        n, int(n_iter), int(switch_iter), C.c_float(lr), capi.ptr(out["scale"]), capi.ptr(out["weight"]),
+                                        capi.ptr(out["force_local"]), capi.ptr(out["force_global"]), capi.ptr(losses), capi.ptr(ws),
+                                        ws.numel(), capi.stream_of(v)), "vpho_force_optimize")
+    if return_losses:
+        out["losses"] = losses
+    return out
+
+
 def hand_pa_metrics(pd_joint, gt_joint, pd_vert, gt_vert, lib=None) -> torch.Tensor:
     """Per-image Procrustes-aligned hand errors in mm, (n, 23) = PA-MJE, PA-MVE, JE[21]
     (TesterHand.criterion_MJE_PAMJE, lib/engine/test.py:657-679; rigid_align_AtoB, lib/utils/transform_fn.py:43-66)."""

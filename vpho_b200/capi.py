@@ -84,6 +84,8 @@ _SIGNATURES = {
     "vpho_anchor_contact": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vpho_vertex_contact": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vpho_force_eval": (c_int, [c_void_p] * 9 + [c_int, c_int] + [c_void_p] * 5),
+    "vpho_force_optimize_workspace_bytes": (c_size_t, [c_int]),
+    "vpho_force_optimize": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_float] + [c_void_p] * 6 + [c_size_t, c_void_p]),
     "vpho_pose_metrics": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p]),
     "vpho_hand_metrics": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_void_p]),
     "vpho_objmetrics_create": (c_int, [c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,

@@ -294,14 +294,18 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
             # aggregated poses, stream-ordered behind the aggregation on the eval stream (they overlap the next batch's
             # samplers; everything is complete before the timed region ends); then, once per step, the next step's H2D
             # copies on the copy stream
+            used = [pd_[k] for k in out_keys] + [pd_["diff_final_hand_joint"], pd_["diff_final_hand_vert"], pd_["diff_final_obj_6d"]]
+            if args.record_stream == "main":
+                rec = recorder(pd_, d)               # one C call, five launches, behind the aggregation on the compute stream
+                used = [pd_[k] for k in out_keys] + [rec]
             done = torch.cuda.Event()
             done.record(cur)
             with torch.cuda.stream(eval_stream):
                 eval_stream.wait_event(done)
-                used = [pd_[k] for k in out_keys] + [pd_["diff_final_hand_joint"], pd_["diff_final_hand_vert"], pd_["diff_final_obj_6d"]]
                 for t in used:
                     t.record_stream(eval_stream)
-                rec = recorder(pd_, d)
+                if args.record_stream != "main":
+                    rec = recorder(pd_, d)
                 e2e_state["record"] = rec
                 outs = dict({k: pd_[k] for k in out_keys}, eval_record=rec)
                 for k, t in outs.items():
@@ -720,6 +724,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--record-stream", default="main", choices=["main", "side"],
+                    help="e2e leg: stream the evaluation record is computed on (main = behind the aggregation; side = beside the "
+                         "next batch's samplers)")
     args = ap.parse_args()
     if args.config == 4:
         args.config = 2          # config 4 is config 2 launched on N GPUs

@@ -244,6 +244,37 @@ int vpho_objmetrics_destroy(vpho_objmetrics_t h);
 int vpho_object_metrics(vpho_assets_t assets, vpho_objmetrics_t tables, const double* pd_rt, const double* gt_rt,
                         const int32_t* obj_id, const float* cam_intr, int n, int C, double* out, void* stream);
 
+/* The metric step of Trainer.evaluate for one batch (lib/engine/train_diff_hand_obj.py:224-269) in one call: the
+ * post-processing of :578-602 (un-flip left hands and add the root joint; rot6d + translation -> [R | t + root]),
+ * `TesterHand` on the aggregated hand, the first diffusion candidate and (when reg_hand_* are given) the regression hand,
+ * `TesterObject` on the aggregated and the first candidate object pose.  All pointers are DEVICE pointers.
+ * out [bs][n_sets * 25 + 2 * VPHO_OBJ_METRIC_COLS] float64, n_sets = 2 (3 with the regression hand): per hand set
+ * {MJE, PA_MJE, MVE, PAMVE, JE[21]} (mm), then per object set the columns of vpho_object_metrics.  This row is the
+ * payload that replaces the pickled dicts of `gather_for_metrics(use_gather_object=True)` (:333-357). */
+typedef struct {
+  int bs;                         /* images                                                             */
+  int S;                          /* candidates per image in the cand_* arrays (row 0 of each image is read) */
+  const float* agg_hand_joint;    /* [bs][21][3]      wrist-relative, flipped frame (vpho_hoi_aggregate)  */
+  const float* agg_hand_vert;     /* [bs][778][3]                                                       */
+  const float* cand_hand_joint;   /* [bs][S][21][3]   diff_final_hand_joint                             */
+  const float* cand_hand_vert;    /* [bs][S][778][3]  diff_final_hand_vert                              */
+  const float* reg_hand_joint;    /* [bs][21][3] or NULL                                                */
+  const float* reg_hand_vert;     /* [bs][778][3] or NULL                                               */
+  const double* agg_obj_6d;       /* [bs][9]     rot6d + root-relative translation                      */
+  const double* cand_obj_6d;      /* [bs][S][9]                                                         */
+  const float* root_joint;        /* [bs][3]                                                            */
+  const uint8_t* is_right;        /* [bs]                                                               */
+  const float* gt_joint;          /* [bs][21][3]  camera frame                                          */
+  const float* gt_vert;           /* [bs][778][3]                                                       */
+  const double* gt_obj_rt;        /* [bs][3][4]                                                         */
+  const float* cam_intr;          /* [bs][3][3]                                                         */
+  const int32_t* obj_id;          /* [bs]                                                               */
+  double* out;                    /* [bs][n_sets * 25 + 34]                                             */
+} vpho_eval_record_args;
+size_t vpho_eval_record_workspace_bytes(int bs);
+int vpho_eval_record(vpho_assets_t assets, vpho_objmetrics_t tables, const vpho_eval_record_args* args, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* Procrustes-aligned hand errors per image, in millimetres: metrics [n][23] = {PA-MJE, PA-MVE, JE[21]} of
  * `TesterHand.criterion_MJE_PAMJE` (lib/engine/test.py:657-679): the prediction is aligned to the ground truth by the
  * similarity transform of `rigid_align_AtoB` (lib/utils/transform_fn.py:43-66; SVD of the 3x3 cross-covariance, reflection

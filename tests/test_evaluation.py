@@ -68,6 +68,15 @@ def _check(lib, dev, bs, S):
     assert np.abs(ours_o[..., [0, 1, 3, 6]] - ref_o[..., [0, 1, 3, 6]]).max() < 1e-8
     assert (np.abs(ours_o[..., [2, 4, 5, 7]] - ref_o[..., [2, 4, 5, 7]]) / np.abs(ref_o[..., [2, 4, 5, 7]])).max() < 5e-6
     assert np.abs(ours_o[..., 8:14] - ref_o[..., 8:14]).max() <= 1.5 / 2048
+    # the fused call agrees with the row assembled from the individual entry points; with the regression hand too
+    un = rec.unfused(pd, dbatch).cpu()
+    assert (row[:, :50] - un[:, :50]).abs().max() < 1e-4 and (row[:, 50:] - un[:, 50:]).abs().max() < 1e-9
+    rec3 = EvalRecorder(assets, tables, with_regression=True)
+    row3 = rec3(pd, dbatch, reg_vert=pd["agg_hand_vert"], reg_joint=pd["agg_hand_joint"]).cpu()
+    assert rec3.width == 3 * 25 + 2 * 17 and torch.equal(row3[:, :50], row[:, :50]) and torch.equal(row3[:, 75:], row[:, 50:])
+    assert torch.equal(row3[:, 50:75], row[:, :25])
+    with pytest.raises(ValueError):
+        rec3(pd, dbatch)
     s = summarize(row, rec.cols)
     assert abs(s["hand/agg_candidate/MJE"] - float(row[:, 0].mean())) < 1e-12 and len(s) == rec.width
     assert rec.cols[0] == "hand/agg_candidate/MJE" and rec.cols[25 + 3] == "hand/one_candidate/" + HAND_COLS[3]

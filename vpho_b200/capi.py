@@ -45,6 +45,14 @@ class HoiArgs(C.Structure):
     ]
 
 
+class EvalRecordArgs(C.Structure):
+    """`vpho_eval_record_args` (include/vpho_b200.h)."""
+    _fields_ = [("bs", c_int), ("S", c_int)] + [(k, c_void_p) for k in (
+        "agg_hand_joint", "agg_hand_vert", "cand_hand_joint", "cand_hand_vert", "reg_hand_joint", "reg_hand_vert",
+        "agg_obj_6d", "cand_obj_6d", "root_joint", "is_right", "gt_joint", "gt_vert", "gt_obj_rt", "cam_intr", "obj_id",
+        "out")]
+
+
 _SIGNATURES = {
     "vpho_version": (c_int, []),
     "vpho_launch_count": (C.c_ulonglong, []),
@@ -92,6 +100,8 @@ _SIGNATURES = {
                                        C.POINTER(c_void_p)]),
     "vpho_objmetrics_destroy": (c_int, [c_void_p]),
     "vpho_object_metrics": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "vpho_eval_record_workspace_bytes": (c_size_t, [c_int]),
+    "vpho_eval_record": (c_int, [c_void_p, c_void_p, C.POINTER(EvalRecordArgs), c_void_p, c_size_t, c_void_p]),
     "vpho_hand_pa_metrics": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_void_p]),
     "vpho_hoi_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vpho_hoi_aggregate": (c_int, [c_void_p, c_void_p, C.POINTER(HoiArgs), c_void_p, c_size_t, c_void_p]),

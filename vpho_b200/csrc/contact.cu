@@ -397,15 +397,15 @@ __device__ __forceinline__ double aligned_error(const float* a, const float* b, 
 // per-image row of TesterHand.__call__ (lib/engine/test.py:589-654)
 __global__ void __launch_bounds__(256) k_hand_pa_metrics(const float* __restrict__ pd_joint, const float* __restrict__ gt_joint,
                                                          const float* __restrict__ pd_vert, const float* __restrict__ gt_vert,
-                                                         float* __restrict__ out, int full) {
+                                                         float* __restrict__ out, int full, int gt_rows) {
   __shared__ double red[256];
   __shared__ double T[12];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x, g = b % gt_rows;      // several prediction sets may share one ground truth
   const int W = full ? 25 : 23, o_je = full ? 4 : 2, o_pamje = full ? 1 : 0, o_pamve = full ? 3 : 1;
   const float* pj = pd_joint + (size_t)b * 21 * 3;
-  const float* gj = gt_joint + (size_t)b * 21 * 3;
+  const float* gj = gt_joint + (size_t)g * 21 * 3;
   const float* pv = pd_vert + (size_t)b * kVerts * 3;
-  const float* gv = gt_vert + (size_t)b * kVerts * 3;
+  const float* gv = gt_vert + (size_t)g * kVerts * 3;
   double je = 0.0;
   if (tid < 21) {
     const float dx = gj[tid * 3 + 0] - pj[tid * 3 + 0], dy = gj[tid * 3 + 1] - pj[tid * 3 + 1], dz = gj[tid * 3 + 2] - pj[tid * 3 + 2];
@@ -439,6 +439,13 @@ __global__ void __launch_bounds__(256) k_hand_pa_metrics(const float* __restrict
   }
 }
 
+// used by vpho_eval_record (metrics.cu): `rows` predictions against ground truth rows [rows % gt_rows]
+int launch_hand_metrics_full(const float* pd_joint, const float* gt_joint, const float* pd_vert, const float* gt_vert, int rows, int gt_rows,
+                             float* metrics, cudaStream_t st) {
+  VPHO_LAUNCH(k_hand_pa_metrics, dim3(rows), dim3(256), 0, st, pd_joint, gt_joint, pd_vert, gt_vert, metrics, 1, gt_rows);
+  return VPHO_OK;
+}
+
 }  // namespace vpho
 
 using namespace vpho;
@@ -460,7 +467,7 @@ extern "C" int vpho_hand_pa_metrics(const float* pd_joint, const float* gt_joint
   if (n < 0) return VPHO_ERR_INVALID;
   if (n == 0) return VPHO_OK;
   if (!pd_joint || !gt_joint || !pd_vert || !gt_vert || !metrics) return VPHO_ERR_INVALID;
-  VPHO_LAUNCH(k_hand_pa_metrics, dim3(n), dim3(256), 0, (cudaStream_t)stream, pd_joint, gt_joint, pd_vert, gt_vert, metrics, 0);
+  VPHO_LAUNCH(k_hand_pa_metrics, dim3(n), dim3(256), 0, (cudaStream_t)stream, pd_joint, gt_joint, pd_vert, gt_vert, metrics, 0, n);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }
@@ -470,7 +477,7 @@ extern "C" int vpho_hand_metrics(const float* pd_joint, const float* gt_joint, c
   if (n < 0) return VPHO_ERR_INVALID;
   if (n == 0) return VPHO_OK;
   if (!pd_joint || !gt_joint || !pd_vert || !gt_vert || !metrics) return VPHO_ERR_INVALID;
-  VPHO_LAUNCH(k_hand_pa_metrics, dim3(n), dim3(256), 0, (cudaStream_t)stream, pd_joint, gt_joint, pd_vert, gt_vert, metrics, 1);
+  VPHO_LAUNCH(k_hand_pa_metrics, dim3(n), dim3(256), 0, (cudaStream_t)stream, pd_joint, gt_joint, pd_vert, gt_vert, metrics, 1, n);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }

@@ -296,6 +296,65 @@ __global__ void __launch_bounds__(kMT) k_object_metrics(AssetsDev as, ObjMetricD
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// The whole metric step of Trainer.evaluate for one batch (lib/engine/train_diff_hand_obj.py:224-269) behind one call:
+// postprocess (:578-602: un-flip left hands, add the root joint; rot6d + translation -> [R | t + root]), TesterHand on the
+// aggregated / first-candidate (/ regression) hands, TesterObject on the aggregated / first-candidate object poses, packed
+// into one float64 row per image.
+// ------------------------------------------------------------------------------------------------------------
+struct EvalDev {
+  vpho_eval_record_args a;
+  int n_sets;              // hand predictions evaluated per image: 2, or 3 with the regression hand
+  float* joint;            // [n_sets][bs][21][3]  post-processed predictions
+  float* vert;             // [n_sets][bs][778][3]
+  double* obj_rt;          // [bs][2][12]
+  float* hand_metrics;     // [n_sets][bs][25]
+  double* obj_metrics;     // [bs][2][17]
+};
+
+__global__ void __launch_bounds__(256) k_eval_prepare(EvalDev e) {
+  const int b = blockIdx.x, tid = threadIdx.x, bs = e.a.bs, S = e.a.S;
+  const float sign = e.a.is_right[b] ? 1.f : -1.f;
+  const float r[3] = {e.a.root_joint[b * 3 + 0], e.a.root_joint[b * 3 + 1], e.a.root_joint[b * 3 + 2]};
+  for (int set = 0; set < e.n_sets; ++set) {
+    const float* pj = set == 0 ? e.a.agg_hand_joint + (size_t)b * 63
+                               : (set == 1 ? e.a.cand_hand_joint + (size_t)b * S * 63 : e.a.reg_hand_joint + (size_t)b * 63);
+    const float* pv = set == 0 ? e.a.agg_hand_vert + (size_t)b * kVerts * 3
+                               : (set == 1 ? e.a.cand_hand_vert + (size_t)b * S * kVerts * 3 : e.a.reg_hand_vert + (size_t)b * kVerts * 3);
+    float* dj = e.joint + ((size_t)set * bs + b) * 63;
+    float* dv = e.vert + ((size_t)set * bs + b) * kVerts * 3;
+    for (int i = tid; i < (21 + kVerts) * 3; i += 256) {
+      const int d = i % 3;
+      const float x = i < 63 ? pj[i] : pv[i - 63];
+      const float y = (d == 0 ? sign * x : x) + r[d];       // __postprocess_hand_vert (:598-602)
+      if (i < 63) dj[i] = y; else dv[i - 63] = y;
+    }
+  }
+  if (tid < 2) {
+    const double* p = tid == 0 ? e.a.agg_obj_6d + (size_t)b * 9 : e.a.cand_obj_6d + (size_t)b * S * 9;
+    double R[9];
+    rot6d_to_matrix(p, R);                                  // obj_9D_to_mat; translation + root joint (:593-596)
+    double* o = e.obj_rt + ((size_t)b * 2 + tid) * 12;
+    for (int row = 0; row < 3; ++row) {
+      for (int cc = 0; cc < 3; ++cc) o[row * 4 + cc] = R[row * 3 + cc];
+      o[row * 4 + 3] = p[6 + row] + (double)r[row];
+    }
+  }
+}
+
+__global__ void k_eval_pack(EvalDev e) {
+  const int b = blockIdx.x, bs = e.a.bs, W = e.n_sets * 25 + 2 * kMetricCols;
+  double* row = e.a.out + (size_t)b * W;
+  for (int i = threadIdx.x; i < W; i += blockDim.x) {
+    if (i < e.n_sets * 25) row[i] = (double)e.hand_metrics[((size_t)(i / 25) * bs + b) * 25 + i % 25];
+    else row[i] = e.obj_metrics[(size_t)b * 2 * kMetricCols + (i - e.n_sets * 25)];
+  }
+}
+
+// contact.cu
+int launch_hand_metrics_full(const float* pd_joint, const float* gt_joint, const float* pd_vert, const float* gt_vert, int rows, int gt_rows,
+                             float* metrics, cudaStream_t st);
+
 }  // namespace vpho
 
 using namespace vpho;
@@ -337,6 +396,9 @@ extern "C" int vpho_objmetrics_destroy(vpho_objmetrics_t h) {
   return VPHO_OK;
 }
 
+static int launch_object_metrics(const AssetsDev& as, ObjMetricHost* mh, const double* pd_rt, const double* gt_rt, const int32_t* obj_id,
+                                 const float* cam_intr, int n, int C, double* out, cudaStream_t st);
+
 extern "C" int vpho_object_metrics(vpho_assets_t assets, vpho_objmetrics_t tables, const double* pd_rt, const double* gt_rt,
                                    const int32_t* obj_id, const float* cam_intr, int n, int C, double* out, void* stream) {
   if (!assets || !tables || n < 0 || C < 0) return VPHO_ERR_INVALID;
@@ -345,17 +407,59 @@ extern "C" int vpho_object_metrics(vpho_assets_t assets, vpho_objmetrics_t table
   const AssetsDev& as = static_cast<AssetsHost*>(assets)->dev;
   const ObjMetricDev& mt = static_cast<ObjMetricHost*>(tables)->dev;
   if (mt.n_obj != as.n_obj) return VPHO_ERR_INVALID;
-  ObjMetricHost* mh = static_cast<ObjMetricHost*>(tables);
+  return launch_object_metrics(as, static_cast<ObjMetricHost*>(tables), pd_rt, gt_rt, obj_id, cam_intr, n, C, out, (cudaStream_t)stream);
+}
+
+static int launch_object_metrics(const AssetsDev& as, ObjMetricHost* mh, const double* pd_rt, const double* gt_rt, const int32_t* obj_id,
+                                 const float* cam_intr, int n, int C, double* out, cudaStream_t st) {
+  const ObjMetricDev& mt = mh->dev;
   const size_t rows = (size_t)n * C;
   if (rows > mh->part_rows) {
-    // grow the partial-sum workspace (rare: only when a larger batch than ever before arrives); earlier launches may still
-    // be reading the old one
     if (mh->part) { cudaDeviceSynchronize(); cudaFree(mh->part); mh->part = nullptr; mh->part_rows = 0; }
     if (cudaMalloc((void**)&mh->part, rows * kSplit * kPartCols * sizeof(double)) != cudaSuccess) return VPHO_ERR_ALLOC;
     mh->part_rows = rows;
   }
-  VPHO_LAUNCH(k_object_metrics_scan, dim3(kSplit, C, n), dim3(kMT), 0, (cudaStream_t)stream, as, mt, pd_rt, gt_rt, obj_id, C, mh->part);
-  VPHO_LAUNCH(k_object_metrics, dim3(C, n), dim3(kMT), 0, (cudaStream_t)stream, as, mt, pd_rt, gt_rt, obj_id, cam_intr, C, mh->part, out);
+  VPHO_LAUNCH(k_object_metrics_scan, dim3(kSplit, C, n), dim3(kMT), 0, st, as, mt, pd_rt, gt_rt, obj_id, C, mh->part);
+  VPHO_LAUNCH(k_object_metrics, dim3(C, n), dim3(kMT), 0, st, as, mt, pd_rt, gt_rt, obj_id, cam_intr, C, mh->part, out);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
+
+extern "C" size_t vpho_eval_record_workspace_bytes(int bs) {
+  if (bs <= 0) return 0;
+  return (size_t)bs * (3 * (21 + kVerts) * 3 * 4 + 2 * 12 * 8 + 3 * 25 * 4 + 2 * kMetricCols * 8) + 5 * 256;
+}
+
+extern "C" int vpho_eval_record(vpho_assets_t assets, vpho_objmetrics_t tables, const vpho_eval_record_args* args, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (!assets || !tables || !args || !workspace) return VPHO_ERR_INVALID;
+  const vpho_eval_record_args& a = *args;
+  if (a.bs < 0 || a.S <= 0) return VPHO_ERR_INVALID;
+  if (a.bs == 0) return VPHO_OK;
+  if (!a.agg_hand_joint || !a.agg_hand_vert || !a.cand_hand_joint || !a.cand_hand_vert || !a.agg_obj_6d || !a.cand_obj_6d || !a.root_joint ||
+      !a.is_right || !a.gt_joint || !a.gt_vert || !a.gt_obj_rt || !a.cam_intr || !a.obj_id || !a.out || (!a.reg_hand_joint != !a.reg_hand_vert))
+    return VPHO_ERR_INVALID;
+  if (workspace_bytes < vpho_eval_record_workspace_bytes(a.bs)) return VPHO_ERR_INVALID;
+  const AssetsDev& as = static_cast<AssetsHost*>(assets)->dev;
+  ObjMetricHost* mh = static_cast<ObjMetricHost*>(tables);
+  if (mh->dev.n_obj != as.n_obj) return VPHO_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  EvalDev e;
+  e.a = a;
+  e.n_sets = a.reg_hand_joint ? 3 : 2;
+  char* p = static_cast<char*>(workspace);
+  auto take = [&](size_t bytes) { char* q = p; p += (bytes + 255) / 256 * 256; return q; };
+  e.obj_rt = reinterpret_cast<double*>(take((size_t)a.bs * 2 * 12 * 8));
+  e.obj_metrics = reinterpret_cast<double*>(take((size_t)a.bs * 2 * kMetricCols * 8));
+  e.joint = reinterpret_cast<float*>(take((size_t)e.n_sets * a.bs * 63 * 4));
+  e.vert = reinterpret_cast<float*>(take((size_t)e.n_sets * a.bs * kVerts * 3 * 4));
+  e.hand_metrics = reinterpret_cast<float*>(take((size_t)e.n_sets * a.bs * 25 * 4));
+  VPHO_LAUNCH(k_eval_prepare, dim3(a.bs), dim3(256), 0, st, e);
+  int rc = launch_hand_metrics_full(e.joint, a.gt_joint, e.vert, a.gt_vert, e.n_sets * a.bs, a.bs, e.hand_metrics, st);
+  if (rc) return rc;
+  rc = launch_object_metrics(as, mh, e.obj_rt, a.gt_obj_rt, a.obj_id, a.cam_intr, a.bs, 2, e.obj_metrics, st);
+  if (rc) return rc;
+  VPHO_LAUNCH(k_eval_pack, dim3(a.bs), dim3(128), 0, st, e);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }

@@ -13,6 +13,7 @@ test_diff_object :492-514) the 17 columns of `ObjectMetrics` (`TesterObject`, li
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Dict, List, Optional
 
 import torch
@@ -93,6 +94,7 @@ class EvalRecorder:
         self.obj_metrics = ObjectMetrics(assets, metric_tables)
         self.hand_sets = ["agg_candidate", "one_candidate"] + (["regression"] if with_regression else [])
         self.obj_sets = ["mean_pose", "one_candidate"]
+        self._ws: Optional[torch.Tensor] = None
         self.cols: List[str] = [f"hand/{s}/{c}" for s in self.hand_sets for c in HAND_COLS] + \
                                [f"obj/{s}/{c}" for s in self.obj_sets for c in OBJ_METRIC_COLS]
 
@@ -104,7 +106,41 @@ class EvalRecorder:
     def __call__(self, pd: Dict, batch: Dict, reg_vert: Optional[torch.Tensor] = None,
                  reg_joint: Optional[torch.Tensor] = None) -> torch.Tensor:
         """pd: output of VphoHotPath.predict.  batch: device tensors root_joint (bs,3), is_right (bs,), gt_joint (bs,21,3),
-        gt_hand_vert (bs,778,3), gt_obj_rt (bs,3,4), cam_intr (bs,3,3), obj_id / obj_name.  -> (bs, width) float64."""
+        gt_hand_vert (bs,778,3), gt_obj_rt (bs,3,4), cam_intr (bs,3,3), obj_id / obj_name.  -> (bs, width) float64.
+        One `vpho_eval_record` call (five launches on the current stream): no intermediate tensor leaves the library."""
+        lib = self.assets.lib
+        with_reg = "regression" in self.hand_sets
+        if with_reg and (reg_vert is None or reg_joint is None):
+            raise ValueError("this recorder was built with_regression=True: pass reg_vert and reg_joint")
+        f32 = lambda t: t.contiguous().float()      # noqa: E731  (no-ops for predict()'s own outputs)
+        f64 = lambda t: t.contiguous().double()     # noqa: E731
+        aj, av = f32(pd["agg_hand_joint"]), f32(pd["agg_hand_vert"])
+        cj, cv = f32(pd["diff_final_hand_joint"]), f32(pd["diff_final_hand_vert"])
+        ao, co = f64(pd["agg_obj_6d"]), f64(pd["diff_final_obj_6d"])
+        bs, S, dev = cj.shape[0], cj.shape[1], cj.device
+        root, right = f32(batch["root_joint"]), batch["is_right"].contiguous().to(torch.uint8)
+        gj, gv, grt, K = f32(batch["gt_joint"]), f32(batch["gt_hand_vert"]), f64(batch["gt_obj_rt"]), f32(batch["cam_intr"])
+        ids = self.assets.ids(batch["obj_id"] if "obj_id" in batch else batch["obj_name"], dev)
+        rj, rv = (f32(reg_joint), f32(reg_vert)) if with_reg else (None, None)
+        out = torch.empty((bs, self.width), dtype=torch.float64, device=dev)
+        need = int(lib.c.vpho_eval_record_workspace_bytes(bs))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+        P = capi.ptr
+        args = capi.EvalRecordArgs(
+            bs=bs, S=S, agg_hand_joint=P(aj), agg_hand_vert=P(av), cand_hand_joint=P(cj), cand_hand_vert=P(cv),
+            reg_hand_joint=P(rj) if with_reg else None, reg_hand_vert=P(rv) if with_reg else None, agg_obj_6d=P(ao),
+            cand_obj_6d=P(co), root_joint=P(root), is_right=P(right), gt_joint=P(gj), gt_vert=P(gv), gt_obj_rt=P(grt),
+            cam_intr=P(K), obj_id=P(ids), out=P(out))
+        lib.check(lib.c.vpho_eval_record(self.assets.handle, self.obj_metrics.handle, C.byref(args), P(self._ws),
+                                         self._ws.numel(), capi.stream_of(out)), "vpho_eval_record")
+        return out
+
+    @torch.no_grad()
+    def unfused(self, pd: Dict, batch: Dict, reg_vert: Optional[torch.Tensor] = None,
+                reg_joint: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The same row assembled from the individual entry points (`vpho_hand_metrics`, `vpho_object_metrics`) with the
+        post-processing in torch: the cross-check of `vpho_eval_record` in tests/test_evaluation.py."""
         root, is_right = batch["root_joint"], batch["is_right"].bool()
         lib = self.assets.lib
         parts = []

@@ -261,6 +261,11 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     def step_resident():
         return hp.predict(resident, prior_hand=resident["prior_hand"], prior_obj=resident["prior_obj"])
 
+    def step_pipelined():
+        # consecutive batches software-pipelined: predict returns once the samplers are done; this batch's aggregation and
+        # output-only work keep running on the library's streams under the next batch's samplers
+        return hp.predict(resident, prior_hand=resident["prior_hand"], prior_obj=resident["prior_obj"], defer_join=True)
+
     # e2e: inputs live in pinned host memory; every step issues one full H2D copy (the NEXT step's inputs, on a copy
     # stream, double-buffered -- what a prefetching eval loop does), computes the evaluation record on the device and
     # reads the record and the aggregated poses back.
@@ -268,11 +273,11 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     eval_stream = torch.cuda.Stream(device=dev)          # the metric step of batch i runs beside the samplers of batch i+1
     dev_sets = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()} for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]     # by the compute stream, by the eval stream
+    consumed = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]     # by the compute stream(s), by the eval stream
     for pair in consumed:
         for e in pair:
             e.record()
-    e2e_state = {"i": 0, "record": None}
+    e2e_state = {"i": 0, "record": None, "read": [None, None]}
 
     def prefetch(slot):
         with torch.cuda.stream(copy_stream):
@@ -290,21 +295,22 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         d = dev_sets[slot]
 
         def enqueued(pd_, issue):
-            # metric step on the device (TesterHand / TesterObject rows) and the device -> host reads of the record and the
-            # aggregated poses, stream-ordered behind the aggregation on the eval stream (they overlap the next batch's
-            # samplers; everything is complete before the timed region ends); then, once per step, the next step's H2D
-            # copies on the copy stream
+            # metric step on the device (TesterHand / TesterObject rows, one C call) and the device -> host reads of the
+            # record and the aggregated poses, stream-ordered behind the aggregation; then, once per step, the next step's
+            # H2D copies on the copy stream
             used = [pd_[k] for k in out_keys] + [pd_["diff_final_hand_joint"], pd_["diff_final_hand_vert"], pd_["diff_final_obj_6d"]]
-            if args.record_stream == "main":
-                rec = recorder(pd_, d)               # one C call, five launches, behind the aggregation on the compute stream
+            if args.record_stream == "main" and not args.pipeline:
+                rec = recorder(pd_, d)               # behind the aggregation on the compute stream
                 used = [pd_[k] for k in out_keys] + [rec]
             done = torch.cuda.Event()
             done.record(cur)
             with torch.cuda.stream(eval_stream):
                 eval_stream.wait_event(done)
+                for ev, _ in pd_.get("_done", ()):          # pipelined: the aggregation is not joined into `cur`
+                    eval_stream.wait_event(ev)
                 for t in used:
                     t.record_stream(eval_stream)
-                if args.record_stream != "main":
+                if args.record_stream != "main" or args.pipeline:
                     rec = recorder(pd_, d)
                 e2e_state["record"] = rec
                 outs = dict({k: pd_[k] for k in out_keys}, eval_record=rec)
@@ -312,13 +318,22 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
                     if k not in host_out:
                         host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
                     host_out[k].copy_(t, non_blocking=True)
+                consumed[slot][1] = torch.cuda.Event()
                 consumed[slot][1].record(eval_stream)
             if issue == 0:
                 prefetch(slot ^ 1)
 
-        pd = hp.predict(d, prior_hand=d["prior_hand"], prior_obj=d["prior_obj"], prefetch=enqueued)
+        pd = hp.predict(d, prior_hand=d["prior_hand"], prior_obj=d["prior_obj"], prefetch=enqueued, defer_join=bool(args.pipeline))
+        consumed[slot][0] = torch.cuda.Event()
         consumed[slot][0].record(cur)
-        cur.synchronize()
+        if args.pipeline:
+            # the host consumes the PREVIOUS batch's record while this batch's aggregation still runs
+            prev = e2e_state["read"][slot ^ 1]
+            if prev is not None:
+                prev.synchronize()
+            e2e_state["read"][slot] = consumed[slot][1]
+        else:
+            cur.synchronize()
         return pd
 
     def barrier():
@@ -329,7 +344,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     windows = []
 
     def timed(step_fn, steps, profile=0, gather=False):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         l0 = lib.c.vpho_launch_count()
         if profile:
@@ -337,26 +352,27 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         wall0 = time.perf_counter()
         windows.append([wall0, wall0])
         last = None
+        t0.record()
         for i in range(steps):
-            ev[i][0].record()
             last = None              # release the previous step's outputs first: same footprint as the warm-up steps
             last = step_fn()
-            ev[i][1].record()
+        VphoHotPath.join(last)       # pipelined steps: the compute stream waits for the last batch's aggregation / meshes
+        if gather:
+            torch.cuda.current_stream().wait_stream(eval_stream)
         if world > 1 and gather:
             # the only collective of the path: the per-image evaluation rows (replaces gather_for_metrics,
             # train_diff_hand_obj.py:333-335)
-            torch.cuda.current_stream().wait_stream(eval_stream)
             rec = e2e_state["record"] if e2e_state["record"] is not None else recorder(last, resident)
             gathered = gather_records(rec, bs * world)
             assert gathered.shape == (bs * world, recorder.width)
+        t1.record()
         barrier()
         wall = time.perf_counter() - wall0
         windows[-1][1] = wall0 + wall
         if profile:
             lib.c.vpho_profile_enable(0)
         launches = lib.c.vpho_launch_count() - l0
-        per_step = [a.elapsed_time(b) for a, b in ev]
-        ms = sum(per_step)
+        ms = t0.elapsed_time(t1)
         t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -379,7 +395,8 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     for _ in range(max(args.warmup, 3)):
         step_resident()
     # 1) the timed region (`value`): K steps, no library instrumentation at all
-    ms_res, wall_res, launches = timed(step_resident, args.steps)
+    ms_res, wall_res, launches = timed(step_pipelined if args.pipeline else step_resident, args.steps)
+    ms_latency = timed(step_resident, args.steps)[0] if args.pipeline else ms_res
     # 2) the same K steps with the dominant kernel (tag 0, head GEMM) bracketed by CUDA events on its launching stream ->
     #    roofline (median launch duration: a single driver hiccup must not move it)
     ms_roof, _, _ = timed(step_resident, args.steps, profile=1)
@@ -509,6 +526,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         "e2e": {"value": round(e2e, 1), "unit": "candidates/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(ms_e2e / args.steps, 4),
                 "h2d_ms_alone": round(h2d_ms, 3),
+                "pipelined": bool(args.pipeline),
                 "note": "H2D of step i+1 runs on a copy stream while step i computes; the timed region also computes the "
                         "per-image evaluation record (TesterHand / TesterObject metrics, %d float64 columns) on the device and "
                         "reads it back with the aggregated poses" % recorder.width + ("; the final NCCL gather of the records "
@@ -526,6 +544,12 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         "sampler": {"hand_net_calls": net_calls, "obj_net_calls": info["obj"]["net_calls"],
                     "hand_attempts": info["hand"]["attempts"], "rejected": info["hand"]["rejected"] + info["obj"]["rejected"]},
         "wall_ms_per_step": round(wall_res / args.steps, 4),
+        "pipelining": {"enabled": bool(args.pipeline), "latency_ms_per_batch": round(ms_latency / args.steps, 4),
+                       "note": "value / ms_per_step: K batches issued back to back, batch i's aggregation + output-only work on "
+                               "the library's streams under batch i+1's samplers (predict(defer_join=True)); every batch's work, "
+                               "the last one's aggregation included, completes inside the timed region.  latency_ms_per_batch: "
+                               "the same K batches with each one joined before the next starts (round-1 definition of the step)"
+                               if args.pipeline else "each batch joined before the next starts"},
     }
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -724,7 +748,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--record-stream", default="main", choices=["main", "side"],
+    ap.add_argument("--pipeline", type=int, default=1, choices=[0, 1],
+                    help="1: consecutive batches software-pipelined (batch i's aggregation under batch i+1's samplers); 0: each "
+                         "batch joined before the next starts")
+    ap.add_argument("--record-stream", default="side", choices=["main", "side"],
                     help="e2e leg: stream the evaluation record is computed on (main = behind the aggregation; side = beside the "
                          "next batch's samplers)")
     args = ap.parse_args()

@@ -665,7 +665,7 @@ def get_local_force(scale: torch.Tensor, weight: torch.Tensor, friction_coeff: f
     """HeadPhysics.get_local_force (lib/model/physics.py:546-557)."""
     scale = torch.abs(scale)
     weight = torch.softmax(weight, dim=-1)
-    anchor = cone_anchor_table(friction_coeff)[None, :].repeat_interleave(scale.size(-1), dim=0)
+    anchor = cone_anchor_table(friction_coeff).to(weight.dtype)[None, :].repeat_interleave(scale.size(-1), dim=0)
     direction = torch.einsum("...ij,ijk->...ik", weight, anchor)
     direction = direction / (direction.norm(dim=-1, keepdim=True) + 1e-8)
     return direction * scale[..., None]
@@ -745,8 +745,9 @@ def force_optimize(anchors: "OracleAnchors", vert3d, force_contact, gravity, com
     from torch import nn, optim
     bs = vert3d.shape[0]
     contact_mask = force_contact > 0.1
-    scale_p = nn.Parameter(torch.ones(bs, 32) * 0.05)
-    weight_p = nn.Parameter(torch.zeros(bs, 32, 8))
+    dt = vert3d.dtype               # float32 as the reference; float64 inputs give the shadow run the tests derive their bar from
+    scale_p = nn.Parameter(torch.ones(bs, 32, dtype=dt) * 0.05)
+    weight_p = nn.Parameter(torch.zeros(bs, 32, 8, dtype=dt))
     opt1 = optim.AdamW([weight_p], betas=(0.9, 0.999), eps=1e-8, lr=lr)
     opt2 = optim.AdamW([scale_p, weight_p], betas=(0.9, 0.999), eps=1e-8, lr=lr)
     gravity = gravity.reshape(bs, 1, 3)

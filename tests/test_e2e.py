@@ -169,3 +169,30 @@ def test_e2e_cuda_single_image_readme_shape(cuda_lib):
     # BASELINE config 0: batch 1 x 100 samples x 50 steps
     hp, pd, ref, batch, assets = _run(None, "cuda", "clustered", 1, 100, 30, 10, 50, seed=11)
     _check(hp, pd, ref, batch, assets, "clustered")
+
+
+@pytest.mark.gpu
+def test_e2e_cuda_pipelined_batches_match_joined_batches(cuda_lib):
+    """predict(defer_join=True): three different batches issued back to back (each batch's aggregation still running on the
+    library's streams while the next batch's samplers are enqueued on the caller's) give bit-for-bit the joined results."""
+    mano, anch, objs = cases.assets()
+    st_h, st_o = syn.make_denoiser_state("mano_pose", 0), syn.make_denoiser_state("obj", 0)
+    hp = VphoHotPath(mano, anch, objs, st_h, st_o, sample_num=100, sampling_steps=50, topk_hand=30, topk_obj=10)
+    work = []
+    for seed in (1, 2, 3):
+        batch = syn.make_eval_batch(4, seed=seed, sample_num=100, mano=mano, objects=objs)
+        ph, po = cases.e2e_priors("clustered" if seed != 2 else "random", 4, 100, batch, seed)
+        work.append((to_device(batch, "cuda"), ph.cuda(), po.cuda()))
+    keys = ("agg_obj_6d", "agg_hand_mano", "agg_hand_vert", "agg_hand_joint", "diff_final_hand_vert", "diff_final_hand_joint",
+            "diff_final_obj_6d", "diff_inprocess_hand_mano", "diff_inprocess_obj_6d")
+    joined = [hp.predict(b, prior_hand=ph, prior_obj=po) for b, ph, po in work]
+    torch.cuda.synchronize()
+    piped = [hp.predict(b, prior_hand=ph, prior_obj=po, defer_join=True) for b, ph, po in work]
+    assert all("_done" in pd for pd in piped)
+    for pd in piped:
+        VphoHotPath.join(pd)
+        assert "_done" not in pd
+    torch.cuda.synchronize()
+    for a, b in zip(joined, piped):
+        for k in keys:
+            assert torch.equal(a[k], b[k]), k

@@ -1,8 +1,11 @@
 """`force_optimize` (one persistent kernel, analytic backward + AdamW; C ABI `vpho_force_optimize`) against the oracle's
 autograd restatement of ForceOptimizer.optimize_batch (lib/engine/force_optimization.py:110-207, torch.optim.AdamW).
 
-Tolerance: the loss trace 1e-4 relative, parameters 2e-5 absolute after 60 iterations (lr 1e-3: the parameters have moved by up
-to 0.06) -- Adam divides by sqrt(v), so a gradient whose sign is decided by FP32 rounding would show up as 2 lr per step."""
+Tolerance: the loss trace 1e-4 relative; parameters 2e-5 absolute after 60 iterations (lr 1e-3: they have moved by up to
+0.06) or, where larger, 3x the reference's OWN rounding floor: the same autograd oracle re-run in float64.  Adam divides by
+sqrt(v), so softmax logits whose gradient is at rounding level (an anchor that carries no force) drift by a visible fraction
+of lr per step in ANY float32 implementation -- the float64 shadow moves the reference's `weight` by 4e-5 .. 7e-5 on these
+cases while scale / forces / losses stay at 1e-7."""
 import numpy as np
 import pytest
 import torch
@@ -27,11 +30,14 @@ def _case(lib, dev, bs, n_iter, switch, seed=0):
     out = {k: t.cpu() for k, t in out.items()}
     lo, lr_ = out["losses"].double(), ref["losses"].double()
     assert ((lo - lr_).abs() <= 1e-4 * lr_.abs() + 1e-9).all(), (lo - lr_).abs().max()
-    assert (out["scale"] - ref["scale"]).abs().max().item() < 2e-5
-    assert (out["weight"] - ref["weight"]).abs().max().item() < 2e-5
+    sh = O.force_optimize(O.OracleAnchors(anch, torch.float64), v.double(), fc.double(), grav.double(), com.double(), n_iter=n_iter,
+                          switch_iter=switch)
     keep = grasp.float()[:, None, None]
-    assert (out["force_local"] - ref["force_local"] * keep).abs().max().item() < 2e-5
-    assert (out["force_global"] - ref["force_global"] * keep).abs().max().item() < 2e-5
+    for k, mask in (("scale", 1.0), ("weight", 1.0), ("force_local", keep), ("force_global", keep)):
+        floor = (sh[k].double() - ref[k].double()).abs().max().item()
+        err = (out[k] - ref[k] * mask).abs()
+        assert err.max().item() < max(2e-5, 3.0 * floor), (k, err.max().item(), floor)
+        assert torch.quantile(err.reshape(-1).double(), 0.99).item() < 2e-5, k
     # both phases ran and the second one reduced the force residual
     assert lr_[switch:, 1].min() < lr_[0, 1]
 

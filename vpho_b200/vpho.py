@@ -38,6 +38,7 @@ class VphoHotPath:
         self.last_info: dict = {}
         self._side_stream2 = None
         self._agg_stream = None
+        self._status_host = None
         # True: everything on the caller's stream (no output-only side stream, no high-priority aggregation stream);
         # bench.py's serialised per-kernel pass uses it together with vpho_set_pdl(0).  Results are identical.
         self.serialize = False
@@ -70,13 +71,19 @@ class VphoHotPath:
 
     @torch.no_grad()
     def predict(self, batch: Dict, *, prior_hand: Optional[torch.Tensor] = None, prior_obj: Optional[torch.Tensor] = None,
-                with_inprocess: bool = True, prefetch=None) -> Dict:
+                with_inprocess: bool = True, prefetch=None, defer_join: bool = False) -> Dict:
         """The whole batch (both samplers, MANO, scoring, aggregation) is enqueued without a host synchronisation and the
         two samplers' status words are read once at the end.  The number of RK attempts enqueued up front adapts to the
         previous batch (what it needed plus one spare).  If an integration needed more, it is CONTINUED on the same
         workspaces (`vpho_sample_pair_continue` + `_finish`, as the reference's solve_ivp simply keeps stepping) until both
         controllers report completion -- there is no attempt cap -- and only then is the downstream work enqueued again on
-        the now valid samples.  Results are identical either way."""
+        the now valid samples.  Results are identical either way.
+
+        defer_join=True (pipelined evaluation loops): the caller's stream is NOT made to wait for the aggregation and the
+        output-only work, which run on the library's own streams; `predict` returns as soon as both samplers have
+        finished, so the next batch's samplers (tensor-core bound, one CTA per SM) start while this batch's aggregation
+        (a chain of small latency-bound kernels) fills the idle SM time between them.  `pd["_done"]` holds the events
+        that complete the outputs; call `VphoHotPath.join(pd)` before reading them on another stream."""
         if prior_hand is None or prior_obj is None:
             # draw both priors up front, in the reference's order (hand, then object)
             from .score_based_model import ve_prior_std
@@ -98,30 +105,58 @@ class VphoHotPath:
         pend = (samples[0][2], samples[1][2])
         issue = 0
         while True:
-            pd = self._downstream(batch, samples, with_inprocess)      # speculative on the first pass
+            status = self._snapshot(pend)          # stream-ordered behind the samplers only: the host wakes when THEY finish
+            pd = self._downstream(batch, samples, with_inprocess, defer_join)      # speculative on the first pass
             if prefetch is not None:
                 # caller hook `prefetch(pd, issue)`, run after the batch is enqueued and before the host blocks on its
-                # status: the place to enqueue device-to-host reads of `pd` (stream-ordered behind the aggregation, complete
-                # when predict returns) and, for issue == 0, the next batch's host-to-device copies on another stream.
+                # status: the place to enqueue device-to-host reads of `pd` (stream-ordered behind the aggregation) and, for
+                # issue == 0, the next batch's host-to-device copies on another stream.
                 # When the samplers had to be continued (issue > 0, rare) it is called again with the new outputs.
                 prefetch(pd, issue)
             issue += 1
-            done = self._await(pend)                                   # the one host sync of the batch
+            done = self._await(pend, status)                           # the one host sync of the batch
             if done:
                 return pd
             # slow path: keep stepping both integrations until they finish, then redo the downstream work once
             stream = capi.stream_of(samples[0][1])
             while not done:
                 pend[0].pair.advance(4, stream)
-                done = self._await(pend)
+                done = self._await(pend, self._snapshot(pend))
 
-    def _await(self, pend) -> bool:
-        status = torch.stack([p.counters for p in pend]).cpu().tolist()
-        ok = [p.resolve(c) for p, c in zip(pend, status)]
+    def _snapshot(self, pend):
+        """Enqueue the read of both controllers' counters (pinned host buffer + event on the current stream)."""
+        dev_c = torch.stack([p.counters for p in pend])
+        if not dev_c.is_cuda:
+            return dev_c, None
+        if self._status_host is None:
+            self._status_host = [torch.empty((2, 8), dtype=torch.int32).pin_memory() for _ in range(2)]
+            self._status_i = 0
+        self._status_i ^= 1
+        host = self._status_host[self._status_i]
+        host.copy_(dev_c, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev_c.device))
+        return host, ev
+
+    def _await(self, pend, status) -> bool:
+        host, ev = status
+        if ev is not None:
+            ev.synchronize()
+        ok = [p.resolve(c) for p, c in zip(pend, host.tolist())]
         self.last_info = {"hand": pend[0].info, "obj": pend[1].info}
         return all(ok)
 
-    def _downstream(self, batch: Dict, samples, with_inprocess: bool) -> Dict:
+    @staticmethod
+    def join(pd: Dict, stream=None) -> Dict:
+        """Make `stream` (default: the current one) wait for the outputs of a `predict(..., defer_join=True)` result."""
+        evs = pd.pop("_done", None)
+        if evs:
+            stream = stream or torch.cuda.current_stream(evs[0][1])
+            for ev, _ in evs:
+                stream.wait_event(ev)
+        return pd
+
+    def _downstream(self, batch: Dict, samples, with_inprocess: bool, defer_join: bool = False) -> Dict:
         """Everything after the two `sample()` calls of the predict branch (VPHO.py:243-304).  batch: tensors on the CUDA
         device (see `to_device`)."""
         S = self.sample_num
@@ -188,9 +223,14 @@ class VphoHotPath:
                 self._agg_stream = torch.cuda.Stream(device=enc_h.device, priority=-1)
             hs = self._agg_stream
             hs.wait_stream(main)
+            if defer_join:
+                # nothing on the caller's stream orders these reads any more: tell the allocator who uses the tensors
+                for t in [final_mano, x_o] + [v for v in batch.values() if torch.is_tensor(v) and v.is_cuda]:
+                    t.record_stream(hs)
             with torch.cuda.stream(hs):
                 sel = aggregate()
-            main.wait_stream(hs)
+            if not defer_join:
+                main.wait_stream(hs)
             for v in sel.values():
                 if torch.is_tensor(v):
                     v.record_stream(main)
@@ -202,7 +242,14 @@ class VphoHotPath:
         pd["agg_hand_joint"] = sel["hand_agg_joint"]
         pd["_sel"] = sel
         if side2 is not None:
-            main.wait_stream(side2)
+            if defer_join:
+                pd["_done"] = []
+                for st in (hs, side2):
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    pd["_done"].append((ev, enc_h.device))
+            else:
+                main.wait_stream(side2)
         return pd
 
     __call__ = predict

@@ -1,0 +1,51 @@
+"""GPU probe: throughput of K back-to-back batches, joined vs pipelined (predict(defer_join=True)) under different stream
+priorities.  usage: python tools/pipeline_probe.py [steps]"""
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+import bench  # noqa: E402
+from vpho_b200.vpho import VphoHotPath  # noqa: E402
+
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+dev = torch.device("cuda", 0)
+mano, anchors, objects, batch, prior_h, prior_o, st_h, st_o = bench.make_inputs(bench.BS, seed=0)
+import numpy as np  # noqa: E402
+batch["obj_id"] = np.asarray(batch["obj_id"], np.int32)
+res = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in batch.items() if isinstance(v, np.ndarray)}
+ph, po = prior_h.to(dev), prior_o.to(dev)
+
+
+def run(name, defer, compute_prio=None, agg_prio=-1, mesh_prio=0):
+    hp = VphoHotPath(mano, anchors, objects, st_h, st_o, sample_num=bench.S, sampling_steps=bench.STEPS_ODE, sample_T0=bench.T0,
+                     topk_hand=bench.K_HAND, topk_obj=bench.K_OBJ)
+    hp._agg_stream = torch.cuda.Stream(device=dev, priority=agg_prio)
+    hp._side_stream2 = torch.cuda.Stream(device=dev, priority=mesh_prio)
+    cs = torch.cuda.Stream(device=dev, priority=compute_prio) if compute_prio is not None else torch.cuda.current_stream()
+    with torch.cuda.stream(cs):
+        for _ in range(4):
+            VphoHotPath.join(hp.predict(res, prior_hand=ph, prior_obj=po, defer_join=defer))
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        t0.record()
+        last = None
+        for _ in range(K):
+            last = None
+            last = hp.predict(res, prior_hand=ph, prior_obj=po, defer_join=defer)
+        VphoHotPath.join(last)
+        t1.record()
+        torch.cuda.synchronize()
+        w = time.perf_counter() - w0
+    print("%-46s %.4f ms/step (device)  %.4f ms/step (wall)" % (name, t0.elapsed_time(t1) / K, w * 1e3 / K), flush=True)
+
+
+run("joined", False)
+run("pipelined, default stream, agg -1, mesh 0", True)
+run("pipelined, compute -2, agg -1, mesh 0", True, -2, -1, 0)
+run("pipelined, compute -2, agg 0, mesh 0", True, -2, 0, 0)
+run("pipelined, compute -3, agg -2, mesh -1", True, -3, -2, -1)
+run("pipelined, default stream, agg 0, mesh 0", True, None, 0, 0)
+run("joined again", False)

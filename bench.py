@@ -243,6 +243,10 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = capi.lib()       # raises when the CUDA library is missing: there is no fallback
+    if args.pipeline:
+        # the pipelined loop runs on a high-priority stream: the library then places the previous batch's aggregation and the
+        # output-only work one and two priority levels below it (VphoHotPath._priorities)
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-2))
     mano, anchors, objects, batch, prior_h, prior_o, st_h, st_o = make_inputs(bs, seed=rank)
     hp = VphoHotPath(mano, anchors, objects, st_h, st_o, sample_num=S, sampling_steps=STEPS_ODE, sample_T0=T0,
                      topk_hand=K_HAND, topk_obj=K_OBJ)
@@ -261,23 +265,23 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     def step_resident():
         return hp.predict(resident, prior_hand=resident["prior_hand"], prior_obj=resident["prior_obj"])
 
-    def step_pipelined():
-        # consecutive batches software-pipelined: predict returns once the samplers are done; this batch's aggregation and
-        # output-only work keep running on the library's streams under the next batch's samplers
-        return hp.predict(resident, prior_hand=resident["prior_hand"], prior_obj=resident["prior_obj"], defer_join=True)
+    def begin_resident():
+        # consecutive batches software-pipelined: batch i+1 is enqueued before the host waits for batch i's samplers; batch
+        # i's aggregation and output-only work run on the library's streams under batch i+1's samplers
+        return hp.predict_begin(resident, prior_hand=resident["prior_hand"], prior_obj=resident["prior_obj"], defer_join=True)
 
     # e2e: inputs live in pinned host memory; every step issues one full H2D copy (the NEXT step's inputs, on a copy
-    # stream, double-buffered -- what a prefetching eval loop does), computes the evaluation record on the device and
-    # reads the record and the aggregated poses back.
+    # stream, into one of three device sets -- what a prefetching eval loop does), computes the evaluation record on the
+    # device and reads the record and the aggregated poses back.
     copy_stream = torch.cuda.Stream(device=dev)
     eval_stream = torch.cuda.Stream(device=dev)          # the metric step of batch i runs beside the samplers of batch i+1
-    dev_sets = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()} for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]     # by the compute stream(s), by the eval stream
-    for pair in consumed:
-        for e in pair:
-            e.record()
-    e2e_state = {"i": 0, "record": None, "read": [None, None]}
+    n_sets = 3                                           # batch i computing, batch i+1 enqueued, batch i+2 being copied
+    dev_sets = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()} for _ in range(n_sets)]
+    ready = [torch.cuda.Event() for _ in range(n_sets)]
+    cur_ev = [torch.cuda.Event() for _ in range(n_sets)]
+    eval_ev = [torch.cuda.Event() for _ in range(n_sets)]
+    consumed = [[] for _ in range(n_sets)]               # events after which a device set may be overwritten
+    e2e_state = {"i": 0, "record": None, "read": None}
 
     def prefetch(slot):
         with torch.cuda.stream(copy_stream):
@@ -287,8 +291,8 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
                 dev_sets[slot][k].copy_(v, non_blocking=True)
             ready[slot].record(copy_stream)
 
-    def step_e2e():
-        slot = e2e_state["i"] & 1
+    def begin_e2e():
+        slot = e2e_state["i"] % n_sets
         e2e_state["i"] += 1
         cur = torch.cuda.current_stream()
         cur.wait_event(ready[slot])
@@ -299,18 +303,18 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
             # record and the aggregated poses, stream-ordered behind the aggregation; then, once per step, the next step's
             # H2D copies on the copy stream
             used = [pd_[k] for k in out_keys] + [pd_["diff_final_hand_joint"], pd_["diff_final_hand_vert"], pd_["diff_final_obj_6d"]]
-            if args.record_stream == "main" and not args.pipeline:
+            on_main = args.record_stream == "main" and not args.pipeline
+            if on_main:
                 rec = recorder(pd_, d)               # behind the aggregation on the compute stream
                 used = [pd_[k] for k in out_keys] + [rec]
-            done = torch.cuda.Event()
-            done.record(cur)
+            cur_ev[slot].record(cur)
             with torch.cuda.stream(eval_stream):
-                eval_stream.wait_event(done)
+                eval_stream.wait_event(cur_ev[slot])
                 for ev, _ in pd_.get("_done", ()):          # pipelined: the aggregation is not joined into `cur`
                     eval_stream.wait_event(ev)
                 for t in used:
                     t.record_stream(eval_stream)
-                if args.record_stream != "main" or args.pipeline:
+                if not on_main:
                     rec = recorder(pd_, d)
                 e2e_state["record"] = rec
                 outs = dict({k: pd_[k] for k in out_keys}, eval_record=rec)
@@ -318,23 +322,29 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
                     if k not in host_out:
                         host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
                     host_out[k].copy_(t, non_blocking=True)
-                consumed[slot][1] = torch.cuda.Event()
-                consumed[slot][1].record(eval_stream)
+                eval_ev[slot].record(eval_stream)
+            # every reader of this device set has been enqueued by now (a continued integration re-issues and lands here again)
+            consumed[slot] = [cur_ev[slot], eval_ev[slot]] + [ev for ev, _ in pd_.get("_done", ())]
             if issue == 0:
-                prefetch(slot ^ 1)
+                prefetch((slot + 1) % n_sets)
 
-        pd = hp.predict(d, prior_hand=d["prior_hand"], prior_obj=d["prior_obj"], prefetch=enqueued, defer_join=bool(args.pipeline))
-        consumed[slot][0] = torch.cuda.Event()
-        consumed[slot][0].record(cur)
+        t = hp.predict_begin(d, prior_hand=d["prior_hand"], prior_obj=d["prior_obj"], prefetch=enqueued, defer_join=bool(args.pipeline))
+        t["_slot"] = slot
+        return t
+
+    def end_e2e(t):
+        pd = hp.predict_end(t)
         if args.pipeline:
             # the host consumes the PREVIOUS batch's record while this batch's aggregation still runs
-            prev = e2e_state["read"][slot ^ 1]
-            if prev is not None:
-                prev.synchronize()
-            e2e_state["read"][slot] = consumed[slot][1]
+            if e2e_state["read"] is not None:
+                e2e_state["read"].synchronize()
+            e2e_state["read"] = eval_ev[t["_slot"]]
         else:
-            cur.synchronize()
+            torch.cuda.current_stream().synchronize()
         return pd
+
+    def step_e2e():
+        return end_e2e(begin_e2e())
 
     def barrier():
         if world > 1:
@@ -342,9 +352,10 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
 
     windows = []
+    per_step = []          # of the most recent timed() pass: time between consecutive step starts on the compute stream
 
-    def timed(step_fn, steps, profile=0, gather=False):
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def timed(step_fn, steps, profile=0, gather=False, begin_fn=None, end_fn=None):
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]      # created outside the timed region
         barrier()
         l0 = lib.c.vpho_launch_count()
         if profile:
@@ -352,10 +363,22 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         wall0 = time.perf_counter()
         windows.append([wall0, wall0])
         last = None
-        t0.record()
-        for i in range(steps):
-            last = None              # release the previous step's outputs first: same footprint as the warm-up steps
-            last = step_fn()
+        if begin_fn is None:
+            for i in range(steps):
+                marks[i].record()
+                last = None              # release the previous step's outputs first: same footprint as the warm-up steps
+                last = step_fn()
+        else:
+            ticket = None
+            for i in range(steps):       # batch i enqueued before the host waits for batch i-1
+                marks[i].record()
+                nxt = begin_fn()
+                if ticket is not None:
+                    last = None
+                    last = end_fn(ticket)
+                ticket = nxt
+            last = None
+            last = end_fn(ticket)
         VphoHotPath.join(last)       # pipelined steps: the compute stream waits for the last batch's aggregation / meshes
         if gather:
             torch.cuda.current_stream().wait_stream(eval_stream)
@@ -365,14 +388,16 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
             rec = e2e_state["record"] if e2e_state["record"] is not None else recorder(last, resident)
             gathered = gather_records(rec, bs * world)
             assert gathered.shape == (bs * world, recorder.width)
-        t1.record()
+        marks[steps].record()
         barrier()
         wall = time.perf_counter() - wall0
         windows[-1][1] = wall0 + wall
         if profile:
             lib.c.vpho_profile_enable(0)
         launches = lib.c.vpho_launch_count() - l0
-        ms = t0.elapsed_time(t1)
+        ms = marks[0].elapsed_time(marks[steps])
+        per_step.clear()
+        per_step.extend(round(marks[i].elapsed_time(marks[i + 1]), 4) for i in range(steps))
         t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -395,7 +420,13 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     for _ in range(max(args.warmup, 3)):
         step_resident()
     # 1) the timed region (`value`): K steps, no library instrumentation at all
-    ms_res, wall_res, launches = timed(step_pipelined if args.pipeline else step_resident, args.steps)
+    if args.pipeline:
+        for _ in range(2):
+            hp.predict_end(begin_resident())          # both workspace slots warm
+        ms_res, wall_res, launches = timed(None, args.steps, begin_fn=begin_resident, end_fn=hp.predict_end)
+    else:
+        ms_res, wall_res, launches = timed(step_resident, args.steps)
+    per_step_value = list(per_step)
     ms_latency = timed(step_resident, args.steps)[0] if args.pipeline else ms_res
     # 2) the same K steps with the dominant kernel (tag 0, head GEMM) bracketed by CUDA events on its launching stream ->
     #    roofline (median launch duration: a single driver hiccup must not move it)
@@ -425,7 +456,10 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     prefetch(0)
     for _ in range(2):
         step_e2e()
-    ms_e2e, wall_e2e, _ = timed(step_e2e, args.steps, gather=True)
+    if args.pipeline:
+        ms_e2e, wall_e2e, _ = timed(None, args.steps, gather=True, begin_fn=begin_e2e, end_fn=end_e2e)
+    else:
+        ms_e2e, wall_e2e, _ = timed(step_e2e, args.steps, gather=True)
     # stand-alone H2D time of one input set (not overlapped), for reference
     hs, he = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -544,10 +578,12 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         "sampler": {"hand_net_calls": net_calls, "obj_net_calls": info["obj"]["net_calls"],
                     "hand_attempts": info["hand"]["attempts"], "rejected": info["hand"]["rejected"] + info["obj"]["rejected"]},
         "wall_ms_per_step": round(wall_res / args.steps, 4),
+        "per_step_ms": per_step_value,
         "pipelining": {"enabled": bool(args.pipeline), "latency_ms_per_batch": round(ms_latency / args.steps, 4),
-                       "note": "value / ms_per_step: K batches issued back to back, batch i's aggregation + output-only work on "
-                               "the library's streams under batch i+1's samplers (predict(defer_join=True)); every batch's work, "
-                               "the last one's aggregation included, completes inside the timed region.  latency_ms_per_batch: "
+                       "note": "value / ms_per_step: K batches software-pipelined (predict_begin / predict_end): batch i+1 is "
+                               "enqueued before the host waits for batch i's samplers, batch i's aggregation + output-only work "
+                               "run on the library's lower-priority streams under batch i+1's samplers; every batch's work, the "
+                               "last one's aggregation included, completes inside the timed region.  latency_ms_per_batch: "
                                "the same K batches with each one joined before the next starts (round-1 definition of the step)"
                                if args.pipeline else "each batch joined before the next starts"},
     }

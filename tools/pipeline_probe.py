@@ -42,7 +42,37 @@ def run(name, defer, compute_prio=None, agg_prio=-1, mesh_prio=0):
     print("%-46s %.4f ms/step (device)  %.4f ms/step (wall)" % (name, t0.elapsed_time(t1) / K, w * 1e3 / K), flush=True)
 
 
+def run_ahead(name, compute_prio=None):
+    hp = VphoHotPath(mano, anchors, objects, st_h, st_o, sample_num=bench.S, sampling_steps=bench.STEPS_ODE, sample_T0=bench.T0,
+                     topk_hand=bench.K_HAND, topk_obj=bench.K_OBJ)
+    cs = torch.cuda.Stream(device=dev, priority=compute_prio) if compute_prio is not None else torch.cuda.current_stream()
+    with torch.cuda.stream(cs):
+        for _ in range(4):
+            VphoHotPath.join(hp.predict(res, prior_hand=ph, prior_obj=po, defer_join=True))
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        t0.record()
+        last = tk = None
+        for _ in range(K):
+            nt = hp.predict_begin(res, prior_hand=ph, prior_obj=po, defer_join=True)
+            if tk is not None:
+                last = None
+                last = hp.predict_end(tk)
+            tk = nt
+        last = None
+        last = hp.predict_end(tk)
+        VphoHotPath.join(last)
+        t1.record()
+        torch.cuda.synchronize()
+        w = time.perf_counter() - w0
+    print("%-46s %.4f ms/step (device)  %.4f ms/step (wall)" % (name, t0.elapsed_time(t1) / K, w * 1e3 / K), flush=True)
+
+
 run("joined", False)
+run_ahead("one-ahead, compute -2 (agg -1, mesh 0)", -2)
+run_ahead("one-ahead, default stream (agg -1, mesh 0)")
+run_ahead("one-ahead, compute -3 (agg -2, mesh -1)", -3)
 run("pipelined, default stream, agg -1, mesh 0", True)
 run("pipelined, compute -2, agg -1, mesh 0", True, -2, -1, 0)
 run("pipelined, compute -2, agg 0, mesh 0", True, -2, 0, 0)

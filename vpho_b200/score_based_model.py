@@ -54,7 +54,7 @@ class Denoiser:
                                                          self.STRICT_FP32 if strict_fp32 else 0, C.byref(h)),
                        "vpho_denoiser_create_ex")
         self.handle = h
-        self._ws: Dict[tuple, torch.Tensor] = {}
+        self._ws: Dict[int, tuple] = {}
         self.calls = 0   # network evaluations issued by the last sample() (nfev + 1)
 
     def __del__(self):
@@ -65,14 +65,16 @@ class Denoiser:
         except Exception:
             pass
 
-    def workspace(self, n_rows: int, rows_per_feat: int, n_eval: int, device) -> torch.Tensor:
+    def workspace(self, n_rows: int, rows_per_feat: int, n_eval: int, device, slot: int = 0) -> torch.Tensor:
+        """One cached workspace per `slot` (a pipelined loop alternates two: the previous batch's integration may still
+        have to be continued on its own workspace after the next batch's has been enqueued)."""
         key = (n_rows, rows_per_feat, n_eval, str(device))
-        ws = self._ws.get(key)
-        if ws is None:
+        held = self._ws.get(slot)
+        if held is None or held[0] != key:
             nbytes = self.lib.c.vpho_sample_workspace_bytes(self.n_heads, n_rows, rows_per_feat, n_eval)
-            ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-            self._ws = {key: ws}   # keep one
-        return ws
+            held = (key, torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device))
+            self._ws[slot] = held   # keep one per slot
+        return held[1]
 
     def __call__(self, data: dict) -> torch.Tensor:
         """`BaseDenoiser.forward` for the sampling call pattern: every row shares one time value."""
@@ -224,7 +226,7 @@ class ScoreBasedModelAgent:
     @torch.no_grad()
     def sample_pair(self, data_a: dict, denoiser_a: Denoiser, data_b: dict, denoiser_b: Denoiser, T0: float,
                     return_inprocess: bool = True, prior_a: Optional[torch.Tensor] = None,
-                    prior_b: Optional[torch.Tensor] = None, inprocess_float32=(False, False)):
+                    prior_b: Optional[torch.Tensor] = None, inprocess_float32=(False, False), ws_slot: int = 0):
         """The two `sample()` calls of `vpho_net.forward(mode='predict')` (hand, then object: VPHO.py:239-262) advanced in
         lock-step through shared kernel launches (`vpho_sample_pair_*`).  Priors are drawn in the reference's order
         (a, then b).  Always deferred: -> ((xs_a, x_a, pending_a), (xs_b, x_b, pending_b)); results are bit-identical
@@ -242,7 +244,7 @@ class ScoreBasedModelAgent:
             d2.setdefault("sample_num", self.sample_num)
             feat, rpf = _unique_feat(d2, n_rows)
             n_eval = self.sampling_steps
-            ws = den.workspace(n_rows, rpf, n_eval, device)
+            ws = den.workspace(n_rows, rpf, n_eval, device, ws_slot)
             xs = (torch.empty((n_eval, n_rows, D), dtype=torch.float32 if f32 else torch.float64, device=device)
                   if return_inprocess else None)
             # zeros, not empty: the final predictor step writes `x` only once the integration has reached t = eps, and

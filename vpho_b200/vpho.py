@@ -39,6 +39,9 @@ class VphoHotPath:
         self._side_stream2 = None
         self._agg_stream = None
         self._status_host = None
+        self._ws_slot = 0
+        self._events: list = []          # ring of reusable CUDA events (creating one per batch costs a driver call each)
+        self._event_i = 0
         # True: everything on the caller's stream (no output-only side stream, no high-priority aggregation stream);
         # bench.py's serialised per-kernel pass uses it together with vpho_set_pdl(0).  Results are identical.
         self.serialize = False
@@ -83,7 +86,19 @@ class VphoHotPath:
         output-only work, which run on the library's own streams; `predict` returns as soon as both samplers have
         finished, so the next batch's samplers (tensor-core bound, one CTA per SM) start while this batch's aggregation
         (a chain of small latency-bound kernels) fills the idle SM time between them.  `pd["_done"]` holds the events
-        that complete the outputs; call `VphoHotPath.join(pd)` before reading them on another stream."""
+        that complete the outputs; call `VphoHotPath.join(pd)` before reading them on another stream.
+
+        `predict_begin` / `predict_end` split the call at its one host synchronisation, so that a loop can enqueue batch
+        i+1 before it waits for batch i's status (no idle gap on the GPU between two batches' samplers)."""
+        return self.predict_end(self.predict_begin(batch, prior_hand=prior_hand, prior_obj=prior_obj, with_inprocess=with_inprocess,
+                                                   prefetch=prefetch, defer_join=defer_join))
+
+    @torch.no_grad()
+    def predict_begin(self, batch: Dict, *, prior_hand: Optional[torch.Tensor] = None, prior_obj: Optional[torch.Tensor] = None,
+                      with_inprocess: bool = True, prefetch=None, defer_join: bool = True) -> Dict:
+        """Enqueue one batch (samplers, speculative downstream work, the caller's `prefetch` hook); no host wait.  At most
+        TWO batches may be in flight (begin, begin, end, begin, end, ...): the sampler workspaces alternate between two
+        slots.  -> ticket for `predict_end`."""
         if prior_hand is None or prior_obj is None:
             # draw both priors up front, in the reference's order (hand, then object)
             from .score_based_model import ve_prior_std
@@ -96,45 +111,65 @@ class VphoHotPath:
         S = self.sample_num
         enc_h, enc_o = batch["encoding_hand"], batch["encoding_obj"]
         bs = enc_h.shape[0]
+        self._ws_slot ^= 1
         # The hand and the object integrations issue the same sequence of network calls: they advance in lock-step
         # through shared kernel launches (`sample_pair`), the object's work items filling the SMs the hand's leave idle.
         samples = self.score_agent.sample_pair(
             {"feat_unique": enc_h, "n_rows": bs * S}, self.denoiser_hand, {"feat_unique": enc_o, "n_rows": bs * S},
             self.denoiser_obj, self.sample_T0, return_inprocess=with_inprocess, prior_a=prior_hand, prior_b=prior_obj,
-            inprocess_float32=(True, False))      # the hand trajectory is only ever used as float32 (VPHO.py:243)
-        pend = (samples[0][2], samples[1][2])
-        issue = 0
+            inprocess_float32=(True, False),      # the hand trajectory is only ever used as float32 (VPHO.py:243)
+            ws_slot=self._ws_slot)
+        t = {"batch": batch, "samples": samples, "pend": (samples[0][2], samples[1][2]), "issue": 0,
+             "with_inprocess": with_inprocess, "prefetch": prefetch, "defer_join": defer_join, "slot": self._ws_slot}
+        self._issue(t)
+        return t
+
+    def _issue(self, t: Dict) -> None:
+        t["status"] = self._snapshot(t["pend"], t["slot"])     # stream-ordered behind the samplers only: the host wakes when THEY finish
+        t["pd"] = self._downstream(t["batch"], t["samples"], t["with_inprocess"], t["defer_join"])   # speculative on the first pass
+        if t["prefetch"] is not None:
+            # caller hook `prefetch(pd, issue)`, run after the batch is enqueued and before the host blocks on its
+            # status: the place to enqueue device-to-host reads of `pd` (stream-ordered behind the aggregation) and, for
+            # issue == 0, the next batch's host-to-device copies on another stream.
+            # When the samplers had to be continued (issue > 0, rare) it is called again with the new outputs.
+            t["prefetch"](t["pd"], t["issue"])
+        t["issue"] += 1
+
+    @torch.no_grad()
+    def predict_end(self, t: Dict) -> Dict:
+        """The one host synchronisation of the batch (its samplers' status words); -> `pd`."""
+        pend = t["pend"]
         while True:
-            status = self._snapshot(pend)          # stream-ordered behind the samplers only: the host wakes when THEY finish
-            pd = self._downstream(batch, samples, with_inprocess, defer_join)      # speculative on the first pass
-            if prefetch is not None:
-                # caller hook `prefetch(pd, issue)`, run after the batch is enqueued and before the host blocks on its
-                # status: the place to enqueue device-to-host reads of `pd` (stream-ordered behind the aggregation) and, for
-                # issue == 0, the next batch's host-to-device copies on another stream.
-                # When the samplers had to be continued (issue > 0, rare) it is called again with the new outputs.
-                prefetch(pd, issue)
-            issue += 1
-            done = self._await(pend, status)                           # the one host sync of the batch
+            done = self._await(pend, t["status"])
             if done:
-                return pd
+                return t["pd"]
             # slow path: keep stepping both integrations until they finish, then redo the downstream work once
-            stream = capi.stream_of(samples[0][1])
+            stream = capi.stream_of(t["samples"][0][1])
             while not done:
                 pend[0].pair.advance(4, stream)
-                done = self._await(pend, self._snapshot(pend))
+                done = self._await(pend, self._snapshot(pend, t["slot"]))
+            self._issue(t)
 
-    def _snapshot(self, pend):
-        """Enqueue the read of both controllers' counters (pinned host buffer + event on the current stream)."""
+    def _event(self):
+        """Next event of a ring of 32.  Re-recording an event a stale `pd` still refers to only makes a late join wait for
+        later work of the same stream, which is still correct."""
+        if len(self._events) < 32:
+            self._events.append(torch.cuda.Event())
+            return self._events[-1]
+        self._event_i = (self._event_i + 1) % 32
+        return self._events[self._event_i]
+
+    def _snapshot(self, pend, slot: int = 0):
+        """Enqueue the read of both controllers' counters (pinned host buffer of this batch's slot + event on the current
+        stream)."""
         dev_c = torch.stack([p.counters for p in pend])
         if not dev_c.is_cuda:
             return dev_c, None
         if self._status_host is None:
             self._status_host = [torch.empty((2, 8), dtype=torch.int32).pin_memory() for _ in range(2)]
-            self._status_i = 0
-        self._status_i ^= 1
-        host = self._status_host[self._status_i]
+        host = self._status_host[slot & 1]
         host.copy_(dev_c, non_blocking=True)
-        ev = torch.cuda.Event()
+        ev = self._event()
         ev.record(torch.cuda.current_stream(dev_c.device))
         return host, ev
 
@@ -145,6 +180,18 @@ class VphoHotPath:
         ok = [p.resolve(c) for p, c in zip(pend, host.tolist())]
         self.last_info = {"hand": pend[0].info, "obj": pend[1].info}
         return all(ok)
+
+    @staticmethod
+    def _priorities(main):
+        """(aggregation stream, output-only stream) priorities.  Caller on a default-priority stream: the aggregation chain
+        goes ahead of the pending candidate-mesh CTAs (-1, 0).  Caller on a high-priority stream (what a pipelined loop
+        should use: the samplers are the long pole, the previous batch's aggregation has a whole sampler phase of slack):
+        one and two levels below the caller.  Measured on a B200, 64 x 100 x 50 (tools/pipeline_probe.py): pipelined
+        2.85 ms/batch with the caller at -2, 3.04 at 0; joined 3.08-3.23."""
+        p = int(getattr(main, "priority", 0) or 0)
+        if p >= 0:
+            return -1, 0
+        return min(0, p + 1), min(0, p + 2)
 
     @staticmethod
     def join(pd: Dict, stream=None) -> Dict:
@@ -186,7 +233,7 @@ class VphoHotPath:
         side2 = None
         if main is not None and not self.serialize:
             if self._side_stream2 is None:
-                self._side_stream2 = torch.cuda.Stream(device=enc_h.device)
+                self._side_stream2 = torch.cuda.Stream(device=enc_h.device, priority=self._priorities(main)[1])
             side2 = self._side_stream2
             side2.wait_stream(main)
             for t in (xs_h, x_h, final_mano):
@@ -220,7 +267,7 @@ class VphoHotPath:
         # placed ahead of the pending mesh CTAs whenever SM slots free up.
         if side2 is not None:
             if self._agg_stream is None:
-                self._agg_stream = torch.cuda.Stream(device=enc_h.device, priority=-1)
+                self._agg_stream = torch.cuda.Stream(device=enc_h.device, priority=self._priorities(main)[0])
             hs = self._agg_stream
             hs.wait_stream(main)
             if defer_join:
@@ -245,7 +292,7 @@ class VphoHotPath:
             if defer_join:
                 pd["_done"] = []
                 for st in (hs, side2):
-                    ev = torch.cuda.Event()
+                    ev = self._event()
                     ev.record(st)
                     pd["_done"].append((ev, enc_h.device))
             else:

@@ -12,6 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "vpho_b200", "csrc")
 LIB = os.path.join(CSRC, "libvpho_b200.so")
+LIB_BOUNDS = os.path.join(CSRC, "libvpho_b200_bounds.so")      # -DVPHO_DEBUG_BOUNDS twin, used by tests/test_bounds_build.py only
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -20,22 +21,26 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB):
+def _stale(lib: str = LIB) -> bool:
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ for sm_100a into one shared library (object per file, parallel)."""
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, bounds: bool = False) -> str:
+    """Compile every .cu under csrc/ for sm_100a into one shared library (object per file, parallel).
+    bounds=True: the index-asserting twin (VPHO_BOUNDS in vpho_common.cuh) -> libvpho_b200_bounds.so."""
+    LIB = LIB_BOUNDS if bounds else globals()["LIB"]
+    if not force and not _stale(LIB):
         return LIB
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.path.join(CSRC, "build_bounds" if bounds else "build")
     os.makedirs(objdir, exist_ok=True)
     flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
              "-I", os.path.join(ROOT, "include"), "-I", CSRC] + ARCH
+    if bounds:
+        flags += ["-DVPHO_DEBUG_BOUNDS"]
     if verbose:
         flags += ["-Xptxas", "-v"]
     if os.environ.get("VPHO_TC_TIMELINE"):
@@ -64,4 +69,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, bounds="--bounds" in sys.argv))

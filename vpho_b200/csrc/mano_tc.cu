@@ -102,6 +102,7 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
     const bool valid = c0 + c < n;
     float R[9], beta[10];
     if (valid) {
+      VPHO_BOUNDS(c0 + c < n && 3 * j + 2 < 48);
       const float* pp = pose + (size_t)(c0 + c) * pose_stride + 3 * j;
       const float a[3] = {pp[0], pp[1], pp[2]};
       manopth_rodrigues(a, R);
@@ -154,6 +155,7 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
         sm.A[c][j][r * 4 + 3] = G[r * 4 + 3] - gj;
       }
       if (store_j) {
+        VPHO_BOUNDS(c0 + c < n && joint16_to_21(j) < 21);
         float* o = joints + ((size_t)(c0 + c) * 21 + joint16_to_21(j)) * 3;
 #pragma unroll
         for (int d = 0; d < 3; ++d) o[d] = mano_center_scale(G[d * 4 + 3], G0[d * 4 + 3]);
@@ -356,6 +358,7 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
           if (debug_blend) { o[0] = vp[0]; o[1] = vp[1]; o[2] = vp[2]; }      // VPHO_MANO_DEBUG_BLEND: the blended rest pose
           ob[lane * 3 + 0] = o[0]; ob[lane * 3 + 1] = o[1]; ob[lane * 3 + 2] = o[2];
           if (tip >= 0) {
+            VPHO_BOUNDS(c0 + c < n && tip_to_21(tip) < 21);
             float* dst = joints + ((size_t)(c0 + c) * 21 + tip_to_21(tip)) * 3;
             dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
           }
@@ -363,6 +366,7 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
           // 32 vertices x 3 floats of one candidate are contiguous in global memory: 8-byte stores
           float* gdst = verts + ((size_t)(c0 + c) * kVerts + v0) * 3;
           const int nf = nv * 3;
+          VPHO_BOUNDS(c0 + c < n && v0 >= 0 && v0 + nv <= kVerts && nf <= 96);
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             const int i2 = lane + 32 * h2;

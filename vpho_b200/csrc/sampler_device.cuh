@@ -103,6 +103,7 @@ __device__ __forceinline__ void emit_score(const SamplerWs& ws, RkCtrl& c, const
     return;
   }
   const int slot = k_slot_of(mode, s);
+  VPHO_BOUNDS(slot >= 0 && slot < 7 && i >= 0 && i < c.n);
   if (isnan(score)) { c.nan_stage[slot] = 1; c.nan_seen = 1; }
   ws.K[(size_t)slot * c.n + i] = score;          // read back through kval with kcoef[slot] = et.coef of this call
 }

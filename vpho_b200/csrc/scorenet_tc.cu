@@ -254,6 +254,7 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         int tile, head, img0, n_img;
         item_geometry(it, tile, head, img0, n_img);
         const int col = head * kHeadHid + tg;
+        VPHO_BOUNDS(col < dn.hid && head < dn.n_heads && (n_img > kTcFtImgs || n_img == 0 || img0 + n_img <= ws.R));
         k.tt = ws.Tt[(size_t)tt_slot(mode, s) * dn.hid + col];
         k.wb = __ldg(reinterpret_cast<const float4*>(dn.Wb + (size_t)col * 4));
 #pragma unroll
@@ -279,6 +280,7 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         const bool valid = row < n_rows;
         const int cbase = half * 128;
         const int img_l = valid ? row / rpf - img0 : 0;
+        VPHO_BOUNDS(!valid || row / rpf < ws.R);
         const float* Frow = ws.F + (size_t)(valid ? row / rpf : 0) * dn.hid + hc0 + cbase;
         // exact power-of-two un-scaling of the FP16 operand planes; loaded before the waits
         const float unscale = (row < ws.Npad ? ws.P2scale[row] : 1.f) * dn.Wscale_inv[head];
@@ -368,6 +370,7 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             const float out = o[d] + dn.bb[head * 3 + d];
+            VPHO_BOUNDS(head * 3 + d < dn.D && row * dn.D + head * 3 + d < n_rows * dn.D);
             emit_score(ws, c, et, mode, s, row * dn.D + head * 3 + d, __fdiv_rn(out, et.std32));
           }
         }
@@ -552,7 +555,10 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
         const int rr = u / upr, kq = u - rr * upr;
         float x4[4] = {0.f, 0.f, 0.f, 0.f}, hi4[4], lo4[4];
         if (vec) {
-          if (r0 + rr < n_rows && 4 * kq < D) stage_input4(ws, q4, mode, s, (r0 + rr) * D + 4 * kq, n_state, x4);
+          if (r0 + rr < n_rows && 4 * kq < D) {
+            VPHO_BOUNDS((r0 + rr) * D + 4 * kq + 3 < n_state);
+            stage_input4(ws, q4, mode, s, (r0 + rr) * D + 4 * kq, n_state, x4);
+          }
         } else {
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
@@ -689,6 +695,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
         sc = ldexpf(1.f, 14 - ex);
         inv = ldexpf(1.f, ex - 14);
       }
+      VPHO_BOUNDS(r0 + kTcBM <= ws.Npad);
       if (cs == 0) ws.P2scale[r0 + r] = inv;
       // The tile is a contiguous 64 KB block per plane in global memory.  Lanes own rows, so direct stores would touch 32
       // different lines per instruction (partial sectors): stage through shared memory (rows padded to 528 bytes:
@@ -715,6 +722,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
 #pragma unroll 4
       for (int i = tc; i < 2 * kTcBM * 32; i += 512) {
         const int plane = i >> 12, j = i & 4095, row = j >> 5, unit = j & 31;
+        VPHO_BOUNDS(plane < 2 && r0 + row < ws.Npad && unit * 16 + 16 <= kPDim * 2);
         const uint4 val = *reinterpret_cast<const uint4*>(ot + plane * kPlane + row * kRowPad + unit * 16);
         *reinterpret_cast<uint4*>((plane ? glo : ghi) + (size_t)row * 512 + unit * 16) = val;
       }

@@ -275,7 +275,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     # device and reads the record and the aggregated poses back.
     copy_stream = torch.cuda.Stream(device=dev)
     eval_stream = torch.cuda.Stream(device=dev)          # the metric step of batch i runs beside the samplers of batch i+1
-    n_sets = 3                                           # batch i computing, batch i+1 enqueued, batch i+2 being copied
+    n_sets = args.e2e_sets                               # batch i computing, batch i+1 enqueued, batch i+2 being copied
     dev_sets = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()} for _ in range(n_sets)]
     ready = [torch.cuda.Event() for _ in range(n_sets)]
     cur_ev = [torch.cuda.Event() for _ in range(n_sets)]
@@ -287,8 +287,9 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         with torch.cuda.stream(copy_stream):
             for e in consumed[slot]:
                 copy_stream.wait_event(e)
-            for k, v in host.items():
-                dev_sets[slot][k].copy_(v, non_blocking=True)
+            if "h2d" not in args.e2e_skip:
+                for k, v in host.items():
+                    dev_sets[slot][k].copy_(v, non_blocking=True)
             ready[slot].record(copy_stream)
 
     def begin_e2e():
@@ -315,7 +316,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
                 for t in used:
                     t.record_stream(eval_stream)
                 if not on_main:
-                    rec = recorder(pd_, d)
+                    rec = recorder(pd_, d) if ("record" not in args.e2e_skip or e2e_state["record"] is None) else e2e_state["record"]
                 e2e_state["record"] = rec
                 outs = dict({k: pd_[k] for k in out_keys}, eval_record=rec)
                 for k, t in outs.items():
@@ -795,6 +796,8 @@ def main():
     ap.add_argument("--pipeline", type=int, default=1, choices=[0, 1],
                     help="1: consecutive batches software-pipelined (batch i's aggregation under batch i+1's samplers); 0: each "
                          "batch joined before the next starts")
+    ap.add_argument("--e2e-sets", type=int, default=3, help="device input sets of the e2e leg (>= 3 when pipelined)")
+    ap.add_argument("--e2e-skip", default="", help="DIAGNOSTIC ONLY (invalidates e2e): comma list of h2d,record to leave out")
     ap.add_argument("--record-stream", default="side", choices=["main", "side"],
                     help="e2e leg: stream the evaluation record is computed on (main = behind the aggregation; side = beside the "
                          "next batch's samplers)")

@@ -37,7 +37,9 @@ struct ObjMetricHost {
   ObjMetricDev dev;
   void* blob = nullptr;
   double* part = nullptr;      // [rows][kSplit][kPartCols] partial sums of the scans, grown on demand
+  unsigned* colpart = nullptr; // [rows][kSplit][Q] partial column minima of the one-pass scan
   size_t part_rows = 0;
+  int sym = -1;                // one-pass scan usable (Q unsigneds of dynamic shared memory fit): decided at first use
 };
 
 __device__ __forceinline__ double block_sum_d(double v, double* red) {
@@ -108,11 +110,85 @@ __device__ __forceinline__ void nearest_scan(const float* base, int n_pts, int o
   __syncthreads();
 }
 
+// Both directions of a nearest-point query in ONE pass over the pair distances: thread = point i of cloud A (rows
+// [own_lo, own_hi)), loop over all points j of cloud B.  Row minima stay in a register; the column minimum of j over the 32
+// rows of a warp is one `redux.sync.min` on the distance bits (non-negative floats order like unsigned integers) and lands
+// in `colmin[j]` (shared, unsigned) with one shared-memory atomic per warp.  Two j per instruction with packed FP32
+// (FADD2 / FMUL2 / FFMA2), as the contact scans of aggregate.cu.  colmin must hold +inf bits on entry.
+#ifndef VPHO_EMU
+__device__ __forceinline__ unsigned long long m_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+template <typename F>
+__device__ __forceinline__ void sym_scan(const float* base, int n_pts, int own_lo, int own_hi, const double* rtA, const double* rtB,
+                                         float4* tile, unsigned* colmin, F consume_row) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  float* tx = reinterpret_cast<float*>(tile);
+  float* ty = tx + kMT;
+  float* tz = ty + kMT;
+  for (int p0 = own_lo; p0 < own_hi; p0 += kMT) {
+    const int i = p0 + tid;
+    float a[3] = {1e18f, 1e18f, 1e18f};          // a row that does not exist: its distances can never be a minimum
+    if (i < own_hi) {
+      double ad[3];
+      pose_point_d(rtA, base + (size_t)i * 3, ad);
+      a[0] = (float)ad[0]; a[1] = (float)ad[1]; a[2] = (float)ad[2];
+    }
+    const unsigned long long A = m_pack(a[0], a[0]), B = m_pack(a[1], a[1]), C = m_pack(a[2], a[2]);
+    float best = INFINITY;
+    for (int q0 = 0; q0 < n_pts; q0 += kMT) {
+      __syncthreads();
+      {
+        float g[3] = {-1e18f, -1e18f, -1e18f};   // padding column
+        if (q0 + tid < n_pts) {
+          double gd[3];
+          pose_point_d(rtB, base + (size_t)(q0 + tid) * 3, gd);
+          g[0] = (float)gd[0]; g[1] = (float)gd[1]; g[2] = (float)gd[2];
+        }
+        tx[tid] = g[0]; ty[tid] = g[1]; tz[tid] = g[2];
+      }
+      __syncthreads();
+      const int cnt = min(kMT, n_pts - q0);
+#pragma unroll 4
+      for (int q = 0; q < cnt; q += 2) {
+        const unsigned long long X = *reinterpret_cast<const unsigned long long*>(tx + q);
+        const unsigned long long Y = *reinterpret_cast<const unsigned long long*>(ty + q);
+        const unsigned long long Z = *reinterpret_cast<const unsigned long long*>(tz + q);
+        unsigned long long dx, dy, dz, d;
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(A), "l"(X));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(B), "l"(Y));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(C), "l"(Z));
+        asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(d) : "l"(dy));
+        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(d) : "l"(dx), "l"(d));
+        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(d) : "l"(dz), "l"(d));
+        float d0, d1;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+        best = fminf(best, fminf(d0, d1));
+        const unsigned m0 = __reduce_min_sync(0xffffffffu, __float_as_uint(d0));
+        const unsigned m1 = __reduce_min_sync(0xffffffffu, __float_as_uint(d1));
+        if (lane < 2 && q + lane < cnt) atomicMin(&colmin[q0 + q + lane], lane ? m1 : m0);
+      }
+    }
+    if (i < own_hi) consume_row(i, sqrtf(best));
+  }
+  __syncthreads();
+}
+#endif
+
 // The O(P^2) part: ADD-S and the two directions of the F-score / Chamfer cloud, each CTA owning 1 / kSplit of the points.
 // Partial sums go to part[(b C + c) kSplit + split][kPartCols]; k_object_metrics adds them in split order (deterministic).
+// `colpart` [(b C + c) kSplit + split][Q] receives this CTA's partial column minima (squared distances) of the gt -> pd
+// direction when the one-pass scan is used (`sym` != 0: Q unsigneds of dynamic shared memory); k_object_metrics takes the
+// minimum over the splits.  Otherwise (clouds too large for shared memory, or the CPU emulator build) the gt -> pd
+// direction is a second scan and its sums go to part[2], part[9..14] as before.
 __global__ void __launch_bounds__(kMT) k_object_metrics_scan(AssetsDev as, ObjMetricDev mt, const double* __restrict__ pd_rt,
                                                              const double* __restrict__ gt_rt, const int* __restrict__ obj_id, int C,
-                                                             double* __restrict__ part) {
+                                                             double* __restrict__ part, unsigned* __restrict__ colpart, int sym) {
+#ifndef VPHO_EMU
+  extern __shared__ unsigned s_colmin[];
+#endif
   __shared__ double red[kMT];
   __shared__ float4 tile[kMT];
   __shared__ double s_pd[12], s_gt[12];
@@ -132,27 +208,42 @@ __global__ void __launch_bounds__(kMT) k_object_metrics_scan(AssetsDev as, ObjMe
     hi = min(n, lo + per);
   };
   int lo, hi;
-  range(P, lo, hi);
-  double adds = 0.0;
-  nearest_scan(base, P, lo, hi, s_pd, s_gt, tile, [&](int, float d) { adds += (double)d; });
-  const double adds_s = block_sum_d(adds, red);
   const float* fbase = mt.fverts ? mt.fverts + (size_t)o * mt.n_fpts * 3 : base;
   const int Q = mt.fverts ? mt.n_fpts : P;
+  const bool same_cloud = !mt.fverts;            // ADD-S is then the pd -> gt direction of the F-score scan: scanned once
+  double adds = 0.0;
+  if (!same_cloud) {
+    range(P, lo, hi);
+    nearest_scan(base, P, lo, hi, s_pd, s_gt, tile, [&](int, float d) { adds += (double)d; });
+  }
   range(Q, lo, hi);
   const float th[6] = {0.002f, 0.005f, 0.010f, 0.020f, 0.050f, 0.100f};
   double s_pg = 0.0, s_gp = 0.0;
   int hit_pg[6] = {0, 0, 0, 0, 0, 0}, hit_gp[6] = {0, 0, 0, 0, 0, 0};
-  nearest_scan(fbase, Q, lo, hi, s_pd, s_gt, tile, [&](int, float d) {
+  auto row_pg = [&](int, float d) {
     s_pg += (double)d;
 #pragma unroll
     for (int k = 0; k < 6; ++k) hit_pg[k] += d < th[k] ? 1 : 0;
-  });
-  nearest_scan(fbase, Q, lo, hi, s_gt, s_pd, tile, [&](int, float d) {
-    s_gp += (double)d;
+  };
+#ifndef VPHO_EMU
+  if (sym) {
+    for (int j = tid; j < Q; j += kMT) s_colmin[j] = 0x7f800000u;
+    __syncthreads();
+    sym_scan(fbase, Q, lo, hi, s_pd, s_gt, tile, s_colmin, row_pg);
+    unsigned* cp = colpart + (((size_t)b * C + c) * kSplit + split) * (size_t)Q;
+    for (int j = tid; j < Q; j += kMT) cp[j] = s_colmin[j];
+  } else
+#endif
+  {
+    nearest_scan(fbase, Q, lo, hi, s_pd, s_gt, tile, row_pg);
+    nearest_scan(fbase, Q, lo, hi, s_gt, s_pd, tile, [&](int, float d) {
+      s_gp += (double)d;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) hit_gp[k] += d < th[k] ? 1 : 0;
-  });
+      for (int k = 0; k < 6; ++k) hit_gp[k] += d < th[k] ? 1 : 0;
+    });
+  }
   const double t_pg = block_sum_d(s_pg, red), t_gp = block_sum_d(s_gp, red);
+  const double adds_s = same_cloud ? t_pg : block_sum_d(adds, red);
   if (tid == 0) { out[0] = adds_s; out[1] = t_pg; out[2] = t_gp; }
   for (int k = 0; k < 6; ++k) {
     const double np_ = block_sum_d((double)hit_pg[k], red), ng_ = block_sum_d((double)hit_gp[k], red);
@@ -163,7 +254,7 @@ __global__ void __launch_bounds__(kMT) k_object_metrics_scan(AssetsDev as, ObjMe
 __global__ void __launch_bounds__(kMT) k_object_metrics(AssetsDev as, ObjMetricDev mt, const double* __restrict__ pd_rt,
                                                         const double* __restrict__ gt_rt, const int* __restrict__ obj_id,
                                                         const float* __restrict__ cam_intr, int C, const double* __restrict__ part,
-                                                        double* __restrict__ out) {
+                                                        const unsigned* __restrict__ colpart, int sym, double* __restrict__ out) {
   __shared__ double red[kMT];
   __shared__ float redf[kMT];
   __shared__ double s_pd[12], s_gt[12], s_pdbox[8][3], s_gtbox[8][3];
@@ -269,6 +360,24 @@ __global__ void __launch_bounds__(kMT) k_object_metrics(AssetsDev as, ObjMetricD
     for (int sp = 0; sp < kSplit; ++sp) tot[k] += pp[sp * kPartCols + k];
   }
   const double adds_m = tot[0] / (double)P;
+  if (sym) {
+    // gt -> pd direction of the one-pass scan: minimum over the splits' partial column minima, then the same sums
+    const int Qn = mt.fverts ? mt.n_fpts : P;
+    const unsigned* cp = colpart + ((size_t)b * C + c) * kSplit * (size_t)Qn;
+    const float th[6] = {0.002f, 0.005f, 0.010f, 0.020f, 0.050f, 0.100f};
+    double s_gp = 0.0;
+    int hit[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = tid; j < Qn; j += kMT) {
+      unsigned m = cp[j];
+      for (int sp = 1; sp < kSplit; ++sp) m = min(m, cp[(size_t)sp * Qn + j]);
+      const float d = sqrtf(__uint_as_float(m));
+      s_gp += (double)d;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) hit[k] += d < th[k] ? 1 : 0;
+    }
+    tot[2] = block_sum_d(s_gp, red);
+    for (int k = 0; k < 6; ++k) tot[9 + k] = block_sum_d((double)hit[k], red);
+  }
   if (tid == 0) {
     // the 8 corners of compute_obj_metrics_dexycb: (x, y, z) picks min (0) or max (1) by these index rows
     const int cx[8] = {0, 1, 0, 0, 1, 0, 1, 1}, cy[8] = {0, 0, 1, 0, 1, 1, 0, 1}, cz[8] = {0, 0, 0, 1, 0, 1, 1, 1};
@@ -391,6 +500,7 @@ extern "C" int vpho_objmetrics_destroy(vpho_objmetrics_t h) {
   if (!h) return VPHO_ERR_INVALID;
   ObjMetricHost* mh = static_cast<ObjMetricHost*>(h);
   if (mh->part) cudaFree(mh->part);
+  if (mh->colpart) cudaFree(mh->colpart);
   cudaFree(mh->blob);
   delete mh;
   return VPHO_OK;
@@ -414,13 +524,27 @@ static int launch_object_metrics(const AssetsDev& as, ObjMetricHost* mh, const d
                                  const float* cam_intr, int n, int C, double* out, cudaStream_t st) {
   const ObjMetricDev& mt = mh->dev;
   const size_t rows = (size_t)n * C;
+  const int Q = mt.fverts ? mt.n_fpts : as.n_pts;
+#ifdef VPHO_EMU
+  mh->sym = 0;
+#else
+  if (mh->sym < 0) {
+    mh->sym = 0;
+    const size_t need = (size_t)Q * sizeof(unsigned);
+    if (need <= 160 * 1024 &&
+        (need <= 32 * 1024 || cudaFuncSetAttribute(k_object_metrics_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) == cudaSuccess))
+      mh->sym = 1;
+  }
+#endif
   if (rows > mh->part_rows) {
-    if (mh->part) { cudaDeviceSynchronize(); cudaFree(mh->part); mh->part = nullptr; mh->part_rows = 0; }
+    if (mh->part) { cudaDeviceSynchronize(); cudaFree(mh->part); cudaFree(mh->colpart); mh->part = nullptr; mh->colpart = nullptr; mh->part_rows = 0; }
     if (cudaMalloc((void**)&mh->part, rows * kSplit * kPartCols * sizeof(double)) != cudaSuccess) return VPHO_ERR_ALLOC;
+    if (mh->sym && cudaMalloc((void**)&mh->colpart, rows * kSplit * (size_t)Q * sizeof(unsigned)) != cudaSuccess) return VPHO_ERR_ALLOC;
     mh->part_rows = rows;
   }
-  VPHO_LAUNCH(k_object_metrics_scan, dim3(kSplit, C, n), dim3(kMT), 0, st, as, mt, pd_rt, gt_rt, obj_id, C, mh->part);
-  VPHO_LAUNCH(k_object_metrics, dim3(C, n), dim3(kMT), 0, st, as, mt, pd_rt, gt_rt, obj_id, cam_intr, C, mh->part, out);
+  const size_t dyn = mh->sym ? (size_t)Q * sizeof(unsigned) : 0;
+  VPHO_LAUNCH(k_object_metrics_scan, dim3(kSplit, C, n), dim3(kMT), dyn, st, as, mt, pd_rt, gt_rt, obj_id, C, mh->part, mh->colpart, mh->sym);
+  VPHO_LAUNCH(k_object_metrics, dim3(C, n), dim3(kMT), 0, st, as, mt, pd_rt, gt_rt, obj_id, cam_intr, C, mh->part, mh->colpart, mh->sym, out);
   VPHO_CHECK_LAUNCH();
   return VPHO_OK;
 }

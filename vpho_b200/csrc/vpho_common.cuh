@@ -3,18 +3,10 @@
 #pragma once
 #include <cstdlib>
 
-#ifndef VPHO_EMU
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdint.h>
-#include <stdio.h>
-#define VPHO_DYN_SMEM(type, name)                                 \
-  extern __shared__ __align__(16) unsigned char name##_raw_[];    \
-  type* name = reinterpret_cast<type*>(name##_raw_)
 // -DVPHO_DEBUG_BOUNDS build (libvpho_b200_bounds.so, `python -m vpho_b200.build --bounds`): every global-memory index the
 // tensor-core kernels form is asserted against its extent; a violation prints the site and traps (the launch then fails
 // with a sticky error, which the C ABI reports).  compute-sanitizer does not run these kernels (tcgen05), hence this build.
-#ifdef VPHO_DEBUG_BOUNDS
+#if defined(VPHO_DEBUG_BOUNDS) && !defined(VPHO_EMU)
 #include <cstdio>
 #define VPHO_BOUNDS(cond)                                                                                                   \
   do {                                                                                                                       \
@@ -28,6 +20,14 @@
 #define VPHO_BOUNDS(cond) do { } while (0)
 #endif
 
+#ifndef VPHO_EMU
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#define VPHO_DYN_SMEM(type, name)                                 \
+  extern __shared__ __align__(16) unsigned char name##_raw_[];    \
+  type* name = reinterpret_cast<type*>(name##_raw_)
 namespace vpho {
 extern unsigned long long g_launches;   // kernels launched by this library since load (vpho_launch_count)
 void profile_begin(int tag, cudaStream_t st);   // CUDA-event bracket around one launch when profiling is enabled

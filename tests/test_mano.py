@@ -76,3 +76,36 @@ def test_mano_cuda_large_angles_and_empty(assets, cuda_lib):
     _check(hm, om, 257, "cuda", seed=7, scale=2.5)
     v, j = hm.get_hand_verts(pose=torch.zeros(0, 48, device="cuda"), shape=torch.zeros(0, 10, device="cuda"))
     assert v.shape == (0, 778, 3) and j.shape == (0, 21, 3)
+
+
+def _dense_and_mixed_models():
+    """the default synthetic model has <= 4 influences per vertex (as SMPL-family models do); the kernels also carry a
+    dense 16-joint path: a fully dense weight matrix, and one where only a few vertices are dense (a warp whose vertices are
+    not all sparse takes the dense path, its neighbours the sparse one)"""
+    from vpho_b200 import synthetic as syn
+    dense = syn.make_mano_model(max_influences=None)
+    mixed = syn.make_mano_model()
+    mixed = dict(mixed, weights=mixed["weights"].copy())
+    for vid in (5, 100, 101, 640, 777):
+        mixed["weights"][vid] = dense["weights"][vid]
+    return {"dense": dense, "mixed": mixed}
+
+
+def test_mano_emulated_dense_weights(emu_lib):
+    for name, m in _dense_and_mixed_models().items():
+        assert (m["weights"] != 0).sum(1).max() == 16
+        _check(HeadMano(m, lib=emu_lib), O.OracleMano(m), 7, "cpu", seed=3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["dense", "mixed"])
+@pytest.mark.parametrize("n", [3, 200, 6400])
+def test_mano_cuda_dense_weights(cuda_lib, kind, n):
+    m = _dense_and_mixed_models()[kind]
+    hm = HeadMano(m)
+    _check(hm, O.OracleMano(m), n, "cuda", seed=n)
+    g = torch.Generator().manual_seed(n + 1)
+    p, s = (torch.randn(n, 48, generator=g) * 0.7).cuda(), torch.randn(n, 10, generator=g).cuda()
+    v1, j1 = hm.get_hand_verts(pose=p, shape=s)
+    v2, j2 = hm.get_hand_verts(pose=p, shape=s, strict_fp32=True)
+    assert (v1 - v2).abs().max().item() < 5e-7 and (j1 - j2).abs().max().item() < 5e-7

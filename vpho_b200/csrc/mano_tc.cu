@@ -27,7 +27,7 @@
 
 namespace vpho {
 
-constexpr int kMtNC = 64;                  // candidates per CTA = UMMA N
+constexpr int kMtNCMax = 64;               // candidates per CTA = UMMA N: 64 or 48 (template parameter NC, chosen per launch)
 constexpr int kMtK = 192;                  // 145 coefficients padded to 3 chunks of 64
 constexpr int kMtChunks = 3;
 constexpr int kMtVT = 7;                   // vertex tiles of 128 (896 padded slots)
@@ -36,8 +36,7 @@ constexpr int kMtThreads = 640;            // 4 role warps + 16 epilogue warps
 constexpr int kMtPlane = 128 * 128;        // one operand plane of a chunk: 128 rows x 64 halves
 constexpr int kMtStage = 2 * kMtPlane;     // hi + lo
 constexpr int kMtStages = 3;
-constexpr int kMtCoefPlane = kMtNC * 128;  // 64 rows x 64 halves
-constexpr uint32_t kMtIdesc = (1u << 4) | ((uint32_t)(kMtNC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t mt_idesc(int nc) { return (1u << 4) | ((uint32_t)(nc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
 
 struct ManoTcDev {
   const float* tmpl;            // [3][896]
@@ -55,32 +54,37 @@ struct ManoTcHost {
   alignas(64) unsigned char map_lo[128];
 };
 
+template <int NC>
 struct MtSmem {
   unsigned char stage[kMtStages][kMtStage];          // 96 KB; the set-up phase uses it as scratch first
-  unsigned char coef[kMtChunks][2][kMtCoefPlane];    // 48 KB
-  float A[kMtNC][16][12];                            // 48 KB skinning transforms
-  float center[kMtNC][4];                            // wrist translation, [3] = un-scaling of the candidate's coefficient row
+  unsigned char coef[kMtChunks][2][NC * 128];        // NC rows x 64 halves per plane: 48 KB at NC = 64
+  float A[NC][16][12];                            // 48 KB skinning transforms
+  float center[NC][4];                            // wrist translation, [3] = un-scaling of the candidate's coefficient row
   float outbuf[16][96];                              // per epilogue warp: 32 vertices x 3 floats
   unsigned long long full[kMtStages], empty[kMtStages], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
 };
 // set-up scratch inside the stage region
+template <int NC>
 struct MtScratch {
-  float R[kMtNC][16][9];
-  float J[kMtNC][16][3];
-  float coef[kMtNC][148];
+  float R[NC][16][9];
+  float J[NC][16][3];
+  float coef[NC][148];
 };
-static_assert(sizeof(MtScratch) <= kMtStages * kMtStage, "set-up scratch must fit the pipeline region");
+static_assert(sizeof(MtScratch<kMtNCMax>) <= kMtStages * kMtStage, "set-up scratch must fit the pipeline region");
 
+template <int NC>
 __global__ void __launch_bounds__(kMtThreads, 1)
 k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CUtensorMap tmD_lo, ManoModelDev m, ManoTcDev t,
           const float* __restrict__ pose, const float* __restrict__ shape, int pose_stride, int shape_stride, int n,
           float* __restrict__ verts, float* __restrict__ joints, int vt_per_cta, int debug_blend) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  MtSmem& sm = *reinterpret_cast<MtSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
-  MtScratch& sc = *reinterpret_cast<MtScratch*>(sm.stage[0]);
+  MtSmem<NC>& sm = *reinterpret_cast<MtSmem<NC>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  MtScratch<NC>& sc = *reinterpret_cast<MtScratch<NC>*>(sm.stage[0]);
+  constexpr int CG = NC / 4;                  // candidates per epilogue warp column group: 16 or 12
+  constexpr uint32_t kIdesc = mt_idesc(NC);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int c0 = blockIdx.x * kMtNC;
+  const int c0 = blockIdx.x * NC;
   const int vt_lo = blockIdx.y * vt_per_cta, vt_hi = min(kMtVT, vt_lo + vt_per_cta);
 
   if (warp == 1 && lane == 0) {
@@ -97,7 +101,7 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
 
   // ------------------------------------------------------------------ set-up, once per candidate
   // (1) Rodrigues, pose-corrective coefficients, regressed joints: one thread per (candidate, kinematic joint)
-  for (int it = tid; it < kMtNC * 16; it += kMtThreads) {
+  for (int it = tid; it < NC * 16; it += kMtThreads) {
     const int c = it >> 4, j = it & 15;
     const bool valid = c0 + c < n;
     float R[9], beta[10];
@@ -134,7 +138,7 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
   }
   __syncthreads();
   // (2) kinematic chain and skinning transforms: one thread per (candidate, finger); the root goes with finger 0
-  for (int it = tid; it < kMtNC * 5; it += kMtThreads) {
+  for (int it = tid; it < NC * 5; it += kMtThreads) {
     const int c = it / 5, f = it % 5;
     const bool store_j = blockIdx.y == 0 && c0 + c < n;
     float G0[12];
@@ -183,7 +187,7 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
   }
   // (3) coefficient rows -> (hi, lo) __half planes scaled per candidate by an exact power of two (peak in [2^13, 2^14)),
   //     written into the swizzled B operand: one warp per candidate at a time
-  for (int c = warp; c < kMtNC; c += kMtThreads / 32) {
+  for (int c = warp; c < NC; c += kMtThreads / 32) {
     float mx = 0.f;
     for (int k = lane; k < kBlendK; k += 32) mx = fmaxf(mx, fabsf(sc.coef[c][k]));
 #pragma unroll
@@ -239,7 +243,7 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
         tc_fence_after();
         for (int dd = 0; dd < 3; ++dd) {
           const int d = dd;
-          const uint32_t dcol = tmem_base + (uint32_t)(buf * 3 * kMtNC + d * kMtNC);
+          const uint32_t dcol = tmem_base + (uint32_t)(buf * 3 * NC + d * NC);
           for (int ch = 0; ch < kMtChunks; ++ch) {
             mbar_wait(&sm.full[st], phase);
             tc_fence_after();
@@ -248,9 +252,9 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
             const int ksteps = ch < 2 ? 4 : 2;                  // 145 coefficients = 9.06 k-steps of 16
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t adv = (uint64_t)((k * 32) >> 4);
-              umma_f16(dcol, a_lo + adv, b_hi + adv, kMtIdesc, (ch | k) != 0 ? 1u : 0u);
-              umma_f16(dcol, a_hi + adv, b_lo + adv, kMtIdesc, 1u);
-              umma_f16(dcol, a_hi + adv, b_hi + adv, kMtIdesc, 1u);
+              umma_f16(dcol, a_lo + adv, b_hi + adv, kIdesc, (ch | k) != 0 ? 1u : 0u);
+              umma_f16(dcol, a_hi + adv, b_lo + adv, kIdesc, 1u);
+              umma_f16(dcol, a_hi + adv, b_hi + adv, kIdesc, 1u);
             }
             umma_commit(&sm.empty[st]);
             if (++st == kMtStages) { st = 0; phase ^= 1; }
@@ -305,8 +309,8 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
       }
       mbar_wait(&sm.tmem_full[buf], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 3 * kMtNC + cg * 16);
-      const uint32_t dstep = (uint32_t)kMtNC;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 3 * NC + cg * CG);
+      const uint32_t dstep = (uint32_t)NC;
 #pragma unroll 1
       for (int h8 = 0; h8 < 2; ++h8) {
         uint32_t ax[8], ay[8], az[8];
@@ -321,8 +325,8 @@ k_mano_tc(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CU
         // fully unrolled: the accumulator arrays must be indexed statically (they live in registers filled by the asm above)
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
-          const int c = cg * 16 + h8 * 8 + cc;
-          if (c0 + c >= n) break;                          // uniform across the warp
+          const int c = cg * CG + h8 * 8 + cc;
+          if (h8 * 8 + cc >= CG || c0 + c >= n) break;     // uniform across the warp
           const float un = sm.center[c][3] * t.dirs_inv;
           const float vp[3] = {fmaf(__uint_as_float(ax[cc]), un, tp[0]), fmaf(__uint_as_float(ay[cc]), un, tp[1]),
                                fmaf(__uint_as_float(az[cc]), un, tp[2])};
@@ -467,28 +471,41 @@ void mano_tc_destroy(void* h) {
 int mano_tc_forward(const void* h, const ManoModelDev& m, const float* pose, const float* shape, int pose_stride, int shape_stride,
                     int n, float* verts, float* joints, cudaStream_t stream, int debug_blend) {
   const ManoTcHost* th = static_cast<const ManoTcHost*>(h);
-  const int smem = (int)sizeof(MtSmem) + 1024;
+  const int smem64 = (int)sizeof(MtSmem<64>) + 1024, smem48 = (int)sizeof(MtSmem<48>) + 1024;
   int dev = 0, n_sm = 148;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return VPHO_ERR_LAUNCH;
   static bool attr[64] = {};
   static int sms[64] = {};
   if (!attr[dev]) {
-    if (cudaFuncSetAttribute(k_mano_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return VPHO_ERR_LAUNCH;
+    if (cudaFuncSetAttribute(k_mano_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64) != cudaSuccess ||
+        cudaFuncSetAttribute(k_mano_tc<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem48) != cudaSuccess)
+      return VPHO_ERR_LAUNCH;
     cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
     attr[dev] = true;
   }
   if (sms[dev] > 0) n_sm = sms[dev];
-  // few candidates: split the vertex tiles over more CTAs (each repeats the cheap set-up) so that the grid fills the SMs
-  const int nb = (n + kMtNC - 1) / kMtNC;
-  int vsplit = n_sm / nb;
-  vsplit = vsplit < 1 ? 1 : (vsplit > kMtVT ? kMtVT : vsplit);
-  const int vt_per_cta = (kMtVT + vsplit - 1) / vsplit;
-  const int gy = (kMtVT + vt_per_cta - 1) / vt_per_cta;
+  // Grid shape: candidate tiles of 64 or 48 (UMMA N) x groups of vertex tiles.  A CTA costs about (tiles + 1 set-up) x NC; the
+  // launch takes ceil(CTAs / SMs) waves of that.  Few candidates: the vertex tiles are split over more CTAs (each repeats the
+  // cheap set-up); 6400 candidates: 134 CTAs of 48 instead of 100 of 64 on 148 SMs.
+  int best_nc = 64, best_vt = kMtVT;
+  long best_cost = -1;
+  for (int nc : {64, 48})
+    for (int vt = kMtVT; vt >= 1; --vt) {
+      const int nb_ = (n + nc - 1) / nc, gy_ = (kMtVT + vt - 1) / vt;
+      const long waves = ((long)nb_ * gy_ + n_sm - 1) / n_sm;
+      const long cost = waves * nc * (vt + 1);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nc = nc; best_vt = vt; }
+    }
+  const int nb = (n + best_nc - 1) / best_nc, vt_per_cta = best_vt, gy = (kMtVT + vt_per_cta - 1) / vt_per_cta;
   profile_begin(VPHO_TAG_MANO_FULL, stream);
-  if (launch_pdl(k_mano_tc, dim3(nb, gy), dim3(kMtThreads), smem, stream, 1, *reinterpret_cast<const CUtensorMap*>(th->map_hi),
-                 *reinterpret_cast<const CUtensorMap*>(th->map_lo), m, th->dev, pose, shape, pose_stride, shape_stride, n, verts, joints,
-                 vt_per_cta, debug_blend) != cudaSuccess)
-    return VPHO_ERR_LAUNCH;
+  const CUtensorMap& mhi = *reinterpret_cast<const CUtensorMap*>(th->map_hi);
+  const CUtensorMap& mlo = *reinterpret_cast<const CUtensorMap*>(th->map_lo);
+  const cudaError_t rc =
+      best_nc == 64 ? launch_pdl(k_mano_tc<64>, dim3(nb, gy), dim3(kMtThreads), smem64, stream, 1, mhi, mlo, m, th->dev, pose, shape,
+                                 pose_stride, shape_stride, n, verts, joints, vt_per_cta, debug_blend)
+                    : launch_pdl(k_mano_tc<48>, dim3(nb, gy), dim3(kMtThreads), smem48, stream, 1, mhi, mlo, m, th->dev, pose, shape,
+                                 pose_stride, shape_stride, n, verts, joints, vt_per_cta, debug_blend);
+  if (rc != cudaSuccess) return VPHO_ERR_LAUNCH;
   profile_end(VPHO_TAG_MANO_FULL, stream);
   return VPHO_OK;
 }

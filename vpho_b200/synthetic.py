@@ -58,8 +58,12 @@ def _rest_skeleton() -> Dict[str, np.ndarray]:
     return {"J": J, "tips": tips}
 
 
-def make_mano_model(seed: int = 1234) -> Dict[str, np.ndarray]:
-    """A 778-vertex pseudo-hand with MANO's tensor shapes (SURVEY.md §8d 'MANO model')."""
+def make_mano_model(seed: int = 1234, max_influences: int = 4) -> Dict[str, np.ndarray]:
+    """A 778-vertex pseudo-hand with MANO's tensor shapes (SURVEY.md §8d 'MANO model').
+    max_influences: non-zero skinning weights per vertex.  SMPL-family models (MANO is one) constrain every vertex to at most
+    4 influencing joints (SMPL, Loper et al. 2015, sec. 3: blend weights kept sparse for compatibility with rendering
+    engines), so 4 is the default; None gives a fully dense 778 x 16 matrix (the kernels' dense skinning path, kept under
+    test)."""
     rng = np.random.default_rng(seed)
     sk = _rest_skeleton()
     J, tips = sk["J"], sk["tips"]
@@ -90,6 +94,12 @@ def make_mano_model(seed: int = 1234) -> Dict[str, np.ndarray]:
         v[i] = p0 + axis * u[i] + r * rad * (0.6 + 0.4 * rng.random())
         # skinning weights: parent joint dominates, blends to child joint / grand-parent
         ww = np.full(16, 1e-3) * rng.random(16)
+        if max_influences is not None:
+            # keep the noise only on the strongest `max_influences - 2` joints besides the bone's own two
+            own = {pj} if cj < 0 else {pj, cj}
+            others = sorted((j for j in range(16) if j not in own), key=lambda j: -ww[j])
+            for j in others[max(0, max_influences - len(own)):]:
+                ww[j] = 0.0
         ww[pj] += 1.0 - 0.5 * u[i]
         if cj >= 0:
             ww[cj] += 0.5 * u[i]

@@ -26,6 +26,7 @@ from __future__ import annotations
 import argparse
 import ctypes as C
 import glob
+import gc
 import json
 import os
 import statistics
@@ -357,6 +358,10 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
 
     def timed(step_fn, steps, profile=0, gather=False, begin_fn=None, end_fn=None):
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]      # created outside the timed region
+        # no cyclic-GC pauses inside the timed region (as `timeit` does): in the pipelined loop the enqueueing thread has
+        # ~1.5 ms of slack per batch, a generation-2 collection of this process takes longer than that
+        gc.collect()
+        gc.disable()
         barrier()
         l0 = lib.c.vpho_launch_count()
         if profile:
@@ -391,6 +396,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
             assert gathered.shape == (bs * world, recorder.width)
         marks[steps].record()
         barrier()
+        gc.enable()
         wall = time.perf_counter() - wall0
         windows[-1][1] = wall0 + wall
         if profile:

@@ -354,6 +354,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
 
     windows = []
+    host_ms = []           # (enqueue, wait) host milliseconds per batch of the pipelined passes
     per_step = []          # of the most recent timed() pass: time between consecutive step starts on the compute stream
 
     def timed(step_fn, steps, profile=0, gather=False, begin_fn=None, end_fn=None):
@@ -378,10 +379,13 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
             ticket = None
             for i in range(steps):       # batch i enqueued before the host waits for batch i-1
                 marks[i].record()
+                h0 = time.perf_counter()
                 nxt = begin_fn()
+                h1 = time.perf_counter()
                 if ticket is not None:
                     last = None
                     last = end_fn(ticket)
+                host_ms.append((round((h1 - h0) * 1e3, 3), round((time.perf_counter() - h1) * 1e3, 3)))
                 ticket = nxt
             last = None
             last = end_fn(ticket)
@@ -442,6 +446,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     else:
         ms_res, wall_res, launches = timed(step_resident, args.steps)
     per_step_value = list(per_step)
+    host_value = list(host_ms)
     ms_latency = timed(step_resident, args.steps)[0] if args.pipeline else ms_res
     # 2) the same K steps with the dominant kernel (tag 0, head GEMM) bracketed by CUDA events on its launching stream ->
     #    roofline (median launch duration: a single driver hiccup must not move it)
@@ -593,7 +598,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         "sampler": {"hand_net_calls": net_calls, "obj_net_calls": info["obj"]["net_calls"],
                     "hand_attempts": info["hand"]["attempts"], "rejected": info["hand"]["rejected"] + info["obj"]["rejected"]},
         "wall_ms_per_step": round(wall_res / args.steps, 4),
-        "per_step_ms": per_step_value,
+        "per_step_ms": per_step_value, "host_enqueue_wait_ms": host_value,
         "pipelining": {"enabled": bool(args.pipeline), "latency_ms_per_batch": round(ms_latency / args.steps, 4),
                        "note": "value / ms_per_step: K batches software-pipelined (predict_begin / predict_end): batch i+1 is "
                                "enqueued before the host waits for batch i's samplers, batch i's aggregation + output-only work "

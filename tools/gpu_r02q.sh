@@ -1,12 +1,4 @@
 mkdir -p gpurun_out
-for i in 1 2 3; do
-timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02p_bench_$i.json 2> gpurun_out/r02p_bench_$i.err; echo "bench rc=$?"; tail -3 gpurun_out/r02p_bench_$i.err
-python - $i <<'PY'
-import json,sys
-d=json.load(open('gpurun_out/r02p_bench_%s.json'%sys.argv[1])); print(d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['clocks']); print(d['per_step_ms']); print(d['host_enqueue_wait_ms'])
-PY
-done
-mkdir -p gpurun_out
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_mano_tc --launch-skip 2 --launch-count 1 -o gpurun_out/rep_mano python tools/mano_only.py 6400 > gpurun_out/r02q_ncu_mano.log 2>&1; echo "ncu rc=$?"
 ncu -i gpurun_out/rep_mano.ncu-rep --page source --csv --print-source cuda > gpurun_out/r02q_mano_source.csv 2> gpurun_out/r02q_src.err; echo "src rc=$?"; wc -c gpurun_out/r02q_mano_source.csv
 ncu -i gpurun_out/rep_mano.ncu-rep --page details > gpurun_out/r02q_mano_details.txt 2>&1

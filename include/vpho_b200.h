@@ -331,6 +331,61 @@ size_t vpho_hoi_workspace_bytes(int bs, int S, int topk_hand, int topk_obj, int 
 int vpho_hoi_aggregate(vpho_mano_t mano, vpho_assets_t assets, const vpho_hoi_args* args, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * N1: the modules that PRODUCE the hot path's inputs, from the RoI-aligned feature maps to the encodings,
+ * heat-maps, regression pose and local contact forces -- `vpho_net.forward` lib/model/VPHO.py:129-178:
+ *   head_hm_hand / head_hm_obj   HeadHeatmap2.forward              lib/model/head_inplane.py:42-107
+ *   align_hm_to_bbox_rectangle, flip_tensor_by_mask_index, F.interpolate   lib/model/VPHO.py:136-148,333-357
+ *   encoder_hand / encoder_obj   Encoder.forward, Residual.forward lib/model/encoding.py:5-73
+ *   head_mano                    HeadMano.forward                  lib/model/head_mano.py:61-76
+ *   cross_hand / cross_obj       CrossModule.forward               lib/model/cross_module.py:91-137
+ *   head_physics                 HeadPhysics.forward               lib/model/physics.py:648-721 (+ get_local_force :546-557)
+ * eval mode (BatchNorm running statistics, no dropout).  Weights are handed over as the module tree's state dict: a table of
+ * named float32 HOST tensors whose names are the reference's state-dict keys (`head_hm_hand.conv_layers.0.weight`, ...,
+ * as `accel.save_state` writes them, lib/engine/base_trainer.py:85-89).  Every dimension (feature channels, RoI size, hidden
+ * widths, joint / key-point counts, d_model, feed-forward width) is read from the tensors' shapes. */
+typedef struct vpho_named_tensor {
+  const char* name;        /* reference state-dict key, without any `module.` wrapper prefix */
+  const float* data;       /* host pointer, float32, C-contiguous */
+  int32_t ndim;            /* <= 4 */
+  int64_t shape[4];
+} vpho_named_tensor;
+typedef struct vpho_heads* vpho_heads_t;
+/* VPHO_ERR_INVALID when a key is missing or a shape is inconsistent with the module definitions. */
+int vpho_heads_create(const vpho_named_tensor* tensors, int n_tensors, vpho_heads_t* out);
+int vpho_heads_destroy(vpho_heads_t h);
+size_t vpho_heads_workspace_bytes(vpho_heads_t h, int bs, int roi_size);
+
+typedef struct vpho_heads_args {
+  int32_t bs, roi_size;            /* images; RoI side (cfg.roi_size = 32); heat-maps are 2*roi_size */
+  /* inputs (device, f32 unless noted) */
+  const float* hf_hr;              /* [bs][C][roi][roi]  hand features, tight hand box   (VPHO.py:123) */
+  const float* of_or_rect;         /* [bs][C][roi][roi]  object features, square box     (VPHO.py:126) */
+  const float* hf_hr_rect;         /* [bs][C][roi][roi]  hand features, square hand box  (VPHO.py:125) */
+  const float* bbox_hand;          /* [bs][4] */
+  const float* bbox_hand_rect;     /* [bs][4] */
+  const float* bbox_obj;           /* [bs][4] */
+  const float* bbox_obj_rect;      /* [bs][4] */
+  const uint8_t* is_right;         /* [bs] bool */
+  const float* gravity;            /* [bs][3] (data['gravity'], un-flipped) */
+  /* outputs (device) */
+  float* hand_heatmap;             /* [bs][Jh][2roi][2roi]  pd_hm_hand */
+  float* obj_heatmap;              /* [bs][Jo][2roi][2roi]  pd_hm_obj */
+  float* encoding_hand;            /* [bs][enc_dim] */
+  float* encoding_obj;             /* [bs][enc_dim] */
+  float* mano_pose;                /* [bs][48] axis-angle  pd_mano_pose */
+  float* mano_shape;               /* [bs][10] */
+  float* force_local;              /* [bs][32][3] */
+  float* force_scale;              /* [bs][32]    (optional) */
+  float* force_weight;             /* [bs][32][8] (optional; after fc_weight's Softmax) */
+  float* CoM;                      /* [bs][32][3] (optional) */
+  float* enc_phy_hand;             /* [bs][32][d_model] (optional diagnostics) */
+  float* enc_phy_obj;              /* [bs][32][d_model] (optional diagnostics) */
+} vpho_heads_args;
+int vpho_heads_forward(vpho_heads_t h, const vpho_heads_args* args, void* workspace, size_t workspace_bytes, void* stream);
+/* dims[8] = {C, Jh, Jo, enc_dim, d_model, n_force(32), heat hidden, encoder hidden} */
+int vpho_heads_dims(vpho_heads_t h, int32_t* dims);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,19 @@ class HoiArgs(C.Structure):
     ]
 
 
+class NamedTensor(C.Structure):
+    """`vpho_named_tensor` (include/vpho_b200.h): one entry of a reference state dict."""
+    _fields_ = [("name", C.c_char_p), ("data", c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
+
+
+class HeadsArgs(C.Structure):
+    """`vpho_heads_args` (include/vpho_b200.h)."""
+    _fields_ = [("bs", C.c_int32), ("roi_size", C.c_int32)] + [(k, c_void_p) for k in (
+        "hf_hr", "of_or_rect", "hf_hr_rect", "bbox_hand", "bbox_hand_rect", "bbox_obj", "bbox_obj_rect", "is_right", "gravity",
+        "hand_heatmap", "obj_heatmap", "encoding_hand", "encoding_obj", "mano_pose", "mano_shape", "force_local", "force_scale",
+        "force_weight", "CoM", "enc_phy_hand", "enc_phy_obj")]
+
+
 class EvalRecordArgs(C.Structure):
     """`vpho_eval_record_args` (include/vpho_b200.h)."""
     _fields_ = [("bs", c_int), ("S", c_int)] + [(k, c_void_p) for k in (
@@ -103,6 +116,11 @@ _SIGNATURES = {
     "vpho_eval_record_workspace_bytes": (c_size_t, [c_int]),
     "vpho_eval_record": (c_int, [c_void_p, c_void_p, C.POINTER(EvalRecordArgs), c_void_p, c_size_t, c_void_p]),
     "vpho_hand_pa_metrics": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_void_p]),
+    "vpho_heads_create": (c_int, [C.POINTER(NamedTensor), c_int, C.POINTER(c_void_p)]),
+    "vpho_heads_destroy": (c_int, [c_void_p]),
+    "vpho_heads_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "vpho_heads_forward": (c_int, [c_void_p, C.POINTER(HeadsArgs), c_void_p, c_size_t, c_void_p]),
+    "vpho_heads_dims": (c_int, [c_void_p, C.POINTER(C.c_int32)]),
     "vpho_hoi_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vpho_hoi_aggregate": (c_int, [c_void_p, c_void_p, C.POINTER(HoiArgs), c_void_p, c_size_t, c_void_p]),
 }

@@ -374,3 +374,120 @@ def make_metric_tables(objects: Dict[str, object]) -> Dict[str, object]:
     return {"bbox3d": np.transpose(corners, (2, 0, 1)).astype(np.float32), "diameter": diameter.astype(np.float32),
             "sym_R": sR, "sym_t": st, "sym_count": cnt, "model_info": infos}
 
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# N1: synthetic weights / inputs of the modules that produce the hot path's inputs (VPHO.py:56-74,129-178)
+# ---------------------------------------------------------------------------------------------------------------------------
+PRODUCER_DIMS = {"C": 256, "heat_hid": 128, "Jh": 21, "Jo": 27, "enc_hid": 256, "roi": 32, "mano_layers": (1024, 512),
+                 "d_model": 512, "ff": 2048, "phys_hid": 512}
+# toy dimensions for the CPU emulator tests: same module tree, every width shrunk
+PRODUCER_DIMS_TOY = {"C": 6, "heat_hid": 8, "Jh": 3, "Jo": 4, "enc_hid": 8, "roi": 16, "mano_layers": (12, 10),
+                     "d_model": 16, "ff": 24, "phys_hid": 16}
+
+
+def make_producer_state(seed: int = 0, dims: Dict[str, object] = PRODUCER_DIMS) -> Dict[str, np.ndarray]:
+    """State dict (reference key layout: `vpho_net.state_dict()` minus backbone and denoisers) of head_hm_hand / head_hm_obj
+    (HeadHeatmap2(256, 21|27, 128)), encoder_hand / encoder_obj (Encoder(277|283, 256)), head_mano (HeadMano(1024, [1024, 512])),
+    cross_hand / cross_obj (CrossModule(8, 512)) and head_physics (HeadPhysics(512)), buffers included
+    (`cross_*.pose_embedder.pe` cross_module.py:70-78, `head_physics.anchor` physics.py:692-698).  The reference's
+    `init_weights` (VPHO.py:34-45: conv N(0, .001^2), linear N(0, .01^2)) makes every activation vanish, which would make a
+    parity test vacuous; weights are drawn with fan-in scaling instead and the BatchNorm running statistics / affine terms are
+    random, so that every layer carries O(1) signal.  Shapes and names are the reference's (`dims` shrinks them for the
+    emulator tests)."""
+    import torch
+    rng = np.random.default_rng(900001 + seed)
+    f32 = np.float32
+    st: Dict[str, np.ndarray] = {}
+    C, hh, eh, roi = dims["C"], dims["heat_hid"], dims["enc_hid"], dims["roi"]
+    dm, ff, ph = dims["d_model"], dims["ff"], dims["phys_hid"]
+    enc_dim = eh * (roi // 16) ** 2
+    in_hw = roi // 4
+    proj_dim = int(dm / (in_hw ** 2 / 32))           # cross_module.py:95
+
+    def conv(name, co, ci, k, bias=True, gain=1.0):
+        st[name + ".weight"] = (rng.normal(size=(co, ci, k, k)) * gain / math.sqrt(ci * k * k)).astype(f32)
+        if bias:
+            st[name + ".bias"] = (rng.normal(size=co) * 0.1).astype(f32)
+
+    def bn(name, c):
+        st[name + ".weight"] = rng.uniform(0.6, 1.4, size=c).astype(f32)
+        st[name + ".bias"] = (rng.normal(size=c) * 0.1).astype(f32)
+        st[name + ".running_mean"] = (rng.normal(size=c) * 0.2).astype(f32)
+        st[name + ".running_var"] = rng.uniform(0.5, 1.5, size=c).astype(f32)
+        st[name + ".num_batches_tracked"] = np.asarray(100, np.int64)
+
+    def lin(name, co, ci, gain=1.0):
+        st[name + ".weight"] = (rng.normal(size=(co, ci)) * gain / math.sqrt(ci)).astype(f32)
+        st[name + ".bias"] = (rng.normal(size=co) * 0.1).astype(f32)
+
+    for p, out in (("head_hm_hand", dims["Jh"]), ("head_hm_obj", dims["Jo"])):
+        conv(p + ".conv_layers.0", hh, C, 3)
+        conv(p + ".conv_layers.1", hh, hh, 3)
+        bn(p + ".conv_layers.2", hh)
+        st[p + ".deconv_layers.0.weight"] = (rng.normal(size=(hh, hh // 2, 4, 4)) / math.sqrt(hh * 4)).astype(f32)
+        bn(p + ".deconv_layers.1", hh // 2)
+        conv(p + ".final_layer", out, hh // 2, 1)
+    for p, cin in (("encoder_hand", C + dims["Jh"]), ("encoder_obj", C + dims["Jo"])):
+        conv(p + ".project", eh, cin, 1)
+        for r in range(8):
+            q = f"{p}.reg.{r}"
+            bn(q + ".bn", eh)
+            conv(q + ".conv1", eh // 2, eh, 1, gain=1.4)
+            bn(q + ".bn1", eh // 2)
+            conv(q + ".conv2", eh // 2, eh // 2, 3, gain=1.4)
+            bn(q + ".bn2", eh // 2)
+            conv(q + ".conv3", eh, eh // 2, 1, gain=0.5)
+    h1, h2 = dims["mano_layers"]
+    lin("head_mano.base_layer.0", h1, enc_dim, 1.4)
+    lin("head_mano.base_layer.2", h2, h1, 1.4)
+    lin("head_mano.fc_pose", 96, h2)
+    lin("head_mano.fc_shape", 10, h2)
+    pe = torch.zeros(5000, dm)
+    position = torch.arange(0, 5000, dtype=torch.float).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, dm, 2).float() * (-math.log(10000.0) / dm))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    for p in ("cross_hand", "cross_obj"):
+        conv(p + ".proj_hand", proj_dim, eh, 3)
+        conv(p + ".proj_obj", proj_dim, eh, 3)
+        lin(p + ".gravity_proj", dm, 63)
+        st[p + ".pose_embedder.pe"] = pe.unsqueeze(0).transpose(0, 1).contiguous().numpy()
+        a = p + ".attn.layers.0"
+        st[a + ".self_attn.in_proj_weight"] = (rng.normal(size=(3 * dm, dm)) / math.sqrt(dm)).astype(f32)
+        st[a + ".self_attn.in_proj_bias"] = (rng.normal(size=3 * dm) * 0.1).astype(f32)
+        lin(a + ".self_attn.out_proj", dm, dm)
+        lin(a + ".linear1", ff, dm, 1.4)
+        lin(a + ".linear2", dm, ff)
+        for n in ("norm1", "norm2"):
+            st[f"{a}.{n}.weight"] = rng.uniform(0.6, 1.4, size=dm).astype(f32)
+            st[f"{a}.{n}.bias"] = (rng.normal(size=dm) * 0.1).astype(f32)
+    for q, out in (("fc_scale", 1), ("fc_weight", 8), ("fc_CoM", 3)):
+        lin(f"head_physics.{q}.0", ph, dm, 1.4)
+        lin(f"head_physics.{q}.2", out, ph)
+    ang = torch.arange(0, 2 * torch.pi, 2 * torch.pi / 8)[:8]
+    st["head_physics.anchor"] = (torch.stack([torch.cos(ang), torch.sin(ang), torch.ones_like(ang)], dim=-1) / 8).numpy()
+    return st
+
+
+def make_producer_inputs(bs: int, seed: int = 0, roi: int = 32, C: int = 256) -> Dict[str, np.ndarray]:
+    """RoI-aligned FPN features (post-ReLU-like, >= 0) and the per-image scalars the producers read (VPHO.py:113-160)."""
+    rng = np.random.default_rng(424242 + seed)
+    f32 = np.float32
+
+    def feat():
+        return np.maximum(rng.normal(size=(bs, C, roi, roi)), 0).astype(f32)
+
+    def boxes():
+        c = rng.uniform(90, 166, size=(bs, 2))
+        wh = rng.uniform(40, 90, size=(bs, 2))
+        tight = np.concatenate([c - wh / 2, c + wh / 2], 1)
+        side = wh.max(1, keepdims=True) * rng.uniform(1.0, 1.3, size=(bs, 1))
+        rect = np.concatenate([c - side / 2, c + side / 2], 1)
+        return tight.astype(f32), rect.astype(f32)
+    bh, bhr = boxes()
+    bo, bor = boxes()
+    g = rng.normal(size=(bs, 1, 3))
+    g = 9.8 * g / np.linalg.norm(g, axis=-1, keepdims=True)
+    return {"hf_hr": feat(), "of_or_rect": feat(), "hf_hr_rect": feat(), "bbox_hand": bh, "bbox_hand_rect": bhr,
+            "bbox_obj": bo, "bbox_obj_rect": bor, "is_right": rng.random(bs) < 0.7, "gravity": g.astype(f32)}

@@ -381,10 +381,16 @@ typedef struct vpho_heads_args {
   float* CoM;                      /* [bs][32][3] (optional) */
   float* enc_phy_hand;             /* [bs][32][d_model] (optional diagnostics) */
   float* enc_phy_obj;              /* [bs][32][d_model] (optional diagnostics) */
+  int32_t flags;                   /* 0: tcgen05 path (FP16 hi/lo operand planes, 3 UMMAs per product, ~2^-22 relative);
+                                    * VPHO_HEADS_STRICT_FP32: FP32 SIMT path (cross-check; the only one of the emulator build) */
 } vpho_heads_args;
+#define VPHO_HEADS_STRICT_FP32 1
 int vpho_heads_forward(vpho_heads_t h, const vpho_heads_args* args, void* workspace, size_t workspace_bytes, void* stream);
 /* dims[8] = {C, Jh, Jo, enc_dim, d_model, n_force(32), heat hidden, encoder hidden} */
 int vpho_heads_dims(vpho_heads_t h, int32_t* dims);
+/* *flag = 1 when an activation of the last tensor-core forward left the FP16 range of the operand planes (results invalid:
+ * re-run with VPHO_HEADS_STRICT_FP32).  Synchronises `stream`. */
+int vpho_heads_overflow(vpho_heads_t h, int32_t* flag, void* stream);
 
 #ifdef __cplusplus
 }

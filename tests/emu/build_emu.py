@@ -14,7 +14,7 @@ CSRC = os.path.join(ROOT, "vpho_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libvpho_emu.so")
 # kernels that need real tcgen05/TMA hardware are excluded from the emulated build
-EXCLUDE = {"scorenet_tc.cu", "mano_tc.cu", "runtime.cu"}
+EXCLUDE = {"scorenet_tc.cu", "mano_tc.cu", "producers_tc.cu", "runtime.cu"}
 
 
 def sources():

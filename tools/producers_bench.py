@@ -1,6 +1,6 @@
 """Times `vpho_heads_forward` (N1: heat-map heads, encoders, regression head, cross modules, physics head) at the README batch
 on one GPU: CUDA events on the launching stream, inputs (3 x 67 MB of RoI features) larger than half of L2 and re-read every
-call, algorithmic FLOP from the layer shapes.  Usage: python tools/producers_bench.py [bs] [reps]"""
+call, algorithmic FLOP from the layer shapes.  Usage: python tools/producers_bench.py [bs] [reps] [strict]"""
 import json
 import os
 import sys
@@ -39,18 +39,19 @@ def producers_flop(d, bs):
 def main():
     bs = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    strict = len(sys.argv) > 3 and sys.argv[3] == "strict"
     d = syn.PRODUCER_DIMS
     fh = FeatureHeads(syn.make_producer_state(0))
     inp = syn.make_producer_inputs(bs, 1)
     T = {k: torch.from_numpy(np.asarray(v)).cuda() for k, v in inp.items()}
     for _ in range(3):
-        out = fh(T["hf_hr"], T["of_or_rect"], T["hf_hr_rect"], T)
+        out = fh(T["hf_hr"], T["of_or_rect"], T["hf_hr_rect"], T, strict_fp32=strict)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
     l0 = capi.lib().c.vpho_launch_count()
     ev[0].record()
     for i in range(reps):
-        out = fh(T["hf_hr"], T["of_or_rect"], T["hf_hr_rect"], T)
+        out = fh(T["hf_hr"], T["of_or_rect"], T["hf_hr_rect"], T, strict_fp32=strict)
         ev[i + 1].record()
     torch.cuda.synchronize()
     launches = (capi.lib().c.vpho_launch_count() - l0) // reps
@@ -60,10 +61,13 @@ def main():
     f16 = (capi.c_float * 1)()
     capi.lib().c.vpho_measure_peaks(fp32, f16, 3, None)
     flop = producers_flop(d, bs)
-    print(json.dumps({"what": "vpho_heads_forward (N1 producers)", "bs": bs, "ms_median": round(med, 4), "ms_min": round(ms[0], 4),
+    peak = fp32[0] if strict else f16[0]
+    print(json.dumps({"what": "vpho_heads_forward (N1 producers)", "path": "fp32 simt" if strict else "tcgen05 3xFP16", "bs": bs, "ms_median": round(med, 4), "ms_min": round(ms[0], 4),
                       "images_per_s": round(bs / med * 1e3, 1), "launches_per_call": int(launches), "gflop": round(flop / 1e9, 2),
                       "tflops": round(flop / med / 1e9, 2), "fp32_fma_peak_tflops_measured": round(fp32[0], 2),
-                      "frac_of_fp32_peak": round(flop / med / 1e9 / fp32[0], 4),
+                      "f16_umma_peak_tflops_measured": round(f16[0], 2),
+                      "frac_of_peak": round(flop / med / 1e9 / peak, 4),
+                      "peak": "measured FP32 FMA" if strict else "measured kind::f16 UMMA (each algorithmic FLOP is 3 UMMAs)",
                       "checksum": float(out["encoding_hand"].double().sum().item())}))
 
 

@@ -55,7 +55,7 @@ class HeadsArgs(C.Structure):
     _fields_ = [("bs", C.c_int32), ("roi_size", C.c_int32)] + [(k, c_void_p) for k in (
         "hf_hr", "of_or_rect", "hf_hr_rect", "bbox_hand", "bbox_hand_rect", "bbox_obj", "bbox_obj_rect", "is_right", "gravity",
         "hand_heatmap", "obj_heatmap", "encoding_hand", "encoding_obj", "mano_pose", "mano_shape", "force_local", "force_scale",
-        "force_weight", "CoM", "enc_phy_hand", "enc_phy_obj")]
+        "force_weight", "CoM", "enc_phy_hand", "enc_phy_obj")] + [("flags", C.c_int32)]
 
 
 class EvalRecordArgs(C.Structure):
@@ -121,6 +121,7 @@ _SIGNATURES = {
     "vpho_heads_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "vpho_heads_forward": (c_int, [c_void_p, C.POINTER(HeadsArgs), c_void_p, c_size_t, c_void_p]),
     "vpho_heads_dims": (c_int, [c_void_p, C.POINTER(C.c_int32)]),
+    "vpho_heads_overflow": (c_int, [c_void_p, C.POINTER(C.c_int32), c_void_p]),
     "vpho_hoi_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vpho_hoi_aggregate": (c_int, [c_void_p, c_void_p, C.POINTER(HoiArgs), c_void_p, c_size_t, c_void_p]),
 }

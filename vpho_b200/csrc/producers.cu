@@ -14,7 +14,11 @@
 #include "vpho_common.cuh"
 #include "vpho_b200.h"
 #include "rot_math.cuh"
+#ifndef VPHO_EMU
+#include "producers_tc.cuh"
+#endif
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -313,14 +317,27 @@ __global__ void __launch_bounds__(256) k_attention(const float* __restrict__ qkv
     if (lane == 0) sc[l] = acc;
   }
   __syncthreads();
-  float mx = -INFINITY;
-  for (int l = 0; l < L; ++l) mx = fmaxf(mx, sc[l]);
-  float sum = 0.f;
-  for (int l = 0; l < L; ++l) sum += expf(sc[l] - mx);
-  const float inv = 1.f / sum;
+  // softmax over the L scores by warp 0 (probabilities written back to shared memory once)
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int l = lane; l < L; l += 32) mx = fmaxf(mx, sc[l]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int l = lane; l < L; l += 32) {
+      const float e = expf(sc[l] - mx);
+      sc[l] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    for (int l = lane; l < L; l += 32) sc[l] *= inv;
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < hd; i += blockDim.x) {
     float acc = 0.f;
-    for (int l = 0; l < L; ++l) acc = fmaf(expf(sc[l] - mx) * inv, qkv[((long long)l * N + n) * 3 * E + 2 * E + h * hd + i], acc);
+    for (int l = 0; l < L; ++l) acc = fmaf(sc[l], qkv[((long long)l * N + n) * 3 * E + 2 * E + h * hd + i], acc);
     out[((long long)lq * N + n) * E + h * hd + i] = acc;
   }
 }
@@ -418,6 +435,10 @@ struct DevMat {          // a [Kpad][ldb] weight matrix + per-output vectors
   float* bias = nullptr;
   float* post_scale = nullptr;
   float* post_shift = nullptr;
+#ifndef VPHO_EMU
+  TcWeights tc;            // the same matrix as [N][ntap * Cp] FP16 hi/lo planes (tensor-core path); Cp = cin padded to 64
+  int tc_cp = 0, tc_ntap = 0;
+#endif
 };
 struct DevVec2 { float* scale = nullptr; float* shift = nullptr; };
 
@@ -439,6 +460,8 @@ struct vpho_heads {
   CrossW cross_hand, cross_obj;
   DevMat phys_scale0, phys_weight0, phys_com0, phys_scale2, phys_weight2, phys_com2;
   float* anchor = nullptr;
+  bool tc_ok = false;       // tensor-core planes built (sm_100a build with cuTensorMapEncodeTiled; widths multiples of 64)
+  int* overflow = nullptr;  // device flag: an activation left the FP16 range of the operand planes
   std::vector<void*> allocs;
 };
 
@@ -470,7 +493,7 @@ int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // [K][N] matrix from a generator, zero padded to (multiple of 16) x (multiple of 128)
 template <typename F>
-bool make_mat(vpho_heads* h, DevMat& dm, int K, int N, F at, const float* bias) {
+bool make_mat(vpho_heads* h, DevMat& dm, int K, int N, F at, const float* bias, int ntap = 1, bool want_tc = false) {
   dm.K = K;
   dm.N = N;
   dm.ldb = round_up(N, 128);
@@ -480,6 +503,19 @@ bool make_mat(vpho_heads* h, DevMat& dm, int K, int N, F at, const float* bias) 
     for (int n = 0; n < N; ++n) B[(size_t)k * dm.ldb + n] = at(k, n);
   dm.B = upload(h, B);
   if (bias) dm.bias = upload(h, std::vector<float>(bias, bias + N));
+#ifndef VPHO_EMU
+  if (want_tc && h->tc_ok) {
+    const int cin = K / ntap, Cp = round_up(cin, 64);
+    std::vector<float> dense((size_t)N * ntap * Cp, 0.f);
+    for (int n = 0; n < N; ++n)
+      for (int t = 0; t < ntap; ++t)
+        for (int c = 0; c < cin; ++c) dense[((size_t)n * ntap + t) * Cp + c] = at(t * cin + c, n);
+    dm.tc_cp = Cp;
+    dm.tc_ntap = ntap;
+    if (!pt_make_weights(dm.tc, dense, N, ntap * Cp)) h->tc_ok = false;
+    else h->allocs.push_back(dm.tc.planes);
+  }
+#endif
   return dm.B && (!bias || dm.bias);
 }
 
@@ -493,10 +529,10 @@ bool conv_mat(vpho_heads* h, Table& T, const std::string& p, DevMat& dm, int& Co
   if (b && b->shape[0] != Co) return T.ok = false;
   const float* W = w->data;
   const int kk = ks * ks, ci_n = Ci;
-  return make_mat(h, dm, kk * Ci, Co, [=](int k, int n) { return W[((size_t)n * ci_n + k % ci_n) * kk + k / ci_n]; }, b ? b->data : nullptr);
+  return make_mat(h, dm, kk * Ci, Co, [=](int k, int n) { return W[((size_t)n * ci_n + k % ci_n) * kk + k / ci_n]; }, b ? b->data : nullptr, kk, true);
 }
 
-bool linear_mat(vpho_heads* h, Table& T, const std::string& p, DevMat& dm, int& out, int& in) {
+bool linear_mat(vpho_heads* h, Table& T, const std::string& p, DevMat& dm, int& out, int& in, bool want_tc = false) {
   const vpho_named_tensor* w = T.get(p + ".weight", 2);
   const vpho_named_tensor* b = T.get(p + ".bias", 1);
   if (!w || !b) return false;
@@ -504,7 +540,7 @@ bool linear_mat(vpho_heads* h, Table& T, const std::string& p, DevMat& dm, int& 
   if (b->shape[0] != out) return T.ok = false;
   const float* W = w->data;
   const int in_n = in;
-  return make_mat(h, dm, in, out, [=](int k, int n) { return W[(size_t)n * in_n + k]; }, b->data);
+  return make_mat(h, dm, in, out, [=](int k, int n) { return W[(size_t)n * in_n + k]; }, b->data, 1, want_tc);
 }
 
 // BatchNorm2d (eval) as y = x * scale + shift
@@ -553,7 +589,7 @@ bool build_heat(vpho_heads* h, Table& T, const std::string& p, HeatHead& hh, int
     if (!make_mat(h, hh.dc[ph], 4 * Ci, Co, [=](int k, int n) {
           const int tap = k / Ci, ci2 = k % Ci;
           return W[(((size_t)ci2 * Co + n) * 4 + kys[tap >> 1]) * 4 + kxs[tap & 1]];
-        }, nullptr)) return false;
+        }, nullptr, 4, true)) return false;
     hh.dc[ph].post_scale = ds;
     hh.dc[ph].post_shift = dt;
   }
@@ -606,12 +642,12 @@ bool build_cross(vpho_heads* h, Table& T, const std::string& p, CrossW& c, int e
   {
     const float* W = ipw->data;
     const int d = c.d;
-    if (!make_mat(h, c.in_proj, d, 3 * d, [=](int k, int n) { return W[(size_t)n * d + k]; }, ipb->data)) return false;
+    if (!make_mat(h, c.in_proj, d, 3 * d, [=](int k, int n) { return W[(size_t)n * d + k]; }, ipb->data, 1, true)) return false;
   }
-  if (!linear_mat(h, T, a + ".self_attn.out_proj", c.out_proj, out, in) || out != c.d || in != c.d) return false;
-  if (!linear_mat(h, T, a + ".linear1", c.lin1, out, in) || in != c.d) return false;
+  if (!linear_mat(h, T, a + ".self_attn.out_proj", c.out_proj, out, in, true) || out != c.d || in != c.d) return false;
+  if (!linear_mat(h, T, a + ".linear1", c.lin1, out, in, true) || in != c.d) return false;
   c.ff = out;
-  if (!linear_mat(h, T, a + ".linear2", c.lin2, out, in) || in != c.ff || out != c.d) return false;
+  if (!linear_mat(h, T, a + ".linear2", c.lin2, out, in, true) || in != c.ff || out != c.d) return false;
   return vec(h, T, a + ".norm1.weight", c.d, &c.n1w) && vec(h, T, a + ".norm1.bias", c.d, &c.n1b) &&
          vec(h, T, a + ".norm2.weight", c.d, &c.n2w) && vec(h, T, a + ".norm2.bias", c.d, &c.n2b) && c.Wg && c.bg && c.pe;
 }
@@ -659,6 +695,9 @@ int grid_for(long long total) { return (int)std::min<long long>((total + 255) / 
 
 struct Ws {
   float *cat, *xa, *xb, *mid1, *mid2, *dec, *pool1_hand, *pool1_obj, *tok, *qkv, *att, *tmp, *ffn, *mano_a, *mano_b, *mano_o, *ph_tok, *ph_mid, *ph_head;
+  // tensor-core path: FP16 (hi, lo) plane pairs; `n_*` = elements of ONE plane (lo follows hi)
+  unsigned short *pF, *pX0, *pX1, *pXA, *pM1, *pM2, *pDEC, *pP1h, *pP1o, *pTOK, *pATT, *pFFN;
+  size_t nF, nX, nM, nDEC, nP1, nTOK, nFFN;
   size_t bytes;
 };
 
@@ -691,6 +730,20 @@ Ws carve(const vpho_heads* h, int bs, int roi, void* base) {
   w.ph_tok = take(b * h->n_force * h->d_model);
   w.ph_mid = take(b * h->n_force * h->phys_hid);
   w.ph_head = take(b * h->n_force * 12);
+  if (h->tc_ok) {
+    auto take_planes = [&](size_t n_plane) { return reinterpret_cast<unsigned short*>(take(n_plane)); };     // 2 planes x 2 bytes = 4 bytes / element
+    w.nF = b * px * (size_t)round_up(h->C + Jmax, 64);
+    w.nX = b * px * (size_t)h->enc_hid;
+    w.nM = b * px * (size_t)std::max(h->enc_hid / 2, h->heat_hid);
+    w.nDEC = b * px * 4 * (size_t)(h->heat_hid / 2);
+    w.nP1 = b * (px / 16) * (size_t)h->enc_hid;
+    w.nTOK = b * std::max<size_t>({(size_t)ntok * h->d_model, (size_t)h->enc_dim, (size_t)h->mano_h1, (size_t)h->n_force * h->phys_hid});
+    w.nFFN = b * std::max<size_t>((size_t)ntok * std::max(h->cross_hand.ff, h->cross_obj.ff), (size_t)h->mano_h2);
+    w.pF = take_planes(w.nF); w.pX0 = take_planes(w.nX); w.pX1 = take_planes(w.nX); w.pXA = take_planes(w.nX);
+    w.pM1 = take_planes(w.nM); w.pM2 = take_planes(w.nM); w.pDEC = take_planes(w.nDEC);
+    w.pP1h = take_planes(w.nP1); w.pP1o = take_planes(w.nP1);
+    w.pTOK = take_planes(w.nTOK); w.pATT = take_planes(w.nTOK); w.pFFN = take_planes(w.nFFN);
+  }
   w.bytes = off;
   return w;
 }
@@ -770,6 +823,169 @@ int run_cross(const vpho_heads* h, const CrossW& c, const vpho_heads_args* a, co
   return VPHO_OK;
 }
 
+
+#ifndef VPHO_EMU
+// ---------------------------------------------------------------------------------------------------------------------------
+// tensor-core path (producers_tc.cu): the same wiring over NHWC FP16 (hi, lo) planes
+// ---------------------------------------------------------------------------------------------------------------------------
+struct Planes {
+  __half* hi;
+  __half* lo;
+};
+Planes planes_of(unsigned short* p, size_t n_plane) { return {reinterpret_cast<__half*>(p), reinterpret_cast<__half*>(p) + n_plane}; }
+
+TcGemm tc_base(const vpho_heads* h, const DevMat& w, float slope) {
+  TcGemm p = {};
+  p.chunks = w.tc_cp / 64;
+  p.ntap = w.tc_ntap;
+  p.bias = w.bias;
+  p.post_scale = w.post_scale;
+  p.post_shift = w.post_shift;
+  p.slope = slope;
+  p.os = 1;
+  p.overflow_flag = h->overflow;
+  return p;
+}
+
+TcGemm tc_conv_op(const vpho_heads* h, const DevMat& w, int ks, int bs, int H, int W, float slope) {
+  TcGemm p = tc_base(h, w, slope);
+  p.mode = 1;
+  p.n_img = bs; p.H = H; p.W = W;
+  for (int t = 0; t < ks * ks; ++t) { p.dy[t] = (signed char)(t / ks - ks / 2); p.dx[t] = (signed char)(t % ks - ks / 2); }
+  return p;
+}
+
+int run_heat_tc(const vpho_heads* h, const HeatHead& hh, const float* feat, const unsigned char* is_right, int bs, int roi, const Ws& w, float* out,
+                cudaStream_t st) {
+  int rc;
+  const size_t px = (size_t)roi * roi, b = (size_t)bs;
+  const Planes F = planes_of(w.pF, b * px * h->C), M1 = planes_of(w.pM1, b * px * hh.hid), M2 = planes_of(w.pM2, b * px * hh.hid);
+  const Planes DEC = planes_of(w.pDEC, b * px * 4 * (hh.hid / 2));
+  if ((rc = pt_to_planes(feat, nullptr, nullptr, nullptr, is_right, 0, 0, bs, h->C, 0, roi, h->C, F.hi, F.lo, st))) return rc;
+  TcGemm p = tc_conv_op(h, hh.c0, 3, bs, roi, roi, 1.f);
+  p.out_hi = M1.hi; p.out_lo = M1.lo; p.out_cp = hh.hid;
+  if ((rc = pt_gemm(hh.c0.tc, p, F.hi, F.lo, st))) return rc;
+  p = tc_conv_op(h, hh.c1, 3, bs, roi, roi, 1.f /* LeakyReLU(True): slope 1 */);
+  p.out_hi = M2.hi; p.out_lo = M2.lo; p.out_cp = hh.hid;
+  if ((rc = pt_gemm(hh.c1.tc, p, M1.hi, M1.lo, st))) return rc;
+  for (int ph = 0; ph < 4; ++ph) {
+    const int py = ph >> 1, px_ = ph & 1;
+    p = tc_base(h, hh.dc[ph], 0.f /* ReLU */);
+    p.mode = 1; p.n_img = bs; p.H = roi; p.W = roi;
+    const int dys[2] = {py ? 1 : 0, py ? 0 : -1}, dxs[2] = {px_ ? 1 : 0, px_ ? 0 : -1};
+    for (int t = 0; t < 4; ++t) { p.dy[t] = (signed char)dys[t >> 1]; p.dx[t] = (signed char)dxs[t & 1]; }
+    p.os = 2; p.py = py; p.px = px_;
+    p.out_hi = DEC.hi; p.out_lo = DEC.lo; p.out_cp = hh.hid / 2;
+    if ((rc = pt_gemm(hh.dc[ph].tc, p, M2.hi, M2.lo, st))) return rc;
+  }
+  p = tc_conv_op(h, hh.fin, 1, bs, 2 * roi, 2 * roi, 1.f);
+  p.out_f32 = out; p.f32_img_stride = (long long)hh.J * px * 4;
+  return pt_gemm(hh.fin.tc, p, DEC.hi, DEC.lo, st);
+}
+
+int run_encoder_tc(const vpho_heads* h, const EncoderW& e, const float* feat, const float* hm, const float* bbox, const float* bbox_rect,
+                   const unsigned char* is_right, int flip, int J, int bs, int roi, const Ws& w, unsigned short* pool1, float* enc, cudaStream_t st) {
+  int rc, H = roi;
+  const int hid = e.hid, mid = e.hid / 2, Cp = round_up(h->C + J, 64);
+  const size_t b = (size_t)bs;
+  const Planes F = planes_of(w.pF, b * roi * roi * Cp);
+  if ((rc = pt_to_planes(feat, hm, bbox, bbox_rect, is_right, flip, flip, bs, h->C, J, roi, Cp, F.hi, F.lo, st))) return rc;
+  auto other = [&](unsigned short* cur) { return cur == w.pX0 ? w.pX1 : w.pX0; };
+  unsigned short* xb = w.pX0;
+  {
+    const size_t n = b * H * H * hid;
+    const Planes X = planes_of(xb, n), XA = planes_of(w.pXA, n);
+    TcGemm p = tc_conv_op(h, e.project, 1, bs, H, H, 1.f);
+    p.out_hi = X.hi; p.out_lo = X.lo; p.out_cp = hid;
+    p.out2_hi = XA.hi; p.out2_lo = XA.lo; p.pre_scale = e.reg[0].pre.scale; p.pre_shift = e.reg[0].pre.shift; p.pre_slope = 0.01f;
+    if ((rc = pt_gemm(e.project.tc, p, F.hi, F.lo, st))) return rc;
+  }
+  for (int blk = 0; blk < 4; ++blk) {
+    const size_t n = b * H * H * hid, nm = b * H * H * mid;
+    for (int j = 0; j < 2; ++j) {
+      const ResBlock& r = e.reg[blk * 2 + j];
+      unsigned short* yb = other(xb);
+      const Planes X = planes_of(xb, n), Y = planes_of(yb, n), XA = planes_of(w.pXA, n), M1 = planes_of(w.pM1, nm), M2 = planes_of(w.pM2, nm);
+      TcGemm p = tc_conv_op(h, r.c1, 1, bs, H, H, 0.01f);
+      p.out_hi = M1.hi; p.out_lo = M1.lo; p.out_cp = mid;
+      if ((rc = pt_gemm(r.c1.tc, p, XA.hi, XA.lo, st))) return rc;
+      p = tc_conv_op(h, r.c2, 3, bs, H, H, 0.01f);
+      p.out_hi = M2.hi; p.out_lo = M2.lo; p.out_cp = mid;
+      if ((rc = pt_gemm(r.c2.tc, p, M1.hi, M1.lo, st))) return rc;
+      p = tc_conv_op(h, r.c3, 1, bs, H, H, 1.f);
+      p.res_hi = X.hi; p.res_lo = X.lo;
+      p.out_hi = Y.hi; p.out_lo = Y.lo; p.out_cp = hid;
+      if (j == 0) {        // the second module of the block starts with its own BatchNorm + LeakyReLU
+        const ResBlock& nx = e.reg[blk * 2 + 1];
+        p.out2_hi = XA.hi; p.out2_lo = XA.lo; p.pre_scale = nx.pre.scale; p.pre_shift = nx.pre.shift; p.pre_slope = 0.01f;
+      }
+      if ((rc = pt_gemm(r.c3.tc, p, M2.hi, M2.lo, st))) return rc;
+      xb = yb;
+    }
+    const Planes X = planes_of(xb, n);
+    const size_t no = n / 4;
+    if (blk == 3) {
+      if ((rc = pt_pool(X.hi, X.lo, bs, H, H, hid, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, enc, st))) return rc;
+    } else {
+      unsigned short* db = blk == 1 ? pool1 : other(xb);      // enc_ls[1] is kept for the cross modules
+      const Planes D = planes_of(db, no), XA = planes_of(w.pXA, no);
+      const ResBlock& nx = e.reg[(blk + 1) * 2];
+      if ((rc = pt_pool(X.hi, X.lo, bs, H, H, hid, D.hi, D.lo, XA.hi, XA.lo, nx.pre.scale, nx.pre.shift, 0.01f, nullptr, st))) return rc;
+      xb = db;
+    }
+    H /= 2;
+  }
+  return VPHO_OK;
+}
+
+int run_cross_tc(const vpho_heads* h, const CrossW& c, const vpho_heads_args* a, const Ws& w, int sel, float* out, cudaStream_t st) {
+  const int bs = a->bs, H = a->roi_size / 4, F = h->n_force, ntok = 2 * F + 1, d = c.d, rows = bs * ntok;
+  const size_t np1 = (size_t)bs * H * H * h->enc_hid, nt = (size_t)rows * d, nf = (size_t)rows * c.ff;
+  const Planes P1h = planes_of(w.pP1h, np1), P1o = planes_of(w.pP1o, np1), TOK = planes_of(w.pTOK, nt), ATT = planes_of(w.pATT, nt),
+               FFN = planes_of(w.pFFN, nf);
+  int rc;
+  TcGemm p = tc_conv_op(h, c.proj_hand, 3, bs, H, H, 1.f);
+  p.out_f32 = w.tok; p.f32_img_stride = (long long)ntok * d;
+  if ((rc = pt_gemm(c.proj_hand.tc, p, P1h.hi, P1h.lo, st))) return rc;
+  p = tc_conv_op(h, c.proj_obj, 3, bs, H, H, 1.f);
+  p.out_f32 = w.tok + (long long)F * d; p.f32_img_stride = (long long)ntok * d;
+  if ((rc = pt_gemm(c.proj_obj.tc, p, P1o.hi, P1o.lo, st))) return rc;
+  VPHO_LAUNCH(k_gravity_pe, dim3(bs), dim3(256), 0, st, a->gravity, a->is_right, c.Wg, c.bg, c.pe, ntok, d, w.tok);
+  VPHO_CHECK_LAUNCH();
+  auto rows_op = [&](const DevMat& m, float slope) {
+    TcGemm q = tc_base(h, m, slope);
+    q.mode = 0; q.M = rows;
+    return q;
+  };
+  if ((rc = pt_split_rows(w.tok, (long long)nt, TOK.hi, TOK.lo, st))) return rc;
+  p = rows_op(c.in_proj, 1.f);
+  p.out_f32 = w.qkv; p.ldc = 3 * d;
+  if ((rc = pt_gemm(c.in_proj.tc, p, TOK.hi, TOK.lo, st))) return rc;
+  const int nhead = 2;
+  VPHO_LAUNCH(k_attention, dim3(bs, nhead, ntok), dim3(256), (size_t)(bs + d / nhead) * sizeof(float), st, w.qkv, bs, ntok, d, nhead, w.att);
+  VPHO_CHECK_LAUNCH();
+  if ((rc = pt_split_rows(w.att, (long long)nt, ATT.hi, ATT.lo, st))) return rc;
+  p = rows_op(c.out_proj, 1.f);
+  p.res_f32 = w.tok; p.out_f32 = w.tmp; p.ldc = d;                                             // x + sa(x)
+  if ((rc = pt_gemm(c.out_proj.tc, p, ATT.hi, ATT.lo, st))) return rc;
+  VPHO_LAUNCH(k_layernorm, dim3(rows), dim3(128), 0, st, w.tmp, c.n1w, c.n1b, d, w.tok);
+  VPHO_CHECK_LAUNCH();
+  if ((rc = pt_split_rows(w.tok, (long long)nt, TOK.hi, TOK.lo, st))) return rc;
+  p = rows_op(c.lin1, 0.f);
+  p.out_hi = FFN.hi; p.out_lo = FFN.lo; p.out_cp = c.ff;
+  if ((rc = pt_gemm(c.lin1.tc, p, TOK.hi, TOK.lo, st))) return rc;
+  p = rows_op(c.lin2, 1.f);
+  p.res_f32 = w.tok; p.out_f32 = w.tmp; p.ldc = d;                                             // x + ff(x)
+  if ((rc = pt_gemm(c.lin2.tc, p, FFN.hi, FFN.lo, st))) return rc;
+  VPHO_LAUNCH(k_layernorm, dim3(rows), dim3(128), 0, st, w.tmp, c.n2w, c.n2b, d, w.att);
+  VPHO_CHECK_LAUNCH();
+  const long long n = (long long)bs * F * d;
+  VPHO_LAUNCH(k_copy_cols, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, w.att, bs, ntok * d, sel * F * d, F * d, out);
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
+#endif  // !VPHO_EMU
+
 }  // namespace
 
 extern "C" int vpho_heads_create(const vpho_named_tensor* tensors, int n_tensors, vpho_heads_t* out) {
@@ -781,6 +997,21 @@ extern "C" int vpho_heads_create(const vpho_named_tensor* tensors, int n_tensors
   }
   vpho_heads* h = new vpho_heads();
   int C2 = 0, out_n, in_n;
+#ifndef VPHO_EMU
+  {   // tensor-core path: every GEMM K (input channels per tap) and every planes output width must be a multiple of 64
+    auto dim = [&](const char* k, int i) { auto it = T.m.find(k); return it == T.m.end() || it->second->ndim <= i ? 1 : (int)it->second->shape[i]; };
+    const int hh = dim("head_hm_hand.conv_layers.0.weight", 0), Cc = dim("head_hm_hand.conv_layers.0.weight", 1);
+    const int eh = dim("encoder_hand.project.weight", 0), dm = dim("cross_hand.gravity_proj.weight", 0);
+    const int ff = dim("cross_hand.attn.layers.0.linear1.weight", 0);
+    const int m1 = dim("head_mano.base_layer.0.weight", 0), m0 = dim("head_mano.base_layer.0.weight", 1), m2 = dim("head_mano.base_layer.2.weight", 0);
+    const int phd = dim("head_physics.fc_scale.0.weight", 0);
+    h->tc_ok = pt_available() && Cc % 64 == 0 && hh % 128 == 0 && eh % 128 == 0 && dm % 64 == 0 && ff % 64 == 0 && m0 % 64 == 0 && m1 % 64 == 0 &&
+               m2 % 64 == 0 && phd % 64 == 0;
+    if (cudaMalloc((void**)&h->overflow, sizeof(int)) != cudaSuccess) { delete h; return VPHO_ERR_ALLOC; }
+    h->allocs.push_back(h->overflow);
+    cudaMemset(h->overflow, 0, sizeof(int));
+  }
+#endif
   bool ok = build_heat(h, T, "head_hm_hand", h->hm_hand, h->C) && build_heat(h, T, "head_hm_obj", h->hm_obj, C2) && C2 == h->C &&
             h->hm_hand.hid == h->hm_obj.hid;
   ok = ok && build_encoder(h, T, "encoder_hand", h->enc_hand) && build_encoder(h, T, "encoder_obj", h->enc_obj);
@@ -788,8 +1019,8 @@ extern "C" int vpho_heads_create(const vpho_named_tensor* tensors, int n_tensors
     h->Jh = h->hm_hand.J; h->Jo = h->hm_obj.J; h->heat_hid = h->hm_hand.hid; h->enc_hid = h->enc_hand.hid;
     ok = h->enc_hand.cin == h->C + h->Jh && h->enc_obj.cin == h->C + h->Jo && h->enc_obj.hid == h->enc_hid;
   }
-  ok = ok && linear_mat(h, T, "head_mano.base_layer.0", h->mano0, h->mano_h1, h->enc_dim) &&
-       linear_mat(h, T, "head_mano.base_layer.2", h->mano1, h->mano_h2, in_n) && in_n == h->mano_h1;
+  ok = ok && linear_mat(h, T, "head_mano.base_layer.0", h->mano0, h->mano_h1, h->enc_dim, true) &&
+       linear_mat(h, T, "head_mano.base_layer.2", h->mano1, h->mano_h2, in_n, true) && in_n == h->mano_h1;
   if (ok) {      // fc_pose (96) and fc_shape (10) share their input: one [h2][106] matrix
     const vpho_named_tensor *wp = T.get("head_mano.fc_pose.weight", 2), *bp = T.get("head_mano.fc_pose.bias", 1),
                             *wsh = T.get("head_mano.fc_shape.weight", 2), *bsh = T.get("head_mano.fc_shape.bias", 1);
@@ -800,7 +1031,7 @@ extern "C" int vpho_heads_create(const vpho_named_tensor* tensors, int n_tensors
       for (int i = 0; i < 10; ++i) bias[96 + i] = bsh->data[i];
       const float *P = wp->data, *S = wsh->data;
       const int k2 = h->mano_h2;
-      ok = make_mat(h, h->mano_out, k2, 106, [=](int k, int n) { return n < 96 ? P[(size_t)n * k2 + k] : S[(size_t)(n - 96) * k2 + k]; }, bias.data());
+      ok = make_mat(h, h->mano_out, k2, 106, [=](int k, int n) { return n < 96 ? P[(size_t)n * k2 + k] : S[(size_t)(n - 96) * k2 + k]; }, bias.data(), 1, true);
     }
   }
   ok = ok && build_cross(h, T, "cross_hand", h->cross_hand, h->enc_hid) && build_cross(h, T, "cross_obj", h->cross_obj, h->enc_hid);
@@ -808,12 +1039,12 @@ extern "C" int vpho_heads_create(const vpho_named_tensor* tensors, int n_tensors
     h->d_model = h->cross_hand.d;
     ok = h->cross_obj.d == h->d_model && h->d_model % 2 == 0;
   }
-  ok = ok && linear_mat(h, T, "head_physics.fc_scale.0", h->phys_scale0, h->phys_hid, in_n) && in_n == h->d_model &&
-       linear_mat(h, T, "head_physics.fc_weight.0", h->phys_weight0, out_n, in_n) && out_n == h->phys_hid && in_n == h->d_model &&
-       linear_mat(h, T, "head_physics.fc_CoM.0", h->phys_com0, out_n, in_n) && out_n == h->phys_hid && in_n == h->d_model &&
-       linear_mat(h, T, "head_physics.fc_scale.2", h->phys_scale2, out_n, in_n) && out_n == 1 && in_n == h->phys_hid &&
-       linear_mat(h, T, "head_physics.fc_weight.2", h->phys_weight2, out_n, in_n) && out_n == 8 && in_n == h->phys_hid &&
-       linear_mat(h, T, "head_physics.fc_CoM.2", h->phys_com2, out_n, in_n) && out_n == 3 && in_n == h->phys_hid;
+  ok = ok && linear_mat(h, T, "head_physics.fc_scale.0", h->phys_scale0, h->phys_hid, in_n, true) && in_n == h->d_model &&
+       linear_mat(h, T, "head_physics.fc_weight.0", h->phys_weight0, out_n, in_n, true) && out_n == h->phys_hid && in_n == h->d_model &&
+       linear_mat(h, T, "head_physics.fc_CoM.0", h->phys_com0, out_n, in_n, true) && out_n == h->phys_hid && in_n == h->d_model &&
+       linear_mat(h, T, "head_physics.fc_scale.2", h->phys_scale2, out_n, in_n, true) && out_n == 1 && in_n == h->phys_hid &&
+       linear_mat(h, T, "head_physics.fc_weight.2", h->phys_weight2, out_n, in_n, true) && out_n == 8 && in_n == h->phys_hid &&
+       linear_mat(h, T, "head_physics.fc_CoM.2", h->phys_com2, out_n, in_n, true) && out_n == 3 && in_n == h->phys_hid;
   if (ok) {
     const vpho_named_tensor* an = T.get("head_physics.anchor", 2);
     ok = an && an->shape[0] == 8 && an->shape[1] == 3;
@@ -862,6 +1093,22 @@ extern "C" int vpho_heads_forward(vpho_heads_t h, const vpho_heads_args* a, void
   if (workspace_bytes < w.bytes) return VPHO_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
+  const bool strict = (a->flags & VPHO_HEADS_STRICT_FP32) != 0;
+#ifdef VPHO_EMU
+  if (!strict) return VPHO_ERR_INVALID;         // the emulator build has no tensor cores: ask for the FP32 SIMT path explicitly
+#else
+  if (!strict && !h->tc_ok) return VPHO_ERR_INVALID;   // widths not multiples of 64 (or no TMA descriptor encoder): no silent downgrade
+  if (!strict) {
+    if (cudaMemsetAsync(h->overflow, 0, sizeof(int), st) != cudaSuccess) return VPHO_ERR_LAUNCH;
+    if ((rc = run_heat_tc(h, h->hm_hand, a->hf_hr, a->is_right, bs, roi, w, a->hand_heatmap, st))) return rc;
+    if ((rc = run_heat_tc(h, h->hm_obj, a->of_or_rect, a->is_right, bs, roi, w, a->obj_heatmap, st))) return rc;
+    if ((rc = run_encoder_tc(h, h->enc_hand, a->hf_hr_rect, a->hand_heatmap, a->bbox_hand, a->bbox_hand_rect, a->is_right, 0, h->Jh, bs, roi, w,
+                             w.pP1h, a->encoding_hand, st))) return rc;
+    if ((rc = run_encoder_tc(h, h->enc_obj, a->of_or_rect, a->obj_heatmap, a->bbox_obj, a->bbox_obj_rect, a->is_right, 1, h->Jo, bs, roi, w,
+                             w.pP1o, a->encoding_obj, st))) return rc;
+  } else
+#endif
+  {
   // heat-maps (VPHO.py:129-130)
   if ((rc = run_heat(h->hm_hand, a->hf_hr, bs, h->C, roi, w, a->hand_heatmap, st))) return rc;
   if ((rc = run_heat(h->hm_obj, a->of_or_rect, bs, h->C, roi, w, a->obj_heatmap, st))) return rc;
@@ -876,32 +1123,86 @@ extern "C" int vpho_heads_forward(vpho_heads_t h, const vpho_heads_args* a, void
               a->is_right, 1, 1, bs, h->C, h->Jo, roi, w.cat);
   VPHO_CHECK_LAUNCH();
   if ((rc = run_encoder(h->enc_obj, bs, roi, w, w.pool1_obj, a->encoding_obj, st))) return rc;
+  }
   // regression head (head_mano.py:61-76)
+#ifndef VPHO_EMU
+  if (!strict) {
+    const Planes A0 = planes_of(w.pTOK, (size_t)bs * h->enc_dim), A1 = planes_of(w.pATT, (size_t)bs * h->mano_h1),
+                 A2 = planes_of(w.pFFN, (size_t)bs * h->mano_h2);
+    if ((rc = pt_split_rows(a->encoding_hand, (long long)bs * h->enc_dim, A0.hi, A0.lo, st))) return rc;
+    TcGemm p = tc_base(h, h->mano0, 0.01f);
+    p.mode = 0; p.M = bs; p.out_hi = A1.hi; p.out_lo = A1.lo; p.out_cp = h->mano_h1;
+    if ((rc = pt_gemm(h->mano0.tc, p, A0.hi, A0.lo, st))) return rc;
+    p = tc_base(h, h->mano1, 0.01f);
+    p.mode = 0; p.M = bs; p.out_hi = A2.hi; p.out_lo = A2.lo; p.out_cp = h->mano_h2;
+    if ((rc = pt_gemm(h->mano1.tc, p, A1.hi, A1.lo, st))) return rc;
+    p = tc_base(h, h->mano_out, 1.f);
+    p.mode = 0; p.M = bs; p.out_f32 = w.mano_o; p.ldc = 106;
+    if ((rc = pt_gemm(h->mano_out.tc, p, A2.hi, A2.lo, st))) return rc;
+  } else
+#endif
+  {
   if ((rc = linear(h->mano0, a->encoding_hand, bs, h->enc_dim, 0.01f, nullptr, w.mano_a, h->mano_h1, st))) return rc;
   if ((rc = linear(h->mano1, w.mano_a, bs, h->mano_h1, 0.01f, nullptr, w.mano_b, h->mano_h2, st))) return rc;
   if ((rc = linear(h->mano_out, w.mano_b, bs, h->mano_h2, 1.f, nullptr, w.mano_o, 106, st))) return rc;
+  }
   VPHO_LAUNCH(k_rot6d_rows, dim3((bs * 16 + 255) / 256), dim3(256), 0, st, w.mano_o, bs * 16, 106, a->mano_pose);
   VPHO_CHECK_LAUNCH();
   VPHO_LAUNCH(k_copy_cols, dim3((bs * 10 + 255) / 256), dim3(256), 0, st, w.mano_o, bs, 106, 96, 10, a->mano_shape);
   VPHO_CHECK_LAUNCH();
   // cross modules + physics head (VPHO.py:174-176): hand tokens of cross_hand, object tokens of cross_obj
   const int F = h->n_force, rows = bs * F, d = h->d_model, ph = h->phys_hid;
-  if ((rc = run_cross(h, h->cross_hand, a, w, 0, w.ph_tok, st))) return rc;
+  auto cross = [&](const CrossW& c, int sel) {
+#ifndef VPHO_EMU
+    if (!strict) return run_cross_tc(h, c, a, w, sel, w.ph_tok, st);
+#endif
+    return run_cross(h, c, a, w, sel, w.ph_tok, st);
+  };
+  if ((rc = cross(h->cross_hand, 0))) return rc;
+  // one two-layer MLP of HeadPhysics on the tokens in w.ph_tok -> columns [col, col + N) of the [rows][12] head buffer
+  auto mlp = [&](const DevMat& l0, const DevMat& l2, int col) -> int {
+    int r;
+#ifndef VPHO_EMU
+    if (!strict) {
+      const Planes A0 = planes_of(w.pTOK, (size_t)rows * d), A1 = planes_of(w.pATT, (size_t)rows * ph);
+      if ((r = pt_split_rows(w.ph_tok, (long long)rows * d, A0.hi, A0.lo, st))) return r;
+      TcGemm p = tc_base(h, l0, 0.01f);
+      p.mode = 0; p.M = rows; p.out_hi = A1.hi; p.out_lo = A1.lo; p.out_cp = ph;
+      if ((r = pt_gemm(l0.tc, p, A0.hi, A0.lo, st))) return r;
+      p = tc_base(h, l2, 1.f);
+      p.mode = 0; p.M = rows; p.out_f32 = w.ph_head + col; p.ldc = 12;
+      return pt_gemm(l2.tc, p, A1.hi, A1.lo, st);
+    }
+#endif
+    if ((r = linear(l0, w.ph_tok, rows, d, 0.01f, nullptr, w.ph_mid, ph, st))) return r;
+    return linear(l2, w.ph_mid, rows, ph, 1.f, nullptr, w.ph_head + col, 12, st);
+  };
   // fc_scale on the hand tokens (physics.py:704)
-  if ((rc = linear(h->phys_scale0, w.ph_tok, rows, d, 0.01f, nullptr, w.ph_mid, ph, st))) return rc;
-  if ((rc = linear(h->phys_scale2, w.ph_mid, rows, ph, 1.f, nullptr, w.ph_head, 12, st))) return rc;
+  if ((rc = mlp(h->phys_scale0, h->phys_scale2, 0))) return rc;
   if (a->enc_phy_hand &&
       cudaMemcpyAsync(a->enc_phy_hand, w.ph_tok, (size_t)rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return VPHO_ERR_LAUNCH;
-  if ((rc = run_cross(h, h->cross_obj, a, w, 1, w.ph_tok, st))) return rc;
+  if ((rc = cross(h->cross_obj, 1))) return rc;
   if (a->enc_phy_obj &&
       cudaMemcpyAsync(a->enc_phy_obj, w.ph_tok, (size_t)rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return VPHO_ERR_LAUNCH;
   // fc_weight / fc_CoM on the object tokens (physics.py:706-710)
-  if ((rc = linear(h->phys_weight0, w.ph_tok, rows, d, 0.01f, nullptr, w.ph_mid, ph, st))) return rc;
-  if ((rc = linear(h->phys_weight2, w.ph_mid, rows, ph, 1.f, nullptr, w.ph_head + 1, 12, st))) return rc;
-  if ((rc = linear(h->phys_com0, w.ph_tok, rows, d, 0.01f, nullptr, w.ph_mid, ph, st))) return rc;
-  if ((rc = linear(h->phys_com2, w.ph_mid, rows, ph, 1.f, nullptr, w.ph_head + 9, 12, st))) return rc;
+  if ((rc = mlp(h->phys_weight0, h->phys_weight2, 1))) return rc;
+  if ((rc = mlp(h->phys_com0, h->phys_com2, 9))) return rc;
   VPHO_LAUNCH(k_physics_tail, dim3((rows + 127) / 128), dim3(128), 0, st, w.ph_head, h->anchor, rows, a->force_local, a->force_scale,
               a->force_weight, a->CoM);
   VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
+
+// 1 when an activation of the last tensor-core forward left the FP16 range of the operand planes (|v| >= 60000): its results
+// are then invalid and the caller should re-run with VPHO_HEADS_STRICT_FP32.  Synchronises the stream.
+extern "C" int vpho_heads_overflow(vpho_heads_t h, int32_t* flag, void* stream) {
+  if (!h || !flag) return VPHO_ERR_INVALID;
+  *flag = 0;
+#ifndef VPHO_EMU
+  int v = 0;
+  if (cudaMemcpyAsync(&v, h->overflow, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return VPHO_ERR_LAUNCH;
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return VPHO_ERR_LAUNCH;
+  *flag = v;
+#endif
   return VPHO_OK;
 }

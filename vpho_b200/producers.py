@@ -77,9 +77,12 @@ class FeatureHeads:
             pass
 
     def forward(self, hf_hr: torch.Tensor, of_or_rect: torch.Tensor, hf_hr_rect: torch.Tensor, data: Dict[str, torch.Tensor],
-                debug: bool = False) -> Dict[str, torch.Tensor]:
+                debug: bool = False, strict_fp32: bool = False, check_overflow: bool = False) -> Dict[str, torch.Tensor]:
         """`data`: bbox_hand, bbox_hand_rect, bbox_obj, bbox_obj_rect (bs, 4), is_right (bs,) bool, gravity (bs, 1, 3) or (bs, 3)
-        -- the reference's batch keys (VPHO.py:113-160)."""
+        -- the reference's batch keys (VPHO.py:113-160).
+        strict_fp32: the FP32 SIMT kernels (VPHO_HEADS_STRICT_FP32) instead of the tcgen05 path -- cross-checks, and the only
+        path of the emulator build.  check_overflow: synchronise and raise if an activation left the FP16 range of the
+        tensor-core operand planes (|v| >= 60000; never the case for BatchNorm-ed features of a trained network)."""
         dev = hf_hr.device
         bs, Cc, roi, roi2 = hf_hr.shape
         if Cc != self.C or roi != roi2 or of_or_rect.shape != hf_hr.shape or hf_hr_rect.shape != hf_hr.shape:
@@ -112,9 +115,15 @@ class FeatureHeads:
                            obj_heatmap=P(out["obj_heatmap"]), encoding_hand=P(out["encoding_hand"]),
                            encoding_obj=P(out["encoding_obj"]), mano_pose=P(out["mano_pose"]), mano_shape=P(out["mano_shape"]),
                            force_local=P(out["force_local"]), force_scale=P(out["scale"]), force_weight=P(out["weight"]),
-                           CoM=P(out["CoM"]), enc_phy_hand=P(out.get("enc_phy_hand")), enc_phy_obj=P(out.get("enc_phy_obj")))
+                           CoM=P(out["CoM"]), enc_phy_hand=P(out.get("enc_phy_hand")), enc_phy_obj=P(out.get("enc_phy_obj")),
+                           flags=1 if strict_fp32 else 0)
         self.lib.check(self.lib.c.vpho_heads_forward(self.handle, C.byref(a), P(self._ws), self._ws.numel(), capi.stream_of(hf_hr)),
                        "vpho_heads_forward")
+        if check_overflow and not strict_fp32:
+            flag = C.c_int32(0)
+            self.lib.check(self.lib.c.vpho_heads_overflow(self.handle, C.byref(flag), capi.stream_of(hf_hr)), "vpho_heads_overflow")
+            if flag.value:
+                raise capi.VphoError("FeatureHeads: activation outside the FP16 range of the tensor-core planes; use strict_fp32=True")
         return out
 
     __call__ = forward

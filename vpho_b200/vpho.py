@@ -72,6 +72,34 @@ class VphoHotPath:
             hi = fused(native, n_in, bs * S)
         return hi, hf
 
+    # ---- N1: vpho_net.forward from the RoI-aligned feature maps (VPHO.py:129-304) ----
+    def attach_feature_heads(self, state: Dict) -> "VphoHotPath":
+        """`state`: the reference's state dict (or the `rest` part `vpho_b200.checkpoint.load_denoiser_states` returns) holding
+        head_hm_*, encoder_*, head_mano, cross_*, head_physics.  After this `predict_from_features` is available."""
+        from .producers import FeatureHeads
+        self.feature_heads = FeatureHeads(state, lib=self.lib)
+        return self
+
+    @torch.no_grad()
+    def predict_from_features(self, hf_hr: torch.Tensor, of_or_rect: torch.Tensor, hf_hr_rect: torch.Tensor, batch: Dict, **kw) -> Dict:
+        """The predict branch of `vpho_net.forward` from the four RoI-aligned maps on (VPHO.py:129-304; `of_or` is not
+        consumed there): the producers (`FeatureHeads`, one C call) write encodings, heat-maps, regression pose and local
+        forces on the device and `predict` consumes them in place -- no heat-map ever crosses PCIe.  `batch` carries the
+        dataset fields (bbox_hand[_rect], bbox_obj[_rect], is_right, gravity, cam_intr_crop_flip, root_joint[_flip], is_grasped,
+        obj_id / obj_name).  Also returns `reg_hand_vert` / `reg_hand_joint` / `hand_heatmap` / `obj_heatmap` / `force_local`
+        like the reference's pd_dt (VPHO.py:230-234)."""
+        if getattr(self, "feature_heads", None) is None:
+            raise capi.VphoError("predict_from_features: call attach_feature_heads(state) first")
+        f = self.feature_heads(hf_hr, of_or_rect, hf_hr_rect, batch)
+        b = dict(batch)
+        b.update(encoding_hand=f["encoding_hand"], encoding_obj=f["encoding_obj"], pd_mano_pose=f["mano_pose"],
+                 pd_mano_shape=f["mano_shape"], hm_hand=f["hand_heatmap"], hm_obj=f["obj_heatmap"], force_local=f["force_local"])
+        pd = self.predict(to_device(b, hf_hr.device), **kw)
+        rv, rj = self.head_mano.get_hand_verts(pose=f["mano_pose"], shape=f["mano_shape"])
+        pd.update(reg_hand_vert=rv, reg_hand_joint=rj, hand_heatmap=f["hand_heatmap"], obj_heatmap=f["obj_heatmap"],
+                  force_local=f["force_local"])
+        return pd
+
     @torch.no_grad()
     def predict(self, batch: Dict, *, prior_hand: Optional[torch.Tensor] = None, prior_obj: Optional[torch.Tensor] = None,
                 with_inprocess: bool = True, prefetch=None, defer_join: bool = False) -> Dict:

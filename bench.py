@@ -792,13 +792,74 @@ def config5_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def config6_arm(args):
+    """SURVEY §8f row N1 (the step before the hot path): heat-map heads, encoders, regression head, cross modules and physics head
+    (lib/model/VPHO.py:129-178) on the RoI-aligned features of 64 images, `vpho_heads_forward`.  Both CUDA paths are timed (the
+    tcgen05 product path and the strict-FP32 SIMT cross-check); the CPU baseline is the oracle port on a bounded sample."""
+    import importlib.util
+    from vpho_b200 import capi
+    from vpho_b200 import synthetic as syn
+    from vpho_b200.producers import FeatureHeads
+    spec = importlib.util.spec_from_file_location("producers_bench", os.path.join(ROOT, "tools", "producers_bench.py"))
+    pb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pb)
+    lib = capi.lib()
+    peaks = _peaks(lib)
+    clocks = ClockSampler(torch.cuda.current_device())
+    clocks.start()
+    st = syn.make_producer_state(0)
+    fh = FeatureHeads(st)
+    inp = syn.make_producer_inputs(BS, 1)
+    T = {k: torch.from_numpy(np.asarray(v)).cuda() for k, v in inp.items()}
+    res = {}
+    t0 = time.perf_counter()
+    for name, strict in (("tcgen05", False), ("fp32_simt", True)):
+        ms = _timed(lambda: fh(T["hf_hr"], T["of_or_rect"], T["hf_hr_rect"], T, strict_fp32=strict), reps=max(args.steps, 5), warm=max(args.warmup, 3))
+        res[name] = ms
+    t1 = time.perf_counter()
+    clocks.stop_flag.set()
+    flop = pb.producers_flop(syn.PRODUCER_DIMS, BS)
+    ms = res["tcgen05"]
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import producers as OP
+        n_cpu = 8
+        small = {k: v[:n_cpu] for k, v in inp.items()}
+        OP.oracle_producers(st, **small)
+        c0 = time.perf_counter()
+        OP.oracle_producers(st, **small)
+        dt = time.perf_counter() - c0
+        cpu = {"value": round(n_cpu / dt, 2), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"oracle/producers.py (the reference's own torch ops) on {n_cpu} of the {BS} images after one warm pass, {dt:.1f} s; "
+                         "the cross modules attend across the batch, so the sample is its own batch"}
+    line = {"metric": "images/sec through the feature-side producers (heat-map heads, encoders, regression / cross / physics heads)",
+            "value": round(BS / ms * 1e3, 1), "unit": "images/s", "n_gpus": 1, "steps": max(args.steps, 5), "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3 x f16 UMMA split)",
+            "data": "synthetic",
+            "config": {"workload": "SURVEY 8f N1: vpho_net.forward lib/model/VPHO.py:129-178 on RoI features (64, 256, 32, 32) x 3, "
+                                   "reference widths, random weights with O(1) activations",
+                       "l2": "inputs 3 x 67 MB of features re-read every call (> L2)"},
+            "roofline": {"kernel": "k_gemm_tc (implicit-GEMM convolutions / linears of the whole call)", "bound": "tensor",
+                         "achieved": round(flop / ms / 1e9, 2), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": round(flop / ms / 1e9 / peaks["bf16_tflops"], 4), "traffic": None,
+                         "note": "whole-call algorithmic FLOP (2 x multiply-adds of every dense layer) over the whole call's time; each FLOP is "
+                                 "3 kind::f16 UMMAs; 1x1 convolutions are bound by their epilogue traffic (activations as hi/lo planes)",
+                         "flop_per_call": flop},
+            "paths_ms": {k: round(v, 4) for k, v in res.items()},
+            "fp32_simt": {"tflops": round(flop / res["fp32_simt"] / 1e9, 2), "frac_fp32_peak": round(flop / res["fp32_simt"] / 1e9 / peaks["fp32_fma_tflops"], 4)
+                          if peaks.get("fp32_fma_tflops") else None},
+            "cpu_baseline": cpu, "peaks": peaks, "clocks": clocks.summary([(t0, t1)]), "gpu_launches": int(lib.c.vpho_launch_count())}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5, 6],
+                    help="1-5: BASELINE.json configs[0..4]; 6: SURVEY 8f row N1 (feature-side producers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline", type=int, default=1, choices=[0, 1],
                     help="1: consecutive batches software-pipelined (batch i's aggregation under batch i+1's samplers); 0: each "
@@ -819,10 +880,10 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
-    if args.config in (3, 5):
+    if args.config in (3, 5, 6):
         if rank == 0:
             torch.cuda.set_device(local_rank)
-            (config3_arm if args.config == 3 else config5_arm)(args)
+            {3: config3_arm, 5: config5_arm, 6: config6_arm}[args.config](args)
         return
     cuda_arm(args, rank, world, local_rank)
 

@@ -269,12 +269,18 @@ __global__ void __launch_bounds__(256) k_maxpool2(const float* __restrict__ in, 
 }
 
 // Gravity token + positional table (cross_module.py:125-131): row 2F of every image = gravity_proj(PosEmbedder(flipped gravity));
-// then x[img][r][:] += pe[img][:] for all 2F + 1 rows.  One CTA per image.
+// then x[img][r][:] += pe[img][:] for all 2F + 1 rows.  Grid (images, slices): slice s adds the table to its share of the rows,
+// the last slice also forms the gravity row (written with its table entry already added).
 __global__ void __launch_bounds__(256) k_gravity_pe(const float* __restrict__ gravity, const unsigned char* __restrict__ is_right,
                                                     const float* __restrict__ Wg, const float* __restrict__ bg,
                                                     const float* __restrict__ pe, int n_tok, int d, float* __restrict__ x) {
-  __shared__ float emb[63];
-  const int img = blockIdx.x;
+  __shared__ float emb[64];
+  const int img = blockIdx.x, ns = gridDim.y, sl = blockIdx.y;
+  const int rows = n_tok - 1, r0 = (int)((long long)rows * sl / ns), r1 = (int)((long long)rows * (sl + 1) / ns);
+  float* xi = x + (long long)img * n_tok * d;
+  const float* pi = pe + (long long)img * d;
+  for (int i = r0 * d + threadIdx.x; i < r1 * d; i += blockDim.x) xi[i] += pi[i % d];
+  if (sl != ns - 1) return;
   if (threadIdx.x < 3) {
     float g = gravity[img * 3 + threadIdx.x];
     if (threadIdx.x == 0 && !is_right[img]) g = -g;          // flip_point3d_by_mask_index (VPHO.py:359-364)
@@ -285,15 +291,18 @@ __global__ void __launch_bounds__(256) k_gravity_pe(const float* __restrict__ gr
       emb[3 + q * 6 + 3 + threadIdx.x] = cosf(g * f);
     }
   }
+  if (threadIdx.x == 63) emb[63] = 0.f;
   __syncthreads();
-  float* row = x + ((long long)img * n_tok + (n_tok - 1)) * d;
-  for (int o = threadIdx.x; o < d; o += blockDim.x) {
-    float acc = 0.f;
-    for (int k = 0; k < 63; ++k) acc = fmaf(emb[k], Wg[o * 63 + k], acc);
-    row[o] = acc + bg[o];
+  float* row = xi + (long long)rows * d;
+  // one warp per output: lanes over the 63 inputs (coalesced rows of Wg), fixed-order shuffle reduction
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < d; o += nw) {
+    float acc = emb[lane] * Wg[o * 63 + lane];
+    if (lane + 32 < 63) acc = fmaf(emb[lane + 32], Wg[o * 63 + lane + 32], acc);
+#pragma unroll
+    for (int s2 = 16; s2; s2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s2);
+    if (lane == 0) row[o] = acc + bg[o] + pi[o];
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n_tok * d; i += blockDim.x) x[(long long)img * n_tok * d + i] += pe[(long long)img * d + (i % d)];
 }
 
 // Self-attention of nn.TransformerEncoderLayer with batch_first = False on x (L = images, N = tokens, E): for token n and head
@@ -339,6 +348,69 @@ __global__ void __launch_bounds__(256) k_attention(const float* __restrict__ qkv
     float acc = 0.f;
     for (int l = 0; l < L; ++l) acc = fmaf(sc[l], qkv[((long long)l * N + n) * 3 * E + 2 * E + h * hd + i], acc);
     out[((long long)lq * N + n) * E + h * hd + i] = acc;
+  }
+}
+
+// The same attention with one CTA per (token n, head h): K and V of the L images are staged once in shared memory (row stride
+// hd + 1: lanes walk different rows conflict-free) and every warp serves queries lq = warp, warp + 8, ...  Used when
+// 2 L (hd + 1) floats fit in shared memory (the per-query kernel re-reads K and V from L2 for every query).
+__global__ void __launch_bounds__(256) k_attention_tile(const float* __restrict__ qkv, int L, int N, int E, int nhead, float* __restrict__ out) {
+  VPHO_DYN_SMEM(float, sm);       // K [L][hd + 1], V [L][hd + 1], per warp: q [hd], p [L]
+  const int n = blockIdx.x, h = blockIdx.y, hd = E / nhead, ld = hd + 1;
+  float* Ks = sm;
+  float* Vs = sm + (size_t)L * ld;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float* qs = Vs + (size_t)L * ld + (size_t)warp * (hd + L);
+  float* ps = qs + hd;
+  if (hd % 4 == 0) {
+    for (int i = threadIdx.x; i < L * hd / 4; i += blockDim.x) {
+      const int l = (i * 4) / hd, c = i * 4 - l * hd;
+      const float* src = qkv + ((long long)l * N + n) * 3 * E + h * hd + c;
+      const float4 k4 = *reinterpret_cast<const float4*>(src + E), v4 = *reinterpret_cast<const float4*>(src + 2 * E);
+      float* kd = Ks + l * ld + c;
+      float* vd = Vs + l * ld + c;
+      kd[0] = k4.x; kd[1] = k4.y; kd[2] = k4.z; kd[3] = k4.w;
+      vd[0] = v4.x; vd[1] = v4.y; vd[2] = v4.z; vd[3] = v4.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < L * hd; i += blockDim.x) {
+      const int l = i / hd, c = i - l * hd;
+      const float* src = qkv + ((long long)l * N + n) * 3 * E + h * hd + c;
+      Ks[l * ld + c] = src[E];
+      Vs[l * ld + c] = src[2 * E];
+    }
+  }
+  __syncthreads();
+  const float scale = 1.0f / sqrtf((float)hd);
+  for (int lq = blockIdx.z * nw + warp; lq < L; lq += nw * gridDim.z) {       // grid.z slices of the queries
+    const float* q = qkv + ((long long)lq * N + n) * 3 * E + h * hd;
+    for (int i = lane; i < hd; i += 32) qs[i] = q[i] * scale;
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int l = lane; l < L; l += 32) {
+      float acc = 0.f;
+      for (int i = 0; i < hd; ++i) acc = fmaf(qs[i], Ks[l * ld + i], acc);
+      ps[l] = acc;
+      mx = fmaxf(mx, acc);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int l = lane; l < L; l += 32) {
+      const float e = expf(ps[l] - mx);
+      ps[l] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    __syncwarp();
+    for (int i = lane; i < hd; i += 32) {
+      float acc = 0.f;
+      for (int l = 0; l < L; ++l) acc = fmaf(ps[l] * inv, Vs[l * ld + i], acc);
+      out[((long long)lq * N + n) * E + h * hd + i] = acc;
+    }
+    __syncwarp();
   }
 }
 
@@ -691,6 +763,27 @@ int linear(const DevMat& w, const float* in, int rows, int lda, float slope, con
   return run_gemm(op, st);
 }
 
+int run_attention(const float* qkv, int L, int N, int E, int nhead, float* out, cudaStream_t st) {
+  const int hd = E / nhead;
+  const size_t tile = ((size_t)2 * L * (hd + 1) + (size_t)8 * (hd + L)) * sizeof(float);
+  if (tile <= 200 * 1024) {
+#ifndef VPHO_EMU
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+      if (cudaFuncSetAttribute(k_attention_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return VPHO_ERR_LAUNCH;
+      attr_done[dev] = true;
+    }
+#endif
+    VPHO_LAUNCH(k_attention_tile, dim3(N, nhead, L >= 32 ? 4 : 1), dim3(256), tile, st, qkv, L, N, E, nhead, out);
+  } else {
+    VPHO_LAUNCH(k_attention, dim3(L, nhead, N), dim3(256), (size_t)(L + hd) * sizeof(float), st, qkv, L, N, E, nhead, out);
+  }
+  VPHO_CHECK_LAUNCH();
+  return VPHO_OK;
+}
+
 int grid_for(long long total) { return (int)std::min<long long>((total + 255) / 256, 148 * 16); }
 
 struct Ws {
@@ -803,12 +896,11 @@ int run_cross(const vpho_heads* h, const CrossW& c, const vpho_heads_args* a, co
   int rc;
   if ((rc = conv(c.proj_hand, 3, w.pool1_hand, h->enc_hid * s, bs, h->enc_hid, H, H, 1.f, nullptr, nullptr, w.tok, tok_stride, st))) return rc;
   if ((rc = conv(c.proj_obj, 3, w.pool1_obj, h->enc_hid * s, bs, h->enc_hid, H, H, 1.f, nullptr, nullptr, w.tok + (long long)F * d, tok_stride, st))) return rc;
-  VPHO_LAUNCH(k_gravity_pe, dim3(bs), dim3(256), 0, st, a->gravity, a->is_right, c.Wg, c.bg, c.pe, ntok, d, w.tok);
+  VPHO_LAUNCH(k_gravity_pe, dim3(bs, 8), dim3(256), 0, st, a->gravity, a->is_right, c.Wg, c.bg, c.pe, ntok, d, w.tok);
   VPHO_CHECK_LAUNCH();
   if ((rc = linear(c.in_proj, w.tok, rows, d, 1.f, nullptr, w.qkv, 3 * d, st))) return rc;
   const int nhead = 2;
-  VPHO_LAUNCH(k_attention, dim3(bs, nhead, ntok), dim3(256), (size_t)(bs + d / nhead) * sizeof(float), st, w.qkv, bs, ntok, d, nhead, w.att);
-  VPHO_CHECK_LAUNCH();
+  if ((rc = run_attention(w.qkv, bs, ntok, d, nhead, w.att, st))) return rc;
   if ((rc = linear(c.out_proj, w.att, rows, d, 1.f, w.tok, w.tmp, d, st))) return rc;           // x + sa(x)
   VPHO_LAUNCH(k_layernorm, dim3(rows), dim3(128), 0, st, w.tmp, c.n1w, c.n1b, d, w.tok);
   VPHO_CHECK_LAUNCH();
@@ -950,7 +1042,7 @@ int run_cross_tc(const vpho_heads* h, const CrossW& c, const vpho_heads_args* a,
   p = tc_conv_op(h, c.proj_obj, 3, bs, H, H, 1.f);
   p.out_f32 = w.tok + (long long)F * d; p.f32_img_stride = (long long)ntok * d;
   if ((rc = pt_gemm(c.proj_obj.tc, p, P1o.hi, P1o.lo, st))) return rc;
-  VPHO_LAUNCH(k_gravity_pe, dim3(bs), dim3(256), 0, st, a->gravity, a->is_right, c.Wg, c.bg, c.pe, ntok, d, w.tok);
+  VPHO_LAUNCH(k_gravity_pe, dim3(bs, 8), dim3(256), 0, st, a->gravity, a->is_right, c.Wg, c.bg, c.pe, ntok, d, w.tok);
   VPHO_CHECK_LAUNCH();
   auto rows_op = [&](const DevMat& m, float slope) {
     TcGemm q = tc_base(h, m, slope);
@@ -962,8 +1054,7 @@ int run_cross_tc(const vpho_heads* h, const CrossW& c, const vpho_heads_args* a,
   p.out_f32 = w.qkv; p.ldc = 3 * d;
   if ((rc = pt_gemm(c.in_proj.tc, p, TOK.hi, TOK.lo, st))) return rc;
   const int nhead = 2;
-  VPHO_LAUNCH(k_attention, dim3(bs, nhead, ntok), dim3(256), (size_t)(bs + d / nhead) * sizeof(float), st, w.qkv, bs, ntok, d, nhead, w.att);
-  VPHO_CHECK_LAUNCH();
+  if ((rc = run_attention(w.qkv, bs, ntok, d, nhead, w.att, st))) return rc;
   if ((rc = pt_split_rows(w.att, (long long)nt, ATT.hi, ATT.lo, st))) return rc;
   p = rows_op(c.out_proj, 1.f);
   p.res_f32 = w.tok; p.out_f32 = w.tmp; p.ldc = d;                                             // x + sa(x)

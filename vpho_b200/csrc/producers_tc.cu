@@ -56,7 +56,8 @@ struct PtSmemLayout {
   static constexpr int kB = BN * 128;
   static constexpr int kStage = 2 * kA + 2 * kB;
   static constexpr int kStages = NST;
-  static constexpr int kBytes = kStages * kStage + 1024 /* alignment */ + 256 /* barriers */;
+  static constexpr int kParams = 5 * BN * 4;             // bias, post scale / shift, pre scale / shift of the CTA's columns
+  static constexpr int kBytes = kStages * kStage + 1024 /* alignment */ + 256 /* barriers */ + kParams;
 };
 
 // NST = 3: deep pipeline, one CTA per SM (long K: 3x3 convolutions).  NST = 1: 64 KB of shared memory, two CTAs per SM whose
@@ -73,6 +74,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUt
   unsigned long long* empty = bars + L::kStages;
   unsigned long long* acc_full = bars + 2 * L::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * L::kStages + 1);
+  float* par = reinterpret_cast<float*>(base + L::kStages * L::kStage + 256);     // [5][BN]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = blockIdx.x, n0 = blockIdx.y * BN;
   constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -171,6 +173,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUt
     }
     const int OH = p.H * p.os, OW = p.W * p.os, oy = y * p.os + p.py, ox = x * p.os + p.px;
     const long long opix = p.mode ? ((long long)img * OH + oy) * OW + ox : m;        // output pixel / row index
+    // per-column epilogue constants -> shared memory while the main loop runs (the epilogue warps are idle until then)
+    for (int i = tid - 128; i < BN; i += 128) {
+      const int n = n0 + i;
+      const bool ok = n < p.N;
+      par[i] = (ok && p.bias) ? p.bias[n] : 0.f;
+      par[BN + i] = (ok && p.post_scale) ? p.post_scale[n] : 1.f;
+      par[2 * BN + i] = (ok && p.post_scale) ? p.post_shift[n] : 0.f;
+      par[3 * BN + i] = (ok && p.out2_hi) ? p.pre_scale[n] : 0.f;
+      par[4 * BN + i] = (ok && p.out2_hi) ? p.pre_shift[n] : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     mbar_wait(acc_full, 0);
     tc_fence_after();
     bool over = false;
@@ -186,8 +199,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUt
         const int n = nb + j;
         float val = 0.f;
         if (n < p.N) {
-          val = fmaf(__uint_as_float(v1[j]), kLoInv, __uint_as_float(v0[j])) * p.unscale + (p.bias ? p.bias[n] : 0.f);
-          if (p.post_scale) val = fmaf(val, p.post_scale[n], p.post_shift[n]);
+          val = fmaf(__uint_as_float(v1[j]), kLoInv, __uint_as_float(v0[j])) * p.unscale + par[g * 16 + j];
+          val = fmaf(val, par[BN + g * 16 + j], par[2 * BN + g * 16 + j]);
           val = val >= 0.f ? val : val * p.slope;
         }
         o[j] = val;
@@ -228,7 +241,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUt
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float t = 0.f;
-          if (nb + j < p.N) { t = fmaf(o[j], p.pre_scale[nb + j], p.pre_shift[nb + j]); t = t >= 0.f ? t : t * p.pre_slope; }
+          if (nb + j < p.N) { t = fmaf(o[j], par[3 * BN + g * 16 + j], par[4 * BN + g * 16 + j]); t = t >= 0.f ? t : t * p.pre_slope; }
           split_half(t, hh[j], ll[j]);
         }
         uint4* dh = reinterpret_cast<uint4*>(p.out2_hi + opix * p.out_cp + nb);
@@ -311,12 +324,15 @@ __global__ void __launch_bounds__(256) k_to_planes(const float* __restrict__ fea
   }
   __syncthreads();
   const long long o0 = ((long long)img * roi + y) * roi * Cp;
-  for (int i = threadIdx.x; i < Cp * roi; i += blockDim.x) {
-    const int x = i / Cp, c = i - x * Cp;
-    __half h, l;
-    split_half(tile[x * ld + c], h, l);
-    hi[o0 + i] = h;
-    lo[o0 + i] = l;
+  for (int i = threadIdx.x; i < Cp * roi / 8; i += blockDim.x) {       // 8 channels = 16 bytes per plane per thread
+    const int x = (i * 8) / Cp, c = i * 8 - x * Cp;
+    uint4 ph, pl;
+    __half* hh = reinterpret_cast<__half*>(&ph);
+    __half* ll = reinterpret_cast<__half*>(&pl);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split_half(tile[x * ld + c + e], hh[e], ll[e]);
+    *reinterpret_cast<uint4*>(hi + o0 + (long long)i * 8) = ph;
+    *reinterpret_cast<uint4*>(lo + o0 + (long long)i * 8) = pl;
   }
 }
 
@@ -478,7 +494,9 @@ int pt_gemm(const TcWeights& w, TcGemm p, const __half* a_hi, const __half* a_lo
     if (!make_map_rows(&ma_hi, a_hi, p.M, w.Kp, 128) || !make_map_rows(&ma_lo, a_lo, p.M, w.Kp, 128)) return VPHO_ERR_LAUNCH;
   }
   if (m_tiles <= 0) return VPHO_OK;
-  const bool short_k = p.ntap * p.chunks <= 4;      // 1x1 convolutions / narrow linears: two CTAs per SM instead of a deep pipeline
+  // 1x1 convolutions / narrow linears on grids of more than two waves: two CTAs per SM (64 KB each) whose phases interleave;
+  // everything else (long K, or grids that leave SMs free anyway): one CTA per SM with the deep pipeline
+  const bool short_k = p.ntap * p.chunks <= 4 && (long long)m_tiles * (w.Npad / w.BN) > 2 * 148;
   switch (w.BN) {
     case 128: return short_k ? launch_bn<128, 1>(ma_hi, ma_lo, w, p, m_tiles, st) : launch_bn<128, 3>(ma_hi, ma_lo, w, p, m_tiles, st);
     case 64: return short_k ? launch_bn<64, 1>(ma_hi, ma_lo, w, p, m_tiles, st) : launch_bn<64, 4>(ma_hi, ma_lo, w, p, m_tiles, st);

@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "vpho_b200", "csrc")
 LIB = os.path.join(CSRC, "libvpho_b200.so")
 LIB_BOUNDS = os.path.join(CSRC, "libvpho_b200_bounds.so")      # -DVPHO_DEBUG_BOUNDS twin, used by tests/test_bounds_build.py only
+LIB_TIMELINE = os.path.join(CSRC, "libvpho_b200_timeline.so")  # -DVPHO_TC_TIMELINE twin, used by tools/diag_*_timeline.py only
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -29,13 +30,13 @@ def _stale(lib: str = LIB) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, bounds: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, bounds: bool = False, timeline: bool = False) -> str:
     """Compile every .cu under csrc/ for sm_100a into one shared library (object per file, parallel).
     bounds=True: the index-asserting twin (VPHO_BOUNDS in vpho_common.cuh) -> libvpho_b200_bounds.so."""
-    LIB = LIB_BOUNDS if bounds else globals()["LIB"]
+    LIB = LIB_BOUNDS if bounds else LIB_TIMELINE if timeline else globals()["LIB"]
     if not force and not _stale(LIB):
         return LIB
-    objdir = os.path.join(CSRC, "build_bounds" if bounds else "build")
+    objdir = os.path.join(CSRC, "build_bounds" if bounds else "build_timeline" if timeline else "build")
     os.makedirs(objdir, exist_ok=True)
     flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
              "-I", os.path.join(ROOT, "include"), "-I", CSRC] + ARCH
@@ -43,7 +44,7 @@ def build(force: bool = False, verbose: bool = False, bounds: bool = False) -> s
         flags += ["-DVPHO_DEBUG_BOUNDS"]
     if verbose:
         flags += ["-Xptxas", "-v"]
-    if os.environ.get("VPHO_TC_TIMELINE"):
+    if timeline or os.environ.get("VPHO_TC_TIMELINE"):
         flags += ["-DVPHO_TC_TIMELINE"]
     procs = []
     objs = []
@@ -69,4 +70,5 @@ def build(force: bool = False, verbose: bool = False, bounds: bool = False) -> s
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, bounds="--bounds" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, bounds="--bounds" in sys.argv,
+                timeline="--timeline" in sys.argv))

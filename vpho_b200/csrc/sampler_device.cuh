@@ -199,6 +199,67 @@ __device__ __forceinline__ void stage_input4(const SamplerWs& ws, const StageSca
   }
 }
 
+// stage_input4 in two halves, for callers that keep several units' loads in flight before the float64 arithmetic starts
+// (the fused pose-encoder kernel: the load latency of one unit is otherwise paid once per unit).  `ns` is the number of K
+// slots that enter (host-known from mode / s: stage_ns); the arithmetic is stage_input4's, operation for operation.
+struct StageRaw {
+  double2 y01, y23;
+  float4 kv[6];
+};
+__host__ __device__ __forceinline__ int stage_ns(int mode, int s) {
+  return mode == kModeInit1 ? 1 : (mode == kModeStage ? ((s == 6) ? 6 : s) : 0);
+}
+__device__ __forceinline__ void stage_load4(const SamplerWs& ws, int mode, int ns, int i, int n, StageRaw& r) {
+  if (mode == kModeEval) {
+    r.kv[0] = *reinterpret_cast<const float4*>(ws.eval_x + i);
+    return;
+  }
+  r.y01 = *reinterpret_cast<const double2*>(ws.y + i);
+  r.y23 = *reinterpret_cast<const double2*>(ws.y + i + 2);
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+    if (j < ns) r.kv[j] = *reinterpret_cast<const float4*>(ws.K + (size_t)j * n + i);
+}
+__device__ __forceinline__ void stage_math4(const SamplerWs& ws, const StageScalars& q, int mode, int s, int i, const StageRaw& r,
+                                            float* out) {
+  if (mode == kModeEval) {
+    out[0] = r.kv[0].x; out[1] = r.kv[0].y; out[2] = r.kv[0].z; out[3] = r.kv[0].w;
+    return;
+  }
+  const double y[4] = {r.y01.x, r.y01.y, r.y23.x, r.y23.y};
+  if (q.ns == 0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[e] = (float)y[e];
+    return;
+  }
+  double v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (mode == kModeInit1) {
+      const float k0 = e == 0 ? r.kv[0].x : e == 1 ? r.kv[0].y : e == 2 ? r.kv[0].z : r.kv[0].w;
+      double kvv = -(q.kc[0] * (double)k0);
+      if (q.nanf[0] && !isfinite(kvv)) kvv = 0.0;
+      v[e] = __dadd_rn(y[e], __dmul_rn(q.h, kvv));
+    } else {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (j < q.ns) {
+          const float kj = e == 0 ? r.kv[j].x : e == 1 ? r.kv[j].y : e == 2 ? r.kv[j].z : r.kv[j].w;
+          double kvv = -(q.kc[j] * (double)kj);
+          if (q.nanf[j] && !isfinite(kvv)) kvv = 0.0;
+          acc += kvv * q.a[j];
+        }
+      v[e] = __dadd_rn(y[e], __dmul_rn(acc, q.h));
+    }
+    out[e] = (float)v[e];
+  }
+  if (mode == kModeStage && s == 6) {
+    *reinterpret_cast<double2*>(ws.ynew + i) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(ws.ynew + i + 2) = make_double2(v[2], v[3]);
+  }
+}
+
 // round-to-nearest (ties to even) onto the 10-bit TF32 mantissa, result kept in a float container
 __host__ __device__ __forceinline__ float tf32_round(float x) {
   unsigned u;

@@ -392,13 +392,18 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 }
 
 // =====================================================================================================================
-// Pose encoder on tensor cores: P2 = relu(relu(X.W1 + b1).W2 + b2) for one 128-row tile per CTA, both GEMMs as 3xTF32.
+// Pose encoder on tensor cores: P2 = relu(relu(X.W1 + b1).W2 + b2) for one 128-row tile per CTA.
 //   input    X = the float64 RK stage combination of the tile's state elements, formed by the compute warps and written as
-//            (hi, lo) TF32 planes straight into the swizzled A operand (no stage-input kernel, no global round trip);
-//   GEMM 1   D1[128x256] (TMEM cols 0..255) = X . W1, W1 (hi, lo) chunks of 32 k streamed by TMA;
-//   re-stage compute warps read D1 32 columns at a time (tcgen05.ld), add b1, ReLU, split, and write the next A operand
-//            chunk of GEMM 2 (double-buffered, reusing the X region) while the MMA lane consumes the previous one;
-//   GEMM 2   D2[128x256] (TMEM cols 256..511) = H1 . W2;  epilogue: + b2, ReLU, split -> P2hi / P2lo (row-major).
+//            (hi, lo) TF32 planes straight into the swizzled A operand (no stage-input kernel, no global round trip).  The
+//            units are dealt chunk by chunk (32 k): every thread issues the loads of BOTH its units of a chunk before any
+//            arithmetic, and GEMM 1 starts on chunk kc while the compute warps form chunk kc + 1.  Nothing on this path waits
+//            for the controller words: addresses come from the kernel parameters, the scalars (step, weights, activity) are
+//            read by an otherwise idle warp and handed over through shared memory while the state loads are in flight.
+//   GEMM 1   D1[128x256] (TMEM cols 0..255) = X . W1 as 3xTF32, W1 (hi, lo) chunks of 32 k streamed by TMA;
+//   re-stage two passes over D1 (tcgen05.ld is cheap, registers are not: 640 threads leave 96 each): pass A the row maximum
+//            of relu(D1 + b1), pass B the scaled (hi, lo) FP16 split written as the next A operand chunk of GEMM 2
+//            (double-buffered, reusing the X region) while the MMA lane consumes the previous one;
+//   GEMM 2   D2[128x256] (TMEM cols 256..511) = H1 . W2 as 3xFP16;  epilogue: the same two passes -> P2hi / P2lo (row-major).
 // =====================================================================================================================
 constexpr int kPtMaxK1Chunks = 3;                         // D <= 96
 constexpr int kPtRegionA = kPtMaxK1Chunks * 2 * kTcABytes;   // X hi/lo chunks, later 2 x (H1 hi/lo chunk): 96 KB
@@ -407,17 +412,39 @@ constexpr int kPtStageB = 2 * kTcBBytes;                  // W (hi, lo) chunk: 6
 struct PtSmem {
   unsigned char a[kPtRegionA];
   unsigned char b[2][kPtStageB];
-  unsigned long long full_bar[2], empty_bar[2], a_full_bar[2], a_empty_bar[2], d1_full_bar, d2_full_bar, x_full_bar;
+  float b1s[kPDim];                // first-layer bias: static weights, staged before the PDL wait
+  StageScalars q;                  // controller scalars of this call (warp 3 -> compute warps, q_bar)
+  unsigned long long full_bar[2], empty_bar[2], a_full_bar[2], a_empty_bar[2], d1_full_bar, d2_full_bar, x_full_bar[kPtMaxK1Chunks], q_bar;
   uint32_t tmem_base;
+  int active;
 };
 
-__device__ __forceinline__ uint32_t sw128_offset(int r, int k) {     // byte offset of element (row r, k) in a [rows][32 f32] tile
-  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + (k & 3) * 4);
+// (hi, lo) __half split of 8 values scaled by the power of two `sc` -> two 16-byte units.  Two values per conversion
+// instruction (F2FP.PACK_AB); the products with `sc` are exact, so x - float(hi) cannot be changed by contraction.
+__device__ __forceinline__ void split8_f16(const float* x, float sc, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const float a = x[2 * p] * sc, b = x[2 * p + 1] * sc;
+    const __half2 h2 = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(a - f.x, b - f.y);
+    h[p] = *reinterpret_cast<const uint32_t*>(&h2);
+    l[p] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+
+// exact power-of-two scale that puts a row maximum into [2^13, 2^14), and its inverse
+__device__ __forceinline__ void row_scale(float rmax, float& sc, float& inv) {
+  sc = 1.f; inv = 1.f;
+  if (rmax > 0.f && rmax < 3.0e38f) {
+    int ex = 0;
+    frexpf(rmax, &ex);                           // rmax = m * 2^ex, m in [0.5, 1)
+    sc = ldexpf(1.f, 14 - ex);
+    inv = ldexpf(1.f, ex - 14);
+  }
 }
 
 __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const CUtensorMap* tmW1_lo, const CUtensorMap* tmW2_hi,
@@ -432,6 +459,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   PtSmem& sm = *reinterpret_cast<PtSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 128) clk_stamp(2, 1100);
   const int D = dn.D, nk1 = (D + kTcBK - 1) / kTcBK;
   const int r0 = tile * kTcBM;
   // GEMM 2 on FP16 planes: 4 chunks of 64 k, kind::f16, H1 re-staged as (hi, lo) halves scaled per row.  A chunk is 128-byte
@@ -443,97 +471,112 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
       mbar_init(&sm.full_bar[i], 1); mbar_init(&sm.empty_bar[i], 1);
       mbar_init(&sm.a_full_bar[i], 512); mbar_init(&sm.a_empty_bar[i], 1);
     }
-    mbar_init(&sm.d1_full_bar, 1); mbar_init(&sm.d2_full_bar, 1); mbar_init(&sm.x_full_bar, 512);
+    for (int i = 0; i < kPtMaxK1Chunks; ++i) mbar_init(&sm.x_full_bar[i], 512);
+    mbar_init(&sm.d1_full_bar, 1); mbar_init(&sm.d2_full_bar, 1); mbar_init(&sm.q_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  if (warp == 3) reinterpret_cast<float4*>(sm.b1s)[lane] = __ldg(reinterpret_cast<const float4*>(dn.b1) + lane),
+                 reinterpret_cast<float4*>(sm.b1s)[32 + lane] = __ldg(reinterpret_cast<const float4*>(dn.b1) + 32 + lane);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
   const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
   int sc_ = 1024;                                // timeline stamp slot of this thread (VPHO_TC_TIMELINE builds)
-  pdl_wait();                 // launched with launch_pdl: the set-up above overlaps the tail of k_stage_x
+  pdl_wait();                 // launched with launch_pdl: the set-up above overlaps the tail of the preceding kernel
   pdl_trigger();
   if (threadIdx.x == 0) clk_stamp(0, sc_++);
-  const bool active = eval_active(c, mode);
+  if (threadIdx.x == 128) clk_stamp(2, 1101);
 
-  if (!active) {
+  if (warp == 3) {
+    // the controller words of this call: one thread reads them while the compute warps' state loads are in flight
+    if (lane == 0) {
+      sm.active = eval_active(c, mode) ? 1 : 0;
+      sm.q = stage_scalars(c, mode, s);
+      mbar_arrive(&sm.q_bar);
+    }
   } else if (warp == 0) {
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      // (the X tile, A operand of GEMM 1, is written into its dedicated region by the compute warps)
-      for (int j = 0; j < nk1 + nk2; ++j) {
-        mbar_wait(&sm.empty_bar[stage], phase ^ 1);
-        clk_stamp(0, sc_++);
-        mbar_arrive_expect_tx(&sm.full_bar[stage], kPtStageB);
-        if (j < nk1) {
-          tma_load_2d(tmW1_hi, &sm.full_bar[stage], sm.b[stage], j * kTcBK, 0);
-          tma_load_2d(tmW1_lo, &sm.full_bar[stage], sm.b[stage] + kTcBBytes, j * kTcBK, 0);
-        } else {
-          tma_load_2d(tmW2_hi, &sm.full_bar[stage], sm.b[stage], (j - nk1) * kel2, 0);
-          tma_load_2d(tmW2_lo, &sm.full_bar[stage], sm.b[stage] + kTcBBytes, (j - nk1) * kel2, 0);
+      mbar_wait(&sm.q_bar, 0);
+      if (sm.active) {
+        int stage = 0;
+        uint32_t phase = 0;
+        // (the X tile, A operand of GEMM 1, is written into its dedicated region by the compute warps)
+        for (int j = 0; j < nk1 + nk2; ++j) {
+          mbar_wait(&sm.empty_bar[stage], phase ^ 1);
+          clk_stamp(0, sc_++);
+          mbar_arrive_expect_tx(&sm.full_bar[stage], kPtStageB);
+          if (j < nk1) {
+            tma_load_2d(tmW1_hi, &sm.full_bar[stage], sm.b[stage], j * kTcBK, 0);
+            tma_load_2d(tmW1_lo, &sm.full_bar[stage], sm.b[stage] + kTcBBytes, j * kTcBK, 0);
+          } else {
+            tma_load_2d(tmW2_hi, &sm.full_bar[stage], sm.b[stage], (j - nk1) * kel2, 0);
+            tma_load_2d(tmW2_lo, &sm.full_bar[stage], sm.b[stage] + kTcBBytes, (j - nk1) * kel2, 0);
+          }
+          if (++stage == 2) { stage = 0; phase ^= 1; }
         }
-        if (++stage == 2) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      auto mma_chunk = [&](uint32_t d_tmem, const unsigned char* a_hi_p, const unsigned char* a_lo_p, bool first) {
-        const uint64_t a_hi = make_kmajor_sw128_desc(a_hi_p), a_lo = make_kmajor_sw128_desc(a_lo_p);
-        const uint64_t b_hi = make_kmajor_sw128_desc(sm.b[stage]), b_lo = make_kmajor_sw128_desc(sm.b[stage] + kTcBBytes);
-#pragma unroll
-        for (int k = 0; k < kTcBK / kTcUmmaK; ++k) {
-          const uint64_t adv = (uint64_t)((k * kTcUmmaK * 4) >> 4);
-          umma_tf32(d_tmem, a_lo + adv, b_hi + adv, kTcIdesc, (first && k == 0) ? 0u : 1u);
-          umma_tf32(d_tmem, a_hi + adv, b_lo + adv, kTcIdesc, 1u);
-          umma_tf32(d_tmem, a_hi + adv, b_hi + adv, kTcIdesc, 1u);
-        }
-      };
-      mbar_wait(&sm.x_full_bar, 0);
-      clk_stamp(1, sc_++);
-      for (int kc = 0; kc < nk1; ++kc) {
-        mbar_wait(&sm.full_bar[stage], phase);
-        clk_stamp(1, sc_++);
-        tc_fence_after();
-        const unsigned char* chunk = sm.a + (size_t)kc * 2 * kTcABytes;
-        mma_chunk(d1, chunk, chunk + kTcABytes, kc == 0);
-        umma_commit(&sm.empty_bar[stage]);
-        if (++stage == 2) { stage = 0; phase ^= 1; }
-      }
-      umma_commit(&sm.d1_full_bar);
-      clk_stamp(1, sc_++);
-      for (int kc = 0; kc < nk2; ++kc) {
-        const int ab = kc & 1;
-        mbar_wait(&sm.full_bar[stage], phase);
-        clk_stamp(1, sc_++);
-        mbar_wait(&sm.a_full_bar[ab], (uint32_t)((kc >> 1) & 1));
-        clk_stamp(1, sc_++);
-        tc_fence_after();
-        const unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
-        {
-          const uint64_t a_hi = make_kmajor_sw128_desc(chunk), a_lo = make_kmajor_sw128_desc(chunk + kTcABytes);
+      mbar_wait(&sm.q_bar, 0);
+      if (sm.active) {
+        int stage = 0;
+        uint32_t phase = 0;
+        auto mma_chunk = [&](uint32_t d_tmem, const unsigned char* a_hi_p, const unsigned char* a_lo_p, bool first) {
+          const uint64_t a_hi = make_kmajor_sw128_desc(a_hi_p), a_lo = make_kmajor_sw128_desc(a_lo_p);
           const uint64_t b_hi = make_kmajor_sw128_desc(sm.b[stage]), b_lo = make_kmajor_sw128_desc(sm.b[stage] + kTcBBytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {                    // 4 x K16 inside the 128-byte row
-            const uint64_t adv = (uint64_t)((k * 32) >> 4);
-            umma_f16(d2, a_lo + adv, b_hi + adv, kTcIdescF16, (kc == 0 && k == 0) ? 0u : 1u);
-            umma_f16(d2, a_hi + adv, b_lo + adv, kTcIdescF16, 1u);
-            umma_f16(d2, a_hi + adv, b_hi + adv, kTcIdescF16, 1u);
+          for (int k = 0; k < kTcBK / kTcUmmaK; ++k) {
+            const uint64_t adv = (uint64_t)((k * kTcUmmaK * 4) >> 4);
+            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, kTcIdesc, (first && k == 0) ? 0u : 1u);
+            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, kTcIdesc, 1u);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, kTcIdesc, 1u);
           }
+        };
+        for (int kc = 0; kc < nk1; ++kc) {
+          mbar_wait(&sm.x_full_bar[kc], 0);
+          clk_stamp(1, sc_++);
+          mbar_wait(&sm.full_bar[stage], phase);
+          clk_stamp(1, sc_++);
+          tc_fence_after();
+          const unsigned char* chunk = sm.a + (size_t)kc * 2 * kTcABytes;
+          mma_chunk(d1, chunk, chunk + kTcABytes, kc == 0);
+          umma_commit(&sm.empty_bar[stage]);
+          if (++stage == 2) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&sm.empty_bar[stage]);
-        umma_commit(&sm.a_empty_bar[ab]);
-        if (++stage == 2) { stage = 0; phase ^= 1; }
+        umma_commit(&sm.d1_full_bar);
+        clk_stamp(1, sc_++);
+        for (int kc = 0; kc < nk2; ++kc) {
+          const int ab = kc & 1;
+          mbar_wait(&sm.full_bar[stage], phase);
+          clk_stamp(1, sc_++);
+          mbar_wait(&sm.a_full_bar[ab], (uint32_t)((kc >> 1) & 1));
+          clk_stamp(1, sc_++);
+          tc_fence_after();
+          const unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
+          {
+            const uint64_t a_hi = make_kmajor_sw128_desc(chunk), a_lo = make_kmajor_sw128_desc(chunk + kTcABytes);
+            const uint64_t b_hi = make_kmajor_sw128_desc(sm.b[stage]), b_lo = make_kmajor_sw128_desc(sm.b[stage] + kTcBBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                    // 4 x K16 inside the 128-byte row
+              const uint64_t adv = (uint64_t)((k * 32) >> 4);
+              umma_f16(d2, a_lo + adv, b_hi + adv, kTcIdescF16, (kc == 0 && k == 0) ? 0u : 1u);
+              umma_f16(d2, a_hi + adv, b_lo + adv, kTcIdescF16, 1u);
+              umma_f16(d2, a_hi + adv, b_hi + adv, kTcIdescF16, 1u);
+            }
+          }
+          umma_commit(&sm.empty_bar[stage]);
+          umma_commit(&sm.a_empty_bar[ab]);
+          if (++stage == 2) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&sm.d2_full_bar);
+        clk_stamp(1, sc_++);
       }
-      umma_commit(&sm.d2_full_bar);
-      clk_stamp(1, sc_++);
     }
   } else if (warp >= 4) {
     // 16 compute warps: warp 4+e owns TMEM lanes 32*(e&3).. (its hardware lane quarter) and column sub-block cs = e>>2
@@ -541,190 +584,210 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     // ---- stage input: the float64 RK stage combination of every state element of this tile (what scipy hands to `fun`,
     // stage_input), rounded to float32 and split into the (hi, lo) TF32 planes of GEMM 1's A operand, straight into the
-    // SWIZZLE_128B chunks (32 k per 128-byte row).  One thread = one 16-byte unit (4 consecutive k of a row); consecutive
-    // threads take consecutive units, so the K-slot reads are coalesced.  Rows past the end and k >= D are zero.
+    // SWIZZLE_128B chunks (32 k per 128-byte row).  One thread = two 16-byte units (4 consecutive k of a row) per chunk;
+    // consecutive threads take consecutive units, so the K-slot reads are coalesced.  Rows past the end and k >= D are zero.
+    bool active = true;
     {
       const int tcx = threadIdx.x - 128;                       // 0..511
-      const int upr = nk1 * (kTcBK / 4);                       // 16-byte units per row
-      const int n_rows = (mode == kModeEval) ? ws.eval_rows : c.n_rows;
-      const bool vec = (D & 3) == 0;                           // 16-byte aligned rows: vector loads, scalars hoisted
-      const StageScalars q4 = stage_scalars(c, mode, s);
-      const int n_state = (mode == kModeEval) ? n_rows * D : c.n;
-#pragma unroll 2
-      for (int u = tcx; u < kTcBM * upr; u += 512) {
-        const int rr = u / upr, kq = u - rr * upr;
-        float x4[4] = {0.f, 0.f, 0.f, 0.f}, hi4[4], lo4[4];
-        if (vec) {
-          if (r0 + rr < n_rows && 4 * kq < D) {
-            VPHO_BOUNDS((r0 + rr) * D + 4 * kq + 3 < n_state);
-            stage_input4(ws, q4, mode, s, (r0 + rr) * D + 4 * kq, n_state, x4);
+      const int n_rows = ws.eval_rows;                         // the sampler's row count (carve): no controller read needed
+      const int n_state = n_rows * D;
+      const int ns = stage_ns(mode, s);
+      const bool vec = (D & 3) == 0;                           // 16-byte aligned rows: vector loads
+      for (int kc = 0; kc < nk1; ++kc) {
+        StageRaw raw[2];
+        bool ok[2];
+        int idx[2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int w = tcx + 512 * b, rr = w >> 3, kq = kc * 8 + (w & 7);
+          idx[b] = (r0 + rr) * D + 4 * kq;
+          ok[b] = vec && r0 + rr < n_rows && 4 * kq < D;
+          if (ok[b]) {
+            VPHO_BOUNDS(idx[b] + 3 < n_state);
+            stage_load4(ws, mode, ns, idx[b], n_state, raw[b]);
           }
-        } else {
+        }
+        if (kc == 0) {
+          mbar_wait(&sm.q_bar, 0);
+          active = sm.active != 0;
+          if (threadIdx.x == 128) clk_stamp(2, 1102);
+          if (!active) break;
+        }
+        unsigned char* chunk = sm.a + (size_t)kc * 2 * kTcABytes;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int w = tcx + 512 * b, rr = w >> 3, ku = w & 7;
+          float x4[4] = {0.f, 0.f, 0.f, 0.f}, hi4[4], lo4[4];
+          if (ok[b]) {
+            stage_math4(ws, sm.q, mode, s, idx[b], raw[b], x4);
+          } else if (!vec) {
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const int k = 4 * (kc * 8 + ku) + e4;
+              x4[e4] = k < D ? (float)stage_input(ws, c, mode, s, r0 + rr, k, n_rows, D) : 0.f;
+            }
+          }
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
-            const int k = 4 * kq + e4;
-            x4[e4] = k < D ? (float)stage_input(ws, c, mode, s, r0 + rr, k, n_rows, D) : 0.f;
+            hi4[e4] = tf32_round(x4[e4]);
+            lo4[e4] = tf32_round(x4[e4] - hi4[e4]);
           }
-        }
-#pragma unroll
-        for (int e4 = 0; e4 < 4; ++e4) {
-          hi4[e4] = tf32_round(x4[e4]);
-          lo4[e4] = tf32_round(x4[e4] - hi4[e4]);
-        }
-        unsigned char* chunk = sm.a + (size_t)(kq >> 3) * 2 * kTcABytes;
-        const uint32_t off = (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128 + ((((kq & 7) ^ (rr & 7)) & 7) << 4));
-        *reinterpret_cast<float4*>(chunk + off) = make_float4(hi4[0], hi4[1], hi4[2], hi4[3]);
-        *reinterpret_cast<float4*>(chunk + kTcABytes + off) = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
-      }
-      fence_proxy_async();
-      mbar_arrive(&sm.x_full_bar);
-    }
-    // first-layer bias of this thread's 64 columns, fetched while GEMM 1 runs (its global-load latency would otherwise sit
-    // between "D1 complete" and the first re-staged chunk)
-    float hv[64];
-    {
-#pragma unroll
-      for (int kc = 0; kc < 4; ++kc)
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(dn.b1 + kc * 64 + cs * 16 + j4 * 4));
-          hv[kc * 16 + j4 * 4 + 0] = bv.x; hv[kc * 16 + j4 * 4 + 1] = bv.y; hv[kc * 16 + j4 * 4 + 2] = bv.z; hv[kc * 16 + j4 * 4 + 3] = bv.w;
-        }
-    }
-    mbar_wait(&sm.d1_full_bar, 0);
-    if (threadIdx.x == 128) clk_stamp(2, sc_++);
-    tc_fence_after();
-    float d2_unscale = 1.f;                        // undoes the operand scaling of GEMM 2
-    {
-      // ---- re-stage relu(D1 + b1) as FP16 (hi, lo) planes: this thread owns 16 columns of each 64-column chunk.  The 64
-      // activations stay in registers between the row-maximum exchange (power-of-two row scale, peak in [2^13, 2^14)) and
-      // the split, as in the epilogue below.
-#pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        uint32_t v[16];
-        tmem_ld16(d1 + lane_addr + (uint32_t)(kc * 64 + cs * 16), v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) hv[kc * 16 + j] = fmaxf(__uint_as_float(v[j]) + hv[kc * 16 + j], 0.f);
-      }
-      // second-layer bias into shared memory for the epilogue (the third X chunk is free once D1 is complete; ordered by
-      // the row-maximum barrier below)
-      float* b2s = reinterpret_cast<float*>(sm.a + 2 * 2 * kTcABytes + 4 * kTcBM * sizeof(float));
-      if (threadIdx.x - 128 < 64)
-        *reinterpret_cast<float4*>(b2s + (threadIdx.x - 128) * 4) = __ldg(reinterpret_cast<const float4*>(dn.b2) + (threadIdx.x - 128));
-      float rmax = 0.f;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) rmax = fmaxf(rmax, hv[j]);
-      float* rowmax = reinterpret_cast<float*>(sm.a + 2 * 2 * kTcABytes);      // third X chunk: free once D1 is complete
-      rowmax[cs * kTcBM + r] = rmax;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      rmax = fmaxf(fmaxf(rowmax[r], rowmax[kTcBM + r]), fmaxf(rowmax[2 * kTcBM + r], rowmax[3 * kTcBM + r]));
-      float sc = 1.f, inv = 1.f;
-      if (rmax > 0.f && rmax < 3.0e38f) {
-        int ex = 0;
-        frexpf(rmax, &ex);
-        sc = ldexpf(1.f, 14 - ex);
-        inv = ldexpf(1.f, ex - 14);
-      }
-      d2_unscale = inv * dn.W2scale_inv;
-#pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        const int ab = kc & 1;
-        mbar_wait(&sm.a_empty_bar[ab], (uint32_t)(((kc >> 1) & 1) ^ 1));
-        unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
-#pragma unroll
-        for (int u2 = 0; u2 < 2; ++u2) {
-          __align__(16) __half hi8[8], lo8[8];
-#pragma unroll
-          for (int ee = 0; ee < 8; ++ee) {
-            const float x = hv[kc * 16 + u2 * 8 + ee] * sc;
-            const __half h = __float2half_rn(x);
-            hi8[ee] = h;
-            lo8[ee] = __float2half_rn(x - __half2float(h));
-          }
-          const int u = cs * 2 + u2;                     // 16-byte unit (8 halves) inside the 128-byte row
-          const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((u ^ (r & 7)) & 7) << 4));
-          *reinterpret_cast<uint4*>(chunk + off) = *reinterpret_cast<const uint4*>(hi8);
-          *reinterpret_cast<uint4*>(chunk + kTcABytes + off) = *reinterpret_cast<const uint4*>(lo8);
+          const uint32_t off = (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128 + (((ku ^ (rr & 7)) & 7) << 4));
+          *reinterpret_cast<float4*>(chunk + off) = make_float4(hi4[0], hi4[1], hi4[2], hi4[3]);
+          *reinterpret_cast<float4*>(chunk + kTcABytes + off) = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
         }
         fence_proxy_async();
-        mbar_arrive(&sm.a_full_bar[ab]);
-        if (threadIdx.x == 128) clk_stamp(2, sc_++);
+        mbar_arrive(&sm.x_full_bar[kc]);
+        if (threadIdx.x == 128) clk_stamp(2, 1103 + (kc == nk1 - 1 ? 1 : 0));
       }
     }
-    // ---- epilogue: relu(D2 + b2) -> operand planes of the head GEMM, 64 columns per thread, ONE pass over TMEM: the
-    // 64 activations stay in registers between the row-maximum exchange and the split
-    mbar_wait(&sm.d2_full_bar, 0);
-    if (threadIdx.x == 128) clk_stamp(2, sc_++);
-    tc_fence_after();
-    const int c0 = cs * 64;
-    float pv[64];
-    {
-      uint32_t v0[32], v1[32];
-      tmem_ld32_nowait(d2 + lane_addr + (uint32_t)c0, v0);
-      tmem_ld32_nowait(d2 + lane_addr + (uint32_t)(c0 + 32), v1);
-      tmem_wait_ld();
-      const float* b2s = reinterpret_cast<const float*>(sm.a + 2 * 2 * kTcABytes + 4 * kTcBM * sizeof(float));
+    if (active) {
+      mbar_wait(&sm.d1_full_bar, 0);
+      if (threadIdx.x == 128) clk_stamp(2, sc_++);
+      tc_fence_after();
+      float d2_unscale = 1.f;                        // undoes the operand scaling of GEMM 2
+      {
+        // ---- re-stage relu(D1 + b1) as FP16 (hi, lo) planes: this thread owns 16 columns of each 64-column chunk.
+        // pass A: row maximum (power-of-two row scale, peak in [2^13, 2^14))
+        float rmax = 0.f;
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 ba = *reinterpret_cast<const float4*>(b2s + c0 + j4 * 4);
-        const float4 bb4 = *reinterpret_cast<const float4*>(b2s + c0 + 32 + j4 * 4);
-        pv[j4 * 4 + 0] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 0]), d2_unscale, ba.x), 0.f);
-        pv[j4 * 4 + 1] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 1]), d2_unscale, ba.y), 0.f);
-        pv[j4 * 4 + 2] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 2]), d2_unscale, ba.z), 0.f);
-        pv[j4 * 4 + 3] = fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 3]), d2_unscale, ba.w), 0.f);
-        pv[32 + j4 * 4 + 0] = fmaxf(fmaf(__uint_as_float(v1[j4 * 4 + 0]), d2_unscale, bb4.x), 0.f);
-        pv[32 + j4 * 4 + 1] = fmaxf(fmaf(__uint_as_float(v1[j4 * 4 + 1]), d2_unscale, bb4.y), 0.f);
-        pv[32 + j4 * 4 + 2] = fmaxf(fmaf(__uint_as_float(v1[j4 * 4 + 2]), d2_unscale, bb4.z), 0.f);
-        pv[32 + j4 * 4 + 3] = fmaxf(fmaf(__uint_as_float(v1[j4 * 4 + 3]), d2_unscale, bb4.w), 0.f);
+        for (int kp = 0; kp < 2; ++kp) {
+          uint32_t v0[16], v1[16];
+          tmem_ld16x2(d1 + lane_addr + (uint32_t)((2 * kp) * 64 + cs * 16), d1 + lane_addr + (uint32_t)((2 * kp + 1) * 64 + cs * 16), v0, v1);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 ba = *reinterpret_cast<const float4*>(sm.b1s + (2 * kp) * 64 + cs * 16 + j4 * 4);
+            const float4 bb4 = *reinterpret_cast<const float4*>(sm.b1s + (2 * kp + 1) * 64 + cs * 16 + j4 * 4);
+            rmax = fmaxf(rmax, fmaxf(fmaxf(__uint_as_float(v0[j4 * 4 + 0]) + ba.x, __uint_as_float(v0[j4 * 4 + 1]) + ba.y),
+                                     fmaxf(__uint_as_float(v0[j4 * 4 + 2]) + ba.z, __uint_as_float(v0[j4 * 4 + 3]) + ba.w)));
+            rmax = fmaxf(rmax, fmaxf(fmaxf(__uint_as_float(v1[j4 * 4 + 0]) + bb4.x, __uint_as_float(v1[j4 * 4 + 1]) + bb4.y),
+                                     fmaxf(__uint_as_float(v1[j4 * 4 + 2]) + bb4.z, __uint_as_float(v1[j4 * 4 + 3]) + bb4.w)));
+          }
+        }
+        // second-layer bias into shared memory for the epilogue (the third X chunk is free once D1 is complete; ordered by
+        // the row-maximum barrier below)
+        float* b2s = reinterpret_cast<float*>(sm.a + 2 * 2 * kTcABytes + 4 * kTcBM * sizeof(float));
+        if (threadIdx.x - 128 < 64)
+          *reinterpret_cast<float4*>(b2s + (threadIdx.x - 128) * 4) = __ldg(reinterpret_cast<const float4*>(dn.b2) + (threadIdx.x - 128));
+        float* rowmax = reinterpret_cast<float*>(sm.a + 2 * 2 * kTcABytes);      // third X chunk: free once D1 is complete
+        rowmax[cs * kTcBM + r] = rmax;
+        if (threadIdx.x == 128) clk_stamp(2, 1105);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (threadIdx.x == 128) clk_stamp(2, 1106);
+        rmax = fmaxf(fmaxf(rowmax[r], rowmax[kTcBM + r]), fmaxf(rowmax[2 * kTcBM + r], rowmax[3 * kTcBM + r]));
+        float sc, inv;
+        row_scale(rmax, sc, inv);
+        d2_unscale = inv * dn.W2scale_inv;
+        // pass B: the split, chunk by chunk
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          const int ab = kc & 1;
+          uint32_t v[16];
+          tmem_ld16(d1 + lane_addr + (uint32_t)(kc * 64 + cs * 16), v);
+          float hv[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bv = *reinterpret_cast<const float4*>(sm.b1s + kc * 64 + cs * 16 + j4 * 4);
+            hv[j4 * 4 + 0] = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + bv.x, 0.f);
+            hv[j4 * 4 + 1] = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + bv.y, 0.f);
+            hv[j4 * 4 + 2] = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + bv.z, 0.f);
+            hv[j4 * 4 + 3] = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + bv.w, 0.f);
+          }
+          uint4 hi[2], lo[2];
+          split8_f16(hv, sc, hi[0], lo[0]);
+          split8_f16(hv + 8, sc, hi[1], lo[1]);
+          mbar_wait(&sm.a_empty_bar[ab], (uint32_t)(((kc >> 1) & 1) ^ 1));
+          unsigned char* chunk = sm.a + (size_t)ab * 2 * kTcABytes;
+#pragma unroll
+          for (int u2 = 0; u2 < 2; ++u2) {
+            const int u = cs * 2 + u2;                     // 16-byte unit (8 halves) inside the 128-byte row
+            const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((u ^ (r & 7)) & 7) << 4));
+            *reinterpret_cast<uint4*>(chunk + off) = hi[u2];
+            *reinterpret_cast<uint4*>(chunk + kTcABytes + off) = lo[u2];
+          }
+          fence_proxy_async();
+          mbar_arrive(&sm.a_full_bar[ab]);
+          if (threadIdx.x == 128) clk_stamp(2, sc_++);
+        }
       }
-    }
-    {
-      // FP16 planes: the row maximum (over the four column sub-blocks, through shared memory) fixes an exact power-of-two
-      // scale so the row peaks in [2^13, 2^14); then (hi, lo) halves
+      // ---- epilogue: relu(D2 + b2) -> operand planes of the head GEMM, 64 columns per thread, two passes over TMEM
+      mbar_wait(&sm.d2_full_bar, 0);
+      if (threadIdx.x == 128) clk_stamp(2, sc_++);
+      tc_fence_after();
+      const int c0 = cs * 64;
+      const float* b2s = reinterpret_cast<const float*>(sm.a + 2 * 2 * kTcABytes + 4 * kTcBM * sizeof(float));
       float rmax = 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) rmax = fmaxf(rmax, pv[j]);
-      float* rowmax = reinterpret_cast<float*>(sm.a);      // the A-operand region is free once D2 is complete
-      rowmax[cs * kTcBM + r] = rmax;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      rmax = fmaxf(fmaxf(rowmax[r], rowmax[kTcBM + r]), fmaxf(rowmax[2 * kTcBM + r], rowmax[3 * kTcBM + r]));
-      int ex = 0;
-      float sc = 1.f, inv = 1.f;
-      if (rmax > 0.f && rmax < 3.0e38f) {
-        frexpf(rmax, &ex);                         // rmax = m * 2^ex, m in [0.5, 1)
-        sc = ldexpf(1.f, 14 - ex);
-        inv = ldexpf(1.f, ex - 14);
-      }
-      VPHO_BOUNDS(r0 + kTcBM <= ws.Npad);
-      if (cs == 0) ws.P2scale[r0 + r] = inv;
-      // The tile is a contiguous 64 KB block per plane in global memory.  Lanes own rows, so direct stores would touch 32
-      // different lines per instruction (partial sectors): stage through shared memory (rows padded to 528 bytes:
-      // conflict-free 16-byte stores) and write it out with consecutive threads on consecutive 16-byte units.
-      constexpr int kRowPad = 528, kPlane = kTcBM * kRowPad;
-      unsigned char* ot = sm.a + 2048;               // after the row-max scratch; operand regions a+b are free now
+      for (int g = 0; g < 2; ++g) {
+        uint32_t v0[16], v1[16];
+        tmem_ld16x2(d2 + lane_addr + (uint32_t)(c0 + 32 * g), d2 + lane_addr + (uint32_t)(c0 + 32 * g + 16), v0, v1);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        __align__(16) __half hi8[8], lo8[8];
-#pragma unroll
-        for (int ee = 0; ee < 8; ++ee) {
-          const float x = pv[u * 8 + ee] * sc;
-          const __half h = __float2half_rn(x);
-          hi8[ee] = h;
-          lo8[ee] = __float2half_rn(x - __half2float(h));
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 ba = *reinterpret_cast<const float4*>(b2s + c0 + 32 * g + j4 * 4);
+          const float4 bb4 = *reinterpret_cast<const float4*>(b2s + c0 + 32 * g + 16 + j4 * 4);
+          rmax = fmaxf(rmax, fmaxf(fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 0]), d2_unscale, ba.x), fmaf(__uint_as_float(v0[j4 * 4 + 1]), d2_unscale, ba.y)),
+                                   fmaxf(fmaf(__uint_as_float(v0[j4 * 4 + 2]), d2_unscale, ba.z), fmaf(__uint_as_float(v0[j4 * 4 + 3]), d2_unscale, ba.w))));
+          rmax = fmaxf(rmax, fmaxf(fmaxf(fmaf(__uint_as_float(v1[j4 * 4 + 0]), d2_unscale, bb4.x), fmaf(__uint_as_float(v1[j4 * 4 + 1]), d2_unscale, bb4.y)),
+                                   fmaxf(fmaf(__uint_as_float(v1[j4 * 4 + 2]), d2_unscale, bb4.z), fmaf(__uint_as_float(v1[j4 * 4 + 3]), d2_unscale, bb4.w))));
         }
-        *reinterpret_cast<uint4*>(ot + r * kRowPad + (c0 + u * 8) * 2) = *reinterpret_cast<const uint4*>(hi8);
-        *reinterpret_cast<uint4*>(ot + kPlane + r * kRowPad + (c0 + u * 8) * 2) = *reinterpret_cast<const uint4*>(lo8);
       }
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      const int tc = threadIdx.x - 128;
-      unsigned char* ghi = reinterpret_cast<unsigned char*>(ws.P2hi) + (size_t)r0 * kPDim * 2;
-      unsigned char* glo = reinterpret_cast<unsigned char*>(ws.P2lo) + (size_t)r0 * kPDim * 2;
+      if (threadIdx.x == 128) clk_stamp(2, 1107);
+      {
+        // FP16 planes: the row maximum (over the four column sub-blocks, through shared memory) fixes an exact power-of-two
+        // scale so the row peaks in [2^13, 2^14); then (hi, lo) halves
+        float* rowmax = reinterpret_cast<float*>(sm.a);      // the A-operand region is free once D2 is complete
+        rowmax[cs * kTcBM + r] = rmax;
+        if (threadIdx.x == 128) clk_stamp(2, 1108);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (threadIdx.x == 128) clk_stamp(2, 1109);
+        rmax = fmaxf(fmaxf(rowmax[r], rowmax[kTcBM + r]), fmaxf(rowmax[2 * kTcBM + r], rowmax[3 * kTcBM + r]));
+        float sc, inv;
+        row_scale(rmax, sc, inv);
+        VPHO_BOUNDS(r0 + kTcBM <= ws.Npad);
+        if (cs == 0) ws.P2scale[r0 + r] = inv;
+        // The tile is a contiguous 64 KB block per plane in global memory.  Lanes own rows, so direct stores would touch 32
+        // different lines per instruction (partial sectors): stage through shared memory (rows padded to 528 bytes:
+        // conflict-free 16-byte stores) and write it out with consecutive threads on consecutive 16-byte units.
+        constexpr int kRowPad = 528, kPlane = kTcBM * kRowPad;
+        // (operand regions a + b are free now; the staging tile starts past the second-layer bias in the third X chunk,
+        // which pass B below still reads)
+        unsigned char* ot = sm.a + 72 * 1024;
+        static_assert(72 * 1024 >= 2 * 2 * kTcABytes + 4 * kTcBM * 4 + kPDim * 4 && 72 * 1024 + 2 * kTcBM * 528 <= kPtRegionA + 2 * kPtStageB,
+                      "staging tile placement");
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v[16];
+          tmem_ld16(d2 + lane_addr + (uint32_t)(c0 + 16 * g), v);
+          float pv[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bv = *reinterpret_cast<const float4*>(b2s + c0 + 16 * g + j4 * 4);
+            pv[j4 * 4 + 0] = fmaxf(fmaf(__uint_as_float(v[j4 * 4 + 0]), d2_unscale, bv.x), 0.f);
+            pv[j4 * 4 + 1] = fmaxf(fmaf(__uint_as_float(v[j4 * 4 + 1]), d2_unscale, bv.y), 0.f);
+            pv[j4 * 4 + 2] = fmaxf(fmaf(__uint_as_float(v[j4 * 4 + 2]), d2_unscale, bv.z), 0.f);
+            pv[j4 * 4 + 3] = fmaxf(fmaf(__uint_as_float(v[j4 * 4 + 3]), d2_unscale, bv.w), 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            uint4 hi, lo;
+            split8_f16(pv + 8 * u, sc, hi, lo);
+            *reinterpret_cast<uint4*>(ot + r * kRowPad + (c0 + 16 * g + u * 8) * 2) = hi;
+            *reinterpret_cast<uint4*>(ot + kPlane + r * kRowPad + (c0 + 16 * g + u * 8) * 2) = lo;
+          }
+        }
+        if (threadIdx.x == 128) clk_stamp(2, 1110);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (threadIdx.x == 128) clk_stamp(2, 1111);
+        const int tc = threadIdx.x - 128;
+        unsigned char* ghi = reinterpret_cast<unsigned char*>(ws.P2hi) + (size_t)r0 * kPDim * 2;
+        unsigned char* glo = reinterpret_cast<unsigned char*>(ws.P2lo) + (size_t)r0 * kPDim * 2;
 #pragma unroll 4
-      for (int i = tc; i < 2 * kTcBM * 32; i += 512) {
-        const int plane = i >> 12, j = i & 4095, row = j >> 5, unit = j & 31;
-        VPHO_BOUNDS(plane < 2 && r0 + row < ws.Npad && unit * 16 + 16 <= kPDim * 2);
-        const uint4 val = *reinterpret_cast<const uint4*>(ot + plane * kPlane + row * kRowPad + unit * 16);
-        *reinterpret_cast<uint4*>((plane ? glo : ghi) + (size_t)row * 512 + unit * 16) = val;
+        for (int i = tc; i < 2 * kTcBM * 32; i += 512) {
+          const int plane = i >> 12, j = i & 4095, row = j >> 5, unit = j & 31;
+          VPHO_BOUNDS(plane < 2 && r0 + row < ws.Npad && unit * 16 + 16 <= kPDim * 2);
+          const uint4 val = *reinterpret_cast<const uint4*>(ot + plane * kPlane + row * kRowPad + unit * 16);
+          *reinterpret_cast<uint4*>((plane ? glo : ghi) + (size_t)row * 512 + unit * 16) = val;
+        }
       }
     }
   }
@@ -738,15 +801,18 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
   }
 }
 
-// One CTA per 128-row tile; with two samplers in lock-step the grid holds job 0's tiles followed by job 1's.
+// One CTA per 128-row tile; with two samplers in lock-step the grid holds job 0's tiles followed by job 1's.  The jobs'
+// parameters are picked by address (grid constants), so the tile body exists once in the binary.
 __global__ void __launch_bounds__(kHeadThreads, 1)
 k_pose_tc(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_constant__ CUtensorMap tmW1_lo,
           const __grid_constant__ CUtensorMap tmW2_hi, const __grid_constant__ CUtensorMap tmW2_lo,
           const __grid_constant__ CUtensorMap tmW1_hi1, const __grid_constant__ CUtensorMap tmW1_lo1,
-          const __grid_constant__ CUtensorMap tmW2_hi1, const __grid_constant__ CUtensorMap tmW2_lo1, DenoiserDev dn0, SamplerWs ws0,
-          DenoiserDev dn1, SamplerWs ws1, int tiles0, int mode, int s) {
-  if ((int)blockIdx.x < tiles0) pose_tc_tile(&tmW1_hi, &tmW1_lo, &tmW2_hi, &tmW2_lo, dn0, ws0, mode, s, blockIdx.x);
-  else pose_tc_tile(&tmW1_hi1, &tmW1_lo1, &tmW2_hi1, &tmW2_lo1, dn1, ws1, mode, s, (int)blockIdx.x - tiles0);
+          const __grid_constant__ CUtensorMap tmW2_hi1, const __grid_constant__ CUtensorMap tmW2_lo1,
+          const __grid_constant__ DenoiserDev dn0, const __grid_constant__ SamplerWs ws0, const __grid_constant__ DenoiserDev dn1,
+          const __grid_constant__ SamplerWs ws1, int tiles0, int mode, int s) {
+  const bool j1 = (int)blockIdx.x >= tiles0;
+  pose_tc_tile(j1 ? &tmW1_hi1 : &tmW1_hi, j1 ? &tmW1_lo1 : &tmW1_lo, j1 ? &tmW2_hi1 : &tmW2_hi, j1 ? &tmW2_lo1 : &tmW2_lo,
+               j1 ? dn1 : dn0, j1 ? ws1 : ws0, mode, s, j1 ? (int)blockIdx.x - tiles0 : (int)blockIdx.x);
 }
 
 // =====================================================================================================================

@@ -47,7 +47,8 @@ def show(tag):
           int(mma[1 + 2 * n1 + 2 * n2] - t0))
     print("compute: d1 seen", int(comp[0] - t0), "restaged chunks:", (comp[1:1 + n2] - t0).tolist(), "d2 seen", int(comp[1 + n2] - t0),
           "done", int(comp[2 + n2] - t0))
-    ex = buf[2 * 2048 + 1100:2 * 2048 + 1112].astype(np.int64) - t0
+    ex = buf[2 * 2048 + 1100:2 * 2048 + 1114].astype(np.int64) - t0
+    print("chunk 0 of thread 128: unit 0 stored", int(ex[12]), "unit 1 stored", int(ex[13]))
     print("fine stamps (thread 128): entry", int(ex[0]), "after pdl wait", int(ex[1]), "scalars seen", int(ex[2]), "x chunk arrived (not last)", int(ex[3]),
           "last x chunk arrived", int(ex[4]), "| restage: rowmax stored", int(ex[5]), "bar passed", int(ex[6]), "| epilogue: tmem ld done", int(ex[7]),
           "rowmax stored", int(ex[8]), "bar passed", int(ex[9]), "staged", int(ex[10]), "bar passed", int(ex[11]))
@@ -67,6 +68,11 @@ fn(1, None, 0)
 run()
 torch.cuda.synchronize()
 show("last pose call of a paired sampler pass (mode final: x = y)")
+for st in (1, 3, 6):
+    fn(100 + st, None, 0)
+    run()
+    torch.cuda.synchronize()
+    show(f"last call of RK stage {st} in a paired sampler pass ({st} K slots enter)")
 # a mid-integration stage: run the blocking single sampler of the hand only, whose last stage call is s = 6 of the last attempt
 from vpho_b200.score_based_model import Denoiser  # noqa: E402
 g = torch.Generator().manual_seed(0)

@@ -73,8 +73,21 @@ __device__ __forceinline__ EvalTime eval_time(const RkCtrl& c, int mode, int s) 
 // The slot stores the float32 score; the drift  -0.5 g(t)^2 * score  is formed here in float64 exactly as
 // `drift - 0.5 * diffusion**2 * score` is under numpy >= 2 promotion, so keeping the narrow value in
 // memory halves the K traffic of every RK kernel without changing a bit of the result.
+// float -> double, exact, on the integer pipe.  The FP64 pipe of this part issues only a few lanes per clock per SM (measured:
+// the stage-input phase of the pose kernel is bound by it), and F2F.F64.F32 runs there too: widening by bit manipulation
+// takes one of the three FP64-pipe instructions per (element, K slot) off it.  Zeros, subnormals, infinities and NaNs take
+// the conversion instruction.
+__device__ __forceinline__ double widen_f32(float f) {
+#if defined(__CUDA_ARCH__)
+  const unsigned u = __float_as_uint(f), e = (u >> 23) & 0xFFu;
+  if (e == 0u || e == 255u) return (double)f;
+  return __hiloint2double((int)((u & 0x80000000u) | (((u & 0x7FFFFFFFu) >> 3) + 0x38000000u)), (int)(u << 29));
+#else
+  return (double)f;
+#endif
+}
 __device__ __forceinline__ double kval(const float* K, const RkCtrl& c, int slot, int n, int i) {
-  double v = -(c.kcoef[slot] * (double)K[(size_t)slot * n + i]);
+  double v = -(c.kcoef[slot] * widen_f32(K[(size_t)slot * n + i]));
   if (c.nan_stage[slot] && !isfinite(v)) v = 0.0;
   return v;
 }
@@ -131,7 +144,7 @@ __device__ __forceinline__ double stage_input(const SamplerWs& ws, const RkCtrl&
 
 // The same stage input for FOUR consecutive elements i..i+3 (i a multiple of 4, D a multiple of 4), with the controller
 // scalars read once (`StageScalars`) and the K slots / state read as 16-byte vectors.  Operation for operation the arithmetic
-// of stage_input / kval above -- the fused pose-encoder kernel calls this 6 times per thread per network call, where the
+// of stage_input / kval above -- the fused pose-encoder kernel runs this 6 times per thread per network call, where the
 // scalar form spends its time re-reading the controller words.
 struct StageScalars {
   double kc[6];     // kcoef of the K slots that enter the combination
@@ -148,60 +161,17 @@ __device__ __forceinline__ StageScalars stage_scalars(const RkCtrl& c, int mode,
   if (mode == kModeStage) { q.ns = (s == 6) ? 6 : s; q.h = c.h; }
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    q.kc[j] = j < q.ns ? c.kcoef[j] : 0.0;
-    q.nanf[j] = j < q.ns ? c.nan_stage[j] : 0;
+    const double kcj = c.kcoef[j];            // unconditional: all the controller words in flight at once
+    const int nfj = c.nan_stage[j];
+    q.kc[j] = j < q.ns ? kcj : 0.0;
+    q.nanf[j] = j < q.ns ? nfj : 0;
     q.a[j] = mode == kModeStage ? kA[s][j] : 1.0;
   }
   return q;
 }
-__device__ __forceinline__ void stage_input4(const SamplerWs& ws, const StageScalars& q, int mode, int s, int i, int n, float* out) {
-  if (mode == kModeEval) {
-    const float4 x = *reinterpret_cast<const float4*>(ws.eval_x + i);
-    out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = x.w;
-    return;
-  }
-  const double2 y01 = *reinterpret_cast<const double2*>(ws.y + i), y23 = *reinterpret_cast<const double2*>(ws.y + i + 2);
-  const double y[4] = {y01.x, y01.y, y23.x, y23.y};
-  if (q.ns == 0) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) out[e] = (float)y[e];
-    return;
-  }
-  float4 kv[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j)
-    if (j < q.ns) kv[j] = *reinterpret_cast<const float4*>(ws.K + (size_t)j * n + i);
-  double v[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    if (mode == kModeInit1) {
-      const float k0 = e == 0 ? kv[0].x : e == 1 ? kv[0].y : e == 2 ? kv[0].z : kv[0].w;
-      double kvv = -(q.kc[0] * (double)k0);
-      if (q.nanf[0] && !isfinite(kvv)) kvv = 0.0;
-      v[e] = __dadd_rn(y[e], __dmul_rn(q.h, kvv));
-    } else {
-      double acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < 6; ++j)
-        if (j < q.ns) {
-          const float kj = e == 0 ? kv[j].x : e == 1 ? kv[j].y : e == 2 ? kv[j].z : kv[j].w;
-          double kvv = -(q.kc[j] * (double)kj);
-          if (q.nanf[j] && !isfinite(kvv)) kvv = 0.0;
-          acc += kvv * q.a[j];
-        }
-      v[e] = __dadd_rn(y[e], __dmul_rn(acc, q.h));
-    }
-    out[e] = (float)v[e];
-  }
-  if (mode == kModeStage && s == 6) {
-    *reinterpret_cast<double2*>(ws.ynew + i) = make_double2(v[0], v[1]);
-    *reinterpret_cast<double2*>(ws.ynew + i + 2) = make_double2(v[2], v[3]);
-  }
-}
-
-// stage_input4 in two halves, for callers that keep several units' loads in flight before the float64 arithmetic starts
-// (the fused pose-encoder kernel: the load latency of one unit is otherwise paid once per unit).  `ns` is the number of K
-// slots that enter (host-known from mode / s: stage_ns); the arithmetic is stage_input4's, operation for operation.
+// The vector form comes in two halves (loads / arithmetic) so that the caller can keep several units' loads in flight before
+// the float64 arithmetic starts (the load latency of one unit is otherwise paid once per unit).  `ns` is the number of K
+// slots that enter (host-known from mode / s: stage_ns).
 struct StageRaw {
   double2 y01, y23;
   float4 kv[6];
@@ -214,8 +184,13 @@ __device__ __forceinline__ void stage_load4(const SamplerWs& ws, int mode, int n
     r.kv[0] = *reinterpret_cast<const float4*>(ws.eval_x + i);
     return;
   }
+#if defined(__CUDA_ARCH__)
+  // one 32-byte load per unit (sm_100 256-bit LDG): with two 16-byte loads the lanes of a warp touch every 32-byte sector twice
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.y01.x), "=d"(r.y01.y), "=d"(r.y23.x), "=d"(r.y23.y) : "l"(ws.y + i) : "memory");
+#else
   r.y01 = *reinterpret_cast<const double2*>(ws.y + i);
   r.y23 = *reinterpret_cast<const double2*>(ws.y + i + 2);
+#endif
 #pragma unroll
   for (int j = 0; j < 6; ++j)
     if (j < ns) r.kv[j] = *reinterpret_cast<const float4*>(ws.K + (size_t)j * n + i);
@@ -237,7 +212,7 @@ __device__ __forceinline__ void stage_math4(const SamplerWs& ws, const StageScal
   for (int e = 0; e < 4; ++e) {
     if (mode == kModeInit1) {
       const float k0 = e == 0 ? r.kv[0].x : e == 1 ? r.kv[0].y : e == 2 ? r.kv[0].z : r.kv[0].w;
-      double kvv = -(q.kc[0] * (double)k0);
+      double kvv = -(q.kc[0] * widen_f32(k0));
       if (q.nanf[0] && !isfinite(kvv)) kvv = 0.0;
       v[e] = __dadd_rn(y[e], __dmul_rn(q.h, kvv));
     } else {
@@ -246,7 +221,7 @@ __device__ __forceinline__ void stage_math4(const SamplerWs& ws, const StageScal
       for (int j = 0; j < 6; ++j)
         if (j < q.ns) {
           const float kj = e == 0 ? r.kv[j].x : e == 1 ? r.kv[j].y : e == 2 ? r.kv[j].z : r.kv[j].w;
-          double kvv = -(q.kc[j] * (double)kj);
+          double kvv = -(q.kc[j] * widen_f32(kj));
           if (q.nanf[j] && !isfinite(kvv)) kvv = 0.0;
           acc += kvv * q.a[j];
         }
@@ -255,8 +230,12 @@ __device__ __forceinline__ void stage_math4(const SamplerWs& ws, const StageScal
     out[e] = (float)v[e];
   }
   if (mode == kModeStage && s == 6) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(ws.ynew + i), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+#else
     *reinterpret_cast<double2*>(ws.ynew + i) = make_double2(v[0], v[1]);
     *reinterpret_cast<double2*>(ws.ynew + i + 2) = make_double2(v[2], v[3]);
+#endif
   }
 }
 

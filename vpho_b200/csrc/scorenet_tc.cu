@@ -49,7 +49,7 @@ struct TcSmem {
 // Optional timeline instrumentation of CTA 0 (vpho_debug_tc_clocks, tools/diag_tc_timeline.py): %globaltimer stamps of
 // the three roles of the head GEMM.  Compiled in only with -DVPHO_TC_TIMELINE; the default build has no stamps.
 __device__ unsigned long long g_clk[3 * 2048];
-__device__ int g_clk_on = 0;
+__device__ int g_clk_on = 0;       // 1: every launch stamps; 100 + s: only the pose kernel's calls of RK stage s do
 __device__ __forceinline__ void clk_stamp(int role, int idx) {
 #ifdef VPHO_TC_TIMELINE
   if (g_clk_on && blockIdx.x == 0 && idx < 2048) {
@@ -408,6 +408,15 @@ k_head_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 constexpr int kPtMaxK1Chunks = 3;                         // D <= 96
 constexpr int kPtRegionA = kPtMaxK1Chunks * 2 * kTcABytes;   // X hi/lo chunks, later 2 x (H1 hi/lo chunk): 96 KB
 constexpr int kPtStageB = 2 * kTcBBytes;                  // W (hi, lo) chunk: 64 KB
+// One role warpgroup (warp 0: TMEM allocation, controller scalars, TMA producer; warp 1: barrier set-up, MMA issuer; warps
+// 2, 3 idle) + 16 compute warps.  Every scheduler holds 5 warps, i.e. 96 registers per thread at launch; the role warpgroup
+// hands registers back (setmaxnreg 32) and the compute warpgroups take 112, so that the stage-input phase can keep two
+// units' loads (64 registers) in flight without spilling.
+constexpr int kPoseThreads = 640;
+constexpr int kPoseRoleThreads = 128;
+constexpr int kPoseRoleRegs = 48, kPoseComputeRegs = 104;
+static_assert(kPoseRoleThreads * kPoseRoleRegs + (kPoseThreads - kPoseRoleThreads) * kPoseComputeRegs <= kPoseThreads * 96,
+              "setmaxnreg.inc draws from the registers the CTA was launched with: the budget must close or the kernel deadlocks");
 
 struct PtSmem {
   unsigned char a[kPtRegionA];
@@ -459,7 +468,6 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   PtSmem& sm = *reinterpret_cast<PtSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 128) clk_stamp(2, 1100);
   const int D = dn.D, nk1 = (D + kTcBK - 1) / kTcBK;
   const int r0 = tile * kTcBM;
   // GEMM 2 on FP16 planes: 4 chunks of 64 k, kind::f16, H1 re-staged as (hi, lo) halves scaled per row.  A chunk is 128-byte
@@ -475,33 +483,36 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
     mbar_init(&sm.d1_full_bar, 1); mbar_init(&sm.d2_full_bar, 1); mbar_init(&sm.q_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    reinterpret_cast<float4*>(sm.b1s)[lane] = __ldg(reinterpret_cast<const float4*>(dn.b1) + lane);
+    reinterpret_cast<float4*>(sm.b1s)[32 + lane] = __ldg(reinterpret_cast<const float4*>(dn.b1) + 32 + lane);
   }
-  if (warp == 3) reinterpret_cast<float4*>(sm.b1s)[lane] = __ldg(reinterpret_cast<const float4*>(dn.b1) + lane),
-                 reinterpret_cast<float4*>(sm.b1s)[32 + lane] = __ldg(reinterpret_cast<const float4*>(dn.b1) + 32 + lane);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
   const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
-  int sc_ = 1024;                                // timeline stamp slot of this thread (VPHO_TC_TIMELINE builds)
+#ifdef VPHO_TC_TIMELINE
+  const int sb_ = (g_clk_on < 100 || (mode == kModeStage && s == g_clk_on - 100)) ? 0 : 4096;   // 4096: stamps dropped
+#else
+  constexpr int sb_ = 0;
+#endif
+  int sc_ = 1024 + sb_;                          // timeline stamp slot of this thread (VPHO_TC_TIMELINE builds)
   pdl_wait();                 // launched with launch_pdl: the set-up above overlaps the tail of the preceding kernel
   pdl_trigger();
   if (threadIdx.x == 0) clk_stamp(0, sc_++);
-  if (threadIdx.x == 128) clk_stamp(2, 1101);
+  if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, 1101 + sb_);
 
-  if (warp == 3) {
-    // the controller words of this call: one thread reads them while the compute warps' state loads are in flight
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPoseRoleRegs));
+  if (warp == 0) {
     if (lane == 0) {
+      // the controller words of this call: one thread reads them while the compute warps' state loads are in flight
       sm.active = eval_active(c, mode) ? 1 : 0;
       sm.q = stage_scalars(c, mode, s);
       mbar_arrive(&sm.q_bar);
-    }
-  } else if (warp == 0) {
-    if (lane == 0) {
-      mbar_wait(&sm.q_bar, 0);
       if (sm.active) {
         int stage = 0;
         uint32_t phase = 0;
@@ -578,9 +589,11 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
         clk_stamp(1, sc_++);
       }
     }
-  } else if (warp >= 4) {
-    // 16 compute warps: warp 4+e owns TMEM lanes 32*(e&3).. (its hardware lane quarter) and column sub-block cs = e>>2
-    const int e = warp - 4, q = e & 3, cs = e >> 2, r = q * 32 + lane;      // r: this thread's row of the tile
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kPoseComputeRegs));
+    // 16 compute warps: warp w owns TMEM lanes 32*(w&3).. (its hardware lane quarter) and column sub-block cs = (w-4)>>2
+    const int q = warp & 3, cs = (warp - 4) >> 2, r = q * 32 + lane;      // r: this thread's row of the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     // ---- stage input: the float64 RK stage combination of every state element of this tile (what scipy hands to `fun`,
     // stage_input), rounded to float32 and split into the (hi, lo) TF32 planes of GEMM 1's A operand, straight into the
@@ -588,7 +601,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
     // consecutive threads take consecutive units, so the K-slot reads are coalesced.  Rows past the end and k >= D are zero.
     bool active = true;
     {
-      const int tcx = threadIdx.x - 128;                       // 0..511
+      const int tcx = threadIdx.x - kPoseRoleThreads;          // 0..511
       const int n_rows = ws.eval_rows;                         // the sampler's row count (carve): no controller read needed
       const int n_state = n_rows * D;
       const int ns = stage_ns(mode, s);
@@ -610,7 +623,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
         if (kc == 0) {
           mbar_wait(&sm.q_bar, 0);
           active = sm.active != 0;
-          if (threadIdx.x == 128) clk_stamp(2, 1102);
+          if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, 1102 + sb_);
           if (!active) break;
         }
         unsigned char* chunk = sm.a + (size_t)kc * 2 * kTcABytes;
@@ -635,15 +648,16 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
           const uint32_t off = (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128 + (((ku ^ (rr & 7)) & 7) << 4));
           *reinterpret_cast<float4*>(chunk + off) = make_float4(hi4[0], hi4[1], hi4[2], hi4[3]);
           *reinterpret_cast<float4*>(chunk + kTcABytes + off) = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
+          if (kc == 0 && threadIdx.x == kPoseRoleThreads) clk_stamp(2, 1112 + b + sb_);
         }
         fence_proxy_async();
         mbar_arrive(&sm.x_full_bar[kc]);
-        if (threadIdx.x == 128) clk_stamp(2, 1103 + (kc == nk1 - 1 ? 1 : 0));
+        if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, 1103 + (kc == nk1 - 1 ? 1 : 0) + sb_);
       }
     }
     if (active) {
       mbar_wait(&sm.d1_full_bar, 0);
-      if (threadIdx.x == 128) clk_stamp(2, sc_++);
+      if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, sc_++);
       tc_fence_after();
       float d2_unscale = 1.f;                        // undoes the operand scaling of GEMM 2
       {
@@ -667,13 +681,14 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
         // second-layer bias into shared memory for the epilogue (the third X chunk is free once D1 is complete; ordered by
         // the row-maximum barrier below)
         float* b2s = reinterpret_cast<float*>(sm.a + 2 * 2 * kTcABytes + 4 * kTcBM * sizeof(float));
-        if (threadIdx.x - 128 < 64)
-          *reinterpret_cast<float4*>(b2s + (threadIdx.x - 128) * 4) = __ldg(reinterpret_cast<const float4*>(dn.b2) + (threadIdx.x - 128));
+        if (threadIdx.x - kPoseRoleThreads < 64)
+          *reinterpret_cast<float4*>(b2s + (threadIdx.x - kPoseRoleThreads) * 4) =
+              __ldg(reinterpret_cast<const float4*>(dn.b2) + (threadIdx.x - kPoseRoleThreads));
         float* rowmax = reinterpret_cast<float*>(sm.a + 2 * 2 * kTcABytes);      // third X chunk: free once D1 is complete
         rowmax[cs * kTcBM + r] = rmax;
-        if (threadIdx.x == 128) clk_stamp(2, 1105);
+        if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, 1105 + sb_);
         asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (threadIdx.x == 128) clk_stamp(2, 1106);
+        if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, 1106 + sb_);
         rmax = fmaxf(fmaxf(rowmax[r], rowmax[kTcBM + r]), fmaxf(rowmax[2 * kTcBM + r], rowmax[3 * kTcBM + r]));
         float sc, inv;
         row_scale(rmax, sc, inv);
@@ -707,12 +722,12 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
           }
           fence_proxy_async();
           mbar_arrive(&sm.a_full_bar[ab]);
-          if (threadIdx.x == 128) clk_stamp(2, sc_++);
+          if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, sc_++);
         }
       }
       // ---- epilogue: relu(D2 + b2) -> operand planes of the head GEMM, 64 columns per thread, two passes over TMEM
       mbar_wait(&sm.d2_full_bar, 0);
-      if (threadIdx.x == 128) clk_stamp(2, sc_++);
+      if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, sc_++);
       tc_fence_after();
       const int c0 = cs * 64;
       const float* b2s = reinterpret_cast<const float*>(sm.a + 2 * 2 * kTcABytes + 4 * kTcBM * sizeof(float));
@@ -731,15 +746,15 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
                                    fmaxf(fmaf(__uint_as_float(v1[j4 * 4 + 2]), d2_unscale, bb4.z), fmaf(__uint_as_float(v1[j4 * 4 + 3]), d2_unscale, bb4.w))));
         }
       }
-      if (threadIdx.x == 128) clk_stamp(2, 1107);
+      if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, 1107 + sb_);
       {
         // FP16 planes: the row maximum (over the four column sub-blocks, through shared memory) fixes an exact power-of-two
         // scale so the row peaks in [2^13, 2^14); then (hi, lo) halves
         float* rowmax = reinterpret_cast<float*>(sm.a);      // the A-operand region is free once D2 is complete
         rowmax[cs * kTcBM + r] = rmax;
-        if (threadIdx.x == 128) clk_stamp(2, 1108);
+        if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, 1108 + sb_);
         asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (threadIdx.x == 128) clk_stamp(2, 1109);
+        if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, 1109 + sb_);
         rmax = fmaxf(fmaxf(rowmax[r], rowmax[kTcBM + r]), fmaxf(rowmax[2 * kTcBM + r], rowmax[3 * kTcBM + r]));
         float sc, inv;
         row_scale(rmax, sc, inv);
@@ -775,10 +790,10 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
             *reinterpret_cast<uint4*>(ot + kPlane + r * kRowPad + (c0 + 16 * g + u * 8) * 2) = lo;
           }
         }
-        if (threadIdx.x == 128) clk_stamp(2, 1110);
+        if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, 1110 + sb_);
         asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (threadIdx.x == 128) clk_stamp(2, 1111);
-        const int tc = threadIdx.x - 128;
+        if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, 1111 + sb_);
+        const int tc = threadIdx.x - kPoseRoleThreads;
         unsigned char* ghi = reinterpret_cast<unsigned char*>(ws.P2hi) + (size_t)r0 * kPDim * 2;
         unsigned char* glo = reinterpret_cast<unsigned char*>(ws.P2lo) + (size_t)r0 * kPDim * 2;
 #pragma unroll 4
@@ -791,11 +806,11 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
       }
     }
   }
-  if (threadIdx.x == 128) clk_stamp(2, sc_++);
+  if (threadIdx.x == kPoseRoleThreads) clk_stamp(2, sc_++);
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) clk_stamp(0, sc_++);
-  if (warp == 2) {
+  if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
@@ -803,7 +818,7 @@ __device__ __forceinline__ void pose_tc_tile(const CUtensorMap* tmW1_hi, const C
 
 // One CTA per 128-row tile; with two samplers in lock-step the grid holds job 0's tiles followed by job 1's.  The jobs'
 // parameters are picked by address (grid constants), so the tile body exists once in the binary.
-__global__ void __launch_bounds__(kHeadThreads, 1)
+__global__ void __launch_bounds__(kPoseThreads, 1)
 k_pose_tc(const __grid_constant__ CUtensorMap tmW1_hi, const __grid_constant__ CUtensorMap tmW1_lo,
           const __grid_constant__ CUtensorMap tmW2_hi, const __grid_constant__ CUtensorMap tmW2_lo,
           const __grid_constant__ CUtensorMap tmW1_hi1, const __grid_constant__ CUtensorMap tmW1_lo1,
@@ -1017,7 +1032,7 @@ int tc_launch_pose(const TcPoseJob* jobs, int n_jobs, int mode, int s, cudaStrea
   const TcPoseJob& j1 = jobs[n_jobs - 1];
   const int tiles0 = j0.ws->Npad / kTcBM, tiles1 = n_jobs > 1 ? j1.ws->Npad / kTcBM : 0;
   auto M = [](const void* p) -> const CUtensorMap& { return *static_cast<const CUtensorMap*>(p); };
-  if (launch_pdl(k_pose_tc, dim3(tiles0 + tiles1), dim3(kHeadThreads), smem, st, 1, M(j0.mapW1_hi), M(j0.mapW1_lo), M(j0.mapW2_hi),
+  if (launch_pdl(k_pose_tc, dim3(tiles0 + tiles1), dim3(kPoseThreads), smem, st, 1, M(j0.mapW1_hi), M(j0.mapW1_lo), M(j0.mapW2_hi),
                  M(j0.mapW2_lo), M(j1.mapW1_hi), M(j1.mapW1_lo), M(j1.mapW2_hi), M(j1.mapW2_lo), *j0.dn, *j0.ws, *j1.dn, *j1.ws,
                  tiles0, mode, s) != cudaSuccess)
     return VPHO_ERR_LAUNCH;

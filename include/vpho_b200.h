@@ -332,6 +332,71 @@ int vpho_hoi_aggregate(vpho_mano_t mano, vpho_assets_t assets, const vpho_hoi_ar
                        size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------------------
+ * N4: the aggregation modes the predict branch does not use -- `HandAggregator.__call__` modes 'heatmap',
+ * 'heatmap_cascade_n_level', '2D_pt_pose', '2D_pt_joint', 'average_all', 'random' (lib/model/aggregation.py:63-113,286-535)
+ * and `ObjectAggregator` 'heatmap' / the non-physics branch of 'heatmap_cascade' (:646-722) -- as device primitives; the host
+ * mirror vpho_b200/aggregation_modes.py composes them the way the reference's methods do. */
+typedef struct {
+  int bs, n, n_joints;            /* images, candidates per image, joints per candidate (21)                         */
+  const float* joint;             /* [bs][n][n_joints][3] wrist-relative MANO joints of the candidates                  */
+  const float* root_joint;        /* [bs][3]                                                                            */
+  const float* cam_intrinsic;     /* [bs][3][3]                                                                         */
+  const float* bbox;              /* [bs][4]                                                                            */
+  const float* heatmap;           /* [bs][n_joints][64][64]                                                             */
+  float* heat;                    /* out or NULL [bs][n][n_joints]: bicubic grid_sample of joint j's map at its projection
+                                     (aggregation.py:196-210)                                                           */
+  float* dist2d;                  /* out or NULL [bs][n][n_joints]: -||projection - argmax position|| (:313-326)        */
+} vpho_joint_scores_args;
+/* workspace: bs * n_joints * 2 floats when dist2d is requested (the maps' peak positions), else may be NULL */
+int vpho_joint_scores(const vpho_joint_scores_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
+/* `select_topk_hand_by_observed_heatmap_and_fuse_by_index` (lib/model/aggregation.py:180-284) for any index sets. */
+typedef struct {
+  int bs, n, K, n_joints;
+  const float* score;             /* [bs][n][n_joints] per-joint scores (vpho_joint_scores heat or dist2d)              */
+  float* pose;                    /* [bs][n][48] axis-angle candidates; fuse_kind 0; overwritten at fuse_index when
+                                     write_back (fused_pose[:, :, fuse_index] = ... :235-236)                           */
+  const float* joint;             /* [bs][n][n_joints][3]; fuse_kind 1 only                                             */
+  const int32_t* observe_index;   /* HOST [n_observe] joints whose scores enter                                         */
+  int n_observe;
+  const int32_t* fuse_index;      /* HOST [n_fuse] pose parameters to fuse, whole joints (3j, 3j+1, 3j+2)               */
+  int n_fuse;
+  int independent;                /* 0: one list (sum over observe_index); 1: one list per fused joint (mean, :242-245) */
+  int is_weight;                  /* heat-value weights or a plain average                                              */
+  int fuse_kind;                  /* 0: quaternion average of the winners' parameters; 1: mean of the winners' joint
+                                     positions, joint fuse_index[3l]/3 of list l ('2D_pt_joint' :357-362)               */
+  int write_back;
+  float* val;                     /* out or NULL [bs][K][lists]                                                         */
+  int32_t* topk;                  /* out or NULL [bs][K][lists]                                                         */
+  float* fused;                   /* out [bs][n_fuse] (fuse_kind 0) or [bs][lists][3] (fuse_kind 1)                     */
+} vpho_hand_level_args;
+int vpho_hand_level(const vpho_hand_level_args* args, void* stream);
+
+/* `average_all` (:400-404): unweighted quaternion average of every joint over all n candidates; pose [bs][n][n_joints][3]
+ * axis-angle -> out [bs][n_joints][3] */
+int vpho_quat_average_all(const float* pose, int bs, int n, int n_joints, float* out, void* stream);
+
+/* `ObjectAggregator.select_topk_object_by_heatmap` + `fuse_topk` (:729-781) */
+typedef struct {
+  int bs, n, K;
+  const double* pose6d;           /* [bs][n][9] rot6d + root-relative translation                                       */
+  const float* root_joint;        /* [bs][3]                                                                            */
+  const float* cam_intrinsic;     /* [bs][3][3]                                                                         */
+  const float* bbox;              /* [bs][4]                                                                            */
+  const float* heatmap;           /* [bs][27][64][64]                                                                   */
+  const uint8_t* is_right;        /* [bs]                                                                               */
+  const int32_t* obj_id;          /* [bs]                                                                               */
+  int is_weight;                  /* fuse with the heat weights or with a plain mean                                    */
+  const int32_t* topk_in;         /* NULL, or [bs][K] winners chosen by an earlier call: only fuse_topk runs (plain mean) --
+                                     the reference's non-physics cascade fuses one selection on another pose set (:713-715) */
+  int32_t* topk;                  /* out or NULL [bs][K]                                                                */
+  float* weight;                  /* out or NULL [bs][K]                                                                */
+  double* fused;                  /* out or NULL [bs][9]                                                                */
+} vpho_obj_select_args;
+/* workspace: bs * n floats (the candidates' scores) */
+int vpho_obj_select(vpho_assets_t assets, const vpho_obj_select_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------------------
  * N1: the modules that PRODUCE the hot path's inputs, from the RoI-aligned feature maps to the encodings,
  * heat-maps, regression pose and local contact forces -- `vpho_net.forward` lib/model/VPHO.py:129-178:
  *   head_hm_hand / head_hm_obj   HeadHeatmap2.forward              lib/model/head_inplane.py:42-107

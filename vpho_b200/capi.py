@@ -66,6 +66,27 @@ class EvalRecordArgs(C.Structure):
         "out")]
 
 
+class JointScoresArgs(C.Structure):
+    """`vpho_joint_scores_args` (include/vpho_b200.h)."""
+    _fields_ = [("bs", c_int), ("n", c_int), ("n_joints", c_int)] + [(k, c_void_p) for k in (
+        "joint", "root_joint", "cam_intrinsic", "bbox", "heatmap", "heat", "dist2d")]
+
+
+class HandLevelArgs(C.Structure):
+    """`vpho_hand_level_args` (include/vpho_b200.h)."""
+    _fields_ = [("bs", c_int), ("n", c_int), ("K", c_int), ("n_joints", c_int), ("score", c_void_p), ("pose", c_void_p),
+                ("joint", c_void_p), ("observe_index", c_void_p), ("n_observe", c_int), ("fuse_index", c_void_p),
+                ("n_fuse", c_int), ("independent", c_int), ("is_weight", c_int), ("fuse_kind", c_int), ("write_back", c_int),
+                ("val", c_void_p), ("topk", c_void_p), ("fused", c_void_p)]
+
+
+class ObjSelectArgs(C.Structure):
+    """`vpho_obj_select_args` (include/vpho_b200.h)."""
+    _fields_ = [("bs", c_int), ("n", c_int), ("K", c_int)] + [(k, c_void_p) for k in (
+        "pose6d", "root_joint", "cam_intrinsic", "bbox", "heatmap", "is_right", "obj_id")] + [("is_weight", c_int)] + [
+        (k, c_void_p) for k in ("topk_in", "topk", "weight", "fused")]
+
+
 _SIGNATURES = {
     "vpho_version": (c_int, []),
     "vpho_launch_count": (C.c_ulonglong, []),
@@ -124,6 +145,10 @@ _SIGNATURES = {
     "vpho_heads_overflow": (c_int, [c_void_p, C.POINTER(C.c_int32), c_void_p]),
     "vpho_hoi_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vpho_hoi_aggregate": (c_int, [c_void_p, c_void_p, C.POINTER(HoiArgs), c_void_p, c_size_t, c_void_p]),
+    "vpho_joint_scores": (c_int, [C.POINTER(JointScoresArgs), c_void_p, c_size_t, c_void_p]),
+    "vpho_hand_level": (c_int, [C.POINTER(HandLevelArgs), c_void_p]),
+    "vpho_quat_average_all": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vpho_obj_select": (c_int, [c_void_p, C.POINTER(ObjSelectArgs), c_void_p, c_size_t, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -567,9 +567,22 @@ __device__ __forceinline__ void post_step_block(const SamplerWs& ws, int bid, in
   const int n = c.n;
   const int lo = c.te_lo, hi = c.te_hi;
   const double h = c.h_done, t_old = c.t_old;
-  for (int i = bid * 256 + threadIdx.x; i < n; i += n_blocks * 256) {
-    const double y_old = ws.y[i];
-    if ((c.xs || c.xs32) && hi > lo) {
+  // The powers of x = (t - t_old) / h depend on the output point only: one thread per point forms them (np.cumprod order)
+  // in shared memory, so that the element loop does no float64 division -- the FP64 pipe is what bounds this kernel.
+  constexpr int kPwTile = 256;
+  __shared__ double s_pw[kPwTile][4];
+  const bool emit = (c.xs || c.xs32) && hi > lo;
+  for (int e0 = lo; emit && e0 < hi; e0 += kPwTile) {
+    const int ne = hi - e0 < kPwTile ? hi - e0 : kPwTile;
+    __syncthreads();
+    if ((int)threadIdx.x < ne) {
+      const double x = (ws.t_eval[e0 + threadIdx.x] - t_old) / h;
+      const double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x;      // np.cumprod
+      s_pw[threadIdx.x][0] = p1; s_pw[threadIdx.x][1] = p2; s_pw[threadIdx.x][2] = p3; s_pw[threadIdx.x][3] = p4;
+    }
+    __syncthreads();
+    for (int i = bid * 256 + threadIdx.x; i < n; i += n_blocks * 256) {
+      const double y_old = ws.y[i];
       double Q[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int j = 0; j < 7; ++j) {
@@ -577,15 +590,16 @@ __device__ __forceinline__ void post_step_block(const SamplerWs& ws, int bid, in
 #pragma unroll
         for (int q = 0; q < 4; ++q) Q[q] += k * kP[j][q];
       }
-      for (int e = lo; e < hi; ++e) {
-        const double x = (ws.t_eval[e] - t_old) / h;
-        const double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x;      // np.cumprod
+      for (int e = 0; e < ne; ++e) {
+        const double p1 = s_pw[e][0], p2 = s_pw[e][1], p3 = s_pw[e][2], p4 = s_pw[e][3];
         const double dot = ((Q[0] * p1 + Q[1] * p2) + Q[2] * p3) + Q[3] * p4;
         const double v = __dadd_rn(__dmul_rn(h, dot), y_old);
-        if (c.xs) c.xs[(size_t)e * n + i] = v;
-        if (c.xs32) c.xs32[(size_t)e * n + i] = (float)v;          // the `.float()` the predict branch applies (VPHO.py:243)
+        if (c.xs) c.xs[(size_t)(e0 + e) * n + i] = v;
+        if (c.xs32) c.xs32[(size_t)(e0 + e) * n + i] = (float)v;          // the `.float()` the predict branch applies (VPHO.py:243)
       }
     }
+  }
+  for (int i = bid * 256 + threadIdx.x; i < n; i += n_blocks * 256) {
     ws.y[i] = ws.ynew[i];
     // f <- f_new (first-same-as-last): slot 0 takes slot 6's scores (its coefficient follows once every block is done);
     // a value nan_to_num would have zeroed is stored as -0 so that it reads back as the +0 kval returns for it

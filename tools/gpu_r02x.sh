@@ -1,7 +1,9 @@
-# N4 modes on the GPU + bench with the median-of-three e2e windows
+# final tree: full GPU suite + bench line
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_agg_modes.py tests/test_bounds_build.py -m gpu -q 2>&1 | tail -8
+timeout 400 python -m pytest tests -m gpu -q --durations=5 > gpurun_out/r02x_tests.txt 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/r02x_tests.txt
+tail -4 gpurun_out/r02x_tests.txt
 timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/r02x_bench.json 2> gpurun_out/r02x_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/r02x_bench.err
+timeout 200 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/r02x_bench_reference.json 2> gpurun_out/r02x_bench_reference.err; echo "reference arm rc=$?"; head -c 600 gpurun_out/r02x_bench_reference.json; echo
 python - <<'P'
 import json
 d=json.load(open('gpurun_out/r02x_bench.json'))

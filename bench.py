@@ -128,7 +128,7 @@ class ClockSampler(threading.Thread):
                         self.rows.append([x.strip() for x in out.splitlines()[0].split(",")] + [time.perf_counter()])
             except Exception:
                 pass
-            self.stop_flag.wait(0.02 if self.nvml is not None else 0.5)
+            self.stop_flag.wait(0.05 if self.nvml is not None else 0.5)      # (a driver query every 20 ms is a suspect for the rare 50-100 ms stalls of the enqueueing thread)
 
     def summary(self, windows):
         """Only samples taken inside one of the timed windows [(t0, t1), ...] count."""
@@ -436,10 +436,19 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         # enqueued, one awaited, one held by the caller) the caching allocator keeps growing its pool for the first batches,
         # and a cudaMalloc of a 100 MB block stalls the enqueueing thread for 5-25 ms
         timed(None, max(args.steps, 12), begin_fn=begin_resident, end_fn=hp.predict_end)
-        host_ms.clear()
-        ms_res, wall_res, launches = timed(None, args.steps, begin_fn=begin_resident, end_fn=hp.predict_end)
+        # Three windows of exactly K steps, the MEDIAN reported (all listed in `value_windows_ms`): the enqueueing thread
+        # occasionally stalls for 50-100 ms inside one driver call (seen once in the e2e loop and once here, on otherwise
+        # identical code), and one such stall inside a 60 ms window decides the number.
+        value_windows = []
+        for _ in range(3):
+            host_ms.clear()
+            value_windows.append(timed(None, args.steps, begin_fn=begin_resident, end_fn=hp.predict_end) + (list(per_step), list(host_ms)))
+        ms_res, wall_res, launches, per_step_sel, host_sel = sorted(value_windows, key=lambda w: w[0])[1]
+        per_step[:] = per_step_sel
+        host_ms[:] = host_sel
     else:
-        ms_res, wall_res, launches = timed(step_resident, args.steps)
+        value_windows = [timed(step_resident, args.steps)]
+        ms_res, wall_res, launches = value_windows[0]
     per_step_value = list(per_step)
     host_value = list(host_ms)
     ms_latency = timed(step_resident, args.steps)[0] if args.pipeline else ms_res
@@ -600,6 +609,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         "sampler": {"hand_net_calls": net_calls, "obj_net_calls": info["obj"]["net_calls"],
                     "hand_attempts": info["hand"]["attempts"], "rejected": info["hand"]["rejected"] + info["obj"]["rejected"]},
         "wall_ms_per_step": round(wall_res / args.steps, 4),
+        "value_windows_ms": [round(w[0], 3) for w in value_windows], "value_window_rule": "median of three windows of exactly K steps",
         "per_step_ms": per_step_value, "host_enqueue_wait_ms": host_value,
         "pipelining": {"enabled": bool(args.pipeline), "latency_ms_per_batch": round(ms_latency / args.steps, 4),
                        "note": "value / ms_per_step: K batches software-pipelined (predict_begin / predict_end): batch i+1 is "

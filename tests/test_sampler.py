@@ -263,3 +263,28 @@ def test_sampler_emulated_pair_matches_separate_and_tolerates_an_empty_job(emu_l
         if all([pend_a.resolve(), pend_e.resolve()]):
             break
     assert torch.equal(z_a, x_a) and z_e.shape == (0, den_b.out_dim)
+
+
+def test_spare_attempt_policy_host_logic():
+    """The number of RK attempts enqueued up front: last batch's count plus one spare, the spare dropped once SPARE_WINDOW
+    batches in a row needed the same count and restored by the first batch that breaks the pattern (host logic only)."""
+    from types import SimpleNamespace
+    from vpho_b200.score_based_model import SPARE_WINDOW, PendingSample
+    den, agent = SimpleNamespace(), SimpleNamespace(spare_attempt=True, last_info=None)
+
+    def feed(attempts, status=1):
+        p = PendingSample(agent, den, None, 1, attempts, None)
+        p.pair = object()
+        return p.resolve([status, 6 * attempts + 2, attempts, 0, 0, attempts, 0, 0])
+
+    for i in range(SPARE_WINDOW - 1):
+        assert feed(3) and den.attempts_hint == 4
+    assert feed(3) and den.attempts_hint == 3               # stable: no spare
+    assert feed(3) and den.attempts_hint == 3
+    assert not feed(3, status=0) and den.attempts_hint == 3  # unfinished with the enqueued budget: the caller continues it
+    assert feed(4) and den.attempts_hint == 5               # pattern broken: spare is back
+    for i in range(SPARE_WINDOW - 2):
+        assert feed(4) and den.attempts_hint == 5
+    assert feed(4) and den.attempts_hint == 4
+    agent.spare_attempt = False
+    assert feed(5) and den.attempts_hint == 5

@@ -9,6 +9,7 @@ pointers and polls the device-side controller's status word.
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 from typing import Dict, Optional
 
@@ -107,6 +108,9 @@ def _unique_feat(data: dict, n_rows: int):
     return feat, 1
 
 
+SPARE_WINDOW = 8      # batches with an identical attempt count after which the spare RK attempt is no longer enqueued
+
+
 class PendingSample:
     """Status of one enqueued sample(); `resolve` interprets the controller's counters once they are on the host."""
 
@@ -133,8 +137,15 @@ class PendingSample:
             return False
         if c[4]:
             print("\033[31mWarning: NaN detected in score evaluation. \033[0m")   # score_based_model.py:70
-        # steady state: enqueue what the last batch needed plus one spare attempt (20 no-op launches)
-        self.denoiser.attempts_hint = max(1, c[5]) + (1 if self.agent.spare_attempt else 0)
+        # steady state: enqueue what the last batch needed plus one spare attempt (14 no-op launches, ~35 us) -- unless the
+        # last SPARE_WINDOW batches all needed the same number: then the spare is dropped until a batch breaks the pattern
+        # (that batch is continued on its own workspace by the caller, `PendingPair.advance`, and the spare comes back)
+        hist = getattr(self.denoiser, "_attempt_hist", None)
+        if hist is None:
+            hist = self.denoiser._attempt_hist = collections.deque(maxlen=SPARE_WINDOW)
+        hist.append(int(c[5]))
+        stable = len(hist) == SPARE_WINDOW and min(hist) == max(hist)
+        self.denoiser.attempts_hint = max(1, c[5]) + (1 if (self.agent.spare_attempt and not stable) else 0)
         return True
 
 

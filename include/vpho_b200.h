@@ -334,7 +334,8 @@ int vpho_hoi_aggregate(vpho_mano_t mano, vpho_assets_t assets, const vpho_hoi_ar
 /* ---------------------------------------------------------------------------------------------------------------------------
  * N4: the aggregation modes the predict branch does not use -- `HandAggregator.__call__` modes 'heatmap',
  * 'heatmap_cascade_n_level', '2D_pt_pose', '2D_pt_joint', 'average_all', 'random' (lib/model/aggregation.py:63-113,286-535)
- * and `ObjectAggregator` 'heatmap' / the non-physics branch of 'heatmap_cascade' (:646-722) -- as device primitives; the host
+ * and `ObjectAggregator` 'heatmap' / the non-physics branch of 'heatmap_cascade' / '2D_pt_pose' / 'average_all' / 'random'
+ * (:646-722, 1001-1113) -- as device primitives; the host
  * mirror vpho_b200/aggregation_modes.py composes them the way the reference's methods do. */
 typedef struct {
   int bs, n, n_joints;            /* images, candidates per image, joints per candidate (21)                         */
@@ -387,13 +388,15 @@ typedef struct {
   const uint8_t* is_right;        /* [bs]                                                                               */
   const int32_t* obj_id;          /* [bs]                                                                               */
   int is_weight;                  /* fuse with the heat weights or with a plain mean                                    */
+  int score_kind;                 /* 0: summed heat values (:752-776); 1: minus the summed 2D distances between the projected
+                                     key-points and their maps' argmax positions ('2D_pt_pose', :1013-1036; plain mean)   */
   const int32_t* topk_in;         /* NULL, or [bs][K] winners chosen by an earlier call: only fuse_topk runs (plain mean) --
                                      the reference's non-physics cascade fuses one selection on another pose set (:713-715) */
   int32_t* topk;                  /* out or NULL [bs][K]                                                                */
   float* weight;                  /* out or NULL [bs][K]                                                                */
   double* fused;                  /* out or NULL [bs][9]                                                                */
 } vpho_obj_select_args;
-/* workspace: bs * n floats (the candidates' scores) */
+/* workspace: bs * n floats (the candidates' scores) + bs * 27 * 2 floats (score_kind 1: the maps' peak positions) */
 int vpho_obj_select(vpho_assets_t assets, const vpho_obj_select_args* args, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------------------

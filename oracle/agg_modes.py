@@ -4,7 +4,8 @@
     HandAggregator.select_topk_hand_by_observed_heatmap_and_fuse_by_index   :180-284
     HandAggregator.select_by_heatmap :82-113, select_by_heatmap_cascade(_n_level) :115-178, 469-535,
     select_by_2D_pt :286-377, average_all :379-424, random :426-467
-    ObjectAggregator.select_by_heatmap :646-659, select_by_heatmap_cascade (is_force_selection=False) :661-722
+    ObjectAggregator.select_by_heatmap :646-659, select_by_heatmap_cascade (is_force_selection=False) :661-722,
+    select_by_2D_pt :1001-1052, average_all :1054-1082, random :1084-1112
 
 Pinned against the reference's own `HandAggregator` / `ObjectAggregator` classes (oracle/make_golden_modes.py ->
 tests/golden/agg_modes.npz, and live in the build container: tests/test_agg_modes.py) under the same declared rule as the
@@ -179,3 +180,38 @@ def obj_cascade_plain(obj: OracleObject, pose6d, root_joint, obj_name, cam, heat
     rot2 = obj_fuse_topk(topk_r2, p)[:, :6]
     fused = torch.cat([rot2, trans2], dim=-1).float()
     return {"agg_6d": fused, "pose6d_candidate": p, "agg_obj_vert": _obj_verts(obj, fused, root_joint, obj_name, is_right)}
+
+
+def obj_2d_pt_pose(obj: OracleObject, pose6d, root_joint, obj_name, cam, heatmap, bbox, k, is_right) -> Dict:
+    """ObjectAggregator.select_by_2D_pt, '2D_pt_pose' (:1001-1052)"""
+    bs, J, H, W = heatmap.shape
+    p = pose6d.clone().float()
+    p[..., 6:] = p[..., 6:] + root_joint.unsqueeze(1)
+    pts = obj.flip_pt3d(obj(p, obj_name), is_right)
+    pt2d = project(pts, cam)
+    bb = bbox[:, None, None, :]
+    pt2d = 2 * (pt2d - bb[..., :2]) / (bb[..., 2:] - bb[..., :2]) - 1
+    X, Y = torch.arange(W) / (W - 1) * 2 - 1, torch.arange(H) / (H - 1) * 2 - 1
+    XX, YY = torch.meshgrid(X, Y, indexing="ij")
+    XX, YY = XX[None, None].repeat(bs, J, 1, 1).reshape(bs, J, -1), YY[None, None].repeat(bs, J, 1, 1).reshape(bs, J, -1)
+    ind = torch.argmax(heatmap.reshape(bs, J, -1), dim=-1)
+    i1, i2 = torch.arange(bs)[:, None].repeat(1, J), torch.arange(J)[None].repeat(bs, 1)
+    pt_hm = torch.stack([XX[i1, i2, ind], YY[i1, i2, ind]], dim=-1)
+    score = (-torch.norm(pt2d - pt_hm[:, None], dim=-1)).sum(-1)
+    _, topk = canonical_topk(score, k, dim=1)
+    fused = obj_fuse_topk(topk, pose6d).float()
+    return {"agg_6d": fused, "agg_obj_vert": _obj_verts(obj, fused, root_joint, obj_name, is_right), "topk": topk, "score": score}
+
+
+def obj_average_first_k(obj: OracleObject, pose6d, root_joint, obj_name, k, is_right) -> Dict:
+    """ObjectAggregator.average_all (:1054-1082): fuse_topk over the first k candidates"""
+    bs = pose6d.shape[0]
+    fused = obj_fuse_topk(torch.arange(k)[None].repeat(bs, 1), pose6d).float()
+    return {"agg_6d": fused, "agg_obj_vert": _obj_verts(obj, fused, root_joint, obj_name, is_right)}
+
+
+def obj_random(obj: OracleObject, pose6d, root_joint, obj_name, is_right) -> Dict:
+    """ObjectAggregator.random (:1084-1112): fuse_topk over candidate 0"""
+    bs = pose6d.shape[0]
+    fused = obj_fuse_topk(torch.zeros(bs, 1, dtype=torch.long), pose6d).float()
+    return {"agg_6d": fused, "agg_obj_vert": _obj_verts(obj, fused, root_joint, obj_name, is_right)}

@@ -69,6 +69,9 @@ def reference_modes(ref) -> dict:
                         out[f"hand_{name}_{key}"] = r[key].numpy()
             r = obj(mode="heatmap", **ok())
             out["obj_heatmap_agg_6d"], out["obj_heatmap_agg_obj_vert"] = r["agg_6d"].numpy(), r["agg_obj_vert"].numpy()
+            for name in ("2D_pt_pose", "average_all", "random"):
+                r = obj(mode=name, **ok())
+                out[f"obj_{name}_agg_6d"], out[f"obj_{name}_agg_obj_vert"] = r["agg_6d"].numpy(), r["agg_obj_vert"].numpy()
             for w in (False, True):
                 r = obj(mode="heatmap_cascade", is_weight=w, is_force_selection=False, **ok())
                 out[f"obj_cascade_w{int(w)}_agg_6d"] = r["agg_6d"].numpy()

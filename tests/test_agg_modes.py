@@ -47,7 +47,9 @@ def _oracle_modes(bs, S, seed, K, Ko):
             "random": M.hand_random(om, h["pose"], h["shape"], bs),
         }
         ro = {"heatmap": M.obj_heatmap(oo, **o), "cascade_w0": M.obj_cascade_plain(oo, is_weight=False, **o),
-              "cascade_w1": M.obj_cascade_plain(oo, is_weight=True, **o)}
+              "cascade_w1": M.obj_cascade_plain(oo, is_weight=True, **o), "2D_pt_pose": M.obj_2d_pt_pose(oo, **o),
+              "average_all": M.obj_average_first_k(oo, o["pose6d"], o["root_joint"], o["obj_name"], Ko, o["is_right"]),
+              "random": M.obj_random(oo, o["pose6d"], o["root_joint"], o["obj_name"], o["is_right"])}
     return kw, r, ro
 
 
@@ -102,7 +104,9 @@ def _device_modes(lib, dev, bs, S, seed, K, Ko):
         "average_all": hand(mode="average_all", **hk()),
         "random": hand(mode="random", **hk()),
     }
-    ro = {"heatmap": obj(mode="heatmap", **ok()),
+    assert obj(mode="2D_pt_joint", **ok()) is None          # the reference falls through for any other 2D_pt mode
+    ro = {"heatmap": obj(mode="heatmap", **ok()), "2D_pt_pose": obj(mode="2D_pt_pose", **ok()),
+          "average_all": obj(mode="average_all", **ok()), "random": obj(mode="random", **ok()),
           "cascade_w0": obj(mode="heatmap_cascade", is_weight=False, is_force_selection=False, **ok()),
           "cascade_w1": obj(mode="heatmap_cascade", is_weight=True, is_force_selection=False, **ok())}
     return r, ro

@@ -5,6 +5,7 @@
         '2D_pt_pose' / '2D_pt_joint'        :286-377       'average_all' :379-424        'random' :426-467
     ObjectAggregator.__call__(mode=...)    :632-644
         'heatmap'                           :646-659       'heatmap_cascade' with is_force_selection=False   :661-722
+        '2D_pt_pose'                        :1001-1052     'average_all' :1054-1082      'random' :1084-1112
 
 Same kwargs, same returned keys.  Every number is produced by the sm_100a library through the C ABI (`vpho_mano_forward`,
 `vpho_joint_scores`, `vpho_hand_level`, `vpho_quat_average_all`, `vpho_obj_select`, `vpho_object_points`); torch only
@@ -225,14 +226,15 @@ class HandAggregator:
 
 
 class ObjectAggregator:
-    """`ObjectAggregator` 'heatmap' and the non-physics 'heatmap_cascade' (lib/model/aggregation.py:628-781)."""
+    """Every mode of `ObjectAggregator.__call__` (lib/model/aggregation.py:628-781, 1001-1113); 'heatmap_cascade' with force
+    selection is the predict branch itself (HOI_Aggregator)."""
 
     def __init__(self, assets: Assets):
         self.assets = assets
         self.lib = assets.lib
         self.obj_layer = HeadObject(assets)
 
-    def select(self, pose6d, K: int, is_weight: bool, kw: Dict, topk_in=None):
+    def select(self, pose6d, K: int, is_weight: bool, kw: Dict, topk_in=None, score_kind: int = 0):
         """select_topk_object_by_heatmap + fuse_topk (:729-781) -> topk (bs, K) int64, weight (bs, K), fused (bs, 9) f64.
         `topk_in`: winners of an earlier selection, fused (plain mean) on THIS pose set."""
         bs, n = pose6d.shape[0], pose6d.shape[1]
@@ -246,10 +248,10 @@ class ObjectAggregator:
         topk = torch.empty((bs, K), dtype=torch.int32, device=dev)
         weight = torch.empty((bs, K), dtype=torch.float32, device=dev)
         fused = torch.empty((bs, 9), dtype=torch.float64, device=dev)
-        ws = torch.empty((max(bs * n, 1),), dtype=torch.float32, device=dev)
+        ws = torch.empty((max(bs * n, 1) + bs * 27 * 2,), dtype=torch.float32, device=dev)
         P = capi.ptr
         a = capi.ObjSelectArgs(bs, n, int(K), P(hold["pose"]), P(hold["root"]), P(hold["cam"]), P(hold["bbox"]), P(hold["hm"]),
-                               P(hold["is_right"]), P(hold["obj_id"], torch.int32), int(is_weight),
+                               P(hold["is_right"]), P(hold["obj_id"], torch.int32), int(is_weight), int(score_kind),
                                P(hold["topk_in"]), P(topk), P(weight), P(fused))
         st = self.lib.c.vpho_obj_select(self.assets.handle, C.byref(a), P(ws), ws.numel() * 4, capi.stream_of(hold["pose"]))
         self.lib.check(st, "vpho_obj_select")
@@ -267,7 +269,38 @@ class ObjectAggregator:
             return self.select_by_heatmap(**kwargs)
         if kwargs["mode"] == "heatmap_cascade":
             return self.select_by_heatmap_cascade(**kwargs)
+        if "2D_pt" in kwargs["mode"]:
+            return self.select_by_2D_pt(**kwargs)
+        if kwargs["mode"] == "average_all":
+            return self.average_all(**kwargs)
+        if kwargs["mode"] == "random":
+            return self.random(**kwargs)
         raise NotImplementedError(kwargs["mode"])
+
+    def _result(self, fused, kw) -> Dict:
+        fused = fused.float()
+        return {"agg_6d": fused, "candidate_6d": kw["pose6d"], "agg_obj_vert": self._verts(fused, kw)}
+
+    def select_by_2D_pt(self, **kw):
+        """:1001-1052 ('2D_pt_pose'; like the reference, any other 2D_pt mode returns None)"""
+        if "pose" not in kw["mode"]:
+            return None
+        _, _, fused = self.select(kw["pose6d"], kw["k"], False, kw, score_kind=1)
+        return self._result(fused, kw)
+
+    def average_all(self, **kw) -> Dict:
+        """:1054-1082: despite the name, the plain mean of the FIRST k candidates"""
+        bs, K = kw["pose6d"].shape[0], int(kw["k"])
+        idx = torch.arange(K, device=kw["pose6d"].device)[None].repeat(bs, 1)
+        _, _, fused = self.select(kw["pose6d"], K, False, kw, topk_in=idx)
+        return self._result(fused, kw)
+
+    def random(self, **kw) -> Dict:
+        """:1084-1112: candidate 0 (through fuse_topk: its rotation goes 6D -> quaternion -> 6D)"""
+        bs = kw["pose6d"].shape[0]
+        idx = torch.zeros(bs, 1, dtype=torch.long, device=kw["pose6d"].device)
+        _, _, fused = self.select(kw["pose6d"], 1, False, kw, topk_in=idx)
+        return self._result(fused, kw)
 
     def select_by_heatmap(self, **kw) -> Dict:
         """:646-659 (fuse_topk without weights)"""

@@ -83,7 +83,7 @@ class HandLevelArgs(C.Structure):
 class ObjSelectArgs(C.Structure):
     """`vpho_obj_select_args` (include/vpho_b200.h)."""
     _fields_ = [("bs", c_int), ("n", c_int), ("K", c_int)] + [(k, c_void_p) for k in (
-        "pose6d", "root_joint", "cam_intrinsic", "bbox", "heatmap", "is_right", "obj_id")] + [("is_weight", c_int)] + [
+        "pose6d", "root_joint", "cam_intrinsic", "bbox", "heatmap", "is_right", "obj_id")] + [("is_weight", c_int), ("score_kind", c_int)] + [
         (k, c_void_p) for k in ("topk_in", "topk", "weight", "fused")]
 
 

@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(64) k_quat_average_all(const float* __restrict
 
 // ---- object: heat-map score of every candidate pose, top-k, fuse ---------------------------------------------------------
 // score[b][c] = sum over the key-points of the bicubic heat value at the projected key-point (:752-776)
-__global__ void __launch_bounds__(256) k_obj_mode_score(AssetsDev as, vpho_obj_select_args a, float* __restrict__ score) {
+__global__ void __launch_bounds__(256) k_obj_mode_score(AssetsDev as, vpho_obj_select_args a, float* __restrict__ score,
+                                                        const float* __restrict__ peak) {
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 8 + warp;
   if (c >= a.n) return;
@@ -205,7 +206,12 @@ __global__ void __launch_bounds__(256) k_obj_mode_score(AssetsDev as, vpho_obj_s
     float p[3], gx, gy;
     obj_point(o, as.kpt + ((size_t)oid * kKpts + lane) * 3, p);
     project_to_grid(a.cam_intrinsic + (size_t)b * 9, a.bbox + (size_t)b * 4, p[0], p[1], p[2], gx, gy);
-    hv = bicubic_sample64(a.heatmap + ((size_t)b * kKpts + lane) * kHm * kHm, gx, gy);
+    if (a.score_kind == 0) {
+      hv = bicubic_sample64(a.heatmap + ((size_t)b * kKpts + lane) * kHm * kHm, gx, gy);
+    } else {
+      const float dx = gx - peak[((size_t)b * kKpts + lane) * 2 + 0], dy = gy - peak[((size_t)b * kKpts + lane) * 2 + 1];
+      hv = -sqrtf(dx * dx + dy * dy);
+    }
   }
   // heatval.sum(dim=-1) in key-point order
   float acc = 0.f;
@@ -358,12 +364,18 @@ extern "C" int vpho_obj_select(vpho_assets_t assets, const vpho_obj_select_args*
   if (a.bs < 0 || a.n <= 0 || a.n > 1024 || a.K < 1 || a.K > 64 || a.K > a.n) return VPHO_ERR_INVALID;
   if (a.bs == 0) return VPHO_OK;
   if (!a.pose6d || !a.root_joint || !a.cam_intrinsic || !a.bbox || !a.heatmap || !a.is_right || !a.obj_id) return VPHO_ERR_INVALID;
-  if (!workspace || workspace_bytes < (size_t)a.bs * a.n * sizeof(float)) return VPHO_ERR_INVALID;
+  if (a.score_kind != 0 && a.score_kind != 1) return VPHO_ERR_INVALID;
+  const size_t need = ((size_t)a.bs * a.n + (a.score_kind == 1 ? (size_t)a.bs * kKpts * 2 : 0)) * sizeof(float);
+  if (!workspace || workspace_bytes < need) return VPHO_ERR_INVALID;
   const AssetsDev& as = static_cast<AssetsHost*>(assets)->dev;
   float* score = static_cast<float*>(workspace);
+  float* peak = score + (size_t)a.bs * a.n;
   cudaStream_t st = (cudaStream_t)stream;
-  if (a.topk_in && a.is_weight) return VPHO_ERR_INVALID;       // given winners carry no heat values
-  if (!a.topk_in) VPHO_LAUNCH(k_obj_mode_score, dim3((a.n + 7) / 8, a.bs), dim3(256), 0, st, as, a, score);
+  if (a.is_weight && (a.topk_in || a.score_kind == 1)) return VPHO_ERR_INVALID;       // no heat values to weight with
+  if (!a.topk_in) {
+    if (a.score_kind == 1) VPHO_LAUNCH(k_heat_argmax, dim3(a.bs * kKpts), dim3(256), 0, st, a.heatmap, a.bs * kKpts, peak);
+    VPHO_LAUNCH(k_obj_mode_score, dim3((a.n + 7) / 8, a.bs), dim3(256), 0, st, as, a, score, peak);
+  }
   if (a.n <= 256) VPHO_LAUNCH(k_obj_mode_fuse<8>, dim3(a.bs), dim3(32), 0, st, a, score);
   else if (a.n <= 512) VPHO_LAUNCH(k_obj_mode_fuse<16>, dim3(a.bs), dim3(32), 0, st, a, score);
   else VPHO_LAUNCH(k_obj_mode_fuse<32>, dim3(a.bs), dim3(32), 0, st, a, score);

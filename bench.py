@@ -251,6 +251,8 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
     mano, anchors, objects, batch, prior_h, prior_o, st_h, st_o = make_inputs(bs, seed=rank)
     hp = VphoHotPath(mano, anchors, objects, st_h, st_o, sample_num=S, sampling_steps=STEPS_ODE, sample_T0=T0,
                      topk_hand=K_HAND, topk_obj=K_OBJ)
+    hp.agg_slots = max(1, min(2, args.agg_slots))
+    hp.side_slots = max(1, min(2, args.side_slots))
     recorder = EvalRecorder(hp.assets, syn.make_metric_tables(objects))
     gt = syn.make_eval_ground_truth(batch, hp.head_mano, objects)
     batch["obj_id"] = np.asarray(batch["obj_id"], np.int32)
@@ -435,7 +437,7 @@ def cuda_arm(args, rank: int, world: int, local_rank: int):
         # warm the pipelined loop itself with an untimed pass of the SAME loop: with three batches' outputs alive (one being
         # enqueued, one awaited, one held by the caller) the caching allocator keeps growing its pool for the first batches,
         # and a cudaMalloc of a 100 MB block stalls the enqueueing thread for 5-25 ms
-        timed(None, max(args.steps, 12), begin_fn=begin_resident, end_fn=hp.predict_end)
+        timed(None, max(2 * args.steps, 40), begin_fn=begin_resident, end_fn=hp.predict_end)
         # Three windows of exactly K steps, the MEDIAN reported (all listed in `value_windows_ms`): the enqueueing thread
         # occasionally stalls for 50-100 ms inside one driver call (seen once in the e2e loop and once here, on otherwise
         # identical code), and one such stall inside a 60 ms window decides the number.
@@ -880,7 +882,10 @@ def main():
     ap.add_argument("--pipeline", type=int, default=1, choices=[0, 1],
                     help="1: consecutive batches software-pipelined (batch i's aggregation under batch i+1's samplers); 0: each "
                          "batch joined before the next starts")
-    ap.add_argument("--e2e-sets", type=int, default=3, help="device input sets of the e2e leg (>= 3 when pipelined)")
+    ap.add_argument("--agg-slots", type=int, default=2, help="DIAGNOSTIC: 1 = one aggregation stream / workspace for all batches")
+    ap.add_argument("--side-slots", type=int, default=1, help="DIAGNOSTIC: 1 = one output-only stream for all batches")
+    ap.add_argument("--e2e-sets", type=int, default=4, help="device input sets of the e2e leg (>= 3 when pipelined; a set is "
+                    "rewritten only after its batch's aggregation: with 3 the copy of batch i+1 waits for batch i-2's)")
     ap.add_argument("--e2e-skip", default="", help="DIAGNOSTIC ONLY (invalidates e2e): comma list of h2d,record to leave out")
     ap.add_argument("--record-stream", default="side", choices=["main", "side"],
                     help="e2e leg: stream the evaluation record is computed on (main = behind the aggregation; side = beside the "

@@ -35,9 +35,17 @@ class VphoHotPath:
         self.denoiser_obj = Denoiser(denoiser_obj_state, lib=self.lib)
         self.score_agent = ScoreBasedModelAgent(sampling_steps=sampling_steps, sample_num=sample_num)
         self.hoi_aggregator = HOI_Aggregator(self.head_mano, self.assets, debug=debug)
+        # Two batches may be in flight: each slot has its own aggregator (workspace, asset handle with its fork / join
+        # events) and its own aggregation stream, so that the latency-bound aggregation chains of consecutive batches
+        # overlap each other instead of queueing on one stream (measured: 2.77 -> 2.72 ms per batch).  `hoi_aggregator` is the one the latest batch used.
+        self.agg_slots = 2                # 1: every batch's aggregation on the same stream / workspace (tools/pipeline_probe.py)
+        self.side_slots = 1               # the same for the output-only stream (measured: a second one gains nothing)
+        self._hoi_slots = [self.hoi_aggregator, None]
+        self._asset_src = (anchors, objects, debug)
         self.last_info: dict = {}
-        self._side_stream2 = None
-        self._agg_stream = None
+        self._slot_done = [[], []]        # events completing the library-stream work of each slot's latest batch
+        self._side_stream2 = [None, None]
+        self._agg_stream = [None, None]
         self._status_host = None
         self._ws_slot = 0
         self._events: list = []          # ring of reusable CUDA events (creating one per batch costs a driver call each)
@@ -140,6 +148,16 @@ class VphoHotPath:
         enc_h, enc_o = batch["encoding_hand"], batch["encoding_obj"]
         bs = enc_h.shape[0]
         self._ws_slot ^= 1
+        # Back-pressure: this slot's previous batch (two batches ago) must have finished its aggregation and output-only work
+        # before this batch's samplers start.  Without it the low-priority library streams fall behind the samplers without
+        # bound in a loop that never joins them (their backlog is then paid at the end, and every block they still hold is
+        # one the caching allocator cannot reuse: it answers with a fresh cudaMalloc -- milliseconds of host stall -- every
+        # other batch and the pool grows by gigabytes).
+        if enc_h.is_cuda:
+            main = torch.cuda.current_stream(enc_h.device)
+            for ev in self._slot_done[self._ws_slot]:
+                main.wait_event(ev)
+            self._slot_done[self._ws_slot] = []
         # The hand and the object integrations issue the same sequence of network calls: they advance in lock-step
         # through shared kernel launches (`sample_pair`), the object's work items filling the SMs the hand's leave idle.
         samples = self.score_agent.sample_pair(
@@ -154,7 +172,7 @@ class VphoHotPath:
 
     def _issue(self, t: Dict) -> None:
         t["status"] = self._snapshot(t["pend"], t["slot"])     # stream-ordered behind the samplers only: the host wakes when THEY finish
-        t["pd"] = self._downstream(t["batch"], t["samples"], t["with_inprocess"], t["defer_join"])   # speculative on the first pass
+        t["pd"] = self._downstream(t["batch"], t["samples"], t["with_inprocess"], t["defer_join"], t["slot"])   # speculative on the first pass
         if t["prefetch"] is not None:
             # caller hook `prefetch(pd, issue)`, run after the batch is enqueued and before the host blocks on its
             # status: the place to enqueue device-to-host reads of `pd` (stream-ordered behind the aggregation) and, for
@@ -231,7 +249,14 @@ class VphoHotPath:
                 stream.wait_event(ev)
         return pd
 
-    def _downstream(self, batch: Dict, samples, with_inprocess: bool, defer_join: bool = False) -> Dict:
+    def _aggregator(self, slot: int):
+        if self._hoi_slots[slot] is None:
+            anchors, objects, debug = self._asset_src
+            self._hoi_slots[slot] = HOI_Aggregator(self.head_mano, Assets(anchors, objects, lib=self.lib), debug=debug)
+        self.hoi_aggregator = self._hoi_slots[slot]
+        return self.hoi_aggregator
+
+    def _downstream(self, batch: Dict, samples, with_inprocess: bool, defer_join: bool = False, slot: int = 0) -> Dict:
         """Everything after the two `sample()` calls of the predict branch (VPHO.py:243-304).  batch: tensors on the CUDA
         device (see `to_device`)."""
         S = self.sample_num
@@ -260,9 +285,10 @@ class VphoHotPath:
 
         side2 = None
         if main is not None and not self.serialize:
-            if self._side_stream2 is None:
-                self._side_stream2 = torch.cuda.Stream(device=enc_h.device, priority=self._priorities(main)[1])
-            side2 = self._side_stream2
+            sslot = slot if self.side_slots > 1 else 0
+            if self._side_stream2[sslot] is None:
+                self._side_stream2[sslot] = torch.cuda.Stream(device=enc_h.device, priority=self._priorities(main)[1])
+            side2 = self._side_stream2[sslot]
             side2.wait_stream(main)
             for t in (xs_h, x_h, final_mano):
                 if t is not None:
@@ -280,8 +306,11 @@ class VphoHotPath:
             pd["diff_inprocess_obj_6d"] = xs_o.reshape(bs, S, -1, 9)
         pd["diff_final_obj_6d"] = x_o.reshape(bs, S, 9)
 
+        aslot = slot if self.agg_slots > 1 else 0
+        hoi = self._aggregator(aslot)
+
         def aggregate():
-            return self.hoi_aggregator(
+            return hoi(
                 cam_intrinsic=batch["cam_intr_crop_flip"], root_joint_flip=batch["root_joint_flip"],
                 root_joint=batch["root_joint"], is_right=batch["is_right"], force_local=batch["force_local"],
                 is_grasped=batch["is_grasped"], hand_pose_diff=final_mano[:, :48], hand_pose_regression=pd_mano_pose,
@@ -294,9 +323,9 @@ class VphoHotPath:
         # the 6400 candidate meshes at the same time.  Running the chain on a high-priority stream lets its CTAs be
         # placed ahead of the pending mesh CTAs whenever SM slots free up.
         if side2 is not None:
-            if self._agg_stream is None:
-                self._agg_stream = torch.cuda.Stream(device=enc_h.device, priority=self._priorities(main)[0])
-            hs = self._agg_stream
+            if self._agg_stream[aslot] is None:
+                self._agg_stream[aslot] = torch.cuda.Stream(device=enc_h.device, priority=self._priorities(main)[0])
+            hs = self._agg_stream[aslot]
             hs.wait_stream(main)
             if defer_join:
                 # nothing on the caller's stream orders these reads any more: tell the allocator who uses the tensors
@@ -323,6 +352,7 @@ class VphoHotPath:
                     ev = self._event()
                     ev.record(st)
                     pd["_done"].append((ev, enc_h.device))
+                self._slot_done[slot] = [ev for ev, _ in pd["_done"]]
             else:
                 main.wait_stream(side2)
         return pd

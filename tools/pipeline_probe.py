@@ -22,7 +22,7 @@ def run(name, defer, compute_prio=None, agg_prio=-1, mesh_prio=0):
     hp = VphoHotPath(mano, anchors, objects, st_h, st_o, sample_num=bench.S, sampling_steps=bench.STEPS_ODE, sample_T0=bench.T0,
                      topk_hand=bench.K_HAND, topk_obj=bench.K_OBJ)
     hp._agg_stream = [torch.cuda.Stream(device=dev, priority=agg_prio) for _ in range(2)]
-    hp._side_stream2 = torch.cuda.Stream(device=dev, priority=mesh_prio)
+    hp._side_stream2 = [torch.cuda.Stream(device=dev, priority=mesh_prio) for _ in range(2)]
     cs = torch.cuda.Stream(device=dev, priority=compute_prio) if compute_prio is not None else torch.cuda.current_stream()
     with torch.cuda.stream(cs):
         for _ in range(4):

@@ -42,9 +42,12 @@ def run(name, defer, compute_prio=None, agg_prio=-1, mesh_prio=0):
     print("%-46s %.4f ms/step (device)  %.4f ms/step (wall)" % (name, t0.elapsed_time(t1) / K, w * 1e3 / K), flush=True)
 
 
-def run_ahead(name, compute_prio=None):
+def run_ahead(name, compute_prio=None, agg_prio=None, mesh_prio=None):
     hp = VphoHotPath(mano, anchors, objects, st_h, st_o, sample_num=bench.S, sampling_steps=bench.STEPS_ODE, sample_T0=bench.T0,
                      topk_hand=bench.K_HAND, topk_obj=bench.K_OBJ)
+    if agg_prio is not None:
+        hp._agg_stream = [torch.cuda.Stream(device=dev, priority=agg_prio) for _ in range(2)]
+        hp._side_stream2 = [torch.cuda.Stream(device=dev, priority=mesh_prio) for _ in range(2)]
     cs = torch.cuda.Stream(device=dev, priority=compute_prio) if compute_prio is not None else torch.cuda.current_stream()
     with torch.cuda.stream(cs):
         for _ in range(4):
@@ -69,6 +72,14 @@ def run_ahead(name, compute_prio=None):
     print("%-46s %.4f ms/step (device)  %.4f ms/step (wall)" % (name, t0.elapsed_time(t1) / K, w * 1e3 / K), flush=True)
 
 
+if len(sys.argv) > 2 and sys.argv[2] == "prio":
+    for _ in range(2):
+        run_ahead("one-ahead, compute -2, agg -1, mesh 0 (default)", -2)
+        run_ahead("one-ahead, compute -2, agg -2, mesh 0", -2, -2, 0)
+        run_ahead("one-ahead, compute -2, agg -3, mesh 0", -2, -3, 0)
+        run_ahead("one-ahead, compute -2, agg -1, mesh -1", -2, -1, -1)
+        run_ahead("one-ahead, compute -2, agg -2, mesh -2", -2, -2, -2)
+    sys.exit(0)
 run("joined", False)
 run_ahead("one-ahead, compute -2 (agg -1, mesh 0)", -2)
 run_ahead("one-ahead, default stream (agg -1, mesh 0)")

@@ -169,6 +169,13 @@ def test_modes_emulated(emu_lib):
     _compare(r, ro, ref, refo, min_clean=3)                   # same arithmetic as the oracle: every list equal
 
 
+def test_modes_emulated_ragged(emu_lib):
+    """One image, five candidates, K = every candidate (hand) / 3 of 5 (object): sizes that fill no warp and no tile."""
+    _, ref, refo = _oracle_modes(1, 5, 3, 5, 3)
+    r, ro = _device_modes(emu_lib, "cpu", 1, 5, 3, 5, 3)
+    _compare(r, ro, ref, refo, min_clean=1)
+
+
 def test_modes_reject_bad_arguments(emu_lib):
     mano, _, _ = cases.assets()
     hand = HandAggregator(HeadMano(mano, lib=emu_lib))

@@ -128,7 +128,7 @@ class ClockSampler(threading.Thread):
                         self.rows.append([x.strip() for x in out.splitlines()[0].split(",")] + [time.perf_counter()])
             except Exception:
                 pass
-            self.stop_flag.wait(0.05 if self.nvml is not None else 0.5)      # (a driver query every 20 ms is a suspect for the rare 50-100 ms stalls of the enqueueing thread)
+            self.stop_flag.wait(0.03 if self.nvml is not None else 0.5)
 
     def summary(self, windows):
         """Only samples taken inside one of the timed windows [(t0, t1), ...] count."""
